@@ -1,0 +1,1225 @@
+"""Model handlers: local learning, merging and evaluation of gossip models.
+
+Behavioural reference: ``gossipy/model/handler.py`` (cited per class).  Architectural
+difference: a handler does not own a graph of Python objects that is deep-copied on every send;
+it owns ONE flat fp32 *row* in an HBM arena (``engine.arena``).  Consequently
+
+* ``_merge``      = one fused weighted-merge kernel over rows (the peer row is read in place,
+                    over NVLink when it lives on another GPU) -- ``ops.merge_*``;
+* ``_update``     = one fused local-epoch kernel for the kernel families (``mlp1``, ``logreg``,
+                    ``linear``) or autograd + one flat optimizer kernel for arbitrary modules;
+* ``caching``     = one D2D snapshot copy into an arena row (skipped when an identical
+                    snapshot is already in flight);
+* ``evaluate``    = a device-side confusion matrix, only ``C*C`` integers reach the host.
+
+All device work of a handler is enqueued on the CUDA stream of the gossip node that owns it;
+snapshots carry events, so exchanges between disjoint node pairs overlap on the GPU.
+"""
+from __future__ import annotations
+
+import copy
+from abc import ABC, abstractmethod
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .. import CACHE, LOG, CacheKey, GlobalSettings, Sizeable
+from .. import ops
+from ..core import CreateModelMode
+from ..engine import arena as _arena
+from ..engine import rng as _rng
+from ..engine.flat import FlatLayout
+from ..ops import metrics as _metrics
+from . import TorchModel
+from .nn import AdaLine
+from .sampling import TorchModelPartition, TorchModelSampling, sample_dict_to_flat
+
+__all__ = ["ModelHandler", "TorchModelHandler", "AdaLineHandler", "PegasosHandler",
+           "SamplingTMH", "PartitionedTMH", "MFModelHandler", "KMeansHandler", "WeightedTMH",
+           "LimitedMergeTMH", "LimitedMergeMixin", "PendingEval"]
+
+
+# --------------------------------------------------------------------------------------
+# deferred evaluation results
+# --------------------------------------------------------------------------------------
+class PendingEval:
+    """Evaluation whose sufficient statistics are still on the device.
+
+    ``result()`` performs the (tiny) device->host read and returns the metric dict.  The
+    simulators enqueue the evaluation of every node first and resolve afterwards, so a round has
+    one host synchronisation instead of one per node.
+    """
+
+    def __init__(self, finish: Callable[[], Dict[str, float]]) -> None:
+        self._finish = finish
+        self._value: Optional[Dict[str, float]] = None
+
+    def result(self) -> Dict[str, float]:
+        if self._value is None:
+            self._value = self._finish()
+            self._finish = None
+        return self._value
+
+
+def _resolved(d: Dict[str, float]) -> PendingEval:
+    p = PendingEval(lambda: d)
+    return p
+
+
+# --------------------------------------------------------------------------------------
+# base class
+# --------------------------------------------------------------------------------------
+class ModelHandler(Sizeable, ABC):
+    """Interface of the learn / merge / evaluate object of a node (ref ``handler.py:58-182``)."""
+
+    def __init__(self, create_model_mode: CreateModelMode = CreateModelMode.MERGE_UPDATE,
+                 *args, **kwargs) -> None:
+        self.model: Any = None
+        self.mode = create_model_mode
+        self.n_updates: Any = 0
+        self.owner: int = -1      # id of the node that owns this handler (stream selection)
+        self._version = 0         # bumped on every change of the model's values
+
+    # -- to implement --------------------------------------------------------------------
+    @abstractmethod
+    def init(self, *args, **kwargs) -> None: ...
+
+    @abstractmethod
+    def _update(self, data: Any, *args, **kwargs) -> None: ...
+
+    @abstractmethod
+    def _merge(self, other_model_handler: "ModelHandler", *args, **kwargs) -> None: ...
+
+    @abstractmethod
+    def evaluate(self, *args, **kwargs) -> Any: ...
+
+    # -- behaviour shared by all handlers ----------------------------------------------
+    def _adopt(self, other: "ModelHandler") -> None:
+        """Replace this model's values by ``other``'s (reference: ``deepcopy(recv.model)``)."""
+        self.model = copy.deepcopy(other.model)
+        self._version += 1
+
+    def _scratch_copy(self, other: "ModelHandler") -> "ModelHandler":
+        """A private, trainable copy of a received model (for ``UPDATE_MERGE``)."""
+        return other.copy()
+
+    def __call__(self, recv_model: Any, data: Any, *args, **kwargs) -> None:
+        """Combine a received model with the local one according to ``self.mode``
+        (ref ``handler.py:117-136``)."""
+        mode = self.mode
+        if mode == CreateModelMode.UPDATE:
+            # train the received model on local data and adopt it: adopting first and training
+            # the local row is the same computation without mutating the in-flight snapshot
+            self._adopt(recv_model)
+            self.n_updates = copy.copy(recv_model.n_updates)
+            self._update(data)
+        elif mode == CreateModelMode.MERGE_UPDATE:
+            self._merge(recv_model, *args, **kwargs)
+            self._update(data)
+        elif mode == CreateModelMode.UPDATE_MERGE:
+            self._update(data)
+            tmp = self._scratch_copy(recv_model)
+            tmp._update(data)
+            self._merge(tmp, *args, **kwargs)
+            _dispose(tmp)
+        elif mode == CreateModelMode.PASS:
+            self._adopt(recv_model)
+        else:
+            raise ValueError("Unknown create model mode %s" % str(mode))
+
+    def evaluate_async(self, *args, **kwargs) -> PendingEval:
+        return _resolved(self.evaluate(*args, **kwargs))
+
+    def copy(self) -> Any:
+        return copy.deepcopy(self)
+
+    def get_size(self) -> int:
+        return self.model.get_size() if self.model is not None else 0
+
+    def _age_key(self) -> Any:
+        return self.n_updates
+
+    def caching(self, owner: int) -> CacheKey:
+        """Put a snapshot of this model "on the wire" and return its key.
+
+        The key is ``(owner, age, version)``; when the same version is already in flight only a
+        reference is added (no copy) -- e.g. an all-to-all node pushing to 20 neighbours takes
+        one snapshot, not 20.
+        """
+        key = CacheKey(owner, self._age_key(), self._version)
+        if key in CACHE:
+            CACHE.push(key, None)
+        else:
+            CACHE.push(key, self._snapshot())
+        return key
+
+    def _snapshot(self) -> "ModelHandler":
+        return self.copy()
+
+    def release(self) -> None:
+        """Return device resources (called when a snapshot leaves the cache)."""
+
+    def __eq__(self, other: Any) -> bool:
+        return isinstance(other, self.__class__) and _state_eq(self.__dict__, other.__dict__)
+
+    def __ne__(self, other: Any) -> bool:
+        return not self.__eq__(other)
+
+    __hash__ = object.__hash__
+
+    def __repr__(self) -> str:
+        return str(self)
+
+    def __str__(self) -> str:
+        return "%s(model=%s_%s, mode=%s)" % (self.__class__.__name__, str(self.model),
+                                             self.n_updates, self.mode)
+
+
+def _dispose(h: Any) -> None:
+    rel = getattr(h, "release", None)
+    if callable(rel):
+        rel()
+
+
+def _state_eq(a: Dict[str, Any], b: Dict[str, Any]) -> bool:
+    skip = {"_row", "_module", "_proto", "_grad_row", "_opt_rows", "_torch_opt", "owner",
+            "_version", "_is_snapshot", "_bound_to", "_grad_bound", "_update_counter",
+            "_part_id_dev", "_seg_dev", "layout"}
+    for k in a.keys() | b.keys():
+        if k in skip:
+            continue
+        va, vb = a.get(k), b.get(k)
+        if isinstance(va, np.ndarray) or isinstance(vb, np.ndarray):
+            if not np.array_equal(va, vb):
+                return False
+        elif isinstance(va, torch.Tensor) or isinstance(vb, torch.Tensor):
+            if not (isinstance(va, torch.Tensor) and isinstance(vb, torch.Tensor)
+                    and torch.equal(va.cpu(), vb.cpu())):
+                return False
+        elif isinstance(va, torch.nn.Module) and isinstance(vb, torch.nn.Module):
+            if str(va) != str(vb):
+                return False
+        elif callable(va) and callable(vb):
+            continue
+        elif va != vb:
+            return False
+    return True
+
+
+# --------------------------------------------------------------------------------------
+# device-resident data: every distinct host tensor is uploaded once and shared by all handlers
+# --------------------------------------------------------------------------------------
+_DEVICE_CACHE: Dict[Tuple[int, str], Tuple[Any, Any]] = {}
+
+
+def _move(t: Any, dev: torch.device) -> Any:
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t))
+    if not isinstance(t, torch.Tensor):
+        return t
+    if t.dtype == torch.float64:
+        t = t.float()
+    if t.device == dev:
+        return t
+    key = (id(t), str(dev))
+    hit = _DEVICE_CACHE.get(key)
+    if hit is not None and hit[0] is t:
+        return hit[1]
+    moved = t.to(dev, non_blocking=True).contiguous()
+    _DEVICE_CACHE[key] = (t, moved)  # holding `t` keeps id() unique
+    return moved
+
+
+def to_device_cached(data: Any, dev: torch.device) -> Any:
+    if data is None:
+        return None
+    if isinstance(data, (tuple, list)):
+        return tuple(_move(t, dev) for t in data)
+    return _move(data, dev)
+
+
+def clear_device_cache() -> None:
+    _DEVICE_CACHE.clear()
+
+
+# --------------------------------------------------------------------------------------
+# row-backed handlers
+# --------------------------------------------------------------------------------------
+class RowHandler(ModelHandler):
+    """A handler whose model values live in one arena row (see module docstring)."""
+
+    def __init__(self, create_model_mode: CreateModelMode) -> None:
+        super().__init__(create_model_mode)
+        self._row: Optional[_arena.Row] = None
+        self._row_numel = 0
+        self._is_snapshot = False
+
+    # -- device / stream plumbing -------------------------------------------------------
+    @property
+    def device(self) -> torch.device:
+        return GlobalSettings().get_device()
+
+    def _stream(self):
+        return _arena.stream_for(self.device, self.owner)
+
+    def _ensure_row(self) -> _arena.Row:
+        dev = self.device
+        if self._row is None:
+            self._row = _arena.arena_for(dev, self._row_numel).alloc()
+            self._on_new_row(None)
+        elif self._row.tensor.device.type != dev.type:
+            old = self._row
+            self._row = _arena.arena_for(dev, self._row_numel).alloc()
+            self._row.tensor.copy_(old.tensor)
+            old.release()
+            self._on_new_row(old)
+        return self._row
+
+    def _on_new_row(self, old: Optional[_arena.Row]) -> None:
+        """Hook: (re)bind views after the row moved."""
+
+    @property
+    def row(self) -> torch.Tensor:
+        return self._ensure_row().tensor
+
+    def _to_device(self, data: Any) -> Any:
+        """Device-resident copy of a node's shard / the eval set, uploaded once."""
+        return to_device_cached(data, self.device)
+
+    # -- snapshot / copy ------------------------------------------------------------------
+    def _clone_shell(self) -> "RowHandler":
+        new = object.__new__(self.__class__)
+        new.__dict__.update(self.__dict__)
+        new._row = None
+        new.n_updates = copy.copy(self.n_updates)
+        return new
+
+    def _snapshot(self) -> "RowHandler":
+        """Light clone: new arena row filled by a D2D copy on the owner's stream."""
+        src = self._ensure_row()
+        new = self._clone_shell()
+        new._is_snapshot = True
+        new._after_clone(self, light=True)
+        dst = _arena.arena_for(self.device, self._row_numel).alloc()
+        s = self._stream()
+        with _arena.on_stream(s):
+            _arena.before_write(dst, s if s is not None else _arena.current(self.device))
+            ops.snapshot(dst.tensor, src.tensor)
+            _arena.after_write(dst, s if s is not None else _arena.current(self.device), shared=True)
+        new._row = dst
+        return new
+
+    def copy(self) -> "RowHandler":
+        new = self._clone_shell()
+        new._is_snapshot = False
+        new._after_clone(self, light=False)
+        if self._row is not None:
+            dst = new._ensure_row()
+            s = self._stream()
+            with _arena.on_stream(s):
+                ops.snapshot(dst.tensor, self._row.tensor)
+        return new
+
+    def __deepcopy__(self, memo) -> "RowHandler":
+        return self.copy()
+
+    def _after_clone(self, src: "RowHandler", light: bool) -> None:
+        """Hook: fix up per-instance members of a fresh clone."""
+
+    def release(self) -> None:
+        if self.__dict__.get("_cache_refs", 0) > 0:
+            return  # still referenced by other in-flight messages
+        if self._row is not None:
+            self._row.release()
+            self._row = None
+
+    # -- generic row operations ----------------------------------------------------------
+    def _src_row(self, other: "RowHandler", s) -> torch.Tensor:
+        orow = other._ensure_row()
+        _arena.before_read(orow, s if s is not None else _arena.current(self.device))
+        return orow.tensor
+
+    def _done_with(self, other: "RowHandler", s) -> None:
+        _arena.after_read(other._row, s if s is not None else _arena.current(self.device))
+
+    def _adopt(self, other: "RowHandler") -> None:
+        s = self._stream()
+        with _arena.on_stream(s):
+            ops.merge_pair(self.row, self._src_row(other, s), 0.0, 1.0)
+            self._done_with(other, s)
+        self._version += 1
+
+    def _scratch_copy(self, other: "RowHandler") -> "RowHandler":
+        tmp = other._clone_shell()
+        tmp._is_snapshot = True
+        tmp._after_clone(other, light=True)
+        tmp.owner = self.owner
+        s = self._stream()
+        with _arena.on_stream(s):
+            tmp._ensure_row()
+            ops.snapshot(tmp._row.tensor, self._src_row(other, s))
+            self._done_with(other, s)
+        return tmp
+
+    def _weighted_merge(self, other: "RowHandler", w_self: float, w_other: float,
+                        lo: int = 0, hi: Optional[int] = None) -> None:
+        s = self._stream()
+        with _arena.on_stream(s):
+            ops.merge_pair(self.row, self._src_row(other, s), w_self, w_other, lo, hi)
+            self._done_with(other, s)
+        self._version += 1
+
+    # -- (de)serialisation: rows travel as CPU tensors ------------------------------------
+    def __getstate__(self) -> Dict[str, Any]:
+        st = dict(self.__dict__)
+        st["_row"] = None if self._row is None else self._row.tensor.detach().cpu().clone()
+        st.pop("_module", None)
+        st.pop("_torch_opt", None)
+        st["_grad_row"] = None
+        opt = st.get("_opt_rows")
+        if opt:
+            st["_opt_rows"] = {k: v.detach().cpu().clone() for k, v in opt.items()}
+        return st
+
+    def __setstate__(self, st: Dict[str, Any]) -> None:
+        saved = st.pop("_row", None)
+        self.__dict__.update(st)
+        self._row = None
+        self._restore_members()
+        if saved is not None:
+            self._ensure_row().tensor.copy_(saved)
+        opt = self.__dict__.get("_opt_rows")
+        if opt:
+            self._opt_rows = {k: v.to(self.device) for k, v in opt.items()}
+
+    def _restore_members(self) -> None:
+        """Hook: rebuild members dropped by ``__getstate__``."""
+
+
+# --------------------------------------------------------------------------------------
+# TorchModelHandler
+# --------------------------------------------------------------------------------------
+def _is_plain_ce(criterion: Any) -> bool:
+    if criterion is F.cross_entropy:
+        return True
+    if isinstance(criterion, torch.nn.CrossEntropyLoss):
+        return (criterion.weight is None and criterion.reduction == "mean"
+                and getattr(criterion, "label_smoothing", 0.0) == 0.0
+                and criterion.ignore_index == -100)
+    return False
+
+
+class TorchModelHandler(RowHandler):
+    """Mini-batch gradient learner for any :class:`TorchModel` (ref ``handler.py:185-334``).
+
+    Parameters as in the reference: ``net, optimizer (class), optimizer_params, criterion,
+    local_epochs=1, batch_size=32, create_model_mode=MERGE_UPDATE, copy_model=True``.
+
+    Execution paths chosen once at construction:
+
+    ``fused``    the net advertises a kernel family (``TorchMLP`` with one ReLU hidden layer,
+                 ``LogisticRegression``), the optimizer is momentum-free SGD and the criterion is
+                 mean cross-entropy -> a whole local epoch (shuffle, forward, backward, SGD) is
+                 ONE persistent kernel launch, weights never leave the SM.
+    ``generic``  everything else -> the module's parameters are views of the row, autograd runs
+                 the step, and SGD(+momentum/nesterov) / Adam / AdamW are a single flat kernel
+                 over the row (other optimizer classes fall back to the torch optimizer).
+    """
+
+    def __init__(self, net: TorchModel, optimizer: Any, optimizer_params: Dict[str, Any],
+                 criterion: Callable, local_epochs: int = 1, batch_size: int = 32,
+                 create_model_mode: CreateModelMode = CreateModelMode.MERGE_UPDATE,
+                 copy_model: bool = True) -> None:
+        super().__init__(create_model_mode)
+        assert (batch_size == 0 and local_epochs > 0) or (batch_size > 0)
+        # `_proto` is an unbound template (architecture + initial values) shared by all clones;
+        # `_module` is this handler's live module whose tensors are views of the row (lazy).
+        self._proto = copy.deepcopy(net)
+        self._module = None if copy_model else net
+        self.layout = FlatLayout(self._proto)
+        self._row_numel = self.layout.padded
+        self.optimizer_cls = optimizer
+        self.optimizer_params = dict(optimizer_params)
+        self.criterion = criterion
+        self.local_epochs = local_epochs
+        self.batch_size = batch_size
+        self._family = self._proto.fused_family() if hasattr(self._proto, "fused_family") else None
+        self._opt_kind = self._classify_optimizer()
+        self._fused = (self._family is not None and self._family[0] in ("mlp1", "logreg")
+                       and self._opt_kind == "sgd_plain" and _is_plain_ce(criterion))
+        self._grad_row: Optional[torch.Tensor] = None
+        self._opt_rows: Dict[str, torch.Tensor] = {}
+        self._opt_steps = 0
+        self._torch_opt = None
+        self._update_counter = 0
+        self._bound_to = None
+        self._int_state: Optional[Dict[str, torch.Tensor]] = None
+
+    # -- construction helpers -------------------------------------------------------------
+    def _classify_optimizer(self) -> str:
+        p = self.optimizer_params
+        if self.optimizer_cls is torch.optim.SGD:
+            extra = set(p) - {"lr", "weight_decay", "momentum", "dampening", "nesterov"}
+            if extra:
+                return "torch"
+            if not p.get("momentum", 0) and not p.get("nesterov", False):
+                return "sgd_plain"
+            return "sgd_momentum"
+        if self.optimizer_cls in (torch.optim.Adam, torch.optim.AdamW):
+            extra = set(p) - {"lr", "betas", "eps", "weight_decay"}
+            return "torch" if extra else ("adamw" if self.optimizer_cls is torch.optim.AdamW
+                                          else "adam")
+        return "torch"
+
+    @property
+    def model(self) -> TorchModel:
+        """The live ``nn.Module`` whose parameters are views of this handler's row."""
+        if self._module is None:
+            self._module = copy.deepcopy(self._proto)
+            self._bound_to = None
+            if self._int_state:
+                bufs = dict(self._module.named_buffers())
+                for n, v in self._int_state.items():
+                    bufs[n].copy_(v)
+        self._bind()
+        return self._module
+
+    @model.setter
+    def model(self, value: Any) -> None:
+        if value is None:
+            return
+        row = self._ensure_row()
+        if value.__dict__.get("_parameters") is not None:
+            dev = row.tensor.device
+            if any(p.device != dev for p in value.parameters()):
+                value = copy.deepcopy(value).to(dev)
+        self.layout.gather(value, row.tensor)
+        self._module = value
+        self._bound_to = None
+        self._version += 1
+
+    def _bind(self) -> None:
+        row = self._ensure_row()
+        if self._bound_to is not row.tensor and self._module is not None:
+            if self.layout.entries:
+                dev = row.tensor.device
+                if next(self._module.parameters()).device != dev:
+                    self._module.to(dev)
+            self.layout.bind(self._module, row.tensor, None)
+            self._bound_to = row.tensor
+            self._grad_bound = False
+
+    def _on_new_row(self, old) -> None:
+        if old is None and not self._is_snapshot:
+            # first materialisation of a live handler: start from the template's values
+            src = self._module if self._module is not None else self._proto
+            self.layout.gather(src, self._row.tensor)
+        self._bound_to = None
+        self._grad_row = None
+
+    def _after_clone(self, src: "TorchModelHandler", light: bool) -> None:
+        self._grad_row = None
+        self._torch_opt = None
+        self._bound_to = None
+        self._module = None  # rebuilt lazily from the shared template when someone asks for it
+        self._int_state = src._int_values() if self.layout.int_buffers else None
+        need_state = (not light) or self.mode in (CreateModelMode.UPDATE,
+                                                  CreateModelMode.UPDATE_MERGE)
+        self._opt_rows = ({k: v.clone() for k, v in src._opt_rows.items()} if need_state else {})
+        if not light and src._row is None and src._module is not None:
+            # copying a never-materialised handler built with copy_model=False
+            self._proto = copy.deepcopy(src._module)
+
+    def _restore_members(self) -> None:
+        self._torch_opt = None
+        self._bound_to = None
+        self._module = None
+
+    def __getstate__(self) -> Dict[str, Any]:
+        st = super().__getstate__()
+        st["_module"] = None
+        st["_bound_to"] = None
+        return st
+
+    # -- API --------------------------------------------------------------------------------
+    def init(self) -> None:
+        mod = self.model
+        with _arena.on_stream(self._stream()):
+            mod.init_weights()
+        self._version += 1
+
+    def get_size(self) -> int:
+        return self._proto.get_size()
+
+    # -- local learning -------------------------------------------------------------------
+    def _next_key(self) -> int:
+        self._update_counter += 1
+        return _rng.derive(0x5EED, self.owner if self.owner >= 0 else 0, self._update_counter,
+                           int(np.sum(self.n_updates)))
+
+    def _elem_scale(self) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+        return None
+
+    def _count_steps(self, steps: int) -> None:
+        self.n_updates += steps
+
+    def _update(self, data: Tuple[torch.Tensor, torch.Tensor]) -> None:
+        x, y = self._to_device(data)
+        s = self._stream()
+        with _arena.on_stream(s):
+            if self._fused:
+                steps = self._update_fused(x, y)
+            else:
+                steps = self._update_generic(x, y)
+        self._count_steps(steps)
+        self._version += 1
+
+    def _update_fused(self, x: torch.Tensor, y: torch.Tensor) -> int:
+        fam, dims = self._family
+        lr = float(self.optimizer_params.get("lr", 1e-3))
+        wd = float(self.optimizer_params.get("weight_decay", 0.0))
+        fn = ops.mlp1_train if fam == "mlp1" else ops.logreg_train
+        if x.dim() > 2:
+            x = x.reshape(x.shape[0], -1)
+        return fn(self.row, x, y, dims, self.batch_size, self.local_epochs, lr, wd,
+                  self._next_key(), self._elem_scale())
+
+    def _ensure_grad(self) -> torch.Tensor:
+        mod = self.model
+        if self._grad_row is None or self._grad_row.device != self.row.device:
+            self._grad_row = torch.zeros_like(self.row)
+            self._grad_bound = False
+        if not getattr(self, "_grad_bound", False):
+            self.layout.bind(mod, self.row, self._grad_row)
+            self._grad_bound = True
+        return self._grad_row
+
+    def _update_generic(self, x: torch.Tensor, y: torch.Tensor) -> int:
+        mod = self.model
+        n = x.size(0)
+        bs = n if not self.batch_size else self.batch_size
+        gen_key = self._next_key()
+        steps = 0
+        if self.local_epochs > 0:
+            for e in range(self.local_epochs):
+                perm = torch.from_numpy(ops.torch_ref.perm_indices(n, _rng.mix64(gen_key ^ e))).to(x.device)
+                for i in range(0, n, bs):
+                    idx = perm[i:i + bs]
+                    self._local_step(mod, x[idx], y[idx])
+                    steps += 1
+        else:
+            perm = torch.from_numpy(ops.torch_ref.perm_indices(n, _rng.mix64(gen_key))).to(x.device)
+            idx = perm[:bs]
+            self._local_step(mod, x[idx], y[idx])
+            steps = 1
+        return steps
+
+    def _local_step(self, mod: TorchModel, x: torch.Tensor, y: torch.Tensor) -> None:
+        """forward / loss / backward / optimizer step (ref ``handler.py:250-258``)."""
+        mod.train()
+        g = self._ensure_grad()
+        g.zero_()
+        loss = self.criterion(mod(x), y)
+        loss.backward()
+        self._pre_step()
+        self._apply_optimizer(g)
+
+    def _pre_step(self) -> None:
+        """Hook between backward and the optimizer step (gradient adjustment)."""
+
+    def _apply_optimizer(self, g: torch.Tensor) -> None:
+        p = self.optimizer_params
+        n = self.layout.n_params
+        row = self.row
+        kind = self._opt_kind
+        if kind in ("sgd_plain", "sgd_momentum"):
+            mom = float(p.get("momentum", 0.0))
+            buf = None
+            first = False
+            if mom:
+                buf = self._opt_rows.get("momentum")
+                if buf is None:
+                    buf = self._opt_rows["momentum"] = torch.zeros_like(row)
+                    first = True
+            ops.sgd_step(row, g, n, float(p.get("lr", 1e-3)), float(p.get("weight_decay", 0.0)),
+                         mom, buf, float(p.get("dampening", 0.0)), bool(p.get("nesterov", False)),
+                         first, self._grad_scale())
+        elif kind in ("adam", "adamw"):
+            m = self._opt_rows.get("exp_avg")
+            if m is None:
+                m = self._opt_rows["exp_avg"] = torch.zeros_like(row)
+                self._opt_rows["exp_avg_sq"] = torch.zeros_like(row)
+                self._opt_steps = 0
+            self._opt_steps += 1
+            b1, b2 = p.get("betas", (0.9, 0.999))
+            default_wd = 0.01 if kind == "adamw" else 0.0
+            ops.adam_step(row, g, n, m, self._opt_rows["exp_avg_sq"], self._opt_steps,
+                          float(p.get("lr", 1e-3)), float(b1), float(b2), float(p.get("eps", 1e-8)),
+                          float(p.get("weight_decay", default_wd)), kind == "adamw")
+        else:
+            if self._torch_opt is None:
+                self._torch_opt = self.optimizer_cls(self.model.parameters(), **p)
+            self._torch_opt.step()
+
+    def _grad_scale(self) -> Optional[torch.Tensor]:
+        return None
+
+    # -- merging -----------------------------------------------------------------------------
+    def _merge(self, other_model_handler: Union["TorchModelHandler", Iterable["TorchModelHandler"]]
+               ) -> None:
+        """Uniform average with one or several models; age = max (ref ``handler.py:260-280``)."""
+        if isinstance(other_model_handler, TorchModelHandler):
+            self._weighted_merge(other_model_handler, 0.5, 0.5)
+            self.n_updates = max(self.n_updates, other_model_handler.n_updates)
+        else:
+            others = list(other_model_handler)
+            k = len(others) + 1
+            self._kway_merge(others, [1.0 / k] * k)
+            self.n_updates = max([self.n_updates] + [o.n_updates for o in others])
+        self._merge_int_buffers(other_model_handler)
+
+    def _kway_merge(self, others: Sequence["TorchModelHandler"], weights: Sequence[float]) -> None:
+        s = self._stream()
+        with _arena.on_stream(s):
+            srcs = [self._src_row(o, s) for o in others]
+            ops.merge_kway(self.row, srcs, weights)
+            for o in others:
+                self._done_with(o, s)
+        self._version += 1
+
+    def _merge_int_buffers(self, other: Any) -> None:
+        """Integer buffers (BN ``num_batches_tracked``) are combined with ``max``."""
+        if not self.layout.int_buffers:
+            return
+        others = [other] if isinstance(other, TorchModelHandler) else list(other)
+        mine = dict(self.model.named_buffers())
+        for o in others:
+            theirs = o._int_values()
+            for name in self.layout.int_buffers:
+                mine[name].copy_(torch.maximum(mine[name], theirs[name].to(mine[name].device)))
+
+    def _int_values(self) -> Dict[str, torch.Tensor]:
+        """Current integer-buffer values (live module if there is one, else the carried copy)."""
+        if not self.layout.int_buffers:
+            return {}
+        if self._module is not None:
+            bufs = dict(self._module.named_buffers())
+            return {n: bufs[n].detach().clone() for n in self.layout.int_buffers}
+        if self._int_state is not None:
+            return self._int_state
+        bufs = dict(self._proto.named_buffers())
+        return {n: bufs[n].detach().clone() for n in self.layout.int_buffers}
+
+    # -- evaluation -----------------------------------------------------------------------------
+    def _forward_scores(self, x: torch.Tensor) -> torch.Tensor:
+        mod = self._module
+        if mod is not None:
+            self._bind()
+            mod.eval()
+            with torch.no_grad():
+                return mod(x)
+        proto = self._proto
+        if self.layout.entries and next(proto.parameters()).device != self.row.device:
+            proto.to(self.row.device)
+        views = self.layout.views(self.row)
+        was_training = proto.training
+        proto.eval()
+        try:
+            with torch.no_grad():
+                return torch.func.functional_call(proto, views, (x,))
+        finally:
+            proto.train(was_training)
+
+    def evaluate_async(self, data: Tuple[torch.Tensor, torch.Tensor]) -> PendingEval:
+        """accuracy / macro precision / recall / F1 (+AUC for 2 outputs) -- ref ``:282-334``."""
+        x, y = self._to_device(data)
+        if y.dim() > 1:
+            y = torch.argmax(y, dim=-1)
+        s = self._stream()
+        with _arena.on_stream(s):
+            _arena.before_read(self._ensure_row(), s if s is not None else _arena.current(self.device))
+            fam = self._family
+            auc_in = None
+            if fam is not None and fam[0] == "mlp1":
+                n_out = fam[1][2]
+                xx = x.reshape(x.shape[0], -1) if x.dim() > 2 else x
+                if n_out == 2:
+                    scores = ops.torch_ref.mlp1_logits(self.row, xx, fam[1])
+                    cm = ops.torch_ref.confusion_matrix(y, scores.argmax(1), 2)
+                    auc_in = scores[:, 1]
+                else:
+                    cm = ops.mlp1_eval(self.row, xx, y, fam[1], n_out)
+            else:
+                if fam is not None and fam[0] == "logreg":
+                    scores = ops.logreg_scores(self.row, x, fam[1])
+                else:
+                    scores = self._forward_scores(x)
+                n_out = scores.shape[1]
+                cm = ops.torch_ref.confusion_matrix(y, scores.argmax(dim=-1), n_out)
+                if n_out == 2:
+                    auc_in = scores[:, 1]
+            auc_t = None
+            if auc_in is not None:
+                auc_t = (y == 1, auc_in.detach())
+
+        def finish() -> Dict[str, float]:
+            res = _metrics.classification_report(cm.cpu().numpy())
+            if auc_t is not None:
+                pos, sc = auc_t
+                if int(pos.sum()) in (0, pos.numel()):
+                    LOG.warning("# of classes != 2. AUC is set to 0.5.")
+                    res["auc"] = 0.5
+                else:
+                    res["auc"] = _metrics.roc_auc(pos, sc)
+            return res
+        return PendingEval(finish)
+
+    def evaluate(self, data: Tuple[torch.Tensor, torch.Tensor]) -> Dict[str, float]:
+        return self.evaluate_async(data).result()
+
+    def __str__(self) -> str:
+        return "%s(model=%s_%s, mode=%s)" % (self.__class__.__name__, str(self._proto),
+                                             self.n_updates, self.mode)
+
+
+# --------------------------------------------------------------------------------------
+# AdaLine / Pegasos
+# --------------------------------------------------------------------------------------
+class AdaLineHandler(RowHandler):
+    """Widrow-Hoff learner on a bare weight vector (ref ``handler.py:337-391``)."""
+
+    def __init__(self, net: AdaLine, learning_rate: float,
+                 create_model_mode: CreateModelMode = CreateModelMode.UPDATE,
+                 copy_model: bool = True) -> None:
+        super().__init__(create_model_mode)
+        self._module = copy.deepcopy(net) if copy_model else net
+        self.dim = self._module.input_dim
+        self.learning_rate = learning_rate
+        self._row_numel = max(32, (self.dim + 31) // 32 * 32)
+
+    @property
+    def model(self) -> AdaLine:
+        mod = self._module
+        w = self.row[:self.dim]
+        if mod.model.data_ptr() != w.data_ptr():
+            mod.model.data = w
+        return mod
+
+    @model.setter
+    def model(self, value: Any) -> None:
+        if value is None:
+            return
+        self._module = value
+        if self._row is not None:
+            self.row[:self.dim].copy_(value.model.detach().to(self.row.device))
+            self._version += 1
+
+    def _on_new_row(self, old) -> None:
+        if old is None and not self._is_snapshot:
+            self._row.tensor.zero_()
+            self._row.tensor[:self.dim].copy_(self._module.model.detach().to(self._row.tensor.device))
+
+    def _after_clone(self, src: "AdaLineHandler", light: bool) -> None:
+        # a materialised source's values arrive through the row copy; otherwise keep its net
+        self._module = AdaLine(src.dim) if src._row is not None else copy.deepcopy(src._module)
+
+    def __getstate__(self) -> Dict[str, Any]:
+        st = super().__getstate__()
+        st["_module"] = AdaLine(self.dim)
+        return st
+
+    def init(self) -> None:
+        self.model.init_weights()
+        self._version += 1
+
+    def get_size(self) -> int:
+        return self.dim
+
+    def _w(self) -> torch.Tensor:
+        return self.row[:self.dim]
+
+    def _update(self, data: Tuple[torch.Tensor, torch.Tensor]) -> None:
+        x, y = self._to_device(data)
+        with _arena.on_stream(self._stream()):
+            ops.adaline_update(self._w(), x, y.to(torch.float32), self.learning_rate)
+        self.n_updates += len(y)
+        self._version += 1
+
+    def _merge(self, other_model_handler: "AdaLineHandler") -> None:
+        self._weighted_merge(other_model_handler, 0.5, 0.5)
+        self.n_updates = max(self.n_updates, other_model_handler.n_updates)
+
+    def evaluate_async(self, data: Tuple[torch.Tensor, torch.Tensor]) -> PendingEval:
+        x, y = self._to_device(data)
+        with _arena.on_stream(self._stream()):
+            scores = x.float() @ self._w()
+            pred_pos = scores >= 0
+            true_pos = y > 0
+            cm = ops.torch_ref.confusion_matrix(true_pos.long(), pred_pos.long(), 2)
+            sc = scores.detach()
+
+        def finish() -> Dict[str, float]:
+            res = _metrics.classification_report(cm.cpu().numpy())
+            res["auc"] = _metrics.roc_auc(true_pos, sc)
+            return res
+        return PendingEval(finish)
+
+    def evaluate(self, data: Tuple[torch.Tensor, torch.Tensor]) -> Dict[str, float]:
+        return self.evaluate_async(data).result()
+
+
+class PegasosHandler(AdaLineHandler):
+    """Pegasos SVM steps, one per local sample (ref ``handler.py:394-423``)."""
+
+    def _update(self, data: Tuple[torch.Tensor, torch.Tensor]) -> None:
+        x, y = self._to_device(data)
+        with _arena.on_stream(self._stream()):
+            self.n_updates = ops.pegasos_update(self._w(), x, y.to(torch.float32),
+                                                self.learning_rate, int(self.n_updates))
+        self._version += 1
+
+
+# --------------------------------------------------------------------------------------
+# sampled / partitioned / weighted / limited merges
+# --------------------------------------------------------------------------------------
+class SamplingTMH(TorchModelHandler):
+    """Merge only a random subset of coordinates (ref ``handler.py:426-452``)."""
+
+    def __init__(self, sample_size: float, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        self.sample_size = sample_size
+
+    def draw_sample(self) -> torch.Tensor:
+        """Flat positions to merge, generated on the handler's device."""
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(_rng.derive(0x5A3F, max(self.owner, 0), self._next_key() & 0xFFFFFFFF))
+        return TorchModelSampling.sample_flat(self.sample_size, self.layout.n_params,
+                                              device=self.device, generator=gen)
+
+    def _merge(self, other_model_handler: "SamplingTMH", sample: Any) -> None:
+        if isinstance(sample, dict):
+            sample = sample_dict_to_flat(sample, self._proto)
+        s = self._stream()
+        with _arena.on_stream(s):
+            idx = sample.to(self.device)
+            ops.merge_indexed(self.row, self._src_row(other_model_handler, s), idx, 0.5, 0.5)
+            self._done_with(other_model_handler, s)
+        self._version += 1
+
+    def __call__(self, recv_model: Any, data: Any, sample: Any) -> None:
+        if self.mode == CreateModelMode.PASS:
+            raise ValueError("Mode PASS not allowed for sampled models.")
+        if self.mode == CreateModelMode.UPDATE:
+            tmp = self._scratch_copy(recv_model)
+            tmp._update(data)
+            self._merge(tmp, sample)
+            _dispose(tmp)
+        else:
+            super().__call__(recv_model, data, sample)
+
+
+class PartitionedTMH(TorchModelHandler):
+    """Per-partition ages and merges (ref ``handler.py:455-525``).
+
+    ``n_updates`` is an int array with one age per partition.  Every local step increments all
+    ages and divides the gradient of partition ``p`` by its age (a per-partition ``1/t``
+    learning-rate decay) -- folded into the fused kernels' SGD epilogue / the flat optimizer.
+    """
+
+    def __init__(self, net: TorchModel, tm_partition: TorchModelPartition, optimizer: Any,
+                 optimizer_params: Dict[str, Any], criterion: Callable, local_epochs: int = 1,
+                 batch_size: int = 32,
+                 create_model_mode: CreateModelMode = CreateModelMode.MERGE_UPDATE,
+                 copy_model: bool = True) -> None:
+        super().__init__(net, optimizer, optimizer_params, criterion, local_epochs, batch_size,
+                         create_model_mode, copy_model)
+        self.tm_partition = tm_partition
+        self.n_updates = np.zeros(tm_partition.n_parts, dtype=int)
+        self._part_id_dev: Optional[torch.Tensor] = None
+        self._seg_dev: Dict[int, torch.Tensor] = {}
+
+    def _part_ids(self) -> torch.Tensor:
+        if self._part_id_dev is None or self._part_id_dev.device != self.row.device:
+            self._part_id_dev = self.tm_partition.part_id.to(self.row.device)
+        return self._part_id_dev
+
+    def _elem_scale(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        return (self._part_ids(), torch.as_tensor(self.n_updates, dtype=torch.int64,
+                                                  device=self.row.device))
+
+    def _count_steps(self, steps: int) -> None:
+        if self._fused:
+            self.n_updates = self.n_updates + steps  # generic path counts per step
+
+    def _pre_step(self) -> None:
+        self.n_updates = self.n_updates + 1
+
+    def _grad_scale(self) -> torch.Tensor:
+        inv = 1.0 / torch.as_tensor(self.n_updates, dtype=torch.float32, device=self.row.device)
+        scale = torch.ones_like(self.row)
+        scale[:self.layout.n_params] = inv[self._part_ids()]
+        return scale
+
+    def __call__(self, recv_model: Any, data: Any, id_part: int) -> None:
+        if self.mode == CreateModelMode.PASS:
+            raise ValueError("Mode PASS not allowed for partitioned models.")
+        if self.mode == CreateModelMode.UPDATE:
+            tmp = self._scratch_copy(recv_model)
+            tmp._update(data)
+            self._merge(tmp, id_part)
+            _dispose(tmp)
+        else:
+            super().__call__(recv_model, data, id_part)
+
+    def _merge(self, other_model_handler: "PartitionedTMH", id_part: int) -> None:
+        pid = id_part % self.tm_partition.n_parts
+        a, b = int(self.n_updates[pid]), int(other_model_handler.n_updates[pid])
+        w1, w2 = TorchModelPartition.mixing_weights((a, b))
+        seg = self._seg_dev.get(pid)
+        if seg is None or seg.device != self.row.device:
+            seg = self._seg_dev[pid] = self.tm_partition.segments(pid).to(self.row.device)
+        s = self._stream()
+        with _arena.on_stream(s):
+            ops.merge_segments(self.row, self._src_row(other_model_handler, s), seg, w1, w2)
+            self._done_with(other_model_handler, s)
+        self.n_updates[pid] = max(a, b)
+        self._version += 1
+
+    def _age_key(self) -> str:
+        return str(self.n_updates)
+
+    def _after_clone(self, src: "PartitionedTMH", light: bool) -> None:
+        super()._after_clone(src, light)
+        self.n_updates = np.array(src.n_updates, copy=True)
+
+    def __getstate__(self) -> Dict[str, Any]:
+        st = super().__getstate__()
+        st["_part_id_dev"] = None
+        st["_seg_dev"] = {}
+        return st
+
+
+class WeightedTMH(TorchModelHandler):
+    """Weighted neighbourhood averaging for decentralised SGD (ref ``handler.py:642-688``)."""
+
+    def __call__(self, recv_model: Any, data: Any, weights: Iterable[float]) -> None:
+        if self.mode == CreateModelMode.UPDATE:
+            super().__call__(recv_model, data)
+        elif self.mode == CreateModelMode.MERGE_UPDATE:
+            self._merge(recv_model, weights)
+            self._update(data)
+        elif self.mode == CreateModelMode.UPDATE_MERGE:
+            self._update(data)
+            recvs = list(recv_model) if not isinstance(recv_model, TorchModelHandler) else [recv_model]
+            tmps = [self._scratch_copy(r) for r in recvs]
+            for t in tmps:
+                t._update(data)
+            self._merge(tmps if not isinstance(recv_model, TorchModelHandler) else tmps[0], weights)
+            for t in tmps:
+                _dispose(t)
+        else:
+            raise ValueError("Invalid create model mode %s for WeightedTMH." % str(self.mode))
+
+    def _merge(self, other_model_handler: Union[TorchModelHandler, Iterable[TorchModelHandler]],
+               weights: Iterable[float]) -> None:
+        w = [float(x) for x in weights]
+        others = ([other_model_handler] if isinstance(other_model_handler, TorchModelHandler)
+                  else list(other_model_handler))
+        self._kway_merge(others, w[:len(others) + 1])
+        self.n_updates = max([self.n_updates] + [o.n_updates for o in others])
+        self._merge_int_buffers(others)
+
+
+class LimitedMergeMixin:
+    """Age-limited merge of Danner et al. 2023 (ref ``handler.py:690-715``)."""
+
+    def __init__(self, age_diff_threshold: int = 1) -> None:
+        self.L = age_diff_threshold
+
+    def _merge(self, other_model_handler: Any) -> None:
+        if not isinstance(other_model_handler, TorchModelHandler):
+            raise ValueError("Invalid type for other_model_handler: %s" % type(other_model_handler))
+        a, b = self.n_updates, other_model_handler.n_updates
+        if a > b + self.L:
+            pass  # own model is much older: keep it
+        elif b > a + self.L:
+            self._adopt(other_model_handler)
+        else:
+            tot = a + b
+            if tot == 0:
+                self._weighted_merge(other_model_handler, 0.5, 0.5)
+            else:
+                self._weighted_merge(other_model_handler, a / tot, b / tot)
+        self.n_updates = max(a, b)
+
+
+class LimitedMergeTMH(LimitedMergeMixin, TorchModelHandler):
+    def __init__(self, net: TorchModel, optimizer: Any, optimizer_params: Dict[str, Any],
+                 criterion: Callable, local_epochs: int = 1, batch_size: int = 32,
+                 create_model_mode: CreateModelMode = CreateModelMode.MERGE_UPDATE,
+                 age_diff_threshold: int = 1, copy_model: bool = True) -> None:
+        TorchModelHandler.__init__(self, net, optimizer, optimizer_params, criterion,
+                                   local_epochs, batch_size, create_model_mode, copy_model)
+        LimitedMergeMixin.__init__(self, age_diff_threshold)
+
+
+# --------------------------------------------------------------------------------------
+# matrix factorisation
+# --------------------------------------------------------------------------------------
+class MFModelHandler(RowHandler):
+    """Rank-k matrix factorisation of one user's ratings (ref ``handler.py:528-576``).
+
+    Row layout ``[Y (n_items*k) | c (n_items) | X (k) | b (1)]``: the shared item factors are a
+    contiguous prefix, so the merge (item side only) is one ranged merge kernel.
+    """
+
+    def __init__(self, dim: int, n_items: int, lam_reg: float = 0.1, learning_rate: float = 0.001,
+                 create_model_mode: CreateModelMode = CreateModelMode.UPDATE) -> None:
+        super().__init__(create_model_mode)
+        self.reg, self.k, self.lr, self.n_items = lam_reg, dim, learning_rate, n_items
+        self.n_updates = 1
+        n = n_items * dim + n_items + dim + 1
+        self._n_shared = n_items * dim + n_items
+        self._row_numel = (n + 31) // 32 * 32
+
+    def _parts(self):
+        r, k, m = self.row, self.k, self.n_items
+        Y = r[:m * k].view(m, k)
+        c = r[m * k:m * k + m]
+        X = r[m * k + m:m * k + m + k]
+        b = r[m * k + m + k:m * k + m + k + 1]
+        return X, b, Y, c
+
+    @property
+    def model(self):
+        if self._row is None:
+            return None
+        X, b, Y, c = self._parts()
+        return ((X.cpu().numpy().reshape(1, -1), float(b[0])), (Y.cpu().numpy(), c.cpu().numpy()))
+
+    @model.setter
+    def model(self, value: Any) -> None:
+        if value is None:
+            return
+        (Xn, bn), (Yn, cn) = value
+        X, b, Y, c = self._parts()
+        X.copy_(torch.as_tensor(np.asarray(Xn).reshape(-1), dtype=torch.float32))
+        b.fill_(float(bn))
+        Y.copy_(torch.as_tensor(np.asarray(Yn), dtype=torch.float32))
+        c.copy_(torch.as_tensor(np.asarray(cn), dtype=torch.float32))
+        self._version += 1
+
+    def init(self, r_min: int = 1, r_max: int = 5) -> None:
+        mul = float(np.sqrt((r_max - r_min) / self.k))
+        X, b, Y, c = self._parts()
+        gen = torch.Generator().manual_seed(_rng.derive(0x3F, max(self.owner, 0)))
+        X.copy_(torch.rand(self.k, generator=gen) * mul)
+        Y.copy_(torch.rand(self.n_items, self.k, generator=gen) * mul)
+        b.fill_(r_min / 2.0)
+        c.fill_(r_min / 2.0)
+        self._version += 1
+
+    def _update(self, data: Any) -> None:
+        ratings = self._to_device(data)
+        if isinstance(ratings, (list, tuple)):
+            ratings = torch.as_tensor(np.asarray(ratings), dtype=torch.float32, device=self.device)
+        ratings = ratings.to(torch.float32).reshape(-1, 2)
+        X, b, Y, c = self._parts()
+        with _arena.on_stream(self._stream()):
+            self.n_updates += ops.mf_update(X, b, Y, c, ratings, self.reg, self.lr)
+        self._version += 1
+
+    def _merge(self, other_model_handler: "MFModelHandler") -> None:
+        """Item factors only: ``Y = (Y n + Y' n') / (2 (n + n'))`` -- the extra 1/2 is the
+        reference's (``handler.py:566-567``) and is kept by default because it shapes
+        the published-style curves."""
+        a, b = self.n_updates, other_model_handler.n_updates
+        den = 2.0 * (a + b)
+        self._weighted_merge(other_model_handler, a / den, b / den, 0, self._n_shared)
+
+    def evaluate(self, ratings: Any) -> Dict[str, float]:
+        r = self._to_device(ratings)
+        if not isinstance(r, torch.Tensor):
+            r = torch.as_tensor(np.asarray(r), dtype=torch.float32, device=self.device)
+        r = r.to(torch.float32).reshape(-1, 2)
+        X, b, Y, c = self._parts()
+        with _arena.on_stream(self._stream()):
+            idx = r[:, 0].long()
+            pred = Y[idx] @ X + b + c[idx]
+            rmse = torch.sqrt(torch.mean((r[:, 1] - pred) ** 2))
+        return {"rmse": float(rmse)}
+
+    def get_size(self) -> int:
+        return self.k * (self.n_items + 1)
+
+
+# --------------------------------------------------------------------------------------
+# k-means
+# --------------------------------------------------------------------------------------
+class KMeansHandler(RowHandler):
+    """Online k-means with centroid gossip (ref ``handler.py:579-639``)."""
+
+    def __init__(self, k: int, dim: int, alpha: float = 0.1, matching: str = "naive",
+                 create_model_mode: CreateModelMode = CreateModelMode.UPDATE) -> None:
+        assert matching in {"naive", "hungarian"}, "Invalid matching method."
+        super().__init__(create_model_mode)
+        self.k, self.dim, self.matching, self.alpha = k, dim, matching, alpha
+        self._row_numel = max(32, (k * dim + 31) // 32 * 32)
+
+    @property
+    def model(self) -> Optional[torch.Tensor]:
+        if self._row is None:
+            return None
+        return self.row[:self.k * self.dim].view(self.k, self.dim)
+
+    @model.setter
+    def model(self, value: Any) -> None:
+        if value is None:
+            return
+        self.row[:self.k * self.dim].copy_(torch.as_tensor(value, dtype=torch.float32).reshape(-1))
+        self._version += 1
+
+    def init(self) -> None:
+        gen = torch.Generator().manual_seed(_rng.derive(0x4B, max(self.owner, 0)))
+        self.model = torch.rand(self.k, self.dim, generator=gen)
+
+    def _update(self, data: Tuple[torch.Tensor, Any]) -> None:
+        x, _ = self._to_device(data)
+        with _arena.on_stream(self._stream()):
+            ops.kmeans_update(self.model, x.float().reshape(-1, self.dim), self.alpha)
+        self.n_updates += 1
+        self._version += 1
+
+    def _merge(self, other_model_handler: "KMeansHandler") -> None:
+        """Average centroids, optionally after optimal (Hungarian) matching.
+
+        FIX(B16): the reference indexes with the *row* assignment (an identity), so its
+        "hungarian" equals "naive"; here the peer's centroids are permuted by the column
+        assignment.  With ``reference_compat`` the identity behaviour is reproduced."""
+        if self.matching == "naive" or GlobalSettings().reference_compat:
+            self._weighted_merge(other_model_handler, 0.5, 0.5)
+            return
+        from scipy.optimize import linear_sum_assignment
+        s = self._stream()
+        with _arena.on_stream(s):
+            theirs = self._src_row(other_model_handler, s)[:self.k * self.dim].view(self.k, self.dim)
+            cost = torch.cdist(self.model, theirs).cpu().numpy()
+            cols = linear_sum_assignment(cost)[1]
+            perm = torch.as_tensor(cols, device=self.row.device)
+            self.model.copy_((self.model + theirs[perm]) / 2)
+            self._done_with(other_model_handler, s)
+        self._version += 1
+
+    def evaluate(self, data: Tuple[torch.Tensor, torch.Tensor]) -> Dict[str, float]:
+        X, y = self._to_device(data)
+        with _arena.on_stream(self._stream()):
+            pred = ops.kmeans_assign(self.model, X.float().reshape(-1, self.dim))
+            yl = y.long().reshape(-1)
+            n_true = int(yl.max()) + 1 if yl.numel() else 1
+            ct = torch.bincount(yl * self.k + pred.long(), minlength=n_true * self.k)
+        return {"nmi": _metrics.nmi_from_contingency(ct.view(n_true, self.k).cpu().numpy())}
+
+    def get_size(self) -> int:
+        return self.k * self.dim

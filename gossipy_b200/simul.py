@@ -1,0 +1,435 @@
+"""Discrete-time gossip simulators and their observability layer.
+
+Behavioural reference: ``gossipy/simul.py`` (cited per class).  The reference has three almost
+identical copies of the timestep loop; here one engine (:meth:`GossipSimulator._run`) implements
+the four phases of a tick and the variants override two hooks:
+
+* ``_tick_node(i, t)``        what a node does when examined in phase A (fire / earn a token /
+                              merge the cached neighbourhood and broadcast);
+* ``_after_delivery(msg, reply, t)``  reaction to a delivered message (token accounts).
+
+Ordering facts preserved from the reference: within a tick all sends (snapshots)
+precede all deliveries; deliveries happen in queue order; replies after first-leg messages; a
+delay-0 PUSH_PULL completes inside its tick; sent counters tick at send time for first-leg
+messages and at delivery time for replies; the drop test is ``>=`` for sends and ``>`` for
+replies.  The host loop never waits for the GPU: device work is enqueued on per-node streams and
+only the per-round metrics (a few integers per node) are read back, once per round.
+"""
+from __future__ import annotations
+
+import json
+import pickle
+from abc import ABC, abstractmethod
+from collections import defaultdict
+from copy import deepcopy
+from typing import Any, Callable, DefaultDict, Dict, Iterable, List, Optional, Tuple, Union
+
+import numpy as np
+
+from . import CACHE, LOG, CacheKey
+from .core import AntiEntropyProtocol, ConstantDelay, Delay, Message, MixingMatrix, UniformMixing
+from .data import DataDispatcher
+from .flow_control import TokenAccount
+from .model.handler import ModelHandler, PendingEval
+from .node import All2AllGossipNode, GossipNode
+from .utils import StringEncoder
+
+try:
+    import dill as _pickler
+except Exception:  # pragma: no cover
+    _pickler = pickle
+
+__all__ = ["SimulationEventReceiver", "SimulationEventSender", "SimulationReport",
+           "GossipSimulator", "TokenizedGossipSimulator", "All2AllGossipSimulator"]
+
+
+# --------------------------------------------------------------------------------------
+# observers
+# --------------------------------------------------------------------------------------
+class SimulationEventReceiver(ABC):
+    """Observer interface (ref ``simul.py:37-88``)."""
+
+    @abstractmethod
+    def update_message(self, failed: bool, msg: Optional[Message] = None) -> None: ...
+
+    def update_evaluation(self, round: int, on_user: bool,
+                          evaluation: List[Dict[str, float]]) -> None:
+        pass
+
+    @abstractmethod
+    def update_end(self) -> None: ...
+
+    @abstractmethod
+    def update_timestep(self, t: int) -> None: ...
+
+
+class SimulationEventSender(ABC):
+    """Observable side.  FIX(B8): the receiver list is per instance, not class-wide."""
+
+    @property
+    def _receivers(self) -> List[SimulationEventReceiver]:
+        lst = self.__dict__.get("_receiver_list")
+        if lst is None:
+            lst = self.__dict__["_receiver_list"] = []
+        return lst
+
+    def add_receiver(self, receiver: SimulationEventReceiver) -> None:
+        if receiver not in self._receivers:
+            self._receivers.append(receiver)
+
+    def remove_receiver(self, receiver: SimulationEventReceiver) -> None:
+        if receiver in self._receivers:
+            self._receivers.remove(receiver)
+
+    def notify_message(self, falied: bool, msg: Optional[Message] = None) -> None:
+        for r in self._receivers:
+            r.update_message(falied, msg)
+
+    def notify_evaluation(self, round: int, on_user: bool,
+                          evaluation: List[Dict[str, float]]) -> None:
+        for r in self._receivers:
+            r.update_evaluation(round, on_user, evaluation)
+
+    def notify_timestep(self, t: int) -> None:
+        for r in self._receivers:
+            r.update_timestep(t)
+
+    def notify_end(self) -> None:
+        for r in self._receivers:
+            r.update_end()
+
+
+class SimulationReport(SimulationEventReceiver):
+    """Message counters and per-round mean metrics (ref ``simul.py:180-270``)."""
+
+    def __init__(self) -> None:
+        self.clear()
+
+    def clear(self) -> None:
+        self._sent_messages = 0
+        self._total_size = 0
+        self._failed_messages = 0
+        self._global_evaluations: List[Tuple[int, Dict[str, float]]] = []
+        self._local_evaluations: List[Tuple[int, Dict[str, float]]] = []
+
+    def update_message(self, failed: bool, msg: Optional[Message] = None) -> None:
+        if failed:
+            self._failed_messages += 1
+            return
+        assert msg is not None, "msg is not set"
+        self._sent_messages += 1
+        self._total_size += msg.get_size()
+
+    def update_evaluation(self, round: int, on_user: bool,
+                          evaluation: List[Dict[str, float]]) -> None:
+        target = self._local_evaluations if on_user else self._global_evaluations
+        target.append((round, self._collect_results(evaluation)))
+
+    def update_end(self) -> None:
+        LOG.info("# Sent messages: %d" % self._sent_messages)
+        LOG.info("# Failed messages: %d" % self._failed_messages)
+        LOG.info("Total size: %d" % self._total_size)
+
+    @staticmethod
+    def _collect_results(results: List[Dict[str, float]]) -> Dict[str, float]:
+        if not results:
+            return {}
+        return {k: float(np.mean([r[k] for r in results])) for k in results[0]}
+
+    def get_evaluation(self, local: bool = False) -> List[Tuple[int, Dict[str, float]]]:
+        return self._local_evaluations if local else self._global_evaluations
+
+    def update_timestep(self, t: int) -> None:
+        pass
+
+
+# --------------------------------------------------------------------------------------
+# the engine
+# --------------------------------------------------------------------------------------
+def _model_key(msg: Optional[Message]) -> Optional[CacheKey]:
+    if msg is not None and msg.value and isinstance(msg.value[0], CacheKey):
+        return msg.value[0]
+    return None
+
+
+class GossipSimulator(SimulationEventSender):
+    """Vanilla gossip learning simulator (ref ``simul.py:273-503``).
+
+    Parameters as in the reference: ``nodes, data_dispatcher, delta, protocol, drop_prob=0,
+    online_prob=1, delay=ConstantDelay(0), sampling_eval=0``.
+    """
+
+    def __init__(self, nodes: Dict[int, GossipNode], data_dispatcher: DataDispatcher, delta: int,
+                 protocol: AntiEntropyProtocol, drop_prob: float = 0., online_prob: float = 1.,
+                 delay: Delay = ConstantDelay(0), sampling_eval: float = 0.) -> None:
+        assert 0 <= drop_prob <= 1, "drop_prob must be in the range [0,1]."
+        assert 0 <= online_prob <= 1, "online_prob must be in the range [0,1]."
+        assert 0 <= sampling_eval <= 1, "sampling_eval must be in the range [0,1]."
+        self.data_dispatcher = data_dispatcher
+        self.n_nodes = len(nodes)
+        self.delta = delta
+        self.protocol = protocol
+        self.drop_prob = drop_prob
+        self.online_prob = online_prob
+        self.delay = delay
+        self.sampling_eval = sampling_eval
+        self.initialized = False
+        self.nodes = nodes
+        self.progress = True
+        self._clock = 0  # next tick to simulate (kept for checkpoint/resume)
+        self._msg_queues: DefaultDict[int, List[Message]] = defaultdict(list)
+        self._rep_queues: DefaultDict[int, List[Message]] = defaultdict(list)
+
+    # -- set-up -------------------------------------------------------------------------------
+    def init_nodes(self, seed: int = 98765) -> None:
+        """Initialise every node's model (one local update each).
+
+        FIX(B7): ``seed`` is honoured (the reference ignores it): it seeds the engine's
+        counter-based RNG used for model init / shuffles, leaving the host RNG streams alone.
+        """
+        from .engine import rng as _rng
+        if seed is not None:
+            _rng.set_base_seed(seed)
+        self.initialized = True
+        for node in self.nodes.values():
+            node.init_model()
+
+    # -- message plumbing ---------------------------------------------------------------------
+    def _lost(self, msg: Optional[Message]) -> None:
+        """Account a lost message and free its in-flight snapshot (FIX B10)."""
+        self.notify_message(True)
+        key = _model_key(msg)
+        if key is not None:
+            CACHE.drop(key)
+
+    def _dispatch(self, msg: Optional[Message], t: int) -> None:
+        """Send-side bookkeeping of a first-leg message: count, drop test, delay, enqueue."""
+        self.notify_message(False, msg)
+        if not msg:
+            return
+        if np.random.random() >= self.drop_prob:
+            self._msg_queues[t + self.delay.get(msg)].append(msg)
+        else:
+            self._lost(msg)
+
+    def _fire(self, node: GossipNode, t: int) -> bool:
+        """Let ``node`` gossip with one random peer.  Returns False when it has no peer."""
+        peer = node.get_peer()
+        if peer is None:
+            return False  # FIX(B6): skip this node instead of aborting the whole node loop
+        self._dispatch(node.send(t, peer, self.protocol), t)
+        return True
+
+    # -- hooks ------------------------------------------------------------------------------------
+    def _tick_node(self, i: int, t: int) -> None:
+        node = self.nodes[i]
+        if node.timed_out(t):
+            self._fire(node, t)
+
+    def _after_delivery(self, msg: Message, reply: Optional[Message], sender_mh: Any,
+                        t: int) -> None:
+        pass
+
+    def _peek_sender(self, msg: Message) -> Any:
+        return None
+
+    # -- the four phases of a tick -----------------------------------------------------------
+    def _deliver_messages(self, t: int, is_online: np.ndarray) -> None:
+        queue = self._msg_queues.get(t)
+        if not queue:
+            self._msg_queues.pop(t, None)
+            return
+        i = 0
+        while i < len(queue):  # the queue may grow while we walk it (reactive delay-0 sends)
+            msg = queue[i]
+            i += 1
+            if not is_online[msg.receiver]:
+                self._lost(msg)
+                continue
+            sender_mh = self._peek_sender(msg)
+            reply = self.nodes[msg.receiver].receive(t, msg)
+            if reply:
+                if np.random.random() > self.drop_prob:
+                    self._rep_queues[t + self.delay.get(reply)].append(reply)
+                else:
+                    self._lost(reply)
+            self._after_delivery(msg, reply, sender_mh, t)
+        del self._msg_queues[t]
+
+    def _deliver_replies(self, t: int, is_online: np.ndarray) -> None:
+        queue = self._rep_queues.pop(t, None)
+        if not queue:
+            return
+        for reply in queue:
+            if is_online[reply.receiver]:
+                self.notify_message(False, reply)
+                self.nodes[reply.receiver].receive(t, reply)
+            else:
+                self._lost(reply)
+
+    def _evaluate_round(self, t: int) -> None:
+        if self.sampling_eval > 0:
+            k = max(int(self.n_nodes * self.sampling_eval), 1)
+            sample = [self.nodes[int(i)] for i in np.random.choice(list(self.nodes.keys()), k)]
+        else:
+            sample = list(self.nodes.values())
+        local: List[PendingEval] = [n.evaluate_async() for n in sample if n.has_test()]
+        glob: List[PendingEval] = []
+        if self.data_dispatcher.has_test():
+            eval_set = self.data_dispatcher.get_eval_set()
+            glob = [n.evaluate_async(eval_set) for n in sample]
+        # everything is enqueued; only now touch the host (one wait per round, not per node)
+        if local:
+            self.notify_evaluation(t, True, [p.result() for p in local])
+        if glob:
+            self.notify_evaluation(t, False, [p.result() for p in glob])
+
+    def _run(self, n_rounds: int, resume: bool = False) -> None:
+        assert self.initialized, \
+            "The simulator is not inizialized. Please, call the method 'init_nodes'."
+        LOG.info("Simulation started.")
+        if not resume:
+            self._clock = 0
+            self._msg_queues = defaultdict(list)
+            self._rep_queues = defaultdict(list)
+            self._node_order = np.arange(self.n_nodes)
+        first, last = self._clock, self._clock + n_rounds * self.delta
+        ticks: Iterable[int] = range(first, last)
+        bar = None
+        if self.progress:
+            try:
+                from rich.progress import track
+                bar = track(ticks, description="Simulating...")
+                ticks = bar
+            except Exception:
+                bar = None
+        try:
+            for t in ticks:
+                if t % self.delta == 0:
+                    np.random.shuffle(self._node_order)
+                for i in self._node_order:
+                    self._tick_node(int(i), t)
+                is_online = np.random.random(self.n_nodes) <= self.online_prob
+                self._deliver_messages(t, is_online)
+                self._deliver_replies(t, is_online)
+                if (t + 1) % self.delta == 0:
+                    self._evaluate_round(t)
+                self.notify_timestep(t)
+                self._clock = t + 1
+        except KeyboardInterrupt:
+            LOG.warning("Simulation interrupted by user.")
+        if bar is not None and hasattr(bar, "close"):
+            bar.close()
+        self.notify_end()
+
+    def start(self, n_rounds: int = 100, resume: bool = False) -> None:
+        """Run ``n_rounds`` rounds of ``delta`` ticks.  ``resume=True`` continues the clock and
+        the pending message queues of a previous (possibly checkpointed) run."""
+        self._run(n_rounds, resume)
+
+    # -- checkpointing ---------------------------------------------------------------------------
+    def save(self, filename: str) -> None:
+        """Serialise simulator + in-flight models (ref ``simul.py:460-474``).
+
+        Model rows are pulled off the device as CPU tensors; the clock and the pending message
+        queues are part of the state, so ``load(...).start(n, resume=True)`` continues the run.
+        """
+        with open(filename, "wb") as f:
+            _pickler.dump({"simul": self, "cache": CACHE.get_cache()}, f)
+
+    @classmethod
+    def load(cls, filename: str) -> "GossipSimulator":
+        with open(filename, "rb") as f:
+            loaded = _pickler.load(f)
+        CACHE.load(loaded["cache"])
+        return loaded["simul"]
+
+    def __getstate__(self) -> Dict[str, Any]:
+        st = dict(self.__dict__)
+        st["_receiver_list"] = list(self._receivers)
+        return st
+
+    def __repr__(self) -> str:
+        return str(self)
+
+    def __str__(self) -> str:
+        skip = {"nodes", "model_handler_params", "gossip_node_params", "_msg_queues",
+                "_rep_queues", "_receiver_list", "_node_order", "accounts"}
+        attrs = {k: v for k, v in self.__dict__.items() if k not in skip}
+        return "%s %s" % (self.__class__.__name__,
+                          json.dumps(attrs, indent=4, sort_keys=True, cls=StringEncoder))
+
+
+class TokenizedGossipSimulator(GossipSimulator):
+    """Token-account flow control on top of the vanilla loop (ref ``simul.py:506-689``).
+
+    On timeout a node sends with probability ``proactive()`` and otherwise banks a token; when
+    a model message is delivered (and no reply is due) the *receiver* reacts with
+    ``reactive(utility)`` extra sends.  FIX(B4/B5): the reference issues the reactive sends from
+    a stale loop variable and may read an unbound ``sender_mh``; here the receiver reacts and the
+    sender's handler is looked up per message.
+    """
+
+    def __init__(self, nodes: Dict[int, GossipNode], data_dispatcher: DataDispatcher,
+                 token_account: TokenAccount,
+                 utility_fun: Callable[[ModelHandler, ModelHandler, Message], int], delta: int,
+                 protocol: AntiEntropyProtocol, drop_prob: float = 0., online_prob: float = 1.,
+                 delay: Delay = ConstantDelay(0), sampling_eval: float = 0.) -> None:
+        super().__init__(nodes, data_dispatcher, delta, protocol, drop_prob, online_prob, delay,
+                         sampling_eval)
+        self.utility_fun = utility_fun
+        self.token_account_proto = token_account
+        self.accounts: Dict[int, TokenAccount] = {}
+
+    def init_nodes(self, seed: int = 98765) -> None:
+        super().init_nodes(seed)
+        self.accounts = {i: deepcopy(self.token_account_proto) for i in range(self.n_nodes)}
+
+    def _tick_node(self, i: int, t: int) -> None:
+        node = self.nodes[i]
+        if not node.timed_out(t):
+            return
+        if np.random.random() < self.accounts[i].proactive():
+            self._fire(node, t)
+        else:
+            self.accounts[i].add(1)
+
+    def _peek_sender(self, msg: Message) -> Any:
+        key = _model_key(msg)
+        return CACHE[key] if key is not None else None
+
+    def _after_delivery(self, msg: Message, reply: Optional[Message], sender_mh: Any,
+                        t: int) -> None:
+        if reply:
+            return
+        receiver = self.nodes[msg.receiver]
+        utility = self.utility_fun(receiver.model_handler, sender_mh, msg)
+        account = self.accounts[msg.receiver]
+        reaction = account.reactive(utility)
+        if reaction:
+            account.sub(reaction)
+            for _ in range(int(reaction)):
+                if not self._fire(receiver, t):
+                    break
+
+    def __getstate__(self) -> Dict[str, Any]:
+        return super().__getstate__()
+
+
+class All2AllGossipSimulator(GossipSimulator):
+    """Decentralised SGD with neighbourhood averaging (ref ``simul.py:720-852``).
+
+    ``start(W_matrix, n_rounds)``: on timeout a node first merges the models cached from its
+    neighbours with row ``W[i]`` and trains, then pushes its model to *every* peer.
+    """
+
+    def _tick_node(self, i: int, t: int) -> None:
+        node: All2AllGossipNode = self.nodes[i]  # type: ignore[assignment]
+        if node.timed_out(t, self._W[i]):
+            for peer in node.get_peers():
+                self._dispatch(node.send(t, peer, self.protocol), t)
+
+    def start(self, W_matrix: MixingMatrix, n_rounds: int = 100,  # type: ignore[override]
+              resume: bool = False) -> None:
+        self._W = W_matrix
+        self._run(n_rounds, resume)
