@@ -77,8 +77,8 @@ def merge_segments(dst: torch.Tensor, src: torch.Tensor, segments: torch.Tensor,
     ``start + r*run_stride + c``.  A column-major partition of a row-major ``[out,in]`` weight is
     a handful of such blocks (ref ``sampling.py:201-234``)."""
     for start, n_runs, run_len, stride in segments.tolist():
-        d = torch.as_strided(dst, (n_runs, run_len), (stride, 1), start)
-        s = torch.as_strided(src, (n_runs, run_len), (stride, 1), start)
+        d = torch.as_strided(dst, (n_runs, run_len), (stride, 1), dst.storage_offset() + start)
+        s = torch.as_strided(src, (n_runs, run_len), (stride, 1), src.storage_offset() + start)
         d.mul_(w_dst).add_(s, alpha=w_src)
 
 
