@@ -178,3 +178,16 @@ def sync_all_streams(device: torch.device) -> None:
             ev = torch.cuda.Event()
             ev.record(s)
             cur.wait_event(ev)
+
+
+def fork_from_current(device: torch.device) -> None:
+    """Make every node stream wait for the work already enqueued on the current stream."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        return
+    cur = torch.cuda.current_stream(device)
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    for (dev_idx, _), s in _STREAMS.items():
+        if dev_idx == device.index and s is not cur:
+            s.wait_event(ev)

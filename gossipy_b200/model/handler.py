@@ -52,15 +52,28 @@ class PendingEval:
     one host synchronisation instead of one per node.
     """
 
-    def __init__(self, finish: Callable[[], Dict[str, float]]) -> None:
+    def __init__(self, finish: Callable[[], Dict[str, float]], event: Any = None) -> None:
         self._finish = finish
         self._value: Optional[Dict[str, float]] = None
+        self._event = event   # recorded on the stream that produced the statistics
 
     def result(self) -> Dict[str, float]:
         if self._value is None:
+            if self._event is not None:
+                self._event.synchronize()
             self._value = self._finish()
             self._finish = None
         return self._value
+
+
+def _mark(device: Any):
+    """Event on the *current* stream of ``device`` (None on CPU)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        return None
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    return ev
 
 
 def _resolved(d: Dict[str, float]) -> PendingEval:
@@ -227,7 +240,10 @@ def _move(t: Any, dev: torch.device) -> Any:
     hit = _DEVICE_CACHE.get(key)
     if hit is not None and hit[0] is t:
         return hit[1]
-    moved = t.to(dev, non_blocking=True).contiguous()
+    moved = t.to(dev).contiguous()
+    if dev.type == "cuda":
+        # the upload ran on whatever stream was current; later users sit on other (node) streams
+        torch.cuda.current_stream(dev).synchronize()
     _DEVICE_CACHE[key] = (t, moved)  # holding `t` keeps id() unique
     return moved
 
@@ -242,6 +258,33 @@ def to_device_cached(data: Any, dev: torch.device) -> Any:
 
 def clear_device_cache() -> None:
     _DEVICE_CACHE.clear()
+    _PINNED.clear()
+
+
+_PINNED: Dict[int, Tuple[Any, torch.Tensor]] = {}
+
+
+def refresh_device_copy(data: Any, dev: torch.device) -> int:
+    """Re-upload ``data`` from *pinned* host memory into its resident device buffers (async on the
+    current stream).  Used by the simulators' ``stream_inputs`` mode (fresh inputs every round);
+    returns the number of bytes copied."""
+    if data is None or dev.type != "cuda":
+        return 0
+    total = 0
+    for t in (data if isinstance(data, (tuple, list)) else (data,)):
+        if not isinstance(t, torch.Tensor) or t.device == dev:
+            continue
+        hit = _DEVICE_CACHE.get((id(t), str(dev)))
+        if hit is None or hit[0] is not t:
+            _move(t, dev)
+            hit = _DEVICE_CACHE[(id(t), str(dev))]
+        pin = _PINNED.get(id(t))
+        if pin is None or pin[0] is not t:
+            src = t.float() if t.dtype == torch.float64 else t
+            pin = _PINNED[id(t)] = (t, src.contiguous().pin_memory())
+        hit[1].copy_(pin[1], non_blocking=True)
+        total += pin[1].numel() * pin[1].element_size()
+    return total
 
 
 # --------------------------------------------------------------------------------------
@@ -287,6 +330,11 @@ class RowHandler(ModelHandler):
     def _to_device(self, data: Any) -> Any:
         """Device-resident copy of a node's shard / the eval set, uploaded once."""
         return to_device_cached(data, self.device)
+
+    def refresh_inputs(self, data: Any) -> int:
+        """Re-upload this node's inputs from pinned host memory on the node's stream."""
+        with _arena.on_stream(self._stream()):
+            return refresh_device_copy(data, self.device)
 
     # -- snapshot / copy ------------------------------------------------------------------
     def _clone_shell(self) -> "RowHandler":
@@ -763,6 +811,7 @@ class TorchModelHandler(RowHandler):
             auc_t = None
             if auc_in is not None:
                 auc_t = (y == 1, auc_in.detach())
+            done = _mark(self.device)
 
         def finish() -> Dict[str, float]:
             res = _metrics.classification_report(cm.cpu().numpy())
@@ -774,7 +823,7 @@ class TorchModelHandler(RowHandler):
                 else:
                     res["auc"] = _metrics.roc_auc(pos, sc)
             return res
-        return PendingEval(finish)
+        return PendingEval(finish, done)
 
     def evaluate(self, data: Tuple[torch.Tensor, torch.Tensor]) -> Dict[str, float]:
         return self.evaluate_async(data).result()
@@ -859,12 +908,13 @@ class AdaLineHandler(RowHandler):
             true_pos = y > 0
             cm = ops.torch_ref.confusion_matrix(true_pos.long(), pred_pos.long(), 2)
             sc = scores.detach()
+            done = _mark(self.device)
 
         def finish() -> Dict[str, float]:
             res = _metrics.classification_report(cm.cpu().numpy())
             res["auc"] = _metrics.roc_auc(true_pos, sc)
             return res
-        return PendingEval(finish)
+        return PendingEval(finish, done)
 
     def evaluate(self, data: Tuple[torch.Tensor, torch.Tensor]) -> Dict[str, float]:
         return self.evaluate_async(data).result()
@@ -1148,8 +1198,8 @@ class MFModelHandler(RowHandler):
         with _arena.on_stream(self._stream()):
             idx = r[:, 0].long()
             pred = Y[idx] @ X + b + c[idx]
-            rmse = torch.sqrt(torch.mean((r[:, 1] - pred) ** 2))
-        return {"rmse": float(rmse)}
+            rmse = float(torch.sqrt(torch.mean((r[:, 1] - pred) ** 2)))   # syncs the node's stream
+        return {"rmse": rmse}
 
     def get_size(self) -> int:
         return self.k * (self.n_items + 1)
@@ -1219,7 +1269,8 @@ class KMeansHandler(RowHandler):
             yl = y.long().reshape(-1)
             n_true = int(yl.max()) + 1 if yl.numel() else 1
             ct = torch.bincount(yl * self.k + pred.long(), minlength=n_true * self.k)
-        return {"nmi": _metrics.nmi_from_contingency(ct.view(n_true, self.k).cpu().numpy())}
+            ct = ct.view(n_true, self.k).cpu().numpy()                    # syncs the node's stream
+        return {"nmi": _metrics.nmi_from_contingency(ct)}
 
     def get_size(self) -> int:
         return self.k * self.dim

@@ -176,6 +176,7 @@ class GossipSimulator(SimulationEventSender):
         self.initialized = False
         self.nodes = nodes
         self.progress = True
+        self.stream_inputs = False  # True: re-upload every node's shard from pinned memory each round
         self._clock = 0  # next tick to simulate (kept for checkpoint/resume)
         self._msg_queues: DefaultDict[int, List[Message]] = defaultdict(list)
         self._rep_queues: DefaultDict[int, List[Message]] = defaultdict(list)
@@ -284,6 +285,13 @@ class GossipSimulator(SimulationEventSender):
         if glob:
             self.notify_evaluation(t, False, [p.result() for p in glob])
 
+    def _stream_round_inputs(self) -> None:
+        """Fresh inputs for the coming round: host (pinned) -> device, async on each node's stream."""
+        for node in self.nodes.values():
+            refresh = getattr(node.model_handler, "refresh_inputs", None)
+            if refresh is not None:
+                refresh(node.data[0])
+
     def _run(self, n_rounds: int, resume: bool = False) -> None:
         assert self.initialized, \
             "The simulator is not inizialized. Please, call the method 'init_nodes'."
@@ -307,6 +315,8 @@ class GossipSimulator(SimulationEventSender):
             for t in ticks:
                 if t % self.delta == 0:
                     np.random.shuffle(self._node_order)
+                    if self.stream_inputs:
+                        self._stream_round_inputs()
                 for i in self._node_order:
                     self._tick_node(int(i), t)
                 is_online = np.random.random(self.n_nodes) <= self.online_prob

@@ -1,0 +1,246 @@
+"""sm_100a kernels vs the plain PyTorch fp32 oracle (``ops.torch_ref``).  GPU only."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _cuda():
+    import gossipy_b200 as g
+    g.GlobalSettings().set_device("cuda:0")
+    yield
+    torch.cuda.synchronize()
+    g.GlobalSettings().set_device("cpu")
+
+
+def _ops():
+    from gossipy_b200 import ops
+    from gossipy_b200.ops import torch_ref
+    return ops, torch_ref
+
+
+def test_extension_is_loaded_and_has_kernels():
+    from gossipy_b200.ops.native import native
+    mod = native()
+    assert hasattr(mod, "merge_pair") and hasattr(mod, "mlp1_train")
+    assert mod.device_sm_count() >= 100
+
+
+@pytest.mark.parametrize("n", [1, 3, 31, 32, 116, 79510 + 2, 1 << 20, (1 << 22) + 5])
+@pytest.mark.parametrize("w", [(.5, .5), (0., 1.), (1., 0.), (.25, .75)])
+def test_merge_pair_sizes_alignment_weights(n, w):
+    ops, ref = _ops()
+    base = torch.randn(n + 8, device="cuda")
+    src_base = torch.randn(n + 8, device="cuda")
+    for off_d, off_s in ((0, 0), (1, 1), (4, 2), (3, 0)):
+        d, s = base[off_d:off_d + n].clone(), src_base[off_s:off_s + n]
+        d_view = base.clone()[off_d:off_d + n]
+        d_view.copy_(d)
+        want = d.clone()
+        ref.merge_pair(want, s, *w)
+        ops.merge_pair(d_view, s, *w)
+        torch.testing.assert_close(d_view, want, rtol=1e-6, atol=1e-6)
+    if n > 8:   # ranged merge (MF item factors)
+        d = base[:n].clone(); want = d.clone()
+        ref.merge_pair(want, src_base[:n], .3, .7, 3, n - 2)
+        ops.merge_pair(d, src_base[:n], .3, .7, 3, n - 2)
+        torch.testing.assert_close(d, want, rtol=1e-6, atol=1e-6)
+
+
+def test_self_merge_and_kway():
+    ops, ref = _ops()
+    n = 79510 + 2
+    d = torch.randn(n, device="cuda"); want = d.clone()
+    ops.merge_pair(d, d.clone(), .5, .5)
+    torch.testing.assert_close(d, want)
+    for k in (1, 7, 20, 40):
+        srcs = [torch.randn(n, device="cuda") for _ in range(k)]
+        w = np.random.rand(k + 1); w /= w.sum()
+        a = torch.randn(n, device="cuda"); b = a.clone()
+        ops.merge_kway(a, srcs, w.tolist()); ref.merge_kway(b, srcs, w.tolist())
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_segment_and_indexed_merges():
+    ops, ref = _ops()
+    from gossipy_b200.model.nn import TorchMLP
+    from gossipy_b200.model.sampling import TorchModelPartition
+    part = TorchModelPartition(TorchMLP(784, 10, (100,)), 4)
+    n = 79520
+    for pid in range(4):
+        seg = part.segments(pid)
+        a = torch.randn(n, device="cuda"); b = a.clone(); s = torch.randn(n, device="cuda")
+        ops.merge_segments(a, s, seg.cuda(), .4, .6); ref.merge_segments(b, s, seg, .4, .6)
+        torch.testing.assert_close(a, b)
+        changed = (a != b.new_tensor(0)).sum()   # touches exactly the partition
+        idx = part.flat_index(pid).cuda()
+        mask = torch.zeros(n, dtype=torch.bool, device="cuda"); mask[idx] = True
+        untouched = torch.randn(n, device="cuda"); u2 = untouched.clone()
+        ops.merge_segments(untouched, s, seg.cuda(), .4, .6)
+        assert torch.equal(untouched[~mask], u2[~mask]) and not torch.equal(untouched[mask], u2[mask])
+    idx = torch.randint(0, n, (30000,), device="cuda")      # with duplicates
+    a = torch.randn(n, device="cuda"); b = a.clone(); s = torch.randn(n, device="cuda")
+    ops.merge_indexed(a, s, idx, .5, .5); ref.merge_indexed(b, s, idx, .5, .5)
+    torch.testing.assert_close(a, b)
+
+
+def test_flat_optimizers():
+    ops, ref = _ops()
+    n = 5000
+    for kw in (dict(momentum=0.), dict(momentum=.9, nesterov=True), dict(momentum=.5, dampening=.1)):
+        p = torch.randn(n + 24, device="cuda"); g = torch.randn(n + 24, device="cuda")
+        q = p.clone(); buf = torch.zeros_like(p); buf2 = buf.clone()
+        sc = torch.rand(n + 24, device="cuda")
+        for step in range(3):
+            first = step == 0
+            ops.sgd_step(p, g, n, .1, .01, kw.get("momentum", 0.), buf if kw.get("momentum") else None,
+                         kw.get("dampening", 0.), kw.get("nesterov", False), first, sc)
+            ref.sgd_step(q, g, n, .1, .01, kw.get("momentum", 0.), buf2 if kw.get("momentum") else None,
+                         kw.get("dampening", 0.), kw.get("nesterov", False), first, sc)
+        torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6)
+    for dec in (False, True):
+        p = torch.randn(n, device="cuda"); q = p.clone(); g = torch.randn(n, device="cuda")
+        m, v = torch.zeros_like(p), torch.zeros_like(p); m2, v2 = m.clone(), v.clone()
+        for step in (1, 2, 3):
+            ops.adam_step(p, g, n, m, v, step, .01, .9, .999, 1e-8, .01, dec)
+            ref.adam_step(q, g, n, m2, v2, step, .01, .9, .999, 1e-8, .01, dec)
+        torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-6)
+
+
+def _mlp_problem(n, d_in, d_h, d_out, seed=0):
+    gen = torch.Generator().manual_seed(seed)
+    X = torch.randn(n, d_in, generator=gen)
+    y = (X @ torch.randn(d_in, d_out, generator=gen)).argmax(1)
+    P = d_h * d_in + d_h + d_out * d_h + d_out
+    row = torch.zeros((P + 31) // 32 * 32)
+    row[:P] = torch.randn(P, generator=gen) * (1.0 / d_in ** .5)
+    return X.cuda(), y.cuda(), row.cuda()
+
+
+@pytest.mark.parametrize("dims,n,bs,ep,wd", [((784, 100, 10), 500, 32, 1, 0.),      # flagship shape, partial last batch
+                                             ((784, 100, 10), 70, 32, 2, .01),
+                                             ((64, 16, 4), 200, 16, 1, .001),
+                                             ((20, 7, 3), 90, 8, 3, 0.),
+                                             ((512, 128, 16), 128, 64, 1, 0.),
+                                             ((784, 100, 10), 300, 32, 0, 0.)])     # local_epochs=0: one batch
+def test_mlp1_train_cluster_matches_oracle(dims, n, bs, ep, wd):
+    ops, ref = _ops()
+    X, y, row = _mlp_problem(n, *dims)
+    want = row.clone()
+    s1 = ref.mlp1_train(want, X, y, dims, bs, ep, .1, wd, 0xABCDEF)
+    s2 = ops.mlp1_train(row, X, y, dims, bs, ep, .1, wd, 0xABCDEF, impl="cluster")
+    assert s1 == s2
+    torch.testing.assert_close(row, want, rtol=2e-3, atol=2e-4)
+    assert not torch.equal(row, _mlp_problem(n, *dims)[2])
+
+
+def test_mlp1_train_partition_scaled_matches_oracle():
+    ops, ref = _ops()
+    from gossipy_b200.model.nn import TorchMLP
+    from gossipy_b200.model.sampling import TorchModelPartition
+    dims = (784, 100, 10)
+    X, y, row = _mlp_problem(200, *dims)
+    part = TorchModelPartition(TorchMLP(*dims[::2], (dims[1],)), 4)
+    pid = part.part_id.cuda(); ages = torch.tensor([3, 0, 7, 1], device="cuda")
+    want = row.clone()
+    ref.mlp1_train(want, X, y, dims, 32, 1, 1., .001, 99, (pid, ages))
+    ops.mlp1_train(row, X, y, dims, 32, 1, 1., .001, 99, (pid, ages), impl="cluster")
+    torch.testing.assert_close(row, want, rtol=2e-3, atol=2e-4)
+
+
+def test_mlp1_eval_confusion_matrix():
+    ops, ref = _ops()
+    dims = (784, 100, 10)
+    X, y, row = _mlp_problem(1000, *dims)
+    cm = ops.mlp1_eval(row, X, y, dims, 10)
+    pred = ref.mlp1_logits(row, X, dims).argmax(1)
+    want = ref.confusion_matrix(y, pred, 10)
+    assert int((cm.long() - want).abs().sum()) <= 4     # fp32 summation-order ties only
+    assert int(cm.sum()) == 1000
+
+
+def test_logreg_train_and_scores():
+    ops, ref = _ops()
+    gen = torch.Generator().manual_seed(0)
+    X = torch.randn(300, 57, generator=gen).cuda()
+    y = (X[:, 0] > 0).long()
+    row = torch.zeros(128, device="cuda"); row[:116] = torch.randn(116, generator=gen).cuda() * .1
+    for bs, ep in ((32, 2), (0, 1), (100, 1)):
+        a, b = row.clone(), row.clone()
+        assert ops.logreg_train(a, X, y, (57, 2), bs, ep, 1., .001, 5) == \
+            ref.logreg_train(b, X, y, (57, 2), bs, ep, 1., .001, 5)
+        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(ops.logreg_scores(row, X, (57, 2)), ref.logreg_scores(row, X, (57, 2)),
+                               rtol=1e-4, atol=1e-5)
+
+
+def test_sequential_learners_kmeans_mf():
+    ops, ref = _ops()
+    gen = torch.Generator().manual_seed(0)
+    X = torch.randn(64, 57, generator=gen); y = torch.sign(X @ torch.randn(57, generator=gen))
+    for kind in ("adaline", "pegasos"):
+        w = torch.zeros(57); wc = w.cuda()
+        if kind == "adaline":
+            ref.adaline_update(w, X, y, .01); ops.adaline_update(wc, X.cuda(), y.cuda(), .01)
+        else:
+            t1 = ref.pegasos_update(w, X, y, .01, 5); t2 = ops.pegasos_update(wc, X.cuda(), y.cuda(), .01, 5)
+            assert t1 == t2 == 69
+        torch.testing.assert_close(wc.cpu(), w, rtol=1e-3, atol=1e-4)
+    C = torch.rand(3, 57, generator=gen); Cc = C.cuda()
+    ref.kmeans_update(C, X, .2); ops.kmeans_update(Cc, X.cuda(), .2)
+    torch.testing.assert_close(Cc.cpu(), C, rtol=1e-5, atol=1e-6)
+    assert torch.equal(ops.kmeans_assign(Cc, X.cuda()).cpu(), ref.kmeans_assign(C, X))
+    k, m = 5, 40
+    Xu, b, Y, c = torch.rand(k), torch.tensor([.5]), torch.rand(m, k), torch.full((m,), .5)
+    ratings = torch.stack([torch.randint(0, m, (30,)).float(), torch.randint(1, 6, (30,)).float()], 1)
+    dev = [t.clone().cuda() for t in (Xu, b, Y, c)]
+    ref.mf_update(Xu, b, Y, c, ratings, .1, .01); ops.mf_update(*dev, ratings.cuda(), .1, .01)
+    for got, want in zip(dev, (Xu, b, Y, c)):
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+
+
+def test_keyed_permutation_device_matches_host():
+    """The fused kernels must visit samples in the oracle's order: train with batch 1, lr on a
+    one-hot problem so that the order is observable."""
+    ops, ref = _ops()
+    dims = (8, 4, 2)
+    X, y, row = _mlp_problem(37, *dims, seed=3)
+    a, b = row.clone(), row.clone()
+    ops.mlp1_train(a, X, y, dims, 1, 2, .3, 0., 777, impl="cluster")
+    ref.mlp1_train(b, X, y, dims, 1, 2, .3, 0., 777)
+    torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
+
+
+def test_handlers_and_simulation_on_gpu_match_cpu_curve():
+    import gossipy_b200 as g
+    from gossipy_b200 import ops
+    from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import TorchModelHandler
+    from gossipy_b200.model.nn import TorchMLP
+    from gossipy_b200.node import GossipNode
+    from gossipy_b200.simul import GossipSimulator, SimulationReport
+
+    def run(device):
+        g.GlobalSettings().set_device(device)
+        g.set_seed(3)
+        (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(1600, 400)
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=8, eval_on_user=False)
+        proto = TorchModelHandler(TorchMLP(784, 10, (100,)), torch.optim.SGD, {"lr": .1},
+                                  torch.nn.CrossEntropyLoss(), batch_size=32)
+        nodes = GossipNode.generate(disp, StaticP2PNetwork(8), proto, 20, True)
+        sim = GossipSimulator(nodes, disp, 20, AntiEntropyProtocol.PUSH_PULL)
+        sim.progress = False
+        rep = SimulationReport(); sim.add_receiver(rep)
+        sim.init_nodes(seed=42); sim.start(3)
+        return [e["accuracy"] for _, e in rep.get_evaluation(False)], rep
+    before = ops.launch_count
+    gpu, rep_g = run("cuda:0")
+    assert ops.launch_count > before
+    cpu, rep_c = run("cpu")
+    assert rep_g._sent_messages == rep_c._sent_messages and rep_g._total_size == rep_c._total_size
+    assert gpu == pytest.approx(cpu, abs=.02)
+    assert gpu[-1] > gpu[0] - .02
