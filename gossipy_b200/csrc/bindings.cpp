@@ -23,6 +23,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgd_step", &gb::sgd_step);
     m.def("adam_step", &gb::adam_step);
     m.def("mlp1_train", &gb::mlp1_train);
+    m.def("mlp1_train_tc_debug", &gb::mlp1_train_tc_debug);
     m.def("mlp1_eval", &gb::mlp1_eval);
     m.def("logreg_train", &gb::logreg_train);
     m.def("logreg_scores", &gb::logreg_scores);
@@ -30,6 +31,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kmeans_update", &gb::kmeans_update);
     m.def("kmeans_assign", &gb::kmeans_assign);
     m.def("mf_update", &gb::mf_update);
+    m.def("tc_probe", &gb::tc_probe);
     m.def("ipc_alloc", &gb::ipc_alloc);
     m.def("ipc_free", &gb::ipc_free);
     m.def("ipc_get_handle", &gb::ipc_get_handle);

@@ -15,6 +15,7 @@
 // The tcgen05 / TMEM implementation of the same op lives in mlp1_train_tc.cu.
 #include "common.cuh"
 #include "ops.h"
+#include "mlp1.h"
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 
@@ -27,13 +28,6 @@ constexpr int OUT_MAX = 16;
 constexpr int CMAX = 8;       // portable cluster size
 constexpr int MAX_PARTS = 16;
 
-struct TrainParams {
-    float* row; const float* X; const int64_t* y;
-    int n, IN, H, OUT, B, epochs;
-    float lr, wd; uint64_t key;
-    const int64_t* part_id; const int64_t* ages; int n_parts;
-    int Hs, C, nbuf;
-};
 
 template <int KPL, bool SCALED>
 __global__ void __launch_bounds__(NW * 32, 1) mlp1_train_cluster_kernel(const TrainParams p) {
@@ -333,7 +327,19 @@ static bool launch_cluster(const TrainParams& p, bool scaled, cudaStream_t strea
     return true;
 }
 
-bool mlp1_train_tc(const TrainParams& p, cudaStream_t stream);   // mlp1_train_tc.cu
+
+static thread_local float* g_debug_ptr = nullptr;
+
+at::Tensor mlp1_train_tc_debug(at::Tensor row, at::Tensor X, at::Tensor y,
+                               std::tuple<int64_t, int64_t, int64_t> dims, int64_t batch_size,
+                               int64_t local_epochs, double lr, double wd, int64_t key) {
+    // runs the tcgen05 kernel and returns relu(z1) [128, 32] of the FIRST step (tests / bring-up)
+    auto dbg = at::zeros({128, 32}, row.options());
+    g_debug_ptr = dbg.data_ptr<float>();
+    mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, wd, key, c10::nullopt, c10::nullopt, "tc");
+    g_debug_ptr = nullptr;
+    return dbg;
+}
 
 int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
                    int64_t batch_size, int64_t local_epochs, double lr, double wd, int64_t key,
@@ -351,6 +357,7 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
     p.epochs = (int)local_epochs;
     p.lr = (float)lr; p.wd = (float)wd; p.key = (uint64_t)key;
     p.row = row.data_ptr<float>(); p.X = X.data_ptr<float>(); p.y = y.data_ptr<int64_t>();
+    p.dbg = g_debug_ptr;
     const bool scaled = part_id.has_value() && ages.has_value();
     if (scaled) {
         TORCH_CHECK(part_id->is_cuda() && part_id->scalar_type() == at::kLong && ages->is_cuda() &&

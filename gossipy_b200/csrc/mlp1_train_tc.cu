@@ -1,0 +1,384 @@
+// Tensor-core (tcgen05 + TMEM) implementation of the fused MLP local update.
+//
+// Idea: the fp32 MASTER WEIGHTS of the first layer never leave Tensor Memory during a local epoch.
+//   * TMEM holds W1 as [lanes = hidden unit (128), columns = input feature]; a CTA pair splits the
+//     input features (each CTA owns FPC <= 400 columns; 784 -> 2 x 392 (+8 zero columns)).
+//   * forward   z1^T[hid, batch]  = W1 . X^T      : tcgen05.mma kind::tf32, A = W1 straight from TMEM
+//                                                   (TS mode), B = X tile in shared memory (K-major);
+//                                                   the fp32 master is the tf32 operand, no bf16 copy.
+//   * update    W1 += (-lr/s dz1)^T . X           : tcgen05.mma kind::tf32 accumulating INTO the master
+//                                                   weights: A = scaled dz1^T (smem, K-major), B = the SAME
+//                                                   X tile read MN-major.  SGD costs no epilogue at all.
+//   * weight decay is a lazy scalar: W_true = s * W_tmem, s *= (1 - lr*wd) per step.
+//   * the two CTAs exchange their partial z1 tiles through distributed shared memory (one cluster
+//     barrier per step); the small second layer (100 -> 10), softmax-CE and its backward run on the
+//     CUDA cores of both CTAs redundantly (bit-identical), so nothing else is communicated.
+//   * X tiles are cp.async'ed straight into the UMMA "core matrix" layout [8 rows x 16 B] (K-major
+//     operand of the forward MMA).  tcgen05 does not transpose 32-bit operands (an MN-major tf32 B
+//     descriptor is silently a no-op -- see benchmarks/probe_tc.py), so while the forward MMA runs the
+//     CTA transposes the tile shared->shared into X^T (features as rows), the K-major B operand of the
+//     update MMA; the next batch is prefetched into the X tile as soon as both are done with it.
+// Reference semantics: gossipy/model/handler.py:235-258.  Accuracy: tf32 products, fp32 accumulate.
+#include "tc_common.cuh"
+#include "mlp1.h"
+#include <cstdio>
+
+namespace gb {
+
+constexpr int TC_THREADS = 128;
+constexpr int TC_B = 32;          // mini-batch tile (N of the forward MMA, K of the update MMA)
+constexpr int TC_HP = 128;        // hidden units padded to the MMA M
+constexpr int TC_OUTP = 16;
+constexpr int TC_FPC_MAX = 400;   // feature columns per CTA (TMEM: 400 + 32 accumulator columns <= 512)
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_HS_STRIDE = 33;
+
+struct TcSmem {   // offsets in bytes inside dynamic shared memory (1024-aligned base)
+    static constexpr int x0 = 0;                                     // X   [4 row groups][100 chunks][8][16B]
+    static constexpr int x_bytes = TC_B * TC_FPC_MAX * 4;            // 51200
+    static constexpr int xt = x0 + x_bytes;                          // X^T [50 feat groups][8 chunks][8][16B]
+    static constexpr int a2 = xt + x_bytes;                          // [16 hid groups][8 chunks][8][16B]
+    static constexpr int a2_bytes = TC_HP * TC_B * 4;                // 16384
+    static constexpr int zpart = a2 + a2_bytes;                      // [2][128][32] peer partial z1
+    static constexpr int hs = zpart + 2 * TC_HP * TC_B * 4;          // [128][33]
+    static constexpr int w2 = hs + TC_HP * TC_HS_STRIDE * 4;         // [16][128]
+    static constexpr int z2 = w2 + TC_OUTP * TC_HP * 4;              // [32][16]
+    static constexpr int b1 = z2 + TC_B * TC_OUTP * 4;               // [128]
+    static constexpr int b2 = b1 + TC_HP * 4;                        // [16]
+    static constexpr int idx = b2 + TC_OUTP * 4;                     // [2][32] int
+    static constexpr int ys = idx + 2 * TC_B * 4;                    // [2][32] int
+    static constexpr int mbar = ys + 2 * TC_B * 4;                   // 3 x uint64
+    static constexpr int tslot = mbar + 32;                          // uint32 tmem base
+    static constexpr int total = tslot + 16;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+mlp1_train_tc_kernel(const TrainParams p, const int FPC /* real feature columns per CTA */) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = gb_cluster_ctarank(), peer = rank ^ 1u;
+    const int IN = p.IN, H = p.H, OUT = p.OUT, n = p.n;
+    const int f0 = (int)rank * FPC;                        // first feature column of this CTA
+    const int fcnt = max(0, min(FPC, IN - f0));            // real columns held here
+    const int FP = (FPC + 15) & ~15;                       // padded to the MMA N granularity
+    const int nchunk = FP >> 2;                            // 16-byte chunks per row
+
+    float* xs = reinterpret_cast<float*>(smem + TcSmem::x0);
+    float* xt = reinterpret_cast<float*>(smem + TcSmem::xt);
+    float* a2 = reinterpret_cast<float*>(smem + TcSmem::a2);
+    float* zpart = reinterpret_cast<float*>(smem + TcSmem::zpart);
+    float* hs = reinterpret_cast<float*>(smem + TcSmem::hs);
+    float* w2s = reinterpret_cast<float*>(smem + TcSmem::w2);
+    float* z2s = reinterpret_cast<float*>(smem + TcSmem::z2);
+    float* b1s = reinterpret_cast<float*>(smem + TcSmem::b1);
+    float* b2s = reinterpret_cast<float*>(smem + TcSmem::b2);
+    int* idxs = reinterpret_cast<int*>(smem + TcSmem::idx);
+    int* ysm = reinterpret_cast<int*>(smem + TcSmem::ys);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TcSmem::mbar);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + TcSmem::tslot);
+
+    const float* W1g = p.row;
+    float* b1g = p.row + (size_t)H * IN;
+    float* W2g = b1g + H;
+    float* b2g = W2g + (size_t)OUT * H;
+
+    // ---- one-time set-up -------------------------------------------------------------------------
+    if (warp == 0) tmem_alloc<TC_TMEM_COLS>(tslot);
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init(&mbar[2], 1); mbar_fence_init(); }
+    for (int i = tid; i < 2 * TC_B * TC_FPC_MAX; i += TC_THREADS) xs[i] = 0.f;   // X and X^T (contiguous)
+    for (int i = tid; i < TC_HP * TC_B; i += TC_THREADS) a2[i] = 0.f;
+    for (int i = tid; i < TC_OUTP * TC_HP; i += TC_THREADS) {
+        const int o = i / TC_HP, j = i % TC_HP;
+        w2s[i] = (o < OUT && j < H) ? W2g[(size_t)o * H + j] : 0.f;
+    }
+    b1s[tid] = (tid < H) ? b1g[tid] : 0.f;
+    if (tid < TC_OUTP) b2s[tid] = (tid < OUT) ? b2g[tid] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32-lane quarter
+    const uint32_t t_w1 = 0, t_d1 = TC_FPC_MAX;                    // column offsets
+
+    // master weights -> TMEM : thread `tid` owns hidden unit `tid`
+    for (int c0 = 0; c0 < TC_FPC_MAX; c0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int c = c0 + i;
+            v[i] = (tid < H && c < fcnt) ? W1g[(size_t)tid * IN + f0 + c] : 0.f;
+        }
+        tmem_st16(tlane + t_w1 + c0, v);
+    }
+    tmem_st_wait();
+
+    const int B = p.B;                                   // <= TC_B
+    const int spe = (n + B - 1) / B;
+    const int total_steps = p.epochs > 0 ? p.epochs * spe : 1;
+    const float decay = 1.f - p.lr * p.wd;
+    float sscale = 1.f;                                  // W_true = sscale * W_tmem
+
+    auto stage_indices = [&](int s, int buf) {           // threads 0..31: sample ids + labels of step s
+        if (tid < TC_B) {
+            const int e = p.epochs > 0 ? s / spe : 0;
+            const int pos = p.epochs > 0 ? (s % spe) * B : 0;
+            const int bcur = min(B, n - pos);
+            int id = 0, yy = 0;
+            if (tid < bcur) {
+                GbPerm perm; perm.init((uint32_t)n, gb_mix64(p.key ^ (uint64_t)e));
+                id = (int)perm((uint32_t)(pos + tid));
+                yy = (int)p.y[id];
+            }
+            idxs[buf * TC_B + tid] = id;
+            ysm[buf * TC_B + tid] = yy;
+        }
+    };
+    auto stage_loads = [&](int s, int buf) {             // all threads: cp.async my feature half
+        const int pos = p.epochs > 0 ? (s % spe) * B : 0;
+        const int bcur = min(B, n - pos);
+        float* xb = xs;
+        const int r8 = lane & 7, cc = lane >> 3;
+        const int nreal = fcnt >> 2;                     // real 16-B chunks per row (fcnt % 4 == 0)
+        for (int g = 0; g < TC_B / 8; ++g) {
+            const int b = g * 8 + r8;
+            const float* src = p.X + (size_t)idxs[buf * TC_B + b] * IN + f0;
+            for (int q = warp; q * 4 < nreal; q += TC_THREADS / 32) {
+                const int c = q * 4 + cc;
+                if (c < nreal && b < bcur)
+                    gb_cp_async16(xb + ((size_t)(g * nchunk + c) * 8 + r8) * 4, src + 4 * c);
+            }
+        }
+        gb_cp_async_commit();
+    };
+
+    stage_indices(0, 0);
+    __syncthreads();
+    stage_loads(0, 0);
+    gb_cluster_sync();            // peer is running (its smem may be written from here on)
+
+    const uint32_t idesc_fwd = make_idesc(kFmtTF32, kFmtTF32, 128, TC_B, false, false);
+    const uint32_t x_sbo = (uint32_t)nchunk * 128u;      // distance between 8-row groups of the X tile
+
+    for (int s = 0; s < total_steps; ++s) {
+        const int buf = s & 1, par = s & 1;
+        const int pos = p.epochs > 0 ? (s % spe) * B : 0;
+        const int bcur = min(B, n - pos);
+        const float* xb = xs;
+
+        // (A) this step's X tile has landed -> visible to the tensor core (async proxy)
+        gb_cp_async_wait<0>();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        // (B) forward MMA: D1[128 x 32] = W1(TMEM) . X^T
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t xaddr = smem_u32(xb);
+            for (int k = 0; k < FP / 8; ++k) {
+                const uint64_t bdesc = make_sdesc(xaddr + (uint32_t)k * 256u, 128u, x_sbo);
+                mma_tf32_ts(tmem + t_d1, tmem + t_w1 + (uint32_t)k * 8u, bdesc, idesc_fwd, k > 0);
+            }
+            mma_commit(&mbar[0]);
+        }
+        if (s + 1 < total_steps) stage_indices(s + 1, buf ^ 1);
+
+        // (B2) while the tensor core runs: X -> X^T (shared to shared), the K-major operand of the
+        //      update MMA.  One warp iteration = one 8-feature x 4-sample core matrix (128 B, conflict free).
+        if (s > 0) mbar_wait(&mbar[1], (uint32_t)((s - 1) & 1));     // update(s-1) no longer reads X^T
+        {
+            const int fr = lane >> 2, bq = lane & 3;
+            for (int cm = warp; cm < (FP / 8) * (TC_B / 4); cm += TC_THREADS / 32) {
+                const int fg = cm >> 3, bc = cm & 7;                 // feature group, 4-sample chunk
+                const int f = fg * 8 + fr, b = bc * 4 + bq;
+                const float v = xb[((size_t)((b >> 3) * nchunk + (f >> 2)) * 8 + (b & 7)) * 4 + (f & 3)];
+                xt[(size_t)cm * 32 + lane] = v;                       // ((fg*8 + bc)*8 + fr)*4 + bq
+            }
+        }
+        fence_proxy_async();
+
+        // (C) wait for the accumulator, read my hidden row, exchange partial sums with the peer CTA
+        mbar_wait(&mbar[0], (uint32_t)(s & 1));
+        tc_fence_after();
+        float acc[TC_B];
+        tmem_ld32(tlane + t_d1, acc);
+        tmem_ld_wait();
+        {
+            float* mine = zpart + ((size_t)par * TC_HP + tid) * TC_B;
+            const uint32_t remote = gb_map_shared(mine, peer);
+#pragma unroll
+            for (int q = 0; q < TC_B / 4; ++q)
+                gb_st_cluster4(remote + 16u * q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+        }
+        gb_cluster_sync();
+        float h[TC_B];
+        {
+            const float4* other = reinterpret_cast<const float4*>(zpart + ((size_t)par * TC_HP + tid) * TC_B);
+            const float bj = b1s[tid];
+#pragma unroll
+            for (int q = 0; q < TC_B / 4; ++q) {
+                const float4 o = other[q];
+                h[4 * q] = acc[4 * q] + o.x; h[4 * q + 1] = acc[4 * q + 1] + o.y;
+                h[4 * q + 2] = acc[4 * q + 2] + o.z; h[4 * q + 3] = acc[4 * q + 3] + o.w;
+            }
+#pragma unroll
+            for (int b = 0; b < TC_B; ++b) {
+                const float z = fmaf(sscale, h[b], bj);
+                h[b] = (tid < H) ? fmaxf(z, 0.f) : 0.f;
+                hs[tid * TC_HS_STRIDE + b] = h[b];
+            }
+        }
+        if (p.dbg != nullptr && s == 0 && rank == 0) {
+#pragma unroll
+            for (int b = 0; b < TC_B; ++b) p.dbg[tid * TC_B + b] = h[b];
+        }
+        __syncthreads();
+        if (s + 1 < total_steps) stage_loads(s + 1, buf ^ 1);   // prefetch (buffer's last MMA reader is done)
+
+        // (D) layer 2 forward: thread (b, og) -> logits o = og, og+4, og+8(,+12)
+        {
+            const int b = tid & 31, og = tid >> 5;
+            float zacc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < H; j += 4) {
+                float hv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hv[i] = hs[(j + i) * TC_HS_STRIDE + b];   // rows >= H are zero
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int o = og + 4 * q;
+                    if (o < OUT) {
+                        const float4 wv = *reinterpret_cast<const float4*>(w2s + o * TC_HP + j);
+                        zacc[q] = fmaf(hv[0], wv.x, fmaf(hv[1], wv.y, fmaf(hv[2], wv.z, fmaf(hv[3], wv.w, zacc[q]))));
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int o = og + 4 * q; if (o < OUT) z2s[b * TC_OUTP + o] = zacc[q] + b2s[o]; }
+        }
+        __syncthreads();
+        // (E) softmax cross-entropy gradient, one thread per sample
+        if (tid < TC_B) {
+            float* zr = z2s + tid * TC_OUTP;
+            if (tid < bcur) {
+                float m = zr[0];
+                for (int o = 1; o < OUT; ++o) m = fmaxf(m, zr[o]);
+                float sum = 0.f;
+                for (int o = 0; o < OUT; ++o) { const float ex = __expf(zr[o] - m); zr[o] = ex; sum += ex; }
+                const float inv = 1.f / sum, invb = 1.f / (float)bcur;
+                const int yy = ysm[buf * TC_B + tid];
+                for (int o = 0; o < OUT; ++o) zr[o] = (zr[o] * inv - (o == yy ? 1.f : 0.f)) * invb;
+            } else {
+                for (int o = 0; o < OUT; ++o) zr[o] = 0.f;
+            }
+            for (int o = OUT; o < TC_OUTP; ++o) zr[o] = 0.f;
+        }
+        __syncthreads();
+        // (F) backward through layer 2 (thread = hidden unit): dh, dW2 column, db1; build the A operand
+        const float s_next = sscale * decay;
+        float gw2[TC_OUTP];
+        {
+            float w2c[TC_OUTP];
+#pragma unroll
+            for (int o = 0; o < TC_OUTP; ++o) { w2c[o] = w2s[o * TC_HP + tid]; gw2[o] = 0.f; }
+            const float ascale = -p.lr / s_next;
+            float gb1 = 0.f;
+            float outv[TC_B];
+#pragma unroll
+            for (int b = 0; b < TC_B; ++b) {
+                const float4* dzr = reinterpret_cast<const float4*>(z2s + b * TC_OUTP);
+                float dz[TC_OUTP];
+#pragma unroll
+                for (int q = 0; q < TC_OUTP / 4; ++q) { const float4 t = dzr[q]; dz[4 * q] = t.x; dz[4 * q + 1] = t.y; dz[4 * q + 2] = t.z; dz[4 * q + 3] = t.w; }
+                float dh = 0.f;
+#pragma unroll
+                for (int o = 0; o < TC_OUTP; ++o) { dh = fmaf(dz[o], w2c[o], dh); gw2[o] = fmaf(dz[o], h[b], gw2[o]); }
+                const float dz1 = (h[b] > 0.f) ? dh : 0.f;
+                gb1 += dz1;
+                outv[b] = ascale * dz1;
+            }
+            // A2[hid = tid][batch] in K-major core-matrix layout: ((tid/8)*8 + b/4)*128 + (tid%8)*16 + (b%4)*4
+            float* arow = a2 + (size_t)(tid >> 3) * (8 * 32) + (tid & 7) * 4;
+#pragma unroll
+            for (int q = 0; q < TC_B / 4; ++q)
+                *reinterpret_cast<float4*>(arow + q * 32) = make_float4(outv[4 * q], outv[4 * q + 1], outv[4 * q + 2], outv[4 * q + 3]);
+            b1s[tid] = fmaf(-p.lr, gb1, b1s[tid] * decay);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // (G) update MMA: W1[128 x FP] += A2[128 x 32] . X^T-tile  (both operands K-major, K = batch)
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t taddr = smem_u32(xt), aaddr = smem_u32(a2);
+            for (int n0 = 0; n0 < FP; n0 += 256) {
+                const int nn = min(256, FP - n0);
+                const uint32_t idesc_upd = make_idesc(kFmtTF32, kFmtTF32, 128, nn, false, false);
+                for (int k = 0; k < TC_B / 8; ++k) {
+                    const uint64_t adesc = make_sdesc(aaddr + (uint32_t)k * 256u, 128u, 1024u);
+                    const uint64_t bdesc = make_sdesc(taddr + (uint32_t)(n0 >> 3) * 1024u + (uint32_t)k * 256u,
+                                                      128u, 1024u);
+                    mma_tf32_ss(tmem + t_w1 + (uint32_t)n0, adesc, bdesc, idesc_upd, true);
+                }
+            }
+            mma_commit(&mbar[1]);
+        }
+        // (H) second-layer parameters (after their last readers of this step)
+#pragma unroll
+        for (int o = 0; o < TC_OUTP; ++o)
+            if (o < OUT && tid < H) w2s[o * TC_HP + tid] = fmaf(-p.lr, gw2[o], w2s[o * TC_HP + tid] * decay);
+        if (tid < OUT) {
+            float g = 0.f;
+            for (int b = 0; b < TC_B; ++b) g += z2s[b * TC_OUTP + tid];
+            b2s[tid] = fmaf(-p.lr, g, b2s[tid] * decay);
+        }
+        sscale = s_next;
+    }
+
+    // ---- drain the tensor pipe and write everything back ------------------------------------------------
+    if (tid == 0) mma_commit(&mbar[2]);
+    mbar_wait(&mbar[2], 0u);
+    tc_fence_after();
+    __syncthreads();
+    for (int c0 = 0; c0 < TC_FPC_MAX; c0 += 16) {
+        float v[16];
+        tmem_ld16(tlane + t_w1 + c0, v);
+        tmem_ld_wait();
+        if (tid < H) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int c = c0 + i;
+                if (c < fcnt) p.row[(size_t)tid * IN + f0 + c] = sscale * v[i];
+            }
+        }
+    }
+    if (rank == 0) {
+        for (int i = tid; i < OUT * H; i += TC_THREADS) { const int o = i / H, j = i % H; W2g[i] = w2s[o * TC_HP + j]; }
+        if (tid < H) b1g[tid] = b1s[tid];
+        if (tid < OUT) b2g[tid] = b2s[tid];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TC_TMEM_COLS>(tmem);
+    gb_cluster_sync();
+}
+
+bool mlp1_train_tc(const TrainParams& p, cudaStream_t stream) {
+    // shape envelope of this kernel; anything else falls back to the cluster (CUDA-core) kernel
+    if (p.H > TC_HP || p.H % 4 != 0 || p.OUT > TC_OUTP || p.B > TC_B || p.IN % 8 != 0) return false;
+    const int FPC = ((p.IN / 2) + 3) & ~3;               // feature columns per CTA, multiple of 4
+    if (FPC > TC_FPC_MAX - 0 || ((FPC + 15) & ~15) > TC_FPC_MAX) return false;
+    if (p.IN - FPC > FPC || p.IN - FPC <= 0) return false;
+    const int spe = (p.n + p.B - 1) / p.B;
+    const double steps = p.epochs > 0 ? (double)p.epochs * spe : 1.0;
+    if (steps * (double)p.lr * (double)p.wd > 20.0) return false;   // lazy decay scale would underflow
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mlp1_train_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TcSmem::total + 1024) != cudaSuccess) return false;
+        configured = true;
+    }
+    mlp1_train_tc_kernel<<<2, TC_THREADS, TcSmem::total + 1024, stream>>>(p, FPC);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+}  // namespace gb

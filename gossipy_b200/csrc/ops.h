@@ -23,6 +23,9 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
                    int64_t batch_size, int64_t local_epochs, double lr, double wd, int64_t key,
                    c10::optional<at::Tensor> part_id, c10::optional<at::Tensor> ages,
                    std::string impl);
+at::Tensor mlp1_train_tc_debug(at::Tensor row, at::Tensor X, at::Tensor y,
+                               std::tuple<int64_t, int64_t, int64_t> dims, int64_t batch_size,
+                               int64_t local_epochs, double lr, double wd, int64_t key);
 at::Tensor mlp1_eval(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
                      int64_t n_classes, c10::optional<at::Tensor> X_lp);
 
@@ -35,5 +38,7 @@ void linear_seq_update(at::Tensor w, at::Tensor X, at::Tensor y, int64_t kind, d
 void kmeans_update(at::Tensor C, at::Tensor X, double alpha);
 at::Tensor kmeans_assign(at::Tensor C, at::Tensor X);
 void mf_update(at::Tensor X, at::Tensor b, at::Tensor Y, at::Tensor c, at::Tensor ratings, double reg, double lr);
+
+at::Tensor tc_probe(at::Tensor A, at::Tensor Bm, int64_t variant);
 
 }  // namespace gb

@@ -1,0 +1,84 @@
+// Bring-up probe for tcgen05 descriptors (tests only): D[128 x N] = A[128 x K] . B[K x N] in tf32,
+// A from shared memory (K-major), B from shared memory in the "X tile" core-matrix layout read either
+// MN-major (variant bit1 = 0) or K-major from an explicitly transposed tile (bit1 = 1).
+#include "tc_common.cuh"
+#include "ops.h"
+#include <ATen/cuda/CUDAContext.h>
+
+namespace gb {
+
+__global__ void __launch_bounds__(128, 1)
+tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ D,
+                int K, int N, int variant) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* a_s = reinterpret_cast<float*>(smem);                 // [16 groups][K/4 chunks][8][4]
+    float* b_s = a_s + 128 * K;                                  // MN layout: [K/8 groups][N/4 chunks][8][4]
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc<512>(&tslot);
+    if (tid == 0) { mbar_init(&mbar, 1); mbar_fence_init(); }
+    const int kch = K / 4, nch = N / 4;
+    for (int i = tid; i < 128 * K; i += 128) {
+        const int m = i / K, k = i % K;
+        a_s[((m / 8) * kch + k / 4) * 32 + (m % 8) * 4 + (k % 4)] = A[i];
+    }
+    const bool b_kmajor = (variant & 2) != 0 || (variant & 8) != 0;
+    const bool sw_mn = (variant & 4) != 0, sw_k = (variant & 8) != 0;
+    for (int i = tid; i < K * N; i += 128) {
+        const int k = i / N, n = i % N;
+        if (sw_mn)         // MN-major SW128: atoms [n/32][k/8], row = k%8, chunk (n%32)/4 ^ row
+            b_s[((n / 32) * (K / 8) + k / 8) * 256 + (k % 8) * 32 + ((((n % 32) / 4) ^ (k % 8)) * 4) + (n % 4)] = Bm[i];
+        else if (sw_k)     // K-major SW128: atoms [k/32][n/8], row = n%8, chunk (k%32)/4 ^ row
+            b_s[((k / 32) * (N / 8) + n / 8) * 256 + (n % 8) * 32 + ((((k % 32) / 4) ^ (n % 8)) * 4) + (k % 4)] = Bm[i];
+        else if (!b_kmajor) b_s[((k / 8) * nch + n / 4) * 32 + (k % 8) * 4 + (n % 4)] = Bm[i];     // X-tile layout
+        else           b_s[((n / 8) * kch + k / 4) * 32 + (n % 8) * 4 + (k % 4)] = Bm[i];     // rows = n
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tslot;
+    if (tid == 0) {
+        const uint32_t aaddr = smem_u32(a_s), baddr = smem_u32(b_s);
+        const uint32_t idesc = make_idesc(kFmtTF32, kFmtTF32, 128, N, false, !b_kmajor);
+        for (int k = 0; k < K / 8; ++k) {
+            const uint64_t adesc = make_sdesc(aaddr + (uint32_t)k * 256u, 128u, (uint32_t)kch * 128u);
+            uint64_t bdesc;
+            if (sw_mn) bdesc = make_sdesc_sw128(baddr + (uint32_t)k * 1024u, (uint32_t)(K / 8) * 1024u, 1024u);
+            else if (sw_k) bdesc = make_sdesc_sw128(baddr + (uint32_t)(k / 4) * (uint32_t)(N / 8) * 1024u + (uint32_t)(k % 4) * 32u, 16u, 1024u);
+            else if (b_kmajor) bdesc = make_sdesc(baddr + (uint32_t)k * 256u, 128u, (uint32_t)kch * 128u);
+            else if (variant & 1) bdesc = make_sdesc(baddr + (uint32_t)k * nch * 128u, 128u, (uint32_t)nch * 128u);
+            else bdesc = make_sdesc(baddr + (uint32_t)k * nch * 128u, (uint32_t)nch * 128u, 128u);
+            mma_tf32_ss(tmem, adesc, bdesc, idesc, k > 0);
+        }
+        mma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    tc_fence_after();
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tlane + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) D[(size_t)tid * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+at::Tensor tc_probe(at::Tensor A, at::Tensor Bm, int64_t variant) {
+    const int K = (int)A.size(1), N = (int)Bm.size(1);
+    TORCH_CHECK(A.size(0) == 128 && Bm.size(0) == K && K % 8 == 0 && N % 16 == 0 && N <= 256);
+    TORCH_CHECK(!(variant & 4) || N % 32 == 0); TORCH_CHECK(!(variant & 8) || K % 32 == 0);
+    auto D = at::zeros({128, N}, A.options());
+    const size_t smem = (size_t)(128 * K + K * N) * 4 + 1024;
+    C10_CUDA_CHECK(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_probe_kernel<<<1, 128, smem, at::cuda::getCurrentCUDAStream()>>>(
+        A.data_ptr<float>(), Bm.data_ptr<float>(), D.data_ptr<float>(), K, N, (int)variant);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return D;
+}
+
+}  // namespace gb

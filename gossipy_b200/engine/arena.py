@@ -20,11 +20,17 @@ import torch
 
 
 class Row:
-    """One parameter vector (a 1-D fp32 tensor view) plus its cross-stream dependencies."""
+    """One parameter vector (a 1-D fp32 tensor view) plus its cross-stream / cross-rank dependencies.
 
-    __slots__ = ("arena", "index", "tensor", "ready", "consumed", "stream", "rank")
+    ``tensor`` is ``None`` for a row of another rank under the ``sendrecv`` transport and a
+    peer-mapped view (CUDA IPC) under ``p2p``.  ``gen`` / ``remote_reads`` are replicated
+    bookkeeping for the flag protocol (see :mod:`gossipy_b200.parallel.runtime`).
+    """
 
-    def __init__(self, arena: "RowArena", index: int, tensor: torch.Tensor) -> None:
+    __slots__ = ("arena", "index", "tensor", "ready", "consumed", "stream", "rank", "gen",
+                 "remote_reads", "flag_ready", "flag_done")
+
+    def __init__(self, arena: "RowArena", index: int, tensor: Optional[torch.Tensor]) -> None:
         self.arena = arena
         self.index = index
         self.tensor = tensor
@@ -32,20 +38,30 @@ class Row:
         self.consumed: List = []  # events: reads since the last write
         self.stream = None       # stream of the last writer
         self.rank = arena.rank
+        self.gen = 0             # number of (shared) writes so far
+        self.remote_reads = 0    # cumulative reads by other ranks
+        self.flag_ready = 0      # device address of the owner's `ready` flag (p2p transport)
+        self.flag_done = 0       # device address of the owner's `done` counter
 
     def release(self) -> None:
         self.arena.free(self)
 
 
 class RowArena:
-    """Pool of equally sized fp32 rows on one device, grown chunk-wise and reused FIFO."""
+    """Pool of equally sized fp32 rows on one device, grown chunk-wise and reused FIFO.
+
+    ``ghost=True`` mirrors the bookkeeping of another rank's arena without owning memory
+    (``sendrecv`` transport); every rank replays the same alloc/free sequence on every mirror, so
+    row indices agree everywhere without any communication.
+    """
 
     def __init__(self, device: torch.device, row_numel: int, chunk_rows: int = 16,
-                 rank: int = 0) -> None:
+                 rank: int = 0, ghost: bool = False) -> None:
         self.device = torch.device(device)
         self.row_numel = int(row_numel)
         self.chunk_rows = chunk_rows
         self.rank = rank
+        self.ghost = ghost
         self._chunks: List[torch.Tensor] = []
         self._free: List[Row] = []
         self._n_rows = 0
@@ -53,11 +69,12 @@ class RowArena:
         self.high_water = 0
 
     def _grow(self) -> None:
-        chunk = torch.zeros(self.chunk_rows, self.row_numel, dtype=torch.float32,
-                            device=self.device)
-        self._chunks.append(chunk)
+        chunk = None if self.ghost else torch.zeros(self.chunk_rows, self.row_numel,
+                                                    dtype=torch.float32, device=self.device)
+        if chunk is not None:
+            self._chunks.append(chunk)
         for i in range(self.chunk_rows):
-            self._free.append(Row(self, self._n_rows + i, chunk[i]))
+            self._free.append(Row(self, self._n_rows + i, None if chunk is None else chunk[i]))
         self._n_rows += self.chunk_rows
         self.chunk_rows = min(self.chunk_rows * 2, 1024)
 
@@ -79,21 +96,80 @@ class RowArena:
         return self._n_rows * self.row_numel * 4
 
 
+class SymmetricArenas:
+    """Identical IPC-shared arenas on every rank (``p2p`` transport).
+
+    Layout of each rank's allocation: ``capacity`` rows of ``row_numel`` floats followed by two
+    uint32 flags per row (``ready`` generation, ``done`` read counter).  Creation is collective.
+    """
+
+    def __init__(self, device: torch.device, row_numel: int) -> None:
+        import torch.distributed as dist
+        from ..ops.native import native
+        from ..parallel import runtime as prt
+        nat = native()
+        self.device = torch.device(device)
+        self.row_numel = int(row_numel)
+        row_bytes = self.row_numel * 4
+        self.capacity = int(max(16, min(512, (1 << 31) // row_bytes)))
+        self.flags_off = self.capacity * row_bytes
+        total = self.flags_off + self.capacity * 8
+        torch.cuda.set_device(self.device)
+        self.base = nat.ipc_alloc(total)
+        handles: List = [None] * prt.world()
+        dist.all_gather_object(handles, nat.ipc_get_handle(self.base))
+        self.bases = [self.base if r == prt.rank() else nat.ipc_open_handle(handles[r])
+                      for r in range(prt.world())]
+        dist.barrier()
+        self.mirrors: List[RowArena] = []
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        for r in range(prt.world()):
+            mirror = RowArena(self.device, row_numel, rank=r, ghost=True)
+            mirror._n_rows = self.capacity
+            for i in range(self.capacity):
+                t = nat.tensor_from_ptr(self.bases[r] + i * row_bytes, [self.row_numel], dev_index, False)
+                row = Row(mirror, i, t)
+                row.flag_ready = self.bases[r] + self.flags_off + 8 * i
+                row.flag_done = self.bases[r] + self.flags_off + 8 * i + 4
+                mirror._free.append(row)
+            mirror._grow = _no_growth  # type: ignore[assignment]
+            self.mirrors.append(mirror)
+
+
+def _no_growth() -> None:
+    raise RuntimeError("symmetric arena exhausted: too many models in flight for the p2p transport")
+
+
 _ARENAS: Dict[tuple, RowArena] = {}
+_SYMMETRIC: Dict[tuple, SymmetricArenas] = {}
 
 
-def arena_for(device: torch.device, row_numel: int) -> RowArena:
-    """The shared arena for rows of ``row_numel`` floats on ``device``."""
+def arena_for(device: torch.device, row_numel: int, rank: Optional[int] = None) -> RowArena:
+    """The arena (mirror) holding rows of ``row_numel`` floats that live on ``rank``."""
+    from ..parallel import runtime as prt
     device = torch.device(device)
-    key = (device.type, device.index, int(row_numel))
+    if rank is None or not prt.active():
+        rank = prt.rank() if prt.active() else 0
+    key = (device.type, device.index, int(row_numel), rank)
     arena = _ARENAS.get(key)
-    if arena is None:
-        arena = _ARENAS[key] = RowArena(device, row_numel)
+    if arena is not None:
+        return arena
+    if prt.active() and prt.transport() == "p2p" and device.type == "cuda":
+        skey = (device.index, int(row_numel))
+        sym = _SYMMETRIC.get(skey)
+        if sym is None:
+            sym = _SYMMETRIC[skey] = SymmetricArenas(device, row_numel)
+        for r, mirror in enumerate(sym.mirrors):
+            _ARENAS[(device.type, device.index, int(row_numel), r)] = mirror
+        return _ARENAS[key]
+    ghost = prt.active() and rank != prt.rank()
+    arena = _ARENAS[key] = RowArena(device, row_numel, rank=rank, ghost=ghost)
     return arena
 
 
 def reset_arenas() -> None:
     _ARENAS.clear()
+    _SYMMETRIC.clear()
     _STREAMS.clear()
 
 

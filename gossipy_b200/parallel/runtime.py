@@ -1,0 +1,135 @@
+"""One-process-per-GPU runtime.
+
+Execution model (world_size > 1): every rank runs the SAME cheap host-side simulation (identical
+seeds -> identical event schedule, ages, token balances, arena allocations) but executes the device
+work only of the gossip nodes it owns (block placement ``node -> rank``).  A model "sent" to a node
+on another GPU is never copied by the sender: its snapshot row stays in the sender's HBM arena and
+the receiver's fused merge kernel *pulls* it.
+
+Transports for a row that lives on another rank:
+
+``p2p``   (CUDA) every rank ``cudaMalloc``'s an identical ("symmetric") arena, exports it through CUDA
+          IPC (handles exchanged once with ``torch.distributed``) and maps all peers' arenas; a peer
+          row is then a device pointer and the merge kernel's loads travel over NVLink/NVSwitch.
+          Cross-GPU ordering uses per-row 32-bit flags inside the arenas: the producer's stream
+          publishes ``ready = generation`` (st.release.sys) after the snapshot kernel, the consumer's
+          stream spins on it (ld.acquire.sys) before the merge kernel and afterwards bumps the
+          producer's ``done`` counter so the row can be recycled -- no host synchronisation, no NCCL.
+``sendrecv`` (CPU/gloo plumbing, and the NCCL baseline on GPUs) the producer sends the row with
+          ``torch.distributed`` and the consumer merges from a staging buffer.
+
+Because the schedule is replicated, matching sends/receives, flag generations and arena row indices
+are derived independently and identically on every rank -- there is no control traffic at all.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from .. import GlobalSettings, LOG
+
+_state: Dict[str, Any] = {"rank": 0, "world": 1, "n_nodes": None, "transport": "none",
+                          "placement": None}
+
+
+def init(rank: Optional[int] = None, world: Optional[int] = None,
+         transport: Optional[str] = None) -> None:
+    """Activate multi-rank execution.  ``torch.distributed`` must already be initialised."""
+    import torch.distributed as dist
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    _state["rank"], _state["world"] = int(rank), int(world)
+    GlobalSettings().set_topology(int(rank), int(world))
+    if transport is None:
+        transport = os.environ.get("GOSSIPY_B200_TRANSPORT", "")
+    if not transport:
+        transport = "p2p" if GlobalSettings().is_cuda() else "sendrecv"
+    _state["transport"] = transport if world > 1 else "none"
+    if world > 1:
+        assert dist.is_initialized(), "initialise torch.distributed before parallel.runtime.init"
+
+
+def shutdown() -> None:
+    _state.update(rank=0, world=1, n_nodes=None, transport="none", placement=None)
+    GlobalSettings().set_topology(0, 1)
+
+
+def active() -> bool:
+    return _state["world"] > 1
+
+
+def rank() -> int:
+    return _state["rank"]
+
+
+def world() -> int:
+    return _state["world"]
+
+
+def transport() -> str:
+    return _state["transport"]
+
+
+def set_num_nodes(n: int, placement: Optional[List[int]] = None) -> None:
+    """Fix the node -> rank placement (block placement unless an explicit list is given)."""
+    _state["n_nodes"] = int(n)
+    _state["placement"] = list(placement) if placement is not None else None
+
+
+def rank_of(node_id: int) -> int:
+    """Rank that owns gossip node ``node_id`` (0 when single-process)."""
+    w = _state["world"]
+    if w == 1 or node_id is None or node_id < 0:
+        return 0 if w == 1 else (0 if node_id is None or node_id < 0 else 0)
+    pl = _state["placement"]
+    if pl is not None:
+        return pl[node_id]
+    n = _state["n_nodes"]
+    if not n:
+        return node_id % w
+    return min(w - 1, node_id * w // n)
+
+
+def is_mine(node_id: int) -> bool:
+    return _state["world"] == 1 or rank_of(node_id) == _state["rank"]
+
+
+# --------------------------------------------------------------------------------------
+# collectives on tiny host-visible results
+# --------------------------------------------------------------------------------------
+METRIC_KEYS = ("accuracy", "precision", "recall", "f1_score", "auc", "rmse", "nmi")
+
+
+def share_metrics(local: List[Optional[Dict[str, float]]]) -> List[Dict[str, float]]:
+    """``local[i]`` is the metric dict of evaluation ``i`` on the rank that computed it and ``None``
+    elsewhere; returns the complete list on every rank (one small all-reduce)."""
+    if not active():
+        return [d for d in local]  # type: ignore[misc]
+    import torch.distributed as dist
+    k = len(METRIC_KEYS)
+    buf = torch.zeros(len(local), 2 * k, dtype=torch.float64)
+    for i, d in enumerate(local):
+        if d is not None:
+            for j, name in enumerate(METRIC_KEYS):
+                if name in d:
+                    buf[i, j] = float(d[name])
+                    buf[i, k + j] = 1.0
+    dev = GlobalSettings().get_device()
+    if dist.get_backend() == "nccl":
+        buf = buf.to(dev)
+    dist.all_reduce(buf)
+    buf = buf.cpu()
+    out = []
+    for i in range(len(local)):
+        out.append({name: float(buf[i, j]) for j, name in enumerate(METRIC_KEYS) if buf[i, k + j] > 0})
+    return out
+
+
+def barrier() -> None:
+    if active():
+        import torch.distributed as dist
+        dist.barrier()

@@ -244,3 +244,44 @@ def test_handlers_and_simulation_on_gpu_match_cpu_curve():
     assert rep_g._sent_messages == rep_c._sent_messages and rep_g._total_size == rep_c._total_size
     assert gpu == pytest.approx(cpu, abs=.02)
     assert gpu[-1] > gpu[0] - .02
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 / TMEM training kernel (tf32 products, fp32 accumulation in tensor memory)
+# ---------------------------------------------------------------------------------------------
+def test_tc_forward_first_step_matches_oracle():
+    """Bring-up check of the TS-mode forward MMA (master weights read from TMEM) + DSMEM reduction."""
+    from gossipy_b200.engine import rng
+    from gossipy_b200.ops.native import native
+    ops, ref = _ops()
+    dims = (784, 100, 10)
+    X, y, row = _mlp_problem(64, *dims)
+    W1, b1, W2, b2 = ref.mlp1_unpack(row.clone(), dims)
+    idx = torch.from_numpy(ref.perm_indices(64, rng.mix64(0x77 ^ 0))).cuda()[:32]
+    want = torch.relu(X[idx] @ W1.t() + b1)                       # [32, 100]
+    got = native().mlp1_train_tc_debug(row.clone(), X, y, dims, 32, 1, 0.0, 0.0, 0x77)   # lr = 0
+    torch.testing.assert_close(got[:100, :].t(), want, rtol=2e-2, atol=2e-2)
+    assert float(got[100:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dims,n,bs,ep,wd,lr", [((784, 100, 10), 96, 32, 1, 0., .1),
+                                                ((784, 100, 10), 500, 32, 1, 0., .1),
+                                                ((784, 100, 10), 70, 32, 2, .01, .1),
+                                                ((64, 16, 4), 200, 16, 1, .001, .1),
+                                                ((512, 128, 16), 128, 32, 1, 0., .05),
+                                                ((784, 100, 10), 300, 32, 0, 0., .1)])
+def test_mlp1_train_tc_matches_oracle(dims, n, bs, ep, wd, lr):
+    ops, ref = _ops()
+    X, y, row = _mlp_problem(n, *dims)
+    want = row.clone()
+    s1 = ref.mlp1_train(want, X, y, dims, bs, ep, lr, wd, 0xABCDEF)
+    s2 = ops.mlp1_train(row, X, y, dims, bs, ep, lr, wd, 0xABCDEF, impl="tc")
+    assert s1 == s2
+    start = _mlp_problem(n, *dims)[2]
+    moved = (want - start).abs().max()
+    err = (row - want).abs().max()
+    assert float(err) < 0.05 * float(moved) + 2e-4, (float(err), float(moved))
+
+    def loss(r):   # same learning signal: both results have the same training loss
+        return float(torch.nn.functional.cross_entropy(ref.mlp1_logits(r, X, dims), y))
+    assert loss(row) == pytest.approx(loss(want), rel=2e-2, abs=2e-3)
