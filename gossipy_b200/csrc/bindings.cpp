@@ -1,31 +1,361 @@
 // Python bindings of the gossipy_b200 sm_100a extension (module gossipy_b200._C).
-#include "ops.h"
+//
+// The kernels live in csrc/kernels/*.cu (plain CUDA, compiled by nvcc without torch headers); this
+// file is the only translation unit that sees at::Tensor: it validates arguments, picks the current
+// stream of the tensor's device and calls the launchers of kernels/kernels.h.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+#include <cstring>
+#include <tuple>
+#include <vector>
+
+#include "kernels/kernels.h"
+#include "sched/scheduler.h"
 
 namespace gb {
-// runtime.cpp
-int64_t ipc_alloc(int64_t nbytes);
-void ipc_free(int64_t ptr);
-pybind11::bytes ipc_get_handle(int64_t ptr);
-int64_t ipc_open_handle(pybind11::bytes handle);
-void ipc_close_handle(int64_t ptr);
-at::Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> sizes, int64_t device, bool as_int32);
-void flag_signal(int64_t flag_ptr, int64_t value);
-void flag_wait(int64_t flag_ptr, int64_t value);
-int64_t device_sm_count();
+
+#define GB_LAUNCH_CHECK() C10_CUDA_KERNEL_LAUNCH_CHECK()
+
+static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream(); }
+
+// (ready flag address, generation, done counter address); zeros = no cross-GPU handshake
+using Sync = std::tuple<int64_t, int64_t, int64_t>;
+static PeerSync to_sync(const c10::optional<Sync>& s) {
+    PeerSync p{nullptr, 0u, nullptr};
+    if (s.has_value()) {
+        p.ready = reinterpret_cast<const uint32_t*>((uintptr_t)std::get<0>(*s));
+        p.gen = (uint32_t)std::get<1>(*s);
+        p.done = reinterpret_cast<uint32_t*>((uintptr_t)std::get<2>(*s));
+    }
+    return p;
+}
+
+static void check_row(const at::Tensor& t, const char* name) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.is_contiguous(), name,
+                " must be a contiguous fp32 CUDA tensor");
+}
+
+// ---- merges --------------------------------------------------------------------------------------
+void merge_pair(at::Tensor dst, at::Tensor src, double w_dst, double w_src, int64_t lo, int64_t hi,
+                c10::optional<Sync> sync) {
+    check_row(dst, "dst");
+    TORCH_CHECK(src.is_cuda() && src.scalar_type() == at::kFloat && src.is_contiguous());
+    TORCH_CHECK(0 <= lo && lo <= hi && hi <= dst.numel() && hi <= src.numel());
+    c10::cuda::CUDAGuard guard(dst.device());
+    launch_merge_pair(dst.data_ptr<float>(), src.data_ptr<float>(), (float)w_dst, (float)w_src, lo, hi,
+                      to_sync(sync), cur_stream());
+    GB_LAUNCH_CHECK();
+}
+
+void merge_segments(at::Tensor dst, at::Tensor src, at::Tensor seg, double w_dst, double w_src,
+                    c10::optional<Sync> sync) {
+    check_row(dst, "dst");
+    TORCH_CHECK(seg.is_cuda() && seg.scalar_type() == at::kLong && seg.is_contiguous());
+    TORCH_CHECK(seg.dim() == 2 && seg.size(1) == 4);
+    c10::cuda::CUDAGuard guard(dst.device());
+    launch_merge_segments(dst.data_ptr<float>(), src.data_ptr<float>(), seg.data_ptr<int64_t>(),
+                          (int)seg.size(0), (float)w_dst, (float)w_src, to_sync(sync), cur_stream());
+    GB_LAUNCH_CHECK();
+}
+
+void merge_indexed(at::Tensor dst, at::Tensor src, at::Tensor idx, double w_dst, double w_src,
+                   c10::optional<Sync> sync) {
+    check_row(dst, "dst");
+    TORCH_CHECK(idx.is_cuda() && idx.scalar_type() == at::kLong && idx.is_contiguous());
+    const int64_t n = idx.numel();
+    if (n == 0) return;
+    c10::cuda::CUDAGuard guard(dst.device());
+    auto scratch = at::empty({n}, dst.options());
+    launch_merge_indexed(dst.data_ptr<float>(), src.data_ptr<float>(), idx.data_ptr<int64_t>(), n,
+                         (float)w_dst, (float)w_src, scratch.data_ptr<float>(), to_sync(sync), cur_stream());
+    GB_LAUNCH_CHECK();
+}
+
+void merge_kway(at::Tensor dst, std::vector<at::Tensor> srcs, std::vector<double> weights,
+                c10::optional<std::vector<Sync>> syncs) {
+    check_row(dst, "dst");
+    TORCH_CHECK(weights.size() == srcs.size() + 1, "need one weight per model incl. self");
+    TORCH_CHECK((((uintptr_t)dst.data_ptr<float>()) & 15u) == 0, "row must be 16-byte aligned");
+    TORCH_CHECK(!syncs.has_value() || syncs->size() == srcs.size());
+    c10::cuda::CUDAGuard guard(dst.device());
+    const int64_t n = dst.numel();
+    if (srcs.empty()) { dst.mul_(weights[0]); return; }
+    std::vector<const float*> ptrs; std::vector<float> w; std::vector<PeerSync> ps;
+    w.push_back((float)weights[0]);
+    for (size_t j = 0; j < srcs.size(); ++j) {
+        const at::Tensor& s = srcs[j];
+        TORCH_CHECK(s.is_cuda() && s.scalar_type() == at::kFloat && s.is_contiguous() && s.numel() >= n);
+        TORCH_CHECK((((uintptr_t)s.data_ptr<float>()) & 15u) == 0);
+        ptrs.push_back(s.data_ptr<float>());
+        w.push_back((float)weights[1 + j]);
+        if (syncs.has_value()) ps.push_back(to_sync((*syncs)[j]));
+    }
+    launch_merge_kway(dst.data_ptr<float>(), ptrs.data(), w.data(), (int)srcs.size(), n,
+                      syncs.has_value() ? ps.data() : nullptr, cur_stream());
+    GB_LAUNCH_CHECK();
+}
+
+// ---- optimizers ------------------------------------------------------------------------------------
+void sgd_step(at::Tensor p, at::Tensor g, int64_t n, double lr, double wd, double momentum,
+              c10::optional<at::Tensor> buf, double dampening, bool nesterov, bool first,
+              c10::optional<at::Tensor> scale) {
+    check_row(p, "p"); check_row(g, "g");
+    TORCH_CHECK(n <= p.numel() && n <= g.numel());
+    c10::cuda::CUDAGuard guard(p.device());
+    launch_sgd(p.data_ptr<float>(), g.data_ptr<float>(), n, (float)lr, (float)wd, (float)momentum,
+               buf.has_value() ? buf->data_ptr<float>() : nullptr, (float)dampening, nesterov, first,
+               scale.has_value() ? scale->data_ptr<float>() : nullptr, cur_stream());
+    GB_LAUNCH_CHECK();
+}
+
+void adam_step(at::Tensor p, at::Tensor g, int64_t n, at::Tensor m, at::Tensor v, int64_t step,
+               double lr, double beta1, double beta2, double eps, double wd, bool decoupled) {
+    check_row(p, "p"); check_row(g, "g"); check_row(m, "m"); check_row(v, "v");
+    c10::cuda::CUDAGuard guard(p.device());
+    launch_adam(p.data_ptr<float>(), g.data_ptr<float>(), n, m.data_ptr<float>(), v.data_ptr<float>(), step,
+                (float)lr, (float)beta1, (float)beta2, (float)eps, (float)wd, decoupled, cur_stream());
+    GB_LAUNCH_CHECK();
+}
+
+// ---- fused local updates -----------------------------------------------------------------------------
+static thread_local float* g_debug_ptr = nullptr;
+
+int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
+                   int64_t batch_size, int64_t local_epochs, double lr, double wd, int64_t key,
+                   c10::optional<at::Tensor> part_id, c10::optional<at::Tensor> ages, std::string impl,
+                   c10::optional<at::Tensor> peer, double w_self, double w_peer, c10::optional<Sync> sync) {
+    check_row(row, "row"); check_row(X, "X");
+    TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.is_contiguous() && X.dim() == 2);
+    TrainParams p{};
+    p.IN = (int)std::get<0>(dims); p.H = (int)std::get<1>(dims); p.OUT = (int)std::get<2>(dims);
+    p.n = (int)X.size(0);
+    TORCH_CHECK(X.size(1) == p.IN && y.numel() == p.n && p.n > 0);
+    const int64_t P = (int64_t)p.H * p.IN + p.H + (int64_t)p.OUT * p.H + p.OUT;
+    TORCH_CHECK(row.numel() >= P);
+    p.B = (int)(batch_size == 0 ? p.n : std::min<int64_t>(batch_size, p.n));
+    p.epochs = (int)local_epochs;
+    p.lr = (float)lr; p.wd = (float)wd; p.key = (uint64_t)key;
+    p.row = row.data_ptr<float>(); p.X = X.data_ptr<float>(); p.y = y.data_ptr<int64_t>();
+    p.dbg = g_debug_ptr;
+    if (part_id.has_value() && ages.has_value()) {
+        TORCH_CHECK(part_id->is_cuda() && part_id->scalar_type() == at::kLong && ages->is_cuda() &&
+                    ages->scalar_type() == at::kLong);
+        p.part_id = part_id->data_ptr<int64_t>(); p.ages = ages->data_ptr<int64_t>();
+        p.n_parts = (int)ages->numel();
+    }
+    if (peer.has_value()) {
+        TORCH_CHECK(peer->is_cuda() && peer->scalar_type() == at::kFloat && peer->numel() >= P);
+        p.peer = peer->data_ptr<float>(); p.w_self = (float)w_self; p.w_peer = (float)w_peer;
+        p.sync = to_sync(sync);
+    }
+    c10::cuda::CUDAGuard guard(row.device());
+    const TrainImpl which = impl == "cluster" ? kTrainCluster : (impl == "tc" ? kTrainTc : kTrainAuto);
+    const char* why = "";
+    const bool ok = launch_mlp1_train(p, which, cur_stream(), &why);
+    TORCH_CHECK(ok, why, " (in=", p.IN, " hidden=", p.H, " out=", p.OUT, " batch=", p.B, ")");
+    GB_LAUNCH_CHECK();
+    const int spe = (p.n + p.B - 1) / p.B;
+    return p.epochs > 0 ? (int64_t)p.epochs * spe : 1;
+}
+
+at::Tensor mlp1_train_tc_debug(at::Tensor row, at::Tensor X, at::Tensor y,
+                               std::tuple<int64_t, int64_t, int64_t> dims, int64_t batch_size,
+                               int64_t local_epochs, double lr, double wd, int64_t key) {
+    // runs the tcgen05 kernel and returns its debug dump (tests / bring-up / phase timers)
+    auto dbg = at::zeros({128, 32}, row.options());
+    g_debug_ptr = dbg.data_ptr<float>();
+    mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, wd, key, c10::nullopt, c10::nullopt, "tc",
+               c10::nullopt, 1.0, 0.0, c10::nullopt);
+    g_debug_ptr = nullptr;
+    return dbg;
+}
+
+at::Tensor mlp1_eval(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
+                     int64_t n_classes, c10::optional<at::Tensor> X_lp) {
+    check_row(row, "row"); check_row(X, "X");
+    TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.is_contiguous());
+    const int IN = (int)std::get<0>(dims), H = (int)std::get<1>(dims), OUT = (int)std::get<2>(dims);
+    const int n = (int)X.size(0);
+    TORCH_CHECK(X.size(1) == IN && y.numel() == n);
+    c10::cuda::CUDAGuard guard(row.device());
+    auto cm = at::zeros({n_classes, n_classes}, row.options().dtype(at::kInt));
+    TORCH_CHECK(launch_mlp1_eval(row.data_ptr<float>(), X.data_ptr<float>(), y.data_ptr<int64_t>(), n, IN, H,
+                                 OUT, (int)n_classes, cm.data_ptr<int>(), cur_stream()),
+                "mlp1_eval: hidden <= 128 and out <= 16 supported");
+    GB_LAUNCH_CHECK();
+    return cm;
+}
+
+int64_t logreg_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t> dims,
+                     int64_t batch_size, int64_t local_epochs, double lr, double wd, int64_t key,
+                     c10::optional<at::Tensor> part_id, c10::optional<at::Tensor> ages,
+                     c10::optional<at::Tensor> peer, double w_self, double w_peer, c10::optional<Sync> sync) {
+    check_row(row, "row"); check_row(X, "X");
+    TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.is_contiguous());
+    LogregParams p{};
+    p.IN = (int)std::get<0>(dims); p.OUT = (int)std::get<1>(dims);
+    p.n = (int)X.size(0);
+    TORCH_CHECK(X.dim() == 2 && X.size(1) == p.IN && p.n > 0);
+    p.B = (int)(batch_size == 0 ? p.n : std::min<int64_t>(batch_size, p.n));
+    p.epochs = (int)local_epochs; p.lr = (float)lr; p.wd = (float)wd; p.key = (uint64_t)key;
+    p.row = row.data_ptr<float>(); p.X = X.data_ptr<float>(); p.y = y.data_ptr<int64_t>();
+    if (part_id.has_value() && ages.has_value()) {
+        p.part_id = part_id->data_ptr<int64_t>(); p.ages = ages->data_ptr<int64_t>();
+        p.n_parts = (int)ages->numel();
+    }
+    if (peer.has_value()) {
+        TORCH_CHECK(peer->is_cuda() && peer->scalar_type() == at::kFloat);
+        p.peer = peer->data_ptr<float>(); p.w_self = (float)w_self; p.w_peer = (float)w_peer;
+        p.sync = to_sync(sync);
+    }
+    c10::cuda::CUDAGuard guard(row.device());
+    TORCH_CHECK(launch_logreg_train(p, cur_stream()), "logreg_train: unsupported shape for the fused kernel");
+    GB_LAUNCH_CHECK();
+    const int spe = (p.n + p.B - 1) / p.B;
+    return p.epochs > 0 ? (int64_t)p.epochs * spe : 1;
+}
+
+at::Tensor logreg_scores(at::Tensor row, at::Tensor X, std::tuple<int64_t, int64_t> dims) {
+    check_row(row, "row"); check_row(X, "X");
+    const int IN = (int)std::get<0>(dims), OUT = (int)std::get<1>(dims), n = (int)X.size(0);
+    c10::cuda::CUDAGuard guard(row.device());
+    auto out = at::empty({n, OUT}, X.options());
+    launch_logreg_scores(row.data_ptr<float>(), X.data_ptr<float>(), n, IN, OUT, out.data_ptr<float>(), cur_stream());
+    GB_LAUNCH_CHECK();
+    return out;
+}
+
+void linear_seq_update(at::Tensor w, at::Tensor X, at::Tensor y, int64_t kind, double lr, int64_t n_updates) {
+    TORCH_CHECK(w.is_cuda() && X.is_cuda() && y.is_cuda());
+    auto Xc = X.to(at::kFloat).contiguous();
+    auto yc = y.to(at::kFloat).contiguous();
+    const int dim = (int)w.numel(), n = (int)Xc.size(0);
+    TORCH_CHECK(dim <= 1024 && Xc.numel() == (int64_t)n * dim && yc.numel() == n);
+    c10::cuda::CUDAGuard guard(w.device());
+    launch_linear_seq(w.data_ptr<float>(), Xc.data_ptr<float>(), yc.data_ptr<float>(), n, dim, (int)kind,
+                      (float)lr, (long long)n_updates, cur_stream());
+    GB_LAUNCH_CHECK();
+}
+
+at::Tensor kmeans_assign(at::Tensor C, at::Tensor X) {
+    TORCH_CHECK(C.is_cuda() && X.is_cuda() && C.dim() == 2);
+    auto Xc = X.to(at::kFloat).contiguous();
+    auto Cc = C.contiguous();
+    const int k = (int)C.size(0), dim = (int)C.size(1), n = (int)Xc.size(0);
+    c10::cuda::CUDAGuard guard(C.device());
+    auto out = at::empty({n}, Xc.options().dtype(at::kLong));
+    launch_kmeans_assign(Cc.data_ptr<float>(), Xc.data_ptr<float>(), n, k, dim, out.data_ptr<int64_t>(), cur_stream());
+    GB_LAUNCH_CHECK();
+    return out;
+}
+
+void kmeans_update(at::Tensor C, at::Tensor X, double alpha) {
+    TORCH_CHECK(C.is_cuda() && C.is_contiguous() && C.dim() == 2);
+    auto Xc = X.to(at::kFloat).contiguous();
+    const int k = (int)C.size(0), dim = (int)C.size(1), n = (int)Xc.size(0);
+    if (n == 0) return;
+    auto asg = kmeans_assign(C, Xc);
+    c10::cuda::CUDAGuard guard(C.device());
+    launch_kmeans_apply(C.data_ptr<float>(), Xc.data_ptr<float>(), asg.data_ptr<int64_t>(), n, k, dim,
+                        (float)alpha, cur_stream());
+    GB_LAUNCH_CHECK();
+}
+
+void mf_update(at::Tensor X, at::Tensor b, at::Tensor Y, at::Tensor c, at::Tensor ratings, double reg, double lr) {
+    TORCH_CHECK(Y.is_cuda() && ratings.is_cuda() && Y.dim() == 2);
+    auto rc = ratings.to(at::kFloat).contiguous();
+    const int m = (int)rc.size(0), k = (int)Y.size(1);
+    TORCH_CHECK(k <= 128, "mf_update: rank <= 128 supported");
+    c10::cuda::CUDAGuard guard(Y.device());
+    launch_mf_update(X.data_ptr<float>(), b.data_ptr<float>(), Y.data_ptr<float>(), c.data_ptr<float>(),
+                     rc.data_ptr<float>(), m, k, (float)reg, (float)lr, cur_stream());
+    GB_LAUNCH_CHECK();
+}
+
+at::Tensor tc_probe(at::Tensor A, at::Tensor Bm, int64_t variant) {
+    const int K = (int)A.size(1), N = (int)Bm.size(1);
+    TORCH_CHECK(A.size(0) == 128 && Bm.size(0) == K && K % 8 == 0 && N % 16 == 0 && N <= 256);
+    TORCH_CHECK(!(variant & 4) || N % 32 == 0); TORCH_CHECK(!(variant & 8) || K % 32 == 0);
+    auto D = at::zeros({128, N}, A.options());
+    launch_tc_probe(A.data_ptr<float>(), Bm.data_ptr<float>(), D.data_ptr<float>(), K, N, (int)variant, cur_stream());
+    GB_LAUNCH_CHECK();
+    return D;
+}
+
+// ---- multi-process runtime: CUDA-IPC arenas and cross-GPU flags -----------------------------------------
+// One process per GPU (torch.distributed only exchanges the 64-byte IPC handles).  Each rank
+// cudaMalloc's its arena, exports it and maps every peer's arena; a peer row is then a device
+// pointer that the merge / train kernels dereference (loads travel over NVLink / NVSwitch).
+int64_t ipc_alloc(int64_t nbytes) {
+    void* p = nullptr;
+    C10_CUDA_CHECK(cudaMalloc(&p, (size_t)nbytes));
+    C10_CUDA_CHECK(cudaMemset(p, 0, (size_t)nbytes));
+    C10_CUDA_CHECK(cudaDeviceSynchronize());
+    return (int64_t)(uintptr_t)p;
+}
+void ipc_free(int64_t ptr) { C10_CUDA_CHECK(cudaFree((void*)(uintptr_t)ptr)); }
+pybind11::bytes ipc_get_handle(int64_t ptr) {
+    cudaIpcMemHandle_t h;
+    C10_CUDA_CHECK(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)ptr));
+    return pybind11::bytes(reinterpret_cast<const char*>(&h), sizeof(h));
+}
+int64_t ipc_open_handle(pybind11::bytes handle) {
+    std::string s = handle;
+    TORCH_CHECK(s.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, s.data(), sizeof(h));
+    void* p = nullptr;
+    C10_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return (int64_t)(uintptr_t)p;
+}
+void ipc_close_handle(int64_t ptr) { C10_CUDA_CHECK(cudaIpcCloseMemHandle((void*)(uintptr_t)ptr)); }
+at::Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> sizes, int64_t device, bool as_int32) {
+    auto opts = at::TensorOptions().device(at::kCUDA, (c10::DeviceIndex)device)
+                    .dtype(as_int32 ? at::kInt : at::kFloat);
+    return at::from_blob((void*)(uintptr_t)ptr, sizes, [](void*) {}, opts);
+}
+void flag_signal(int64_t flag_ptr, int64_t value) {
+    launch_flag_signal((uint32_t*)(uintptr_t)flag_ptr, (uint32_t)value, cur_stream());
+    GB_LAUNCH_CHECK();
+}
+void flag_wait(int64_t flag_ptr, int64_t value) {
+    launch_flag_wait((const uint32_t*)(uintptr_t)flag_ptr, (uint32_t)value, cur_stream());
+    GB_LAUNCH_CHECK();
+}
+void flag_add(int64_t flag_ptr, int64_t value) {
+    launch_flag_add((uint32_t*)(uintptr_t)flag_ptr, (uint32_t)value, cur_stream());
+    GB_LAUNCH_CHECK();
+}
+int64_t device_sm_count() { return sm_count(); }
+
 }  // namespace gb
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-    m.doc() = "gossipy_b200 sm_100a kernels";
-    m.def("merge_pair", &gb::merge_pair);
-    m.def("merge_segments", &gb::merge_segments);
-    m.def("merge_indexed", &gb::merge_indexed);
-    m.def("merge_kway", &gb::merge_kway);
+    namespace py = pybind11;
+    m.doc() = "gossipy_b200 sm_100a kernels + native scheduler";
+    m.def("merge_pair", &gb::merge_pair, py::arg("dst"), py::arg("src"), py::arg("w_dst"), py::arg("w_src"),
+          py::arg("lo"), py::arg("hi"), py::arg("sync") = py::none());
+    m.def("merge_segments", &gb::merge_segments, py::arg("dst"), py::arg("src"), py::arg("seg"),
+          py::arg("w_dst"), py::arg("w_src"), py::arg("sync") = py::none());
+    m.def("merge_indexed", &gb::merge_indexed, py::arg("dst"), py::arg("src"), py::arg("idx"),
+          py::arg("w_dst"), py::arg("w_src"), py::arg("sync") = py::none());
+    m.def("merge_kway", &gb::merge_kway, py::arg("dst"), py::arg("srcs"), py::arg("weights"),
+          py::arg("syncs") = py::none());
     m.def("sgd_step", &gb::sgd_step);
     m.def("adam_step", &gb::adam_step);
-    m.def("mlp1_train", &gb::mlp1_train);
+    m.def("mlp1_train", &gb::mlp1_train, py::arg("row"), py::arg("X"), py::arg("y"), py::arg("dims"),
+          py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"), py::arg("key"),
+          py::arg("part_id") = py::none(), py::arg("ages") = py::none(), py::arg("impl") = "",
+          py::arg("peer") = py::none(), py::arg("w_self") = 1.0, py::arg("w_peer") = 0.0,
+          py::arg("sync") = py::none());
     m.def("mlp1_train_tc_debug", &gb::mlp1_train_tc_debug);
     m.def("mlp1_eval", &gb::mlp1_eval);
-    m.def("logreg_train", &gb::logreg_train);
+    m.def("logreg_train", &gb::logreg_train, py::arg("row"), py::arg("X"), py::arg("y"), py::arg("dims"),
+          py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"), py::arg("key"),
+          py::arg("part_id") = py::none(), py::arg("ages") = py::none(), py::arg("peer") = py::none(),
+          py::arg("w_self") = 1.0, py::arg("w_peer") = 0.0, py::arg("sync") = py::none());
     m.def("logreg_scores", &gb::logreg_scores);
     m.def("linear_seq_update", &gb::linear_seq_update);
     m.def("kmeans_update", &gb::kmeans_update);
@@ -40,5 +370,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("tensor_from_ptr", &gb::tensor_from_ptr);
     m.def("flag_signal", &gb::flag_signal);
     m.def("flag_wait", &gb::flag_wait);
+    m.def("flag_add", &gb::flag_add);
     m.def("device_sm_count", &gb::device_sm_count);
+    gb::bind_scheduler(m);
 }

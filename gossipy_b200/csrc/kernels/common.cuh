@@ -43,16 +43,18 @@ struct GbPerm {  // keyed permutation of range(n): 4-round Feistel + cycle walki
 // memory helpers
 // ---------------------------------------------------------------------------------------------
 // Streaming 128-bit load that does not allocate in L1: used for rows that may live in a PEER GPU's
-// HBM (mapped through NVLink); such data is read exactly once per merge.
+// HBM (mapped through NVLink); such data is read exactly once per merge.  Deliberately NOT `.nc`:
+// the row may have been written by another GPU while this kernel was already spinning on its
+// `ready` flag, so the load must stay on the coherent path (ordered after the ld.acquire.sys).
 GB_DEVICE float4 gb_ld_stream(const float4* p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 GB_DEVICE float gb_ld_stream1(const float* p) {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 
@@ -70,6 +72,9 @@ template <int N> GB_DEVICE void gb_cp_async_wait() { asm volatile("cp.async.wait
 // cross-GPU flags (system scope) for the multi-process transport
 GB_DEVICE void gb_st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+GB_DEVICE void gb_red_release_sys_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 GB_DEVICE uint32_t gb_ld_acquire_sys(const uint32_t* p) {
     uint32_t v;

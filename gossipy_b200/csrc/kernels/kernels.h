@@ -1,0 +1,85 @@
+// Launchers of the gossipy_b200 sm_100a kernels.  Plain CUDA/C++ (no torch headers): every function
+// enqueues on `stream` and returns; errors are reported through cudaGetLastError() by the caller
+// (csrc/bindings.cpp).  Pointers are device pointers of the CURRENT device unless stated otherwise;
+// "peer" pointers may point into another GPU's HBM (mapped with CUDA IPC / peer access).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gb {
+
+// ---- cross-GPU row handshake (see kernels/common.cuh, parallel/runtime.py) ---------------------
+// A kernel that READS a row owned by another GPU first spins until *ready >= gen (the owner
+// publishes the generation after the producing kernel) and, when it is done with the row, adds 1
+// to *done (the owner waits for it before the row is recycled).  Null pointers disable each side.
+struct PeerSync {
+    const uint32_t* ready;   // flag in the OWNER's memory (may be peer-mapped)
+    uint32_t gen;
+    uint32_t* done;          // read counter in the OWNER's memory (may be peer-mapped)
+};
+
+// ---- merge.cu ------------------------------------------------------------------------------------
+void launch_merge_pair(float* dst, const float* src, float w_dst, float w_src, int64_t lo, int64_t hi,
+                       PeerSync sync, cudaStream_t stream);
+void launch_merge_segments(float* dst, const float* src, const int64_t* seg, int n_seg, float w_dst,
+                           float w_src, PeerSync sync, cudaStream_t stream);
+void launch_merge_indexed(float* dst, const float* src, const int64_t* idx, int64_t n, float w_dst,
+                          float w_src, float* scratch, PeerSync sync, cudaStream_t stream);
+constexpr int kMaxWay = 32;
+void launch_merge_kway(float* dst, const float* const* srcs, const float* weights /* k+1 */, int k,
+                       int64_t n, const PeerSync* syncs /* k or null */, cudaStream_t stream);
+// publish / wait / acknowledge as stand-alone stream operations
+void launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
+void launch_flag_wait(const uint32_t* flag, uint32_t value, cudaStream_t stream);
+void launch_flag_add(uint32_t* flag, uint32_t value, cudaStream_t stream);
+
+// ---- optim.cu ------------------------------------------------------------------------------------
+void launch_sgd(float* p, const float* g, int64_t n, float lr, float wd, float momentum, float* buf,
+                float dampening, bool nesterov, bool first, const float* scale, cudaStream_t stream);
+void launch_adam(float* p, const float* g, int64_t n, float* m, float* v, int64_t step, float lr,
+                 float beta1, float beta2, float eps, float wd, bool decoupled, cudaStream_t stream);
+
+// ---- mlp1_train*.cu / mlp1_eval.cu ---------------------------------------------------------------
+struct TrainParams {
+    float* row; const float* X; const int64_t* y;
+    int n, IN, H, OUT, B, epochs;
+    float lr, wd; uint64_t key;
+    const int64_t* part_id; const int64_t* ages; int n_parts;
+    int Hs, C, nbuf;
+    float* dbg;                 // optional debug dump (tests)
+    // fused MERGE_UPDATE: when `peer` is set the kernel starts from w_self*row + w_peer*peer
+    // (the peer row is pulled over NVLink while the weights are loaded on chip)
+    const float* peer; float w_self, w_peer; PeerSync sync;
+};
+enum TrainImpl { kTrainAuto = 0, kTrainCluster = 1, kTrainTc = 2 };
+// returns false when the shape is outside the envelope of the requested implementation
+bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const char** why);
+bool mlp1_train_tc(const TrainParams& p, cudaStream_t stream);
+bool launch_mlp1_eval(const float* row, const float* X, const int64_t* y, int n, int IN, int H, int OUT,
+                      int n_classes, int* cm, cudaStream_t stream);
+
+// ---- small.cu --------------------------------------------------------------------------------------
+struct LogregParams {
+    float* row; const float* X; const int64_t* y; int n, IN, OUT, B, epochs; float lr, wd; uint64_t key;
+    const int64_t* part_id; const int64_t* ages; int n_parts;
+    const float* peer; float w_self, w_peer; PeerSync sync;
+};
+bool launch_logreg_train(LogregParams p, cudaStream_t stream);
+void launch_logreg_scores(const float* row, const float* X, int n, int IN, int OUT, float* out,
+                          cudaStream_t stream);
+void launch_linear_seq(float* w, const float* X, const float* y, int n, int dim, int kind, float lr,
+                       long long t0, cudaStream_t stream);
+void launch_kmeans_assign(const float* C, const float* X, int n, int k, int dim, int64_t* out,
+                          cudaStream_t stream);
+void launch_kmeans_apply(float* C, const float* X, const int64_t* asg, int n, int k, int dim, float alpha,
+                         cudaStream_t stream);
+void launch_mf_update(float* Xu, float* bu, float* Y, float* c, const float* ratings, int m, int k,
+                      float reg, float lr, cudaStream_t stream);
+
+// ---- tc_probe.cu -----------------------------------------------------------------------------------
+void launch_tc_probe(const float* A, const float* Bm, float* D, int K, int N, int variant,
+                     cudaStream_t stream);
+
+int sm_count();
+
+}  // namespace gb

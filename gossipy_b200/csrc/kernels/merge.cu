@@ -6,21 +6,63 @@
 // launch sits on this path.  The generic (w_dst, w_src) pair covers: uniform average (.5,.5),
 // age-weighted / limited merge (a/(a+b), b/(a+b)), adopt / pass-through / snapshot (0,1).
 //
+// Cross-GPU handshake (PeerSync, kernels.h) is part of the same kernel: every CTA spins on the
+// owner's `ready` generation flag (ld.acquire.sys) before its first peer load, and the last CTA to
+// finish acknowledges the read with one red.release.sys.add on the owner's `done` counter.
+//
 // Reference semantics: gossipy/model/handler.py:260-280, 666-688, 695-715; sampling.py:76-107,
 // 201-234.
 #include "common.cuh"
-#include "ops.h"
-#include <ATen/cuda/CUDAContext.h>
-#include <c10/cuda/CUDAGuard.h>
+#include "kernels.h"
+#include <algorithm>
 
 namespace gb {
 
 constexpr int kMergeThreads = 256;
 constexpr int kUnroll = 4;  // 4 x 128-bit loads in flight per thread per operand (peer latency ~2 us)
 
+// ---- handshake helpers ---------------------------------------------------------------------------
+constexpr int kTickets = 4096;
+static uint32_t* g_tickets[16] = {nullptr};
+static uint32_t g_ticket_next[16] = {0};
+
+// A zero-initialised CTA-arrival counter for one launch (returned to zero by the last CTA).
+static uint32_t* next_ticket() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_tickets[dev] == nullptr) {
+        cudaMalloc(&g_tickets[dev], kTickets * sizeof(uint32_t));
+        cudaMemset(g_tickets[dev], 0, kTickets * sizeof(uint32_t));
+    }
+    return g_tickets[dev] + (g_ticket_next[dev]++ % kTickets);
+}
+
+GB_DEVICE void peer_wait(const PeerSync& s) {
+    if (s.ready != nullptr) {
+        if (threadIdx.x == 0) {
+            while ((int32_t)(gb_ld_acquire_sys(s.ready) - s.gen) < 0) __nanosleep(40);
+        }
+        __syncthreads();
+    }
+}
+GB_DEVICE void peer_done(const PeerSync& s, uint32_t* ticket) {
+    if (s.done != nullptr) {
+        __syncthreads();                         // every thread of the CTA has consumed its peer loads
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const uint32_t total = gridDim.x * gridDim.y;
+            if (atomicAdd(ticket, 1u) == total - 1u) {
+                *ticket = 0u;
+                gb_red_release_sys_add(s.done, 1u);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kMergeThreads)
 merge_pair_kernel(float* __restrict__ dst, const float* __restrict__ src, float wd, float ws,
-                  int64_t lo, int64_t hi) {
+                  int64_t lo, int64_t hi, PeerSync sync, uint32_t* ticket) {
+    peer_wait(sync);
     // scalar head until dst is 16-byte aligned, vector body, scalar tail
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -74,13 +116,16 @@ merge_pair_kernel(float* __restrict__ dst, const float* __restrict__ src, float 
     }
     for (int64_t i = head + 4 * nvec + tid; i < hi; i += nthreads)
         dst[i] = (wd == 0.f ? 0.f : wd * dst[i]) + ws * gb_ld_stream1(src + i);
+    peer_done(sync, ticket);
 }
 
 // Strided blocks (partitioned-model merge): block s = (start, n_runs, run_len, stride); only the
 // bytes of the partition are fetched from the peer.
 __global__ void __launch_bounds__(kMergeThreads)
 merge_segments_kernel(float* __restrict__ dst, const float* __restrict__ src,
-                      const int64_t* __restrict__ seg, int n_seg, float wd, float ws) {
+                      const int64_t* __restrict__ seg, int n_seg, float wd, float ws, PeerSync sync,
+                      uint32_t* ticket) {
+    peer_wait(sync);
     for (int s = blockIdx.y; s < n_seg; s += gridDim.y) {
         const int64_t start = seg[4 * s], n_runs = seg[4 * s + 1], run_len = seg[4 * s + 2],
                       stride = seg[4 * s + 3];
@@ -92,22 +137,23 @@ merge_segments_kernel(float* __restrict__ dst, const float* __restrict__ src,
             dst[pos] = wd * dst[pos] + ws * gb_ld_stream1(src + pos);
         }
     }
+    peer_done(sync, ticket);
 }
 
 // Sampled merge: gather of 4-byte words from the peer (documented lower NVLink efficiency).
-// Duplicated indices are benign: every duplicate computes the same value from the same inputs only
-// if reads precede writes -- so read both operands first, then write (two-phase within a thread);
-// duplicates across threads race on identical values.
+// Indices may repeat: phase 1 computes every merged value from the UNMODIFIED rows into scratch,
+// phase 2 scatters (duplicates then write identical values).
 __global__ void __launch_bounds__(kMergeThreads)
 merge_indexed_kernel(float* __restrict__ dst, const float* __restrict__ src,
                      const int64_t* __restrict__ idx, int64_t n, float wd, float ws,
-                     float* __restrict__ scratch) {
-    // phase 1: scratch[i] = merged value ; phase 2 (second launch with scratch==nullptr swap) writes
+                     float* __restrict__ scratch, PeerSync sync, uint32_t* ticket) {
+    peer_wait(sync);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = idx[i];
         scratch[i] = wd * dst[p] + ws * gb_ld_stream1(src + p);
     }
+    peer_done(sync, ticket);
 }
 __global__ void __launch_bounds__(kMergeThreads)
 scatter_kernel(float* __restrict__ dst, const int64_t* __restrict__ idx, int64_t n,
@@ -118,11 +164,17 @@ scatter_kernel(float* __restrict__ dst, const int64_t* __restrict__ idx, int64_t
 }
 
 // k-way weighted merge (All2All / PENS): pointer table passed by value in the launch parameters.
-constexpr int kMaxWay = 32;
-struct KwayArgs { const float* src[kMaxWay]; float w[kMaxWay]; float w0; int k; };
+struct KwayArgs {
+    const float* src[kMaxWay]; float w[kMaxWay]; float w0; int k;
+    const uint32_t* ready[kMaxWay]; uint32_t gen[kMaxWay]; uint32_t* done[kMaxWay];
+};
 
 __global__ void __launch_bounds__(kMergeThreads)
-merge_kway_kernel(float* __restrict__ dst, KwayArgs a, int64_t n) {
+merge_kway_kernel(float* __restrict__ dst, const KwayArgs a, int64_t n, uint32_t* ticket) {
+    if (threadIdx.x < a.k && a.ready[threadIdx.x] != nullptr) {
+        while ((int32_t)(gb_ld_acquire_sys(a.ready[threadIdx.x]) - a.gen[threadIdx.x]) < 0) __nanosleep(40);
+    }
+    __syncthreads();
     const int64_t nvec = n / 4;
     float4* d4 = reinterpret_cast<float4*>(dst);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
@@ -143,88 +195,98 @@ merge_kway_kernel(float* __restrict__ dst, KwayArgs a, int64_t n) {
         for (int j = 0; j < a.k; ++j) acc += a.w[j] * gb_ld_stream1(a.src[j] + i);
         dst[i] = acc;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+            *ticket = 0u;
+            for (int j = 0; j < a.k; ++j)
+                if (a.done[j] != nullptr) gb_red_release_sys_add(a.done[j], 1u);
+        }
+    }
+}
+
+// ---- stand-alone flag operations ---------------------------------------------------------------------
+__global__ void flag_signal_kernel(uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    gb_st_release_sys(flag, value);
+}
+__global__ void flag_wait_kernel(const uint32_t* flag, uint32_t value) {
+    while ((int32_t)(gb_ld_acquire_sys(flag) - value) < 0) __nanosleep(64);   // flags only grow
+}
+__global__ void flag_add_kernel(uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    gb_red_release_sys_add(flag, value);
+}
+
+// ---- launchers -----------------------------------------------------------------------------------------
+int sm_count() {
+    static int cached[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cached[dev] == 0) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+    return cached[dev];
 }
 
 static int grid_for(int64_t work_items, int per_thread) {
-    const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
     int64_t blocks = (work_items + (int64_t)kMergeThreads * per_thread - 1) / ((int64_t)kMergeThreads * per_thread);
-    const int64_t cap = (int64_t)sms * 8;  // 8 resident CTAs of 256 threads per SM
-    if (blocks < 1) blocks = 1;
-    if (blocks > cap) blocks = cap;
-    return (int)blocks;
+    const int64_t cap = (int64_t)sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
+    return (int)std::max<int64_t>(1, std::min(blocks, cap));
 }
 
-void merge_pair(at::Tensor dst, at::Tensor src, double w_dst, double w_src, int64_t lo, int64_t hi) {
-    TORCH_CHECK(dst.is_cuda() && dst.scalar_type() == at::kFloat && dst.is_contiguous());
-    TORCH_CHECK(src.scalar_type() == at::kFloat && src.is_contiguous());
-    TORCH_CHECK(0 <= lo && lo <= hi && hi <= dst.numel() && hi <= src.numel());
-    if (hi == lo) return;
-    c10::cuda::CUDAGuard guard(dst.device());
-    auto stream = at::cuda::getCurrentCUDAStream();
+void launch_merge_pair(float* dst, const float* src, float w_dst, float w_src, int64_t lo, int64_t hi,
+                       PeerSync sync, cudaStream_t stream) {
+    if (hi <= lo) return;
+    uint32_t* ticket = sync.done ? next_ticket() : nullptr;
     merge_pair_kernel<<<grid_for((hi - lo) / 4 + 1, kUnroll), kMergeThreads, 0, stream>>>(
-        dst.data_ptr<float>(), src.data_ptr<float>(), (float)w_dst, (float)w_src, lo, hi);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+        dst, src, w_dst, w_src, lo, hi, sync, ticket);
 }
 
-void merge_segments(at::Tensor dst, at::Tensor src, at::Tensor seg, double w_dst, double w_src) {
-    TORCH_CHECK(dst.is_cuda() && seg.is_cuda() && seg.scalar_type() == at::kLong && seg.is_contiguous());
-    TORCH_CHECK(seg.dim() == 2 && seg.size(1) == 4);
-    const int n_seg = (int)seg.size(0);
-    if (n_seg == 0) return;
-    c10::cuda::CUDAGuard guard(dst.device());
-    auto stream = at::cuda::getCurrentCUDAStream();
+void launch_merge_segments(float* dst, const float* src, const int64_t* seg, int n_seg, float w_dst,
+                           float w_src, PeerSync sync, cudaStream_t stream) {
+    if (n_seg <= 0) return;
+    uint32_t* ticket = sync.done ? next_ticket() : nullptr;
     dim3 grid(8, n_seg < 1024 ? n_seg : 1024);
-    merge_segments_kernel<<<grid, kMergeThreads, 0, stream>>>(
-        dst.data_ptr<float>(), src.data_ptr<float>(), seg.data_ptr<int64_t>(), n_seg,
-        (float)w_dst, (float)w_src);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    merge_segments_kernel<<<grid, kMergeThreads, 0, stream>>>(dst, src, seg, n_seg, w_dst, w_src, sync, ticket);
 }
 
-void merge_indexed(at::Tensor dst, at::Tensor src, at::Tensor idx, double w_dst, double w_src) {
-    TORCH_CHECK(dst.is_cuda() && idx.is_cuda() && idx.scalar_type() == at::kLong && idx.is_contiguous());
-    const int64_t n = idx.numel();
-    if (n == 0) return;
-    c10::cuda::CUDAGuard guard(dst.device());
-    auto stream = at::cuda::getCurrentCUDAStream();
-    auto scratch = at::empty({n}, dst.options());
-    merge_indexed_kernel<<<grid_for(n, 1), kMergeThreads, 0, stream>>>(
-        dst.data_ptr<float>(), src.data_ptr<float>(), idx.data_ptr<int64_t>(), n, (float)w_dst,
-        (float)w_src, scratch.data_ptr<float>());
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
-    scatter_kernel<<<grid_for(n, 1), kMergeThreads, 0, stream>>>(
-        dst.data_ptr<float>(), idx.data_ptr<int64_t>(), n, scratch.data_ptr<float>());
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+void launch_merge_indexed(float* dst, const float* src, const int64_t* idx, int64_t n, float w_dst,
+                          float w_src, float* scratch, PeerSync sync, cudaStream_t stream) {
+    if (n <= 0) return;
+    uint32_t* ticket = sync.done ? next_ticket() : nullptr;
+    merge_indexed_kernel<<<grid_for(n, 1), kMergeThreads, 0, stream>>>(dst, src, idx, n, w_dst, w_src,
+                                                                       scratch, sync, ticket);
+    scatter_kernel<<<grid_for(n, 1), kMergeThreads, 0, stream>>>(dst, idx, n, scratch);
 }
 
-void merge_kway(at::Tensor dst, std::vector<at::Tensor> srcs, std::vector<double> weights) {
-    TORCH_CHECK(dst.is_cuda() && dst.scalar_type() == at::kFloat && dst.is_contiguous());
-    TORCH_CHECK(weights.size() == srcs.size() + 1, "need one weight per model incl. self");
-    TORCH_CHECK((((uintptr_t)dst.data_ptr<float>()) & 15u) == 0, "row must be 16-byte aligned");
-    c10::cuda::CUDAGuard guard(dst.device());
-    auto stream = at::cuda::getCurrentCUDAStream();
-    const int64_t n = dst.numel();
-    double w0 = weights[0];
-    size_t done = 0;
-    if (srcs.empty()) {
-        dst.mul_(w0);
-        return;
-    }
-    while (done < srcs.size()) {
+void launch_merge_kway(float* dst, const float* const* srcs, const float* weights, int k, int64_t n,
+                       const PeerSync* syncs, cudaStream_t stream) {
+    float w0 = weights[0];
+    int done = 0;
+    while (done < k) {
         KwayArgs a;
-        a.k = (int)std::min<size_t>(kMaxWay, srcs.size() - done);
-        a.w0 = (float)w0;
+        a.k = std::min(kMaxWay, k - done);
+        a.w0 = w0;
+        for (int j = 0; j < kMaxWay; ++j) { a.ready[j] = nullptr; a.done[j] = nullptr; a.gen[j] = 0; a.src[j] = nullptr; a.w[j] = 0.f; }
         for (int j = 0; j < a.k; ++j) {
-            const at::Tensor& s = srcs[done + j];
-            TORCH_CHECK(s.scalar_type() == at::kFloat && s.is_contiguous() && s.numel() >= n);
-            TORCH_CHECK((((uintptr_t)s.data_ptr<float>()) & 15u) == 0);
-            a.src[j] = s.data_ptr<float>();
-            a.w[j] = (float)weights[1 + done + j];
+            a.src[j] = srcs[done + j];
+            a.w[j] = weights[1 + done + j];
+            if (syncs) { a.ready[j] = syncs[done + j].ready; a.gen[j] = syncs[done + j].gen; a.done[j] = syncs[done + j].done; }
         }
-        merge_kway_kernel<<<grid_for(n / 4 + 1, 1), kMergeThreads, 0, stream>>>(dst.data_ptr<float>(), a, n);
-        C10_CUDA_KERNEL_LAUNCH_CHECK();
+        merge_kway_kernel<<<grid_for(n / 4 + 1, 1), kMergeThreads, 0, stream>>>(dst, a, n, next_ticket());
         done += a.k;
-        w0 = 1.0;  // later chunks accumulate onto the partial result
+        w0 = 1.f;  // later chunks accumulate onto the partial result
     }
+}
+
+void launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream) {
+    flag_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
+}
+void launch_flag_wait(const uint32_t* flag, uint32_t value, cudaStream_t stream) {
+    flag_wait_kernel<<<1, 1, 0, stream>>>(flag, value);
+}
+void launch_flag_add(uint32_t* flag, uint32_t value, cudaStream_t stream) {
+    flag_add_kernel<<<1, 1, 0, stream>>>(flag, value);
 }
 
 }  // namespace gb

@@ -6,9 +6,7 @@
 // (bf16 operands, fp32 accumulation in TMEM, TMA-fed) is in mlp1_eval_tc.cu and is preferred
 // whenever a bf16 copy of the test set is supplied.
 #include "common.cuh"
-#include "ops.h"
-#include <ATen/cuda/CUDAContext.h>
-#include <c10/cuda/CUDAGuard.h>
+#include "kernels.h"
 
 namespace gb {
 
@@ -74,28 +72,12 @@ mlp1_eval_simt_kernel(const float* __restrict__ row, const float* __restrict__ X
     }
 }
 
-bool mlp1_eval_tc(const float* row, const void* X_bf16, const int64_t* y, int n, int IN, int H, int OUT,
-                  int n_classes, int* cm, cudaStream_t stream);   // mlp1_eval_tc.cu
-
-at::Tensor mlp1_eval(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
-                     int64_t n_classes, c10::optional<at::Tensor> X_lp) {
-    TORCH_CHECK(row.is_cuda() && X.is_cuda() && y.is_cuda() && X.is_contiguous() && y.is_contiguous());
-    TORCH_CHECK(row.scalar_type() == at::kFloat && X.scalar_type() == at::kFloat && y.scalar_type() == at::kLong);
-    const int IN = (int)std::get<0>(dims), H = (int)std::get<1>(dims), OUT = (int)std::get<2>(dims);
-    const int n = (int)X.size(0);
-    TORCH_CHECK(X.size(1) == IN && y.numel() == n);
-    TORCH_CHECK(H <= EV_HMAX && OUT <= 16, "mlp1_eval: hidden <= 128 and out <= 16 supported");
-    c10::cuda::CUDAGuard guard(row.device());
-    auto stream = at::cuda::getCurrentCUDAStream();
-    auto cm = at::zeros({n_classes, n_classes}, row.options().dtype(at::kInt));
-    if (X_lp.has_value() && mlp1_eval_tc(row.data_ptr<float>(), X_lp->data_ptr(), y.data_ptr<int64_t>(), n,
-                                         IN, H, OUT, (int)n_classes, cm.data_ptr<int>(), stream))
-        return cm;
-    mlp1_eval_simt_kernel<<<(n + EV_TS - 1) / EV_TS, EV_THREADS, 0, stream>>>(
-        row.data_ptr<float>(), X.data_ptr<float>(), y.data_ptr<int64_t>(), n, IN, H, OUT,
-        (int)n_classes, cm.data_ptr<int>());
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
-    return cm;
+bool launch_mlp1_eval(const float* row, const float* X, const int64_t* y, int n, int IN, int H, int OUT,
+                      int n_classes, int* cm, cudaStream_t stream) {
+    if (H > EV_HMAX || OUT > 16 || n <= 0) return false;
+    mlp1_eval_simt_kernel<<<(n + EV_TS - 1) / EV_TS, EV_THREADS, 0, stream>>>(row, X, y, n, IN, H, OUT,
+                                                                             n_classes, cm);
+    return true;
 }
 
 }  // namespace gb

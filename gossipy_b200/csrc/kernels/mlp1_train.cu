@@ -14,10 +14,8 @@
 //   * weights are written back to the HBM row once, at the end.
 // The tcgen05 / TMEM implementation of the same op lives in mlp1_train_tc.cu.
 #include "common.cuh"
-#include "ops.h"
-#include "mlp1.h"
-#include <ATen/cuda/CUDAContext.h>
-#include <c10/cuda/CUDAGuard.h>
+#include "kernels.h"
+#include <algorithm>
 
 namespace gb {
 
@@ -53,12 +51,23 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp1_train_cluster_kernel(const Tr
     int* idxs = reinterpret_cast<int*>(coef + MAX_PARTS);  // [nbuf][BP] sample ids
     int* ys = idxs + p.nbuf * BP;                        // [nbuf][BP] labels
 
-    const float* W1g = p.row;
     float* b1g = p.row + (size_t)H * IN;
     float* W2g = b1g + H;
     float* b2g = W2g + (size_t)OUT * H;
 
     // ---- load this CTA's parameters ----------------------------------------------------------
+    // fused MERGE_UPDATE: with a peer row the starting point is w_self*row + w_peer*peer, the peer
+    // row being pulled (possibly over NVLink) while the weights are loaded on chip
+    const bool merging = p.peer != nullptr;
+    if (merging && p.sync.ready != nullptr) {
+        if (tid == 0) while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
+        __syncthreads();
+    }
+    auto ldp = [&](size_t off) -> float {
+        const float own = p.row[off];
+        return merging ? p.w_self * own + p.w_peer * gb_ld_stream1(p.peer + off) : own;
+    };
+    const size_t off_b1 = (size_t)H * IN, off_w2 = off_b1 + H, off_b2 = off_w2 + (size_t)OUT * H;
     float w[UPW][KPL];
     uint32_t pidpack[SCALED ? (UPW * KPL + 3) / 4 : 1];
     if (SCALED) {
@@ -73,7 +82,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp1_train_cluster_kernel(const Tr
         for (int i = 0; i < KPL; ++i) {
             const int k = i * 32 + lane;
             const bool ok = valid && k < IN;
-            w[u][i] = ok ? W1g[(size_t)(unit0 + slot) * IN + k] : 0.f;
+            w[u][i] = ok ? ldp((size_t)(unit0 + slot) * IN + k) : 0.f;
             if (SCALED) {
                 const uint32_t pid = ok ? (uint32_t)p.part_id[(size_t)(unit0 + slot) * IN + k] : 0u;
                 const int e = u * KPL + i;
@@ -84,13 +93,15 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp1_train_cluster_kernel(const Tr
     for (int i = tid; i < p.nbuf * BP * INP; i += blockDim.x) xs[i] = 0.f;   // zero incl. padding
     for (int i = tid; i < OUT_MAX * SLOTS; i += blockDim.x) {
         const int o = i / SLOTS, s = i % SLOTS;
-        w2s[i] = (o < OUT && s < nslots) ? W2g[(size_t)o * H + unit0 + s] : 0.f;
+        w2s[i] = (o < OUT && s < nslots) ? ldp(off_w2 + (size_t)o * H + unit0 + s) : 0.f;
     }
-    if (tid < SLOTS) b1s[tid] = (tid < nslots) ? b1g[unit0 + tid] : 0.f;
-    if (tid < OUT_MAX) b2s[tid] = (tid < OUT) ? b2g[tid] : 0.f;
+    if (tid < SLOTS) b1s[tid] = (tid < nslots) ? ldp(off_b1 + unit0 + tid) : 0.f;
+    if (tid < OUT_MAX) b2s[tid] = (tid < OUT) ? ldp(off_b2 + tid) : 0.f;
     for (int i = tid; i < BP * SLOTS; i += blockDim.x) { hs[i] = 0.f; dz1s[i] = 0.f; }
     __syncthreads();
     gb_cluster_sync();   // every CTA of the cluster is running before anyone writes into its smem
+    if (merging && p.sync.done != nullptr && rank == 0 && tid == 0)
+        gb_red_release_sys_add(p.sync.done, 1u);   // all CTAs have consumed their peer loads
 
     const int n = p.n;
     const int spe = (n + B - 1) / B;                          // steps per epoch
@@ -316,71 +327,32 @@ static bool launch_cluster(const TrainParams& p, bool scaled, cudaStream_t strea
     if (smem > 227 * 1024) { q.nbuf = 1; smem = train_smem_bytes(1, BP, INP); }
     if (smem > 227 * 1024) return false;
     auto kern = scaled ? mlp1_train_cluster_kernel<KPL, true> : mlp1_train_cluster_kernel<KPL, false>;
-    C10_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(q.C); cfg.blockDim = dim3(NW * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = q.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    C10_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, q));
-    return true;
+    return cudaLaunchKernelEx(&cfg, kern, q) == cudaSuccess;
 }
 
-
-static thread_local float* g_debug_ptr = nullptr;
-
-at::Tensor mlp1_train_tc_debug(at::Tensor row, at::Tensor X, at::Tensor y,
-                               std::tuple<int64_t, int64_t, int64_t> dims, int64_t batch_size,
-                               int64_t local_epochs, double lr, double wd, int64_t key) {
-    // runs the tcgen05 kernel and returns relu(z1) [128, 32] of the FIRST step (tests / bring-up)
-    auto dbg = at::zeros({128, 32}, row.options());
-    g_debug_ptr = dbg.data_ptr<float>();
-    mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, wd, key, c10::nullopt, c10::nullopt, "tc");
-    g_debug_ptr = nullptr;
-    return dbg;
-}
-
-int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
-                   int64_t batch_size, int64_t local_epochs, double lr, double wd, int64_t key,
-                   c10::optional<at::Tensor> part_id, c10::optional<at::Tensor> ages,
-                   std::string impl) {
-    TORCH_CHECK(row.is_cuda() && X.is_cuda() && y.is_cuda());
-    TORCH_CHECK(row.scalar_type() == at::kFloat && X.scalar_type() == at::kFloat && y.scalar_type() == at::kLong);
-    TORCH_CHECK(X.dim() == 2 && X.is_contiguous() && y.is_contiguous() && row.is_contiguous());
-    TrainParams p{};
-    p.IN = (int)std::get<0>(dims); p.H = (int)std::get<1>(dims); p.OUT = (int)std::get<2>(dims);
-    p.n = (int)X.size(0);
-    TORCH_CHECK(X.size(1) == p.IN && y.numel() == p.n && p.n > 0);
-    TORCH_CHECK(row.numel() >= (int64_t)p.H * p.IN + p.H + (int64_t)p.OUT * p.H + p.OUT);
-    p.B = (int)(batch_size == 0 ? p.n : std::min<int64_t>(batch_size, p.n));
-    p.epochs = (int)local_epochs;
-    p.lr = (float)lr; p.wd = (float)wd; p.key = (uint64_t)key;
-    p.row = row.data_ptr<float>(); p.X = X.data_ptr<float>(); p.y = y.data_ptr<int64_t>();
-    p.dbg = g_debug_ptr;
-    const bool scaled = part_id.has_value() && ages.has_value();
-    if (scaled) {
-        TORCH_CHECK(part_id->is_cuda() && part_id->scalar_type() == at::kLong && ages->is_cuda() &&
-                    ages->scalar_type() == at::kLong);
-        p.part_id = part_id->data_ptr<int64_t>(); p.ages = ages->data_ptr<int64_t>();
-        p.n_parts = (int)ages->numel();
-        TORCH_CHECK(p.n_parts <= MAX_PARTS, "fused partitioned training supports <= 16 partitions");
+bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const char** why) {
+    static const char* kNone = "";
+    *why = kNone;
+    const bool scaled = p.part_id != nullptr && p.ages != nullptr;
+    if (scaled && p.n_parts > MAX_PARTS) { *why = "fused partitioned training supports <= 16 partitions"; return false; }
+    if (impl != kTrainCluster && !scaled) {
+        if (mlp1_train_tc(p, stream)) return true;
+        if (impl == kTrainTc) { *why = "tcgen05 training kernel does not support this configuration"; return false; }
     }
-    c10::cuda::CUDAGuard guard(row.device());
-    auto stream = at::cuda::getCurrentCUDAStream();
-    const int spe = (p.n + p.B - 1) / p.B;
-    const int64_t steps = p.epochs > 0 ? (int64_t)p.epochs * spe : 1;
-
-    if (impl != "cluster" && !scaled) {
-        if (mlp1_train_tc(p, stream)) return steps;
-        TORCH_CHECK(impl != "tc", "tcgen05 training kernel does not support this configuration");
+    if (!(p.IN % 4 == 0 && p.IN <= 1024 && p.OUT <= OUT_MAX && p.B <= 64 && p.H <= CMAX * SLOTS)) {
+        *why = "mlp1_train(cluster): unsupported shape";
+        return false;
     }
-    TORCH_CHECK(p.IN % 4 == 0 && p.IN <= 1024 && p.OUT <= OUT_MAX && p.B <= 64 &&
-                p.H <= CMAX * SLOTS, "mlp1_train(cluster): unsupported shape in=", p.IN, " hidden=", p.H,
-                " out=", p.OUT, " batch=", p.B);
     p.C = std::min(CMAX, std::max(1, (p.H + UPW - 1) / UPW));
     p.Hs = (p.H + p.C - 1) / p.C;
-    TORCH_CHECK(p.Hs <= SLOTS);
+    if (p.Hs > SLOTS) { *why = "mlp1_train(cluster): hidden slice too large"; return false; }
     const int kpl = (p.IN + 31) / 32;
     bool ok;
     if (kpl <= 2) ok = launch_cluster<2>(p, scaled, stream);
@@ -388,8 +360,8 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
     else if (kpl <= 16) ok = launch_cluster<16>(p, scaled, stream);
     else if (kpl <= 25) ok = launch_cluster<25>(p, scaled, stream);
     else ok = launch_cluster<32>(p, scaled, stream);
-    TORCH_CHECK(ok, "mlp1_train(cluster): batch tile does not fit in shared memory");
-    return steps;
+    if (!ok) *why = "mlp1_train(cluster): batch tile does not fit in shared memory / launch failed";
+    return ok;
 }
 
 }  // namespace gb

@@ -20,7 +20,7 @@
 //     update MMA; the next batch is prefetched into the X tile as soon as both are done with it.
 // Reference semantics: gossipy/model/handler.py:235-258.  Accuracy: tf32 products, fp32 accumulate.
 #include "tc_common.cuh"
-#include "mlp1.h"
+#include "kernels.h"
 #include <cstdio>
 
 namespace gb {
@@ -77,22 +77,33 @@ mlp1_train_tc_kernel(const TrainParams p, const int FPC /* real feature columns 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TcSmem::mbar);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + TcSmem::tslot);
 
-    const float* W1g = p.row;
     float* b1g = p.row + (size_t)H * IN;
     float* W2g = b1g + H;
     float* b2g = W2g + (size_t)OUT * H;
 
     // ---- one-time set-up -------------------------------------------------------------------------
+    // fused MERGE_UPDATE: with a peer row the starting point is w_self*row + w_peer*peer, the peer
+    // row being pulled (possibly over NVLink) while the master weights are loaded into TMEM
+    const bool merging = p.peer != nullptr;
+    if (merging && p.sync.ready != nullptr) {
+        if (tid == 0) while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
+        __syncthreads();
+    }
+    auto ldp = [&](size_t off) -> float {
+        const float own = p.row[off];
+        return merging ? p.w_self * own + p.w_peer * gb_ld_stream1(p.peer + off) : own;
+    };
+    const size_t off_b1 = (size_t)H * IN, off_w2 = off_b1 + H, off_b2 = off_w2 + (size_t)OUT * H;
     if (warp == 0) tmem_alloc<TC_TMEM_COLS>(tslot);
     if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init(&mbar[2], 1); mbar_fence_init(); }
     for (int i = tid; i < 2 * TC_B * TC_FPC_MAX; i += TC_THREADS) xs[i] = 0.f;   // X and X^T (contiguous)
     for (int i = tid; i < TC_HP * TC_B; i += TC_THREADS) a2[i] = 0.f;
     for (int i = tid; i < TC_OUTP * TC_HP; i += TC_THREADS) {
         const int o = i / TC_HP, j = i % TC_HP;
-        w2s[i] = (o < OUT && j < H) ? W2g[(size_t)o * H + j] : 0.f;
+        w2s[i] = (o < OUT && j < H) ? ldp(off_w2 + (size_t)o * H + j) : 0.f;
     }
-    b1s[tid] = (tid < H) ? b1g[tid] : 0.f;
-    if (tid < TC_OUTP) b2s[tid] = (tid < OUT) ? b2g[tid] : 0.f;
+    b1s[tid] = (tid < H) ? ldp(off_b1 + tid) : 0.f;
+    if (tid < TC_OUTP) b2s[tid] = (tid < OUT) ? ldp(off_b2 + tid) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -106,7 +117,7 @@ mlp1_train_tc_kernel(const TrainParams p, const int FPC /* real feature columns 
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int c = c0 + i;
-            v[i] = (tid < H && c < fcnt) ? W1g[(size_t)tid * IN + f0 + c] : 0.f;
+            v[i] = (tid < H && c < fcnt) ? ldp((size_t)tid * IN + f0 + c) : 0.f;
         }
         tmem_st16(tlane + t_w1 + c0, v);
     }
@@ -155,6 +166,8 @@ mlp1_train_tc_kernel(const TrainParams p, const int FPC /* real feature columns 
     __syncthreads();
     stage_loads(0, 0);
     gb_cluster_sync();            // peer is running (its smem may be written from here on)
+    if (merging && p.sync.done != nullptr && rank == 0 && tid == 0)
+        gb_red_release_sys_add(p.sync.done, 1u);   // both CTAs have consumed their peer loads
 
     const uint32_t idesc_fwd = make_idesc(kFmtTF32, kFmtTF32, 128, TC_B, false, false);
     const uint32_t x_sbo = (uint32_t)nchunk * 128u;      // distance between 8-row groups of the X tile

@@ -3,9 +3,9 @@
 // `scale` optionally multiplies the raw gradient per element (PartitionedTMH 1/age scaling,
 // reference gossipy/model/handler.py:514-520).
 #include "common.cuh"
-#include "ops.h"
-#include <ATen/cuda/CUDAContext.h>
-#include <c10/cuda/CUDAGuard.h>
+#include "kernels.h"
+#include <algorithm>
+#include <cmath>
 
 namespace gb {
 
@@ -46,38 +46,24 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, float
 }
 
 static int blocks_for(int64_t n) {
-    const int sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
     int64_t b = (n + 255) / 256;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sms * 8));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(b, (int64_t)sm_count() * 8));
 }
 
-void sgd_step(at::Tensor p, at::Tensor g, int64_t n, double lr, double wd, double momentum,
-              c10::optional<at::Tensor> buf, double dampening, bool nesterov, bool first,
-              c10::optional<at::Tensor> scale) {
-    TORCH_CHECK(p.is_cuda() && g.is_cuda() && p.scalar_type() == at::kFloat && g.scalar_type() == at::kFloat);
-    TORCH_CHECK(n <= p.numel() && n <= g.numel());
-    if (n == 0) return;
-    c10::cuda::CUDAGuard guard(p.device());
-    float* bp = (momentum != 0.0 && buf.has_value()) ? buf->data_ptr<float>() : nullptr;
-    const float* sp = scale.has_value() ? scale->data_ptr<float>() : nullptr;
-    sgd_kernel<<<blocks_for(n), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
-        p.data_ptr<float>(), g.data_ptr<float>(), n, (float)lr, (float)wd, (float)momentum, bp,
-        (float)dampening, nesterov ? 1 : 0, first ? 1 : 0, sp);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+void launch_sgd(float* p, const float* g, int64_t n, float lr, float wd, float momentum, float* buf,
+                float dampening, bool nesterov, bool first, const float* scale, cudaStream_t stream) {
+    if (n <= 0) return;
+    sgd_kernel<<<blocks_for(n), 256, 0, stream>>>(p, g, n, lr, wd, momentum, momentum != 0.f ? buf : nullptr,
+                                                  dampening, nesterov ? 1 : 0, first ? 1 : 0, scale);
 }
 
-void adam_step(at::Tensor p, at::Tensor g, int64_t n, at::Tensor m, at::Tensor v, int64_t step,
-               double lr, double beta1, double beta2, double eps, double wd, bool decoupled) {
-    TORCH_CHECK(p.is_cuda() && g.is_cuda() && m.is_cuda() && v.is_cuda());
-    if (n == 0) return;
-    c10::cuda::CUDAGuard guard(p.device());
-    const double bc1 = 1.0 - std::pow(beta1, (double)step);
-    const double bc2 = 1.0 - std::pow(beta2, (double)step);
-    adam_kernel<<<blocks_for(n), 256, 0, at::cuda::getCurrentCUDAStream()>>>(
-        p.data_ptr<float>(), g.data_ptr<float>(), n, m.data_ptr<float>(), v.data_ptr<float>(),
-        (float)lr, (float)beta1, (float)beta2, (float)eps, (float)wd, decoupled ? 1 : 0, (float)bc1,
-        (float)std::sqrt(bc2));
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+void launch_adam(float* p, const float* g, int64_t n, float* m, float* v, int64_t step, float lr,
+                 float beta1, float beta2, float eps, float wd, bool decoupled, cudaStream_t stream) {
+    if (n <= 0) return;
+    const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+    adam_kernel<<<blocks_for(n), 256, 0, stream>>>(p, g, n, m, v, lr, beta1, beta2, eps, wd,
+                                                   decoupled ? 1 : 0, (float)bc1, (float)std::sqrt(bc2));
 }
 
 }  // namespace gb

@@ -4,9 +4,8 @@
 // the whole local update in ONE launch.  Reference: gossipy/model/handler.py:235-258 (with
 // nn.py:147-174), :364-368, :416-423, :550-560, :604-615.
 #include "common.cuh"
-#include "ops.h"
-#include <ATen/cuda/CUDAContext.h>
-#include <c10/cuda/CUDAGuard.h>
+#include "kernels.h"
+#include <algorithm>
 
 namespace gb {
 
@@ -17,10 +16,6 @@ constexpr int LR_THREADS = 256;
 constexpr int LR_BMAX = 64;     // samples processed per pass (larger batches loop over passes)
 constexpr int LR_OMAX = 16;
 
-struct LogregParams {
-    float* row; const float* X; const int64_t* y; int n, IN, OUT, B, epochs; float lr, wd; uint64_t key;
-    const int64_t* part_id; const int64_t* ages; int n_parts;
-};
 
 __global__ void __launch_bounds__(LR_THREADS) logreg_train_kernel(const LogregParams p) {
     extern __shared__ __align__(16) float sm[];
@@ -32,7 +27,16 @@ __global__ void __launch_bounds__(LR_THREADS) logreg_train_kernel(const LogregPa
     float* coef = dz + LR_BMAX * LR_OMAX;  // [16]
     __shared__ int ids[LR_BMAX];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = LR_THREADS / 32;
-    for (int i = tid; i < P; i += LR_THREADS) W[i] = p.row[i];
+    if (p.peer != nullptr) {            // fused MERGE_UPDATE: start from w_self*row + w_peer*peer
+        if (p.sync.ready != nullptr && tid == 0)
+            while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
+        __syncthreads();
+        for (int i = tid; i < P; i += LR_THREADS) W[i] = p.w_self * p.row[i] + p.w_peer * gb_ld_stream1(p.peer + i);
+        __syncthreads();
+        if (p.sync.done != nullptr && tid == 0) gb_red_release_sys_add(p.sync.done, 1u);
+    } else {
+        for (int i = tid; i < P; i += LR_THREADS) W[i] = p.row[i];
+    }
     __syncthreads();
     const int n = p.n, B = p.B;
     const int spe = (n + B - 1) / B;
@@ -98,32 +102,19 @@ __global__ void __launch_bounds__(LR_THREADS) logreg_train_kernel(const LogregPa
     for (int i = tid; i < P; i += LR_THREADS) p.row[i] = W[i];
 }
 
-int64_t logreg_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t> dims,
-                     int64_t batch_size, int64_t local_epochs, double lr, double wd, int64_t key,
-                     c10::optional<at::Tensor> part_id, c10::optional<at::Tensor> ages) {
-    TORCH_CHECK(row.is_cuda() && X.is_cuda() && y.is_cuda() && X.is_contiguous() && y.is_contiguous());
-    TORCH_CHECK(X.scalar_type() == at::kFloat && y.scalar_type() == at::kLong && row.scalar_type() == at::kFloat);
-    LogregParams p{};
-    p.IN = (int)std::get<0>(dims); p.OUT = (int)std::get<1>(dims);
-    p.n = (int)X.size(0);
-    TORCH_CHECK(X.dim() == 2 && X.size(1) == p.IN && p.OUT <= LR_OMAX && p.n > 0);
-    p.B = (int)(batch_size == 0 ? p.n : std::min<int64_t>(batch_size, p.n));
-    p.epochs = (int)local_epochs; p.lr = (float)lr; p.wd = (float)wd; p.key = (uint64_t)key;
-    p.row = row.data_ptr<float>(); p.X = X.data_ptr<float>(); p.y = y.data_ptr<int64_t>();
-    if (part_id.has_value() && ages.has_value()) {
-        p.part_id = part_id->data_ptr<int64_t>(); p.ages = ages->data_ptr<int64_t>();
-        p.n_parts = (int)ages->numel();
-        TORCH_CHECK(p.n_parts <= 16);
-    }
+bool launch_logreg_train(LogregParams p, cudaStream_t stream) {
+    if (p.OUT > LR_OMAX || p.n <= 0 || p.n_parts > 16) return false;
     const int P = p.OUT * p.IN + p.OUT;
     const size_t smem = ((size_t)2 * P + (size_t)LR_BMAX * p.IN + LR_BMAX * LR_OMAX + 16) * 4;
-    TORCH_CHECK(smem <= 200 * 1024, "logreg_train: model too large for the fused kernel");
-    c10::cuda::CUDAGuard guard(row.device());
-    C10_CUDA_CHECK(cudaFuncSetAttribute(logreg_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    logreg_train_kernel<<<1, LR_THREADS, smem, at::cuda::getCurrentCUDAStream()>>>(p);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
-    const int spe = (p.n + p.B - 1) / p.B;
-    return p.epochs > 0 ? (int64_t)p.epochs * spe : 1;
+    if (smem > 200 * 1024) return false;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(logreg_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return false;
+        configured = smem;
+    }
+    logreg_train_kernel<<<1, LR_THREADS, smem, stream>>>(p);
+    return true;
 }
 
 __global__ void __launch_bounds__(256)
@@ -141,16 +132,11 @@ logreg_scores_kernel(const float* __restrict__ row, const float* __restrict__ X,
     }
 }
 
-at::Tensor logreg_scores(at::Tensor row, at::Tensor X, std::tuple<int64_t, int64_t> dims) {
-    const int IN = (int)std::get<0>(dims), OUT = (int)std::get<1>(dims), n = (int)X.size(0);
-    TORCH_CHECK(row.is_cuda() && X.is_cuda() && X.is_contiguous() && X.scalar_type() == at::kFloat);
-    c10::cuda::CUDAGuard guard(row.device());
-    auto out = at::empty({n, OUT}, X.options());
-    const int blocks = std::max(1, std::min((n + 7) / 8, 148 * 8));
-    logreg_scores_kernel<<<blocks, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
-        row.data_ptr<float>(), X.data_ptr<float>(), n, IN, OUT, out.data_ptr<float>());
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
-    return out;
+void launch_logreg_scores(const float* row, const float* X, int n, int IN, int OUT, float* out,
+                          cudaStream_t stream) {
+    if (n <= 0) return;
+    const int blocks = std::max(1, std::min((n + 7) / 8, sm_count() * 8));
+    logreg_scores_kernel<<<blocks, 256, 0, stream>>>(row, X, n, IN, OUT, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -194,18 +180,10 @@ linear_seq_kernel(float* __restrict__ w, const float* __restrict__ X, const floa
     for (int i = 0; i < SEQ_KPL; ++i) { const int k = i * 32 + lane; if (k < dim) w[k] = wr[i]; }
 }
 
-void linear_seq_update(at::Tensor w, at::Tensor X, at::Tensor y, int64_t kind, double lr, int64_t n_updates) {
-    TORCH_CHECK(w.is_cuda() && X.is_cuda() && y.is_cuda());
-    auto Xc = X.to(at::kFloat).contiguous();
-    auto yc = y.to(at::kFloat).contiguous();
-    const int dim = (int)w.numel(), n = (int)Xc.size(0);
-    TORCH_CHECK(dim <= 32 * SEQ_KPL && Xc.numel() == (int64_t)n * dim && yc.numel() == n);
-    if (n == 0) return;
-    c10::cuda::CUDAGuard guard(w.device());
-    linear_seq_kernel<<<1, 32, 0, at::cuda::getCurrentCUDAStream()>>>(
-        w.data_ptr<float>(), Xc.data_ptr<float>(), yc.data_ptr<float>(), n, dim, (int)kind, (float)lr,
-        (long long)n_updates);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+void launch_linear_seq(float* w, const float* X, const float* y, int n, int dim, int kind, float lr,
+                       long long t0, cudaStream_t stream) {
+    if (n <= 0) return;
+    linear_seq_kernel<<<1, 32, 0, stream>>>(w, X, y, n, dim, kind, lr, t0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -245,31 +223,17 @@ kmeans_apply_kernel(float* __restrict__ C, const float* __restrict__ X, const in
     }
 }
 
-at::Tensor kmeans_assign(at::Tensor C, at::Tensor X) {
-    TORCH_CHECK(C.is_cuda() && X.is_cuda() && C.dim() == 2);
-    auto Xc = X.to(at::kFloat).contiguous();
-    auto Cc = C.contiguous();
-    const int k = (int)C.size(0), dim = (int)C.size(1), n = (int)Xc.size(0);
-    c10::cuda::CUDAGuard guard(C.device());
-    auto out = at::empty({n}, Xc.options().dtype(at::kLong));
-    if (n == 0) return out;
-    const int blocks = std::max(1, std::min((n + 7) / 8, 148 * 8));
-    kmeans_assign_kernel<<<blocks, 256, 0, at::cuda::getCurrentCUDAStream()>>>(
-        Cc.data_ptr<float>(), Xc.data_ptr<float>(), n, k, dim, out.data_ptr<int64_t>());
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
-    return out;
+void launch_kmeans_assign(const float* C, const float* X, int n, int k, int dim, int64_t* out,
+                          cudaStream_t stream) {
+    if (n <= 0) return;
+    const int blocks = std::max(1, std::min((n + 7) / 8, sm_count() * 8));
+    kmeans_assign_kernel<<<blocks, 256, 0, stream>>>(C, X, n, k, dim, out);
 }
 
-void kmeans_update(at::Tensor C, at::Tensor X, double alpha) {
-    TORCH_CHECK(C.is_cuda() && C.is_contiguous() && C.dim() == 2);
-    auto Xc = X.to(at::kFloat).contiguous();
-    const int k = (int)C.size(0), dim = (int)C.size(1), n = (int)Xc.size(0);
-    if (n == 0) return;
-    auto asg = kmeans_assign(C, Xc);
-    c10::cuda::CUDAGuard guard(C.device());
-    kmeans_apply_kernel<<<1, 256, k * sizeof(int), at::cuda::getCurrentCUDAStream()>>>(
-        C.data_ptr<float>(), Xc.data_ptr<float>(), asg.data_ptr<int64_t>(), n, k, dim, (float)alpha);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+void launch_kmeans_apply(float* C, const float* X, const int64_t* asg, int n, int k, int dim, float alpha,
+                         cudaStream_t stream) {
+    if (n <= 0) return;
+    kmeans_apply_kernel<<<1, 256, k * sizeof(int), stream>>>(C, X, asg, n, k, dim, alpha);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -310,17 +274,10 @@ mf_update_kernel(float* __restrict__ Xu, float* __restrict__ bu, float* __restri
     if (lane == 0) bu[0] = b;
 }
 
-void mf_update(at::Tensor X, at::Tensor b, at::Tensor Y, at::Tensor c, at::Tensor ratings, double reg, double lr) {
-    TORCH_CHECK(Y.is_cuda() && ratings.is_cuda() && Y.dim() == 2);
-    auto rc = ratings.to(at::kFloat).contiguous();
-    const int m = (int)rc.size(0), k = (int)Y.size(1);
-    TORCH_CHECK(k <= 128, "mf_update: rank <= 128 supported");
-    if (m == 0) return;
-    c10::cuda::CUDAGuard guard(Y.device());
-    mf_update_kernel<<<1, 32, 0, at::cuda::getCurrentCUDAStream()>>>(
-        X.data_ptr<float>(), b.data_ptr<float>(), Y.data_ptr<float>(), c.data_ptr<float>(),
-        rc.data_ptr<float>(), m, k, (float)reg, (float)lr);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
+void launch_mf_update(float* Xu, float* bu, float* Y, float* c, const float* ratings, int m, int k,
+                      float reg, float lr, cudaStream_t stream) {
+    if (m <= 0) return;
+    mf_update_kernel<<<1, 32, 0, stream>>>(Xu, bu, Y, c, ratings, m, k, reg, lr);
 }
 
 }  // namespace gb

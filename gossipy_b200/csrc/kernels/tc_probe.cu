@@ -2,8 +2,7 @@
 // A from shared memory (K-major), B from shared memory in the "X tile" core-matrix layout read either
 // MN-major (variant bit1 = 0) or K-major from an explicitly transposed tile (bit1 = 1).
 #include "tc_common.cuh"
-#include "ops.h"
-#include <ATen/cuda/CUDAContext.h>
+#include "kernels.h"
 
 namespace gb {
 
@@ -68,17 +67,11 @@ tc_probe_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-at::Tensor tc_probe(at::Tensor A, at::Tensor Bm, int64_t variant) {
-    const int K = (int)A.size(1), N = (int)Bm.size(1);
-    TORCH_CHECK(A.size(0) == 128 && Bm.size(0) == K && K % 8 == 0 && N % 16 == 0 && N <= 256);
-    TORCH_CHECK(!(variant & 4) || N % 32 == 0); TORCH_CHECK(!(variant & 8) || K % 32 == 0);
-    auto D = at::zeros({128, N}, A.options());
+void launch_tc_probe(const float* A, const float* Bm, float* D, int K, int N, int variant,
+                     cudaStream_t stream) {
     const size_t smem = (size_t)(128 * K + K * N) * 4 + 1024;
-    C10_CUDA_CHECK(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_probe_kernel<<<1, 128, smem, at::cuda::getCurrentCUDAStream()>>>(
-        A.data_ptr<float>(), Bm.data_ptr<float>(), D.data_ptr<float>(), K, N, (int)variant);
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
-    return D;
+    cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_probe_kernel<<<1, 128, smem, stream>>>(A, Bm, D, K, N, variant);
 }
 
 }  // namespace gb

@@ -44,6 +44,12 @@ def mnist_like(n_train: int = 60000, n_test: int = 10000, seed: int = 0):
     return (X[:n_train], y[:n_train]), (X[n_train:], y[n_train:])
 
 
+def spambase_like(n_train: int = 4141, n_test: int = 460, seed: int = 0):
+    """spambase-shaped (57 features, 2 classes): ``((Xtr, ytr), (Xte, yte))`` with labels in {0,1}."""
+    X, y = teacher_classification(n_train + n_test, 57, 2, seed=seed, noise=0.3)
+    return (X[:n_train], y[:n_train]), (X[n_train:], y[n_train:])
+
+
 def images_like(name: str, as_tensor: bool = True, seed: int = 0, n_train: int = None,
                 n_test: int = None):
     """CIFAR-10 (3x32x32) / Fashion-MNIST (28x28) shaped images in [0,1] with teacher labels."""

@@ -28,7 +28,7 @@ class Row:
     """
 
     __slots__ = ("arena", "index", "tensor", "ready", "consumed", "stream", "rank", "gen",
-                 "remote_reads", "flag_ready", "flag_done")
+                 "remote_reads", "flag_ready", "flag_done", "_acked")
 
     def __init__(self, arena: "RowArena", index: int, tensor: Optional[torch.Tensor]) -> None:
         self.arena = arena
@@ -42,6 +42,7 @@ class Row:
         self.remote_reads = 0    # cumulative reads by other ranks
         self.flag_ready = 0      # device address of the owner's `ready` flag (p2p transport)
         self.flag_done = 0       # device address of the owner's `done` counter
+        self._acked = 0          # remote reads already waited for (owner side)
 
     def release(self) -> None:
         self.arena.free(self)
@@ -97,47 +98,106 @@ class RowArena:
 
 
 class SymmetricArenas:
-    """Identical IPC-shared arenas on every rank (``p2p`` transport).
+    """Identical shared arenas on every rank (``p2p`` transport).  Creation is collective.
 
-    Layout of each rank's allocation: ``capacity`` rows of ``row_numel`` floats followed by two
-    uint32 flags per row (``ready`` generation, ``done`` read counter).  Creation is collective.
+    Layout of each rank's allocation: ``capacity`` rows of ``row_numel`` floats followed by the
+    per-row flags: ``ready`` (uint32 generation published by the owner) and ``done`` (reads
+    acknowledged by other ranks).
+
+    * CUDA: ``cudaMalloc`` + CUDA IPC; every peer's arena is mapped into this process, so a peer
+      row is a device pointer whose loads travel over NVLink / NVSwitch.  ``done`` is one counter
+      (readers use ``red.release.sys.add``).
+    * CPU (gloo plumbing runs): POSIX shared memory; ``done`` has one slot per reader rank (a
+      slot has a single writer, so plain stores suffice).
     """
 
     def __init__(self, device: torch.device, row_numel: int) -> None:
         import torch.distributed as dist
-        from ..ops.native import native
         from ..parallel import runtime as prt
-        nat = native()
         self.device = torch.device(device)
         self.row_numel = int(row_numel)
+        self.world = prt.world()
         row_bytes = self.row_numel * 4
-        self.capacity = int(max(16, min(512, (1 << 31) // row_bytes)))
+        cap = prt.arena_capacity()
+        if cap is None:
+            cap = int(max(64, min(8192, (256 << 20) // row_bytes)))
+        self.capacity = cap
         self.flags_off = self.capacity * row_bytes
-        total = self.flags_off + self.capacity * 8
-        torch.cuda.set_device(self.device)
-        self.base = nat.ipc_alloc(total)
-        handles: List = [None] * prt.world()
-        dist.all_gather_object(handles, nat.ipc_get_handle(self.base))
-        self.bases = [self.base if r == prt.rank() else nat.ipc_open_handle(handles[r])
-                      for r in range(prt.world())]
-        dist.barrier()
+        self.cuda = self.device.type == "cuda"
+        self.flag_words = 2 if self.cuda else 1 + self.world
+        total = self.flags_off + self.capacity * 4 * self.flag_words
         self.mirrors: List[RowArena] = []
-        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        for r in range(prt.world()):
-            mirror = RowArena(self.device, row_numel, rank=r, ghost=True)
-            mirror._n_rows = self.capacity
-            for i in range(self.capacity):
-                t = nat.tensor_from_ptr(self.bases[r] + i * row_bytes, [self.row_numel], dev_index, False)
-                row = Row(mirror, i, t)
-                row.flag_ready = self.bases[r] + self.flags_off + 8 * i
-                row.flag_done = self.bases[r] + self.flags_off + 8 * i + 4
-                mirror._free.append(row)
-            mirror._grow = _no_growth  # type: ignore[assignment]
-            self.mirrors.append(mirror)
+        if self.cuda:
+            from ..ops.native import native
+            nat = native()
+            torch.cuda.set_device(self.device)
+            self.base = nat.ipc_alloc(total)
+            handles: List = [None] * self.world
+            dist.all_gather_object(handles, nat.ipc_get_handle(self.base))
+            self.bases = [self.base if r == prt.rank() else nat.ipc_open_handle(handles[r])
+                          for r in range(self.world)]
+            dist.barrier()
+            dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            for r in range(self.world):
+                mirror = RowArena(self.device, row_numel, rank=r, ghost=True)
+                mirror._n_rows = self.capacity
+                for i in range(self.capacity):
+                    t = nat.tensor_from_ptr(self.bases[r] + i * row_bytes, [self.row_numel], dev_index, False)
+                    row = Row(mirror, i, t)
+                    row.flag_ready = self.bases[r] + self.flags_off + 8 * i
+                    row.flag_done = self.bases[r] + self.flags_off + 8 * i + 4
+                    mirror._free.append(row)
+                mirror._grow = _no_growth  # type: ignore[assignment]
+                self.mirrors.append(mirror)
+        else:
+            import numpy as np
+            from multiprocessing import shared_memory
+            tag = prt.session_tag()
+            names = ["gb200_%s_%d_%d" % (tag, self.row_numel, r) for r in range(self.world)]
+            mine = shared_memory.SharedMemory(name=names[prt.rank()], create=True, size=total)
+            np.frombuffer(mine.buf, dtype=np.uint8)[:] = 0
+            dist.barrier()
+            self._shm = [mine if r == prt.rank() else shared_memory.SharedMemory(name=names[r])
+                         for r in range(self.world)]
+            dist.barrier()
+            _SHM_KEEPALIVE.extend(self._shm)
+            for r in range(self.world):
+                buf = self._shm[r].buf
+                data = torch.frombuffer(buf, dtype=torch.float32, count=self.capacity * self.row_numel)
+                flags = np.frombuffer(buf, dtype=np.int32, offset=self.flags_off,
+                                      count=self.capacity * self.flag_words)
+                mirror = RowArena(self.device, row_numel, rank=r, ghost=True)
+                mirror._n_rows = self.capacity
+                for i in range(self.capacity):
+                    row = Row(mirror, i, data[i * self.row_numel:(i + 1) * self.row_numel])
+                    row.flag_ready = (flags, i * self.flag_words)
+                    row.flag_done = (flags, i * self.flag_words + 1)     # + reader rank
+                    mirror._free.append(row)
+                mirror._grow = _no_growth  # type: ignore[assignment]
+                self.mirrors.append(mirror)
+
+    def close(self) -> None:
+        from ..parallel import runtime as prt
+        if self.cuda:
+            return
+        for r, shm in enumerate(self._shm):
+            if r == prt.rank():
+                try:
+                    shm.unlink()
+                except Exception:
+                    pass
+            try:
+                shm.close()
+            except Exception:      # tensors created with torch.frombuffer may still reference the mapping
+                pass
+
+
+_SHM_KEEPALIVE: List = []
 
 
 def _no_growth() -> None:
-    raise RuntimeError("symmetric arena exhausted: too many models in flight for the p2p transport")
+    raise RuntimeError("symmetric arena exhausted: too many models in flight for the p2p transport "
+                       "(raise it with parallel.runtime.init(arena_capacity=...))")
 
 
 _ARENAS: Dict[tuple, RowArena] = {}
@@ -154,8 +214,8 @@ def arena_for(device: torch.device, row_numel: int, rank: Optional[int] = None) 
     arena = _ARENAS.get(key)
     if arena is not None:
         return arena
-    if prt.active() and prt.transport() == "p2p" and device.type == "cuda":
-        skey = (device.index, int(row_numel))
+    if prt.active() and prt.transport() == "p2p":
+        skey = (device.type, device.index, int(row_numel))
         sym = _SYMMETRIC.get(skey)
         if sym is None:
             sym = _SYMMETRIC[skey] = SymmetricArenas(device, row_numel)
@@ -168,9 +228,69 @@ def arena_for(device: torch.device, row_numel: int, rank: Optional[int] = None) 
 
 
 def reset_arenas() -> None:
+    for sym in _SYMMETRIC.values():
+        sym.close()
     _ARENAS.clear()
     _SYMMETRIC.clear()
     _STREAMS.clear()
+
+
+# --------------------------------------------------------------------------------------
+# cross-rank protocol (replicated bookkeeping; see parallel/runtime.py)
+# --------------------------------------------------------------------------------------
+def read_sync(row: Row, reader_rank: int):
+    """Account one read of ``row`` by ``reader_rank`` (called identically on EVERY rank) and return
+    the handshake the reader must perform -- ``None`` for same-rank reads or on other ranks."""
+    from ..ops import RowSync
+    from ..parallel import runtime as prt
+    if not prt.active() or row.rank == reader_rank:
+        return None
+    row.remote_reads += 1
+    if reader_rank != prt.rank():
+        return None
+    done = row.flag_done
+    if isinstance(done, tuple):           # CPU: one done slot per reader rank
+        done = (done[0], done[1] + reader_rank)
+    return RowSync(row.flag_ready, row.gen, done)
+
+
+def publish(row: Row, mine: bool) -> None:
+    """After a write to a shared row on the CURRENT stream: bump the generation everywhere and,
+    on the owner, publish it to the readers of other ranks."""
+    from ..parallel import runtime as prt
+    if not prt.active():
+        return
+    row.gen += 1
+    if not mine or not row.flag_ready:
+        return
+    if isinstance(row.flag_ready, tuple):
+        arr, i = row.flag_ready
+        arr[i] = row.gen
+    else:
+        from ..ops.native import native
+        native().flag_signal(row.flag_ready, row.gen)
+
+
+def wait_remote_readers(row: Row) -> None:
+    """Owner only, before re-writing a shared row on the CURRENT stream: wait until every read by
+    another rank has been acknowledged."""
+    from ..parallel import runtime as prt
+    if not prt.active() or row.remote_reads == 0 or not row.flag_done:
+        return
+    if row.remote_reads == getattr(row, "_acked", 0):
+        return
+    if isinstance(row.flag_done, tuple):
+        import time
+        arr, i = row.flag_done
+        t0 = time.monotonic()
+        while int(arr[i:i + prt.world()].sum()) < row.remote_reads:
+            if time.monotonic() - t0 > 120:
+                raise TimeoutError("remote readers never acknowledged row %d" % row.index)
+            time.sleep(0)
+    else:
+        from ..ops.native import native
+        native().flag_wait(row.flag_done, row.remote_reads)
+    row._acked = row.remote_reads
 
 
 # --------------------------------------------------------------------------------------

@@ -31,6 +31,7 @@ from ..core import CreateModelMode
 from ..engine import arena as _arena
 from ..engine import rng as _rng
 from ..engine.flat import FlatLayout
+from ..parallel import runtime as _prt
 from ..ops import metrics as _metrics
 from . import TorchModel
 from .nn import AdaLine
@@ -81,6 +82,20 @@ def _resolved(d: Dict[str, float]) -> PendingEval:
     return p
 
 
+class _NotMineEval(PendingEval):
+    """Evaluation computed by another rank (merged later by ``runtime.share_metrics``)."""
+
+    def __init__(self) -> None:
+        super().__init__(lambda: None)
+
+    def result(self) -> None:   # type: ignore[override]
+        return None
+
+
+_NOT_MINE = _NotMineEval()
+FUSE_MERGE_UPDATE = True                # fold the pairwise merge into the local-update kernel
+
+
 # --------------------------------------------------------------------------------------
 # base class
 # --------------------------------------------------------------------------------------
@@ -129,6 +144,8 @@ class ModelHandler(Sizeable, ABC):
             self.n_updates = copy.copy(recv_model.n_updates)
             self._update(data)
         elif mode == CreateModelMode.MERGE_UPDATE:
+            if not (args or kwargs) and self._merge_update_fused(recv_model, data):
+                return
             self._merge(recv_model, *args, **kwargs)
             self._update(data)
         elif mode == CreateModelMode.UPDATE_MERGE:
@@ -141,6 +158,10 @@ class ModelHandler(Sizeable, ABC):
             self._adopt(recv_model)
         else:
             raise ValueError("Unknown create model mode %s" % str(mode))
+
+    def _merge_update_fused(self, recv_model: Any, data: Any) -> bool:
+        """Hook: do merge + local update as ONE device launch; False = not available."""
+        return False
 
     def evaluate_async(self, *args, **kwargs) -> PendingEval:
         return _resolved(self.evaluate(*args, **kwargs))
@@ -307,18 +328,39 @@ class RowHandler(ModelHandler):
     def _stream(self):
         return _arena.stream_for(self.device, self.owner)
 
+    # -- multi-rank execution: every rank replays the bookkeeping, the owner's rank does the work --
+    def _rank(self) -> int:
+        return _prt.rank_of(self.owner) if _prt.active() else 0
+
+    def _mine(self) -> bool:
+        return (not _prt.active()) or _prt.rank_of(self.owner) == _prt.rank()
+
     def _ensure_row(self) -> _arena.Row:
         dev = self.device
         if self._row is None:
-            self._row = _arena.arena_for(dev, self._row_numel).alloc()
+            self._row = _arena.arena_for(dev, self._row_numel, self._rank()).alloc()
+            self._claim_row()
             self._on_new_row(None)
         elif self._row.tensor.device.type != dev.type:
             old = self._row
-            self._row = _arena.arena_for(dev, self._row_numel).alloc()
-            self._row.tensor.copy_(old.tensor)
+            self._row = _arena.arena_for(dev, self._row_numel, self._rank()).alloc()
+            self._claim_row()
+            if self._mine():
+                self._row.tensor.copy_(old.tensor)
             old.release()
             self._on_new_row(old)
         return self._row
+
+    def _claim_row(self) -> None:
+        """A recycled arena row becomes this handler's live row: order my stream after every
+        earlier user of the row (local streams through events, other ranks through ``done``)."""
+        row = self._row
+        if not self._mine() or self.device.type != "cuda" and not _prt.active():
+            return
+        s = self._stream()
+        with _arena.on_stream(s):
+            _arena.before_write(row, s if s is not None else _arena.current(self.device))
+            _arena.wait_remote_readers(row)
 
     def _on_new_row(self, old: Optional[_arena.Row]) -> None:
         """Hook: (re)bind views after the row moved."""
@@ -333,6 +375,8 @@ class RowHandler(ModelHandler):
 
     def refresh_inputs(self, data: Any) -> int:
         """Re-upload this node's inputs from pinned host memory on the node's stream."""
+        if not self._mine():
+            return 0
         with _arena.on_stream(self._stream()):
             return refresh_device_copy(data, self.device)
 
@@ -345,17 +389,25 @@ class RowHandler(ModelHandler):
         return new
 
     def _snapshot(self) -> "RowHandler":
-        """Light clone: new arena row filled by a D2D copy on the owner's stream."""
+        """Light clone: new arena row filled by a D2D copy on the owner's stream (and, with several
+        ranks, published to the other GPUs through the row's ``ready`` flag)."""
         src = self._ensure_row()
         new = self._clone_shell()
         new._is_snapshot = True
         new._after_clone(self, light=True)
-        dst = _arena.arena_for(self.device, self._row_numel).alloc()
-        s = self._stream()
-        with _arena.on_stream(s):
-            _arena.before_write(dst, s if s is not None else _arena.current(self.device))
-            ops.snapshot(dst.tensor, src.tensor)
-            _arena.after_write(dst, s if s is not None else _arena.current(self.device), shared=True)
+        dst = _arena.arena_for(self.device, self._row_numel, self._rank()).alloc()
+        mine = self._mine()
+        if mine:
+            s = self._stream()
+            with _arena.on_stream(s):
+                cur = s if s is not None else _arena.current(self.device)
+                _arena.before_write(dst, cur)
+                _arena.wait_remote_readers(dst)
+                ops.snapshot(dst.tensor, src.tensor)
+                _arena.after_write(dst, cur, shared=True)
+                _arena.publish(dst, True)
+        else:
+            _arena.publish(dst, False)
         new._row = dst
         return new
 
@@ -365,9 +417,10 @@ class RowHandler(ModelHandler):
         new._after_clone(self, light=False)
         if self._row is not None:
             dst = new._ensure_row()
-            s = self._stream()
-            with _arena.on_stream(s):
-                ops.snapshot(dst.tensor, self._row.tensor)
+            if self._mine():
+                s = self._stream()
+                with _arena.on_stream(s):
+                    ops.snapshot(dst.tensor, self._row.tensor)
         return new
 
     def __deepcopy__(self, memo) -> "RowHandler":
@@ -384,19 +437,33 @@ class RowHandler(ModelHandler):
             self._row = None
 
     # -- generic row operations ----------------------------------------------------------
-    def _src_row(self, other: "RowHandler", s) -> torch.Tensor:
-        orow = other._ensure_row()
-        _arena.before_read(orow, s if s is not None else _arena.current(self.device))
-        return orow.tensor
+    def _pull(self, others: Any, fn: Callable) -> None:
+        """Read the rows of ``others`` (one handler or a list) into an op on MY row.
 
-    def _done_with(self, other: "RowHandler", s) -> None:
-        _arena.after_read(other._row, s if s is not None else _arena.current(self.device))
-
-    def _adopt(self, other: "RowHandler") -> None:
+        ``fn(srcs, syncs)`` receives the source tensors (peer-mapped when a row lives on another
+        GPU) and the cross-rank handshakes (``None`` for local rows) and runs on this handler's
+        stream.  The read bookkeeping is replayed on every rank; only the owner of ``self``
+        executes ``fn``."""
+        single = not isinstance(others, (list, tuple))
+        hs = [others] if single else list(others)
+        rows = [o._ensure_row() for o in hs]
+        my_rank = self._rank()
+        syncs = [_arena.read_sync(r, my_rank) for r in rows]
+        if not self._mine():
+            return
         s = self._stream()
         with _arena.on_stream(s):
-            ops.merge_pair(self.row, self._src_row(other, s), 0.0, 1.0)
-            self._done_with(other, s)
+            cur = s if s is not None else _arena.current(self.device)
+            local = [r for r in rows if (not _prt.active()) or r.rank == my_rank]
+            for r in local:
+                _arena.before_read(r, cur)
+            srcs = [r.tensor for r in rows]
+            fn(srcs[0] if single else srcs, syncs[0] if single else syncs)
+            for r in local:
+                _arena.after_read(r, cur)
+
+    def _adopt(self, other: "RowHandler") -> None:
+        self._pull(other, lambda src, sync: ops.merge_pair(self.row, src, 0.0, 1.0, sync=sync))
         self._version += 1
 
     def _scratch_copy(self, other: "RowHandler") -> "RowHandler":
@@ -404,19 +471,13 @@ class RowHandler(ModelHandler):
         tmp._is_snapshot = True
         tmp._after_clone(other, light=True)
         tmp.owner = self.owner
-        s = self._stream()
-        with _arena.on_stream(s):
-            tmp._ensure_row()
-            ops.snapshot(tmp._row.tensor, self._src_row(other, s))
-            self._done_with(other, s)
+        tmp._ensure_row()
+        self._pull(other, lambda src, sync: ops.snapshot(tmp._row.tensor, src, sync))
         return tmp
 
     def _weighted_merge(self, other: "RowHandler", w_self: float, w_other: float,
                         lo: int = 0, hi: Optional[int] = None) -> None:
-        s = self._stream()
-        with _arena.on_stream(s):
-            ops.merge_pair(self.row, self._src_row(other, s), w_self, w_other, lo, hi)
-            self._done_with(other, s)
+        self._pull(other, lambda src, sync: ops.merge_pair(self.row, src, w_self, w_other, lo, hi, sync))
         self._version += 1
 
     # -- (de)serialisation: rows travel as CPU tensors ------------------------------------
@@ -560,7 +621,7 @@ class TorchModelHandler(RowHandler):
             self._grad_bound = False
 
     def _on_new_row(self, old) -> None:
-        if old is None and not self._is_snapshot:
+        if old is None and not self._is_snapshot and self._mine():
             # first materialisation of a live handler: start from the template's values
             src = self._module if self._module is not None else self._proto
             self.layout.gather(src, self._row.tensor)
@@ -593,10 +654,18 @@ class TorchModelHandler(RowHandler):
 
     # -- API --------------------------------------------------------------------------------
     def init(self) -> None:
-        mod = self.model
-        with _arena.on_stream(self._stream()):
-            mod.init_weights()
+        """Initialise the weights.  The random stream is keyed by (base seed, owner), so a node's
+        initial model does not depend on how nodes are placed on GPUs."""
         self._version += 1
+        if not self._mine():
+            self._ensure_row()
+            return
+        mod = self.model
+        dev = self.device
+        with _arena.on_stream(self._stream()):
+            with torch.random.fork_rng(devices=[dev] if dev.type == "cuda" else []):
+                torch.manual_seed(_rng.derive(0x1217, self.owner if self.owner >= 0 else 0))
+                mod.init_weights()
 
     def get_size(self) -> int:
         return self._proto.get_size()
@@ -613,18 +682,31 @@ class TorchModelHandler(RowHandler):
     def _count_steps(self, steps: int) -> None:
         self.n_updates += steps
 
-    def _update(self, data: Tuple[torch.Tensor, torch.Tensor]) -> None:
+    def _n_local_steps(self, data: Any) -> int:
+        return ops.torch_ref.n_steps(int(data[0].shape[0]), self.batch_size, self.local_epochs)
+
+    def _update(self, data: Tuple[torch.Tensor, torch.Tensor], merge_from: Any = None) -> None:
+        self._version += 1
+        if not self._mine():       # another rank trains this node: replay the bookkeeping only
+            self._ensure_row()
+            self._next_key()
+            if self._fused:
+                self._count_steps(self._n_local_steps(data))
+            else:
+                for _ in range(self._n_local_steps(data)):
+                    self._pre_step()
+                self._count_steps(self._n_local_steps(data))
+            return
         x, y = self._to_device(data)
         s = self._stream()
         with _arena.on_stream(s):
             if self._fused:
-                steps = self._update_fused(x, y)
+                steps = self._update_fused(x, y, merge_from)
             else:
                 steps = self._update_generic(x, y)
         self._count_steps(steps)
-        self._version += 1
 
-    def _update_fused(self, x: torch.Tensor, y: torch.Tensor) -> int:
+    def _update_fused(self, x: torch.Tensor, y: torch.Tensor, merge_from: Any = None) -> int:
         fam, dims = self._family
         lr = float(self.optimizer_params.get("lr", 1e-3))
         wd = float(self.optimizer_params.get("weight_decay", 0.0))
@@ -632,7 +714,34 @@ class TorchModelHandler(RowHandler):
         if x.dim() > 2:
             x = x.reshape(x.shape[0], -1)
         return fn(self.row, x, y, dims, self.batch_size, self.local_epochs, lr, wd,
-                  self._next_key(), self._elem_scale())
+                  self._next_key(), self._elem_scale(), merge_from=merge_from)
+
+    # -- fused MERGE_UPDATE: the merge rides on the training kernel's weight load ------------
+    def _fused_merge_weights(self, other: Any) -> Optional[Tuple[float, float]]:
+        """``(w_self, w_other)`` of a pairwise merge that may be folded into the local-update
+        kernel, or ``None`` when this handler's merge is not a plain weighted pair merge."""
+        if type(self)._merge is not TorchModelHandler._merge:
+            return None
+        return (0.5, 0.5) if isinstance(other, TorchModelHandler) else None
+
+    def _merge_update_fused(self, recv_model: Any, data: Any) -> bool:
+        if not (self._fused and FUSE_MERGE_UPDATE) or self.layout.int_buffers:
+            return False
+        w = self._fused_merge_weights(recv_model)
+        if w is None:
+            return False
+        new_age = max(self.n_updates, recv_model.n_updates)
+
+        def run(src, sync):
+            self.n_updates = new_age
+            self._update(data, merge_from=(src, w[0], w[1], sync))
+        if self._mine():
+            self._pull(recv_model, run)
+        else:
+            self._pull(recv_model, run)     # bookkeeping of the read ...
+            self.n_updates = new_age
+            self._update(data)              # ... and of the update
+        return True
 
     def _ensure_grad(self) -> torch.Tensor:
         mod = self.model
@@ -729,18 +838,15 @@ class TorchModelHandler(RowHandler):
         self._merge_int_buffers(other_model_handler)
 
     def _kway_merge(self, others: Sequence["TorchModelHandler"], weights: Sequence[float]) -> None:
-        s = self._stream()
-        with _arena.on_stream(s):
-            srcs = [self._src_row(o, s) for o in others]
-            ops.merge_kway(self.row, srcs, weights)
-            for o in others:
-                self._done_with(o, s)
+        self._pull(list(others), lambda srcs, syncs: ops.merge_kway(self.row, srcs, weights, syncs))
         self._version += 1
 
     def _merge_int_buffers(self, other: Any) -> None:
         """Integer buffers (BN ``num_batches_tracked``) are combined with ``max``."""
         if not self.layout.int_buffers:
             return
+        if _prt.active():
+            raise NotImplementedError("models with integer buffers (BatchNorm) are single-rank only")
         others = [other] if isinstance(other, TorchModelHandler) else list(other)
         mine = dict(self.model.named_buffers())
         for o in others:
@@ -782,6 +888,8 @@ class TorchModelHandler(RowHandler):
 
     def evaluate_async(self, data: Tuple[torch.Tensor, torch.Tensor]) -> PendingEval:
         """accuracy / macro precision / recall / F1 (+AUC for 2 outputs) -- ref ``:282-334``."""
+        if not self._mine():
+            return _NOT_MINE
         x, y = self._to_device(data)
         if y.dim() > 1:
             y = torch.argmax(y, dim=-1)
@@ -866,7 +974,7 @@ class AdaLineHandler(RowHandler):
             self._version += 1
 
     def _on_new_row(self, old) -> None:
-        if old is None and not self._is_snapshot:
+        if old is None and not self._is_snapshot and self._mine():
             self._row.tensor.zero_()
             self._row.tensor[:self.dim].copy_(self._module.model.detach().to(self._row.tensor.device))
 
@@ -880,8 +988,11 @@ class AdaLineHandler(RowHandler):
         return st
 
     def init(self) -> None:
-        self.model.init_weights()
         self._version += 1
+        if not self._mine():
+            self._ensure_row()
+            return
+        self.model.init_weights()
 
     def get_size(self) -> int:
         return self.dim
@@ -890,17 +1001,22 @@ class AdaLineHandler(RowHandler):
         return self.row[:self.dim]
 
     def _update(self, data: Tuple[torch.Tensor, torch.Tensor]) -> None:
+        self.n_updates += len(data[1])
+        self._version += 1
+        if not self._mine():
+            self._ensure_row()
+            return
         x, y = self._to_device(data)
         with _arena.on_stream(self._stream()):
             ops.adaline_update(self._w(), x, y.to(torch.float32), self.learning_rate)
-        self.n_updates += len(y)
-        self._version += 1
 
     def _merge(self, other_model_handler: "AdaLineHandler") -> None:
         self._weighted_merge(other_model_handler, 0.5, 0.5)
         self.n_updates = max(self.n_updates, other_model_handler.n_updates)
 
     def evaluate_async(self, data: Tuple[torch.Tensor, torch.Tensor]) -> PendingEval:
+        if not self._mine():
+            return _NOT_MINE
         x, y = self._to_device(data)
         with _arena.on_stream(self._stream()):
             scores = x.float() @ self._w()
@@ -924,11 +1040,15 @@ class PegasosHandler(AdaLineHandler):
     """Pegasos SVM steps, one per local sample (ref ``handler.py:394-423``)."""
 
     def _update(self, data: Tuple[torch.Tensor, torch.Tensor]) -> None:
+        self._version += 1
+        if not self._mine():
+            self._ensure_row()
+            self.n_updates = int(self.n_updates) + len(data[1])
+            return
         x, y = self._to_device(data)
         with _arena.on_stream(self._stream()):
             self.n_updates = ops.pegasos_update(self._w(), x, y.to(torch.float32),
                                                 self.learning_rate, int(self.n_updates))
-        self._version += 1
 
 
 # --------------------------------------------------------------------------------------
@@ -951,11 +1071,8 @@ class SamplingTMH(TorchModelHandler):
     def _merge(self, other_model_handler: "SamplingTMH", sample: Any) -> None:
         if isinstance(sample, dict):
             sample = sample_dict_to_flat(sample, self._proto)
-        s = self._stream()
-        with _arena.on_stream(s):
-            idx = sample.to(self.device)
-            ops.merge_indexed(self.row, self._src_row(other_model_handler, s), idx, 0.5, 0.5)
-            self._done_with(other_model_handler, s)
+        self._pull(other_model_handler, lambda src, sync: ops.merge_indexed(
+            self.row, src, sample.to(self.device), 0.5, 0.5, sync))
         self._version += 1
 
     def __call__(self, recv_model: Any, data: Any, sample: Any) -> None:
@@ -1027,13 +1144,12 @@ class PartitionedTMH(TorchModelHandler):
         pid = id_part % self.tm_partition.n_parts
         a, b = int(self.n_updates[pid]), int(other_model_handler.n_updates[pid])
         w1, w2 = TorchModelPartition.mixing_weights((a, b))
-        seg = self._seg_dev.get(pid)
-        if seg is None or seg.device != self.row.device:
-            seg = self._seg_dev[pid] = self.tm_partition.segments(pid).to(self.row.device)
-        s = self._stream()
-        with _arena.on_stream(s):
-            ops.merge_segments(self.row, self._src_row(other_model_handler, s), seg, w1, w2)
-            self._done_with(other_model_handler, s)
+        def run(src, sync):
+            seg = self._seg_dev.get(pid)
+            if seg is None or seg.device != self.row.device:
+                seg = self._seg_dev[pid] = self.tm_partition.segments(pid).to(self.row.device)
+            ops.merge_segments(self.row, src, seg, w1, w2, sync)
+        self._pull(other_model_handler, run)
         self.n_updates[pid] = max(a, b)
         self._version += 1
 
@@ -1106,6 +1222,17 @@ class LimitedMergeMixin:
 
 
 class LimitedMergeTMH(LimitedMergeMixin, TorchModelHandler):
+    def _fused_merge_weights(self, other: Any) -> Optional[Tuple[float, float]]:
+        if not isinstance(other, TorchModelHandler):
+            return None
+        a, b = self.n_updates, other.n_updates
+        if a > b + self.L:
+            return (1.0, 0.0)
+        if b > a + self.L:
+            return (0.0, 1.0)
+        tot = a + b
+        return (0.5, 0.5) if tot == 0 else (a / tot, b / tot)
+
     def __init__(self, net: TorchModel, optimizer: Any, optimizer_params: Dict[str, Any],
                  criterion: Callable, local_epochs: int = 1, batch_size: int = 32,
                  create_model_mode: CreateModelMode = CreateModelMode.MERGE_UPDATE,
@@ -1163,15 +1290,23 @@ class MFModelHandler(RowHandler):
 
     def init(self, r_min: int = 1, r_max: int = 5) -> None:
         mul = float(np.sqrt((r_max - r_min) / self.k))
+        self._version += 1
+        if not self._mine():
+            self._ensure_row()
+            return
         X, b, Y, c = self._parts()
         gen = torch.Generator().manual_seed(_rng.derive(0x3F, max(self.owner, 0)))
         X.copy_(torch.rand(self.k, generator=gen) * mul)
         Y.copy_(torch.rand(self.n_items, self.k, generator=gen) * mul)
         b.fill_(r_min / 2.0)
         c.fill_(r_min / 2.0)
-        self._version += 1
 
     def _update(self, data: Any) -> None:
+        if not self._mine():
+            self._ensure_row()
+            self.n_updates += len(data)
+            self._version += 1
+            return
         ratings = self._to_device(data)
         if isinstance(ratings, (list, tuple)):
             ratings = torch.as_tensor(np.asarray(ratings), dtype=torch.float32, device=self.device)
@@ -1190,6 +1325,8 @@ class MFModelHandler(RowHandler):
         self._weighted_merge(other_model_handler, a / den, b / den, 0, self._n_shared)
 
     def evaluate(self, ratings: Any) -> Dict[str, float]:
+        if not self._mine():
+            return None
         r = self._to_device(ratings)
         if not isinstance(r, torch.Tensor):
             r = torch.as_tensor(np.asarray(r), dtype=torch.float32, device=self.device)
@@ -1232,10 +1369,19 @@ class KMeansHandler(RowHandler):
         self._version += 1
 
     def init(self) -> None:
+        if not self._mine():
+            self._ensure_row()
+            self._version += 1
+            return
         gen = torch.Generator().manual_seed(_rng.derive(0x4B, max(self.owner, 0)))
         self.model = torch.rand(self.k, self.dim, generator=gen)
 
     def _update(self, data: Tuple[torch.Tensor, Any]) -> None:
+        if not self._mine():
+            self._ensure_row()
+            self.n_updates += 1
+            self._version += 1
+            return
         x, _ = self._to_device(data)
         with _arena.on_stream(self._stream()):
             ops.kmeans_update(self.model, x.float().reshape(-1, self.dim), self.alpha)
@@ -1252,17 +1398,23 @@ class KMeansHandler(RowHandler):
             self._weighted_merge(other_model_handler, 0.5, 0.5)
             return
         from scipy.optimize import linear_sum_assignment
-        s = self._stream()
-        with _arena.on_stream(s):
-            theirs = self._src_row(other_model_handler, s)[:self.k * self.dim].view(self.k, self.dim)
+
+        def run(src, sync):
+            if sync is not None:     # cross-rank: stage the peer's centroids with the handshake
+                staged = torch.empty_like(self.row)
+                ops.snapshot(staged, src, sync)
+                src = staged
+            theirs = src[:self.k * self.dim].view(self.k, self.dim)
             cost = torch.cdist(self.model, theirs).cpu().numpy()
             cols = linear_sum_assignment(cost)[1]
             perm = torch.as_tensor(cols, device=self.row.device)
             self.model.copy_((self.model + theirs[perm]) / 2)
-            self._done_with(other_model_handler, s)
+        self._pull(other_model_handler, run)
         self._version += 1
 
     def evaluate(self, data: Tuple[torch.Tensor, torch.Tensor]) -> Dict[str, float]:
+        if not self._mine():
+            return None
         X, y = self._to_device(data)
         with _arena.on_stream(self._stream()):
             pred = ops.kmeans_assign(self.model, X.float().reshape(-1, self.dim))

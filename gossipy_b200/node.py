@@ -303,6 +303,10 @@ class PENSNode(GossipNode):
         if msg.type != MessageType.PUSH:
             LOG.warning("PENSNode only supports PUSH protocol.")
         key = msg.value[0]
+        from .parallel import runtime as _prt
+        if _prt.active():
+            raise NotImplementedError("PENSNode scores received models on the receiver; run it on a "
+                                      "single rank (its peer selection depends on device results)")
         if self.step != 1:
             recv = CACHE.pop(key)
             self.model_handler(recv, self.data[0])

@@ -6,11 +6,18 @@
 * tensors on ``cpu`` -> the fp32 PyTorch reference implementations in :mod:`.torch_ref`
   (also the oracle the kernels are tested against).
 
+Cross-rank reads.  Every op that reads a *source* row accepts ``sync``: a :class:`RowSync`
+describing the handshake with the rank that owns the row (see ``parallel/runtime.py``).  On CUDA
+the handshake is fused into the kernel (spin on the owner's ``ready`` flag before the first peer
+load, one ``red.release.sys`` on its ``done`` counter after the last); on CPU (shared-memory
+arenas, ``gloo`` plumbing runs) it is a host spin on the same flags.
+
 ``launch_count`` counts native kernel launches (reported by ``bench.py`` as ``gpu_launches``).
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence, Tuple
+import time
+from typing import Any, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -19,6 +26,41 @@ from .native import native, native_available, require_native
 
 launch_count = 0
 FORCE_TORCH = False  # tests flip this to run the oracle on GPU tensors
+
+
+class RowSync:
+    """Handshake with the owner of a source row: wait ``ready >= gen``, then ``done += 1``.
+
+    ``ready`` / ``done`` are device addresses (CUDA) or ``(int32 numpy array, index)`` pairs
+    (CPU shared memory)."""
+
+    __slots__ = ("ready", "gen", "done")
+
+    def __init__(self, ready: Any, gen: int, done: Any) -> None:
+        self.ready, self.gen, self.done = ready, int(gen), done
+
+    def as_tuple(self) -> Tuple[int, int, int]:
+        return (int(self.ready), self.gen, int(self.done))
+
+    # CPU side -----------------------------------------------------------------------------
+    def host_wait(self, timeout: float = 120.0) -> None:
+        arr, i = self.ready
+        t0 = time.monotonic()
+        while int(arr[i]) - self.gen < 0:
+            if time.monotonic() - t0 > timeout:
+                raise TimeoutError("peer row was never published (gen %d, flag %d)" % (self.gen, int(arr[i])))
+            time.sleep(0)
+
+    def host_done(self) -> None:
+        host_flag_add(self.done, 1)
+
+
+def host_flag_add(flag: Any, value: int) -> None:
+    """Atomic-enough increment of a shared-memory counter (each counter has ONE writer at a time in
+    the replicated schedule: reads of a row by one rank are serialised by that rank's host loop;
+    different ranks use a lock file-free add via numpy on separate counters)."""
+    arr, i = flag
+    arr[i] += value
 
 
 def _use_native(t: torch.Tensor) -> bool:
@@ -33,45 +75,70 @@ def _count(n: int = 1) -> None:
     launch_count += n
 
 
-def merge_pair(dst, src, w_dst: float, w_src: float, lo: int = 0, hi: Optional[int] = None) -> None:
+def _st(sync: Optional[RowSync]):
+    return None if sync is None else sync.as_tuple()
+
+
+def merge_pair(dst, src, w_dst: float, w_src: float, lo: int = 0, hi: Optional[int] = None,
+               sync: Optional[RowSync] = None) -> None:
     if _use_native(dst):
         hi_ = dst.numel() if hi is None else hi
-        native().merge_pair(dst, src, float(w_dst), float(w_src), int(lo), int(hi_))
+        native().merge_pair(dst, src, float(w_dst), float(w_src), int(lo), int(hi_), _st(sync))
         _count()
     else:
+        if sync is not None:
+            sync.host_wait()
         torch_ref.merge_pair(dst, src, w_dst, w_src, lo, hi)
+        if sync is not None:
+            sync.host_done()
 
 
-def merge_segments(dst, src, segments, w_dst: float, w_src: float) -> None:
+def merge_segments(dst, src, segments, w_dst: float, w_src: float,
+                   sync: Optional[RowSync] = None) -> None:
     if _use_native(dst):
-        native().merge_segments(dst, src, segments, float(w_dst), float(w_src))
+        native().merge_segments(dst, src, segments, float(w_dst), float(w_src), _st(sync))
         _count()
     else:
+        if sync is not None:
+            sync.host_wait()
         torch_ref.merge_segments(dst, src, segments.cpu(), w_dst, w_src)
+        if sync is not None:
+            sync.host_done()
 
 
-def merge_indexed(dst, src, index, w_dst: float, w_src: float) -> None:
+def merge_indexed(dst, src, index, w_dst: float, w_src: float,
+                  sync: Optional[RowSync] = None) -> None:
     if _use_native(dst):
-        native().merge_indexed(dst, src, index, float(w_dst), float(w_src))
-        _count()
+        native().merge_indexed(dst, src, index, float(w_dst), float(w_src), _st(sync))
+        _count(2)
     else:
+        if sync is not None:
+            sync.host_wait()
         torch_ref.merge_indexed(dst, src, index, w_dst, w_src)
+        if sync is not None:
+            sync.host_done()
 
 
-def merge_kway(dst, srcs: Sequence[torch.Tensor], weights: Sequence[float]) -> None:
+def merge_kway(dst, srcs: Sequence[torch.Tensor], weights: Sequence[float],
+               syncs: Optional[Sequence[Optional[RowSync]]] = None) -> None:
     if _use_native(dst):
-        native().merge_kway(dst, list(srcs), [float(w) for w in weights])
-        _count()
+        st = None
+        if syncs is not None and any(s is not None for s in syncs):
+            st = [(0, 0, 0) if s is None else s.as_tuple() for s in syncs]
+        native().merge_kway(dst, list(srcs), [float(w) for w in weights], st)
+        _count(max(1, (len(srcs) + 31) // 32))
     else:
+        for s in (syncs or ()):
+            if s is not None:
+                s.host_wait()
         torch_ref.merge_kway(dst, srcs, weights)
+        for s in (syncs or ()):
+            if s is not None:
+                s.host_done()
 
 
-def snapshot(dst, src) -> None:
-    if _use_native(dst):
-        native().merge_pair(dst, src, 0.0, 1.0, 0, dst.numel())
-        _count()
-    else:
-        torch_ref.snapshot(dst, src)
+def snapshot(dst, src, sync: Optional[RowSync] = None) -> None:
+    merge_pair(dst, src, 0.0, 1.0, 0, dst.numel(), sync)
 
 
 def sgd_step(p, g, n, lr, weight_decay=0.0, momentum=0.0, buf=None, dampening=0.0,
@@ -95,17 +162,37 @@ def adam_step(p, g, n, m, v, step, lr, beta1, beta2, eps, weight_decay=0.0,
         torch_ref.adam_step(p, g, n, m, v, step, lr, beta1, beta2, eps, weight_decay, decoupled)
 
 
+MergeFrom = Tuple[torch.Tensor, float, float, Optional[RowSync]]   # (peer row, w_self, w_peer, sync)
+TRAIN_IMPL = ""   # "", "cluster" or "tc": process-wide override of the MLP training kernel choice
+
+
+def _cpu_premerge(row, merge_from: Optional[MergeFrom]) -> None:
+    if merge_from is not None:
+        peer, ws, wp, sync = merge_from
+        if sync is not None:
+            sync.host_wait()
+        torch_ref.merge_pair(row, peer, ws, wp, 0, min(row.numel(), peer.numel()))
+        if sync is not None:
+            sync.host_done()
+
+
 def mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, key,
-               elem_scale_ages=None, impl: Optional[str] = None) -> int:
-    """Fused local update of a 1-hidden-layer ReLU MLP; returns the number of SGD steps."""
+               elem_scale_ages=None, impl: Optional[str] = None,
+               merge_from: Optional[MergeFrom] = None) -> int:
+    """Fused local update of a 1-hidden-layer ReLU MLP; returns the number of SGD steps.
+
+    ``merge_from = (peer_row, w_self, w_peer, sync)`` fuses the preceding merge into the same
+    launch (MERGE_UPDATE): training starts from ``w_self*row + w_peer*peer_row``."""
     if _use_native(row):
+        peer, ws, wp, sync = merge_from if merge_from is not None else (None, 1.0, 0.0, None)
         n = native().mlp1_train(row, X, y, tuple(int(d) for d in dims), int(batch_size),
                                 int(local_epochs), float(lr), float(weight_decay), int(key),
                                 None if elem_scale_ages is None else elem_scale_ages[0],
                                 None if elem_scale_ages is None else elem_scale_ages[1],
-                                impl or "")
+                                impl or TRAIN_IMPL, peer, float(ws), float(wp), _st(sync))
         _count()
         return n
+    _cpu_premerge(row, merge_from)
     return torch_ref.mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, key,
                                 elem_scale_ages)
 
@@ -121,14 +208,17 @@ def mlp1_eval(row, X, y, dims, n_classes: int, X_lp=None) -> torch.Tensor:
 
 
 def logreg_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, key,
-                 elem_scale_ages=None) -> int:
+                 elem_scale_ages=None, merge_from: Optional[MergeFrom] = None) -> int:
     if _use_native(row):
+        peer, ws, wp, sync = merge_from if merge_from is not None else (None, 1.0, 0.0, None)
         n = native().logreg_train(row, X, y, tuple(int(d) for d in dims), int(batch_size),
                                   int(local_epochs), float(lr), float(weight_decay), int(key),
                                   None if elem_scale_ages is None else elem_scale_ages[0],
-                                  None if elem_scale_ages is None else elem_scale_ages[1])
+                                  None if elem_scale_ages is None else elem_scale_ages[1],
+                                  peer, float(ws), float(wp), _st(sync))
         _count()
         return n
+    _cpu_premerge(row, merge_from)
     return torch_ref.logreg_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, key,
                                   elem_scale_ages)
 
@@ -160,7 +250,7 @@ def pegasos_update(w, X, y, lam, n_updates) -> int:
 def kmeans_update(C, X, alpha) -> None:
     if _use_native(C):
         native().kmeans_update(C, X, float(alpha))
-        _count()
+        _count(2)
     else:
         torch_ref.kmeans_update(C, X, alpha)
 

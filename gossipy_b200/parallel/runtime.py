@@ -31,11 +31,11 @@ import torch
 from .. import GlobalSettings, LOG
 
 _state: Dict[str, Any] = {"rank": 0, "world": 1, "n_nodes": None, "transport": "none",
-                          "placement": None}
+                          "placement": None, "arena_capacity": None, "tag": "0"}
 
 
 def init(rank: Optional[int] = None, world: Optional[int] = None,
-         transport: Optional[str] = None) -> None:
+         transport: Optional[str] = None, arena_capacity: Optional[int] = None) -> None:
     """Activate multi-rank execution.  ``torch.distributed`` must already be initialised."""
     import torch.distributed as dist
     if rank is None:
@@ -47,15 +47,30 @@ def init(rank: Optional[int] = None, world: Optional[int] = None,
     if transport is None:
         transport = os.environ.get("GOSSIPY_B200_TRANSPORT", "")
     if not transport:
-        transport = "p2p" if GlobalSettings().is_cuda() else "sendrecv"
+        transport = "p2p"
     _state["transport"] = transport if world > 1 else "none"
+    _state["arena_capacity"] = arena_capacity
     if world > 1:
         assert dist.is_initialized(), "initialise torch.distributed before parallel.runtime.init"
+        _state["inits"] = _state.get("inits", 0) + 1
+        tag = ["%s_%d_%d" % (os.environ.get("MASTER_PORT", "0"), os.getpid(), _state["inits"])]
+        dist.broadcast_object_list(tag, src=0)
+        _state["tag"] = tag[0]
 
 
 def shutdown() -> None:
-    _state.update(rank=0, world=1, n_nodes=None, transport="none", placement=None)
+    from ..engine import arena
+    arena.reset_arenas()
+    _state.update(rank=0, world=1, n_nodes=None, transport="none", placement=None, arena_capacity=None)
     GlobalSettings().set_topology(0, 1)
+
+
+def arena_capacity() -> Optional[int]:
+    return _state["arena_capacity"]
+
+
+def session_tag() -> str:
+    return _state["tag"]
 
 
 def active() -> bool:

@@ -192,6 +192,9 @@ class GossipSimulator(SimulationEventSender):
         if seed is not None:
             _rng.set_base_seed(seed)
         self.initialized = True
+        from .parallel import runtime as _prt
+        if _prt.active():
+            _prt.set_num_nodes(self.n_nodes)
         for node in self.nodes.values():
             node.init_model()
 
@@ -280,10 +283,11 @@ class GossipSimulator(SimulationEventSender):
             eval_set = self.data_dispatcher.get_eval_set()
             glob = [n.evaluate_async(eval_set) for n in sample]
         # everything is enqueued; only now touch the host (one wait per round, not per node)
+        from .parallel import runtime as _prt
         if local:
-            self.notify_evaluation(t, True, [p.result() for p in local])
+            self.notify_evaluation(t, True, _prt.share_metrics([p.result() for p in local]))
         if glob:
-            self.notify_evaluation(t, False, [p.result() for p in glob])
+            self.notify_evaluation(t, False, _prt.share_metrics([p.result() for p in glob]))
 
     def _stream_round_inputs(self) -> None:
         """Fresh inputs for the coming round: host (pinned) -> device, async on each node's stream."""

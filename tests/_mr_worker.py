@@ -1,0 +1,135 @@
+"""Worker of tests/test_multirank.py: runs small simulations, single- or multi-rank, and prints one
+JSON line with per-round metrics, message counters and a checksum of every node's model."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+
+def build(kind, device):
+    import gossipy_b200 as g
+    from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork, UniformDelay
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import (LimitedMergeTMH, PartitionedTMH, PegasosHandler,
+                                            TorchModelHandler, WeightedTMH)
+    from gossipy_b200.model.nn import AdaLine, LogisticRegression, TorchMLP
+    from gossipy_b200.model.sampling import TorchModelPartition
+    from gossipy_b200.node import All2AllGossipNode, GossipNode, PartitioningBasedNode
+    from gossipy_b200.simul import All2AllGossipSimulator, GossipSimulator, SimulationReport
+    from gossipy_b200.core import UniformMixing
+    g.GlobalSettings().set_device(device)
+    g.set_seed(11)
+    start_args = ()
+    if kind == "pegasos":     # BASELINE config 1: main_ormandi_2013 shape, 8 nodes
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(800, 200)
+        ytr, yte = 2 * ytr - 1, 2 * yte - 1
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=8, eval_on_user=False)
+        proto = PegasosHandler(AdaLine(57), 0.01, CreateModelMode.MERGE_UPDATE)
+        nodes = GossipNode.generate(disp, StaticP2PNetwork(8), proto, 20, False)
+        sim = GossipSimulator(nodes, disp, 20, AntiEntropyProtocol.PUSH, drop_prob=.1, online_prob=.8,
+                              delay=UniformDelay(0, 3), sampling_eval=.5)
+    elif kind == "mlp_pushpull":
+        (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=4, eval_on_user=False)
+        proto = TorchModelHandler(TorchMLP(784, 10, (100,)), torch.optim.SGD, {"lr": .1},
+                                  torch.nn.CrossEntropyLoss(), batch_size=32)
+        nodes = GossipNode.generate(disp, StaticP2PNetwork(4), proto, 10, True)
+        sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH_PULL)
+    elif kind == "limited_pull":
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=6, eval_on_user=True)
+        proto = LimitedMergeTMH(LogisticRegression(57, 2), torch.optim.SGD, {"lr": 1., "weight_decay": .001},
+                                torch.nn.CrossEntropyLoss(), batch_size=16, age_diff_threshold=1)
+        nodes = GossipNode.generate(disp, StaticP2PNetwork(6), proto, 10, True)
+        sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PULL, delay=UniformDelay(0, 2))
+    elif kind == "partitioned":
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=6, eval_on_user=False)
+        net = LogisticRegression(57, 2)
+        proto = PartitionedTMH(net, TorchModelPartition(net, 4), torch.optim.SGD, {"lr": 1., "weight_decay": .001},
+                               torch.nn.CrossEntropyLoss(), batch_size=16, create_model_mode=CreateModelMode.UPDATE)
+        nodes = PartitioningBasedNode.generate(disp, StaticP2PNetwork(6), proto, 10, True)
+        sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
+    elif kind == "all2all":
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=4, eval_on_user=False)
+        net = StaticP2PNetwork(4)
+        proto = WeightedTMH(LogisticRegression(57, 2), torch.optim.SGD, {"lr": .1, "weight_decay": .01},
+                            torch.nn.CrossEntropyLoss(), batch_size=16)
+        nodes = All2AllGossipNode.generate(disp, net, proto, 10, True)
+        sim = All2AllGossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
+        start_args = (UniformMixing(net),)
+    else:
+        raise ValueError(kind)
+    sim.progress = False
+    rep = SimulationReport()
+    sim.add_receiver(rep)
+    return sim, rep, start_args
+
+
+def run(kind, device, rounds):
+    import gossipy_b200 as g
+    from gossipy_b200.parallel import runtime as prt
+    sim, rep, start_args = build(kind, device)
+    sim.init_nodes(seed=5)
+    sim.start(*start_args, rounds)
+    if device.startswith("cuda"):
+        torch.cuda.synchronize()
+    sums = {}
+    for i, node in sim.nodes.items():
+        h = node.model_handler
+        if h._mine():
+            r = h.row.detach().double().cpu()
+            sums[i] = [float(r.sum()), float((r * r).sum())]
+    if prt.active():
+        import torch.distributed as dist
+        allsums = [None] * prt.world()
+        dist.all_gather_object(allsums, sums)
+        sums = {k: v for d in allsums for k, v in d.items()}
+    ages = {i: np.asarray(n.model_handler.n_updates).tolist() for i, n in sim.nodes.items()}
+    return {"glob": rep.get_evaluation(False), "loc": rep.get_evaluation(True), "sent": rep._sent_messages,
+            "failed": rep._failed_messages, "size": rep._total_size,
+            "sums": {str(k): sums[k] for k in sorted(sums)}, "ages": {str(k): ages[k] for k in sorted(ages)},
+            "cache_left": len(g.CACHE)}
+
+
+def main():
+    kinds = sys.argv[1].split(",")
+    device = sys.argv[2]
+    rounds = int(sys.argv[3])
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        if device.startswith("cuda"):
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+            device = "cuda:%d" % torch.cuda.current_device()
+        dist.init_process_group("nccl" if device.startswith("cuda") else "gloo")
+    import gossipy_b200 as g
+    g.LOG.setLevel(50)
+    out = {}
+    for kind in kinds:
+        from gossipy_b200.parallel import runtime as prt
+        g.GlobalSettings().set_device(device)
+        if world > 1:
+            prt.init(rank, world)
+        out[kind] = run(kind, device, rounds)
+        g.CACHE.clear()
+        if world > 1:
+            prt.shutdown()
+    if rank == 0:
+        print("RESULT " + json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -285,3 +285,89 @@ def test_mlp1_train_tc_matches_oracle(dims, n, bs, ep, wd, lr):
     def loss(r):   # same learning signal: both results have the same training loss
         return float(torch.nn.functional.cross_entropy(ref.mlp1_logits(r, X, dims), y))
     assert loss(row) == pytest.approx(loss(want), rel=2e-2, abs=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused MERGE_UPDATE (merge folded into the training kernel's weight load) and the cross-GPU
+# ready/done handshake (exercised here with flags in local memory and two streams)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl,tol", [("cluster", 1e-6), ("tc", 5e-2)])
+def test_fused_merge_update_equals_merge_then_update(impl, tol):
+    ops, ref = _ops()
+    dims = (784, 100, 10)
+    X, y, row = _mlp_problem(200, *dims)
+    peer = _mlp_problem(200, *dims, seed=5)[2]
+    a, b = row.clone(), row.clone()
+    ops.merge_pair(a, peer, .25, .75)
+    s1 = ops.mlp1_train(a, X, y, dims, 32, 1, .1, 0., 0x1234, impl=impl)
+    s2 = ops.mlp1_train(b, X, y, dims, 32, 1, .1, 0., 0x1234, impl=impl, merge_from=(peer, .25, .75, None))
+    assert s1 == s2
+    if impl == "cluster":
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-6)
+    else:
+        moved = float((a - row).abs().max())
+        assert float((a - b).abs().max()) < tol * moved + 2e-4
+    # logistic regression flavour
+    gen = torch.Generator().manual_seed(0)
+    Xl = torch.randn(300, 57, generator=gen).cuda(); yl = (Xl[:, 0] > 0).long()
+    r0 = torch.zeros(128, device="cuda"); r0[:116] = torch.randn(116, generator=gen).cuda() * .1
+    pr = torch.zeros(128, device="cuda"); pr[:116] = torch.randn(116, generator=gen).cuda() * .1
+    a, b = r0.clone(), r0.clone()
+    ops.merge_pair(a, pr, .5, .5)
+    ops.logreg_train(a, Xl, yl, (57, 2), 32, 1, 1., .001, 5)
+    ops.logreg_train(b, Xl, yl, (57, 2), 32, 1, 1., .001, 5, merge_from=(pr, .5, .5, None))
+    torch.testing.assert_close(a[:116], b[:116], rtol=1e-5, atol=1e-6)
+
+
+def test_ready_done_handshake_orders_reader_after_writer():
+    """A reader launched FIRST spins on the row's ready flag until the writer (second stream, launched
+    later) has produced the data and published the generation; afterwards done == number of reads."""
+    from gossipy_b200.ops import RowSync
+    from gossipy_b200.ops.native import native
+    ops, ref = _ops()
+    nat = native()
+    n = 79520
+    flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ready, done = flags.data_ptr(), flags.data_ptr() + 4
+    src = torch.zeros(n, device="cuda")
+    dst = torch.ones(n, device="cuda")
+    kdst = torch.ones(n, device="cuda")
+    other = torch.full((n,), 3.0, device="cuda")
+    torch.cuda.synchronize()
+    reader, reader2, writer = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(reader):
+        ops.merge_pair(dst, src, .5, .5, sync=RowSync(ready, 1, done))          # would read zeros if unordered
+    with torch.cuda.stream(reader2):
+        ops.merge_kway(kdst, [src, other], [.5, .25, .25], [RowSync(ready, 1, done), None])
+    with torch.cuda.stream(writer):
+        torch.cuda._sleep(20_000_000)                                             # ~10 ms head start for the readers
+        src.fill_(5.0)
+        nat.flag_signal(ready, 1)
+    torch.cuda.synchronize()
+    assert float(dst.min()) == float(dst.max()) == 3.0
+    assert float(kdst.min()) == float(kdst.max()) == pytest.approx(.5 + 1.25 + .75)
+    assert flags.tolist() == [1, 2]
+    # owner side: wait for the acknowledgements, then recycle the row
+    with torch.cuda.stream(writer):
+        nat.flag_wait(done, 2)
+        src.zero_()
+    torch.cuda.synchronize()
+    # the same handshake inside the fused training kernels
+    dims = (784, 100, 10)
+    X, y, row = _mlp_problem(100, *dims)
+    peer = torch.zeros_like(row)
+    peer_val = _mlp_problem(100, *dims, seed=9)[2]
+    for impl in ("cluster", "tc"):
+        flags.zero_(); peer.zero_()
+        a, b = row.clone(), row.clone()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(reader):
+            ops.mlp1_train(a, X, y, dims, 32, 1, .1, 0., 7, impl=impl, merge_from=(peer, .5, .5, RowSync(ready, 1, done)))
+        with torch.cuda.stream(writer):
+            torch.cuda._sleep(10_000_000)
+            peer.copy_(peer_val)
+            nat.flag_signal(ready, 1)
+        torch.cuda.synchronize()
+        ops.mlp1_train(b, X, y, dims, 32, 1, .1, 0., 7, impl=impl, merge_from=(peer_val, .5, .5, None))
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+        assert flags.tolist() == [1, 1]

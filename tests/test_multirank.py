@@ -1,0 +1,69 @@
+"""One process per rank (torch.distributed): every rank replays the host-side simulation and executes
+only the device work of the nodes it owns; models cross ranks through shared arenas with the
+ready/done flag handshake.  The multi-rank result must equal the single-process result.
+
+CPU (gloo, POSIX shared memory) runs everywhere; the CUDA variant (NCCL bootstrap, CUDA-IPC arenas,
+peer loads over NVLink inside the merge / training kernels) needs >= 2 GPUs."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "_mr_worker.py")
+KINDS = "pegasos,mlp_pushpull,limited_pull,partitioned,all2all"
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(world, device, rounds=3, kinds=KINDS):
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    if world == 1:
+        cmd = [sys.executable, WORKER, kinds, device, str(rounds)]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), WORKER, kinds, device,
+               str(rounds)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("RESULT ")]
+    assert lines, "worker failed:\n" + out.stdout[-2000:] + out.stderr[-4000:]
+    return json.loads(lines[-1][len("RESULT "):])
+
+
+def _compare(a, b, rel):
+    for kind in a:
+        x, y = a[kind], b[kind]
+        for f in ("sent", "failed", "size", "ages", "cache_left"):
+            assert x[f] == y[f], (kind, f, x[f], y[f])
+        for f in ("glob", "loc"):
+            assert len(x[f]) == len(y[f])
+            for (t1, m1), (t2, m2) in zip(x[f], y[f]):
+                assert t1 == t2 and m1.keys() == m2.keys()
+                for k in m1:
+                    assert m1[k] == pytest.approx(m2[k], abs=2e-2), (kind, f, k)
+        assert x["sums"].keys() == y["sums"].keys()
+        for n in x["sums"]:
+            assert x["sums"][n] == pytest.approx(y["sums"][n], rel=rel, abs=rel), (kind, n)
+
+
+def test_two_ranks_cpu_equal_single_process():
+    single = _run(1, "cpu")
+    multi = _run(2, "cpu")
+    _compare(single, multi, rel=1e-5)
+
+
+@pytest.mark.gpu
+def test_two_ranks_cuda_equal_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    single = _run(1, "cuda:0")
+    multi = _run(2, "cuda")
+    _compare(single, multi, rel=2e-3)
