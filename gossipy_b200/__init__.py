@@ -15,12 +15,19 @@ This module holds the process-wide runtime objects (reference layer L0).
 from __future__ import annotations
 
 import logging
+import os
 import random
 from abc import ABC, abstractmethod
 from typing import Any, Dict, Iterable, Optional, Tuple
 
-import numpy as np
-import torch
+# Kernels of this package spin on flags written by other GPUs; CUDA's default lazy function loading
+# may need a device-wide synchronisation to load a not-yet-used kernel, which deadlocks behind such
+# a spinning kernel.  Ask for eager loading (effective when CUDA has not been initialised yet; the
+# extension additionally force-loads its own kernels on first use, see ops/native.py).
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 __version__ = "0.1.0"
 

@@ -151,7 +151,8 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
         p.sync = to_sync(sync);
     }
     c10::cuda::CUDAGuard guard(row.device());
-    const TrainImpl which = impl == "cluster" ? kTrainCluster : (impl == "tc" ? kTrainTc : kTrainAuto);
+    const TrainImpl which = impl == "cluster" ? kTrainCluster : impl == "tc" ? kTrainTc
+                            : impl == "tc2" ? kTrainTc2 : kTrainAuto;
     const char* why = "";
     const bool ok = launch_mlp1_train(p, which, cur_stream(), &why);
     TORCH_CHECK(ok, why, " (in=", p.IN, " hidden=", p.H, " out=", p.OUT, " batch=", p.B, ")");
@@ -162,14 +163,37 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
 
 at::Tensor mlp1_train_tc_debug(at::Tensor row, at::Tensor X, at::Tensor y,
                                std::tuple<int64_t, int64_t, int64_t> dims, int64_t batch_size,
-                               int64_t local_epochs, double lr, double wd, int64_t key) {
-    // runs the tcgen05 kernel and returns its debug dump (tests / bring-up / phase timers)
+                               int64_t local_epochs, double lr, double wd, int64_t key, std::string impl) {
+    // runs a tcgen05 kernel with its debug buffer attached: lr == 0 -> relu(z1) [128, 32] of the first
+    // step (bring-up test); lr != 0 (tc2) -> average cycles per step of each phase in the first 6 floats
     auto dbg = at::zeros({128, 32}, row.options());
     g_debug_ptr = dbg.data_ptr<float>();
-    mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, wd, key, c10::nullopt, c10::nullopt, "tc",
+    mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, wd, key, c10::nullopt, c10::nullopt, impl,
                c10::nullopt, 1.0, 0.0, c10::nullopt);
     g_debug_ptr = nullptr;
     return dbg;
+}
+
+std::tuple<at::Tensor, at::Tensor, at::Tensor, int64_t> mlp1_stage_debug(at::Tensor X, at::Tensor y,
+                                                                         int64_t batch_size, int64_t local_epochs,
+                                                                         int64_t key) {
+    // runs the device-side loader of the tc2 training kernel and returns (XF, XT, YS, FP)
+    check_row(X, "X");
+    TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.is_contiguous());
+    const int n = (int)X.size(0), IN = (int)X.size(1);
+    const int B = (int)std::min<int64_t>(batch_size, n);
+    int FPC, FP, steps;
+    const size_t bytes = mlp1_stage_bytes(n, IN, B, (int)local_epochs, &FPC, &FP, &steps);
+    c10::cuda::CUDAGuard guard(X.device());
+    auto buf = at::empty({(int64_t)(bytes / 4)}, X.options());
+    TORCH_CHECK(launch_mlp1_stage(X.data_ptr<float>(), y.data_ptr<int64_t>(), n, IN, B, (int)local_epochs,
+                                  (uint64_t)key, buf.data_ptr<float>(), cur_stream()), "unsupported shape");
+    GB_LAUNCH_CHECK();
+    const int64_t tile = 32 * (int64_t)FP;
+    auto xf = buf.narrow(0, 0, steps * 2 * tile).view({steps, 2, tile});
+    auto xt = buf.narrow(0, steps * 2 * tile, steps * 2 * tile).view({steps, 2, tile});
+    auto ys = buf.narrow(0, steps * 4 * tile, steps * 32).view(at::kInt).view({steps, 32});
+    return {xf, xt, ys, (int64_t)FP};
 }
 
 at::Tensor mlp1_eval(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
@@ -329,6 +353,11 @@ void flag_add(int64_t flag_ptr, int64_t value) {
     GB_LAUNCH_CHECK();
 }
 int64_t device_sm_count() { return sm_count(); }
+void preload() {
+    preload_merge(); preload_optim(); preload_small(); preload_eval(); preload_train_cluster();
+    preload_train_tc(); preload_train_tc2(); preload_stage(); preload_probe();
+    cudaGetLastError();
+}
 
 }  // namespace gb
 
@@ -350,7 +379,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("part_id") = py::none(), py::arg("ages") = py::none(), py::arg("impl") = "",
           py::arg("peer") = py::none(), py::arg("w_self") = 1.0, py::arg("w_peer") = 0.0,
           py::arg("sync") = py::none());
-    m.def("mlp1_train_tc_debug", &gb::mlp1_train_tc_debug);
+    m.def("mlp1_train_tc_debug", &gb::mlp1_train_tc_debug, py::arg("row"), py::arg("X"), py::arg("y"),
+          py::arg("dims"), py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"),
+          py::arg("key"), py::arg("impl") = "tc");
+    m.def("mlp1_stage_debug", &gb::mlp1_stage_debug);
     m.def("mlp1_eval", &gb::mlp1_eval);
     m.def("logreg_train", &gb::logreg_train, py::arg("row"), py::arg("X"), py::arg("y"), py::arg("dims"),
           py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"), py::arg("key"),
@@ -372,5 +404,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("flag_wait", &gb::flag_wait);
     m.def("flag_add", &gb::flag_add);
     m.def("device_sm_count", &gb::device_sm_count);
+    m.def("preload", &gb::preload);
     gb::bind_scheduler(m);
 }

@@ -289,4 +289,18 @@ void launch_flag_add(uint32_t* flag, uint32_t value, cudaStream_t stream) {
     flag_add_kernel<<<1, 1, 0, stream>>>(flag, value);
 }
 
+// force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
+// on a cross-GPU flag could deadlock, so the extension loads everything up front)
+void preload_merge() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, merge_pair_kernel);
+    cudaFuncGetAttributes(&a, merge_segments_kernel);
+    cudaFuncGetAttributes(&a, merge_indexed_kernel);
+    cudaFuncGetAttributes(&a, scatter_kernel);
+    cudaFuncGetAttributes(&a, merge_kway_kernel);
+    cudaFuncGetAttributes(&a, flag_signal_kernel);
+    cudaFuncGetAttributes(&a, flag_wait_kernel);
+    cudaFuncGetAttributes(&a, flag_add_kernel);
+}
+
 }  // namespace gb

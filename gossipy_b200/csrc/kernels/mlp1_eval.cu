@@ -80,4 +80,11 @@ bool launch_mlp1_eval(const float* row, const float* X, const int64_t* y, int n,
     return true;
 }
 
+// force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
+// on a cross-GPU flag could deadlock, so the extension loads everything up front)
+void preload_eval() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, mlp1_eval_simt_kernel);
+}
+
 }  // namespace gb

@@ -343,6 +343,8 @@ bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const
     const bool scaled = p.part_id != nullptr && p.ages != nullptr;
     if (scaled && p.n_parts > MAX_PARTS) { *why = "fused partitioned training supports <= 16 partitions"; return false; }
     if (impl != kTrainCluster && !scaled) {
+        if (impl != kTrainTc && mlp1_train_tc2(p, stream)) return true;
+        if (impl == kTrainTc2) { *why = "tcgen05 (tc2) training kernel does not support this configuration"; return false; }
         if (mlp1_train_tc(p, stream)) return true;
         if (impl == kTrainTc) { *why = "tcgen05 training kernel does not support this configuration"; return false; }
     }
@@ -362,6 +364,22 @@ bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const
     else ok = launch_cluster<32>(p, scaled, stream);
     if (!ok) *why = "mlp1_train(cluster): batch tile does not fit in shared memory / launch failed";
     return ok;
+}
+
+// force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
+// on a cross-GPU flag could deadlock, so the extension loads everything up front)
+void preload_train_cluster() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<2, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<2, true>);
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<8, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<8, true>);
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<16, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<16, true>);
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<25, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<25, true>);
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<32, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_cluster_kernel<32, true>);
 }
 
 }  // namespace gb

@@ -394,4 +394,11 @@ bool mlp1_train_tc(const TrainParams& p, cudaStream_t stream) {
     return cudaGetLastError() == cudaSuccess;
 }
 
+// force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
+// on a cross-GPU flag could deadlock, so the extension loads everything up front)
+void preload_train_tc() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, mlp1_train_tc_kernel);
+}
+
 }  // namespace gb

@@ -1,0 +1,463 @@
+// tcgen05 / TMEM training kernel, second generation ("tc2"): the default local-update kernel of the
+// flagship MLP.  Same idea as mlp1_train_tc.cu -- the fp32 MASTER WEIGHTS of the first layer live in
+// Tensor Memory for the whole local epoch, the forward MMA reads them from TMEM (TS mode, tf32) and
+// the SGD update is a tcgen05.mma that accumulates INTO them -- with the per-step critical path cut
+// to what truly depends on the previous step:
+//
+//   * operands arrive pre-shuffled and pre-tiled from the device-side loader (mlp1_stage.cu): two
+//     contiguous 51 KB bulk copies per step (cp.async.bulk + mbarrier complete_tx), no index math,
+//     no per-row gathers and no shared->shared transpose in the training loop;
+//   * 256 threads (8 warps): two warps share each TMEM lane quadrant and split the accumulator
+//     columns, so the CUDA-core phases (second layer, softmax, backward) run 2x wider;
+//   * the X^T tile of step s+1 is requested as soon as the update MMA of step s retires, the X tile
+//     as soon as the forward MMA does -- single buffers, copies fully overlapped;
+//   * forward MMA of step s+1 is queued right behind the update MMA of step s (the tensor pipe
+//     executes in issue order), so the tensor core never waits for a round trip through the CTA.
+//
+// A CTA pair splits the input features (K of the forward GEMM, N of the update GEMM): each CTA owns
+// FPC <= 400 TMEM columns; partial pre-activations are exchanged through distributed shared memory
+// (one cluster barrier per step).  Second layer / softmax-CE / backward run redundantly (bit-identical)
+// on both CTAs.  Weight decay is a lazy scalar (W_true = s * W_tmem).  With `peer` set the initial
+// weights are w_self*row + w_peer*peer (fused MERGE_UPDATE, peer row possibly in another GPU's HBM).
+// Reference semantics: gossipy/model/handler.py:235-258.  tf32 products, fp32 accumulation/master.
+#include "tc_common.cuh"
+#include "kernels.h"
+
+namespace gb {
+
+constexpr int T2_THREADS = 256;
+constexpr int T2_B = 32;          // mini-batch tile
+constexpr int T2_HP = 128;        // hidden units padded to the MMA M
+constexpr int T2_OUTP = 16;
+constexpr int T2_FP_MAX = 400;    // feature columns per CTA (TMEM: 400 + 32 accumulator columns <= 512)
+constexpr int T2_TMEM_COLS = 512;
+constexpr int T2_HS = 33;         // padded stride of hs[j][b]
+constexpr int T2_NG = 8;          // hidden-unit groups of the second-layer forward
+constexpr int T2_ZP = 12;         // stride of the partial-logit rows
+
+struct T2Smem {   // byte offsets inside dynamic shared memory (1024-aligned base)
+    static constexpr int xf = 0;
+    static constexpr int tile_bytes = T2_B * T2_FP_MAX * 4;          // 51200
+    static constexpr int xt = xf + tile_bytes;
+    static constexpr int a2 = xt + tile_bytes;                       // [16 hid groups][8 chunks][8][16B]
+    static constexpr int zpart = a2 + T2_HP * T2_B * 4;              // [2][128][32] peer partial z1
+    static constexpr int hs = zpart + 2 * T2_HP * T2_B * 4;          // [128][33]
+    static constexpr int w2 = hs + T2_HP * T2_HS * 4;                // [16][128]
+    static constexpr int zp = w2 + T2_OUTP * T2_HP * 4;              // [8][32][12] partial logits
+    static constexpr int z2 = zp + T2_NG * T2_B * T2_ZP * 4;         // [32][16] logits -> dL/dz2
+    static constexpr int gws = z2 + T2_B * T2_OUTP * 4;              // [128][12] second-half partial grads
+    static constexpr int b1 = gws + T2_HP * 12 * 4;
+    static constexpr int b2 = b1 + T2_HP * 4;
+    static constexpr int ys = b2 + T2_OUTP * 4;                      // [2][32] int labels
+    static constexpr int mbar = ys + 2 * T2_B * 4;                   // 5 x uint64
+    static constexpr int tslot = mbar + 64;
+    static constexpr int total = tslot + 16;
+};
+
+GB_DEVICE void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const int total_steps,
+                      const float* __restrict__ stage_xf, const float* __restrict__ stage_xt,
+                      const int* __restrict__ stage_ys) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int quad = warp & 3, half = warp >> 2;
+    const int j = quad * 32 + lane;                        // hidden unit = TMEM lane of this thread
+    const uint32_t rank = gb_cluster_ctarank(), peer_cta = rank ^ 1u;
+    const int IN = p.IN, H = p.H, OUT = p.OUT, n = p.n, B = p.B;
+    const int f0 = (int)rank * FPC;
+    const int fcnt = max(0, min(FPC, IN - f0));
+    const int nchunk = FP >> 2;
+
+    float* xf = reinterpret_cast<float*>(smem + T2Smem::xf);
+    float* xt = reinterpret_cast<float*>(smem + T2Smem::xt);
+    float* a2 = reinterpret_cast<float*>(smem + T2Smem::a2);
+    float* zpart = reinterpret_cast<float*>(smem + T2Smem::zpart);
+    float* hs = reinterpret_cast<float*>(smem + T2Smem::hs);
+    float* w2s = reinterpret_cast<float*>(smem + T2Smem::w2);
+    float* zp = reinterpret_cast<float*>(smem + T2Smem::zp);
+    float* z2s = reinterpret_cast<float*>(smem + T2Smem::z2);
+    float* gws = reinterpret_cast<float*>(smem + T2Smem::gws);
+    float* b1s = reinterpret_cast<float*>(smem + T2Smem::b1);
+    float* b2s = reinterpret_cast<float*>(smem + T2Smem::b2);
+    int* ysm = reinterpret_cast<int*>(smem + T2Smem::ys);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T2Smem::mbar);   // 0 xf, 1 xt, 2 fwd, 3 upd, 4 drain
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + T2Smem::tslot);
+
+    float* b1g = p.row + (size_t)H * IN;
+    float* W2g = b1g + H;
+    float* b2g = W2g + (size_t)OUT * H;
+    const uint32_t tile_bytes = (uint32_t)T2_B * (uint32_t)FP * 4u;
+    const size_t tile_floats = (size_t)T2_B * FP;
+    const float* my_xf = stage_xf + (size_t)rank * tile_floats;          // + s * 2 * tile_floats
+    const float* my_xt = stage_xt + (size_t)rank * tile_floats;
+
+    // ---- one-time set-up -------------------------------------------------------------------------
+    const bool merging = p.peer != nullptr;
+    if (merging && p.sync.ready != nullptr) {
+        if (tid == 0) while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
+        __syncthreads();
+    }
+    auto ldp = [&](size_t off) -> float {
+        const float own = p.row[off];
+        return merging ? p.w_self * own + p.w_peer * gb_ld_stream1(p.peer + off) : own;
+    };
+    const size_t off_b1 = (size_t)H * IN, off_w2 = off_b1 + H, off_b2 = off_w2 + (size_t)OUT * H;
+    if (warp == 0) tmem_alloc<T2_TMEM_COLS>(tslot);
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(&mbar[i], 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < T2_HP * T2_B; i += T2_THREADS) a2[i] = 0.f;
+    for (int i = tid; i < T2_OUTP * T2_HP; i += T2_THREADS) {
+        const int o = i / T2_HP, jj = i % T2_HP;
+        w2s[i] = (o < OUT && jj < H) ? ldp(off_w2 + (size_t)o * H + jj) : 0.f;
+    }
+    for (int i = tid; i < T2_HP * T2_HS; i += T2_THREADS) hs[i] = 0.f;
+    if (tid < T2_HP) b1s[tid] = (tid < H) ? ldp(off_b1 + tid) : 0.f;
+    if (tid < T2_OUTP) b2s[tid] = (tid < OUT) ? ldp(off_b2 + tid) : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tslot;
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t t_w1 = 0, t_d1 = T2_FP_MAX;
+
+    // first X / X^T tiles and labels: issue now, they land while the weights are loaded
+    if (tid == 0) {
+        mbar_expect_tx(&mbar[0], tile_bytes);
+        bulk_g2s(xf, my_xf, tile_bytes, &mbar[0]);
+        mbar_expect_tx(&mbar[1], tile_bytes);
+        bulk_g2s(xt, my_xt, tile_bytes, &mbar[1]);
+    }
+    if (tid < T2_B) ysm[tid] = stage_ys[tid];
+
+    // master weights -> TMEM: thread (j, half) fills column groups [half*13, ...) of its lane
+    {
+        const int ngroups = T2_FP_MAX / 16;                               // 25
+        const int g0 = half ? 13 : 0, g1 = half ? ngroups : 13;
+        for (int g = g0; g < g1; ++g) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int c = g * 16 + i;
+                v[i] = (j < H && c < fcnt) ? ldp((size_t)j * IN + f0 + c) : 0.f;
+            }
+            tmem_st16(tlane + t_w1 + g * 16, v);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    gb_cluster_sync();            // peer is running (its smem may be written from here on)
+    tc_fence_after();
+    if (merging && p.sync.done != nullptr && rank == 0 && tid == 0)
+        gb_red_release_sys_add(p.sync.done, 1u);   // both CTAs have consumed their peer loads
+
+    const float decay = 1.f - p.lr * p.wd;
+    float sscale = 1.f;                                  // W_true = sscale * W_tmem
+    const uint32_t idesc_fwd = make_idesc(kFmtTF32, kFmtTF32, 128, T2_B, false, false);
+    const uint32_t x_sbo = (uint32_t)nchunk * 128u;
+    const int spe = (n + B - 1) / B;
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool profiling = p.dbg != nullptr && p.lr == 0.f ? false : (p.dbg != nullptr);
+
+    for (int s = 0; s < total_steps; ++s) {
+        const int par = s & 1;
+        const uint32_t ph = (uint32_t)(s & 1);
+        const int pos = p.epochs > 0 ? (s % spe) * B : 0;
+        const int bcur = min(B, n - pos);
+        long long t0 = 0;
+        if (profiling && tid == 0) t0 = clock64();
+
+        // (A)+(B) forward MMA: D1[128 x 32] = W1(TMEM) . X^T ; queued behind update(s-1)
+        if (tid == 0) {
+            mbar_wait(&mbar[0], ph);                     // X tile of this step has landed
+            tc_fence_after();
+            const uint32_t xaddr = smem_u32(xf);
+            for (int k = 0; k < FP / 8; ++k) {
+                const uint64_t bdesc = make_sdesc(xaddr + (uint32_t)k * 256u, 128u, x_sbo);
+                mma_tf32_ts(tmem + t_d1, tmem + t_w1 + (uint32_t)k * 8u, bdesc, idesc_fwd, k > 0);
+            }
+            mma_commit(&mbar[2]);
+            if (s > 0) {                                 // update(s-1) retired -> X^T buffer is free
+                mbar_wait(&mbar[3], (uint32_t)((s - 1) & 1));
+                mbar_expect_tx(&mbar[1], tile_bytes);
+                bulk_g2s(xt, my_xt + (size_t)s * 2 * tile_floats, tile_bytes, &mbar[1]);
+            }
+        }
+        if (profiling && tid == 0) { const long long t = clock64(); prof[0] += t - t0; t0 = t; }
+
+        // (C) accumulator -> registers, exchange partial sums with the peer CTA
+        mbar_wait(&mbar[2], ph);
+        tc_fence_after();
+        if (tid == 0 && s + 1 < total_steps) {           // forward MMA retired -> X buffer is free
+            mbar_expect_tx(&mbar[0], tile_bytes);
+            bulk_g2s(xf, my_xf + (size_t)(s + 1) * 2 * tile_floats, tile_bytes, &mbar[0]);
+        }
+        float acc[16];
+        tmem_ld16(tlane + t_d1 + 16 * half, acc);
+        tmem_ld_wait();
+        if (profiling && tid == 0) { const long long t = clock64(); prof[1] += t - t0; t0 = t; }
+        {
+            float* mine = zpart + ((size_t)par * T2_HP + j) * T2_B + 16 * half;
+            const uint32_t remote = gb_map_shared(mine, peer_cta);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                gb_st_cluster4(remote + 16u * q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+        }
+        gb_cluster_sync();
+        float h[16];
+        {
+            const float4* other = reinterpret_cast<const float4*>(zpart + ((size_t)par * T2_HP + j) * T2_B + 16 * half);
+            const float bj = b1s[j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 o = other[q];
+                h[4 * q] = acc[4 * q] + o.x; h[4 * q + 1] = acc[4 * q + 1] + o.y;
+                h[4 * q + 2] = acc[4 * q + 2] + o.z; h[4 * q + 3] = acc[4 * q + 3] + o.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float z = fmaf(sscale, h[i], bj);
+                h[i] = (j < H) ? fmaxf(z, 0.f) : 0.f;
+                hs[j * T2_HS + 16 * half + i] = h[i];
+            }
+        }
+        if (p.dbg != nullptr && !profiling && s == 0 && rank == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) p.dbg[j * T2_B + 16 * half + i] = h[i];
+        }
+        __syncthreads();
+        if (profiling && tid == 0) { const long long t = clock64(); prof[2] += t - t0; t0 = t; }
+
+        // (D) layer 2 forward, partial over 16 hidden units: thread (b = lane, g = warp)
+        {
+            const int b = lane, g = warp;
+            float zacc[10];
+#pragma unroll
+            for (int o = 0; o < 10; ++o) zacc[o] = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) {
+                const int jb = 16 * g + jj;
+                const float h0 = hs[(jb + 0) * T2_HS + b], h1 = hs[(jb + 1) * T2_HS + b];
+                const float h2 = hs[(jb + 2) * T2_HS + b], h3 = hs[(jb + 3) * T2_HS + b];
+#pragma unroll
+                for (int o = 0; o < 10; ++o) {
+                    const float4 wv = *reinterpret_cast<const float4*>(w2s + o * T2_HP + jb);
+                    zacc[o] = fmaf(h0, wv.x, fmaf(h1, wv.y, fmaf(h2, wv.z, fmaf(h3, wv.w, zacc[o]))));
+                }
+            }
+            float* dst = zp + ((size_t)g * T2_B + b) * T2_ZP;
+#pragma unroll
+            for (int o = 0; o < 10; ++o) dst[o] = zacc[o];
+        }
+        __syncthreads();
+        // (E1) reduce the 8 partials; (E2) softmax cross-entropy gradient, one thread per sample
+        for (int e = tid; e < T2_B * 10; e += T2_THREADS) {
+            const int b = e / 10, o = e - b * 10;
+            float z = b2s[o];
+#pragma unroll
+            for (int g = 0; g < T2_NG; ++g) z += zp[((size_t)g * T2_B + b) * T2_ZP + o];
+            z2s[b * T2_OUTP + o] = z;
+        }
+        __syncthreads();
+        if (tid < T2_B) {
+            float* zr = z2s + tid * T2_OUTP;
+            if (tid < bcur) {
+                float m = zr[0];
+                for (int o = 1; o < OUT; ++o) m = fmaxf(m, zr[o]);
+                float ex[10], sum = 0.f;
+#pragma unroll
+                for (int o = 0; o < 10; ++o) { ex[o] = (o < OUT) ? __expf(zr[o] - m) : 0.f; sum += ex[o]; }
+                const float inv = 1.f / sum, invb = 1.f / (float)bcur;
+                const int yy = ysm[par * T2_B + tid];
+#pragma unroll
+                for (int o = 0; o < 10; ++o) zr[o] = (o < OUT) ? (ex[o] * inv - (o == yy ? 1.f : 0.f)) * invb : 0.f;
+            } else {
+#pragma unroll
+                for (int o = 0; o < 10; ++o) zr[o] = 0.f;
+            }
+#pragma unroll
+            for (int o = 10; o < T2_OUTP; ++o) zr[o] = 0.f;
+        }
+        if (tid >= 32 && tid < 64 && s + 1 < total_steps)           // labels of the next step
+            ysm[(par ^ 1) * T2_B + (tid - 32)] = stage_ys[(size_t)(s + 1) * T2_B + (tid - 32)];
+        __syncthreads();
+        if (profiling && tid == 0) { const long long t = clock64(); prof[3] += t - t0; t0 = t; }
+
+        // (F) backward through layer 2: thread (j, half) handles its 16 samples
+        const float s_next = sscale * decay;
+        float gw2[10];
+        float gb1 = 0.f;
+        {
+            float w2c[10];
+#pragma unroll
+            for (int o = 0; o < 10; ++o) { w2c[o] = w2s[o * T2_HP + j]; gw2[o] = 0.f; }
+            const float ascale = -p.lr / s_next;
+            float outv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4* dzr = reinterpret_cast<const float4*>(z2s + (16 * half + i) * T2_OUTP);
+                const float4 d0 = dzr[0], d1 = dzr[1], d2 = dzr[2];
+                const float dz[10] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y};
+                float dh = 0.f;
+#pragma unroll
+                for (int o = 0; o < 10; ++o) { dh = fmaf(dz[o], w2c[o], dh); gw2[o] = fmaf(dz[o], h[i], gw2[o]); }
+                const float dz1 = (h[i] > 0.f) ? dh : 0.f;
+                gb1 += dz1;
+                outv[i] = ascale * dz1;
+            }
+            // A2[hid = j][batch] in K-major core-matrix layout: ((j/8)*8 + b/4)*128 B + (j%8)*16 B + (b%4)*4 B
+            float* arow = a2 + (size_t)(j >> 3) * (8 * 32) + (j & 7) * 4 + (4 * half) * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(arow + q * 32) = make_float4(outv[4 * q], outv[4 * q + 1], outv[4 * q + 2], outv[4 * q + 3]);
+            if (half == 1) {
+                float* g = gws + j * 12;
+#pragma unroll
+                for (int o = 0; o < 10; ++o) g[o] = gw2[o];
+                g[10] = gb1;
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (profiling && tid == 0) { const long long t = clock64(); prof[4] += t - t0; t0 = t; }
+
+        // (G) update MMA: W1[128 x FP] += A2[128 x 32] . X^T-tile (both operands K-major, K = batch)
+        if (tid == 0) {
+            mbar_wait(&mbar[1], ph);                     // X^T tile of this step has landed
+            tc_fence_after();
+            const uint32_t taddr = smem_u32(xt), aaddr = smem_u32(a2);
+            for (int n0 = 0; n0 < FP; n0 += 256) {
+                const int nn = min(256, FP - n0);
+                const uint32_t idesc_upd = make_idesc(kFmtTF32, kFmtTF32, 128, nn, false, false);
+                for (int k = 0; k < T2_B / 8; ++k) {
+                    const uint64_t adesc = make_sdesc(aaddr + (uint32_t)k * 256u, 128u, 1024u);
+                    const uint64_t bdesc = make_sdesc(taddr + (uint32_t)(n0 >> 3) * 1024u + (uint32_t)k * 256u,
+                                                      128u, 1024u);
+                    mma_tf32_ss(tmem + t_w1 + (uint32_t)n0, adesc, bdesc, idesc_upd, true);
+                }
+            }
+            mma_commit(&mbar[3]);
+        }
+        // (H) second-layer parameters: thread (j, 0) adds the other half's partial gradients
+        if (half == 0) {
+            const float* g = gws + j * 12;
+            if (j < H) {
+#pragma unroll
+                for (int o = 0; o < 10; ++o)
+                    if (o < OUT) w2s[o * T2_HP + j] = fmaf(-p.lr, gw2[o] + g[o], w2s[o * T2_HP + j] * decay);
+            }
+            b1s[j] = fmaf(-p.lr, gb1 + g[10], b1s[j] * decay);
+        } else if (tid >= 128 && tid < 128 + OUT) {
+            const int o = tid - 128;
+            float gsum = 0.f;
+            for (int b = 0; b < T2_B; ++b) gsum += z2s[b * T2_OUTP + o];
+            b2s[o] = fmaf(-p.lr, gsum, b2s[o] * decay);
+        }
+        sscale = s_next;
+        if (profiling && tid == 0) { const long long t = clock64(); prof[5] += t - t0; t0 = t; }
+    }
+
+    // ---- drain the tensor pipe and write everything back ------------------------------------------------
+    if (tid == 0) mma_commit(&mbar[4]);
+    mbar_wait(&mbar[4], 0u);
+    tc_fence_after();
+    __syncthreads();
+    {
+        const int ngroups = T2_FP_MAX / 16;
+        const int g0 = half ? 13 : 0, g1 = half ? ngroups : 13;
+        for (int g = g0; g < g1; ++g) {
+            float v[16];
+            tmem_ld16(tlane + t_w1 + g * 16, v);
+            tmem_ld_wait();
+            if (j < H) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = g * 16 + i;
+                    if (c < fcnt) p.row[(size_t)j * IN + f0 + c] = sscale * v[i];
+                }
+            }
+        }
+    }
+    if (rank == 0) {
+        for (int i = tid; i < OUT * H; i += T2_THREADS) { const int o = i / H, jj = i % H; W2g[i] = w2s[o * T2_HP + jj]; }
+        if (tid < H) b1g[tid] = b1s[tid];
+        if (tid < OUT) b2g[tid] = b2s[tid];
+    }
+    if (profiling && tid == 0 && rank == 0) {
+        for (int i = 0; i < 6; ++i) p.dbg[i] = (float)((double)prof[i] / (double)total_steps);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<T2_TMEM_COLS>(tmem);
+    gb_cluster_sync();
+}
+
+// staging buffers: one per (device, stream), grown on demand.  The training kernel that consumes a
+// staging buffer is enqueued right behind its loader on the same stream, so successive updates of a
+// stream can reuse the buffer; different streams (= different gossip nodes) get different buffers.
+struct StageBuf { void* ptr; size_t bytes; cudaStream_t stream; int dev; };
+static StageBuf g_stage[512] = {};
+
+static void* stage_buffer_for(cudaStream_t stream, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int free_slot = -1;
+    for (int i = 0; i < 512; ++i) {
+        StageBuf& sb = g_stage[i];
+        if (sb.ptr != nullptr && sb.stream == stream && sb.dev == dev) {
+            if (sb.bytes >= bytes) return sb.ptr;
+            cudaStreamSynchronize(stream);
+            cudaFree(sb.ptr);
+            sb.ptr = nullptr;
+            free_slot = i;
+            break;
+        }
+        if (sb.ptr == nullptr && free_slot < 0) free_slot = i;
+    }
+    if (free_slot < 0) return nullptr;
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    g_stage[free_slot] = StageBuf{ptr, bytes, stream, dev};
+    return ptr;
+}
+
+bool mlp1_train_tc2(const TrainParams& p, cudaStream_t stream) {
+    // shape envelope; anything else falls back to the first-generation tc kernel / the cluster kernel
+    if (p.H > T2_HP || p.OUT > 10 || p.B > T2_B || p.IN % 8 != 0) return false;
+    int FPC, FP, steps;
+    const size_t bytes = mlp1_stage_bytes(p.n, p.IN, p.B, p.epochs, &FPC, &FP, &steps);
+    if (FP > T2_FP_MAX || p.IN - FPC > FPC || p.IN - FPC <= 0) return false;
+    if ((double)steps * (double)p.lr * (double)p.wd > 20.0) return false;   // lazy decay scale would underflow
+    if (bytes > ((size_t)1 << 31)) return false;
+    void* staging = stage_buffer_for(stream, bytes);
+    if (staging == nullptr) return false;
+    if (!launch_mlp1_stage(p.X, p.y, p.n, p.IN, p.B, p.epochs, p.key, staging, stream)) return false;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mlp1_train_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 T2Smem::total + 1024) != cudaSuccess) return false;
+        configured = true;
+    }
+    const size_t tile_floats = (size_t)T2_B * FP;
+    const float* xf = static_cast<const float*>(staging);
+    const float* xt = xf + (size_t)steps * 2 * tile_floats;
+    const int* ys = reinterpret_cast<const int*>(xt + (size_t)steps * 2 * tile_floats);
+    mlp1_train_tc2_kernel<<<2, T2_THREADS, T2Smem::total + 1024, stream>>>(p, FPC, FP, steps, xf, xt, ys);
+    return cudaGetLastError() == cudaSuccess;
+}
+
+// force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
+// on a cross-GPU flag could deadlock, so the extension loads everything up front)
+void preload_train_tc2() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, mlp1_train_tc2_kernel);
+}
+
+}  // namespace gb

@@ -66,4 +66,12 @@ void launch_adam(float* p, const float* g, int64_t n, float* m, float* v, int64_
                                                    decoupled ? 1 : 0, (float)bc1, (float)std::sqrt(bc2));
 }
 
+// force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
+// on a cross-GPU flag could deadlock, so the extension loads everything up front)
+void preload_optim() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, sgd_kernel);
+    cudaFuncGetAttributes(&a, adam_kernel);
+}
+
 }  // namespace gb

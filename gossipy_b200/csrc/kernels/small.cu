@@ -280,4 +280,16 @@ void launch_mf_update(float* Xu, float* bu, float* Y, float* c, const float* rat
     mf_update_kernel<<<1, 32, 0, stream>>>(Xu, bu, Y, c, ratings, m, k, reg, lr);
 }
 
+// force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
+// on a cross-GPU flag could deadlock, so the extension loads everything up front)
+void preload_small() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, logreg_train_kernel);
+    cudaFuncGetAttributes(&a, logreg_scores_kernel);
+    cudaFuncGetAttributes(&a, linear_seq_kernel);
+    cudaFuncGetAttributes(&a, kmeans_assign_kernel);
+    cudaFuncGetAttributes(&a, kmeans_apply_kernel);
+    cudaFuncGetAttributes(&a, mf_update_kernel);
+}
+
 }  // namespace gb

@@ -74,4 +74,11 @@ void launch_tc_probe(const float* A, const float* Bm, float* D, int K, int N, in
     tc_probe_kernel<<<1, 128, smem, stream>>>(A, Bm, D, K, N, variant);
 }
 
+// force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
+// on a cross-GPU flag could deadlock, so the extension loads everything up front)
+void preload_probe() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, tc_probe_kernel);
+}
+
 }  // namespace gb

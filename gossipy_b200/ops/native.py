@@ -29,6 +29,17 @@ def require_native() -> None:
             "at the repo root. There is deliberately no eager fallback on GPU." % (_err,))
 
 
+_preloaded = set()
+
+
 def native():
+    """The extension module; on first use per CUDA device every kernel is force-loaded (CUDA loads
+    functions lazily, and loading one while another kernel spins on a cross-GPU flag can deadlock)."""
     require_native()
+    import torch
+    if torch.cuda.is_available():
+        dev = torch.cuda.current_device()
+        if dev not in _preloaded:
+            _preloaded.add(dev)
+            _mod.preload()
     return _mod
