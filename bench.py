@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--train-impl", default="", help="force a training kernel: cluster | tc")
+    ap.add_argument("--engine", default="native", choices=["native", "python"],
+                    help="control plane of the round loop: C++ scheduler or the Python loop")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--curve", action="store_true", help="also print accuracy per round")
     return ap.parse_args()
@@ -156,7 +158,7 @@ def barrier(world: int):
 # --------------------------------------------------------------------------------------------
 # this framework
 # --------------------------------------------------------------------------------------------
-def build_native(world: int, rank: int, train_impl: str):
+def build_native(world: int, rank: int, train_impl: str, engine: str = "native"):
     import torch
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork
@@ -186,6 +188,7 @@ def build_native(world: int, rank: int, train_impl: str):
     nodes = GossipNode.generate(disp, StaticP2PNetwork(N_NODES), proto, round_len=DELTA, sync=True)
     sim = GossipSimulator(nodes, disp, DELTA, AntiEntropyProtocol.PUSH_PULL)
     sim.progress = False
+    sim.engine = engine          # "native": C++ scheduler (csrc/sched) drives the round loop
     rep = SimulationReport()
     sim.add_receiver(rep)
     if torch.cuda.is_available():
@@ -238,7 +241,7 @@ def run_native(args, rank, world):
     K = args.steps if args.steps is not None else 20
     W = args.warmup if args.warmup is not None else 3
     W = max(W, 3)
-    sim, rep = build_native(world, rank, args.train_impl)
+    sim, rep = build_native(world, rank, args.train_impl, args.engine)
     time_rounds(sim, W, world, resume=False)
     launches0 = ops.launch_count
     with ClockSampler(torch.cuda.current_device() if torch.cuda.is_available() else 0) as clk:
@@ -273,7 +276,7 @@ def run_native(args, rank, world):
                           "parallelism": "gossip-dp: %d nodes over %d GPU(s)" % (N_NODES, world),
                           "l2": "192 MB flush buffer rewritten every round (and at N=1 the inputs, 219 MB, exceed the 126 MB L2)",
                           "placement": "block (node i on rank i*N//8), peer rows pulled over NVLink by the fused merge+train kernel",
-                          "train_kernel": args.train_impl or "auto"},
+                          "train_kernel": args.train_impl or "auto", "engine": args.engine},
                "clocks": clk.summary(), "gpu_launches": launches,
                "test_acc_by_round_tail": acc[-5:], "e2e": e2e}
         if args.curve:

@@ -31,7 +31,7 @@ constexpr int T2_HP = 128;        // hidden units padded to the MMA M
 constexpr int T2_OUTP = 16;
 constexpr int T2_FP_MAX = 400;    // feature columns per CTA (TMEM: 400 + 32 accumulator columns <= 512)
 constexpr int T2_TMEM_COLS = 512;
-constexpr int T2_HS = 33;         // padded stride of hs[j][b]
+constexpr int T2_HS = 132;        // stride of hs[b][j] (sample-major; 132 = 4 mod 32 keeps 128-bit reads conflict free)
 constexpr int T2_NG = 8;          // hidden-unit groups of the second-layer forward
 constexpr int T2_ZP = 12;         // stride of the partial-logit rows
 
@@ -41,15 +41,15 @@ struct T2Smem {   // byte offsets inside dynamic shared memory (1024-aligned bas
     static constexpr int xt = xf + tile_bytes;
     static constexpr int a2 = xt + tile_bytes;                       // [16 hid groups][8 chunks][8][16B]
     static constexpr int zpart = a2 + T2_HP * T2_B * 4;              // [2][128][32] peer partial z1
-    static constexpr int hs = zpart + 2 * T2_HP * T2_B * 4;          // [128][33]
-    static constexpr int w2 = hs + T2_HP * T2_HS * 4;                // [16][128]
+    static constexpr int hs = zpart + 2 * T2_HP * T2_B * 4;          // [32][132]
+    static constexpr int w2 = hs + T2_B * T2_HS * 4;                 // [16][128]
     static constexpr int zp = w2 + T2_OUTP * T2_HP * 4;              // [8][32][12] partial logits
     static constexpr int z2 = zp + T2_NG * T2_B * T2_ZP * 4;         // [32][16] logits -> dL/dz2
     static constexpr int gws = z2 + T2_B * T2_OUTP * 4;              // [128][12] second-half partial grads
     static constexpr int b1 = gws + T2_HP * 12 * 4;
     static constexpr int b2 = b1 + T2_HP * 4;
     static constexpr int ys = b2 + T2_OUTP * 4;                      // [2][32] int labels
-    static constexpr int mbar = ys + 2 * T2_B * 4;                   // 5 x uint64
+    static constexpr int mbar = ys + 2 * T2_B * 4;                   // 8 x uint64
     static constexpr int tslot = mbar + 64;
     static constexpr int total = tslot + 16;
 };
@@ -85,7 +85,7 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
     float* b1s = reinterpret_cast<float*>(smem + T2Smem::b1);
     float* b2s = reinterpret_cast<float*>(smem + T2Smem::b2);
     int* ysm = reinterpret_cast<int*>(smem + T2Smem::ys);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T2Smem::mbar);   // 0 xf, 1 xt, 2 fwd, 3 upd, 4 drain
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T2Smem::mbar);   // 0 xf, 1 xt, 2 fwd, 3 upd, 4 drain, 5/6 exchange
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + T2Smem::tslot);
 
     float* b1g = p.row + (size_t)H * IN;
@@ -109,7 +109,7 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
     const size_t off_b1 = (size_t)H * IN, off_w2 = off_b1 + H, off_b2 = off_w2 + (size_t)OUT * H;
     if (warp == 0) tmem_alloc<T2_TMEM_COLS>(tslot);
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(&mbar[i], 1);
+        for (int i = 0; i < 7; ++i) mbar_init(&mbar[i], 1);
         mbar_fence_init();
     }
     for (int i = tid; i < T2_HP * T2_B; i += T2_THREADS) a2[i] = 0.f;
@@ -117,14 +117,16 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
         const int o = i / T2_HP, jj = i % T2_HP;
         w2s[i] = (o < OUT && jj < H) ? ldp(off_w2 + (size_t)o * H + jj) : 0.f;
     }
-    for (int i = tid; i < T2_HP * T2_HS; i += T2_THREADS) hs[i] = 0.f;
+    for (int i = tid; i < T2_B * T2_HS; i += T2_THREADS) hs[i] = 0.f;
     if (tid < T2_HP) b1s[tid] = (tid < H) ? ldp(off_b1 + tid) : 0.f;
     if (tid < T2_OUTP) b2s[tid] = (tid < OUT) ? ldp(off_b2 + tid) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tslot;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);          // warp-uniform copy for the MMA issuer
     const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t exch_bytes = (uint32_t)H * T2_B * 4u;                // peer partial sums per step (rows < H)
     const uint32_t t_w1 = 0, t_d1 = T2_FP_MAX;
 
     // first X / X^T tiles and labels: issue now, they land while the weights are loaded
@@ -173,20 +175,29 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
         long long t0 = 0;
         if (profiling && tid == 0) t0 = clock64();
 
-        // (A)+(B) forward MMA: D1[128 x 32] = W1(TMEM) . X^T ; queued behind update(s-1)
-        if (tid == 0) {
+        // (A)+(B) forward MMA: D1[128 x 32] = W1(TMEM) . X^T ; queued behind update(s-1).
+        // Warp 0 stays converged and one ELECTED lane issues (operands in uniform registers).
+        if (warp == 0) {
             mbar_wait(&mbar[0], ph);                     // X tile of this step has landed
             tc_fence_after();
-            const uint32_t xaddr = smem_u32(xf);
-            for (int k = 0; k < FP / 8; ++k) {
-                const uint64_t bdesc = make_sdesc(xaddr + (uint32_t)k * 256u, 128u, x_sbo);
-                mma_tf32_ts(tmem + t_d1, tmem + t_w1 + (uint32_t)k * 8u, bdesc, idesc_fwd, k > 0);
+            if (elect_one()) {
+                mbar_expect_tx(&mbar[5 + par], exch_bytes);   // the peer's partial sums of this step
+                const uint64_t bdesc0 = make_sdesc(smem_u32(xf), 128u, x_sbo);
+                const uint32_t d1 = tmem_u + t_d1, a0 = tmem_u + t_w1;
+                mma_tf32_ts(d1, a0, bdesc0, idesc_fwd, false);
+#pragma unroll 7
+                for (int k = 1; k < FP / 8; ++k)          // +256 B per K step = +16 in the address field
+                    mma_tf32_ts(d1, a0 + (uint32_t)k * 8u, bdesc0 + (uint64_t)(k * 16), idesc_fwd, true);
+                mma_commit(&mbar[2]);
             }
-            mma_commit(&mbar[2]);
+            __syncwarp();
             if (s > 0) {                                 // update(s-1) retired -> X^T buffer is free
                 mbar_wait(&mbar[3], (uint32_t)((s - 1) & 1));
-                mbar_expect_tx(&mbar[1], tile_bytes);
-                bulk_g2s(xt, my_xt + (size_t)s * 2 * tile_floats, tile_bytes, &mbar[1]);
+                if (elect_one()) {
+                    mbar_expect_tx(&mbar[1], tile_bytes);
+                    bulk_g2s(xt, my_xt + (size_t)s * 2 * tile_floats, tile_bytes, &mbar[1]);
+                }
+                __syncwarp();
             }
         }
         if (profiling && tid == 0) { const long long t = clock64(); prof[0] += t - t0; t0 = t; }
@@ -194,29 +205,35 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
         // (C) accumulator -> registers, exchange partial sums with the peer CTA
         mbar_wait(&mbar[2], ph);
         tc_fence_after();
-        if (tid == 0 && s + 1 < total_steps) {           // forward MMA retired -> X buffer is free
-            mbar_expect_tx(&mbar[0], tile_bytes);
-            bulk_g2s(xf, my_xf + (size_t)(s + 1) * 2 * tile_floats, tile_bytes, &mbar[0]);
+        if (warp == 0 && s + 1 < total_steps) {          // forward MMA retired -> X buffer is free
+            if (elect_one()) {
+                mbar_expect_tx(&mbar[0], tile_bytes);
+                bulk_g2s(xf, my_xf + (size_t)(s + 1) * 2 * tile_floats, tile_bytes, &mbar[0]);
+            }
+            __syncwarp();
         }
         float acc[16];
         tmem_ld16(tlane + t_d1 + 16 * half, acc);
         tmem_ld_wait();
         if (profiling && tid == 0) { const long long t = clock64(); prof[1] += t - t0; t0 = t; }
-        {
-            float* mine = zpart + ((size_t)par * T2_HP + j) * T2_B + 16 * half;
-            const uint32_t remote = gb_map_shared(mine, peer_cta);
+        // my partial sums -> the peer's zpart; layout [par][half*4 + q][j][4 samples]: every warp-wide
+        // store covers 512 contiguous bytes of the peer's shared memory, each 16-B piece signalling
+        // the peer's exchange mbarrier (st.async complete_tx); rows j >= H carry nothing
+        float* zslot = zpart + (((size_t)par * 8 + half * 4) * T2_HP + j) * 4;
+        if (j < H) {
+            const uint32_t remote = gb_map_shared(zslot, peer_cta);
+            const uint32_t rbar = gb_map_shared(&mbar[5 + par], peer_cta);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                gb_st_cluster4(remote + 16u * q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+                st_async_v4(remote + (uint32_t)(q * T2_HP * 16), make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]), rbar);
         }
-        gb_cluster_sync();
+        mbar_wait_cluster(&mbar[5 + par], (uint32_t)((s >> 1) & 1));   // all of the peer's partials landed
         float h[16];
         {
-            const float4* other = reinterpret_cast<const float4*>(zpart + ((size_t)par * T2_HP + j) * T2_B + 16 * half);
             const float bj = b1s[j];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 o = other[q];
+                const float4 o = (j < H) ? *reinterpret_cast<const float4*>(zslot + (size_t)q * T2_HP * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 h[4 * q] = acc[4 * q] + o.x; h[4 * q + 1] = acc[4 * q + 1] + o.y;
                 h[4 * q + 2] = acc[4 * q + 2] + o.z; h[4 * q + 3] = acc[4 * q + 3] + o.w;
             }
@@ -224,7 +241,7 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
             for (int i = 0; i < 16; ++i) {
                 const float z = fmaf(sscale, h[i], bj);
                 h[i] = (j < H) ? fmaxf(z, 0.f) : 0.f;
-                hs[j * T2_HS + 16 * half + i] = h[i];
+                hs[(16 * half + i) * T2_HS + j] = h[i];
             }
         }
         if (p.dbg != nullptr && !profiling && s == 0 && rank == 0) {
@@ -234,55 +251,51 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
         __syncthreads();
         if (profiling && tid == 0) { const long long t = clock64(); prof[2] += t - t0; t0 = t; }
 
-        // (D) layer 2 forward, partial over 16 hidden units: thread (b = lane, g = warp)
+        // (D)+(E) layer 2 forward and softmax cross-entropy gradient, all 8 warps alike: warp w owns
+        // samples 4w..4w+3; lane = (g = hidden group of 16, bl = sample).  Partial dot products over the
+        // group, butterfly reduction across the 8 groups (lane bits 2..4), then every lane finishes
+        // the softmax of its sample for the outputs o = g and g + 8.
         {
-            const int b = lane, g = warp;
+            const int bl = lane & 3, g = lane >> 2, b = 4 * warp + bl;
             float zacc[10];
 #pragma unroll
             for (int o = 0; o < 10; ++o) zacc[o] = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < 16; jj += 4) {
-                const int jb = 16 * g + jj;
-                const float h0 = hs[(jb + 0) * T2_HS + b], h1 = hs[(jb + 1) * T2_HS + b];
-                const float h2 = hs[(jb + 2) * T2_HS + b], h3 = hs[(jb + 3) * T2_HS + b];
+            for (int c = 0; c < 4; ++c) {
+                const int jb = 16 * g + 4 * c;
+                const float4 hv = *reinterpret_cast<const float4*>(hs + b * T2_HS + jb);
 #pragma unroll
                 for (int o = 0; o < 10; ++o) {
                     const float4 wv = *reinterpret_cast<const float4*>(w2s + o * T2_HP + jb);
-                    zacc[o] = fmaf(h0, wv.x, fmaf(h1, wv.y, fmaf(h2, wv.z, fmaf(h3, wv.w, zacc[o]))));
+                    zacc[o] = fmaf(hv.x, wv.x, fmaf(hv.y, wv.y, fmaf(hv.z, wv.z, fmaf(hv.w, wv.w, zacc[o]))));
                 }
             }
-            float* dst = zp + ((size_t)g * T2_B + b) * T2_ZP;
 #pragma unroll
-            for (int o = 0; o < 10; ++o) dst[o] = zacc[o];
-        }
-        __syncthreads();
-        // (E1) reduce the 8 partials; (E2) softmax cross-entropy gradient, one thread per sample
-        for (int e = tid; e < T2_B * 10; e += T2_THREADS) {
-            const int b = e / 10, o = e - b * 10;
-            float z = b2s[o];
-#pragma unroll
-            for (int g = 0; g < T2_NG; ++g) z += zp[((size_t)g * T2_B + b) * T2_ZP + o];
-            z2s[b * T2_OUTP + o] = z;
-        }
-        __syncthreads();
-        if (tid < T2_B) {
-            float* zr = z2s + tid * T2_OUTP;
-            if (tid < bcur) {
-                float m = zr[0];
-                for (int o = 1; o < OUT; ++o) m = fmaxf(m, zr[o]);
-                float ex[10], sum = 0.f;
-#pragma unroll
-                for (int o = 0; o < 10; ++o) { ex[o] = (o < OUT) ? __expf(zr[o] - m) : 0.f; sum += ex[o]; }
-                const float inv = 1.f / sum, invb = 1.f / (float)bcur;
-                const int yy = ysm[par * T2_B + tid];
-#pragma unroll
-                for (int o = 0; o < 10; ++o) zr[o] = (o < OUT) ? (ex[o] * inv - (o == yy ? 1.f : 0.f)) * invb : 0.f;
-            } else {
-#pragma unroll
-                for (int o = 0; o < 10; ++o) zr[o] = 0.f;
+            for (int o = 0; o < 10; ++o) {
+                zacc[o] += __shfl_xor_sync(0xffffffffu, zacc[o], 4);
+                zacc[o] += __shfl_xor_sync(0xffffffffu, zacc[o], 8);
+                zacc[o] += __shfl_xor_sync(0xffffffffu, zacc[o], 16);
             }
+            float m = -3.0e38f;
 #pragma unroll
-            for (int o = 10; o < T2_OUTP; ++o) zr[o] = 0.f;
+            for (int o = 0; o < 10; ++o) { zacc[o] = (o < OUT) ? zacc[o] + b2s[o] : -3.0e38f; m = fmaxf(m, zacc[o]); }
+            // my outputs: o1 = g, o2 = g + 8 (only groups 0 and 1 have a second one)
+            float z1v = zacc[0], z2v = -3.0e38f;
+#pragma unroll
+            for (int o = 1; o < 8; ++o) z1v = (g == o) ? zacc[o] : z1v;
+            z2v = (g == 0) ? zacc[8] : ((g == 1) ? zacc[9] : z2v);
+            const float e1 = (g < OUT) ? __expf(z1v - m) : 0.f;
+            const float e2 = (g + 8 < OUT && g < 2) ? __expf(z2v - m) : 0.f;
+            float sum = e1 + e2;
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+            const bool live = b < bcur;
+            const float inv = live ? 1.f / sum : 0.f, invb = 1.f / (float)bcur;
+            const int yy = ysm[par * T2_B + b];
+            float* zr = z2s + b * T2_OUTP;
+            zr[g] = (g < OUT && live) ? (e1 * inv - (g == yy ? 1.f : 0.f)) * invb : 0.f;
+            zr[g + 8] = (g < 2 && g + 8 < OUT && live) ? (e2 * inv - (g + 8 == yy ? 1.f : 0.f)) * invb : 0.f;
         }
         if (tid >= 32 && tid < 64 && s + 1 < total_steps)           // labels of the next step
             ysm[(par ^ 1) * T2_B + (tid - 32)] = stage_ys[(size_t)(s + 1) * T2_B + (tid - 32)];
@@ -329,21 +342,24 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
         if (profiling && tid == 0) { const long long t = clock64(); prof[4] += t - t0; t0 = t; }
 
         // (G) update MMA: W1[128 x FP] += A2[128 x 32] . X^T-tile (both operands K-major, K = batch)
-        if (tid == 0) {
+        if (warp == 0) {
             mbar_wait(&mbar[1], ph);                     // X^T tile of this step has landed
             tc_fence_after();
-            const uint32_t taddr = smem_u32(xt), aaddr = smem_u32(a2);
-            for (int n0 = 0; n0 < FP; n0 += 256) {
-                const int nn = min(256, FP - n0);
-                const uint32_t idesc_upd = make_idesc(kFmtTF32, kFmtTF32, 128, nn, false, false);
-                for (int k = 0; k < T2_B / 8; ++k) {
-                    const uint64_t adesc = make_sdesc(aaddr + (uint32_t)k * 256u, 128u, 1024u);
-                    const uint64_t bdesc = make_sdesc(taddr + (uint32_t)(n0 >> 3) * 1024u + (uint32_t)k * 256u,
-                                                      128u, 1024u);
-                    mma_tf32_ss(tmem + t_w1 + (uint32_t)n0, adesc, bdesc, idesc_upd, true);
+            if (elect_one()) {
+                const uint64_t adesc0 = make_sdesc(smem_u32(a2), 128u, 1024u);
+                const uint64_t bdesc0 = make_sdesc(smem_u32(xt), 128u, 1024u);
+                for (int n0 = 0; n0 < FP; n0 += 256) {
+                    const int nn = min(256, FP - n0);
+                    const uint32_t idesc_upd = make_idesc(kFmtTF32, kFmtTF32, 128, nn, false, false);
+                    const uint64_t bn = bdesc0 + (uint64_t)((n0 >> 3) * 64);      // (n0/8) * 1024 B
+#pragma unroll
+                    for (int k = 0; k < T2_B / 8; ++k)
+                        mma_tf32_ss(tmem_u + t_w1 + (uint32_t)n0, adesc0 + (uint64_t)(k * 16), bn + (uint64_t)(k * 16),
+                                    idesc_upd, true);
                 }
+                mma_commit(&mbar[3]);
             }
-            mma_commit(&mbar[3]);
+            __syncwarp();
         }
         // (H) second-layer parameters: thread (j, 0) adds the other half's partial gradients
         if (half == 0) {
@@ -365,7 +381,10 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
     }
 
     // ---- drain the tensor pipe and write everything back ------------------------------------------------
-    if (tid == 0) mma_commit(&mbar[4]);
+    if (warp == 0) {
+        if (elect_one()) mma_commit(&mbar[4]);
+        __syncwarp();
+    }
     mbar_wait(&mbar[4], 0u);
     tc_fence_after();
     __syncthreads();

@@ -90,6 +90,29 @@ GB_DEVICE void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
                  :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
 }
 
+// one elected lane of a CONVERGED warp: code under `if (elect_one())` is known by ptxas to run in a single
+// thread, so tcgen05.mma / bulk-copy operands move to uniform registers without per-lane "waterfall" loops
+GB_DEVICE bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// wait that also acquires writes performed by OTHER CTAs of the cluster (st.async complete_tx)
+GB_DEVICE void mbar_wait_cluster(uint64_t* mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// 16-byte store into a peer CTA's shared memory that signals completion on the PEER's mbarrier
+GB_DEVICE void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];"
+                 :: "r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_mbar) : "memory");
+}
+
 // ---- TMEM <-> registers: each thread of warp w owns TMEM lane 32*(w%4)+laneid -----------------------------
 GB_DEVICE void tmem_ld32(uint32_t taddr, float* v) {   // 32 consecutive columns of my lane
     uint32_t* r = reinterpret_cast<uint32_t*>(v);

@@ -349,7 +349,14 @@ class All2AllGossipNode(GossipNode):
 
     def timed_out(self, t: int, weights: Iterable[float]) -> bool:  # type: ignore[override]
         tout = super().timed_out(t)
-        if tout and self.local_cache:
+        if tout:
+            self.on_timeout(weights)
+        return tout
+
+    def on_timeout(self, weights: Iterable[float]) -> None:
+        """Merge the cached neighbourhood with the mixing weights and train (the part of the
+        reference's ``timed_out`` that has side effects; also called by the native scheduler)."""
+        if self.local_cache:
             senders = list(self.local_cache.keys())
             models = [CACHE.pop(self.local_cache[s]) for s in senders]
             w = np.asarray(weights, dtype=float)
@@ -366,7 +373,6 @@ class All2AllGossipNode(GossipNode):
             for m in models:
                 _release(m)
             self.local_cache = {}
-        return tout
 
     def get_peers(self) -> List[int]:
         return self.p2p_net.get_peers(self.idx)

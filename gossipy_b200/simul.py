@@ -277,17 +277,29 @@ class GossipSimulator(SimulationEventSender):
             sample = [self.nodes[int(i)] for i in np.random.choice(list(self.nodes.keys()), k)]
         else:
             sample = list(self.nodes.values())
+        self._evaluate_nodes(t, sample)
+
+    def _evaluate_nodes(self, t: int, sample: List[GossipNode], defer: bool = False):
+        """Enqueue the evaluation of ``sample`` and report it.  With ``defer`` the (blocking)
+        device->host read is returned as a callable instead, so the caller can enqueue the next
+        round's device work first and keep the GPUs busy while the host waits."""
         local: List[PendingEval] = [n.evaluate_async() for n in sample if n.has_test()]
         glob: List[PendingEval] = []
         if self.data_dispatcher.has_test():
             eval_set = self.data_dispatcher.get_eval_set()
             glob = [n.evaluate_async(eval_set) for n in sample]
-        # everything is enqueued; only now touch the host (one wait per round, not per node)
-        from .parallel import runtime as _prt
-        if local:
-            self.notify_evaluation(t, True, _prt.share_metrics([p.result() for p in local]))
-        if glob:
-            self.notify_evaluation(t, False, _prt.share_metrics([p.result() for p in glob]))
+
+        def finish() -> None:
+            # everything is enqueued; only now touch the host (one wait per round, not per node)
+            from .parallel import runtime as _prt
+            if local:
+                self.notify_evaluation(t, True, _prt.share_metrics([p.result() for p in local]))
+            if glob:
+                self.notify_evaluation(t, False, _prt.share_metrics([p.result() for p in glob]))
+        if defer:
+            return finish
+        finish()
+        return None
 
     def _stream_round_inputs(self) -> None:
         """Fresh inputs for the coming round: host (pinned) -> device, async on each node's stream."""
@@ -338,8 +350,140 @@ class GossipSimulator(SimulationEventSender):
 
     def start(self, n_rounds: int = 100, resume: bool = False) -> None:
         """Run ``n_rounds`` rounds of ``delta`` ticks.  ``resume=True`` continues the clock and
-        the pending message queues of a previous (possibly checkpointed) run."""
-        self._run(n_rounds, resume)
+        the pending message queues of a previous (possibly checkpointed) run.
+
+        ``self.engine`` selects the control plane: ``"python"`` (default; consumes the host RNGs
+        exactly like the reference, used by the differential tests) or ``"native"`` (the C++
+        scheduler of ``csrc/sched``: one call per round instead of ``N x delta`` Python iterations,
+        its own counter-based random streams)."""
+        if self._use_native_engine():
+            self._run_native(n_rounds, resume)
+        else:
+            self._run(n_rounds, resume)
+
+    # -- native control plane ---------------------------------------------------------------------
+    engine = "python"
+    pipeline_eval = True                   # native engine: read round r's metrics after enqueuing round r+1
+    native_utility: Optional[int] = None   # tokenized runs: constant utility evaluated natively
+
+    def _native_supported(self) -> Optional[str]:
+        """``None`` when the C++ scheduler can drive this simulation, else the reason it cannot."""
+        from .ops.native import native_available
+        if not native_available():
+            return "extension not built"
+        for node in self.nodes.values():
+            cls = type(node)
+            if cls.timed_out is not GossipNode.timed_out and not isinstance(node, All2AllGossipNode):
+                return "node class overrides timed_out"
+            if cls.get_peer is not GossipNode.get_peer:
+                return "node class overrides get_peer"
+        from .core import LinearDelay, UniformDelay
+        if type(self.delay) not in (ConstantDelay, UniformDelay, LinearDelay):
+            return "custom delay model"
+        return None
+
+    def _use_native_engine(self) -> bool:
+        if self.engine != "native":
+            return False
+        why = self._native_supported()
+        if why is not None:
+            LOG.warning("native scheduler unavailable (%s); using the Python loop" % why)
+            return False
+        return True
+
+    def _make_scheduler(self):
+        from .core import AntiEntropyProtocol as AEP, LinearDelay, UniformDelay
+        from .engine import rng as _rng
+        from .ops.native import _try_import
+        C = _try_import()
+        proto = {AEP.PUSH: 1, AEP.PULL: 2, AEP.PUSH_PULL: 3}[self.protocol]
+        sch = C.GossipScheduler(self.n_nodes, self.delta, proto, float(self.drop_prob),
+                                float(self.online_prob), float(self.sampling_eval),
+                                _rng.derive(0x5C4ED))
+        ids = sorted(self.nodes)
+        assert ids == list(range(self.n_nodes)), "node ids must be 0..N-1"
+        sch.set_nodes([1 if self.nodes[i].sync else 0 for i in ids], [int(self.nodes[i].delta) for i in ids],
+                      [int(self.nodes[i].round_len) for i in ids])
+        net = self.nodes[0].p2p_net
+        indptr, indices = net.as_csr()
+        sch.set_topology([int(v) for v in indptr], [int(v) for v in indices])
+        if isinstance(self.delay, UniformDelay):
+            sch.set_delay(1, float(self.delay._min_delay), float(self.delay._max_delay))
+        elif isinstance(self.delay, LinearDelay):
+            sch.set_delay(2, float(self.delay._timexunit), float(self.delay._overhead))
+        else:
+            sch.set_delay(0, float(self.delay._delay), 0.0)
+        self._configure_scheduler(sch)
+        return sch
+
+    def _configure_scheduler(self, sch) -> None:
+        node = self.nodes[0]
+        extras = len(node._payload_extras())
+        sch.set_message_sizes(int(node.model_handler.get_size()) + extras, 1)
+
+    def _run_native(self, n_rounds: int, resume: bool = False) -> None:
+        assert self.initialized, \
+            "The simulator is not inizialized. Please, call the method 'init_nodes'."
+        LOG.info("Simulation started (native scheduler).")
+        from .ops.native import _try_import
+        C = _try_import()
+        sch = self.__dict__.get("_scheduler")
+        if sch is None or not resume:
+            sch = self.__dict__["_scheduler"] = self._make_scheduler()
+            self._native_msgs: Dict[int, Message] = {}
+            self._clock = 0
+        SEND, DROP, DELIVER, RSEND, RDELIVER, EVAL, TIMEOUT = (C.EV_SEND, C.EV_DROP, C.EV_DELIVER,
+                                                              C.EV_REPLY_SEND, C.EV_REPLY_DELIVER, C.EV_EVAL,
+                                                              C.EV_TIMEOUT)
+        msgs = self._native_msgs
+        prev_finish = None
+        try:
+            for _ in range(n_rounds):
+                if self.stream_inputs:
+                    self._stream_round_inputs()
+                events = sch.run(1)
+                pending_reply: Optional[Message] = None
+                eval_nodes: List[GossipNode] = []
+                t_last = int(sch.clock) - 1
+                for kind, t, a, b, slot, aux in events.tolist():
+                    if kind == SEND:
+                        msg = self._native_send(self.nodes[a], t, b)
+                        msgs[slot] = msg
+                        self.notify_message(False, msg)
+                    elif kind == DROP:
+                        self._lost(msgs.pop(slot, None))
+                    elif kind == DELIVER:
+                        pending_reply = self.nodes[b].receive(t, msgs.pop(slot))
+                    elif kind == RSEND:
+                        msgs[aux] = pending_reply
+                        pending_reply = None
+                    elif kind == RDELIVER:
+                        reply = msgs.pop(slot)
+                        self.notify_message(False, reply)
+                        self.nodes[a].receive(t, reply)
+                    elif kind == EVAL:
+                        eval_nodes.append(self.nodes[a])
+                    elif kind == TIMEOUT:
+                        self._native_timeout(self.nodes[a], t)
+                # software pipelining of the host: the metrics of round r are read back only after
+                # round r+1 has been enqueued (evaluation snapshots the statistics on the device)
+                finish = self._evaluate_nodes(t_last, eval_nodes, defer=self.pipeline_eval)
+                if prev_finish is not None:
+                    prev_finish()
+                prev_finish = finish
+                self._clock = int(sch.clock)
+                self.notify_timestep(t_last)
+        except KeyboardInterrupt:
+            LOG.warning("Simulation interrupted by user.")
+        if prev_finish is not None:
+            prev_finish()
+        self.notify_end()
+
+    def _native_send(self, node: GossipNode, t: int, peer: int) -> Message:
+        return node.send(t, peer, self.protocol)
+
+    def _native_timeout(self, node: GossipNode, t: int) -> None:
+        pass
 
     # -- checkpointing ---------------------------------------------------------------------------
     def save(self, filename: str) -> None:
@@ -361,6 +505,8 @@ class GossipSimulator(SimulationEventSender):
     def __getstate__(self) -> Dict[str, Any]:
         st = dict(self.__dict__)
         st["_receiver_list"] = list(self._receivers)
+        st.pop("_scheduler", None)      # native scheduler state is not checkpointed: a resumed run
+        st.pop("_native_msgs", None)    # re-draws its schedule (the Python engine resumes exactly)
         return st
 
     def __repr__(self) -> str:
@@ -429,6 +575,16 @@ class TokenizedGossipSimulator(GossipSimulator):
     def __getstate__(self) -> Dict[str, Any]:
         return super().__getstate__()
 
+    def _native_supported(self) -> Optional[str]:
+        if self.native_utility is None:
+            return "utility_fun is a Python callback (set native_utility to a constant to go native)"
+        return super()._native_supported()
+
+    def _configure_scheduler(self, sch) -> None:
+        super()._configure_scheduler(sch)
+        kind, C, A, k = self.token_account_proto.spec()
+        sch.set_token_account(int(kind) + 1, int(C), int(A), max(1, int(k)), int(self.native_utility))
+
 
 class All2AllGossipSimulator(GossipSimulator):
     """Decentralised SGD with neighbourhood averaging (ref ``simul.py:720-852``).
@@ -446,4 +602,14 @@ class All2AllGossipSimulator(GossipSimulator):
     def start(self, W_matrix: MixingMatrix, n_rounds: int = 100,  # type: ignore[override]
               resume: bool = False) -> None:
         self._W = W_matrix
-        self._run(n_rounds, resume)
+        if self._use_native_engine():
+            self._run_native(n_rounds, resume)
+        else:
+            self._run(n_rounds, resume)
+
+    def _configure_scheduler(self, sch) -> None:
+        super()._configure_scheduler(sch)
+        sch.set_broadcast(True)
+
+    def _native_timeout(self, node: GossipNode, t: int) -> None:
+        node.on_timeout(self._W[node.idx])     # type: ignore[attr-defined]

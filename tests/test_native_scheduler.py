@@ -1,0 +1,137 @@
+"""The C++ scheduler (csrc/sched) against the Python round loop: same semantics, different RNG streams,
+so deterministic set-ups must agree exactly and randomised ones statistically."""
+import numpy as np
+import pytest
+import torch
+
+from gossipy_b200.ops.native import native_available
+
+pytestmark = pytest.mark.skipif(not native_available(), reason="extension not built")
+
+
+def _sim(engine, protocol, n=6, ring=False, drop=0., online=1., delay=None, rounds=4, tokenized=None,
+         all2all=False, sampling_eval=0.):
+    import gossipy_b200 as g
+    from gossipy_b200.core import (AntiEntropyProtocol, ConstantDelay, CreateModelMode, StaticP2PNetwork,
+                                   UniformMixing)
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import TorchModelHandler, WeightedTMH
+    from gossipy_b200.model.nn import LogisticRegression
+    from gossipy_b200.node import All2AllGossipNode, GossipNode
+    from gossipy_b200.simul import (All2AllGossipSimulator, GossipSimulator, SimulationReport,
+                                    TokenizedGossipSimulator)
+    g.set_seed(3)
+    (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+    disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
+    topo = None
+    if ring:   # directed ring: every node has exactly ONE peer -> peer choice is deterministic
+        topo = np.zeros((n, n), dtype=int)
+        for i in range(n):
+            topo[i, (i + 1) % n] = 1
+    net = StaticP2PNetwork(n, topo)
+    cls = WeightedTMH if all2all else TorchModelHandler
+    proto = cls(LogisticRegression(57, 2), torch.optim.SGD, {"lr": .5}, torch.nn.CrossEntropyLoss(),
+                batch_size=16)
+    node_cls = All2AllGossipNode if all2all else GossipNode
+    nodes = node_cls.generate(disp, net, proto, 10, True)
+    kw = dict(drop_prob=drop, online_prob=online, delay=delay or ConstantDelay(0), sampling_eval=sampling_eval)
+    if tokenized is not None:
+        sim = TokenizedGossipSimulator(nodes, disp, tokenized, lambda a, b, m: 1, 10, protocol, **kw)
+        sim.native_utility = 1
+    elif all2all:
+        sim = All2AllGossipSimulator(nodes, disp, 10, protocol, **kw)
+    else:
+        sim = GossipSimulator(nodes, disp, 10, protocol, **kw)
+    sim.progress = False
+    sim.engine = engine
+    rep = SimulationReport()
+    sim.add_receiver(rep)
+    sim.init_nodes(seed=9)
+    if all2all:
+        sim.start(UniformMixing(net), rounds)
+    else:
+        sim.start(rounds)
+    rows = {i: nd.model_handler.row.clone() for i, nd in sim.nodes.items()}
+    return rep, rows, sim
+
+
+@pytest.mark.parametrize("protocol", ["PUSH", "PULL", "PUSH_PULL"])
+def test_deterministic_ring_native_equals_python(protocol):
+    """One peer per node, no faults: the event order is fully determined by the nodes' offsets except
+    for the per-round shuffle, which only permutes sends of DIFFERENT ticks... so make it exact by
+    comparing order-independent outcomes: counters, ages and evaluation curves."""
+    from gossipy_b200.core import AntiEntropyProtocol
+    import gossipy_b200 as g
+    p = getattr(AntiEntropyProtocol, protocol)
+    rep_p, rows_p, sim_p = _sim("python", p, ring=True)
+    g.CACHE.clear()
+    rep_n, rows_n, sim_n = _sim("native", p, ring=True)
+    assert rep_p._sent_messages == rep_n._sent_messages
+    assert rep_p._failed_messages == rep_n._failed_messages == 0
+    assert rep_p._total_size == rep_n._total_size
+    ages_p = sorted(int(n.model_handler.n_updates) for n in sim_p.nodes.values())
+    ages_n = sorted(int(n.model_handler.n_updates) for n in sim_n.nodes.values())
+    assert ages_p == ages_n
+    assert len(rep_p.get_evaluation(False)) == len(rep_n.get_evaluation(False)) == 4
+    assert len(g.CACHE) == 0
+
+
+def test_faulty_run_statistics_and_no_leaks():
+    from gossipy_b200.core import AntiEntropyProtocol, UniformDelay
+    import gossipy_b200 as g
+    rep, _, sim = _sim("native", AntiEntropyProtocol.PUSH_PULL, n=8, drop=.2, online=.7, delay=UniformDelay(0, 4),
+                       rounds=30, sampling_eval=.5)
+    # every node fires once per round; requests + delivered replies are counted as sent
+    assert 8 * 30 <= rep._sent_messages <= 2 * 8 * 30
+    frac_failed = rep._failed_messages / (8 * 30 * 2)
+    assert .15 < frac_failed < .6
+    assert len(rep.get_evaluation(False)) == 30
+    # in-flight snapshots: only messages still queued may hold cache entries
+    assert len(g.CACHE) <= sim._scheduler.pending + 1
+    acc = [e["accuracy"] for _, e in rep.get_evaluation(False)]
+    assert np.mean(acc[-5:]) > np.mean(acc[:3]) - .05
+
+
+def test_tokenized_and_all2all_native():
+    from gossipy_b200.core import AntiEntropyProtocol
+    from gossipy_b200.flow_control import RandomizedTokenAccount, SimpleTokenAccount
+    import gossipy_b200 as g
+    rep, _, sim = _sim("native", AntiEntropyProtocol.PUSH, n=8, rounds=40, tokenized=RandomizedTokenAccount(C=6, A=3))
+    assert rep._sent_messages > 0
+    bal = sim._scheduler.token_balances()
+    assert all(0 <= b <= 40 for b in bal)
+    g.CACHE.clear()
+    # warm-up: with C=20, A=10 nothing is sent in the first rounds (proactive() == 0 while a < A-1)
+    rep2, _, _ = _sim("native", AntiEntropyProtocol.PUSH, n=8, rounds=5, tokenized=RandomizedTokenAccount(C=20, A=10))
+    assert rep2._sent_messages == 0
+    g.CACHE.clear()
+    rep3, rows3, _ = _sim("native", AntiEntropyProtocol.PUSH, n=5, rounds=6, all2all=True)
+    g.CACHE.clear()
+    rep4, rows4, _ = _sim("python", AntiEntropyProtocol.PUSH, n=5, rounds=6, all2all=True)
+    assert rep3._sent_messages == rep4._sent_messages == 5 * 4 * 6
+    assert rep3._total_size == rep4._total_size
+
+
+def test_scheduler_event_stream_invariants():
+    from gossipy_b200.ops.native import _try_import
+    C = _try_import()
+    sch = C.GossipScheduler(50, 20, 3, 0.1, 0.8, 0.1, 1234)      # PUSH_PULL
+    sch.set_delay(1, 0, 5)
+    sch.set_message_sizes(117, 1)
+    ev = sch.run(10)
+    kinds = ev[:, 0]
+    sends = ev[kinds == C.EV_SEND]
+    assert len(sends) == 50 * 10                                    # sync nodes fire exactly once per round
+    assert (np.diff(ev[:, 1]) >= 0).all()                           # time never runs backwards
+    ids = set(sends[:, 4].tolist())
+    delivered = ev[kinds == C.EV_DELIVER][:, 4].tolist()
+    dropped = ev[kinds == C.EV_DROP][:, 4].tolist()
+    assert set(delivered) <= ids and len(delivered) == len(set(delivered))
+    # every request is delivered, dropped or still in flight -- never both
+    assert not (set(delivered) & set(dropped))
+    replies = ev[kinds == C.EV_REPLY_SEND]
+    assert len(replies) == len(delivered)
+    assert sch.sent == len(sends) + int((kinds == C.EV_REPLY_DELIVER).sum())
+    assert sch.failed == len(dropped)
+    assert (kinds == C.EV_EVAL).sum() == 10 * 5
