@@ -20,14 +20,14 @@ import random
 from abc import ABC, abstractmethod
 from typing import Any, Dict, Iterable, Optional, Tuple
 
-# Kernels of this package spin on flags written by other GPUs; CUDA's default lazy function loading
-# may need a device-wide synchronisation to load a not-yet-used kernel, which deadlocks behind such
-# a spinning kernel.  Ask for eager loading (effective when CUDA has not been initialised yet; the
-# extension additionally force-loads its own kernels on first use, see ops/native.py).
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+# NOTE on CUDA lazy loading: kernels of this package may spin on flags written by other GPUs, and
+# loading a not-yet-used kernel can need a device-wide synchronisation that would wait behind such a
+# spinning kernel.  The extension therefore force-loads ITS OWN kernels on first use (ops/native.py).
+# (Setting CUDA_MODULE_LOADING=EAGER globally is not an option: it makes the first cuBLAS call load
+# the whole library, minutes on a cold box.)
 
-import numpy as np  # noqa: E402
-import torch  # noqa: E402
+import numpy as np
+import torch
 
 __version__ = "0.1.0"
 

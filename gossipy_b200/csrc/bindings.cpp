@@ -352,10 +352,27 @@ void flag_add(int64_t flag_ptr, int64_t value) {
     launch_flag_add((uint32_t*)(uintptr_t)flag_ptr, (uint32_t)value, cur_stream());
     GB_LAUNCH_CHECK();
 }
+// one-shot all-reduce (mean) of symmetric buffers: NVLS multicast when mc_ptr != 0, P2P pull otherwise
+void allreduce_mean(at::Tensor out, int64_t mc_ptr, std::vector<int64_t> buf_ptrs, std::vector<int64_t> flag_ptrs,
+                    int64_t rank, int64_t epoch, double scale, int64_t n) {
+    check_row(out, "out");
+    const int world = (int)buf_ptrs.size();
+    TORCH_CHECK(world >= 1 && world <= kMaxRanks && (int)flag_ptrs.size() == world && n <= out.numel());
+    AllReduceArgs a{};
+    a.mc = reinterpret_cast<const float*>((uintptr_t)mc_ptr);
+    for (int r = 0; r < world; ++r) {
+        a.bufs[r] = reinterpret_cast<const float*>((uintptr_t)buf_ptrs[r]);
+        a.flags[r] = reinterpret_cast<uint32_t*>((uintptr_t)flag_ptrs[r]);
+    }
+    a.rank = (int)rank; a.world = world; a.epoch = (uint32_t)epoch; a.scale = (float)scale;
+    c10::cuda::CUDAGuard guard(out.device());
+    TORCH_CHECK(launch_allreduce_mean(out.data_ptr<float>(), a, n, cur_stream()), "allreduce_mean: bad arguments");
+    GB_LAUNCH_CHECK();
+}
 int64_t device_sm_count() { return sm_count(); }
 void preload() {
     preload_merge(); preload_optim(); preload_small(); preload_eval(); preload_train_cluster();
-    preload_train_tc(); preload_train_tc2(); preload_stage(); preload_probe();
+    preload_train_tc(); preload_train_tc2(); preload_stage(); preload_probe(); preload_nvls();
     cudaGetLastError();
 }
 
@@ -405,5 +422,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("flag_add", &gb::flag_add);
     m.def("device_sm_count", &gb::device_sm_count);
     m.def("preload", &gb::preload);
+    m.def("allreduce_mean", &gb::allreduce_mean);
     gb::bind_scheduler(m);
 }

@@ -33,6 +33,17 @@ void launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);
 void launch_flag_wait(const uint32_t* flag, uint32_t value, cudaStream_t stream);
 void launch_flag_add(uint32_t* flag, uint32_t value, cudaStream_t stream);
 
+// ---- nvls.cu: one-shot all-reduce (mean) over symmetric buffers, NVLS multicast or P2P pull -----------
+constexpr int kMaxRanks = 16;
+struct AllReduceArgs {
+    const float* mc;                    // multicast VA of the symmetric contribution buffer (null: P2P pull)
+    const float* bufs[kMaxRanks];       // unicast VA of every rank's contribution buffer (peer-mapped)
+    uint32_t* flags[kMaxRanks];         // every rank's flag block: ready[world] then done[world]
+    int rank, world; uint32_t epoch; float scale;
+};
+bool launch_allreduce_mean(float* out, const AllReduceArgs& a, int64_t n, cudaStream_t stream);
+void preload_nvls();
+
 // ---- optim.cu ------------------------------------------------------------------------------------
 void launch_sgd(float* p, const float* g, int64_t n, float lr, float wd, float momentum, float* buf,
                 float dampening, bool nesterov, bool first, const float* scale, cudaStream_t stream);

@@ -1,0 +1,102 @@
+// One-shot all-reduce (weighted mean) of the gossip nodes' parameter rows: the all-to-all round of
+// decentralised SGD on a clique (gossipy/simul.py:756-852, node.py:833-845) as ONE kernel per GPU.
+//
+// Every rank keeps its contribution in a SYMMETRIC buffer (same offset on every GPU).  With NVLink
+// SHARP ("NVLS") the buffers are bound to one multicast object: a single
+//     multimem.ld_reduce.relaxed.sys.global.add.v4.f32
+// makes the NVSwitch fetch the 16 bytes at that offset from ALL GPUs, add them inside the switch and
+// return the sum -- each GPU receives P*4 bytes instead of (W-1)*P*4 and issues no per-peer loads.
+// Without multicast support the same kernel pulls the W-1 peer buffers with ordinary P2P loads.
+//
+// The kernel is self-synchronising (no NCCL, no host barrier): CTA 0 publishes "my input is complete"
+// to every peer's flag block (st.release.sys), all CTAs wait until every peer has published this
+// epoch, reduce, and the last CTA to finish tells every peer "I am done reading" and waits for the
+// same message from all of them, so that on kernel exit the symmetric buffers may be overwritten.
+#include "common.cuh"
+#include "kernels.h"
+#include <algorithm>
+
+namespace gb {
+
+constexpr int kNvlsThreads = 256;
+
+GB_DEVICE float4 multimem_ld_reduce_add(const float* mc_addr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+    return v;
+}
+
+template <bool MULTICAST>
+__global__ void __launch_bounds__(kNvlsThreads)
+allreduce_mean_kernel(float* __restrict__ out, const AllReduceArgs a, int64_t n, uint32_t* ticket) {
+    const int tid = threadIdx.x;
+    // ---- start barrier ------------------------------------------------------------------------------
+    if (blockIdx.x == 0 && tid < a.world) gb_st_release_sys(a.flags[tid] + a.rank, a.epoch);        // ready[rank] @ peer tid
+    if (tid < a.world) {
+        const uint32_t* mine = a.flags[a.rank] + tid;
+        while ((int32_t)(gb_ld_acquire_sys(mine) - a.epoch) < 0) __nanosleep(32);
+    }
+    __syncthreads();
+    // ---- reduce ---------------------------------------------------------------------------------------
+    const int64_t nvec = n / 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + tid; i < nvec; i += stride) {
+        float4 acc;
+        if (MULTICAST) {
+            acc = multimem_ld_reduce_add(a.mc + 4 * i);
+        } else {
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int r = 0; r < a.world; ++r) {
+                const float4 v = gb_ld_stream(reinterpret_cast<const float4*>(a.bufs[r]) + i);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        o4[i] = make_float4(acc.x * a.scale, acc.y * a.scale, acc.z * a.scale, acc.w * a.scale);
+    }
+    // ---- end barrier: nobody leaves before every rank has finished reading ----------------------------------
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const bool last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+        if (last) {
+            *ticket = 0u;
+            for (int r = 0; r < a.world; ++r) gb_st_release_sys(a.flags[r] + a.world + a.rank, a.epoch);  // done[rank] @ peer r
+            for (int r = 0; r < a.world; ++r) {
+                const uint32_t* d = a.flags[a.rank] + a.world + r;
+                while ((int32_t)(gb_ld_acquire_sys(d) - a.epoch) < 0) __nanosleep(32);
+            }
+        }
+    }
+}
+
+static uint32_t* g_nvls_ticket[16] = {nullptr};
+
+bool launch_allreduce_mean(float* out, const AllReduceArgs& a, int64_t n, cudaStream_t stream) {
+    if (a.world < 1 || a.world > kMaxRanks || n % 4 != 0) return false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_nvls_ticket[dev] == nullptr) {
+        cudaMalloc(&g_nvls_ticket[dev], sizeof(uint32_t));
+        cudaMemset(g_nvls_ticket[dev], 0, sizeof(uint32_t));
+    }
+    // few CTAs: the message is small (318 KB for the flagship MLP) and every CTA polls the flags
+    const int64_t nvec = n / 4;
+    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((nvec + kNvlsThreads * 4 - 1) / (kNvlsThreads * 4),
+                                                             (int64_t)sm_count()));
+    if (a.mc != nullptr)
+        allreduce_mean_kernel<true><<<blocks, kNvlsThreads, 0, stream>>>(out, a, n, g_nvls_ticket[dev]);
+    else
+        allreduce_mean_kernel<false><<<blocks, kNvlsThreads, 0, stream>>>(out, a, n, g_nvls_ticket[dev]);
+    return true;
+}
+
+void preload_nvls() {
+    cudaFuncAttributes at;
+    cudaFuncGetAttributes(&at, allreduce_mean_kernel<true>);
+    cudaFuncGetAttributes(&at, allreduce_mean_kernel<false>);
+}
+
+}  // namespace gb

@@ -27,7 +27,8 @@ from typing import Any, Callable, DefaultDict, Dict, Iterable, List, Optional, T
 import numpy as np
 
 from . import CACHE, LOG, CacheKey
-from .core import AntiEntropyProtocol, ConstantDelay, Delay, Message, MixingMatrix, UniformMixing
+from .core import (AntiEntropyProtocol, ConstantDelay, Delay, Message, MessageType, MixingMatrix,
+                   UniformMixing)
 from .data import DataDispatcher
 from .flow_control import TokenAccount
 from .model.handler import ModelHandler, PendingEval
@@ -271,13 +272,14 @@ class GossipSimulator(SimulationEventSender):
             else:
                 self._lost(reply)
 
-    def _evaluate_round(self, t: int) -> None:
+    def _eval_sample(self) -> List[GossipNode]:
         if self.sampling_eval > 0:
             k = max(int(self.n_nodes * self.sampling_eval), 1)
-            sample = [self.nodes[int(i)] for i in np.random.choice(list(self.nodes.keys()), k)]
-        else:
-            sample = list(self.nodes.values())
-        self._evaluate_nodes(t, sample)
+            return [self.nodes[int(i)] for i in np.random.choice(list(self.nodes.keys()), k)]
+        return list(self.nodes.values())
+
+    def _evaluate_round(self, t: int) -> None:
+        self._evaluate_nodes(t, self._eval_sample())
 
     def _evaluate_nodes(self, t: int, sample: List[GossipNode], defer: bool = False):
         """Enqueue the evaluation of ``sample`` and report it.  With ``defer`` the (blocking)
@@ -505,6 +507,7 @@ class GossipSimulator(SimulationEventSender):
     def __getstate__(self) -> Dict[str, Any]:
         st = dict(self.__dict__)
         st["_receiver_list"] = list(self._receivers)
+        st.pop("_collective", None)
         st.pop("_scheduler", None)      # native scheduler state is not checkpointed: a resumed run
         st.pop("_native_msgs", None)    # re-draws its schedule (the Python engine resumes exactly)
         return st
@@ -600,8 +603,16 @@ class All2AllGossipSimulator(GossipSimulator):
                 self._dispatch(node.send(t, peer, self.protocol), t)
 
     def start(self, W_matrix: MixingMatrix, n_rounds: int = 100,  # type: ignore[override]
-              resume: bool = False) -> None:
+              resume: bool = False, synchronous: bool = False) -> None:
+        """``synchronous=True`` runs textbook D-PSGD rounds (Koloskova 2020): every round ALL nodes
+        average simultaneously and then train, instead of the reference's tick-by-tick simulation
+        in which nodes fire at different offsets inside a round.  On a clique with uniform mixing
+        this is one all-reduce per round -- executed by the one-shot NVLS kernel
+        (``parallel.collectives.SymmetricAllReduce``) -- followed by the fused local update."""
         self._W = W_matrix
+        if synchronous:
+            self._run_synchronous(n_rounds)
+            return
         if self._use_native_engine():
             self._run_native(n_rounds, resume)
         else:
@@ -613,3 +624,97 @@ class All2AllGossipSimulator(GossipSimulator):
 
     def _native_timeout(self, node: GossipNode, t: int) -> None:
         node.on_timeout(self._W[node.idx])     # type: ignore[attr-defined]
+
+    # -- synchronous D-PSGD rounds: all-reduce + local update ------------------------------------------
+    def _run_synchronous(self, n_rounds: int) -> None:
+        assert self.initialized, \
+            "The simulator is not inizialized. Please, call the method 'init_nodes'."
+        import torch
+        from . import ops
+        from .engine import arena as _arena
+        from .parallel import runtime as _prt
+        from .parallel.collectives import SymmetricAllReduce
+        ids = sorted(self.nodes)
+        n = len(ids)
+        net = self.nodes[ids[0]].p2p_net
+        for i in ids:
+            if sorted(net.get_peers(i)) != [j for j in ids if j != i]:
+                raise ValueError("synchronous all-to-all rounds need a clique")
+            w = np.asarray(self._W[i], dtype=float)
+            if not np.allclose(w, 1.0 / n):
+                raise ValueError("synchronous all-to-all rounds need uniform mixing weights 1/N")
+        if self.drop_prob or self.online_prob < 1 or self.delay.get(None) != 0:  # type: ignore[arg-type]
+            raise ValueError("synchronous all-to-all rounds model a fault-free network")
+        handlers = {i: self.nodes[i].model_handler for i in ids}
+        mine = [i for i in ids if handlers[i]._mine()]
+        h0 = handlers[ids[0]]
+        dev = h0.device
+        numel = h0._row_numel
+        coll = self.__dict__.get("_collective")
+        if coll is None or coll.numel != numel:
+            coll = self.__dict__["_collective"] = SymmetricAllReduce(numel, dev)
+        mean = None if len(mine) == 1 else torch.zeros(numel, dtype=torch.float32, device=dev)
+        size = int(h0.get_size())
+        LOG.info("Synchronous all-to-all rounds (%s all-reduce)." % coll.kind)
+        try:
+            for r in range(n_rounds):
+                t = self._clock + self.delta - 1
+                if self.stream_inputs:
+                    self._stream_round_inputs()
+                # message accounting of the equivalent push round: every node pushes to N-1 peers
+                msg = Message(t, ids[0], ids[0], MessageType.PUSH, None)
+                for _ in range(n * (n - 1)):
+                    self.notify_message(False, _SizedMessage(msg, size))
+                cur = _arena.current(dev)
+                # 1. this rank's contribution = sum of its nodes' rows (work joins the current stream)
+                for i in mine:
+                    s_i = handlers[i]._stream()
+                    if s_i is not None:
+                        ev = torch.cuda.Event(); ev.record(s_i); cur.wait_event(ev)
+                rows = [handlers[i].row for i in mine]
+                if rows:
+                    ops.merge_pair(coll.contribution, rows[0], 0.0, 1.0, 0, numel)
+                    if len(rows) > 1:
+                        ops.merge_kway(coll.contribution, rows[1:], [1.0] * len(rows))
+                else:
+                    coll.contribution.zero_()
+                # 2. one-shot all-reduce (NVLS multicast / P2P pull) -> mean model
+                target = handlers[mine[0]].row if len(mine) == 1 else mean
+                coll.mean_into(target, n)
+                if cur is not None:
+                    done = torch.cuda.Event(); done.record(cur)
+                age = max(int(np.max(handlers[i].n_updates)) for i in ids)
+                # 3. every node adopts the mean and trains (adopt fused into the training kernel)
+                for i in ids:
+                    h = handlers[i]
+                    h.n_updates = age if np.ndim(h.n_updates) == 0 else np.maximum(h.n_updates, age)
+                    if h._mine():
+                        s_i = h._stream()
+                        if s_i is not None:
+                            s_i.wait_event(done)
+                        if len(mine) > 1:
+                            if getattr(h, "_fused", False):
+                                h._update(self.nodes[i].data[0], merge_from=(mean, 0.0, 1.0, None))
+                                continue
+                            with _arena.on_stream(s_i):
+                                ops.merge_pair(h.row, mean, 0.0, 1.0, 0, numel)
+                    h._update(self.nodes[i].data[0])
+                self._clock += self.delta
+                self._evaluate_nodes(t, self._eval_sample())
+                self.notify_timestep(t)
+        except KeyboardInterrupt:
+            LOG.warning("Simulation interrupted by user.")
+        self.notify_end()
+
+
+class _SizedMessage:
+    """Accounting stand-in for a model message of known size (synchronous rounds)."""
+
+    def __init__(self, msg: Message, size: int) -> None:
+        self._msg, self._size = msg, size
+
+    def get_size(self) -> int:
+        return self._size
+
+    def __getattr__(self, name: str) -> Any:
+        return getattr(self._msg, name)

@@ -65,6 +65,16 @@ def build(kind, device):
         nodes = All2AllGossipNode.generate(disp, net, proto, 10, True)
         sim = All2AllGossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
         start_args = (UniformMixing(net),)
+    elif kind == "all2all_sync":      # synchronous D-PSGD rounds: one all-reduce (NVLS / P2P / gloo) per round
+        (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=4, eval_on_user=False)
+        net = StaticP2PNetwork(4)
+        proto = WeightedTMH(TorchMLP(784, 10, (100,)), torch.optim.SGD, {"lr": .1},
+                            torch.nn.CrossEntropyLoss(), batch_size=32)
+        nodes = All2AllGossipNode.generate(disp, net, proto, 10, True)
+        sim = All2AllGossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
+        start_args = (UniformMixing(net),)
+        sim._mr_kwargs = {"synchronous": True}
     else:
         raise ValueError(kind)
     sim.progress = False
@@ -78,7 +88,7 @@ def run(kind, device, rounds):
     from gossipy_b200.parallel import runtime as prt
     sim, rep, start_args = build(kind, device)
     sim.init_nodes(seed=5)
-    sim.start(*start_args, rounds)
+    sim.start(*start_args, rounds, **getattr(sim, "_mr_kwargs", {}))
     if device.startswith("cuda"):
         torch.cuda.synchronize()
     sums = {}

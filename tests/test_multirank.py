@@ -15,7 +15,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "_mr_worker.py")
-KINDS = "pegasos,mlp_pushpull,limited_pull,partitioned,all2all"
+KINDS = "pegasos,mlp_pushpull,limited_pull,partitioned,all2all,all2all_sync"
 
 
 def _free_port():
