@@ -81,7 +81,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.1)
 
     def __enter__(self):
         self._thr = threading.Thread(target=self._loop, daemon=True)
@@ -238,7 +238,7 @@ def time_rounds(sim, rounds: int, world: int, resume: bool = True):
 def run_native(args, rank, world):
     import torch
     from gossipy_b200 import ops
-    K = args.steps if args.steps is not None else 20
+    K = args.steps if args.steps is not None else 100
     W = args.warmup if args.warmup is not None else 3
     W = max(W, 3)
     sim, rep = build_native(world, rank, args.train_impl, args.engine)

@@ -66,13 +66,13 @@ def bench_train(impl):
     flops = steps * 32 * (2 * 784 * 100 * 2 + 2 * 100 * 10 * 3)
     print(json.dumps({"op": "mlp1_train", "impl": impl or "auto", "ms_per_update": med, "best_ms": best,
                       "us_per_sgd_step": med * 1e3 / steps, "gflops": flops / med / 1e6}))
-    if impl in ("", "tc2"):   # per-phase cycle counters of the tc2 kernel (thread 0 of CTA 0)
+    if impl in ("", "tc2", "tc3"):   # per-phase cycle counters of the tc2/tc3 kernel (thread 0 of CTA 0)
         from gossipy_b200.ops.native import native
-        prof = native().mlp1_train_tc_debug(row, X, y, DIMS, 32, 1, 0.1, 0.0, 1234, "tc2")[0, :6].tolist()
+        prof = native().mlp1_train_tc_debug(row, X, y, DIMS, 32, 1, 0.1, 0.0, 1234, impl or "tc2")[0, :6].tolist()
         names = ["A+B issue fwd MMA (+wait X tile, +wait upd(s-1), request X^T)", "C wait fwd MMA + tmem_ld",
                  "C exchange (DSMEM + cluster barrier) + relu + hs", "D+E layer-2 fwd, softmax-CE",
                  "F backward + A2 operand", "G+H issue update MMA + W2/b update"]
-        print(json.dumps({"op": "mlp1_train_tc2 phase cycles per step (thread 0)",
+        print(json.dumps({"op": "mlp1_train_%s phase cycles per step (thread 0)" % (impl or "tc2"),
                           "phases": {k: round(v) for k, v in zip(names, prof)}, "sum": round(sum(prof))}))
 
 

@@ -152,7 +152,7 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
     }
     c10::cuda::CUDAGuard guard(row.device());
     const TrainImpl which = impl == "cluster" ? kTrainCluster : impl == "tc" ? kTrainTc
-                            : impl == "tc2" ? kTrainTc2 : kTrainAuto;
+                            : impl == "tc2" ? kTrainTc2 : impl == "tc3" ? kTrainTc3 : kTrainAuto;
     const char* why = "";
     const bool ok = launch_mlp1_train(p, which, cur_stream(), &why);
     TORCH_CHECK(ok, why, " (in=", p.IN, " hidden=", p.H, " out=", p.OUT, " batch=", p.B, ")");
@@ -308,6 +308,17 @@ at::Tensor tc_probe(at::Tensor A, at::Tensor Bm, int64_t variant) {
     return D;
 }
 
+at::Tensor tc_probe2(at::Tensor A, at::Tensor Bm, bool a_sw, bool b_sw) {
+    // D[M x N] = A[M x K] . Bm[N x K]^T on the tensor core (bring-up of operand layouts)
+    const int M = (int)A.size(0), K = (int)A.size(1), N = (int)Bm.size(0);
+    TORCH_CHECK((M == 64 || M == 128) && Bm.size(1) == K && K % 8 == 0 && N % 16 == 0 && N <= 256);
+    TORCH_CHECK((!a_sw && !b_sw) || K % 32 == 0);
+    auto D = at::zeros({M, N}, A.options());
+    launch_tc_probe2(A.data_ptr<float>(), Bm.data_ptr<float>(), D.data_ptr<float>(), M, N, K, a_sw, b_sw, cur_stream());
+    GB_LAUNCH_CHECK();
+    return D;
+}
+
 // ---- multi-process runtime: CUDA-IPC arenas and cross-GPU flags -----------------------------------------
 // One process per GPU (torch.distributed only exchanges the 64-byte IPC handles).  Each rank
 // cudaMalloc's its arena, exports it and maps every peer's arena; a peer row is then a device
@@ -372,7 +383,7 @@ void allreduce_mean(at::Tensor out, int64_t mc_ptr, std::vector<int64_t> buf_ptr
 int64_t device_sm_count() { return sm_count(); }
 void preload() {
     preload_merge(); preload_optim(); preload_small(); preload_eval(); preload_train_cluster();
-    preload_train_tc(); preload_train_tc2(); preload_stage(); preload_probe(); preload_nvls();
+    preload_train_tc(); preload_train_tc2(); preload_train_tc3(); preload_stage(); preload_probe(); preload_nvls();
     cudaGetLastError();
 }
 
@@ -411,6 +422,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kmeans_assign", &gb::kmeans_assign);
     m.def("mf_update", &gb::mf_update);
     m.def("tc_probe", &gb::tc_probe);
+    m.def("tc_probe2", &gb::tc_probe2);
     m.def("ipc_alloc", &gb::ipc_alloc);
     m.def("ipc_free", &gb::ipc_free);
     m.def("ipc_get_handle", &gb::ipc_get_handle);

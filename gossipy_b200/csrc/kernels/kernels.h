@@ -62,11 +62,12 @@ struct TrainParams {
     // (the peer row is pulled over NVLink while the weights are loaded on chip)
     const float* peer; float w_self, w_peer; PeerSync sync;
 };
-enum TrainImpl { kTrainAuto = 0, kTrainCluster = 1, kTrainTc = 2, kTrainTc2 = 3 };
+enum TrainImpl { kTrainAuto = 0, kTrainCluster = 1, kTrainTc = 2, kTrainTc2 = 3, kTrainTc3 = 4 };
 // returns false when the shape is outside the envelope of the requested implementation
 bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const char** why);
 bool mlp1_train_tc(const TrainParams& p, cudaStream_t stream);     // first generation (in-kernel gather)
 bool mlp1_train_tc2(const TrainParams& p, cudaStream_t stream);    // staged operands, 256 threads
+bool mlp1_train_tc3(const TrainParams& p, cudaStream_t stream);    // tc2 + second layer on the tensor core
 // device-side data loader of tc2: shuffled mini-batches in both UMMA operand layouts
 size_t mlp1_stage_bytes(int n, int IN, int B, int epochs, int* FPC_out, int* FP_out, int* steps_out);
 bool launch_mlp1_stage(const float* X, const int64_t* y, int n, int IN, int B, int epochs, uint64_t key,
@@ -96,10 +97,13 @@ void launch_mf_update(float* Xu, float* bu, float* Y, float* c, const float* rat
 void launch_tc_probe(const float* A, const float* Bm, float* D, int K, int N, int variant,
                      cudaStream_t stream);
 
+void launch_tc_probe2(const float* A, const float* Bm, float* D, int M, int N, int K, int a_sw, int b_sw,
+                      cudaStream_t stream);
+
 int sm_count();
 // load every kernel of the extension on the current device (see merge.cu: preload_merge)
 void preload_merge(); void preload_optim(); void preload_small(); void preload_eval();
-void preload_train_cluster(); void preload_train_tc(); void preload_train_tc2(); void preload_stage();
+void preload_train_cluster(); void preload_train_tc(); void preload_train_tc2(); void preload_train_tc3(); void preload_stage();
 void preload_probe();
 
 }  // namespace gb

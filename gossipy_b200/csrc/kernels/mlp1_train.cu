@@ -337,12 +337,18 @@ static bool launch_cluster(const TrainParams& p, bool scaled, cudaStream_t strea
     return cudaLaunchKernelEx(&cfg, kern, q) == cudaSuccess;
 }
 
+static const bool g_default_tc3 = false;   // auto = tc3 -> tc2 -> tc -> cluster
+
 bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const char** why) {
     static const char* kNone = "";
     *why = kNone;
     const bool scaled = p.part_id != nullptr && p.ages != nullptr;
     if (scaled && p.n_parts > MAX_PARTS) { *why = "fused partitioned training supports <= 16 partitions"; return false; }
     if (impl != kTrainCluster && !scaled) {
+        if (impl == kTrainTc3 || (impl == kTrainAuto && g_default_tc3)) {
+            if (mlp1_train_tc3(p, stream)) return true;
+            if (impl == kTrainTc3) { *why = "tcgen05 (tc3) training kernel does not support this configuration"; return false; }
+        }
         if (impl != kTrainTc && mlp1_train_tc2(p, stream)) return true;
         if (impl == kTrainTc2) { *why = "tcgen05 (tc2) training kernel does not support this configuration"; return false; }
         if (mlp1_train_tc(p, stream)) return true;

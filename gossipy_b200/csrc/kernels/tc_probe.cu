@@ -74,11 +74,80 @@ void launch_tc_probe(const float* A, const float* Bm, float* D, int K, int N, in
     tc_probe_kernel<<<1, 128, smem, stream>>>(A, Bm, D, K, N, variant);
 }
 
+// Second probe: D[M x N] = A[M x K] . B[N x K]^T (both K-major, tf32) with M in {64, 128} and each
+// operand either in the no-swizzle core-matrix layout or in the 128-byte-swizzle layout -- the
+// building blocks of the tensor-core second layer of mlp1_train_tc2 (M=64/SW128 logits, tiny-K GEMMs).
+__global__ void __launch_bounds__(128, 1)
+tc_probe2_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ D,
+                 int M, int N, int K, int a_sw, int b_sw) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* a_s = reinterpret_cast<float*>(smem);
+    float* b_s = a_s + ((M * K + 255) & ~255);
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc<512>(&tslot);
+    if (tid == 0) { mbar_init(&mbar, 1); mbar_fence_init(); }
+    const int kch = K / 4;
+    auto put = [&](float* dst, int rows, int r, int k, float v, int sw) {
+        if (sw)   // SW128 K-major: atoms [k/32][r/8] of 8 rows x 128 B, 16-B chunk c of row r stored at c ^ (r%8)
+            dst[((k / 32) * (rows / 8) + r / 8) * 256 + (r % 8) * 32 + ((((k % 32) / 4) ^ (r % 8)) * 4) + (k % 4)] = v;
+        else      // no swizzle: [r/8][k/4][r%8][k%4]
+            dst[((r / 8) * kch + k / 4) * 32 + (r % 8) * 4 + (k % 4)] = v;
+    };
+    for (int i = tid; i < M * K; i += 128) put(a_s, M, i / K, i % K, A[i], a_sw);
+    for (int i = tid; i < N * K; i += 128) put(b_s, N, i / K, i % K, Bm[i], b_sw);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tslot, 0);
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t aaddr = smem_u32(a_s), baddr = smem_u32(b_s);
+            const uint32_t idesc = make_idesc(kFmtTF32, kFmtTF32, M, N, false, false);
+            for (int k = 0; k < K / 8; ++k) {
+                const uint64_t adesc = a_sw ? make_sdesc_sw128(aaddr + (uint32_t)(k / 4) * (uint32_t)(M / 8) * 1024u + (uint32_t)(k % 4) * 32u, 16u, 1024u)
+                                            : make_sdesc(aaddr + (uint32_t)k * 256u, 128u, (uint32_t)kch * 128u);
+                const uint64_t bdesc = b_sw ? make_sdesc_sw128(baddr + (uint32_t)(k / 4) * (uint32_t)(N / 8) * 1024u + (uint32_t)(k % 4) * 32u, 16u, 1024u)
+                                            : make_sdesc(baddr + (uint32_t)k * 256u, 128u, (uint32_t)kch * 128u);
+                mma_tf32_ss(tmem, adesc, bdesc, idesc, k > 0);
+            }
+            mma_commit(&mbar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&mbar, 0);
+    tc_fence_after();
+    // M = 128: row = 32*warp + lane.  M = 64: row = 16*warp + lane for lane < 16 (lanes 16..31 of each quadrant unused)
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int row = (M == 128) ? tid : (lane < 16 ? 16 * warp + lane : -1);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tlane + c0, v);
+        tmem_ld_wait();
+        if (row >= 0)
+            for (int i = 0; i < 16; ++i) D[(size_t)row * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+void launch_tc_probe2(const float* A, const float* Bm, float* D, int M, int N, int K, int a_sw, int b_sw,
+                      cudaStream_t stream) {
+    const size_t smem = (size_t)(((M * K + 255) & ~255) + N * K) * 4 + 2048;
+    cudaFuncSetAttribute(tc_probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_probe2_kernel<<<1, 128, smem, stream>>>(A, Bm, D, M, N, K, a_sw, b_sw);
+}
+
 // force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
 // on a cross-GPU flag could deadlock, so the extension loads everything up front)
 void preload_probe() {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, tc_probe_kernel);
+    cudaFuncGetAttributes(&a, tc_probe2_kernel);
 }
 
 }  // namespace gb

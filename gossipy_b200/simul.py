@@ -34,6 +34,7 @@ from .flow_control import TokenAccount
 from .model.handler import ModelHandler, PendingEval
 from .node import All2AllGossipNode, GossipNode
 from .utils import StringEncoder
+from .utils.profiling import nvtx_range
 
 try:
     import dill as _pickler
@@ -338,10 +339,16 @@ class GossipSimulator(SimulationEventSender):
                 for i in self._node_order:
                     self._tick_node(int(i), t)
                 is_online = np.random.random(self.n_nodes) <= self.online_prob
-                self._deliver_messages(t, is_online)
-                self._deliver_replies(t, is_online)
+                if self._msg_queues.get(t) or self._rep_queues.get(t):
+                    with nvtx_range("deliver"):
+                        self._deliver_messages(t, is_online)
+                        self._deliver_replies(t, is_online)
+                else:
+                    self._msg_queues.pop(t, None)
+                    self._rep_queues.pop(t, None)
                 if (t + 1) % self.delta == 0:
-                    self._evaluate_round(t)
+                    with nvtx_range("evaluate"):
+                        self._evaluate_round(t)
                 self.notify_timestep(t)
                 self._clock = t + 1
         except KeyboardInterrupt:
@@ -443,7 +450,8 @@ class GossipSimulator(SimulationEventSender):
             for _ in range(n_rounds):
                 if self.stream_inputs:
                     self._stream_round_inputs()
-                events = sch.run(1)
+                with nvtx_range("schedule"):
+                    events = sch.run(1)
                 pending_reply: Optional[Message] = None
                 eval_nodes: List[GossipNode] = []
                 t_last = int(sch.clock) - 1

@@ -93,3 +93,5 @@ def plot_evaluation(evals: List[List[Dict]], title: str = "Untitled plot") -> No
 class StringEncoder(JSONEncoder):
     def default(self, o):  # noqa: D102
         return str(o)
+
+from . import profiling  # noqa: E402,F401  (nvtx_range, DeviceTimer, PhaseProfile)

@@ -259,7 +259,7 @@ def test_tc_forward_first_step_matches_oracle():
     W1, b1, W2, b2 = ref.mlp1_unpack(row.clone(), dims)
     idx = torch.from_numpy(ref.perm_indices(64, rng.mix64(0x77 ^ 0))).cuda()[:32]
     want = torch.relu(X[idx] @ W1.t() + b1)                       # [32, 100]
-    for impl in ("tc", "tc2"):
+    for impl in ("tc", "tc2", "tc3"):
         got = native().mlp1_train_tc_debug(row.clone(), X, y, dims, 32, 1, 0.0, 0.0, 0x77, impl)   # lr = 0
         torch.testing.assert_close(got[:100, :].t(), want, rtol=2e-2, atol=2e-2)
         assert float(got[100:].abs().max()) == 0.0
@@ -271,11 +271,11 @@ def test_tc_forward_first_step_matches_oracle():
                                                 ((64, 16, 4), 200, 16, 1, .001, .1),
                                                 ((512, 128, 16), 128, 32, 1, 0., .05),
                                                 ((784, 100, 10), 300, 32, 0, 0., .1)])
-@pytest.mark.parametrize("impl", ["tc", "tc2"])
+@pytest.mark.parametrize("impl", ["tc", "tc2", "tc3"])
 def test_mlp1_train_tc_matches_oracle(dims, n, bs, ep, wd, lr, impl):
     ops, ref = _ops()
-    if impl == "tc2" and dims[2] > 10:
-        pytest.skip("tc2 handles <= 10 outputs")
+    if impl in ("tc2", "tc3") and dims[2] > 10:
+        pytest.skip("tc2/tc3 handle <= 10 outputs")
     X, y, row = _mlp_problem(n, *dims)
     want = row.clone()
     s1 = ref.mlp1_train(want, X, y, dims, bs, ep, lr, wd, 0xABCDEF)
@@ -295,7 +295,7 @@ def test_mlp1_train_tc_matches_oracle(dims, n, bs, ep, wd, lr, impl):
 # fused MERGE_UPDATE (merge folded into the training kernel's weight load) and the cross-GPU
 # ready/done handshake (exercised here with flags in local memory and two streams)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("impl,tol", [("cluster", 1e-6), ("tc", 5e-2), ("tc2", 5e-2)])
+@pytest.mark.parametrize("impl,tol", [("cluster", 1e-6), ("tc", 5e-2), ("tc2", 5e-2), ("tc3", 5e-2)])
 def test_fused_merge_update_equals_merge_then_update(impl, tol):
     ops, ref = _ops()
     dims = (784, 100, 10)
@@ -365,7 +365,7 @@ def test_ready_done_handshake_orders_reader_after_writer():
     X, y, row = _mlp_problem(100, *dims)
     peer = torch.zeros_like(row)
     peer_val = _mlp_problem(100, *dims, seed=9)[2]
-    for impl in ("cluster", "tc", "tc2"):
+    for impl in ("cluster", "tc", "tc2", "tc3"):
         flags.zero_(); peer.zero_()
         a, b = row.clone(), row.clone()
         torch.cuda.synchronize()
