@@ -337,7 +337,7 @@ static bool launch_cluster(const TrainParams& p, bool scaled, cudaStream_t strea
     return cudaLaunchKernelEx(&cfg, kern, q) == cudaSuccess;
 }
 
-static const bool g_default_tc3 = false;   // auto = tc3 -> tc2 -> tc -> cluster
+static const bool g_default_tc3 = true;    // auto = tc3 -> tc2 -> tc -> cluster
 
 bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const char** why) {
     static const char* kNone = "";

@@ -274,8 +274,9 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
             if (elect_one()) {
                 const uint32_t idesc_d2 = make_idesc(kFmtTF32, kFmtTF32, 64, 16, false, false);
                 const uint32_t ha = smem_u32(hA), wk = smem_u32(w2k);
-#pragma unroll
-                for (int k = 0; k < T3_HP / 8; ++k) {
+                const int ksteps = (H + 7) >> 3;        // columns j >= H of both operands are zero
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
                     const uint64_t ad = make_sdesc_sw128(ha + (uint32_t)(k >> 2) * 8u * 1024u + (uint32_t)(k & 3) * 32u, 16u, 1024u);
                     const uint64_t bd = make_sdesc_sw128(wk + (uint32_t)(k >> 2) * 2u * 1024u + (uint32_t)(k & 3) * 32u, 16u, 1024u);
                     mma_tf32_ss(tmem_u + t_d2, ad, bd, idesc_d2, k > 0);

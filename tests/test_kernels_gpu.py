@@ -404,3 +404,65 @@ def test_stage_loader_layouts():
             assert torch.equal(f.permute(0, 2, 1, 3).reshape(B, FP), half)
             t = xt[s, r].view(FP // 8, 8, 8, 4)          # [fg][bc][fr][4] -> X[4bc+i][fg*8+fr]
             assert torch.equal(t.permute(1, 3, 0, 2).reshape(B, FP), half)
+
+
+# ---------------------------------------------------------------------------------------------
+# one-shot all-reduce kernel (single GPU: the P2P flavour over one rank), native scheduler and
+# synchronous all-to-all rounds on the device
+# ---------------------------------------------------------------------------------------------
+def test_symmetric_allreduce_single_rank():
+    from gossipy_b200.parallel.collectives import SymmetricAllReduce
+    coll = SymmetricAllReduce(79520, torch.device("cuda:0"))
+    assert coll.kind == "p2p"
+    coll.contribution.normal_()
+    out = torch.zeros(79520, device="cuda")
+    for _ in range(3):                      # epochs advance, flags are reused
+        coll.mean_into(out, 4)
+    torch.testing.assert_close(out, coll.contribution / 4)
+
+
+def _gpu_sim(engine, all2all=False, rounds=3):
+    import gossipy_b200 as g
+    from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork, UniformMixing
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import TorchModelHandler, WeightedTMH
+    from gossipy_b200.model.nn import TorchMLP
+    from gossipy_b200.node import All2AllGossipNode, GossipNode
+    from gossipy_b200.simul import All2AllGossipSimulator, GossipSimulator, SimulationReport
+    g.GlobalSettings().set_device("cuda:0")
+    g.set_seed(3)
+    (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(1600, 400)
+    disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=8, eval_on_user=False)
+    net = StaticP2PNetwork(8)
+    cls = WeightedTMH if all2all else TorchModelHandler
+    proto = cls(TorchMLP(784, 10, (100,)), torch.optim.SGD, {"lr": .1}, torch.nn.CrossEntropyLoss(), batch_size=32)
+    nodes = (All2AllGossipNode if all2all else GossipNode).generate(disp, net, proto, 20, True)
+    if all2all:
+        sim = All2AllGossipSimulator(nodes, disp, 20, AntiEntropyProtocol.PUSH)
+    else:
+        sim = GossipSimulator(nodes, disp, 20, AntiEntropyProtocol.PUSH_PULL)
+    sim.progress = False
+    sim.engine = engine
+    rep = SimulationReport(); sim.add_receiver(rep)
+    sim.init_nodes(seed=42)
+    if all2all:
+        sim.start(UniformMixing(net), rounds, synchronous=True)
+    else:
+        sim.start(rounds)
+    torch.cuda.synchronize()
+    return [e["accuracy"] for _, e in rep.get_evaluation(False)], rep
+
+
+def test_native_scheduler_drives_gpu_simulation():
+    import gossipy_b200 as g
+    acc, rep = _gpu_sim("native", rounds=4)
+    assert len(acc) == 4 and acc[-1] > acc[0] - .02 and all(0 <= a <= 1 for a in acc)
+    assert rep._sent_messages == 4 * 8 * 2 and rep._failed_messages == 0      # request + reply per node per round
+    assert len(g.CACHE) == 0
+
+
+def test_synchronous_all2all_rounds_on_gpu():
+    acc, rep = _gpu_sim("python", all2all=True, rounds=4)
+    assert len(acc) == 4 and acc[-1] >= acc[0] - .02
+    assert rep._sent_messages == 4 * 8 * 7
