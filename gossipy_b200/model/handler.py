@@ -846,7 +846,13 @@ class TorchModelHandler(RowHandler):
         if not self.layout.int_buffers:
             return
         if _prt.active():
-            raise NotImplementedError("models with integer buffers (BatchNorm) are single-rank only")
+            # several ranks: the counters follow the same recurrences as the model age (max on merge,
+            # += steps on update, both start at 0), which every rank already replicates -- derive them
+            if self._mine():
+                for name, buf in self.model.named_buffers():
+                    if name in self.layout.int_buffers:
+                        buf.fill_(int(np.max(self.n_updates)))
+            return
         others = [other] if isinstance(other, TorchModelHandler) else list(other)
         mine = dict(self.model.named_buffers())
         for o in others:
