@@ -230,6 +230,8 @@ def time_rounds(sim, rounds: int, world: int, resume: bool = True):
     arena.fork_from_current(dev)          # node streams start after `start`
     sim.start(rounds, resume=resume)
     arena.sync_all_streams(dev)           # ... and `stop` waits for all of them
+    from gossipy_b200.model.handler import join_copy_streams
+    join_copy_streams(dev)                # ... and for the input prefetch issued in the last round
     stop.record()
     barrier(world)
     return start.elapsed_time(stop)

@@ -78,10 +78,14 @@ def bench_train(impl):
 
 def bench_eval():
     X, y, row = problem(10000)
-    med, best = timeit(lambda: ops.mlp1_eval(row, X, y, DIMS, 10), iters=10)
     flops = 10000 * 2 * (784 * 100 + 100 * 10)
-    print(json.dumps({"op": "mlp1_eval", "ms": med, "best_ms": best, "tflops": flops / med / 1e9,
-                      "x_read_gbs": 10000 * 784 * 4 / med / 1e6}))
+    for impl in ("simt", "tc"):
+        ops.EVAL_IMPL = impl
+        med, best = timeit(lambda: ops.mlp1_eval(row, X, y, DIMS, 10), iters=10)
+        print(json.dumps({"op": "mlp1_eval", "impl": impl, "ms": med, "best_ms": best, "tflops": flops / med / 1e9,
+                          "x_read_gbs": 10000 * 784 * 4 / med / 1e6,
+                          "frac_of_measured_hbm": 10000 * 784 * 4 / med / 1e6 / PEAKS["hbm_gbs"]}))
+    ops.EVAL_IMPL = ""
 
 
 def bench_merge():

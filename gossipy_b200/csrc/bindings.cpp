@@ -205,11 +205,32 @@ at::Tensor mlp1_eval(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int6
     TORCH_CHECK(X.size(1) == IN && y.numel() == n);
     c10::cuda::CUDAGuard guard(row.device());
     auto cm = at::zeros({n_classes, n_classes}, row.options().dtype(at::kInt));
+    if (X_lp.has_value()) {      // pre-tiled test set -> tensor-core kernel
+        TORCH_CHECK(X_lp->is_cuda() && X_lp->scalar_type() == at::kFloat && X_lp->is_contiguous() &&
+                    X_lp->numel() == mlp1_eval_pretile_floats(n, IN), "X_lp must come from mlp1_eval_pretile(X)");
+        if (launch_mlp1_eval_tc(row.data_ptr<float>(), X_lp->data_ptr<float>(), y.data_ptr<int64_t>(), n, IN, H,
+                                OUT, (int)n_classes, cm.data_ptr<int>(), cur_stream())) {
+            GB_LAUNCH_CHECK();
+            return cm;
+        }
+    }
     TORCH_CHECK(launch_mlp1_eval(row.data_ptr<float>(), X.data_ptr<float>(), y.data_ptr<int64_t>(), n, IN, H,
                                  OUT, (int)n_classes, cm.data_ptr<int>(), cur_stream()),
                 "mlp1_eval: hidden <= 128 and out <= 16 supported");
     GB_LAUNCH_CHECK();
     return cm;
+}
+
+at::Tensor mlp1_eval_pretile(at::Tensor X) {
+    // the test set in the operand image of the tensor-core evaluation kernel (done once per data set)
+    check_row(X, "X");
+    TORCH_CHECK(X.dim() == 2);
+    const int n = (int)X.size(0), IN = (int)X.size(1);
+    c10::cuda::CUDAGuard guard(X.device());
+    auto out = at::empty({mlp1_eval_pretile_floats(n, IN)}, X.options());
+    launch_mlp1_eval_pretile(X.data_ptr<float>(), n, IN, out.data_ptr<float>(), cur_stream());
+    GB_LAUNCH_CHECK();
+    return out;
 }
 
 int64_t logreg_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t> dims,
@@ -383,7 +404,7 @@ void allreduce_mean(at::Tensor out, int64_t mc_ptr, std::vector<int64_t> buf_ptr
 int64_t device_sm_count() { return sm_count(); }
 void preload() {
     preload_merge(); preload_optim(); preload_small(); preload_eval(); preload_train_cluster();
-    preload_train_tc(); preload_train_tc2(); preload_train_tc3(); preload_stage(); preload_probe(); preload_nvls();
+    preload_train_tc(); preload_train_tc2(); preload_train_tc3(); preload_stage(); preload_probe(); preload_nvls(); preload_eval_tc();
     cudaGetLastError();
 }
 
@@ -412,6 +433,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("key"), py::arg("impl") = "tc");
     m.def("mlp1_stage_debug", &gb::mlp1_stage_debug);
     m.def("mlp1_eval", &gb::mlp1_eval);
+    m.def("mlp1_eval_pretile", &gb::mlp1_eval_pretile);
     m.def("logreg_train", &gb::logreg_train, py::arg("row"), py::arg("X"), py::arg("y"), py::arg("dims"),
           py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"), py::arg("key"),
           py::arg("part_id") = py::none(), py::arg("ages") = py::none(), py::arg("peer") = py::none(),

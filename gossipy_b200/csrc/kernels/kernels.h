@@ -74,6 +74,12 @@ bool launch_mlp1_stage(const float* X, const int64_t* y, int n, int IN, int B, i
                        void* staging, cudaStream_t stream);
 bool launch_mlp1_eval(const float* row, const float* X, const int64_t* y, int n, int IN, int H, int OUT,
                       int n_classes, int* cm, cudaStream_t stream);
+// tcgen05 evaluation on a PRE-TILED copy of the test set (mlp1_eval_tc.cu)
+int64_t mlp1_eval_pretile_floats(int n, int IN);
+void launch_mlp1_eval_pretile(const float* X, int n, int IN, float* out, cudaStream_t stream);
+bool launch_mlp1_eval_tc(const float* row, const float* xt, const int64_t* y, int n, int IN, int H, int OUT,
+                         int n_classes, int* cm, cudaStream_t stream);
+void preload_eval_tc();
 
 // ---- small.cu --------------------------------------------------------------------------------------
 struct LogregParams {

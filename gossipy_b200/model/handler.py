@@ -280,32 +280,70 @@ def to_device_cached(data: Any, dev: torch.device) -> Any:
 def clear_device_cache() -> None:
     _DEVICE_CACHE.clear()
     _PINNED.clear()
+    _STREAMED.clear()
+    _COPY_STREAMS.clear()
 
 
 _PINNED: Dict[int, Tuple[Any, torch.Tensor]] = {}
+_STREAMED: Dict[Tuple[int, str], Dict[str, Any]] = {}     # double buffers of streamed inputs
+_COPY_STREAMS: Dict[str, Any] = {}
 
 
 def refresh_device_copy(data: Any, dev: torch.device) -> int:
-    """Re-upload ``data`` from *pinned* host memory into its resident device buffers (async on the
-    current stream).  Used by the simulators' ``stream_inputs`` mode (fresh inputs every round);
-    returns the number of bytes copied."""
+    """Fresh inputs for the coming round, host (pinned) -> device (``stream_inputs`` mode of the
+    simulators).  Double buffered: the copy for round r+1 runs on a dedicated copy stream while
+    round r computes; calling this at the start of a round (on the node's stream) makes the buffer
+    filled during the previous round current -- the node's stream only waits for that copy's event --
+    and starts the next prefetch into the buffer the previous round has finished reading.
+    Returns the number of bytes copied per call."""
     if data is None or dev.type != "cuda":
         return 0
     total = 0
+    node_stream = torch.cuda.current_stream(dev)
+    cs = _COPY_STREAMS.get(str(dev))
+    if cs is None:
+        cs = _COPY_STREAMS[str(dev)] = torch.cuda.Stream(device=dev)
     for t in (data if isinstance(data, (tuple, list)) else (data,)):
         if not isinstance(t, torch.Tensor) or t.device == dev:
             continue
-        hit = _DEVICE_CACHE.get((id(t), str(dev)))
+        key = (id(t), str(dev))
+        hit = _DEVICE_CACHE.get(key)
         if hit is None or hit[0] is not t:
             _move(t, dev)
-            hit = _DEVICE_CACHE[(id(t), str(dev))]
+            hit = _DEVICE_CACHE[key]
         pin = _PINNED.get(id(t))
         if pin is None or pin[0] is not t:
             src = t.float() if t.dtype == torch.float64 else t
             pin = _PINNED[id(t)] = (t, src.contiguous().pin_memory())
-        hit[1].copy_(pin[1], non_blocking=True)
+        st = _STREAMED.get(key)
+        if st is None:      # first round: upload in line, allocate the second buffer
+            st = _STREAMED[key] = {"bufs": [hit[1], torch.empty_like(hit[1])], "cur": 0, "event": None}
+            hit[1].copy_(pin[1], non_blocking=True)
+        else:               # the prefetched buffer becomes the resident copy
+            st["cur"] ^= 1
+            node_stream.wait_event(st["event"])
+            _DEVICE_CACHE[key] = (t, st["bufs"][st["cur"]])
+        other = st["bufs"][st["cur"] ^ 1]
+        free = torch.cuda.Event()
+        free.record(node_stream)            # the previous round's readers of `other` sit before this point
+        cs.wait_event(free)
+        with torch.cuda.stream(cs):
+            other.copy_(pin[1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        st["event"] = ev
         total += pin[1].numel() * pin[1].element_size()
     return total
+
+
+def join_copy_streams(dev: torch.device) -> None:
+    """Make the current stream wait for every in-flight input prefetch (used before stopping a timer)."""
+    dev = torch.device(dev)
+    cs = _COPY_STREAMS.get(str(dev))
+    if cs is not None and dev.type == "cuda":
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        torch.cuda.current_stream(dev).wait_event(ev)
 
 
 # --------------------------------------------------------------------------------------
