@@ -340,6 +340,57 @@ at::Tensor tc_probe2(at::Tensor A, at::Tensor Bm, bool a_sw, bool b_sw) {
     return D;
 }
 
+// ---- bank of linear learners ----------------------------------------------------------------------------
+static BankView bank_view(at::Tensor W, at::Tensor age, at::Tensor S, at::Tensor slot_age, at::Tensor X, at::Tensor y,
+                          at::Tensor off, at::Tensor cnt, int64_t D, int64_t kind, int64_t mode, double lr) {
+    TORCH_CHECK(W.is_cuda() && W.scalar_type() == at::kFloat && W.is_contiguous() && W.dim() == 2);
+    TORCH_CHECK(S.is_cuda() && S.scalar_type() == at::kFloat && S.is_contiguous() && S.dim() == 2 && S.size(1) == W.size(1));
+    TORCH_CHECK(age.scalar_type() == at::kLong && slot_age.scalar_type() == at::kLong && off.scalar_type() == at::kLong &&
+                cnt.scalar_type() == at::kInt && X.scalar_type() == at::kFloat && y.scalar_type() == at::kFloat);
+    TORCH_CHECK(X.is_contiguous() && y.is_contiguous() && age.numel() == W.size(0) && slot_age.numel() == S.size(0));
+    BankView b{};
+    b.W = W.data_ptr<float>(); b.age = reinterpret_cast<long long*>(age.data_ptr<int64_t>());
+    b.S = S.data_ptr<float>(); b.slot_age = reinterpret_cast<long long*>(slot_age.data_ptr<int64_t>());
+    b.D = (int)D; b.Dp = (int)W.size(1);
+    b.X = X.data_ptr<float>(); b.y = y.data_ptr<float>();
+    b.off = off.data_ptr<int64_t>(); b.cnt = cnt.data_ptr<int>();
+    b.kind = (int)kind; b.mode = (int)mode; b.lr = (float)lr;
+    return b;
+}
+#define BANK_ARGS at::Tensor W, at::Tensor age, at::Tensor S, at::Tensor slot_age, at::Tensor X, at::Tensor y, \
+                  at::Tensor off, at::Tensor cnt, int64_t D, int64_t kind, int64_t mode, double lr
+#define BANK_PASS W, age, S, slot_age, X, y, off, cnt, D, kind, mode, lr
+static void check_idx(const at::Tensor& t) { TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kInt && t.is_contiguous()); }
+void bank_snapshot(BANK_ARGS, at::Tensor sender, at::Tensor slot) {
+    check_idx(sender); check_idx(slot);
+    c10::cuda::CUDAGuard guard(W.device());
+    launch_bank_snapshot(bank_view(BANK_PASS), sender.data_ptr<int>(), slot.data_ptr<int>(), (int)sender.numel(), cur_stream());
+    GB_LAUNCH_CHECK();
+}
+void bank_deliver(BANK_ARGS, at::Tensor recv, at::Tensor slot) {
+    check_idx(recv); check_idx(slot);
+    c10::cuda::CUDAGuard guard(W.device());
+    TORCH_CHECK(launch_bank_deliver(bank_view(BANK_PASS), recv.data_ptr<int>(), slot.data_ptr<int>(), (int)recv.numel(),
+                                    cur_stream()), "bank: dim <= 1024 supported");
+    GB_LAUNCH_CHECK();
+}
+void bank_update(BANK_ARGS, at::Tensor nodes) {
+    check_idx(nodes);
+    c10::cuda::CUDAGuard guard(W.device());
+    TORCH_CHECK(launch_bank_update(bank_view(BANK_PASS), nodes.data_ptr<int>(), (int)nodes.numel(), cur_stream()),
+                "bank: dim <= 1024 supported");
+    GB_LAUNCH_CHECK();
+}
+at::Tensor bank_scores(BANK_ARGS, at::Tensor nodes, at::Tensor Xte) {
+    check_idx(nodes); check_row(Xte, "Xte");
+    c10::cuda::CUDAGuard guard(W.device());
+    auto out = at::empty({nodes.numel(), Xte.size(0)}, W.options());
+    launch_bank_scores(bank_view(BANK_PASS), nodes.data_ptr<int>(), (int)nodes.numel(), Xte.data_ptr<float>(),
+                       (int)Xte.size(0), out.data_ptr<float>(), cur_stream());
+    GB_LAUNCH_CHECK();
+    return out;
+}
+
 // ---- multi-process runtime: CUDA-IPC arenas and cross-GPU flags -----------------------------------------
 // One process per GPU (torch.distributed only exchanges the 64-byte IPC handles).  Each rank
 // cudaMalloc's its arena, exports it and maps every peer's arena; a peer row is then a device
@@ -404,7 +455,7 @@ void allreduce_mean(at::Tensor out, int64_t mc_ptr, std::vector<int64_t> buf_ptr
 int64_t device_sm_count() { return sm_count(); }
 void preload() {
     preload_merge(); preload_optim(); preload_small(); preload_eval(); preload_train_cluster();
-    preload_train_tc(); preload_train_tc2(); preload_train_tc3(); preload_stage(); preload_probe(); preload_nvls(); preload_eval_tc();
+    preload_train_tc(); preload_train_tc2(); preload_train_tc3(); preload_stage(); preload_probe(); preload_nvls(); preload_eval_tc(); preload_bank();
     cudaGetLastError();
 }
 
@@ -443,6 +494,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kmeans_update", &gb::kmeans_update);
     m.def("kmeans_assign", &gb::kmeans_assign);
     m.def("mf_update", &gb::mf_update);
+    m.def("bank_snapshot", &gb::bank_snapshot);
+    m.def("bank_deliver", &gb::bank_deliver);
+    m.def("bank_update", &gb::bank_update);
+    m.def("bank_scores", &gb::bank_scores);
     m.def("tc_probe", &gb::tc_probe);
     m.def("tc_probe2", &gb::tc_probe2);
     m.def("ipc_alloc", &gb::ipc_alloc);

@@ -99,6 +99,24 @@ void launch_kmeans_apply(float* C, const float* X, const int64_t* asg, int n, in
 void launch_mf_update(float* Xu, float* bu, float* Y, float* c, const float* ratings, int m, int k,
                       float reg, float lr, cudaStream_t stream);
 
+// ---- bank.cu: many linear learners (AdaLine / Pegasos) per launch ---------------------------------------
+struct BankView {
+    float* W; long long* age;            // live models [N][Dp] and their ages
+    float* S; long long* slot_age;       // in-flight snapshots [slots][Dp]
+    int D, Dp;
+    const float* X; const float* y;      // all nodes' samples, concatenated; labels as float (+-1)
+    const int64_t* off; const int* cnt;  // node -> first sample, number of samples
+    int kind;                            // 0 AdaLine, 1 Pegasos
+    int mode;                            // CreateModelMode value (1 UPDATE, 2 MERGE_UPDATE, 3 UPDATE_MERGE, 4 PASS)
+    float lr;
+};
+void launch_bank_snapshot(const BankView& b, const int* sender, const int* slot, int n, cudaStream_t st);
+bool launch_bank_deliver(const BankView& b, const int* recv, const int* slot, int n, cudaStream_t st);
+bool launch_bank_update(const BankView& b, const int* nodes, int n, cudaStream_t st);
+void launch_bank_scores(const BankView& b, const int* nodes, int n_nodes, const float* Xte, int n_te, float* scores,
+                        cudaStream_t st);
+void preload_bank();
+
 // ---- tc_probe.cu -----------------------------------------------------------------------------------
 void launch_tc_probe(const float* A, const float* Bm, float* D, int K, int N, int variant,
                      cudaStream_t stream);

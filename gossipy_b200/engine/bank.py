@@ -1,0 +1,368 @@
+"""Batched execution of the linear learners: many gossip nodes per kernel launch.
+
+The reference's experiments with AdaLine / Pegasos models run one node per training sample
+(4 141 nodes, ``main_ormandi_2013.py`` / ``main_giaretta_2019.py``); a model is 57 floats.  Executing
+such a simulation event by event -- one snapshot object and one launch per message -- is pure
+overhead.  :class:`LinearBank` keeps ALL nodes' models in one device tensor ``W[N, Dp]`` (ages in
+``age[N]``), in-flight snapshots in ``S[slots, Dp]``, and turns the event list of a whole round
+(produced by the native scheduler, ``csrc/sched``) into one launch per *phase of a tick*
+(``csrc/kernels/bank.cu``; vectorised torch ops on CPU):
+
+    phase A  all sends of the tick            -> one snapshot launch
+    phase B  deliveries, in conflict-free waves (the k-th delivery of every receiver), each followed
+             by the snapshot of the replies it triggers (PULL / PUSH_PULL)
+    phase C  deliveries of replies, in waves
+    phase D  end of round: one launch computes the scores of all sampled nodes on the test set
+
+Ordering inside a tick is exactly the per-event order of the reference for every single node;
+only events that touch *different* nodes are executed together.  Used by
+``GossipSimulator`` when ``engine="native"`` and the set-up is bankable (plain ``GossipNode``s, one
+shared AdaLine/Pegasos handler configuration, global evaluation set); the handlers' rows and ages
+are written back when the run ends, so the object API sees the same final state.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..core import CreateModelMode
+from ..ops import metrics as _metrics
+
+_RING = 1 << 22     # in-flight message ids are far younger than this
+
+_MODE = {CreateModelMode.UPDATE: 1, CreateModelMode.MERGE_UPDATE: 2, CreateModelMode.UPDATE_MERGE: 3,
+         CreateModelMode.PASS: 4}
+
+
+def bankable(sim) -> Optional[str]:
+    """``None`` if :class:`LinearBank` can execute ``sim``; otherwise the reason it cannot."""
+    from ..model.handler import AdaLineHandler
+    from ..node import GossipNode
+    from ..parallel import runtime as prt
+    if prt.active():
+        return "multi-rank run"
+    nodes = list(sim.nodes.values())
+    h0 = nodes[0].model_handler
+    if not isinstance(h0, AdaLineHandler):
+        return "handler is not AdaLine/Pegasos"
+    for n in nodes:
+        h = n.model_handler
+        if type(n) is not GossipNode:
+            return "node subclass"
+        if type(h) is not type(h0) or h.learning_rate != h0.learning_rate or h.dim != h0.dim or h.mode != h0.mode:
+            return "heterogeneous handlers"
+        if n.has_test():
+            return "per-node test sets"
+    if h0.mode not in _MODE:
+        return "unsupported mode"
+    if type(sim).__name__ != "GossipSimulator":
+        return "simulator variant"
+    return None
+
+
+class LinearBank:
+    def __init__(self, sim) -> None:
+        from ..model.handler import PegasosHandler
+        self.sim = sim
+        ids = sorted(sim.nodes)
+        self.n = len(ids)
+        h0 = sim.nodes[ids[0]].model_handler
+        self.device = h0.device
+        self.D = int(h0.dim)
+        self.Dp = (self.D + 31) // 32 * 32
+        self.kind = 1 if isinstance(h0, PegasosHandler) else 0
+        self.mode = _MODE[h0.mode]
+        self.lr = float(h0.learning_rate)
+        dev = self.device
+        # models and ages
+        self.W = torch.zeros(self.n, self.Dp, dtype=torch.float32, device=dev)
+        self.age = torch.zeros(self.n, dtype=torch.int64, device=dev)
+        for i in ids:
+            h = sim.nodes[i].model_handler
+            self.W[i, :self.D].copy_(h.row[:self.D])
+            self.age[i] = int(h.n_updates)
+        # data: all shards concatenated
+        xs, ys, off, cnt = [], [], [], []
+        pos = 0
+        for i in ids:
+            x, y = sim.nodes[i].data[0]
+            x = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x, dtype=torch.float32)
+            y = torch.as_tensor(np.asarray(y) if not isinstance(y, torch.Tensor) else y, dtype=torch.float32)
+            x = x.reshape(-1, self.D)
+            xs.append(x); ys.append(y.reshape(-1))
+            off.append(pos); cnt.append(x.shape[0]); pos += x.shape[0]
+        self.X = torch.cat(xs).contiguous().to(dev)
+        self.y = torch.cat(ys).contiguous().to(dev)
+        self.off = torch.tensor(off, dtype=torch.int64, device=dev)
+        self.cnt = torch.tensor(cnt, dtype=torch.int32, device=dev)
+        self.max_cnt = int(max(cnt)) if cnt else 0
+        # snapshot slots
+        self.cap = max(64, 4 * self.n)
+        self.S = torch.zeros(self.cap, self.Dp, dtype=torch.float32, device=dev)
+        self.slot_age = torch.zeros(self.cap, dtype=torch.int64, device=dev)
+        self.free = np.arange(self.cap - 1, -1, -1, dtype=np.int64)   # stack of free slots
+        self.n_free = self.cap
+        self.slot_map = np.full(_RING, -1, dtype=np.int64)            # message id (mod ring) -> slot
+        # evaluation set
+        self.Xte = self.yte = None
+        if sim.data_dispatcher.has_test():
+            Xte, yte = sim.data_dispatcher.get_eval_set()
+            self.Xte = torch.as_tensor(Xte, dtype=torch.float32).reshape(-1, self.D).contiguous().to(dev)
+            self.yte = torch.as_tensor(yte).reshape(-1).to(dev)
+        self.size_model = int(h0.get_size())
+
+    # -- low level ops (CUDA kernels / torch on CPU) ---------------------------------------------
+    def _args(self):
+        return (self.W, self.age, self.S, self.slot_age, self.X, self.y, self.off, self.cnt, self.D, self.kind,
+                self.mode, self.lr)
+
+    def _idx(self, a) -> torch.Tensor:
+        return torch.as_tensor(np.asarray(a, dtype=np.int32), device=self.device)
+
+    def _snapshot(self, senders, slots) -> None:
+        if len(senders) == 0:
+            return
+        if self.device.type == "cuda":
+            from ..ops.native import native
+            native().bank_snapshot(*self._args(), self._idx(senders), self._idx(slots))
+            ops._count()
+            return
+        s = torch.as_tensor(np.asarray(senders), dtype=torch.int64)
+        d = torch.as_tensor(np.asarray(slots), dtype=torch.int64)
+        keep = d >= 0
+        self.S[d[keep]] = self.W[s[keep]]
+        self.slot_age[d[keep]] = self.age[s[keep]]
+
+    def _update_cpu(self, w: torch.Tensor, age: torch.Tensor, nodes: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Vectorised over nodes: step i of every node's sequential pass happens at once."""
+        cnt = self.cnt[nodes].long()
+        off = self.off[nodes]
+        for i in range(int(cnt.max()) if cnt.numel() else 0):
+            live = cnt > i
+            if not bool(live.any()):
+                break
+            rows = (off + i)[live]
+            x = torch.zeros(int(live.sum()), self.Dp)
+            x[:, :self.D] = self.X[rows]
+            ys = self.y[rows]
+            wl = w[live]
+            yhat = (wl * x).sum(1)
+            if self.kind == 0:
+                wl = wl + (self.lr * (ys - yhat))[:, None] * x
+                age[live] += 1
+            else:
+                age[live] += 1
+                eta = 1.0 / (age[live].float() * self.lr)
+                wl = wl * (1.0 - eta * self.lr)[:, None]
+                hit = (yhat * ys - 1.0) < 0
+                wl = wl + (hit.float() * eta * ys)[:, None] * x
+            w[live] = wl
+        return w, age
+
+    def _deliver(self, recvs, slots) -> None:
+        if len(recvs) == 0:
+            return
+        if self.device.type == "cuda":
+            from ..ops.native import native
+            native().bank_deliver(*self._args(), self._idx(recvs), self._idx(slots))
+            ops._count()
+            return
+        r = torch.as_tensor(np.asarray(recvs), dtype=torch.int64)
+        s = torch.as_tensor(np.asarray(slots), dtype=torch.int64)
+        keep = s >= 0
+        r, s = r[keep], s[keep]
+        if r.numel() == 0:
+            return
+        w, sv = self.W[r].clone(), self.S[s].clone()
+        aw, asn = self.age[r].clone(), self.slot_age[s].clone()
+        if self.mode == 1:
+            w, aw = sv, asn
+            w, aw = self._update_cpu(w, aw, r)
+        elif self.mode == 2:
+            w = 0.5 * (w + sv)
+            aw = torch.maximum(aw, asn)
+            w, aw = self._update_cpu(w, aw, r)
+        elif self.mode == 3:
+            w, aw = self._update_cpu(w, aw, r)
+            sv, asn = self._update_cpu(sv, asn, r)
+            w = 0.5 * (w + sv)
+            aw = torch.maximum(aw, asn)
+        else:
+            w = sv
+        self.W[r] = w
+        self.age[r] = aw
+
+    def _scores(self, nodes) -> torch.Tensor:
+        if self.device.type == "cuda":
+            from ..ops.native import native
+            out = native().bank_scores(*self._args(), self._idx(nodes), self.Xte)
+            ops._count()
+            return out
+        idx = torch.as_tensor(np.asarray(nodes), dtype=torch.int64)
+        return self.W[idx, :self.D] @ self.Xte.t()
+
+    # -- one round ----------------------------------------------------------------------------------
+    def _alloc(self, k: int) -> np.ndarray:
+        if self.n_free < k:
+            grow = max(self.cap, k)
+            self.S = torch.cat([self.S, torch.zeros(grow, self.Dp, dtype=torch.float32, device=self.device)])
+            self.slot_age = torch.cat([self.slot_age, torch.zeros(grow, dtype=torch.int64, device=self.device)])
+            self.free = np.concatenate([self.free[:self.n_free], np.arange(self.cap, self.cap + grow, dtype=np.int64)])
+            self.n_free += grow
+            self.cap += grow
+        out = self.free[self.n_free - k:self.n_free].copy()
+        self.n_free -= k
+        return out
+
+    def _release(self, slots: np.ndarray) -> None:
+        slots = slots[slots >= 0]
+        k = slots.size
+        if k:
+            if self.n_free + k > self.free.size:
+                self.free = np.concatenate([self.free, np.empty(self.n_free + k - self.free.size, dtype=np.int64)])
+            self.free[self.n_free:self.n_free + k] = slots
+            self.n_free += k
+
+    @staticmethod
+    def _waves(recv: np.ndarray) -> List[np.ndarray]:
+        """Indices of ``recv`` grouped so that wave k holds the k-th occurrence of every receiver."""
+        if recv.size == 0:
+            return []
+        order = np.argsort(recv, kind="stable")
+        sorted_r = recv[order]
+        first = np.r_[True, sorted_r[1:] != sorted_r[:-1]]
+        start = np.maximum.accumulate(np.where(first, np.arange(recv.size), 0))
+        rank = np.empty(recv.size, dtype=np.int64)
+        rank[order] = np.arange(recv.size) - start
+        return [np.flatnonzero(rank == k) for k in range(int(rank.max()) + 1)]
+
+    def run_round(self, events: np.ndarray, C: Any) -> Tuple[List[int], Dict[str, int]]:
+        """Execute one round's event list; returns (nodes to evaluate, message counters)."""
+        kind, tick, a, b, slot, aux = (events[:, i] for i in range(6))
+        counters = {"sent": 0, "sent_size": 0, "failed": 0}
+        evals: List[int] = []
+        if events.shape[0] == 0:
+            return evals, counters
+        bounds = np.flatnonzero(np.r_[True, tick[1:] != tick[:-1], True])
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            k, ea, eb, es, ex = kind[lo:hi], a[lo:hi], b[lo:hi], slot[lo:hi], aux[lo:hi]
+            # ---- phase A: sends (a snapshot per model-carrying message) -------------------------------
+            m = k == C.EV_SEND
+            if m.any():
+                senders, mids, mtypes = ea[m], es[m], ex[m]
+                carries = mtypes != 2                                   # 2 = PULL request
+                slots = np.full(senders.size, -1, dtype=np.int64)
+                slots[carries] = self._alloc(int(carries.sum()))
+                self.slot_map[mids % _RING] = slots
+                self._snapshot(senders, slots)
+                counters["sent"] += int(senders.size)
+                counters["sent_size"] += int(carries.sum()) * self.size_model + int((~carries).sum())
+            # ---- phase B: deliveries (+ the replies they trigger), conflict-free waves ---------------
+            m = k == C.EV_DELIVER
+            if m.any():
+                recv, mids = eb[m], es[m]
+                # replies: EV_REPLY_SEND(slot = request id, aux = reply id) follows its delivery
+                rs = k == C.EV_REPLY_SEND
+                req_ids, rep_ids = es[rs], ex[rs]
+                has_reply = np.isin(mids, req_ids) if req_ids.size else np.zeros(mids.size, dtype=bool)
+                rep_of = None
+                if req_ids.size:
+                    srt = np.argsort(req_ids)
+                    pos_in = np.searchsorted(req_ids[srt], mids[has_reply])
+                    rep_of = np.full(mids.size, -1, dtype=np.int64)
+                    rep_of[has_reply] = rep_ids[srt][pos_in]
+                for idx in self._waves(recv):
+                    r_w, mid_w = recv[idx], mids[idx]
+                    s_w = self.slot_map[mid_w % _RING].copy()
+                    self._deliver(r_w, s_w)
+                    self._release(s_w)
+                    if rep_of is not None:
+                        sel = has_reply[idx]
+                        if sel.any():
+                            rslots = self._alloc(int(sel.sum()))
+                            self.slot_map[rep_of[idx][sel] % _RING] = rslots
+                            self._snapshot(r_w[sel], rslots)
+            # ---- phase C: replies delivered ------------------------------------------------------------
+            m = k == C.EV_REPLY_DELIVER
+            if m.any():
+                recv, mids = ea[m], es[m]
+                counters["sent"] += int(recv.size)
+                counters["sent_size"] += int(recv.size) * self.size_model
+                for idx in self._waves(recv):
+                    s_w = self.slot_map[mids[idx] % _RING].copy()
+                    self._deliver(recv[idx], s_w)
+                    self._release(s_w)
+            # ---- losses: free the snapshot -------------------------------------------------------------
+            m = k == C.EV_DROP
+            if m.any():
+                counters["failed"] += int(m.sum())
+                dropped = self.slot_map[es[m] % _RING].copy()
+                self.slot_map[es[m] % _RING] = -1
+                self._release(dropped)
+            m = k == C.EV_EVAL
+            if m.any():
+                evals.extend(ea[m].tolist())
+        return evals, counters
+
+    # -- evaluation ------------------------------------------------------------------------------------
+    def evaluate(self, nodes: List[int]) -> List[Dict[str, float]]:
+        """Metric dicts of ``nodes`` on the global evaluation set: one scores launch, metrics (incl. the
+        rank-based AUC with average ranks for ties) vectorised over the nodes on the device, one read-back."""
+        if not nodes or self.Xte is None:
+            return []
+        scores = self._scores(nodes)                                   # [E, T]
+        E, T = scores.shape
+        pos = (self.yte > 0)
+        pred = scores >= 0
+        tp = (pred & pos[None, :]).sum(1).double()
+        fp = (pred & ~pos[None, :]).sum(1).double()
+        fn = (~pred & pos[None, :]).sum(1).double()
+        tn = (~pred & ~pos[None, :]).sum(1).double()
+        # AUC = (rank sum of positives - n+(n+ + 1)/2) / (n+ n-), average ranks inside tie groups
+        srt, order = torch.sort(scores.double(), dim=1)
+        pos_sorted = pos[order].double()
+        idx = torch.arange(T, device=scores.device).expand(E, T)
+        first = torch.ones(E, T, dtype=torch.bool, device=scores.device)
+        first[:, 1:] = srt[:, 1:] != srt[:, :-1]
+        last = torch.ones(E, T, dtype=torch.bool, device=scores.device)
+        last[:, :-1] = srt[:, :-1] != srt[:, 1:]
+        start = torch.cummax(torch.where(first, idx, torch.zeros_like(idx)), dim=1).values
+        end = torch.flip(torch.cummin(torch.flip(torch.where(last, idx, torch.full_like(idx, T - 1)), [1]), dim=1).values, [1])
+        rank = (start + end).double() / 2.0 + 1.0
+        n_pos = float(pos.sum())
+        n_neg = float(T) - n_pos
+        if n_pos == 0 or n_neg == 0:
+            auc = torch.full((E,), 0.5, dtype=torch.float64, device=scores.device)
+        else:
+            auc = ((rank * pos_sorted).sum(1) - n_pos * (n_pos + 1) / 2.0) / (n_pos * n_neg)
+        stats = torch.stack([tn, fp, fn, tp, auc], 1).cpu().numpy()
+        tn, fp, fn, tp, auc = (stats[:, i] for i in range(5))
+        total = tn + fp + fn + tp
+        with np.errstate(divide="ignore", invalid="ignore"):
+            # class 0 = negative, class 1 = positive; macro average over the classes that occur (sklearn)
+            p1 = np.where(tp + fp > 0, tp / (tp + fp), 0.0); r1 = np.where(tp + fn > 0, tp / (tp + fn), 0.0)
+            p0 = np.where(tn + fn > 0, tn / (tn + fn), 0.0); r0 = np.where(tn + fp > 0, tn / (tn + fp), 0.0)
+            f1_1 = np.where(p1 + r1 > 0, 2 * p1 * r1 / (p1 + r1), 0.0)
+            f1_0 = np.where(p0 + r0 > 0, 2 * p0 * r0 / (p0 + r0), 0.0)
+            pres1 = ((tp + fp) + (tp + fn)) > 0
+            pres0 = ((tn + fn) + (tn + fp)) > 0
+            kk = np.maximum(pres1.astype(float) + pres0.astype(float), 1.0)
+            acc = np.where(total > 0, (tp + tn) / total, 0.0)
+            prec = (p1 * pres1 + p0 * pres0) / kk
+            recl = (r1 * pres1 + r0 * pres0) / kk
+            f1 = (f1_1 * pres1 + f1_0 * pres0) / kk
+        return [{"accuracy": float(acc[e]), "precision": float(prec[e]), "recall": float(recl[e]),
+                 "f1_score": float(f1[e]), "auc": float(auc[e])} for e in range(E)]
+
+    # -- synchronise the object API -----------------------------------------------------------------------
+    def writeback(self) -> None:
+        W = self.W[:, :self.D]
+        ages = self.age.cpu().tolist()
+        for i, node in self.sim.nodes.items():
+            h = node.model_handler
+            h.row[:self.D].copy_(W[i])
+            h.n_updates = int(ages[i])
+            h._version += 1

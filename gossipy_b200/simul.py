@@ -26,7 +26,7 @@ from typing import Any, Callable, DefaultDict, Dict, Iterable, List, Optional, T
 
 import numpy as np
 
-from . import CACHE, LOG, CacheKey
+from . import CACHE, LOG, CacheKey, GlobalSettings
 from .core import (AntiEntropyProtocol, ConstantDelay, Delay, Message, MessageType, MixingMatrix,
                    UniformMixing)
 from .data import DataDispatcher
@@ -199,6 +199,30 @@ class GossipSimulator(SimulationEventSender):
             _prt.set_num_nodes(self.n_nodes)
         for node in self.nodes.values():
             node.init_model()
+        self._prime_device_paths()
+
+    def _prime_device_paths(self) -> None:
+        """Run every node's evaluation once, before any cross-GPU dependency exists, and discard the
+        result: first-use costs (pre-tiling of the test set, scratch buffers, allocator growth --
+        ``cudaMalloc`` is an implicit device-wide barrier) are paid here instead of in the middle of
+        round 1, when kernels of other nodes may be waiting on flags of other GPUs."""
+        if GlobalSettings().get_device().type != "cuda":
+            return
+        try:
+            eval_set = self.data_dispatcher.get_eval_set() if self.data_dispatcher.has_test() else None
+        except Exception:
+            eval_set = None
+        pend = []
+        for node in self.nodes.values():
+            fn = getattr(node, "evaluate_async", None)
+            if fn is None:
+                continue
+            if node.has_test():
+                pend.append(fn())
+            if eval_set is not None:
+                pend.append(fn(eval_set))
+        for p in pend:
+            p.result()
 
     # -- message plumbing ---------------------------------------------------------------------
     def _lost(self, msg: Optional[Message]) -> None:
@@ -441,6 +465,12 @@ class GossipSimulator(SimulationEventSender):
             sch = self.__dict__["_scheduler"] = self._make_scheduler()
             self._native_msgs: Dict[int, Message] = {}
             self._clock = 0
+        if self.batched and type(self) is GossipSimulator:
+            from .engine import bank as _bank
+            why = _bank.bankable(self)
+            if why is None:
+                self._run_native_banked(sch, n_rounds, C)
+                return
         SEND, DROP, DELIVER, RSEND, RDELIVER, EVAL, TIMEOUT = (C.EV_SEND, C.EV_DROP, C.EV_DELIVER,
                                                               C.EV_REPLY_SEND, C.EV_REPLY_DELIVER, C.EV_EVAL,
                                                               C.EV_TIMEOUT)
@@ -489,6 +519,49 @@ class GossipSimulator(SimulationEventSender):
             prev_finish()
         self.notify_end()
 
+    batched = True    # native engine: execute bankable set-ups (linear learners) many nodes per launch
+
+    def _run_native_banked(self, sch, n_rounds: int, C) -> None:
+        """Rounds of a bankable simulation: the scheduler's event list of a round is executed by
+        ``engine.bank.LinearBank`` with one kernel launch per phase of a tick."""
+        from .engine.bank import LinearBank
+        bank = self.__dict__.get("_bank")
+        if bank is None:
+            bank = self.__dict__["_bank"] = LinearBank(self)
+        reports = [r for r in self._receivers if type(r) is SimulationReport]
+        others = [r for r in self._receivers if type(r) is not SimulationReport]
+        try:
+            for _ in range(n_rounds):
+                with nvtx_range("schedule"):
+                    events = sch.run(1)
+                t_last = int(sch.clock) - 1
+                with nvtx_range("bank"):
+                    evals, cnt = bank.run_round(events, C)
+                for r in reports:                      # bulk accounting (same totals as per-message calls)
+                    r._sent_messages += cnt["sent"]
+                    r._total_size += cnt["sent_size"]
+                    r._failed_messages += cnt["failed"]
+                if others:
+                    n_model = (cnt["sent_size"] - cnt["sent"]) // max(1, bank.size_model - 1) if bank.size_model > 1 else cnt["sent"]
+                    stub_model = _SizedMessage(Message(t_last, 0, 0, MessageType.PUSH, None), bank.size_model)
+                    stub_small = _SizedMessage(Message(t_last, 0, 0, MessageType.PULL, None), 1)
+                    for r in others:
+                        for _i in range(n_model):
+                            r.update_message(False, stub_model)
+                        for _i in range(cnt["sent"] - n_model):
+                            r.update_message(False, stub_small)
+                        for _i in range(cnt["failed"]):
+                            r.update_message(True)
+                if evals:
+                    with nvtx_range("evaluate"):
+                        self.notify_evaluation(t_last, False, bank.evaluate(evals))
+                self._clock = int(sch.clock)
+                self.notify_timestep(t_last)
+        except KeyboardInterrupt:
+            LOG.warning("Simulation interrupted by user.")
+        bank.writeback()
+        self.notify_end()
+
     def _native_send(self, node: GossipNode, t: int, peer: int) -> Message:
         return node.send(t, peer, self.protocol)
 
@@ -516,6 +589,7 @@ class GossipSimulator(SimulationEventSender):
         st = dict(self.__dict__)
         st["_receiver_list"] = list(self._receivers)
         st.pop("_collective", None)
+        st.pop("_bank", None)
         st.pop("_scheduler", None)      # native scheduler state is not checkpointed: a resumed run
         st.pop("_native_msgs", None)    # re-draws its schedule (the Python engine resumes exactly)
         return st

@@ -479,3 +479,24 @@ def test_synchronous_all2all_rounds_on_gpu():
     acc, rep = _gpu_sim("python", all2all=True, rounds=4)
     assert len(acc) == 4 and acc[-1] >= acc[0] - .02
     assert rep._sent_messages == 4 * 8 * 7
+
+
+@pytest.mark.parametrize("protocol,mode,handler", [("PUSH_PULL", "MERGE_UPDATE", "pegasos"), ("PUSH", "UPDATE_MERGE", "adaline"),
+                                                   ("PULL", "UPDATE", "pegasos")])
+def test_bank_kernels_equal_per_event_kernels(protocol, mode, handler):
+    """Many-nodes-per-launch kernels (bank.cu) against the per-node kernels on the same event schedule."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_native_scheduler import _linear_sim
+    import gossipy_b200 as g
+    rep_a, rows_a, ages_a, _ = _linear_sim(False, protocol, mode, handler, device="cuda:0")
+    rep_b, rows_b, ages_b, sim_b = _linear_sim(True, protocol, mode, handler, device="cuda:0")
+    assert "_bank" in sim_b.__dict__
+    assert (rep_a._sent_messages, rep_a._failed_messages, rep_a._total_size) == \
+        (rep_b._sent_messages, rep_b._failed_messages, rep_b._total_size)
+    assert ages_a == ages_b
+    torch.testing.assert_close(rows_a, rows_b, rtol=1e-3, atol=1e-4)
+    for (_, m1), (_, m2) in zip(rep_a.get_evaluation(False), rep_b.get_evaluation(False)):
+        for k in m1:
+            assert m1[k] == pytest.approx(m2[k], abs=2e-2), k
+    g.CACHE.clear()

@@ -135,3 +135,65 @@ def test_scheduler_event_stream_invariants():
     assert sch.sent == len(sends) + int((kinds == C.EV_REPLY_DELIVER).sum())
     assert sch.failed == len(dropped)
     assert (kinds == C.EV_EVAL).sum() == 10 * 5
+
+
+# ---------------------------------------------------------------------------------------------
+# batched execution of the linear learners (engine.bank.LinearBank): same schedule, same results as
+# the per-event executor
+# ---------------------------------------------------------------------------------------------
+def _linear_sim(batched, protocol, mode, handler="pegasos", n=40, rounds=6, device="cpu", faults=True, sync=False):
+    import gossipy_b200 as g
+    from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork, UniformDelay
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import AdaLineHandler, PegasosHandler
+    from gossipy_b200.model.nn import AdaLine
+    from gossipy_b200.node import GossipNode
+    from gossipy_b200.simul import GossipSimulator, SimulationReport
+    g.GlobalSettings().set_device(device)
+    g.CACHE.clear()
+    g.set_seed(5)
+    (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(3 * n + 7, 150)
+    disp = DataDispatcher(ClassificationDataHandler(Xtr, 2 * ytr - 1, Xte, 2 * yte - 1), n=n, eval_on_user=False)
+    cls = PegasosHandler if handler == "pegasos" else AdaLineHandler
+    proto = cls(AdaLine(57), .01 if handler == "pegasos" else .001, getattr(CreateModelMode, mode))
+    nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, sync)
+    kw = dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 3), sampling_eval=.3) if faults else {}
+    sim = GossipSimulator(nodes, disp, 10, getattr(AntiEntropyProtocol, protocol), **kw)
+    sim.progress = False
+    sim.engine = "native"
+    sim.batched = batched
+    rep = SimulationReport(); sim.add_receiver(rep)
+    sim.init_nodes(seed=9)
+    sim.start(rounds)
+    rows = torch.stack([sim.nodes[i].model_handler.row[:57].detach().cpu().clone() for i in range(n)])
+    ages = [int(sim.nodes[i].model_handler.n_updates) for i in range(n)]
+    return rep, rows, ages, sim
+
+
+@pytest.mark.parametrize("protocol,mode,handler", [("PUSH", "MERGE_UPDATE", "pegasos"), ("PUSH_PULL", "MERGE_UPDATE", "pegasos"),
+                                                   ("PULL", "UPDATE", "pegasos"), ("PUSH", "UPDATE_MERGE", "adaline"),
+                                                   ("PUSH_PULL", "UPDATE", "adaline"), ("PUSH", "PASS", "pegasos")])
+def test_banked_execution_equals_per_event_execution(protocol, mode, handler):
+    import gossipy_b200 as g
+    rep_a, rows_a, ages_a, sim_a = _linear_sim(False, protocol, mode, handler)
+    assert "_bank" not in sim_a.__dict__
+    rep_b, rows_b, ages_b, sim_b = _linear_sim(True, protocol, mode, handler)
+    assert "_bank" in sim_b.__dict__
+    assert (rep_a._sent_messages, rep_a._failed_messages, rep_a._total_size) == \
+        (rep_b._sent_messages, rep_b._failed_messages, rep_b._total_size)
+    assert ages_a == ages_b
+    torch.testing.assert_close(rows_a, rows_b, rtol=1e-4, atol=1e-5)
+    ev_a, ev_b = rep_a.get_evaluation(False), rep_b.get_evaluation(False)
+    assert len(ev_a) == len(ev_b) == 6
+    for (t1, m1), (t2, m2) in zip(ev_a, ev_b):
+        assert t1 == t2
+        for k in m1:
+            assert m1[k] == pytest.approx(m2[k], abs=1e-4), k
+    g.CACHE.clear()
+
+
+def test_bank_falls_back_when_not_bankable():
+    from gossipy_b200.engine.bank import bankable
+    rep, _, sim = _sim("native", __import__("gossipy_b200").core.AntiEntropyProtocol.PUSH, n=5, rounds=2)
+    assert bankable(sim) is not None and "_bank" not in sim.__dict__
