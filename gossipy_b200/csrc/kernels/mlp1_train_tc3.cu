@@ -104,15 +104,44 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
     const float* my_xt = stage_xt + (size_t)rank * tile_floats;
 
     // ---- one-time set-up -------------------------------------------------------------------------
-    const bool merging = p.peer != nullptr;
-    if (merging && p.sync.ready != nullptr) {
-        if (tid == 0) while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
-        __syncthreads();
+    // Fused MERGE_UPDATE.  With a peer row the starting point is w_self*row + w_peer*peer: the CTA pair
+    // first streams the peer's row -- possibly out of ANOTHER GPU's HBM, after spinning on its `ready`
+    // flag -- with coalesced 128-bit loads (NVLink moves 32-byte sectors: the per-thread 4-byte pattern of
+    // the TMEM fill below would fetch every sector eight times), folds it into the own row in place,
+    // acknowledges the read on the owner's `done` counter, and only then loads the weights on chip.
+    if (p.peer != nullptr) {
+        if (p.sync.ready != nullptr) {
+            if (tid == 0) while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
+            __syncthreads();
+        }
+        const int64_t P = (int64_t)H * IN + H + (int64_t)OUT * H + OUT;
+        const int64_t n4 = ((P + 31) & ~(int64_t)31) >> 2;              // rows are padded to 32 floats
+        float4* own4 = reinterpret_cast<float4*>(p.row);
+        const float4* peer4 = reinterpret_cast<const float4*>(p.peer);
+        constexpr int U = 4;
+        const int64_t stride = 2 * T3_THREADS;
+        int64_t i = (int64_t)rank * T3_THREADS + tid;
+        for (; i + (U - 1) * stride < n4; i += U * stride) {
+            float4 q[U], o[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) q[u] = gb_ld_stream(peer4 + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < U; ++u) o[u] = own4[i + u * stride];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                own4[i + u * stride] = make_float4(p.w_self * o[u].x + p.w_peer * q[u].x, p.w_self * o[u].y + p.w_peer * q[u].y,
+                                                   p.w_self * o[u].z + p.w_peer * q[u].z, p.w_self * o[u].w + p.w_peer * q[u].w);
+        }
+        for (; i < n4; i += stride) {
+            const float4 q = gb_ld_stream(peer4 + i), o = own4[i];
+            own4[i] = make_float4(p.w_self * o.x + p.w_peer * q.x, p.w_self * o.y + p.w_peer * q.y,
+                                  p.w_self * o.z + p.w_peer * q.z, p.w_self * o.w + p.w_peer * q.w);
+        }
+        __threadfence();
+        gb_cluster_sync();                                       // the merged row is visible to both CTAs
+        if (p.sync.done != nullptr && rank == 0 && tid == 0) gb_red_release_sys_add(p.sync.done, 1u);
     }
-    auto ldp = [&](size_t off) -> float {
-        const float own = p.row[off];
-        return merging ? p.w_self * own + p.w_peer * gb_ld_stream1(p.peer + off) : own;
-    };
+    auto ldp = [&](size_t off) -> float { return p.row[off]; };
     const size_t off_b1 = (size_t)H * IN, off_w2 = off_b1 + H, off_b2 = off_w2 + (size_t)OUT * H;
     if (warp == 0) tmem_alloc<T3_TMEM_COLS>(tslot);
     if (tid == 0) {
@@ -167,8 +196,6 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
     tc_fence_before();
     gb_cluster_sync();            // peer is running (its smem may be written from here on)
     tc_fence_after();
-    if (merging && p.sync.done != nullptr && rank == 0 && tid == 0)
-        gb_red_release_sys_add(p.sync.done, 1u);   // both CTAs have consumed their peer loads
 
     const float decay = 1.f - p.lr * p.wd;
     float sscale = 1.f;                                  // W_true = sscale * W_tmem

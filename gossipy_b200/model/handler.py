@@ -706,7 +706,10 @@ class TorchModelHandler(RowHandler):
                 mod.init_weights()
 
     def get_size(self) -> int:
-        return self._proto.get_size()
+        size = self.__dict__.get("_size_cache")
+        if size is None:            # every message asks for it; the architecture never changes
+            size = self.__dict__["_size_cache"] = int(self._proto.get_size())
+        return size
 
     # -- local learning -------------------------------------------------------------------
     def _next_key(self) -> int:
