@@ -218,7 +218,7 @@ def _dispose(h: Any) -> None:
 
 
 def _state_eq(a: Dict[str, Any], b: Dict[str, Any]) -> bool:
-    skip = {"_row", "_module", "_proto", "_grad_row", "_opt_rows", "_torch_opt", "owner",
+    skip = {"_row", "_module", "_proto", "_grad_row", "_opt_rows", "_torch_opt", "owner", "_size_cache",
             "_version", "_is_snapshot", "_bound_to", "_grad_bound", "_update_counter",
             "_part_id_dev", "_seg_dev", "layout"}
     for k in a.keys() | b.keys():
@@ -587,6 +587,7 @@ class TorchModelHandler(RowHandler):
         self._module = None if copy_model else net
         self.layout = FlatLayout(self._proto)
         self._row_numel = self.layout.padded
+        self._size_cache = int(self._proto.get_size())
         self.optimizer_cls = optimizer
         self.optimizer_params = dict(optimizer_params)
         self.criterion = criterion
