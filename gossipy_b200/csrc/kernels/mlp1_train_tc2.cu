@@ -32,8 +32,6 @@ constexpr int T2_OUTP = 16;
 constexpr int T2_FP_MAX = 400;    // feature columns per CTA (TMEM: 400 + 32 accumulator columns <= 512)
 constexpr int T2_TMEM_COLS = 512;
 constexpr int T2_HS = 132;        // stride of hs[b][j] (sample-major; 132 = 4 mod 32 keeps 128-bit reads conflict free)
-constexpr int T2_NG = 8;          // hidden-unit groups of the second-layer forward
-constexpr int T2_ZP = 12;         // stride of the partial-logit rows
 
 struct T2Smem {   // byte offsets inside dynamic shared memory (1024-aligned base)
     static constexpr int xf = 0;
@@ -43,8 +41,7 @@ struct T2Smem {   // byte offsets inside dynamic shared memory (1024-aligned bas
     static constexpr int zpart = a2 + T2_HP * T2_B * 4;              // [2][128][32] peer partial z1
     static constexpr int hs = zpart + 2 * T2_HP * T2_B * 4;          // [32][132]
     static constexpr int w2 = hs + T2_B * T2_HS * 4;                 // [16][128]
-    static constexpr int zp = w2 + T2_OUTP * T2_HP * 4;              // [8][32][12] partial logits
-    static constexpr int z2 = zp + T2_NG * T2_B * T2_ZP * 4;         // [32][16] logits -> dL/dz2
+    static constexpr int z2 = w2 + T2_OUTP * T2_HP * 4;              // [32][16] logits -> dL/dz2
     static constexpr int gws = z2 + T2_B * T2_OUTP * 4;              // [128][12] second-half partial grads
     static constexpr int b1 = gws + T2_HP * 12 * 4;
     static constexpr int b2 = b1 + T2_HP * 4;
@@ -79,7 +76,6 @@ mlp1_train_tc2_kernel(const TrainParams p, const int FPC, const int FP, const in
     float* zpart = reinterpret_cast<float*>(smem + T2Smem::zpart);
     float* hs = reinterpret_cast<float*>(smem + T2Smem::hs);
     float* w2s = reinterpret_cast<float*>(smem + T2Smem::w2);
-    float* zp = reinterpret_cast<float*>(smem + T2Smem::zp);
     float* z2s = reinterpret_cast<float*>(smem + T2Smem::z2);
     float* gws = reinterpret_cast<float*>(smem + T2Smem::gws);
     float* b1s = reinterpret_cast<float*>(smem + T2Smem::b1);

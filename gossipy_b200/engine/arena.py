@@ -22,9 +22,9 @@ import torch
 class Row:
     """One parameter vector (a 1-D fp32 tensor view) plus its cross-stream / cross-rank dependencies.
 
-    ``tensor`` is ``None`` for a row of another rank under the ``sendrecv`` transport and a
-    peer-mapped view (CUDA IPC) under ``p2p``.  ``gen`` / ``remote_reads`` are replicated
-    bookkeeping for the flag protocol (see :mod:`gossipy_b200.parallel.runtime`).
+    For a row of another rank ``tensor`` is a peer-mapped view (CUDA IPC on GPUs, POSIX shared
+    memory on CPU).  ``gen`` / ``remote_reads`` are replicated bookkeeping for the flag protocol
+    (see :mod:`gossipy_b200.parallel.runtime`).
     """
 
     __slots__ = ("arena", "index", "tensor", "ready", "consumed", "stream", "rank", "gen",
@@ -51,8 +51,8 @@ class Row:
 class RowArena:
     """Pool of equally sized fp32 rows on one device, grown chunk-wise and reused FIFO.
 
-    ``ghost=True`` mirrors the bookkeeping of another rank's arena without owning memory
-    (``sendrecv`` transport); every rank replays the same alloc/free sequence on every mirror, so
+    ``ghost=True`` mirrors the bookkeeping of another rank's arena (its rows are views of that
+    rank's shared memory); every rank replays the same alloc/free sequence on every mirror, so
     row indices agree everywhere without any communication.
     """
 

@@ -56,9 +56,9 @@ class RowSync:
 
 
 def host_flag_add(flag: Any, value: int) -> None:
-    """Atomic-enough increment of a shared-memory counter (each counter has ONE writer at a time in
-    the replicated schedule: reads of a row by one rank are serialised by that rank's host loop;
-    different ranks use a lock file-free add via numpy on separate counters)."""
+    """Increment a shared-memory counter (CPU transport).  Every counter has exactly ONE writing process:
+    the ``done`` word of a row has one slot per reader rank (``engine/arena.py``), so a plain
+    read-modify-write is race free."""
     arr, i = flag
     arr[i] += value
 

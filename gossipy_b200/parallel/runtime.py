@@ -6,17 +6,14 @@ work only of the gossip nodes it owns (block placement ``node -> rank``).  A mod
 on another GPU is never copied by the sender: its snapshot row stays in the sender's HBM arena and
 the receiver's fused merge kernel *pulls* it.
 
-Transports for a row that lives on another rank:
-
-``p2p``   (CUDA) every rank ``cudaMalloc``'s an identical ("symmetric") arena, exports it through CUDA
-          IPC (handles exchanged once with ``torch.distributed``) and maps all peers' arenas; a peer
-          row is then a device pointer and the merge kernel's loads travel over NVLink/NVSwitch.
-          Cross-GPU ordering uses per-row 32-bit flags inside the arenas: the producer's stream
-          publishes ``ready = generation`` (st.release.sys) after the snapshot kernel, the consumer's
-          stream spins on it (ld.acquire.sys) before the merge kernel and afterwards bumps the
-          producer's ``done`` counter so the row can be recycled -- no host synchronisation, no NCCL.
-``sendrecv`` (CPU/gloo plumbing, and the NCCL baseline on GPUs) the producer sends the row with
-          ``torch.distributed`` and the consumer merges from a staging buffer.
+Transport (``p2p``) for a row that lives on another rank: every rank allocates an identical
+("symmetric") arena and maps all peers' arenas -- ``cudaMalloc`` + CUDA IPC on GPUs (handles exchanged
+once with ``torch.distributed``; a peer row is then a device pointer and the merge / training kernels'
+loads travel over NVLink/NVSwitch), POSIX shared memory on CPU (gloo plumbing runs).  Cross-rank
+ordering uses two words per row inside the arenas: the producer publishes ``ready = generation``
+(``st.release.sys`` after the snapshot kernel), the consumer's kernel spins on it
+(``ld.acquire.sys``) before its first peer load and afterwards bumps the producer's ``done``
+counter so the row can be recycled -- no host synchronisation, no NCCL on the data path.
 
 Because the schedule is replicated, matching sends/receives, flag generations and arena row indices
 are derived independently and identically on every rank -- there is no control traffic at all.
