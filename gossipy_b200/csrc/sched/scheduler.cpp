@@ -172,6 +172,54 @@ public:
         for (auto& kv : rep_q_) c += (int64_t)kv.second.size();
         return c;
     }
+    // Dynamic state (random-stream counters, round order, token balances, in-flight messages,
+    // counters): together with the constructor/set_* configuration it determines every future event,
+    // so a checkpointed simulation resumes on exactly the schedule it would have followed.
+    py::dict get_state() const {
+        py::dict d;
+        std::vector<uint64_t> ctr;
+        for (const Stream* r : {&r_order_, &r_peer_, &r_drop_, &r_online_, &r_delay_, &r_eval_, &r_token_}) ctr.push_back(r->ctr);
+        d["streams"] = ctr;
+        d["order"] = order_;
+        d["balances"] = token_balances();
+        auto dump = [](const std::map<int64_t, std::deque<Msg>>& q) {
+            std::vector<std::vector<int64_t>> out;
+            for (const auto& kv : q)
+                for (const Msg& m : kv.second) out.push_back({kv.first, m.id, m.sender, m.receiver, m.type, m.size});
+            return out;
+        };
+        d["msg_q"] = dump(msg_q_);
+        d["rep_q"] = dump(rep_q_);
+        d["clock"] = clock_; d["sent"] = sent_; d["failed"] = failed_; d["total_size"] = total_size_;
+        d["next_id"] = next_id_;
+        d["n_nodes"] = n_;
+        return d;
+    }
+    void set_state(const py::dict& d) {
+        if (d["n_nodes"].cast<int>() != n_) throw std::invalid_argument("state belongs to a different node count");
+        const auto ctr = d["streams"].cast<std::vector<uint64_t>>();
+        Stream* rs[7] = {&r_order_, &r_peer_, &r_drop_, &r_online_, &r_delay_, &r_eval_, &r_token_};
+        if (ctr.size() != 7) throw std::invalid_argument("7 stream counters expected");
+        for (int i = 0; i < 7; ++i) rs[i]->ctr = ctr[i];
+        order_ = d["order"].cast<std::vector<int>>();
+        if ((int)order_.size() != n_) throw std::invalid_argument("order must have one entry per node");
+        const auto bal = d["balances"].cast<std::vector<int64_t>>();
+        for (int i = 0; i < n_ && i < (int)bal.size(); ++i) accounts_[i].n = bal[i];
+        auto load = [](std::map<int64_t, std::deque<Msg>>& q, const std::vector<std::vector<int64_t>>& rows) {
+            q.clear();
+            for (const auto& r : rows) {
+                if (r.size() != 6) throw std::invalid_argument("queue rows are (due, id, sender, receiver, type, size)");
+                Msg m; m.id = (int32_t)r[1]; m.sender = (int32_t)r[2]; m.receiver = (int32_t)r[3]; m.type = (int32_t)r[4];
+                m.size = r[5];
+                q[r[0]].push_back(m);
+            }
+        };
+        load(msg_q_, d["msg_q"].cast<std::vector<std::vector<int64_t>>>());
+        load(rep_q_, d["rep_q"].cast<std::vector<std::vector<int64_t>>>());
+        clock_ = d["clock"].cast<int64_t>(); sent_ = d["sent"].cast<int64_t>(); failed_ = d["failed"].cast<int64_t>();
+        total_size_ = d["total_size"].cast<int64_t>(); next_id_ = d["next_id"].cast<int32_t>();
+    }
+
     std::vector<int64_t> token_balances() const {
         std::vector<int64_t> v(n_);
         for (int i = 0; i < n_; ++i) v[i] = accounts_[i].n;
@@ -322,7 +370,9 @@ void bind_scheduler(py::module_& m) {
         .def_property_readonly("failed", &GossipScheduler::failed)
         .def_property_readonly("total_size", &GossipScheduler::total_size)
         .def_property_readonly("pending", &GossipScheduler::pending)
-        .def("token_balances", &GossipScheduler::token_balances);
+        .def("token_balances", &GossipScheduler::token_balances)
+        .def("get_state", &GossipScheduler::get_state)
+        .def("set_state", &GossipScheduler::set_state);
     m.attr("EV_SEND") = (int)EV_SEND; m.attr("EV_DROP") = (int)EV_DROP; m.attr("EV_DELIVER") = (int)EV_DELIVER;
     m.attr("EV_REPLY_SEND") = (int)EV_REPLY_SEND; m.attr("EV_REPLY_DELIVER") = (int)EV_REPLY_DELIVER;
     m.attr("EV_EVAL") = (int)EV_EVAL; m.attr("EV_TOKEN") = (int)EV_TOKEN; m.attr("EV_TIMEOUT") = (int)EV_TIMEOUT;

@@ -358,6 +358,26 @@ class LinearBank:
                  "f1_score": float(f1[e]), "auc": float(auc[e])} for e in range(E)]
 
     # -- synchronise the object API -----------------------------------------------------------------------
+    # -- checkpointing -----------------------------------------------------------------------------
+    def export_inflight(self, message_ids: List[int]) -> Dict[str, Any]:
+        """Snapshots of the messages that are still on the wire (ids from the scheduler's queues)."""
+        ids = np.asarray(message_ids, dtype=np.int64)
+        slots = self.slot_map[ids % _RING] if ids.size else np.zeros(0, dtype=np.int64)
+        keep = slots >= 0
+        ids, slots = ids[keep], slots[keep]
+        idx = torch.as_tensor(slots, dtype=torch.int64, device=self.device)
+        return {"ids": ids, "rows": self.S[idx].cpu(), "ages": self.slot_age[idx].cpu()}
+
+    def import_inflight(self, st: Dict[str, Any]) -> None:
+        ids = np.asarray(st["ids"], dtype=np.int64)
+        if ids.size == 0:
+            return
+        slots = self._alloc(int(ids.size))
+        idx = torch.as_tensor(slots, dtype=torch.int64, device=self.device)
+        self.S[idx] = st["rows"].to(self.device)
+        self.slot_age[idx] = st["ages"].to(self.device)
+        self.slot_map[ids % _RING] = slots
+
     def writeback(self) -> None:
         W = self.W[:, :self.D]
         ages = self.age.cpu().tolist()

@@ -461,10 +461,23 @@ class GossipSimulator(SimulationEventSender):
         from .ops.native import _try_import
         C = _try_import()
         sch = self.__dict__.get("_scheduler")
-        if sch is None or not resume:
+        saved = self.__dict__.pop("_scheduler_state", None)
+        if resume and sch is None and saved is not None:
+            # a checkpoint taken under the native engine: same configuration + the saved dynamic
+            # state (stream counters, queues, balances) continue the exact schedule
+            sch = self.__dict__["_scheduler"] = self._make_scheduler()
+            sch.set_state(saved)
+            self.__dict__.setdefault("_native_msgs", {})
+        elif sch is None or not resume:
             sch = self.__dict__["_scheduler"] = self._make_scheduler()
             self._native_msgs: Dict[int, Message] = {}
-            self._clock = 0
+            self.__dict__.pop("_bank_inflight", None)
+            if resume and getattr(self, "_clock", 0):
+                # checkpoint taken under the Python engine: keep the clock (and the evaluation phase
+                # of sync nodes) but the pending Python queues are not transferable
+                sch.clock = int(self._clock)
+            else:
+                self._clock = 0
         if self.batched and type(self) is GossipSimulator:
             from .engine import bank as _bank
             why = _bank.bankable(self)
@@ -528,6 +541,9 @@ class GossipSimulator(SimulationEventSender):
         bank = self.__dict__.get("_bank")
         if bank is None:
             bank = self.__dict__["_bank"] = LinearBank(self)
+            inflight = self.__dict__.pop("_bank_inflight", None)
+            if inflight is not None:
+                bank.import_inflight(inflight)
         reports = [r for r in self._receivers if type(r) is SimulationReport]
         others = [r for r in self._receivers if type(r) is not SimulationReport]
         try:
@@ -589,9 +605,16 @@ class GossipSimulator(SimulationEventSender):
         st = dict(self.__dict__)
         st["_receiver_list"] = list(self._receivers)
         st.pop("_collective", None)
-        st.pop("_bank", None)
-        st.pop("_scheduler", None)      # native scheduler state is not checkpointed: a resumed run
-        st.pop("_native_msgs", None)    # re-draws its schedule (the Python engine resumes exactly)
+        bank = st.pop("_bank", None)
+        sch = st.pop("_scheduler", None)
+        if sch is not None:
+            # native engine: the scheduler's dynamic state + the in-flight messages (their models are
+            # snapshot handlers in CACHE, or snapshot slots of the bank) -> an exact resume
+            state = dict(sch.get_state())
+            st["_scheduler_state"] = state
+            if bank is not None:
+                pending = [int(r[1]) for r in state["msg_q"] if int(r[4]) != 2] + [int(r[1]) for r in state["rep_q"]]
+                st["_bank_inflight"] = bank.export_inflight(pending)
         return st
 
     def __repr__(self) -> str:

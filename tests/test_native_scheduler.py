@@ -197,3 +197,64 @@ def test_bank_falls_back_when_not_bankable():
     from gossipy_b200.engine.bank import bankable
     rep, _, sim = _sim("native", __import__("gossipy_b200").core.AntiEntropyProtocol.PUSH, n=5, rounds=2)
     assert bankable(sim) is not None and "_bank" not in sim.__dict__
+
+
+# ---------------------------------------------------------------------------------------------
+# checkpoint / resume under the native engine: the scheduler's dynamic state and the in-flight
+# snapshots are part of the checkpoint, so an interrupted run continues on the identical schedule
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batched", [False, True])
+def test_native_checkpoint_resume_is_exact(batched, tmp_path):
+    import gossipy_b200 as g
+    from gossipy_b200.simul import GossipSimulator
+    rep_full, rows_full, ages_full, _ = _linear_sim(batched, "PUSH_PULL", "MERGE_UPDATE", rounds=6)
+    g.CACHE.clear()
+    rep_a, _, _, sim = _linear_sim(batched, "PUSH_PULL", "MERGE_UPDATE", rounds=3)
+    assert sim._scheduler.pending > 0          # delays up to 3 ticks: messages are on the wire at the cut
+    path = str(tmp_path / "ckpt.pkl")
+    sim.save(path)
+    g.CACHE.clear()
+    del sim
+    sim2 = GossipSimulator.load(path)
+    assert "_scheduler" not in sim2.__dict__ and "_scheduler_state" in sim2.__dict__
+    rep_b = [r for r in sim2._receivers if type(r).__name__ == "SimulationReport"][0]
+    sim2.start(3, resume=True)
+    assert ("_bank" in sim2.__dict__) == batched
+    n = len(sim2.nodes)
+    rows = torch.stack([sim2.nodes[i].model_handler.row[:57].detach().cpu().clone() for i in range(n)])
+    ages = [int(sim2.nodes[i].model_handler.n_updates) for i in range(n)]
+    assert ages == ages_full
+    torch.testing.assert_close(rows, rows_full, rtol=1e-5, atol=1e-6)
+    assert (rep_b._sent_messages, rep_b._failed_messages, rep_b._total_size) == \
+        (rep_full._sent_messages, rep_full._failed_messages, rep_full._total_size)
+    ev_full, ev_b = rep_full.get_evaluation(False), rep_b.get_evaluation(False)
+    assert [t for t, _ in ev_b] == [t for t, _ in ev_full]
+    for (_, m1), (_, m2) in zip(ev_full, ev_b):
+        for k in m1:
+            assert m1[k] == pytest.approx(m2[k], abs=1e-6), k
+    g.CACHE.clear()
+
+
+def test_scheduler_state_roundtrip():
+    from gossipy_b200.ops.native import _try_import
+    C = _try_import()
+
+    def make():
+        s = C.GossipScheduler(12, 10, 3, 0.2, 0.9, 0.5, 77)
+        s.set_nodes([0] * 12, [3 + i % 4 for i in range(12)], [10] * 12)
+        s.set_delay(1, 0, 5)
+        s.set_token_account(5, 6, 3, 1, 1)          # randomized token account
+        return s
+    a = make()
+    full = np.concatenate([a.run(1) for _ in range(8)])
+    b = make()
+    head = [b.run(1) for _ in range(4)]
+    st = dict(b.get_state())
+    c = make()
+    c.set_state(st)
+    tail = [c.run(1) for _ in range(4)]
+    assert np.array_equal(np.concatenate(head + tail), full)
+    assert (c.sent, c.failed, c.total_size, c.clock) == (a.sent, a.failed, a.total_size, a.clock)
+    assert c.token_balances() == a.token_balances()
+    with pytest.raises(Exception):
+        C.GossipScheduler(5, 10, 3, 0., 1., 0., 1).set_state(st)
