@@ -304,9 +304,8 @@ class PENSNode(GossipNode):
             LOG.warning("PENSNode only supports PUSH protocol.")
         key = msg.value[0]
         from .parallel import runtime as _prt
-        if _prt.active():
-            raise NotImplementedError("PENSNode scores received models on the receiver; run it on a "
-                                      "single rank (its peer selection depends on device results)")
+        if _prt.active() and self.step == 1:
+            return self._receive_step1_multirank(msg, _prt)
         if self.step != 1:
             recv = CACHE.pop(key)
             self.model_handler(recv, self.data[0])
@@ -329,6 +328,40 @@ class PENSNode(GossipNode):
             self.cache = {}
             for s in top:
                 self.neigh_counter[s] += 1
+        return None
+
+
+    def _receive_step1_multirank(self, msg: Message, _prt: Any) -> None:
+        """Step 1 with the nodes spread over several ranks.
+
+        The received snapshot (possibly in another GPU's arena) is pulled ONCE into a scratch row of
+        this node -- over NVLink, on the node's stream, with the usual ready/done handshake -- and
+        scored there; the later k-way merge reads the local scratch rows.  Which senders make the
+        top-m is only known on the owner (it depends on device results): the owner broadcasts the m
+        sender ids, so ages, selection counters and the arena bookkeeping stay identical on every
+        rank (the peer choice of step 2 is part of the replicated schedule)."""
+        snap = CACHE.pop(msg.value[0])
+        local = self.model_handler._scratch_copy(snap)
+        _release(snap)
+        res = local.evaluate(self.data[0])
+        score = -float(res["accuracy"]) if res is not None else 0.0
+        stale = self.cache.get(msg.sender)
+        if stale is not None:
+            stale[0].release()
+        self.cache[msg.sender] = (local, score)      # newest model per sender
+        if len(self.cache) < self.n_sampled:
+            return None
+        owner = _prt.rank_of(self.idx)
+        top = None
+        if _prt.rank() == owner:
+            top = sorted(self.cache, key=lambda s: self.cache[s][1])[:self.m_top]
+        top = _prt.share_ints(top, owner, min(self.m_top, len(self.cache)))
+        self.model_handler([self.cache[s][0] for s in top], self.data[0])
+        for s in self.cache:                          # canonical release order: same free lists everywhere
+            self.cache[s][0].release()
+        self.cache = {}
+        for s in top:
+            self.neigh_counter[s] += 1
         return None
 
 

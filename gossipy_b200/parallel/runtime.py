@@ -141,6 +141,23 @@ def share_metrics(local: List[Optional[Dict[str, float]]]) -> List[Dict[str, flo
     return out
 
 
+def share_ints(values: Optional[List[int]], src_rank: int, n: int) -> List[int]:
+    """Broadcast ``n`` small integers decided on ``src_rank`` (a data-dependent choice such as PENS'
+    top-m senders) so that the replicated bookkeeping stays identical everywhere.  Every rank calls it
+    at the same point of the (replicated) event sequence; ``values`` is ignored off ``src_rank``."""
+    if not active():
+        return list(values or [])
+    import torch.distributed as dist
+    buf = torch.zeros(n, dtype=torch.int64)
+    if rank() == src_rank:
+        assert values is not None and len(values) == n
+        buf.copy_(torch.as_tensor(list(values), dtype=torch.int64))
+    if dist.get_backend() == "nccl":
+        buf = buf.to(GlobalSettings().get_device())
+    dist.broadcast(buf, src=src_rank)
+    return [int(v) for v in buf.cpu().tolist()]
+
+
 def barrier() -> None:
     if active():
         import torch.distributed as dist

@@ -75,6 +75,15 @@ def build(kind, device):
         sim = All2AllGossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
         start_args = (UniformMixing(net),)
         sim._mr_kwargs = {"synchronous": True}
+    elif kind == "pens":              # performance-based neighbour selection: data-dependent top-m, then step 2
+        from gossipy_b200.node import PENSNode
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=6, eval_on_user=False)
+        proto = TorchModelHandler(LogisticRegression(57, 2), torch.optim.SGD, {"lr": .5},
+                                  torch.nn.CrossEntropyLoss(), batch_size=16,
+                                  create_model_mode=CreateModelMode.MERGE_UPDATE)
+        nodes = PENSNode.generate(disp, StaticP2PNetwork(6), proto, 10, True, n_sampled=2, m_top=1, step1_rounds=5)
+        sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
     else:
         raise ValueError(kind)
     sim.progress = False
@@ -106,7 +115,8 @@ def run(kind, device, rounds):
     return {"glob": rep.get_evaluation(False), "loc": rep.get_evaluation(True), "sent": rep._sent_messages,
             "failed": rep._failed_messages, "size": rep._total_size,
             "sums": {str(k): sums[k] for k in sorted(sums)}, "ages": {str(k): ages[k] for k in sorted(ages)},
-            "cache_left": len(g.CACHE)}
+            "cache_left": len(g.CACHE),
+            "best": {str(i): getattr(n, "best_nodes", None) for i, n in sim.nodes.items()}}
 
 
 def main():

@@ -38,10 +38,12 @@ def _run(world, device, rounds=3, kinds=KINDS):
     return json.loads(lines[-1][len("RESULT "):])
 
 
-def _compare(a, b, rel):
+def _compare(a, b, rel, skip=()):
     for kind in a:
         x, y = a[kind], b[kind]
-        for f in ("sent", "failed", "size", "ages", "cache_left"):
+        for f in ("sent", "failed", "size", "ages", "cache_left", "best"):
+            if f in skip:
+                continue
             assert x[f] == y[f], (kind, f, x[f], y[f])
         for f in ("glob", "loc"):
             assert len(x[f]) == len(y[f])
@@ -58,6 +60,15 @@ def test_two_ranks_cpu_equal_single_process():
     single = _run(1, "cpu")
     multi = _run(2, "cpu")
     _compare(single, multi, rel=1e-5)
+
+
+def test_pens_two_and_three_ranks_cpu_equal_single_process():
+    """PENS: the top-m choice is made on the owner from device results and broadcast; both steps run."""
+    single = _run(1, "cpu", rounds=9, kinds="pens")
+    assert any(v for v in single["pens"]["best"].values()), "step 2 was never reached"
+    # (multi-rank nodes hold their step-1 candidates as local scratch rows instead of CACHE entries)
+    _compare(single, _run(2, "cpu", rounds=9, kinds="pens"), rel=1e-5, skip=("cache_left",))
+    _compare(single, _run(3, "cpu", rounds=9, kinds="pens"), rel=1e-5, skip=("cache_left",))
 
 
 @pytest.mark.gpu
