@@ -66,6 +66,14 @@ def bench_train(impl):
     flops = steps * 32 * (2 * 784 * 100 * 2 + 2 * 100 * 10 * 3)
     print(json.dumps({"op": "mlp1_train", "impl": impl or "auto", "ms_per_update": med, "best_ms": best,
                       "us_per_sgd_step": med * 1e3 / steps, "gflops": flops / med / 1e6}))
+    from gossipy_b200.ops.native import native as _nat
+    med_s, best_s = timeit(lambda: _nat().mlp1_stage_debug(X, y, 32, 1, 1234), iters=8)
+    print(json.dumps({"op": "mlp1_stage (device-side loader, 235 steps)", "us": med_s * 1e3, "best_us": best_s * 1e3}))
+    Xs, ys_ = X[:320].contiguous(), y[:320].contiguous()      # 10 SGD steps: what a launch costs besides its steps
+    med10, best10 = timeit(lambda: ops.mlp1_train(row, Xs, ys_, DIMS, 32, 1, 0.1, 0.0, 1234, impl=impl), iters=8)
+    per_step = (med - med10) / (steps - 10)
+    print(json.dumps({"op": "mlp1_train fixed cost", "impl": impl or "auto", "ms_10_steps": med10,
+                      "us_per_step_marginal": per_step * 1e3, "fixed_us_per_launch": (med10 - 10 * per_step) * 1e3}))
     if impl in ("", "tc2", "tc3"):   # per-phase cycle counters of the tc2/tc3 kernel (thread 0 of CTA 0)
         from gossipy_b200.ops.native import native
         prof = native().mlp1_train_tc_debug(row, X, y, DIMS, 32, 1, 0.1, 0.0, 1234, impl or "tc2")[0, :6].tolist()

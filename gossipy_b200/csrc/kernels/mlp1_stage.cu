@@ -2,7 +2,7 @@
 //
 // One local update visits the node's shard in a keyed pseudo-random order (the engine's Feistel
 // permutation, one key per epoch).  Instead of gathering 32 random rows per SGD step INSIDE the
-// latency-critical training kernel, this kernel -- wide, bandwidth-bound, ~10 us for a 23.5 MB shard
+// latency-critical training kernel, this kernel -- wide, one CTA per (step, feature half)
 // -- writes the whole update's mini-batches ahead of time, already shuffled and already in the two
 // shared-memory images the tensor core wants, so that the training kernel fetches each step's operands
 // with two contiguous bulk copies (cp.async.bulk -> UBLKCP) and never touches an index:
@@ -47,11 +47,40 @@ mlp1_stage_kernel(const float* __restrict__ X, const int64_t* __restrict__ y, in
         if (r == 0) ys[(size_t)s * ST_B + tid] = id >= 0 ? (int)y[id] : -1;
     }
     __syncthreads();
-    // gather the 32 rows of this mini-batch (my feature half) into shared memory
-    for (int i = tid; i < ST_B * FP; i += ST_THREADS) {
-        const int b = i / FP, c = i - b * FP;
-        const int id = ids[b];
-        tile[b * ld + c] = (id >= 0 && c < fcnt) ? X[(size_t)id * IN + f0 + c] : 0.f;
+    // gather the 32 rows of this mini-batch (my feature half) into shared memory.  The rows are random,
+    // so the loop is a chain of DRAM round trips unless several loads are in flight per thread: 128-bit
+    // loads, four issued back to back before the first one is consumed.
+    if ((IN & 3) == 0) {                                 // f0, fcnt and every row start are multiples of 4 floats
+        const int nch = FP >> 2, total = ST_B * nch;
+        constexpr int U = 4;
+        for (int i0 = tid; i0 < total; i0 += U * ST_THREADS) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * ST_THREADS;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < total) {
+                    const int b = i / nch, c = (i - b * nch) << 2;
+                    const int id = ids[b];
+                    if (id >= 0 && c < fcnt) v[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)id * IN + f0 + c));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * ST_THREADS;
+                if (i < total) {
+                    const int b = i / nch, c = (i - b * nch) << 2;
+                    float* d = tile + b * ld + c;
+                    d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < ST_B * FP; i += ST_THREADS) {
+            const int b = i / FP, c = i - b * FP;
+            const int id = ids[b];
+            tile[b * ld + c] = (id >= 0 && c < fcnt) ? X[(size_t)id * IN + f0 + c] : 0.f;
+        }
     }
     __syncthreads();
     const size_t tile_floats = (size_t)ST_B * FP;

@@ -25,6 +25,8 @@ constexpr int T3_HP = 128;        // hidden units padded to the MMA M
 constexpr int T3_OUTP = 16;
 constexpr int T3_FP_MAX = 400;    // feature columns per CTA (TMEM: 400 + 32 accumulator columns <= 512)
 constexpr int T3_TMEM_COLS = 512;
+constexpr int T3_WCB = 64;        // weight columns moved per pass of the TMEM fill / write-back
+constexpr int T3_WLD = 65;        // row pitch of the [128][64] scratch (odd: conflict-free column access)
 
 // shared-memory images of the second-layer operands (float offsets)
 GB_DEVICE int sw128_off(int rows, int r, int k) {    // K-major, 128-byte swizzle: element (row r, k)
@@ -56,6 +58,8 @@ struct T3Smem {   // byte offsets inside dynamic shared memory (base rounded up 
 };
 static_assert(T3Smem::hA % 1024 == 0 && T3Smem::w2k % 1024 == 0, "swizzled operands need 1024-byte alignment");
 static_assert(T3Smem::total + 1024 <= 227 * 1024, "shared memory budget");
+static_assert(T3_HP * T3_WLD * 4 <= T3Smem::hA - T3Smem::a2, "fill / write-back scratch must fit in a2 + zpart");
+static_assert(T3_WCB == 64, "index arithmetic below assumes 16 float4 per scratch row and 4 column groups per pass");
 
 
 GB_DEVICE void bulk_g2s3(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
@@ -148,7 +152,6 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
         for (int i = 0; i < 9; ++i) mbar_init(&mbar[i], 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < T3_HP * T3_B; i += T3_THREADS) a2[i] = 0.f;
     for (int i = tid; i < 64 * T3_HP; i += T3_THREADS) hA[i] = 0.f;          // rows 32..63 stay zero (MMA M = 64)
     for (int i = tid; i < T3_HP * T3_B; i += T3_THREADS) hT[i] = 0.f;
     for (int i = tid; i < 2 * T3_B * 16; i += T3_THREADS) dzs[i] = 0.f;      // dz2 and dz2^T (contiguous)
@@ -178,20 +181,37 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
     }
     if (tid < T3_B) ysm[tid] = stage_ys[tid];
 
-    // master weights -> TMEM: thread (j, half) fills column groups [half*13, ...) of its lane
+    // master weights -> TMEM.  Thread (j, half) owns TMEM lane j, but reading "its" weight row straight from
+    // global memory makes every warp-wide load touch 32 different cache lines; instead the CTA moves
+    // 64-column blocks through shared memory: coalesced 128-bit loads (16 consecutive threads = 256
+    // contiguous bytes of one row) -> [128][65] scratch (a2 + zpart, unused until the cluster barrier
+    // below) -> conflict-free column reads -> tcgen05.st.
     {
-        const int ngroups = T3_FP_MAX / 16;                               // 25
-        const int g0 = half ? 13 : 0, g1 = half ? ngroups : 13;
-        for (int g = g0; g < g1; ++g) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int c = g * 16 + i;
-                v[i] = (j < H && c < fcnt) ? ldp((size_t)j * IN + f0 + c) : 0.f;
+        float* wbuf = a2;
+        for (int cb = 0; cb * T3_WCB < T3_FP_MAX; ++cb) {
+            const int c0 = cb * T3_WCB;
+            for (int idx = tid; idx < H * (T3_WCB / 4); idx += T3_THREADS) {
+                const int rr = idx >> 4, c = c0 + ((idx & 15) << 2);
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < fcnt) w = *reinterpret_cast<const float4*>(p.row + (size_t)rr * IN + f0 + c);
+                float* d = wbuf + rr * T3_WLD + (c - c0);
+                d[0] = w.x; d[1] = w.y; d[2] = w.z; d[3] = w.w;
             }
-            tmem_st16(tlane + t_w1 + g * 16, v);
+            __syncthreads();
+#pragma unroll
+            for (int gl = 0; gl < 2; ++gl) {
+                const int g = cb * 4 + half * 2 + gl;                     // warp-uniform
+                if (g < T3_FP_MAX / 16) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = (j < H) ? wbuf[j * T3_WLD + (half * 2 + gl) * 16 + i] : 0.f;
+                    tmem_st16(tlane + t_w1 + g * 16, v);
+                }
+            }
+            __syncthreads();
         }
         tmem_st_wait();
+        for (int i = tid; i < T3_HP * T3_B; i += T3_THREADS) a2[i] = 0.f;
     }
     tc_fence_before();
     gb_cluster_sync();            // peer is running (its smem may be written from here on)
@@ -457,20 +477,32 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
     mbar_wait(&mbar[4], 0u);
     tc_fence_after();
     __syncthreads();
-    {
-        const int ngroups = T3_FP_MAX / 16;
-        const int g0 = half ? 13 : 0, g1 = half ? ngroups : 13;
-        for (int g = g0; g < g1; ++g) {
-            float v[16];
-            tmem_ld16(tlane + t_w1 + g * 16, v);
-            tmem_ld_wait();
-            if (j < H) {
+    {   // master weights TMEM -> global through the same [128][65] scratch, written back with coalesced 128-bit stores
+        float* wbuf = a2;                                                 // every MMA has retired, the last exchange is consumed
+        for (int cb = 0; cb * T3_WCB < T3_FP_MAX; ++cb) {
+            const int c0 = cb * T3_WCB;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = g * 16 + i;
-                    if (c < fcnt) p.row[(size_t)j * IN + f0 + c] = sscale * v[i];
+            for (int gl = 0; gl < 2; ++gl) {
+                const int g = cb * 4 + half * 2 + gl;
+                if (g < T3_FP_MAX / 16) {
+                    float v[16];
+                    tmem_ld16(tlane + t_w1 + g * 16, v);
+                    tmem_ld_wait();
+                    if (j < H) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) wbuf[j * T3_WLD + (half * 2 + gl) * 16 + i] = sscale * v[i];
+                    }
                 }
             }
+            __syncthreads();
+            for (int idx = tid; idx < H * (T3_WCB / 4); idx += T3_THREADS) {
+                const int rr = idx >> 4, c = c0 + ((idx & 15) << 2);
+                if (c < fcnt) {
+                    const float* sp = wbuf + rr * T3_WLD + (c - c0);
+                    *reinterpret_cast<float4*>(p.row + (size_t)rr * IN + f0 + c) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
+            }
+            __syncthreads();
         }
     }
     if (rank == 0) {
