@@ -76,10 +76,24 @@ def bench_train(impl):
                       "us_per_step_marginal": per_step * 1e3, "fixed_us_per_launch": (med10 - 10 * per_step) * 1e3}))
     if impl in ("", "tc2", "tc3"):   # per-phase cycle counters of the tc2/tc3 kernel (thread 0 of CTA 0)
         from gossipy_b200.ops.native import native
-        prof = native().mlp1_train_tc_debug(row, X, y, DIMS, 32, 1, 0.1, 0.0, 1234, impl or "tc2")[0, :6].tolist()
+        dbg = native().mlp1_train_tc_debug(row, X, y, DIMS, 32, 1, 0.1, 0.0, 1234, impl or "tc2")
+        raw = dbg[0, :17].tolist()
+        raw1 = dbg[1, :17].tolist()          # CTA 1 of the pair (tc3)
         names = ["A+B issue fwd MMA (+wait X tile, +wait upd(s-1), request X^T)", "C wait fwd MMA + tmem_ld",
                  "C exchange (DSMEM + cluster barrier) + relu + hs", "D+E layer-2 fwd, softmax-CE",
                  "F backward + A2 operand", "G+H issue update MMA + W2/b update"]
+        if impl == "tc3":     # 17 fine-grained stamps; the six coarse phases are sums of them
+            fine = ["A+B issue fwd", "C wait fwd + ld", "C st.async issued", "C peer partials landed", "C relu + h stores",
+                    "C fences + barrier", "D issue logits MMAs", "E wait logits", "E tmem_ld", "E softmax + dz stores + fence",
+                    "E barrier (+labels)", "F issue dh/gw2 MMAs", "F wait", "F ld + relu mask + A2 stores", "F fences + barrier",
+                    "G issue update MMAs", "H second-layer update"]
+            print(json.dumps({"op": "mlp1_train_tc3 fine phase cycles per step (thread 0)",
+                              "phases": {k: round(v) for k, v in zip(fine, raw)}, "sum": round(sum(raw))}))
+            print(json.dumps({"op": "mlp1_train_tc3 fine phase cycles per step (thread 0 of CTA 1)",
+                              "phases": {k: round(v) for k, v in zip(fine, raw1)}, "sum": round(sum(raw1))}))
+            prof = [raw[0], raw[1], sum(raw[2:6]), sum(raw[6:11]), sum(raw[11:15]), sum(raw[15:17])]
+        else:
+            prof = raw[:6]
         print(json.dumps({"op": "mlp1_train_%s phase cycles per step (thread 0)" % (impl or "tc2"),
                           "phases": {k: round(v) for k, v in zip(names, prof)}, "sum": round(sum(prof))}))
 
@@ -138,7 +152,12 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="")
     a = ap.parse_args()
     if a.what in ("train", "all"):
-        bench_train(a.impl)
+        for var in os.environ.get("MICRO_TC3_VARIANTS", "").split(",") if a.impl == "tc3" else [""]:
+            if var:
+                os.environ["GB_TC3_VARIANT"] = var
+                print(json.dumps({"GB_TC3_VARIANT": var}))
+            bench_train(a.impl)
+        os.environ.pop("GB_TC3_VARIANT", None)
     if a.what in ("eval", "all"):
         bench_eval()
     if a.what in ("merge", "all"):

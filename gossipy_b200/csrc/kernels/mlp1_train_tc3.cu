@@ -25,6 +25,7 @@ constexpr int T3_HP = 128;        // hidden units padded to the MMA M
 constexpr int T3_OUTP = 16;
 constexpr int T3_FP_MAX = 400;    // feature columns per CTA (TMEM: 400 + 32 accumulator columns <= 512)
 constexpr int T3_TMEM_COLS = 512;
+constexpr int T3_MMA_WARP = 4;    // issues the forward / update MMAs and their bulk copies (warp 0 issues the small second-layer GEMMs)
 constexpr int T3_WCB = 64;        // weight columns moved per pass of the TMEM fill / write-back
 constexpr int T3_WLD = 65;        // row pitch of the [128][64] scratch (odd: conflict-free column access)
 
@@ -48,11 +49,10 @@ struct T3Smem {   // byte offsets inside dynamic shared memory (base rounded up 
     static constexpr int w2t = hT + T3_HP * T3_B * 4;                // W2^T [128(j) x 16(o)]
     static constexpr int dz = w2t + T3_HP * 16 * 4;                  // dz2   [32(b) x 16(o)]
     static constexpr int dzT = dz + T3_B * 16 * 4;                   // dz2^T [16(o) x 32(b)]
-    static constexpr int gb1p = dzT + 16 * T3_B * 4;                 // [128] second-half partial of db1
-    static constexpr int b1 = gb1p + T3_HP * 4;
-    static constexpr int b2 = b1 + T3_HP * 4;
+    static constexpr int gb1p = dzT + 16 * T3_B * 4;                 // [2][128] per-half partials of db1
+    static constexpr int b2 = gb1p + 2 * T3_HP * 4;
     static constexpr int ys = b2 + 16 * 4;                           // [2][32] int labels
-    static constexpr int mbar = ys + 2 * T3_B * 4;                   // 9 x uint64
+    static constexpr int mbar = ys + 2 * T3_B * 4;                   // 10 x uint64
     static constexpr int tslot = mbar + 96;
     static constexpr int total = tslot + 16;
 };
@@ -72,7 +72,9 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
                       const float* __restrict__ stage_xf, const float* __restrict__ stage_xt,
                       const int* __restrict__ stage_ys) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // round the base up to 1024 B on the SHARED-window address and keep `smem` derived from `smem_raw`:
+    // going through uintptr_t loses the address space and turns every LDS/STS below into a generic LD/ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quad = warp & 3, half = warp >> 2;
     const int j = quad * 32 + lane;                        // hidden unit = TMEM lane of this thread
@@ -93,10 +95,9 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
     float* dzs = reinterpret_cast<float*>(smem + T3Smem::dz);
     float* dzT = reinterpret_cast<float*>(smem + T3Smem::dzT);
     float* gb1p = reinterpret_cast<float*>(smem + T3Smem::gb1p);
-    float* b1s = reinterpret_cast<float*>(smem + T3Smem::b1);
     float* b2s = reinterpret_cast<float*>(smem + T3Smem::b2);
     int* ysm = reinterpret_cast<int*>(smem + T3Smem::ys);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T3Smem::mbar);   // 0 xf, 1 xt, 2 fwd, 3 upd, 4 drain, 5/6 exchange, 7 d2, 8 dh+gw2
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + T3Smem::mbar);   // 0 xf, 1 xt, 2 fwd, 3 upd, 4 drain, 5/6 exchange, 7 d2, 8 dh, 9 gw2
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + T3Smem::tslot);
 
     float* b1g = p.row + (size_t)H * IN;
@@ -149,7 +150,7 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
     const size_t off_b1 = (size_t)H * IN, off_w2 = off_b1 + H, off_b2 = off_w2 + (size_t)OUT * H;
     if (warp == 0) tmem_alloc<T3_TMEM_COLS>(tslot);
     if (tid == 0) {
-        for (int i = 0; i < 9; ++i) mbar_init(&mbar[i], 1);
+        for (int i = 0; i < 10; ++i) mbar_init(&mbar[i], 1);
         mbar_fence_init();
     }
     for (int i = tid; i < 64 * T3_HP; i += T3_THREADS) hA[i] = 0.f;          // rows 32..63 stay zero (MMA M = 64)
@@ -161,8 +162,8 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
         w2k[sw128_off(16, o, jj)] = v;
         w2t[kmaj_off(4, jj, o)] = v;
     }
-    if (tid < T3_HP) b1s[tid] = (tid < H) ? ldp(off_b1 + tid) : 0.f;
-    if (tid < T3_OUTP) b2s[tid] = (tid < OUT) ? ldp(off_b2 + tid) : 0.f;
+    float b1r = (j < H) ? ldp(off_b1 + j) : 0.f;           // both threads of hidden unit j carry its bias
+    if (tid < T3_OUTP) b2s[tid] = (tid < OUT) ? ldp(off_b2 + tid) : -3.0e38f;   // padding classes: logit -inf, probability 0
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -222,7 +223,11 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
     const uint32_t idesc_fwd = make_idesc(kFmtTF32, kFmtTF32, 128, T3_B, false, false);
     const uint32_t x_sbo = (uint32_t)nchunk * 128u;
     const int spe = (n + B - 1) / B;
-    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned prof[17];                                   // fine-grained phase counters (thread 0, profiling runs only)
+#pragma unroll
+    for (int i = 0; i < 17; ++i) prof[i] = 0u;
+    unsigned tprev = 0u;
+#define T3_STAMP(i) do { if (profiling && tid == 0) { const unsigned t_ = (unsigned)clock(); prof[i] += t_ - tprev; tprev = t_; } } while (0)
     const bool profiling = p.dbg != nullptr && p.lr == 0.f ? false : (p.dbg != nullptr);
 
     for (int s = 0; s < total_steps; ++s) {
@@ -230,12 +235,11 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
         const uint32_t ph = (uint32_t)(s & 1);
         const int pos = p.epochs > 0 ? (s % spe) * B : 0;
         const int bcur = min(B, n - pos);
-        long long t0 = 0;
-        if (profiling && tid == 0) t0 = clock64();
+        if (profiling && tid == 0) tprev = (unsigned)clock();
 
         // (A)+(B) forward MMA: D1[128 x 32] = W1(TMEM) . X^T ; queued behind update(s-1).
         // Warp 0 stays converged and one ELECTED lane issues (operands in uniform registers).
-        if (warp == 0) {
+        if (warp == T3_MMA_WARP) {
             mbar_wait(&mbar[0], ph);                     // X tile of this step has landed
             tc_fence_after();
             if (elect_one()) {
@@ -258,12 +262,12 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
                 __syncwarp();
             }
         }
-        if (profiling && tid == 0) { const long long t = clock64(); prof[0] += t - t0; t0 = t; }
+        T3_STAMP(0);
 
         // (C) accumulator -> registers, exchange partial sums with the peer CTA
         mbar_wait(&mbar[2], ph);
         tc_fence_after();
-        if (warp == 0 && s + 1 < total_steps) {          // forward MMA retired -> X buffer is free
+        if (warp == T3_MMA_WARP && s + 1 < total_steps) {   // forward MMA retired -> X buffer is free
             if (elect_one()) {
                 mbar_expect_tx(&mbar[0], tile_bytes);
                 bulk_g2s3(xf, my_xf + (size_t)(s + 1) * 2 * tile_floats, tile_bytes, &mbar[0]);
@@ -273,7 +277,7 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
         float acc[16];
         tmem_ld16(tlane + t_d1 + 16 * half, acc);
         tmem_ld_wait();
-        if (profiling && tid == 0) { const long long t = clock64(); prof[1] += t - t0; t0 = t; }
+        T3_STAMP(1);
         // my partial sums -> the peer's zpart; layout [par][half*4 + q][j][4 samples]: every warp-wide
         // store covers 512 contiguous bytes of the peer's shared memory, each 16-B piece signalling
         // the peer's exchange mbarrier (st.async complete_tx); rows j >= H carry nothing
@@ -285,10 +289,12 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
             for (int q = 0; q < 4; ++q)
                 st_async_v4(remote + (uint32_t)(q * T3_HP * 16), make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]), rbar);
         }
+        T3_STAMP(2);
         mbar_wait_cluster(&mbar[5 + par], (uint32_t)((s >> 1) & 1));   // all of the peer's partials landed
+        T3_STAMP(3);
         float h[16];
         {
-            const float bj = b1s[j];
+            const float bj = b1r;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 o = (j < H) ? *reinterpret_cast<const float4*>(zslot + (size_t)q * T3_HP * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -306,6 +312,7 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
             for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(trow + q * 32) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
         }
+        T3_STAMP(4);
         fence_proxy_async();
         tc_fence_before();
         if (p.dbg != nullptr && !profiling && s == 0 && rank == 0) {
@@ -313,7 +320,7 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
             for (int i = 0; i < 16; ++i) p.dbg[j * T3_B + 16 * half + i] = h[i];
         }
         __syncthreads();
-        if (profiling && tid == 0) { const long long t = clock64(); prof[2] += t - t0; t0 = t; }
+        T3_STAMP(5);
 
         // (D) logits on the tensor core: z2[64 x 16] = h . W2^T (M64 N16 K128, both operands 128B-swizzled)
         if (warp == 0) {
@@ -322,38 +329,45 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
                 const uint32_t idesc_d2 = make_idesc(kFmtTF32, kFmtTF32, 64, 16, false, false);
                 const uint32_t ha = smem_u32(hA), wk = smem_u32(w2k);
                 const int ksteps = (H + 7) >> 3;        // columns j >= H of both operands are zero
-#pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t ad = make_sdesc_sw128(ha + (uint32_t)(k >> 2) * 8u * 1024u + (uint32_t)(k & 3) * 32u, 16u, 1024u);
-                    const uint64_t bd = make_sdesc_sw128(wk + (uint32_t)(k >> 2) * 2u * 1024u + (uint32_t)(k & 3) * 32u, 16u, 1024u);
-                    mma_tf32_ss(tmem_u + t_d2, ad, bd, idesc_d2, k > 0);
-                }
+                // K step k covers j = 8k .. 8k+7: swizzle atom k/4 (8 KB apart in h, 2 KB in W2), 32 B inside the atom;
+                // fully unrolled so that the descriptors are base + constant
+                const uint64_t ad0 = make_sdesc_sw128(ha, 16u, 1024u), bd0 = make_sdesc_sw128(wk, 16u, 1024u);
+#pragma unroll
+                for (int k = 0; k < T3_HP / 8; ++k)
+                    if (k < ksteps)
+                        mma_tf32_ss(tmem_u + t_d2, ad0 + (uint64_t)((k >> 2) * 512 + (k & 3) * 2),
+                                    bd0 + (uint64_t)((k >> 2) * 128 + (k & 3) * 2), idesc_d2, k > 0);
                 mma_commit(&mbar[7]);
             }
             __syncwarp();
         }
+        T3_STAMP(6);
         // (E) softmax cross-entropy gradient: M = 64 accumulators put sample b on lane b%16 of quadrant
         // b/16, i.e. lanes 0..15 of warps 0 and 1 own the 32 samples
         if (warp < 2) {
             mbar_wait(&mbar[7], ph);
             tc_fence_after();
+            T3_STAMP(7);
             float z[16];
             tmem_ld16(tlane + t_d2, z);
             tmem_ld_wait();
+            T3_STAMP(8);
             if (lane < 16) {
                 const int b = 16 * warp + lane;
                 float dzv[16];
                 if (b < bcur) {
+                    // straight-line: the bias image carries -3e38 for the padding classes o >= OUT, so they
+                    // drop out of the max and get probability exactly 0 without a predicate per class
                     float m = -3.0e38f;
 #pragma unroll
-                    for (int o = 0; o < 10; ++o) { z[o] = (o < OUT) ? z[o] + b2s[o] : -3.0e38f; m = fmaxf(m, z[o]); }
+                    for (int o = 0; o < 10; ++o) { z[o] += b2s[o]; m = fmaxf(m, z[o]); }
                     float sum = 0.f;
 #pragma unroll
-                    for (int o = 0; o < 10; ++o) { z[o] = (o < OUT) ? __expf(z[o] - m) : 0.f; sum += z[o]; }
+                    for (int o = 0; o < 10; ++o) { z[o] = __expf(z[o] - m); sum += z[o]; }
                     const float inv = 1.f / sum, invb = 1.f / (float)bcur;
                     const int yy = ysm[par * T3_B + b];
 #pragma unroll
-                    for (int o = 0; o < 16; ++o) dzv[o] = (o < 10 && o < OUT) ? (z[o] * inv - (o == yy ? 1.f : 0.f)) * invb : 0.f;
+                    for (int o = 0; o < 16; ++o) dzv[o] = (o < 10) ? (z[o] * inv - (o == yy ? 1.f : 0.f)) * invb : 0.f;
                 } else {
 #pragma unroll
                     for (int o = 0; o < 16; ++o) dzv[o] = 0.f;
@@ -366,12 +380,13 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
                 for (int o = 0; o < 16; ++o) dzT[kmaj_off(8, o, b)] = dzv[o];             // dz2^T[o][b]: K = b
             }
             fence_proxy_async();
+            T3_STAMP(9);
         }
         if (tid >= 64 && tid < 96 && s + 1 < total_steps)            // labels of the next step
             ysm[(par ^ 1) * T3_B + (tid - 64)] = stage_ys[(size_t)(s + 1) * T3_B + (tid - 64)];
         tc_fence_before();
         __syncthreads();
-        if (profiling && tid == 0) { const long long t = clock64(); prof[3] += t - t0; t0 = t; }
+        T3_STAMP(10);
 
         // (F) backward GEMMs: dh^T = W2^T . dz2^T (K = 16) and gW2^T = h^T . dz2 (K = 32)
         if (warp == 0) {
@@ -384,22 +399,24 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
                     mma_tf32_ss(tmem_u + t_dh, wt + (uint64_t)(k * 16), dd + (uint64_t)(k * 16), idesc_dh, k > 0);
+                mma_commit(&mbar[8]);                    // dh is on the critical path ...
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     mma_tf32_ss(tmem_u + t_gw, ht + (uint64_t)(k * 16), dt + (uint64_t)(k * 16), idesc_gw, k > 0);
-                mma_commit(&mbar[8]);
+                mma_commit(&mbar[9]);                    // ... gW2 only feeds the off-path second-layer update
             }
             __syncwarp();
         }
+        T3_STAMP(11);
         mbar_wait(&mbar[8], ph);
         tc_fence_after();
+        T3_STAMP(12);
         const float s_next = sscale * decay;
         float gw2[16];
         float gb1 = 0.f;
         {
             float dh[16];
             tmem_ld16(tlane + t_dh + 16 * half, dh);
-            if (half == 0) tmem_ld16(tlane + t_gw, gw2);
             tmem_ld_wait();
             const float ascale = -p.lr / s_next;
             float outv[16];
@@ -414,15 +431,16 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(arow + q * 32) = make_float4(outv[4 * q], outv[4 * q + 1], outv[4 * q + 2], outv[4 * q + 3]);
-            if (half == 1) gb1p[j] = gb1;
+            gb1p[half * T3_HP + j] = gb1;                // partial bias gradient of my 16 samples
         }
+        T3_STAMP(13);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (profiling && tid == 0) { const long long t = clock64(); prof[4] += t - t0; t0 = t; }
+        T3_STAMP(14);
 
         // (G) update MMA: W1[128 x FP] += A2[128 x 32] . X^T-tile (both operands K-major, K = batch)
-        if (warp == 0) {
+        if (warp == T3_MMA_WARP) {
             mbar_wait(&mbar[1], ph);                     // X^T tile of this step has landed
             tc_fence_after();
             if (elect_one()) {
@@ -441,8 +459,13 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
             }
             __syncwarp();
         }
-        // (H) second-layer parameters: thread (j, 0) owns column j of W2 (both operand images) and b1[j]
+        T3_STAMP(15);
+        // (H) second-layer parameters: thread (j, 0) owns column j of W2 (both operand images)
+        mbar_wait(&mbar[9], ph);                         // gW2 retired (every warp: h^T / dz2^T are rewritten next step)
+        tc_fence_after();
         if (half == 0) {
+            tmem_ld16(tlane + t_gw, gw2);
+            tmem_ld_wait();
             if (j < H) {
                 float* wrow = w2t + (size_t)(j >> 3) * (4 * 32) + (j & 7) * 4;          // W2^T[j][o], 4 chunks of 4 outputs
                 float wn[12];
@@ -458,19 +481,19 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
                 for (int q = 0; q < 3; ++q)
                     *reinterpret_cast<float4*>(wrow + q * 32) = make_float4(wn[4 * q], wn[4 * q + 1], wn[4 * q + 2], wn[4 * q + 3]);
             }
-            b1s[j] = fmaf(-p.lr, gb1 + gb1p[j], b1s[j] * decay);
-        } else if (tid >= 128 && tid < 128 + OUT) {
-            const int o = tid - 128;
+        } else if (tid >= 160 && tid < 160 + OUT) {     // (warp 5: warp 4 is busy issuing the update MMAs)
+            const int o = tid - 160;
             float gsum = 0.f;
             for (int b = 0; b < T3_B; ++b) gsum += dzs[kmaj_off(4, b, o)];
             b2s[o] = fmaf(-p.lr, gsum, b2s[o] * decay);
         }
+        b1r = fmaf(-p.lr, gb1 + gb1p[(half ^ 1) * T3_HP + j], b1r * decay);
         sscale = s_next;
-        if (profiling && tid == 0) { const long long t = clock64(); prof[5] += t - t0; t0 = t; }
+        T3_STAMP(16);
     }
 
     // ---- drain the tensor pipe and write everything back ------------------------------------------------
-    if (warp == 0) {
+    if (warp == T3_MMA_WARP) {
         if (elect_one()) mma_commit(&mbar[4]);
         __syncwarp();
     }
@@ -507,16 +530,17 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
     }
     if (rank == 0) {
         for (int i = tid; i < OUT * H; i += T3_THREADS) { const int o = i / H, jj = i % H; W2g[i] = w2t[kmaj_off(4, jj, o)]; }
-        if (tid < H) b1g[tid] = b1s[tid];
+        if (half == 0 && j < H) b1g[j] = b1r;
         if (tid < OUT) b2g[tid] = b2s[tid];
     }
-    if (profiling && tid == 0 && rank == 0) {
-        for (int i = 0; i < 6; ++i) p.dbg[i] = (float)((double)prof[i] / (double)total_steps);
+    if (profiling && tid == 0) {
+        for (int i = 0; i < 17; ++i) p.dbg[rank * 32 + i] = (float)((double)prof[i] / (double)total_steps);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<T3_TMEM_COLS>(tmem);
     gb_cluster_sync();
+#undef T3_STAMP
 }
 
 // staging buffers: one per (device, stream), grown on demand.  The training kernel that consumes a

@@ -108,6 +108,11 @@ GB_DEVICE void mbar_wait_cluster(uint64_t* mbar, uint32_t parity) {
     } while (!done);
 }
 // 16-byte store into a peer CTA's shared memory that signals completion on the PEER's mbarrier
+// one arrival on a barrier in ANOTHER CTA of the cluster; release at cluster scope publishes the
+// caller's earlier (remote) stores to whoever acquires the barrier phase
+GB_DEVICE void mbar_arrive_cluster_release(uint32_t remote_mbar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote_mbar) : "memory");
+}
 GB_DEVICE void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_mbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1,%2,%3,%4}, [%5];"
                  :: "r"(remote_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_mbar) : "memory");
