@@ -78,3 +78,12 @@ def test_two_ranks_cuda_equal_single_gpu():
     single = _run(1, "cuda:0")
     multi = _run(2, "cuda")
     _compare(single, multi, rel=2e-3)
+
+
+@pytest.mark.gpu
+def test_pens_two_ranks_cuda_equal_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    single = _run(1, "cuda:0", rounds=9, kinds="pens")
+    multi = _run(2, "cuda", rounds=9, kinds="pens")
+    _compare(single, multi, rel=2e-3, skip=("cache_left",))
