@@ -9,6 +9,7 @@
 3  main_all2all        8-node all-to-all averaging, NVLS multicast all-reduce
 4  main_giaretta_2019  partitioned-model merge, 64 nodes over 8 GPUs (8 nodes per GPU)
 5  main_onoszko_2021   ResNet-20 on CIFAR-shape data, 8 nodes, TokenAccount flow control
+6  weak scaling        config 2 with 8 nodes PER GPU (8 x world nodes, 7 500 samples each): aggregate node-rounds/s
 
 Rank 0 prints one JSON line: rounds/s (device time, max over ranks), metric curve tail, message counters.
 ``--scale`` shrinks the data sets (1.0 = the sizes named above)."""
@@ -115,8 +116,18 @@ def main():
                                        AEP.PUSH, sampling_eval=0.)
         sim.native_utility = 1
         desc = "ResNet-20, CIFAR-shape, 8 nodes, RandomizedTokenAccount(4,2)"
+    elif a.config == 6:
+        n_nodes = 8 * world
+        (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(int(7500 * n_nodes * sc), int(10000 * sc))
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n_nodes, eval_on_user=False, auto_assign=False)
+        disp.set_assignments(AssignmentHandler(42).label_pathological_skew(ytr, n_nodes, 2), None)
+        proto = TorchModelHandler(TorchMLP(784, 10, (100,)), torch.optim.SGD, {"lr": .1},
+                                  torch.nn.CrossEntropyLoss(), batch_size=32)
+        nodes = GossipNode.generate(disp, StaticP2PNetwork(n_nodes), proto, 100, True)
+        sim = GossipSimulator(nodes, disp, 100, AEP.PUSH_PULL)
+        desc = "weak scaling: MLP 784-100-10 push-pull, %d nodes (8 per GPU), non-IID" % n_nodes
     else:
-        raise SystemExit("config must be 1..5")
+        raise SystemExit("config must be 1..6")
     sim.progress = False
     sim.engine = a.engine
     rep = SimulationReport()
@@ -149,6 +160,7 @@ def main():
         from gossipy_b200 import ops
         print(json.dumps({"config": a.config, "what": desc, "n_gpus": world, "rounds": a.rounds,
                           "rounds_per_s": a.rounds / sec, "ms_per_round": sec / a.rounds * 1e3,
+                          "node_rounds_per_s": a.rounds / sec * len(sim.nodes),
                           "timing": "host wall clock around synchronised device work, max over ranks",
                           "last_eval": {k: round(v, 4) for k, v in (ev[-1][1].items() if ev else [])},
                           "first_eval": {k: round(v, 4) for k, v in (ev[0][1].items() if ev else [])},
