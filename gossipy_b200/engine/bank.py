@@ -29,7 +29,6 @@ import torch
 
 from .. import ops
 from ..core import CreateModelMode
-from ..ops import metrics as _metrics
 
 _RING = 1 << 22     # in-flight message ids are far younger than this
 

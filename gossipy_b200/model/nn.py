@@ -5,7 +5,7 @@ Larger architectures (ResNet-20) live in :mod:`gossipy_b200.models`.
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Sequence, Tuple
+from typing import Sequence
 
 import torch
 from torch import nn

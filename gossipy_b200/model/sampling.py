@@ -10,7 +10,6 @@ view is still available (``partitions`` / ``sample``) for API parity.
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -18,7 +17,6 @@ import torch
 from torch import LongTensor
 
 from .. import LOG
-from ..engine.flat import FlatLayout
 from . import TorchModel
 
 __all__ = ["TorchModelSampling", "TorchModelPartition"]

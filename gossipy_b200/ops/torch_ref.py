@@ -6,7 +6,7 @@ function documents the reference line whose arithmetic it reproduces.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch

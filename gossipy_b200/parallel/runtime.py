@@ -25,7 +25,7 @@ from typing import Any, Dict, List, Optional
 
 import torch
 
-from .. import GlobalSettings, LOG
+from .. import GlobalSettings
 
 _state: Dict[str, Any] = {"rank": 0, "world": 1, "n_nodes": None, "transport": "none",
                           "placement": None, "arena_capacity": None, "tag": "0"}

@@ -22,7 +22,7 @@ import pickle
 from abc import ABC, abstractmethod
 from collections import defaultdict
 from copy import deepcopy
-from typing import Any, Callable, DefaultDict, Dict, Iterable, List, Optional, Tuple, Union
+from typing import Any, Callable, DefaultDict, Dict, Iterable, List, Optional, Tuple
 
 import numpy as np
 
