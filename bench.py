@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--train-impl", default="", help="force a training kernel: cluster | tc")
     ap.add_argument("--engine", default="native", choices=["native", "python"],
                     help="control plane of the round loop: C++ scheduler or the Python loop")
+    ap.add_argument("--executor", default="native", choices=["native", "python"],
+                    help="native engine only: C++ executor (csrc/exec) or the per-event Python executor")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--curve", action="store_true", help="also print accuracy per round")
     return ap.parse_args()
@@ -158,7 +160,7 @@ def barrier(world: int):
 # --------------------------------------------------------------------------------------------
 # this framework
 # --------------------------------------------------------------------------------------------
-def build_native(world: int, rank: int, train_impl: str, engine: str = "native"):
+def build_native(world: int, rank: int, train_impl: str, engine: str = "native", executor: str = "native"):
     import torch
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork
@@ -189,6 +191,7 @@ def build_native(world: int, rank: int, train_impl: str, engine: str = "native")
     sim = GossipSimulator(nodes, disp, DELTA, AntiEntropyProtocol.PUSH_PULL)
     sim.progress = False
     sim.engine = engine          # "native": C++ scheduler (csrc/sched) drives the round loop
+    sim.native_executor = executor == "native"   # ... and the C++ executor (csrc/exec) enqueues it (one rank)
     rep = SimulationReport()
     sim.add_receiver(rep)
     if torch.cuda.is_available():
@@ -243,7 +246,7 @@ def run_native(args, rank, world):
     K = args.steps if args.steps is not None else 100
     W = args.warmup if args.warmup is not None else 3
     W = max(W, 3)
-    sim, rep = build_native(world, rank, args.train_impl, args.engine)
+    sim, rep = build_native(world, rank, args.train_impl, args.engine, args.executor)
     time_rounds(sim, W, world, resume=False)
     launches0 = ops.launch_count
     with ClockSampler(torch.cuda.current_device() if torch.cuda.is_available() else 0) as clk:
@@ -278,7 +281,8 @@ def run_native(args, rank, world):
                           "parallelism": "gossip-dp: %d nodes over %d GPU(s)" % (N_NODES, world),
                           "l2": "192 MB flush buffer rewritten every round (and at N=1 the inputs, 219 MB, exceed the 126 MB L2)",
                           "placement": "block (node i on rank i*N//8), peer rows pulled over NVLink by the fused merge+train kernel",
-                          "train_kernel": args.train_impl or "auto", "engine": args.engine},
+                          "train_kernel": args.train_impl or "auto", "engine": args.engine,
+                          "executor": ("c++ (csrc/exec)" if "_stream_exec" in sim.__dict__ else "python (per event)")},
                "clocks": clk.summary(), "gpu_launches": launches,
                "test_acc_by_round_tail": acc[-5:], "e2e": e2e}
         if args.curve:

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "kernels/kernels.h"
+#include "exec/executor.h"
 #include "sched/scheduler.h"
 
 namespace gb {
@@ -513,4 +514,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("preload", &gb::preload);
     m.def("allreduce_mean", &gb::allreduce_mean);
     gb::bind_scheduler(m);
+    gb::bind_executor(m);
 }

@@ -1,0 +1,270 @@
+// Native executor: turns the scheduler's event list of a round into device work on per-node CUDA
+// streams WITHOUT going back to Python per event.
+//
+// The reference walks Python objects for every message (gossipy/simul.py:389-451 -> node.py:171-204 ->
+// handler.py:117-136).  For the common set-up -- plain GossipNode, TorchModelHandler whose local update
+// is one fused kernel (1-hidden-layer MLP / logistic regression, SGD, cross-entropy), MERGE_UPDATE --
+// everything an event needs is a handful of integers and device pointers, so the whole round is
+// enqueued from C++:
+//
+//   SEND / REPLY_SEND  snapshot kernel  slot <- sender's row            on the SENDER's stream
+//   DELIVER / REPLY    fused merge + local-update kernel (reads slot)   on the RECEIVER's stream
+//
+// with two CUDA events per snapshot slot ordering the streams (slot written -> reader may start; slot
+// read -> slot may be overwritten).  Disjoint node pairs therefore overlap on the device, and the host
+// cost per event is a few hundred nanoseconds plus the launches.  Model ages, per-node update counters
+// and the counter-based shuffle keys are the same functions as in model/handler.py, so a run is
+// bit-identical to the Python executor's (tests/test_stream_executor.py).
+//
+// Memory is owned by Python (arena rows, one tensor of snapshot slots, the nodes' torch streams); this
+// file only holds pointers.  `use_cuda = false` replaces the two launches by Python callbacks: the CPU
+// tests exercise all of the bookkeeping below against the Python executor.
+#include "executor.h"
+
+#include <cuda_runtime.h>
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/stl.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../kernels/kernels.h"
+
+namespace py = pybind11;
+
+namespace gb {
+
+namespace {
+
+inline uint64_t mix64(uint64_t x) {          // engine/rng.py::mix64
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// event kinds / message types of csrc/sched/scheduler.cpp
+enum : int32_t { EV_SEND = 0, EV_DROP = 1, EV_DELIVER = 2, EV_REPLY_SEND = 3, EV_REPLY_DELIVER = 4, EV_EVAL = 5 };
+enum : int32_t { MT_PUSH = 1, MT_PULL = 2, MT_REPLY = 3, MT_PUSH_PULL = 4 };
+
+struct Node {
+    float* row = nullptr; const float* X = nullptr; const int64_t* y = nullptr;
+    int n = 0; int64_t age = 0, counter = 0; cudaStream_t stream = nullptr;
+};
+
+struct Slot { int64_t age = 0; cudaEvent_t written = nullptr, read = nullptr; bool has_reader = false; };
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+}  // namespace
+
+class StreamExecutor {
+public:
+    // family 0 = mlp1 (dims IN, H, OUT), 1 = logreg (dims IN, OUT; H ignored)
+    StreamExecutor(int n_nodes, int family, int IN, int H, int OUT, int batch_size, int epochs, double lr, double wd,
+                   uint64_t base_seed, bool use_cuda)
+        : nodes_(n_nodes), family_(family), IN_(IN), H_(H), OUT_(OUT), B_(batch_size), epochs_(epochs),
+          lr_((float)lr), wd_((float)wd), seed_(base_seed), cuda_(use_cuda) {
+        if (n_nodes <= 0) throw std::invalid_argument("n_nodes must be positive");
+    }
+    ~StreamExecutor() {
+        for (Slot& s : slots_) {
+            if (s.written) cudaEventDestroy(s.written);
+            if (s.read) cudaEventDestroy(s.read);
+        }
+    }
+
+    void set_node(int i, uintptr_t row, uintptr_t X, uintptr_t y, int n, int64_t age, int64_t counter, uintptr_t stream) {
+        Node& nd = nodes_.at(i);
+        nd.row = reinterpret_cast<float*>(row); nd.X = reinterpret_cast<const float*>(X);
+        nd.y = reinterpret_cast<const int64_t*>(y); nd.n = n; nd.age = age; nd.counter = counter;
+        nd.stream = reinterpret_cast<cudaStream_t>(stream);
+    }
+    void set_node_data(int i, uintptr_t X, uintptr_t y, int n) {       // streamed inputs: the buffers alternate per round
+        Node& nd = nodes_.at(i);
+        nd.X = reinterpret_cast<const float*>(X); nd.y = reinterpret_cast<const int64_t*>(y); nd.n = n;
+    }
+    // the snapshot slots: one [cap, stride] fp32 tensor owned by Python; growing keeps the old contents (Python copies)
+    void set_slots(uintptr_t base, int cap, int64_t stride_floats, int64_t row_floats) {
+        if (cap < (int)slots_.size()) throw std::invalid_argument("the slot pool cannot shrink");
+        slot_base_ = reinterpret_cast<float*>(base); stride_ = stride_floats; row_floats_ = row_floats;
+        for (int s = (int)slots_.size(); s < cap; ++s) { slots_.emplace_back(); free_.push_back(s); }
+    }
+    void set_callbacks(py::function snapshot, py::function train) { cb_snapshot_ = snapshot; cb_train_ = train; }
+    int slots_needed() const { return (int)slots_.size(); }
+    int free_slots() const { return (int)free_.size(); }
+
+    // Executes one round's events [n, 6] = (kind, tick, a, b, slot, aux).  Returns the nodes to evaluate.
+    // Raises if the pool runs out of slots: the caller grows it (set_slots) and calls again with `start`
+    // = the index reported in the exception state (`resume_at`).
+    std::vector<int> run(py::array_t<int32_t, py::array::c_style | py::array::forcecast> events, int64_t start) {
+        const auto ev = events.unchecked<2>();
+        std::vector<int> evals;
+        resume_at_ = -1;
+        for (int64_t i = start; i < ev.shape(0); ++i) {
+            const int32_t kind = ev(i, 0), a = ev(i, 2), b = ev(i, 3), id = ev(i, 4), aux = ev(i, 5);
+            switch (kind) {
+                case EV_SEND:
+                    if (aux != MT_PULL) { if (!snapshot(a, id)) { resume_at_ = i; return evals; } }
+                    break;
+                case EV_REPLY_SEND:                       // b answers with its (just updated) model; reply id in aux
+                    if (!snapshot(b, aux)) { resume_at_ = i; return evals; }
+                    break;
+                case EV_DROP: {
+                    auto it = inflight_.find(id);
+                    if (it != inflight_.end()) { free_.push_back(it->second); inflight_.erase(it); }
+                    break;
+                }
+                case EV_DELIVER:
+                    if (aux == MT_PUSH || aux == MT_PUSH_PULL) consume(b, id);
+                    break;
+                case EV_REPLY_DELIVER:
+                    consume(a, id);
+                    break;
+                case EV_EVAL:
+                    evals.push_back(a);
+                    break;
+                default:
+                    break;
+            }
+        }
+        return evals;
+    }
+    int64_t resume_at() const { return resume_at_; }
+
+    std::vector<int64_t> ages() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.age); return v; }
+    std::vector<int64_t> counters() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.counter); return v; }
+    int64_t launches() const { return launches_; }
+    // messages on the wire: (message id, slot, age) -- checkpointing
+    std::vector<std::vector<int64_t>> inflight() const {
+        std::vector<std::vector<int64_t>> v;
+        for (const auto& kv : inflight_) v.push_back({kv.first, kv.second, slots_[kv.second].age});
+        std::sort(v.begin(), v.end());
+        return v;
+    }
+    void import_inflight(const std::vector<std::vector<int64_t>>& rows) {     // slots already filled by Python
+        for (const auto& r : rows) {
+            const int s = (int)r.at(1);
+            auto it = std::find(free_.begin(), free_.end(), s);
+            if (it == free_.end()) throw std::invalid_argument("slot is not free");
+            free_.erase(it);
+            slots_.at(s).age = r.at(2);
+            inflight_[(int32_t)r.at(0)] = s;
+        }
+    }
+
+private:
+    float* slot_ptr(int s) const { return slot_base_ + (size_t)s * stride_; }
+    int steps_of(const Node& nd) const {
+        const int bs = B_ == 0 ? nd.n : std::min(B_, nd.n);
+        return epochs_ > 0 ? epochs_ * ((nd.n + bs - 1) / bs) : 1;
+    }
+    uint64_t key_of(int node, const Node& nd) const {     // model/handler.py::_next_key -> engine/rng.py::derive
+        uint64_t h = mix64(seed_);
+        const uint64_t parts[4] = {0x5EEDull, (uint64_t)node, (uint64_t)nd.counter, (uint64_t)nd.age};
+        for (uint64_t p : parts) h = mix64(h ^ p);
+        return h & ((1ull << 63) - 1);
+    }
+
+    bool snapshot(int node, int32_t msg_id) {
+        if (free_.empty()) return false;
+        const int s = free_.back(); free_.pop_back();
+        Node& nd = nodes_.at(node);
+        Slot& sl = slots_[s];
+        sl.age = nd.age;
+        if (cuda_) {
+            // the slot's previous life: its reader (WAR) and -- for a dropped message nobody read -- its writer (WAW)
+            if (sl.has_reader) cuda_check(cudaStreamWaitEvent(nd.stream, sl.read, 0), "wait for the slot's last reader");
+            if (sl.written) cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the slot's last writer");
+            launch_merge_pair(slot_ptr(s), nd.row, 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr}, nd.stream);
+            if (!sl.written) cuda_check(cudaEventCreateWithFlags(&sl.written, cudaEventDisableTiming), "event");
+            cuda_check(cudaEventRecord(sl.written, nd.stream), "record slot written");
+            cuda_check(cudaGetLastError(), "snapshot launch");
+        } else {
+            cb_snapshot_(node, s);
+        }
+        ++launches_;
+        inflight_[msg_id] = s;
+        return true;
+    }
+
+    void consume(int node, int32_t msg_id) {               // MERGE_UPDATE: 0.5 / 0.5 merge folded into the local update
+        auto it = inflight_.find(msg_id);
+        if (it == inflight_.end()) throw std::runtime_error("delivery of an unknown message");
+        const int s = it->second;
+        inflight_.erase(it);
+        Node& nd = nodes_.at(node);
+        Slot& sl = slots_[s];
+        nd.age = std::max(nd.age, sl.age);
+        nd.counter += 1;
+        const uint64_t key = key_of(node, nd);
+        if (cuda_) {
+            cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
+            bool ok;
+            const char* why = "";
+            if (family_ == 0) {
+                TrainParams p{};
+                p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.H = H_; p.OUT = OUT_;
+                p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
+                p.peer = slot_ptr(s); p.w_self = 0.5f; p.w_peer = 0.5f;
+                ok = launch_mlp1_train(p, kTrainAuto, nd.stream, &why);
+            } else {
+                LogregParams p{};
+                p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.OUT = OUT_;
+                p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
+                p.peer = slot_ptr(s); p.w_self = 0.5f; p.w_peer = 0.5f;
+                ok = launch_logreg_train(p, nd.stream);
+            }
+            if (!ok) throw std::runtime_error(std::string("training kernel rejected the shape: ") + why);
+            if (!sl.read) cuda_check(cudaEventCreateWithFlags(&sl.read, cudaEventDisableTiming), "event");
+            cuda_check(cudaEventRecord(sl.read, nd.stream), "record slot read");
+            sl.has_reader = true;
+            cuda_check(cudaGetLastError(), "training launch");
+        } else {
+            cb_train_(node, s, (int64_t)key);
+        }
+        ++launches_;
+        nd.age += steps_of(nd);
+        free_.push_back(s);
+    }
+
+    std::vector<Node> nodes_;
+    int family_, IN_, H_, OUT_, B_, epochs_;
+    float lr_, wd_;
+    uint64_t seed_;
+    bool cuda_;
+    float* slot_base_ = nullptr; int64_t stride_ = 0, row_floats_ = 0;
+    std::vector<Slot> slots_;
+    std::vector<int> free_;
+    std::unordered_map<int32_t, int> inflight_;
+    py::function cb_snapshot_, cb_train_;
+    int64_t launches_ = 0, resume_at_ = -1;
+};
+
+void bind_executor(py::module_& m) {
+    py::class_<StreamExecutor>(m, "StreamExecutor", "Native executor of a round's event list (csrc/exec/executor.cpp)")
+        .def(py::init<int, int, int, int, int, int, int, double, double, uint64_t, bool>(), py::arg("n_nodes"),
+             py::arg("family"), py::arg("IN"), py::arg("H"), py::arg("OUT"), py::arg("batch_size"), py::arg("epochs"),
+             py::arg("lr"), py::arg("wd"), py::arg("base_seed"), py::arg("use_cuda"))
+        .def("set_node", &StreamExecutor::set_node)
+        .def("set_node_data", &StreamExecutor::set_node_data)
+        .def("set_slots", &StreamExecutor::set_slots)
+        .def("set_callbacks", &StreamExecutor::set_callbacks)
+        .def("run", &StreamExecutor::run, py::arg("events"), py::arg("start") = 0)
+        .def_property_readonly("resume_at", &StreamExecutor::resume_at)
+        .def_property_readonly("free_slots", &StreamExecutor::free_slots)
+        .def_property_readonly("launches", &StreamExecutor::launches)
+        .def("ages", &StreamExecutor::ages)
+        .def("counters", &StreamExecutor::counters)
+        .def("inflight", &StreamExecutor::inflight)
+        .def("import_inflight", &StreamExecutor::import_inflight);
+}
+
+}  // namespace gb

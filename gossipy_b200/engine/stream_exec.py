@@ -1,0 +1,192 @@
+"""Glue of the native executor (``csrc/exec/executor.cpp``): a round's event list is enqueued from C++.
+
+Eligible simulations (``eligible`` returns ``None``): a plain :class:`GossipSimulator` of plain
+:class:`GossipNode` s whose handlers are :class:`TorchModelHandler` s on the fused kernel path (1-hidden-
+layer ReLU MLP or logistic regression, momentum-free SGD, mean cross-entropy), ``MERGE_UPDATE``, identical
+hyper-parameters on all nodes, one rank.  That is the reference's ``main_hegedus_2021`` shape and the
+headline benchmark.  Everything else keeps the per-event Python executor (or the bank for linear learners).
+
+Python owns all memory -- the handlers' arena rows, ONE tensor of snapshot slots, the nodes' torch streams
+(so evaluation, which stays in Python, is ordered after the native launches on the same streams) -- and
+mirrors ages / update counters back into the handlers after every ``start``.  On CPU the two launches are
+Python callbacks into :mod:`gossipy_b200.ops`, which makes the native bookkeeping testable without a GPU.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..core import CreateModelMode
+from . import arena as _arena
+from . import rng as _rng
+
+
+def eligible(sim: Any) -> Optional[str]:
+    """``None`` when the native executor can run ``sim``, else the reason it cannot."""
+    from ..model import handler as H
+    from ..node import GossipNode
+    from ..parallel import runtime as prt
+    if type(sim).__name__ != "GossipSimulator":
+        return "simulator variant"
+    if prt.active():
+        return "several ranks"
+    if not H.FUSE_MERGE_UPDATE:
+        return "fused merge+update disabled"
+    ids = sorted(sim.nodes)
+    if ids != list(range(len(ids))):
+        return "node ids must be 0..N-1"
+    ref = None
+    for i in ids:
+        node = sim.nodes[i]
+        h = node.model_handler
+        if type(node) is not GossipNode:
+            return "node class %s" % type(node).__name__
+        if type(h) is not H.TorchModelHandler:
+            return "handler class %s" % type(h).__name__
+        if not h._fused or h.mode != CreateModelMode.MERGE_UPDATE or h.layout.int_buffers:
+            return "handler is not on the fused MERGE_UPDATE path"
+        if not isinstance(h.n_updates, (int, np.integer)):
+            return "vector-valued model age"
+        sig = (h._family, h.batch_size, h.local_epochs, float(h.optimizer_params.get("lr", 1e-3)),
+               float(h.optimizer_params.get("weight_decay", 0.0)), h._row_numel)
+        if ref is None:
+            ref = sig
+        elif sig != ref:
+            return "nodes differ in architecture or hyper-parameters"
+        x = node.data[0][0] if isinstance(node.data[0], (tuple, list)) else None
+        if x is None or int(x.shape[0]) == 0:
+            return "node without training data"
+    return None
+
+
+class StreamExec:
+    def __init__(self, sim: Any) -> None:
+        from ..ops.native import _try_import
+        self.sim = sim
+        self.C = _try_import()
+        ids = sorted(sim.nodes)
+        h0 = sim.nodes[ids[0]].model_handler
+        self.device = h0.device
+        self.cuda = self.device.type == "cuda"
+        fam, dims = h0._family
+        self.family = fam
+        self.dims = tuple(int(d) for d in dims)
+        self.bs, self.epochs = int(h0.batch_size), int(h0.local_epochs)
+        self.lr = float(h0.optimizer_params.get("lr", 1e-3))
+        self.wd = float(h0.optimizer_params.get("weight_decay", 0.0))
+        self.row_numel = int(h0._row_numel)
+        if fam == "mlp1":
+            IN, Hd, OUT = self.dims
+        else:
+            IN, OUT = self.dims[0], self.dims[-1]
+            Hd = 0
+        self.ex = self.C.StreamExecutor(len(ids), 0 if fam == "mlp1" else 1, IN, Hd, OUT, self.bs, self.epochs,
+                                        self.lr, self.wd, _rng.base_seed(), self.cuda)
+        self.slots = torch.zeros(max(16, 4 * len(ids)), self.row_numel, dtype=torch.float32, device=self.device)
+        self._publish_slots()
+        if not self.cuda:
+            self.ex.set_callbacks(self._cb_snapshot, self._cb_train)
+        self._data: Dict[int, Any] = {}
+        self.bind_nodes()
+
+    # -- state shared with the handlers ---------------------------------------------------------------
+    def _publish_slots(self) -> None:
+        self.ex.set_slots(self.slots.data_ptr(), int(self.slots.shape[0]), int(self.slots.stride(0)), self.row_numel)
+
+    def _node_data(self, i: int):
+        h = self.sim.nodes[i].model_handler
+        with _arena.on_stream(h._stream()):
+            x, y = h._to_device(self.sim.nodes[i].data[0])
+        if x.dim() > 2:
+            x = x.reshape(x.shape[0], -1)
+        if y.dim() > 1:
+            y = torch.argmax(y, dim=-1)
+        x, y = x.contiguous(), y.contiguous()
+        if y.dtype != torch.int64:
+            y = y.long()
+        self._data[i] = (x, y)                  # keeps the tensors alive while C++ holds their addresses
+        return x, y
+
+    def bind_nodes(self) -> None:
+        """(Re)read rows, data, ages, counters and streams from the handlers (start of every ``start``)."""
+        for i, node in self.sim.nodes.items():
+            h = node.model_handler
+            row = h.row
+            x, y = self._node_data(i)
+            s = h._stream()
+            self.ex.set_node(i, row.data_ptr(), x.data_ptr(), y.data_ptr(), int(x.shape[0]), int(h.n_updates),
+                             int(h._update_counter), int(s.cuda_stream) if s is not None else 0)
+
+    def refresh_data(self) -> None:
+        """Streamed inputs: the resident buffers alternate every round."""
+        for i in self.sim.nodes:
+            x, y = self._node_data(i)
+            self.ex.set_node_data(i, x.data_ptr(), y.data_ptr(), int(x.shape[0]))
+
+    def sync_back(self) -> None:
+        ages, counters = self.ex.ages(), self.ex.counters()
+        for i, node in self.sim.nodes.items():
+            h = node.model_handler
+            if int(h.n_updates) != ages[i] or h._update_counter != counters[i]:
+                h._version += 1
+            h.n_updates = int(ages[i])
+            h._update_counter = int(counters[i])
+
+    # -- CPU callbacks -----------------------------------------------------------------------------------
+    def _cb_snapshot(self, node: int, slot: int) -> None:
+        self.slots[slot].copy_(self.sim.nodes[node].model_handler.row)
+
+    def _cb_train(self, node: int, slot: int, key: int) -> None:
+        h = self.sim.nodes[node].model_handler
+        x, y = self._data[node]
+        fn = ops.mlp1_train if self.family == "mlp1" else ops.logreg_train
+        fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key), None,
+           merge_from=(self.slots[slot], 0.5, 0.5, None))
+
+    # -- one round -------------------------------------------------------------------------------------------
+    def run_round(self, events: np.ndarray) -> List[int]:
+        before = self.ex.launches
+        if self.cuda:
+            with torch.cuda.device(self.device):
+                evals = self._run(events)
+            ops._count(int(self.ex.launches - before))
+            return evals
+        return self._run(events)
+
+    def _run(self, events: np.ndarray) -> List[int]:
+        evals = list(self.ex.run(events, 0))
+        while self.ex.resume_at >= 0:           # out of snapshot slots: grow the pool, continue where it stopped
+            self._grow()
+            evals += list(self.ex.run(events, int(self.ex.resume_at)))
+        return evals
+
+    def _grow(self) -> None:
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
+        bigger = torch.zeros(2 * int(self.slots.shape[0]), self.row_numel, dtype=torch.float32, device=self.device)
+        bigger[:self.slots.shape[0]].copy_(self.slots)
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
+        self.slots = bigger
+        self._publish_slots()
+
+    # -- checkpointing -----------------------------------------------------------------------------------------
+    def export_inflight(self) -> Dict[str, Any]:
+        rows = self.ex.inflight()
+        idx = torch.as_tensor([r[1] for r in rows], dtype=torch.int64, device=self.device)
+        return {"ids": [int(r[0]) for r in rows], "ages": [int(r[2]) for r in rows],
+                "rows": self.slots[idx].cpu() if rows else torch.zeros(0, self.row_numel)}
+
+    def import_inflight(self, st: Dict[str, Any]) -> None:
+        n = len(st["ids"])
+        if n == 0:
+            return
+        while int(self.slots.shape[0]) < n or self.ex.free_slots < n:
+            self._grow()
+        taken = {int(r[1]) for r in self.ex.inflight()}
+        free = [s for s in range(int(self.slots.shape[0])) if s not in taken][:n]
+        self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = st["rows"].to(self.device)
+        self.ex.import_inflight([[int(m), int(s), int(a)] for m, s, a in zip(st["ids"], free, st["ages"])])

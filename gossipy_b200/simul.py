@@ -484,6 +484,11 @@ class GossipSimulator(SimulationEventSender):
             if why is None:
                 self._run_native_banked(sch, n_rounds, C)
                 return
+        if self.native_executor and type(self) is GossipSimulator:
+            from .engine import stream_exec as _sx
+            if _sx.eligible(self) is None:
+                self._run_native_streamed(sch, n_rounds)
+                return
         SEND, DROP, DELIVER, RSEND, RDELIVER, EVAL, TIMEOUT = (C.EV_SEND, C.EV_DROP, C.EV_DELIVER,
                                                               C.EV_REPLY_SEND, C.EV_REPLY_DELIVER, C.EV_EVAL,
                                                               C.EV_TIMEOUT)
@@ -533,6 +538,64 @@ class GossipSimulator(SimulationEventSender):
         self.notify_end()
 
     batched = True    # native engine: execute bankable set-ups (linear learners) many nodes per launch
+    native_executor = True    # native engine: enqueue eligible set-ups from C++ (engine/stream_exec.py)
+
+    def _run_native_streamed(self, sch, n_rounds: int) -> None:
+        """Rounds of an eligible simulation (``engine.stream_exec.eligible``): the scheduler's event list
+        goes straight to the C++ executor, which enqueues snapshots and fused merge+update kernels on the
+        nodes' streams; Python only evaluates (on the same streams) and keeps the books per ROUND."""
+        from .engine.stream_exec import StreamExec
+        sx = self.__dict__.get("_stream_exec")
+        if sx is None:
+            sx = self.__dict__["_stream_exec"] = StreamExec(self)
+            inflight = self.__dict__.pop("_exec_inflight", None)
+            if inflight is not None:
+                sx.import_inflight(inflight)
+        else:
+            sx.bind_nodes()
+        reports = [r for r in self._receivers if type(r) is SimulationReport]
+        others = [r for r in self._receivers if type(r) is not SimulationReport]
+        size_model = int(self.nodes[0].model_handler.get_size())
+        prev_finish = None
+        try:
+            for _ in range(n_rounds):
+                if self.stream_inputs:
+                    self._stream_round_inputs()
+                    sx.refresh_data()
+                sent0, failed0, size0 = int(sch.sent), int(sch.failed), int(sch.total_size)
+                with nvtx_range("schedule"):
+                    events = sch.run(1)
+                t_last = int(sch.clock) - 1
+                with nvtx_range("execute"):
+                    evals = sx.run_round(events)
+                sent, failed, size = int(sch.sent) - sent0, int(sch.failed) - failed0, int(sch.total_size) - size0
+                for r in reports:                      # bulk accounting (same totals as per-message calls)
+                    r._sent_messages += sent
+                    r._total_size += size
+                    r._failed_messages += failed
+                if others:
+                    n_model = (size - sent) // (size_model - 1) if size_model > 1 else sent
+                    stub_model = _SizedMessage(Message(t_last, 0, 0, MessageType.PUSH, None), size_model)
+                    stub_small = _SizedMessage(Message(t_last, 0, 0, MessageType.PULL, None), 1)
+                    for r in others:
+                        for _i in range(n_model):
+                            r.update_message(False, stub_model)
+                        for _i in range(sent - n_model):
+                            r.update_message(False, stub_small)
+                        for _i in range(failed):
+                            r.update_message(True)
+                finish = self._evaluate_nodes(t_last, [self.nodes[i] for i in evals], defer=self.pipeline_eval)
+                if prev_finish is not None:
+                    prev_finish()
+                prev_finish = finish
+                self._clock = int(sch.clock)
+                self.notify_timestep(t_last)
+        except KeyboardInterrupt:
+            LOG.warning("Simulation interrupted by user.")
+        if prev_finish is not None:
+            prev_finish()
+        sx.sync_back()
+        self.notify_end()
 
     def _run_native_banked(self, sch, n_rounds: int, C) -> None:
         """Rounds of a bankable simulation: the scheduler's event list of a round is executed by
@@ -606,6 +669,7 @@ class GossipSimulator(SimulationEventSender):
         st["_receiver_list"] = list(self._receivers)
         st.pop("_collective", None)
         bank = st.pop("_bank", None)
+        sx = st.pop("_stream_exec", None)
         sch = st.pop("_scheduler", None)
         if sch is not None:
             # native engine: the scheduler's dynamic state + the in-flight messages (their models are
@@ -615,6 +679,8 @@ class GossipSimulator(SimulationEventSender):
             if bank is not None:
                 pending = [int(r[1]) for r in state["msg_q"] if int(r[4]) != 2] + [int(r[1]) for r in state["rep_q"]]
                 st["_bank_inflight"] = bank.export_inflight(pending)
+            if sx is not None:
+                st["_exec_inflight"] = sx.export_inflight()
         return st
 
     def __repr__(self) -> str:

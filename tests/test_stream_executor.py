@@ -1,0 +1,151 @@
+"""The C++ executor (csrc/exec) against the per-event Python executor: same native schedule, same counter-based
+shuffle keys -> the runs must be identical (weights, ages, counters, message accounting, metrics).  On CPU the
+executor's two launches are callbacks into gossipy_b200.ops, so all of its bookkeeping is exercised here; the CUDA
+stream / event side is covered by the gpu test at the bottom."""
+import numpy as np
+import pytest
+import torch
+
+from gossipy_b200.ops.native import native_available
+
+pytestmark = pytest.mark.skipif(not native_available(), reason="extension not built")
+
+
+def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=4, device="cpu", sync=True, start=True):
+    import gossipy_b200 as g
+    from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork, UniformDelay
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import TorchModelHandler
+    from gossipy_b200.model.nn import LogisticRegression, TorchMLP
+    from gossipy_b200.node import GossipNode
+    from gossipy_b200.simul import GossipSimulator, SimulationReport
+    g.GlobalSettings().set_device(device)
+    g.CACHE.clear()
+    g.set_seed(7)
+    if model == "mlp":
+        (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(96 * n, 120)
+        net, bs = TorchMLP(784, 10, (100,)), 32
+    else:
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(50 * n + 3, 150)
+        net, bs = LogisticRegression(57, 2), 16
+    disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
+    proto = TorchModelHandler(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(),
+                              batch_size=bs)
+    nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, sync)
+    kw = dict(drop_prob=.15, online_prob=.8, delay=UniformDelay(0, 4), sampling_eval=.5) if faults else {}
+    sim = GossipSimulator(nodes, disp, 10, getattr(AntiEntropyProtocol, protocol), **kw)
+    sim.progress = False
+    sim.engine = "native"
+    sim.native_executor = streamed
+    rep = SimulationReport(); sim.add_receiver(rep)
+    sim.init_nodes(seed=11)
+    if start:
+        sim.start(rounds)
+    return sim, rep
+
+
+def _state(sim):
+    n = len(sim.nodes)
+    rows = torch.stack([sim.nodes[i].model_handler.row.detach().cpu().clone() for i in range(n)])
+    ages = [int(sim.nodes[i].model_handler.n_updates) for i in range(n)]
+    ctr = [int(sim.nodes[i].model_handler._update_counter) for i in range(n)]
+    return rows, ages, ctr
+
+
+def _same(sim_a, rep_a, sim_b, rep_b, tol=0.0):
+    ra, aa, ca = _state(sim_a)
+    rb, ab, cb = _state(sim_b)
+    assert aa == ab and ca == cb
+    if tol == 0.0:
+        assert torch.equal(ra, rb)
+    else:
+        torch.testing.assert_close(ra, rb, rtol=tol, atol=tol)
+    assert (rep_a._sent_messages, rep_a._failed_messages, rep_a._total_size) == \
+        (rep_b._sent_messages, rep_b._failed_messages, rep_b._total_size)
+    ea, eb = rep_a.get_evaluation(False), rep_b.get_evaluation(False)
+    assert [t for t, _ in ea] == [t for t, _ in eb] and len(ea) > 0
+    for (_, m1), (_, m2) in zip(ea, eb):
+        for k in m1:
+            assert m1[k] == pytest.approx(m2[k], abs=max(tol, 1e-9)), k
+
+
+@pytest.mark.parametrize("model,protocol,faults,sync", [("mlp", "PUSH_PULL", False, True), ("logreg", "PUSH", True, False),
+                                                        ("logreg", "PULL", True, True), ("mlp", "PUSH", True, True)])
+def test_native_executor_equals_python_executor(model, protocol, faults, sync):
+    import gossipy_b200 as g
+    sim_a, rep_a = _sim(False, model, protocol, faults, sync=sync)
+    assert "_stream_exec" not in sim_a.__dict__
+    sim_b, rep_b = _sim(True, model, protocol, faults, sync=sync)
+    assert "_stream_exec" in sim_b.__dict__ and sim_b._stream_exec.ex.launches > 0
+    _same(sim_a, rep_a, sim_b, rep_b)
+    assert len(g.CACHE) == 0 or not faults      # the native executor never touches the message cache
+    g.CACHE.clear()
+
+
+def test_slot_pool_grows_and_resume_is_exact(tmp_path):
+    import gossipy_b200 as g
+    from gossipy_b200.simul import GossipSimulator
+    sim_full, rep_full = _sim(True, "logreg", "PUSH_PULL", True, n=12, rounds=6)
+    # same run, interrupted after 3 rounds, checkpointed with messages on the wire, resumed; tiny slot pool
+    sim, rep = _sim(True, "logreg", "PUSH_PULL", True, n=12, rounds=0, start=False)
+    sim.start(3)
+    sx = sim._stream_exec
+    assert len(sx.ex.inflight()) > 0
+    path = str(tmp_path / "ck.pkl")
+    sim.save(path)
+    g.CACHE.clear()
+    sim2 = GossipSimulator.load(path)
+    assert "_stream_exec" not in sim2.__dict__ and "_exec_inflight" in sim2.__dict__
+    rep2 = [r for r in sim2._receivers if type(r).__name__ == "SimulationReport"][0]
+    sim2.start(3, resume=True)
+    _same(sim_full, rep_full, sim2, rep2)
+    # growing the pool in the middle of a round keeps the in-flight snapshots
+    sx2 = sim2._stream_exec
+    before = int(sx2.slots.shape[0])
+    sx2._grow()
+    assert int(sx2.slots.shape[0]) == 2 * before and sx2.ex.free_slots >= before
+    g.CACHE.clear()
+
+
+def test_eligibility():
+    from gossipy_b200.engine.stream_exec import eligible
+    from gossipy_b200.core import CreateModelMode
+    sim, _ = _sim(True, start=False)
+    assert eligible(sim) is None
+    sim.nodes[2].model_handler.mode = CreateModelMode.UPDATE
+    assert eligible(sim) is not None
+    sim.start(1)                                   # falls back to the per-event executor
+    assert "_stream_exec" not in sim.__dict__
+
+
+def test_executor_runs_out_of_slots_gracefully():
+    """Direct use of the C++ class: `run` stops at the event it cannot serve and resumes after the pool grew."""
+    from gossipy_b200.ops.native import _try_import
+    C = _try_import()
+    log = []
+    ex = C.StreamExecutor(3, 1, 4, 0, 2, 2, 1, .1, 0., 5, False)
+    for i in range(3):
+        ex.set_node(i, 0, 0, 0, 6, 10 * i, 0, 0)
+    ex.set_callbacks(lambda n, s: log.append(("snap", n, s)), lambda n, s, k: log.append(("train", n, s)))
+    ex.set_slots(0, 1, 8, 8)
+    ev = np.array([[C.EV_SEND, 0, 0, 1, 100, 1], [C.EV_SEND, 0, 2, 1, 101, 1], [C.EV_DELIVER, 0, 0, 1, 100, 1],
+                   [C.EV_DELIVER, 0, 2, 1, 101, 1], [C.EV_EVAL, 0, 1, -1, -1, 0]], dtype=np.int32)
+    assert list(ex.run(ev, 0)) == [] and ex.resume_at == 1
+    ex.set_slots(0, 4, 8, 8)
+    assert list(ex.run(ev, 1)) == [1] and ex.resume_at == -1
+    assert [e[0] for e in log] == ["snap", "snap", "train", "train"]
+    assert ex.ages() == [0, 20 + 3, 20] and ex.counters() == [0, 2, 0] and ex.inflight() == []
+
+
+@pytest.mark.gpu
+def test_native_executor_cuda_equals_python_executor():
+    import gossipy_b200 as g
+    for model, protocol, faults in (("mlp", "PUSH_PULL", False), ("logreg", "PUSH", True)):
+        sim_a, rep_a = _sim(False, model, protocol, faults, n=8, rounds=5, device="cuda:0")
+        sim_b, rep_b = _sim(True, model, protocol, faults, n=8, rounds=5, device="cuda:0")
+        torch.cuda.synchronize()
+        assert "_stream_exec" in sim_b.__dict__
+        _same(sim_a, rep_a, sim_b, rep_b, tol=1e-6)
+        g.CACHE.clear()
+    g.GlobalSettings().set_device("cpu")
