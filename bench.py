@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--train-impl", default="", help="force a training kernel: cluster | tc")
     ap.add_argument("--engine", default="native", choices=["native", "python"],
                     help="control plane of the round loop: C++ scheduler or the Python loop")
-    ap.add_argument("--executor", default="native", choices=["native", "python"],
+    ap.add_argument("--executor", default="python", choices=["native", "python"],
                     help="native engine only: C++ executor (csrc/exec) or the per-event Python executor")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--curve", action="store_true", help="also print accuracy per round")
@@ -160,7 +160,7 @@ def barrier(world: int):
 # --------------------------------------------------------------------------------------------
 # this framework
 # --------------------------------------------------------------------------------------------
-def build_native(world: int, rank: int, train_impl: str, engine: str = "native", executor: str = "native"):
+def build_native(world: int, rank: int, train_impl: str, engine: str = "native", executor: str = "python"):
     import torch
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork

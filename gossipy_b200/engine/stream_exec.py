@@ -85,7 +85,7 @@ class StreamExec:
             Hd = 0
         self.ex = self.C.StreamExecutor(len(ids), 0 if fam == "mlp1" else 1, IN, Hd, OUT, self.bs, self.epochs,
                                         self.lr, self.wd, _rng.base_seed(), self.cuda)
-        self.slots = torch.zeros(max(16, 4 * len(ids)), self.row_numel, dtype=torch.float32, device=self.device)
+        self.slots = torch.zeros(max(32, 6 * len(ids)), self.row_numel, dtype=torch.float32, device=self.device)
         self._publish_slots()
         if not self.cuda:
             self.ex.set_callbacks(self._cb_snapshot, self._cb_train)

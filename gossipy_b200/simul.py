@@ -538,7 +538,7 @@ class GossipSimulator(SimulationEventSender):
         self.notify_end()
 
     batched = True    # native engine: execute bankable set-ups (linear learners) many nodes per launch
-    native_executor = True    # native engine: enqueue eligible set-ups from C++ (engine/stream_exec.py)
+    native_executor = False   # native engine: enqueue eligible set-ups from C++ (engine/stream_exec.py); opt-in
 
     def _run_native_streamed(self, sch, n_rounds: int) -> None:
         """Rounds of an eligible simulation (``engine.stream_exec.eligible``): the scheduler's event list
