@@ -2,13 +2,14 @@
 // streams WITHOUT going back to Python per event.
 //
 // The reference walks Python objects for every message (gossipy/simul.py:389-451 -> node.py:171-204 ->
-// handler.py:117-136).  For the common set-up -- plain GossipNode, TorchModelHandler whose local update
-// is one fused kernel (1-hidden-layer MLP / logistic regression, SGD, cross-entropy), MERGE_UPDATE --
-// everything an event needs is a handful of integers and device pointers, so the whole round is
-// enqueued from C++:
+// handler.py:117-136).  For the common set-up -- plain GossipNode, TorchModelHandler / LimitedMergeTMH
+// whose local update is one fused kernel (1-hidden-layer MLP / logistic regression, SGD, cross-entropy),
+// modes MERGE_UPDATE / UPDATE / PASS -- everything an event needs is a handful of integers and device
+// pointers, so the whole round is enqueued from C++:
 //
 //   SEND / REPLY_SEND  snapshot kernel  slot <- sender's row            on the SENDER's stream
-//   DELIVER / REPLY    fused merge + local-update kernel (reads slot)   on the RECEIVER's stream
+//   DELIVER / REPLY    MERGE_UPDATE: fused merge + local-update kernel (reads the slot)
+//                      UPDATE: adopt (copy) + local-update kernel;  PASS: adopt     on the RECEIVER's stream
 //
 // with two CUDA events per snapshot slot ordering the streams (slot written -> reader may start; slot
 // read -> slot may be overwritten).  Disjoint node pairs therefore overlap on the device, and the host
@@ -69,11 +70,14 @@ void cuda_check(cudaError_t e, const char* what) {
 class StreamExecutor {
 public:
     // family 0 = mlp1 (dims IN, H, OUT), 1 = logreg (dims IN, OUT; H ignored)
+    // mode: CreateModelMode value (1 UPDATE, 2 MERGE_UPDATE, 4 PASS); limited_merge >= 0 selects the age-limited
+    // merge weights of LimitedMergeTMH with that threshold, -1 the uniform 0.5 / 0.5 merge
     StreamExecutor(int n_nodes, int family, int IN, int H, int OUT, int batch_size, int epochs, double lr, double wd,
-                   uint64_t base_seed, bool use_cuda)
+                   uint64_t base_seed, bool use_cuda, int mode, int64_t limited_merge)
         : nodes_(n_nodes), family_(family), IN_(IN), H_(H), OUT_(OUT), B_(batch_size), epochs_(epochs),
-          lr_((float)lr), wd_((float)wd), seed_(base_seed), cuda_(use_cuda) {
+          lr_((float)lr), wd_((float)wd), seed_(base_seed), cuda_(use_cuda), mode_(mode), L_(limited_merge) {
         if (n_nodes <= 0) throw std::invalid_argument("n_nodes must be positive");
+        if (mode != 1 && mode != 2 && mode != 4) throw std::invalid_argument("mode must be UPDATE, MERGE_UPDATE or PASS");
     }
     ~StreamExecutor() {
         for (Slot& s : slots_) {
@@ -98,7 +102,9 @@ public:
         slot_base_ = reinterpret_cast<float*>(base); stride_ = stride_floats; row_floats_ = row_floats;
         for (int s = (int)slots_.size(); s < cap; ++s) { slots_.emplace_back(); free_.push_back(s); }
     }
-    void set_callbacks(py::function snapshot, py::function train) { cb_snapshot_ = snapshot; cb_train_ = train; }
+    void set_callbacks(py::function snapshot, py::function train, py::function adopt) {
+        cb_snapshot_ = snapshot; cb_train_ = train; cb_adopt_ = adopt;
+    }
     int slots_needed() const { return (int)slots_.size(); }
     int free_slots() const { return (int)free_.size(); }
 
@@ -199,43 +205,72 @@ private:
         return true;
     }
 
-    void consume(int node, int32_t msg_id) {               // MERGE_UPDATE: 0.5 / 0.5 merge folded into the local update
+    void merge_weights(int64_t a, int64_t b, float& ws, float& wp) const {   // model/handler.py: _fused_merge_weights
+        if (L_ < 0) { ws = 0.5f; wp = 0.5f; return; }
+        if (a > b + L_) { ws = 1.f; wp = 0.f; return; }
+        if (b > a + L_) { ws = 0.f; wp = 1.f; return; }
+        const int64_t tot = a + b;
+        if (tot == 0) { ws = 0.5f; wp = 0.5f; return; }
+        ws = (float)((double)a / (double)tot); wp = (float)((double)b / (double)tot);
+    }
+
+    void train(int node, Node& nd, const float* peer, float ws, float wp, uint64_t key) {
+        bool ok;
+        const char* why = "";
+        if (family_ == 0) {
+            TrainParams p{};
+            p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.H = H_; p.OUT = OUT_;
+            p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
+            if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; }
+            ok = launch_mlp1_train(p, kTrainAuto, nd.stream, &why);
+        } else {
+            LogregParams p{};
+            p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.OUT = OUT_;
+            p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
+            if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; }
+            ok = launch_logreg_train(p, nd.stream);
+        }
+        if (!ok) throw std::runtime_error(std::string("training kernel rejected the shape: ") + why);
+        (void)node;
+    }
+
+    void consume(int node, int32_t msg_id) {
         auto it = inflight_.find(msg_id);
         if (it == inflight_.end()) throw std::runtime_error("delivery of an unknown message");
         const int s = it->second;
         inflight_.erase(it);
         Node& nd = nodes_.at(node);
         Slot& sl = slots_[s];
-        nd.age = std::max(nd.age, sl.age);
-        nd.counter += 1;
-        const uint64_t key = key_of(node, nd);
-        if (cuda_) {
-            cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
-            bool ok;
-            const char* why = "";
-            if (family_ == 0) {
-                TrainParams p{};
-                p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.H = H_; p.OUT = OUT_;
-                p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
-                p.peer = slot_ptr(s); p.w_self = 0.5f; p.w_peer = 0.5f;
-                ok = launch_mlp1_train(p, kTrainAuto, nd.stream, &why);
-            } else {
-                LogregParams p{};
-                p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.OUT = OUT_;
-                p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
-                p.peer = slot_ptr(s); p.w_self = 0.5f; p.w_peer = 0.5f;
-                ok = launch_logreg_train(p, nd.stream);
+        if (cuda_) cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
+        if (mode_ == 4) {                                  // PASS: adopt the received model, age unchanged
+            if (cuda_) launch_merge_pair(nd.row, slot_ptr(s), 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr}, nd.stream);
+            else cb_adopt_(node, s);
+            ++launches_;
+        } else {
+            float ws = 0.f, wp = 1.f;
+            const bool fused_merge = mode_ == 2;           // MERGE_UPDATE: the merge rides on the training kernel
+            if (fused_merge) {
+                merge_weights(nd.age, sl.age, ws, wp);
+                nd.age = std::max(nd.age, sl.age);
+            } else {                                       // UPDATE: adopt (a true copy: heals a diverged model), then train
+                if (cuda_) launch_merge_pair(nd.row, slot_ptr(s), 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr}, nd.stream);
+                else cb_adopt_(node, s);
+                ++launches_;
+                nd.age = sl.age;
             }
-            if (!ok) throw std::runtime_error(std::string("training kernel rejected the shape: ") + why);
+            nd.counter += 1;
+            const uint64_t key = key_of(node, nd);
+            if (cuda_) train(node, nd, fused_merge ? slot_ptr(s) : nullptr, ws, wp, key);
+            else cb_train_(node, fused_merge ? s : -1, (int64_t)key, ws, wp);
+            ++launches_;
+            nd.age += steps_of(nd);
+        }
+        if (cuda_) {
             if (!sl.read) cuda_check(cudaEventCreateWithFlags(&sl.read, cudaEventDisableTiming), "event");
             cuda_check(cudaEventRecord(sl.read, nd.stream), "record slot read");
             sl.has_reader = true;
-            cuda_check(cudaGetLastError(), "training launch");
-        } else {
-            cb_train_(node, s, (int64_t)key);
+            cuda_check(cudaGetLastError(), "consume launch");
         }
-        ++launches_;
-        nd.age += steps_of(nd);
         free_.push_back(s);
     }
 
@@ -244,19 +279,21 @@ private:
     float lr_, wd_;
     uint64_t seed_;
     bool cuda_;
+    int mode_; int64_t L_;
     float* slot_base_ = nullptr; int64_t stride_ = 0, row_floats_ = 0;
     std::vector<Slot> slots_;
     std::deque<int> free_;     // FIFO: a slot is reused as late as possible (see snapshot())
     std::unordered_map<int32_t, int> inflight_;
-    py::function cb_snapshot_, cb_train_;
+    py::function cb_snapshot_, cb_train_, cb_adopt_;
     int64_t launches_ = 0, resume_at_ = -1;
 };
 
 void bind_executor(py::module_& m) {
     py::class_<StreamExecutor>(m, "StreamExecutor", "Native executor of a round's event list (csrc/exec/executor.cpp)")
-        .def(py::init<int, int, int, int, int, int, int, double, double, uint64_t, bool>(), py::arg("n_nodes"),
+        .def(py::init<int, int, int, int, int, int, int, double, double, uint64_t, bool, int, int64_t>(), py::arg("n_nodes"),
              py::arg("family"), py::arg("IN"), py::arg("H"), py::arg("OUT"), py::arg("batch_size"), py::arg("epochs"),
-             py::arg("lr"), py::arg("wd"), py::arg("base_seed"), py::arg("use_cuda"))
+             py::arg("lr"), py::arg("wd"), py::arg("base_seed"), py::arg("use_cuda"), py::arg("mode") = 2,
+             py::arg("limited_merge") = -1)
         .def("set_node", &StreamExecutor::set_node)
         .def("set_node_data", &StreamExecutor::set_node_data)
         .def("set_slots", &StreamExecutor::set_slots)

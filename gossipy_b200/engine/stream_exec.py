@@ -1,10 +1,12 @@
 """Glue of the native executor (``csrc/exec/executor.cpp``): a round's event list is enqueued from C++.
 
-Eligible simulations (``eligible`` returns ``None``): a plain :class:`GossipSimulator` of plain
-:class:`GossipNode` s whose handlers are :class:`TorchModelHandler` s on the fused kernel path (1-hidden-
-layer ReLU MLP or logistic regression, momentum-free SGD, mean cross-entropy), ``MERGE_UPDATE``, identical
-hyper-parameters on all nodes, one rank.  That is the reference's ``main_hegedus_2021`` shape and the
-headline benchmark.  Everything else keeps the per-event Python executor (or the bank for linear learners).
+Eligible simulations (``eligible`` returns ``None``): a :class:`GossipSimulator` or
+:class:`TokenizedGossipSimulator` of plain :class:`GossipNode` s whose handlers are
+:class:`TorchModelHandler` s / :class:`LimitedMergeTMH` s on the fused kernel path (1-hidden-layer ReLU MLP
+or logistic regression, momentum-free SGD, mean cross-entropy), mode ``MERGE_UPDATE`` / ``UPDATE`` /
+``PASS``, identical hyper-parameters on all nodes, one rank.  That covers the headline benchmark and the
+reference's MLP / logistic-regression scripts.  Everything else keeps the per-event Python executor (or the
+bank for linear learners).
 
 Python owns all memory -- the handlers' arena rows, ONE tensor of snapshot slots, the nodes' torch streams
 (so evaluation, which stays in Python, is ordered after the native launches on the same streams) -- and
@@ -29,7 +31,7 @@ def eligible(sim: Any) -> Optional[str]:
     from ..model import handler as H
     from ..node import GossipNode
     from ..parallel import runtime as prt
-    if type(sim).__name__ != "GossipSimulator":
+    if type(sim).__name__ not in ("GossipSimulator", "TokenizedGossipSimulator"):
         return "simulator variant"
     if prt.active():
         return "several ranks"
@@ -44,14 +46,17 @@ def eligible(sim: Any) -> Optional[str]:
         h = node.model_handler
         if type(node) is not GossipNode:
             return "node class %s" % type(node).__name__
-        if type(h) is not H.TorchModelHandler:
+        if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH):
             return "handler class %s" % type(h).__name__
-        if not h._fused or h.mode != CreateModelMode.MERGE_UPDATE or h.layout.int_buffers:
-            return "handler is not on the fused MERGE_UPDATE path"
+        if not h._fused or h.layout.int_buffers:
+            return "handler is not on the fused kernel path"
+        if h.mode not in (CreateModelMode.MERGE_UPDATE, CreateModelMode.UPDATE, CreateModelMode.PASS):
+            return "mode %s" % h.mode.name
         if not isinstance(h.n_updates, (int, np.integer)):
             return "vector-valued model age"
         sig = (h._family, h.batch_size, h.local_epochs, float(h.optimizer_params.get("lr", 1e-3)),
-               float(h.optimizer_params.get("weight_decay", 0.0)), h._row_numel)
+               float(h.optimizer_params.get("weight_decay", 0.0)), h._row_numel, type(h), h.mode,
+               getattr(h, "L", None))
         if ref is None:
             ref = sig
         elif sig != ref:
@@ -83,12 +88,13 @@ class StreamExec:
         else:
             IN, OUT = self.dims[0], self.dims[-1]
             Hd = 0
+        limited = int(h0.L) if hasattr(h0, "L") else -1          # LimitedMergeTMH: age-limited merge weights
         self.ex = self.C.StreamExecutor(len(ids), 0 if fam == "mlp1" else 1, IN, Hd, OUT, self.bs, self.epochs,
-                                        self.lr, self.wd, _rng.base_seed(), self.cuda)
+                                        self.lr, self.wd, _rng.base_seed(), self.cuda, int(h0.mode.value), limited)
         self.slots = torch.zeros(max(32, 6 * len(ids)), self.row_numel, dtype=torch.float32, device=self.device)
         self._publish_slots()
         if not self.cuda:
-            self.ex.set_callbacks(self._cb_snapshot, self._cb_train)
+            self.ex.set_callbacks(self._cb_snapshot, self._cb_train, self._cb_adopt)
         self._data: Dict[int, Any] = {}
         self.bind_nodes()
 
@@ -139,12 +145,15 @@ class StreamExec:
     def _cb_snapshot(self, node: int, slot: int) -> None:
         self.slots[slot].copy_(self.sim.nodes[node].model_handler.row)
 
-    def _cb_train(self, node: int, slot: int, key: int) -> None:
+    def _cb_adopt(self, node: int, slot: int) -> None:
+        self.sim.nodes[node].model_handler.row.copy_(self.slots[slot])
+
+    def _cb_train(self, node: int, slot: int, key: int, w_self: float, w_peer: float) -> None:
         h = self.sim.nodes[node].model_handler
         x, y = self._data[node]
         fn = ops.mlp1_train if self.family == "mlp1" else ops.logreg_train
-        fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key), None,
-           merge_from=(self.slots[slot], 0.5, 0.5, None))
+        merge = None if slot < 0 else (self.slots[slot], float(w_self), float(w_peer), None)
+        fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key), None, merge_from=merge)
 
     # -- one round -------------------------------------------------------------------------------------------
     def run_round(self, events: np.ndarray) -> List[int]:

@@ -484,7 +484,7 @@ class GossipSimulator(SimulationEventSender):
             if why is None:
                 self._run_native_banked(sch, n_rounds, C)
                 return
-        if self.native_executor and type(self) is GossipSimulator:
+        if self.native_executor and type(self) in (GossipSimulator, TokenizedGossipSimulator):
             from .engine import stream_exec as _sx
             if _sx.eligible(self) is None:
                 self._run_native_streamed(sch, n_rounds)

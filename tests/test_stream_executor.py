@@ -11,12 +11,16 @@ from gossipy_b200.ops.native import native_available
 pytestmark = pytest.mark.skipif(not native_available(), reason="extension not built")
 
 
-def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=4, device="cpu", sync=True, start=True):
+def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=4, device="cpu", sync=True, start=True,
+         mode="MERGE_UPDATE", limited=None, tokenized=False):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork, UniformDelay
     from gossipy_b200.data import DataDispatcher, synthetic
     from gossipy_b200.data.handler import ClassificationDataHandler
-    from gossipy_b200.model.handler import TorchModelHandler
+    from gossipy_b200.core import CreateModelMode
+    from gossipy_b200.flow_control import RandomizedTokenAccount
+    from gossipy_b200.model.handler import LimitedMergeTMH, TorchModelHandler
+    from gossipy_b200.simul import TokenizedGossipSimulator
     from gossipy_b200.model.nn import LogisticRegression, TorchMLP
     from gossipy_b200.node import GossipNode
     from gossipy_b200.simul import GossipSimulator, SimulationReport
@@ -30,11 +34,20 @@ def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=
         (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(50 * n + 3, 150)
         net, bs = LogisticRegression(57, 2), 16
     disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
-    proto = TorchModelHandler(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(),
-                              batch_size=bs)
+    kwh = dict(batch_size=bs, create_model_mode=getattr(CreateModelMode, mode))
+    if limited is not None:
+        proto = LimitedMergeTMH(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(),
+                                age_diff_threshold=limited, **kwh)
+    else:
+        proto = TorchModelHandler(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), **kwh)
     nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, sync)
     kw = dict(drop_prob=.15, online_prob=.8, delay=UniformDelay(0, 4), sampling_eval=.5) if faults else {}
-    sim = GossipSimulator(nodes, disp, 10, getattr(AntiEntropyProtocol, protocol), **kw)
+    if tokenized:
+        sim = TokenizedGossipSimulator(nodes, disp, RandomizedTokenAccount(C=4, A=2), lambda a, b, m: 1, 10,
+                                       getattr(AntiEntropyProtocol, protocol), **kw)
+        sim.native_utility = 1
+    else:
+        sim = GossipSimulator(nodes, disp, 10, getattr(AntiEntropyProtocol, protocol), **kw)
     sim.progress = False
     sim.engine = "native"
     sim.native_executor = streamed
@@ -83,6 +96,19 @@ def test_native_executor_equals_python_executor(model, protocol, faults, sync):
     g.CACHE.clear()
 
 
+@pytest.mark.parametrize("kw", [dict(mode="UPDATE", protocol="PUSH"), dict(mode="PASS", protocol="PUSH_PULL", faults=True),
+                                dict(limited=20, protocol="PULL", faults=True), dict(limited=0, protocol="PUSH_PULL"),
+                                dict(tokenized=True, protocol="PUSH", faults=True), dict(mode="UPDATE", model="mlp", faults=True)])
+def test_native_executor_modes_and_variants(kw):
+    import gossipy_b200 as g
+    kw = dict(dict(model="logreg", sync=False), **kw)
+    sim_a, rep_a = _sim(False, **kw)
+    sim_b, rep_b = _sim(True, **kw)
+    assert "_stream_exec" in sim_b.__dict__ and "_stream_exec" not in sim_a.__dict__
+    _same(sim_a, rep_a, sim_b, rep_b)
+    g.CACHE.clear()
+
+
 def test_slot_pool_grows_and_resume_is_exact(tmp_path):
     import gossipy_b200 as g
     from gossipy_b200.simul import GossipSimulator
@@ -113,7 +139,10 @@ def test_eligibility():
     from gossipy_b200.core import CreateModelMode
     sim, _ = _sim(True, start=False)
     assert eligible(sim) is None
-    sim.nodes[2].model_handler.mode = CreateModelMode.UPDATE
+    sim.nodes[2].model_handler.mode = CreateModelMode.UPDATE        # nodes must agree
+    assert eligible(sim) is not None
+    for nd in sim.nodes.values():
+        nd.model_handler.mode = CreateModelMode.UPDATE_MERGE
     assert eligible(sim) is not None
     sim.start(1)                                   # falls back to the per-event executor
     assert "_stream_exec" not in sim.__dict__
@@ -124,10 +153,11 @@ def test_executor_runs_out_of_slots_gracefully():
     from gossipy_b200.ops.native import _try_import
     C = _try_import()
     log = []
-    ex = C.StreamExecutor(3, 1, 4, 0, 2, 2, 1, .1, 0., 5, False)
+    ex = C.StreamExecutor(3, 1, 4, 0, 2, 2, 1, .1, 0., 5, False, 2, -1)
     for i in range(3):
         ex.set_node(i, 0, 0, 0, 6, 10 * i, 0, 0)
-    ex.set_callbacks(lambda n, s: log.append(("snap", n, s)), lambda n, s, k: log.append(("train", n, s)))
+    ex.set_callbacks(lambda n, s: log.append(("snap", n, s)), lambda n, s, k, ws, wp: log.append(("train", n, s)),
+                     lambda n, s: log.append(("adopt", n, s)))
     ex.set_slots(0, 1, 8, 8)
     ev = np.array([[C.EV_SEND, 0, 0, 1, 100, 1], [C.EV_SEND, 0, 2, 1, 101, 1], [C.EV_DELIVER, 0, 0, 1, 100, 1],
                    [C.EV_DELIVER, 0, 2, 1, 101, 1], [C.EV_EVAL, 0, 1, -1, -1, 0]], dtype=np.int32)
