@@ -241,7 +241,8 @@ private:
         inflight_.erase(it);
         Node& nd = nodes_.at(node);
         Slot& sl = slots_[s];
-        if (cuda_) cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
+        if (cuda_ && sl.written)                           // (a slot restored from a checkpoint has no writer event)
+            cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
         if (mode_ == 4) {                                  // PASS: adopt the received model, age unchanged
             if (cuda_) launch_merge_pair(nd.row, slot_ptr(s), 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr}, nd.stream);
             else cb_adopt_(node, s);

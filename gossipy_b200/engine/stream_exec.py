@@ -198,4 +198,6 @@ class StreamExec:
         taken = {int(r[1]) for r in self.ex.inflight()}
         free = [s for s in range(int(self.slots.shape[0])) if s not in taken][:n]
         self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = st["rows"].to(self.device)
+        if self.cuda:
+            torch.cuda.synchronize(self.device)     # the node streams read these slots without a writer event
         self.ex.import_inflight([[int(m), int(s), int(a)] for m, s, a in zip(st["ids"], free, st["ages"])])
