@@ -6,7 +6,8 @@ There is no network on the target boxes, so the data sets are the shape-compatib
 of :mod:`gossipy_b200.data.synthetic` (``load_*`` fall back to them automatically).
 
 Environment: ``GOSSIPY_ROUNDS`` (override the number of rounds), ``GOSSIPY_NODES`` (cap the number
-of nodes), ``GOSSIPY_ENGINE=native|python`` (round-loop control plane), ``GOSSIPY_DEVICE``.
+of nodes), ``GOSSIPY_ENGINE=native|python`` (round-loop control plane), ``GOSSIPY_EXECUTOR=native``
+(with the native engine: enqueue eligible simulations from the C++ executor), ``GOSSIPY_DEVICE``.
 Multi-GPU: launch with ``python -m torch.distributed.run --nproc-per-node N examples/<script>.py``.
 """
 import os
@@ -50,6 +51,7 @@ def cap_nodes(n: int) -> int:
 
 def configure(sim):
     sim.engine = os.environ.get("GOSSIPY_ENGINE", "python")
+    sim.native_executor = os.environ.get("GOSSIPY_EXECUTOR", "python") == "native"
     sim.progress = os.environ.get("GOSSIPY_PROGRESS", "0") == "1"
     return sim
 

@@ -36,3 +36,14 @@ def test_all2all_synchronous_rounds_and_pens():
     out = _run("main_all2all.py", GOSSIPY_SYNC=1, GOSSIPY_NODES=4)
     assert "sent=36" in out                     # 3 rounds x 4 nodes x 3 peers
     _run("main_onoszko_2021.py", GOSSIPY_NODES=4)
+
+
+def test_danner_script_with_the_cpp_executor():
+    """main_danner_2023 (LimitedMergeTMH, churn, delays) is eligible for csrc/exec."""
+    from gossipy_b200.ops.native import native_available
+    if not native_available():
+        pytest.skip("extension not built")
+    a = _run("main_danner_2023.py", GOSSIPY_ENGINE="native", GOSSIPY_EXECUTOR="native")
+    b = _run("main_danner_2023.py", GOSSIPY_ENGINE="native")
+    assert [l for l in a.splitlines() if l.startswith("last evaluation")] == \
+        [l for l in b.splitlines() if l.startswith("last evaluation")]
