@@ -478,7 +478,9 @@ class GossipSimulator(SimulationEventSender):
                 sch.clock = int(self._clock)
             else:
                 self._clock = 0
-        if self.batched and type(self) is GossipSimulator:
+        use_bank = self.batched is True or (self.batched == "auto" and (
+            GlobalSettings().get_device().type == "cuda" or self.n_nodes >= 512))
+        if use_bank and type(self) is GossipSimulator:
             from .engine import bank as _bank
             why = _bank.bankable(self)
             if why is None:
@@ -537,7 +539,9 @@ class GossipSimulator(SimulationEventSender):
             prev_finish()
         self.notify_end()
 
-    batched = True    # native engine: execute bankable set-ups (linear learners) many nodes per launch
+    # native engine: execute bankable set-ups (linear learners) many nodes per launch.  "auto" = on a GPU, or from
+    # 512 nodes on the CPU (where the bank's vectorised-over-nodes update loses to per-node calls for a few big shards)
+    batched: Any = "auto"
     native_executor = False   # native engine: enqueue eligible set-ups from C++ (engine/stream_exec.py); opt-in
 
     def _run_native_streamed(self, sch, n_rounds: int) -> None:
