@@ -42,7 +42,8 @@ configs = st.tuples(
     st.sampled_from(["clique", "ring", "sparse"]))
 
 
-@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=int(__import__("os").environ.get("SCHED_EXAMPLES", "60")), deadline=None, derandomize=True,
+          suppress_health_check=[HealthCheck.too_slow], database=None)
 @given(cfg=configs, rounds=st.integers(1, 6), cut=st.integers(0, 5))
 def test_event_stream_is_a_valid_history(cfg, rounds, cut):
     from gossipy_b200.ops.native import _try_import
