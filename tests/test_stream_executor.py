@@ -179,3 +179,29 @@ def test_native_executor_cuda_equals_python_executor():
         _same(sim_a, rep_a, sim_b, rep_b, tol=1e-6)
         g.CACHE.clear()
     g.GlobalSettings().set_device("cpu")
+
+
+def test_native_executor_equals_python_executor_random_setups():
+    """Derandomised sweep over protocol x mode x faults x clocks x merge rule (hypothesis); EXEC_EXAMPLES to stress."""
+    import os
+    import gossipy_b200 as g
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=int(os.environ.get("EXEC_EXAMPLES", "12")), deadline=None, derandomize=True, database=None,
+              suppress_health_check=list(HealthCheck))
+    @given(protocol=st.sampled_from(["PUSH", "PULL", "PUSH_PULL"]), mode=st.sampled_from(["MERGE_UPDATE", "UPDATE", "PASS"]),
+           faults=st.booleans(), sync=st.booleans(), limited=st.sampled_from([None, 0, 3, 50]), tokenized=st.booleans(),
+           n=st.integers(2, 9), rounds=st.integers(1, 4))
+    def check(protocol, mode, faults, sync, limited, tokenized, n, rounds):
+        kw = dict(model="logreg", protocol=protocol, mode=mode, faults=faults, sync=sync, limited=limited,
+                  tokenized=tokenized, n=n, rounds=rounds)
+        sim_a, rep_a = _sim(False, **kw)
+        sim_b, rep_b = _sim(True, **kw)
+        assert "_stream_exec" in sim_b.__dict__
+        ra, aa, ca = _state(sim_a)
+        rb, ab, cb = _state(sim_b)
+        assert aa == ab and ca == cb and torch.equal(ra, rb)
+        assert (rep_a._sent_messages, rep_a._failed_messages, rep_a._total_size) == \
+            (rep_b._sent_messages, rep_b._failed_messages, rep_b._total_size)
+        g.CACHE.clear()
+    check()
