@@ -33,6 +33,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../kernels/kernels.h"
@@ -59,7 +60,13 @@ struct Node {
     int n = 0; int64_t age = 0, counter = 0; cudaStream_t stream = nullptr;
 };
 
-struct Slot { int64_t age = 0; cudaEvent_t written = nullptr, read = nullptr; bool has_reader = false; };
+struct Slot {
+    int64_t age = 0;
+    cudaEvent_t written = nullptr, read = nullptr; bool has_reader = false;      // same-rank ordering
+    float* data = nullptr;                                                        // peer-mapped when the slot lives on another rank
+    uint32_t* ready = nullptr; uint32_t* done = nullptr;                          // cross-rank handshake words (owner's memory)
+    uint32_t gen = 0, remote_reads = 0, acked = 0;                                // replicated bookkeeping of the handshake
+};
 
 void cuda_check(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
@@ -67,6 +74,11 @@ void cuda_check(cudaError_t e, const char* what) {
 
 }  // namespace
 
+// Several ranks (one process per GPU): every rank runs this executor over the SAME event list and keeps
+// the same books (ages, counters, slot allocation, generations), but launches only the work of the nodes it
+// owns.  A rank's snapshot slots live in its symmetric arena (engine/arena.py), mapped into every peer; a
+// reader on another rank gets the slot's `ready` / `done` words as a PeerSync, i.e. the training kernel
+// itself waits for the snapshot and acknowledges the read over NVLink (kernels/common.cuh).
 class StreamExecutor {
 public:
     // family 0 = mlp1 (dims IN, H, OUT), 1 = logreg (dims IN, OUT; H ignored)
@@ -74,18 +86,26 @@ public:
     // merge weights of LimitedMergeTMH with that threshold, -1 the uniform 0.5 / 0.5 merge
     StreamExecutor(int n_nodes, int family, int IN, int H, int OUT, int batch_size, int epochs, double lr, double wd,
                    uint64_t base_seed, bool use_cuda, int mode, int64_t limited_merge)
-        : nodes_(n_nodes), family_(family), IN_(IN), H_(H), OUT_(OUT), B_(batch_size), epochs_(epochs),
-          lr_((float)lr), wd_((float)wd), seed_(base_seed), cuda_(use_cuda), mode_(mode), L_(limited_merge) {
+        : nodes_(n_nodes), owner_(n_nodes, 0), family_(family), IN_(IN), H_(H), OUT_(OUT), B_(batch_size), epochs_(epochs),
+          lr_((float)lr), wd_((float)wd), seed_(base_seed), cuda_(use_cuda), mode_(mode), L_(limited_merge),
+          pools_(1), free_(1) {
         if (n_nodes <= 0) throw std::invalid_argument("n_nodes must be positive");
         if (mode != 1 && mode != 2 && mode != 4) throw std::invalid_argument("mode must be UPDATE, MERGE_UPDATE or PASS");
     }
     ~StreamExecutor() {
-        for (Slot& s : slots_) {
-            if (s.written) cudaEventDestroy(s.written);
-            if (s.read) cudaEventDestroy(s.read);
-        }
+        for (auto& pool : pools_)
+            for (Slot& s : pool) {
+                if (s.written) cudaEventDestroy(s.written);
+                if (s.read) cudaEventDestroy(s.read);
+            }
     }
 
+    void set_ranks(int my_rank, int world, const std::vector<int>& owner) {
+        if ((int)owner.size() != (int)nodes_.size() || my_rank < 0 || my_rank >= world)
+            throw std::invalid_argument("one owner rank per node expected");
+        rank_ = my_rank; world_ = world; owner_ = owner;
+        pools_.resize(world); free_.resize(world);
+    }
     void set_node(int i, uintptr_t row, uintptr_t X, uintptr_t y, int n, int64_t age, int64_t counter, uintptr_t stream) {
         Node& nd = nodes_.at(i);
         nd.row = reinterpret_cast<float*>(row); nd.X = reinterpret_cast<const float*>(X);
@@ -96,21 +116,36 @@ public:
         Node& nd = nodes_.at(i);
         nd.X = reinterpret_cast<const float*>(X); nd.y = reinterpret_cast<const int64_t*>(y); nd.n = n;
     }
-    // the snapshot slots: one [cap, stride] fp32 tensor owned by Python; growing keeps the old contents (Python copies)
+    // one rank: the snapshot slots are one [cap, stride] fp32 tensor owned by Python; growing keeps the contents (Python copies)
     void set_slots(uintptr_t base, int cap, int64_t stride_floats, int64_t row_floats) {
-        if (cap < (int)slots_.size()) throw std::invalid_argument("the slot pool cannot shrink");
-        slot_base_ = reinterpret_cast<float*>(base); stride_ = stride_floats; row_floats_ = row_floats;
-        for (int s = (int)slots_.size(); s < cap; ++s) { slots_.emplace_back(); free_.push_back(s); }
+        auto& pool = pools_.at(0);
+        if (cap < (int)pool.size()) throw std::invalid_argument("the slot pool cannot shrink");
+        row_floats_ = row_floats;
+        for (int s = (int)pool.size(); s < cap; ++s) { pool.emplace_back(); free_[0].push_back(s); }
+        for (int s = 0; s < cap; ++s) pool[s].data = reinterpret_cast<float*>(base) + (size_t)s * stride_floats;
+    }
+    // several ranks: slot k of `rank`'s pool = a row of that rank's symmetric arena + its two flag words
+    // (gen / remote_reads / acked continue the row's history: arena rows are recycled)
+    int add_slot(int rank, uintptr_t data, uintptr_t ready, uintptr_t done, int64_t row_floats, uint32_t gen,
+                 uint32_t remote_reads, uint32_t acked) {
+        auto& pool = pools_.at(rank);
+        Slot sl;
+        sl.data = reinterpret_cast<float*>(data); sl.ready = reinterpret_cast<uint32_t*>(ready);
+        sl.done = reinterpret_cast<uint32_t*>(done);
+        sl.gen = gen; sl.remote_reads = remote_reads; sl.acked = acked;
+        pool.push_back(sl);
+        free_[rank].push_back((int)pool.size() - 1);
+        row_floats_ = row_floats;
+        return (int)pool.size() - 1;
     }
     void set_callbacks(py::function snapshot, py::function train, py::function adopt) {
         cb_snapshot_ = snapshot; cb_train_ = train; cb_adopt_ = adopt;
     }
-    int slots_needed() const { return (int)slots_.size(); }
-    int free_slots() const { return (int)free_.size(); }
+    int free_slots() const { return (int)free_[world_ > 1 ? rank_ : 0].size(); }
 
-    // Executes one round's events [n, 6] = (kind, tick, a, b, slot, aux).  Returns the nodes to evaluate.
-    // Raises if the pool runs out of slots: the caller grows it (set_slots) and calls again with `start`
-    // = the index reported in the exception state (`resume_at`).
+    // Executes one round's events [n, 6] = (kind, tick, a, b, slot, aux) from index `start`.  Returns the nodes to
+    // evaluate.  When a pool runs out of slots it stops at that event (`resume_at` >= 0): the caller grows the pool
+    // (one rank: set_slots) and calls again with `start = resume_at`.
     std::vector<int> run(py::array_t<int32_t, py::array::c_style | py::array::forcecast> events, int64_t start) {
         const auto ev = events.unchecked<2>();
         std::vector<int> evals;
@@ -126,7 +161,7 @@ public:
                     break;
                 case EV_DROP: {
                     auto it = inflight_.find(id);
-                    if (it != inflight_.end()) { free_.push_back(it->second); inflight_.erase(it); }
+                    if (it != inflight_.end()) { free_[it->second.first].push_back(it->second.second); inflight_.erase(it); }
                     break;
                 }
                 case EV_DELIVER:
@@ -149,26 +184,28 @@ public:
     std::vector<int64_t> ages() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.age); return v; }
     std::vector<int64_t> counters() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.counter); return v; }
     int64_t launches() const { return launches_; }
-    // messages on the wire: (message id, slot, age) -- checkpointing
+    // messages on the wire: (message id, rank, slot, age) -- checkpointing
     std::vector<std::vector<int64_t>> inflight() const {
         std::vector<std::vector<int64_t>> v;
-        for (const auto& kv : inflight_) v.push_back({kv.first, kv.second, slots_[kv.second].age});
+        for (const auto& kv : inflight_)
+            v.push_back({kv.first, kv.second.first, kv.second.second, pools_[kv.second.first][kv.second.second].age});
         std::sort(v.begin(), v.end());
         return v;
     }
     void import_inflight(const std::vector<std::vector<int64_t>>& rows) {     // slots already filled by Python
         for (const auto& r : rows) {
-            const int s = (int)r.at(1);
-            auto it = std::find(free_.begin(), free_.end(), s);
-            if (it == free_.end()) throw std::invalid_argument("slot is not free");
-            free_.erase(it);
-            slots_.at(s).age = r.at(2);
-            inflight_[(int32_t)r.at(0)] = s;
+            const int rk = (int)r.at(1), s = (int)r.at(2);
+            auto& fl = free_.at(rk);
+            auto it = std::find(fl.begin(), fl.end(), s);
+            if (it == fl.end()) throw std::invalid_argument("slot is not free");
+            fl.erase(it);
+            pools_.at(rk).at(s).age = r.at(3);
+            inflight_[(int32_t)r.at(0)] = {rk, s};
         }
     }
 
 private:
-    float* slot_ptr(int s) const { return slot_base_ + (size_t)s * stride_; }
+    bool mine(int node) const { return world_ == 1 || owner_[node] == rank_; }
     int steps_of(const Node& nd) const {
         const int bs = B_ == 0 ? nd.n : std::min(B_, nd.n);
         return epochs_ > 0 ? epochs_ * ((nd.n + bs - 1) / bs) : 1;
@@ -181,27 +218,36 @@ private:
     }
 
     bool snapshot(int node, int32_t msg_id) {
-        if (free_.empty()) return false;
+        const int rk = world_ > 1 ? owner_[node] : 0;
+        auto& fl = free_[rk];
+        if (fl.empty()) return false;
         // oldest free slot first: its last reader is a whole training kernel (~1 ms) on another node's
         // stream, and the WAR wait below would serialise unrelated nodes if a just-freed slot were reused
         // (LIFO reuse measured 74 instead of 190 rounds/s on the headline benchmark)
-        const int s = free_.front(); free_.pop_front();
+        const int s = fl.front(); fl.pop_front();
         Node& nd = nodes_.at(node);
-        Slot& sl = slots_[s];
+        Slot& sl = pools_[rk][s];
         sl.age = nd.age;
-        if (cuda_) {
-            // the slot's previous life: its reader (WAR) and -- for a dropped message nobody read -- its writer (WAW)
-            if (sl.has_reader) cuda_check(cudaStreamWaitEvent(nd.stream, sl.read, 0), "wait for the slot's last reader");
-            if (sl.written) cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the slot's last writer");
-            launch_merge_pair(slot_ptr(s), nd.row, 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr}, nd.stream);
-            if (!sl.written) cuda_check(cudaEventCreateWithFlags(&sl.written, cudaEventDisableTiming), "event");
-            cuda_check(cudaEventRecord(sl.written, nd.stream), "record slot written");
-            cuda_check(cudaGetLastError(), "snapshot launch");
-        } else {
-            cb_snapshot_(node, s);
+        sl.gen += 1;                                      // replicated: every rank knows which generation a reader expects
+        if (mine(node)) {
+            if (cuda_) {
+                // the slot's previous life: its reader (WAR) and -- for a dropped message nobody read -- its writer (WAW);
+                // readers on other ranks acknowledge through the slot's `done` counter
+                if (sl.has_reader) cuda_check(cudaStreamWaitEvent(nd.stream, sl.read, 0), "wait for the slot's last reader");
+                if (sl.written) cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the slot's last writer");
+                if (sl.remote_reads != sl.acked) launch_flag_wait(sl.done, sl.remote_reads, nd.stream);
+                launch_merge_pair(sl.data, nd.row, 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr}, nd.stream);
+                if (!sl.written) cuda_check(cudaEventCreateWithFlags(&sl.written, cudaEventDisableTiming), "event");
+                cuda_check(cudaEventRecord(sl.written, nd.stream), "record slot written");
+                if (world_ > 1) launch_flag_signal(sl.ready, sl.gen, nd.stream);
+                cuda_check(cudaGetLastError(), "snapshot launch");
+            } else {
+                cb_snapshot_(node, rk, s, (int64_t)sl.gen, (int64_t)sl.remote_reads);
+            }
+            ++launches_;
         }
-        ++launches_;
-        inflight_[msg_id] = s;
+        sl.acked = sl.remote_reads;
+        inflight_[msg_id] = {rk, s};
         return true;
     }
 
@@ -214,39 +260,47 @@ private:
         ws = (float)((double)a / (double)tot); wp = (float)((double)b / (double)tot);
     }
 
-    void train(int node, Node& nd, const float* peer, float ws, float wp, uint64_t key) {
+    void train(Node& nd, const float* peer, float ws, float wp, uint64_t key, PeerSync sync) {
         bool ok;
         const char* why = "";
         if (family_ == 0) {
             TrainParams p{};
             p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.H = H_; p.OUT = OUT_;
             p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
-            if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; }
+            if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; p.sync = sync; }
             ok = launch_mlp1_train(p, kTrainAuto, nd.stream, &why);
         } else {
             LogregParams p{};
             p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.OUT = OUT_;
             p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
-            if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; }
+            if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; p.sync = sync; }
             ok = launch_logreg_train(p, nd.stream);
         }
         if (!ok) throw std::runtime_error(std::string("training kernel rejected the shape: ") + why);
-        (void)node;
     }
 
     void consume(int node, int32_t msg_id) {
         auto it = inflight_.find(msg_id);
         if (it == inflight_.end()) throw std::runtime_error("delivery of an unknown message");
-        const int s = it->second;
+        const int rk = it->second.first, s = it->second.second;
         inflight_.erase(it);
         Node& nd = nodes_.at(node);
-        Slot& sl = slots_[s];
-        if (cuda_ && sl.written)                           // (a slot restored from a checkpoint has no writer event)
-            cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
+        Slot& sl = pools_[rk][s];
+        const bool exec = mine(node);
+        const bool remote = world_ > 1 && rk != owner_[node];      // the snapshot lives on another rank than the reader
+        if (remote) sl.remote_reads += 1;                           // replicated: the owner will wait for this many acks
+        PeerSync sync{nullptr, 0, nullptr};
+        if (exec && cuda_) {
+            if (remote) sync = PeerSync{sl.ready, sl.gen, sl.done};
+            else if (sl.written)                                // (a slot restored from a checkpoint has no writer event)
+                cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
+        }
         if (mode_ == 4) {                                  // PASS: adopt the received model, age unchanged
-            if (cuda_) launch_merge_pair(nd.row, slot_ptr(s), 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr}, nd.stream);
-            else cb_adopt_(node, s);
-            ++launches_;
+            if (exec) {
+                if (cuda_) launch_merge_pair(nd.row, sl.data, 0.f, 1.f, 0, row_floats_, sync, nd.stream);
+                else cb_adopt_(node, rk, s, (int64_t)sl.gen);
+                ++launches_;
+            }
         } else {
             float ws = 0.f, wp = 1.f;
             const bool fused_merge = mode_ == 2;           // MERGE_UPDATE: the merge rides on the training kernel
@@ -254,37 +308,43 @@ private:
                 merge_weights(nd.age, sl.age, ws, wp);
                 nd.age = std::max(nd.age, sl.age);
             } else {                                       // UPDATE: adopt (a true copy: heals a diverged model), then train
-                if (cuda_) launch_merge_pair(nd.row, slot_ptr(s), 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr}, nd.stream);
-                else cb_adopt_(node, s);
-                ++launches_;
+                if (exec) {
+                    if (cuda_) launch_merge_pair(nd.row, sl.data, 0.f, 1.f, 0, row_floats_, sync, nd.stream);
+                    else cb_adopt_(node, rk, s, (int64_t)sl.gen);
+                    ++launches_;
+                }
                 nd.age = sl.age;
             }
             nd.counter += 1;
             const uint64_t key = key_of(node, nd);
-            if (cuda_) train(node, nd, fused_merge ? slot_ptr(s) : nullptr, ws, wp, key);
-            else cb_train_(node, fused_merge ? s : -1, (int64_t)key, ws, wp);
-            ++launches_;
+            if (exec) {
+                if (cuda_) train(nd, fused_merge ? sl.data : nullptr, ws, wp, key, sync);
+                else cb_train_(node, rk, fused_merge ? s : -1, (int64_t)key, ws, wp, (int64_t)sl.gen);
+                ++launches_;
+            }
             nd.age += steps_of(nd);
         }
-        if (cuda_) {
+        if (exec && cuda_ && !remote) {
             if (!sl.read) cuda_check(cudaEventCreateWithFlags(&sl.read, cudaEventDisableTiming), "event");
             cuda_check(cudaEventRecord(sl.read, nd.stream), "record slot read");
             sl.has_reader = true;
-            cuda_check(cudaGetLastError(), "consume launch");
         }
-        free_.push_back(s);
+        if (exec && cuda_) cuda_check(cudaGetLastError(), "consume launch");
+        free_[rk].push_back(s);
     }
 
     std::vector<Node> nodes_;
+    std::vector<int> owner_;
     int family_, IN_, H_, OUT_, B_, epochs_;
     float lr_, wd_;
     uint64_t seed_;
     bool cuda_;
     int mode_; int64_t L_;
-    float* slot_base_ = nullptr; int64_t stride_ = 0, row_floats_ = 0;
-    std::vector<Slot> slots_;
-    std::deque<int> free_;     // FIFO: a slot is reused as late as possible (see snapshot())
-    std::unordered_map<int32_t, int> inflight_;
+    int rank_ = 0, world_ = 1;
+    int64_t row_floats_ = 0;
+    std::vector<std::vector<Slot>> pools_;          // per owner rank
+    std::vector<std::deque<int>> free_;             // FIFO: a slot is reused as late as possible (see snapshot())
+    std::unordered_map<int32_t, std::pair<int, int>> inflight_;     // message id -> (rank, slot)
     py::function cb_snapshot_, cb_train_, cb_adopt_;
     int64_t launches_ = 0, resume_at_ = -1;
 };
@@ -295,6 +355,8 @@ void bind_executor(py::module_& m) {
              py::arg("family"), py::arg("IN"), py::arg("H"), py::arg("OUT"), py::arg("batch_size"), py::arg("epochs"),
              py::arg("lr"), py::arg("wd"), py::arg("base_seed"), py::arg("use_cuda"), py::arg("mode") = 2,
              py::arg("limited_merge") = -1)
+        .def("set_ranks", &StreamExecutor::set_ranks)
+        .def("add_slot", &StreamExecutor::add_slot)
         .def("set_node", &StreamExecutor::set_node)
         .def("set_node_data", &StreamExecutor::set_node_data)
         .def("set_slots", &StreamExecutor::set_slots)

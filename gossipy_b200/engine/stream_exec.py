@@ -4,9 +4,14 @@ Eligible simulations (``eligible`` returns ``None``): a :class:`GossipSimulator`
 :class:`TokenizedGossipSimulator` of plain :class:`GossipNode` s whose handlers are
 :class:`TorchModelHandler` s / :class:`LimitedMergeTMH` s on the fused kernel path (1-hidden-layer ReLU MLP
 or logistic regression, momentum-free SGD, mean cross-entropy), mode ``MERGE_UPDATE`` / ``UPDATE`` /
-``PASS``, identical hyper-parameters on all nodes, one rank.  That covers the headline benchmark and the
-reference's MLP / logistic-regression scripts.  Everything else keeps the per-event Python executor (or the
-bank for linear learners).
+``PASS``, identical hyper-parameters on all nodes.  That covers the headline benchmark and the reference's
+MLP / logistic-regression scripts.  Everything else keeps the per-event Python executor (or the bank for
+linear learners).
+
+Several ranks: every rank drives its own executor over the same event list (replicated books), launches
+the work of its own nodes only, and the snapshot slots are rows of the symmetric arenas
+(``engine/arena.py``), so a reader on another GPU hands the slot's ``ready`` / ``done`` words to the
+training kernel exactly like the Python executor does.
 
 Python owns all memory -- the handlers' arena rows, ONE tensor of snapshot slots, the nodes' torch streams
 (so evaluation, which stays in Python, is ordered after the native launches on the same streams) -- and
@@ -33,8 +38,8 @@ def eligible(sim: Any) -> Optional[str]:
     from ..parallel import runtime as prt
     if type(sim).__name__ not in ("GossipSimulator", "TokenizedGossipSimulator"):
         return "simulator variant"
-    if prt.active():
-        return "several ranks"
+    if prt.active() and prt.transport() != "p2p":
+        return "several ranks without shared arenas"
     if not H.FUSE_MERGE_UPDATE:
         return "fused merge+update disabled"
     ids = sorted(sim.nodes)
@@ -91,11 +96,32 @@ class StreamExec:
         limited = int(h0.L) if hasattr(h0, "L") else -1          # LimitedMergeTMH: age-limited merge weights
         self.ex = self.C.StreamExecutor(len(ids), 0 if fam == "mlp1" else 1, IN, Hd, OUT, self.bs, self.epochs,
                                         self.lr, self.wd, _rng.base_seed(), self.cuda, int(h0.mode.value), limited)
-        self.slots = torch.zeros(max(32, 6 * len(ids)), self.row_numel, dtype=torch.float32, device=self.device)
-        self._publish_slots()
+        from ..parallel import runtime as prt
+        self.multi = prt.active()
+        self.rank = prt.rank() if self.multi else 0
+        self._data: Dict[int, Any] = {}
+        if self.multi:
+            self.owner = [int(prt.rank_of(i)) for i in ids]
+            self.ex.set_ranks(self.rank, prt.world(), self.owner)
+            # a rank's slots are rows of ITS symmetric arena (mapped everywhere); every rank performs the same
+            # allocations on every mirror, so (rank, slot) means the same row in all processes
+            per_rank = max(self.owner.count(r) for r in range(prt.world()))
+            k = max(8, 6 * per_rank)
+            self.pool_rows = [[_arena.arena_for(self.device, self.row_numel, r).alloc() for _ in range(k)]
+                              for r in range(prt.world())]
+            for r, rows in enumerate(self.pool_rows):
+                for row in rows:
+                    ready = row.flag_ready if self.cuda else 0
+                    done = row.flag_done if self.cuda else 0
+                    self.ex.add_slot(r, row.tensor.data_ptr(), int(ready), int(done), self.row_numel, int(row.gen),
+                                     int(row.remote_reads), int(getattr(row, "_acked", 0)))
+            self.slots = None
+        else:
+            self.owner = [0] * len(ids)
+            self.slots = torch.zeros(max(32, 6 * len(ids)), self.row_numel, dtype=torch.float32, device=self.device)
+            self._publish_slots()
         if not self.cuda:
             self.ex.set_callbacks(self._cb_snapshot, self._cb_train, self._cb_adopt)
-        self._data: Dict[int, Any] = {}
         self.bind_nodes()
 
     # -- state shared with the handlers ---------------------------------------------------------------
@@ -116,10 +142,16 @@ class StreamExec:
         self._data[i] = (x, y)                  # keeps the tensors alive while C++ holds their addresses
         return x, y
 
+    def _mine(self, i: int) -> bool:
+        return self.owner[i] == self.rank
+
     def bind_nodes(self) -> None:
         """(Re)read rows, data, ages, counters and streams from the handlers (start of every ``start``)."""
         for i, node in self.sim.nodes.items():
             h = node.model_handler
+            if not self._mine(i):      # another rank runs this node: only its sample count and counters matter here
+                self.ex.set_node(i, 0, 0, 0, int(node.data[0][0].shape[0]), int(h.n_updates), int(h._update_counter), 0)
+                continue
             row = h.row
             x, y = self._node_data(i)
             s = h._stream()
@@ -129,8 +161,9 @@ class StreamExec:
     def refresh_data(self) -> None:
         """Streamed inputs: the resident buffers alternate every round."""
         for i in self.sim.nodes:
-            x, y = self._node_data(i)
-            self.ex.set_node_data(i, x.data_ptr(), y.data_ptr(), int(x.shape[0]))
+            if self._mine(i):
+                x, y = self._node_data(i)
+                self.ex.set_node_data(i, x.data_ptr(), y.data_ptr(), int(x.shape[0]))
 
     def sync_back(self) -> None:
         ages, counters = self.ex.ages(), self.ex.counters()
@@ -141,18 +174,42 @@ class StreamExec:
             h.n_updates = int(ages[i])
             h._update_counter = int(counters[i])
 
-    # -- CPU callbacks -----------------------------------------------------------------------------------
-    def _cb_snapshot(self, node: int, slot: int) -> None:
-        self.slots[slot].copy_(self.sim.nodes[node].model_handler.row)
+    # -- CPU callbacks (the same handshakes the kernels perform on a GPU, on the shared-memory flags) ----------
+    def _slot(self, rank: int, slot: int, gen: int):
+        """(tensor, cross-rank handshake or None) of a snapshot slot as seen by THIS rank."""
+        if not self.multi:
+            return self.slots[slot], None
+        row = self.pool_rows[rank][slot]
+        if rank == self.rank:
+            return row.tensor, None
+        done = row.flag_done
+        return row.tensor, ops.RowSync(row.flag_ready, gen, (done[0], done[1] + self.rank))
 
-    def _cb_adopt(self, node: int, slot: int) -> None:
-        self.sim.nodes[node].model_handler.row.copy_(self.slots[slot])
+    def _cb_snapshot(self, node: int, rank: int, slot: int, gen: int, remote_reads: int) -> None:
+        src = self.sim.nodes[node].model_handler.row
+        if not self.multi:
+            self.slots[slot].copy_(src)
+            return
+        row = self.pool_rows[rank][slot]
+        row.remote_reads = remote_reads
+        _arena.wait_remote_readers(row)             # every reader on another rank has acknowledged the slot's last life
+        row.tensor.copy_(src)
+        row.gen = gen
+        arr, i = row.flag_ready
+        arr[i] = gen                                # publish
 
-    def _cb_train(self, node: int, slot: int, key: int, w_self: float, w_peer: float) -> None:
+    def _cb_adopt(self, node: int, rank: int, slot: int, gen: int) -> None:
+        src, sync = self._slot(rank, slot, gen)
+        ops.merge_pair(self.sim.nodes[node].model_handler.row, src, 0.0, 1.0, sync=sync)
+
+    def _cb_train(self, node: int, rank: int, slot: int, key: int, w_self: float, w_peer: float, gen: int) -> None:
         h = self.sim.nodes[node].model_handler
         x, y = self._data[node]
         fn = ops.mlp1_train if self.family == "mlp1" else ops.logreg_train
-        merge = None if slot < 0 else (self.slots[slot], float(w_self), float(w_peer), None)
+        merge = None
+        if slot >= 0:
+            src, sync = self._slot(rank, slot, gen)
+            merge = (src, float(w_self), float(w_peer), sync)
         fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key), None, merge_from=merge)
 
     # -- one round -------------------------------------------------------------------------------------------
@@ -173,6 +230,9 @@ class StreamExec:
         return evals
 
     def _grow(self) -> None:
+        if self.multi:
+            raise RuntimeError("out of snapshot slots: the symmetric arenas do not grow "
+                               "(raise parallel.runtime.init(arena_capacity=...))")
         if self.cuda:
             torch.cuda.synchronize(self.device)
         bigger = torch.zeros(2 * int(self.slots.shape[0]), self.row_numel, dtype=torch.float32, device=self.device)
@@ -184,9 +244,11 @@ class StreamExec:
 
     # -- checkpointing -----------------------------------------------------------------------------------------
     def export_inflight(self) -> Dict[str, Any]:
+        if self.multi:
+            raise NotImplementedError("checkpointing the C++ executor with several ranks")
         rows = self.ex.inflight()
-        idx = torch.as_tensor([r[1] for r in rows], dtype=torch.int64, device=self.device)
-        return {"ids": [int(r[0]) for r in rows], "ages": [int(r[2]) for r in rows],
+        idx = torch.as_tensor([r[2] for r in rows], dtype=torch.int64, device=self.device)
+        return {"ids": [int(r[0]) for r in rows], "ages": [int(r[3]) for r in rows],
                 "rows": self.slots[idx].cpu() if rows else torch.zeros(0, self.row_numel)}
 
     def import_inflight(self, st: Dict[str, Any]) -> None:
@@ -195,9 +257,9 @@ class StreamExec:
             return
         while int(self.slots.shape[0]) < n or self.ex.free_slots < n:
             self._grow()
-        taken = {int(r[1]) for r in self.ex.inflight()}
+        taken = {int(r[2]) for r in self.ex.inflight()}
         free = [s for s in range(int(self.slots.shape[0])) if s not in taken][:n]
         self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = st["rows"].to(self.device)
         if self.cuda:
             torch.cuda.synchronize(self.device)     # the node streams read these slots without a writer event
-        self.ex.import_inflight([[int(m), int(s), int(a)] for m, s, a in zip(st["ids"], free, st["ages"])])
+        self.ex.import_inflight([[int(m), 0, int(s), int(a)] for m, s, a in zip(st["ids"], free, st["ages"])])

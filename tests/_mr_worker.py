@@ -75,6 +75,25 @@ def build(kind, device):
         sim = All2AllGossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
         start_args = (UniformMixing(net),)
         sim._mr_kwargs = {"synchronous": True}
+    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull"):
+        # native engine + the C++ executor (csrc/exec): one executor per rank over the same event list
+        if kind == "x_mlp_pushpull":
+            (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
+            n, bs, net, cls, kwh, proto_, kws = 4, 32, TorchMLP(784, 10, (100,)), TorchModelHandler, {}, AntiEntropyProtocol.PUSH_PULL, {}
+        elif kind == "x_limited_push":
+            (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+            n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), LimitedMergeTMH, {"age_diff_threshold": 2}
+            proto_, kws = AntiEntropyProtocol.PUSH, dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 2), sampling_eval=.5)
+        else:
+            (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(500, 200)
+            n, bs, net, cls = 5, 16, LogisticRegression(57, 2), TorchModelHandler
+            kwh, proto_, kws = {"create_model_mode": CreateModelMode.UPDATE}, AntiEntropyProtocol.PULL, dict(delay=UniformDelay(0, 3))
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
+        proto = cls(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), batch_size=bs, **kwh)
+        nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, kind != "x_limited_push")
+        sim = GossipSimulator(nodes, disp, 10, proto_, **kws)
+        sim.engine = "native"
+        sim.native_executor = True
     elif kind == "pens":              # performance-based neighbour selection: data-dependent top-m, then step 2
         from gossipy_b200.node import PENSNode
         (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
@@ -116,7 +135,8 @@ def run(kind, device, rounds):
             "failed": rep._failed_messages, "size": rep._total_size,
             "sums": {str(k): sums[k] for k in sorted(sums)}, "ages": {str(k): ages[k] for k in sorted(ages)},
             "cache_left": len(g.CACHE),
-            "best": {str(i): getattr(n, "best_nodes", None) for i, n in sim.nodes.items()}}
+            "best": {str(i): getattr(n, "best_nodes", None) for i, n in sim.nodes.items()},
+            "cpp_executor": "_stream_exec" in sim.__dict__}
 
 
 def main():

@@ -71,6 +71,20 @@ def test_pens_two_and_three_ranks_cpu_equal_single_process():
     _compare(single, _run(3, "cpu", rounds=9, kinds="pens"), rel=1e-5, skip=("cache_left",))
 
 
+XKINDS = "x_mlp_pushpull,x_limited_push,x_update_pull"
+
+
+def test_cpp_executor_two_and_three_ranks_cpu_equal_single_process():
+    """csrc/exec with several ranks: replicated books, each rank launches its own nodes, snapshot slots in the
+    symmetric arenas with the ready/done handshake (here: shared-memory flags, host-side waits)."""
+    single = _run(1, "cpu", rounds=4, kinds=XKINDS)
+    assert all(v["cpp_executor"] for v in single.values())
+    for world in (2, 3):
+        multi = _run(world, "cpu", rounds=4, kinds=XKINDS)
+        assert all(v["cpp_executor"] for v in multi.values())
+        _compare(single, multi, rel=1e-5)
+
+
 @pytest.mark.gpu
 def test_two_ranks_cuda_equal_single_gpu():
     if torch.cuda.device_count() < 2:
@@ -87,3 +101,13 @@ def test_pens_two_ranks_cuda_equal_single_gpu():
     single = _run(1, "cuda:0", rounds=9, kinds="pens")
     multi = _run(2, "cuda", rounds=9, kinds="pens")
     _compare(single, multi, rel=2e-3, skip=("cache_left",))
+
+
+@pytest.mark.gpu
+def test_cpp_executor_two_ranks_cuda_equal_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    single = _run(1, "cuda:0", rounds=4, kinds=XKINDS)
+    multi = _run(2, "cuda", rounds=4, kinds=XKINDS)
+    assert all(v["cpp_executor"] for v in multi.values())
+    _compare(single, multi, rel=2e-3)

@@ -156,8 +156,8 @@ def test_executor_runs_out_of_slots_gracefully():
     ex = C.StreamExecutor(3, 1, 4, 0, 2, 2, 1, .1, 0., 5, False, 2, -1)
     for i in range(3):
         ex.set_node(i, 0, 0, 0, 6, 10 * i, 0, 0)
-    ex.set_callbacks(lambda n, s: log.append(("snap", n, s)), lambda n, s, k, ws, wp: log.append(("train", n, s)),
-                     lambda n, s: log.append(("adopt", n, s)))
+    ex.set_callbacks(lambda n, r, s, g, rr: log.append(("snap", n, s)), lambda n, r, s, k, ws, wp, g: log.append(("train", n, s)),
+                     lambda n, r, s, g: log.append(("adopt", n, s)))
     ex.set_slots(0, 1, 8, 8)
     ev = np.array([[C.EV_SEND, 0, 0, 1, 100, 1], [C.EV_SEND, 0, 2, 1, 101, 1], [C.EV_DELIVER, 0, 0, 1, 100, 1],
                    [C.EV_DELIVER, 0, 2, 1, 101, 1], [C.EV_EVAL, 0, 1, -1, -1, 0]], dtype=np.int32)
