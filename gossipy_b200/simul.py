@@ -683,7 +683,7 @@ class GossipSimulator(SimulationEventSender):
             if bank is not None:
                 pending = [int(r[1]) for r in state["msg_q"] if int(r[4]) != 2] + [int(r[1]) for r in state["rep_q"]]
                 st["_bank_inflight"] = bank.export_inflight(pending)
-            if sx is not None:
+            if sx is not None and not sx.multi:      # (several ranks: in-flight snapshots live in other processes)
                 st["_exec_inflight"] = sx.export_inflight()
         return st
 
