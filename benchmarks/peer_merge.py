@@ -7,8 +7,9 @@ over NVLink (BASELINE.json: "peer-merge GB/s vs 900 GB/s").
 Every rank r merges the row of rank (r+1) % W into its own row (dst = .5 dst + .5 peer): W concurrent
 disjoint pairs, the pattern of a gossip round with one node per GPU.  Also measured: adopt (pure pull,
 w_dst = 0), the k-way merge of all W-1 peers, and the one-shot all-reduce (NVLS multicast if the
-system has it, else P2P pull).  Device time (CUDA events), max over ranks; bytes over NVLink per rank
-= 4 * n for the pair merge.  Rows larger than L2 are used for the bandwidth numbers (and an L2 flush
+system has it, else P2P pull).  Next to each, the BASELINE path that only calls NCCL for the same op:
+ncclSend/ncclRecv of the row into a staging buffer + torch element-wise merge, and ``ncclAllReduce`` + scale.
+Device time (CUDA events), max over ranks; bytes over NVLink per rank = 4 * n for the pair merge.  Rows larger than L2 are used for the bandwidth numbers (and an L2 flush
 for the small ones)."""
 import json
 import os
@@ -67,6 +68,22 @@ def main():
                     "concurrent_pairs": world})
         ms = timed(lambda: nat.merge_pair(mine[:n], peer[:n], 0., 1., 0, n, None), do_flush=n < (1 << 26))
         out.append({"op": "adopt(peer)", "floats": n, "us": ms * 1e3, "nvlink_gbs_per_gpu": 4.0 * n / ms / 1e6})
+    # baseline: NCCL point-to-point into a staging buffer, then the merge as torch element-wise ops
+    try:
+        stage = torch.empty(1 << 26, device="cuda")
+        nxt, prv = (rank + 1) % world, (rank - 1) % world
+        for n in (79520, 1 << 20, 1 << 22, 1 << 24, 1 << 26):
+            def nccl_merge(n=n):
+                ops_ = [dist.P2POp(dist.isend, mine[:n], prv), dist.P2POp(dist.irecv, stage[:n], nxt)]
+                for req in dist.batch_isend_irecv(ops_):
+                    req.wait()
+                mine[:n].mul_(.5).add_(stage[:n], alpha=.5)
+            ms = timed(nccl_merge, do_flush=n < (1 << 26))
+            out.append({"op": "baseline: nccl send/recv + torch merge", "floats": n, "us": ms * 1e3,
+                        "nvlink_gbs_per_gpu": 4.0 * n / ms / 1e6, "concurrent_pairs": world})
+        del stage
+    except Exception as exc:  # noqa: BLE001
+        out.append({"op": "baseline: nccl send/recv + torch merge", "error": repr(exc)[:300]})
     if world > 2:
         for n in (79520, 1 << 24):
             srcs = [rows[r][:n] for r in range(world) if r != rank]
@@ -91,6 +108,13 @@ def main():
             err = float((res - ref / world).abs().max())
             out.append({"op": "allreduce_mean(%s)" % coll.kind, "floats": n, "us": ms * 1e3, "max_err_vs_nccl": err,
                         "bytes_received_per_gpu": 4 * n if coll.kind == "nvls" else 4 * n * (world - 1)})
+            if force_p2p:      # once per size: the NCCL call the one-shot kernel replaces
+                def nccl_mean():
+                    res.copy_(coll.contribution)
+                    dist.all_reduce(res)
+                    res.mul_(1.0 / world)
+                ms = timed(nccl_mean, do_flush=True)
+                out.append({"op": "baseline: ncclAllReduce + scale", "floats": n, "us": ms * 1e3})
     except Exception as exc:  # noqa: BLE001
         out.append({"op": "allreduce_mean", "error": repr(exc)[:300]})
     if rank == 0:
