@@ -147,6 +147,10 @@ public:
     // evaluate.  When a pool runs out of slots it stops at that event (`resume_at` >= 0): the caller grows the pool
     // (one rank: set_slots) and calls again with `start = resume_at`.
     std::vector<int> run(py::array_t<int32_t, py::array::c_style | py::array::forcecast> events, int64_t start) {
+        if (events.ndim() != 2 || events.shape(1) != 6) throw std::invalid_argument("events must be an [n, 6] array");
+        if (!cuda_ && (!cb_snapshot_ || !cb_train_ || !cb_adopt_))
+            throw std::runtime_error("CPU mode needs set_callbacks(snapshot, train, adopt)");
+        if (row_floats_ <= 0) throw std::runtime_error("no snapshot slots: call set_slots / add_slot first");
         const auto ev = events.unchecked<2>();
         std::vector<int> evals;
         resume_at_ = -1;
