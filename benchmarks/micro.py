@@ -152,12 +152,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="")
     a = ap.parse_args()
     if a.what in ("train", "all"):
-        for var in os.environ.get("MICRO_TC3_VARIANTS", "").split(",") if a.impl == "tc3" else [""]:
-            if var:
-                os.environ["GB_TC3_VARIANT"] = var
-                print(json.dumps({"GB_TC3_VARIANT": var}))
-            bench_train(a.impl)
-        os.environ.pop("GB_TC3_VARIANT", None)
+        bench_train(a.impl)
     if a.what in ("eval", "all"):
         bench_eval()
     if a.what in ("merge", "all"):
