@@ -1161,8 +1161,14 @@ class PartitionedTMH(TorchModelHandler):
         return self._part_id_dev
 
     def _elem_scale(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        return (self._part_ids(), torch.as_tensor(self.n_updates, dtype=torch.int64,
-                                                  device=self.row.device))
+        ages = torch.as_tensor(np.asarray(self.n_updates, dtype=np.int64))
+        dev = self.row.device
+        if dev.type == "cuda":
+            # through pinned memory, asynchronously on the node's stream: a pageable H2D copy would block the host
+            # until everything queued on that stream has finished (the caching host allocator keeps the staging
+            # buffer alive until the copy has run)
+            ages = ages.pin_memory().to(dev, non_blocking=True)
+        return (self._part_ids(), ages)
 
     def _count_steps(self, steps: int) -> None:
         if self._fused:
