@@ -72,6 +72,24 @@ class TorchModelSampling:
                              dtype=torch.int64)
 
     @classmethod
+    def sample_reference(cls, size: float, net: TorchModel) -> SampleDict:
+        """The reference's draw, call for call, on the NumPy global stream (ref ``sampling.py:56-72``): a tensor per
+        sampled coordinate (probability ~ numel), then an independent index per dimension.  Used under
+        ``GlobalSettings().reference_compat`` so that a simulation consumes the host RNG exactly like the
+        reference (differential tests); the default path draws one device-side ``randint`` instead."""
+        from collections import Counter
+        shapes = _param_shapes(net)
+        probs = np.array([int(np.prod(sh)) if sh else 1 for sh in shapes], dtype="float")
+        total = int(probs.sum())
+        probs /= sum(probs)
+        k = max(1, int(round(size * total)))
+        counter = dict(Counter(list(np.random.choice(len(shapes), size=k, p=probs))))
+        out: SampleDict = {i: None for i in range(len(shapes))}
+        for i, c in counter.items():
+            out[int(i)] = tuple(LongTensor(list(np.random.choice(sdim, size=c))) for sdim in shapes[int(i)])
+        return out
+
+    @classmethod
     def sample(cls, size: float, net: TorchModel) -> SampleDict:
         """The reference's representation: ``{tensor_idx: tuple(index per dim) | None}``."""
         if size >= 0.9:

@@ -223,7 +223,10 @@ class SamplingBasedNode(GossipNode):
     def _consume(self, msg: Message, recv_model: ModelHandler, extras: Tuple[Any, ...]) -> None:
         sample_size = extras[0]
         handler: SamplingTMH = self.model_handler
-        if sample_size == handler.sample_size:
+        if GlobalSettings().reference_compat:      # the reference's own draw on the NumPy stream (differential tests)
+            from .model.sampling import TorchModelSampling
+            sample = TorchModelSampling.sample_reference(sample_size, handler._proto)
+        elif sample_size == handler.sample_size:
             sample = handler.draw_sample()
         else:
             from .model.sampling import TorchModelSampling

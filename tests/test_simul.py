@@ -310,3 +310,31 @@ def test_random_setups_match_reference(ref):
             for k in b:
                 assert a[k] == pytest.approx(float(b[k]), abs=2.5 / (80 * n_nodes)), (k, protocol, mode)   # <= 2 borderline samples
     check()
+
+
+@pytest.mark.parametrize("node_cls", ["SamplingBasedNode", "PartitioningBasedNode"])
+@pytest.mark.parametrize("protocol", ["PUSH", "PULL", "PUSH_PULL"])
+@pytest.mark.parametrize("faults", [False, True])
+def test_sampled_and_partitioned_nodes_match_reference_exactly(ref, node_cls, protocol, faults):
+    """Hegedus 2021 node types under MERGE_UPDATE: same host RNG consumption (the receiver's coordinate sample under
+    ``reference_compat``, the sender's partition id always) -> identical schedules under drop / churn / delay and
+    identical metric curves."""
+    def proto(ns):
+        torch.manual_seed(0)
+        net = ns["nn"].LogisticRegression(10, 2)
+        kw = dict(net=net, optimizer=torch.optim.SGD, criterion=CE, batch_size=0,
+                  create_model_mode=ns["core"].CreateModelMode.MERGE_UPDATE)
+        if node_cls == "SamplingBasedNode":
+            return ns["handler"].SamplingTMH(.4, optimizer_params={"lr": .5}, **kw)
+        return ns["handler"].PartitionedTMH(tm_partition=ns["sampling"].TorchModelPartition(net, 4),
+                                            optimizer_params={"lr": 1.}, **kw)
+    g.GlobalSettings().reference_compat = node_cls == "SamplingBasedNode"
+    kw = (lambda ns: dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5)) if faults else None
+    ours, theirs = _run_both(ref, rounds=3, n_nodes=8, proto_fn=proto, node_cls=node_cls, protocol=protocol, sim_kw=kw)
+    assert (ours._sent_messages, ours._failed_messages, ours._total_size) == \
+        (theirs._sent_messages, theirs._failed_messages, theirs._total_size)
+    eo, er = ours.get_evaluation(False), theirs.get_evaluation(False)
+    assert [t for t, _ in eo] == [t for t, _ in er] and len(eo) == 3
+    for (_, a), (_, b) in zip(eo, er):
+        for k in b:
+            assert a[k] == pytest.approx(float(b[k]), abs=1e-6), k
