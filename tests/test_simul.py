@@ -338,3 +338,57 @@ def test_sampled_and_partitioned_nodes_match_reference_exactly(ref, node_cls, pr
     for (_, a), (_, b) in zip(eo, er):
         for k in b:
             assert a[k] == pytest.approx(float(b[k]), abs=1e-6), k
+
+
+def _run_both_built(ref, build, rounds=3):
+    out = []
+    for ns in (_ns(), _ns(ref)):
+        random.seed(5); np.random.seed(5); torch.manual_seed(5)
+        sim, rep = build(ns)
+        if hasattr(sim, "progress"):
+            sim.progress = False
+        random.seed(11); np.random.seed(11); torch.manual_seed(11)
+        sim.init_nodes(seed=42)
+        random.seed(12); np.random.seed(12)
+        sim.start(n_rounds=rounds)
+        rep.sim = sim
+        out.append(rep)
+    return out
+
+
+def _assert_same_run(ours, theirs, curves=True, tol=1e-6):
+    assert (ours._sent_messages, ours._failed_messages, ours._total_size) == \
+        (theirs._sent_messages, theirs._failed_messages, theirs._total_size)
+    eo, er = ours.get_evaluation(False), theirs.get_evaluation(False)
+    assert [t for t, _ in eo] == [t for t, _ in er] and len(eo) > 0
+    if curves:
+        for (_, a), (_, b) in zip(eo, er):
+            for k in b:
+                assert a[k] == pytest.approx(float(b[k]), abs=tol), k
+
+
+@pytest.mark.parametrize("cls", ["PegasosHandler", "AdaLineHandler"])
+@pytest.mark.parametrize("mode", ["UPDATE", "MERGE_UPDATE"])
+@pytest.mark.parametrize("protocol,faults", [("PUSH", False), ("PUSH", True), ("PUSH_PULL", False), ("PUSH_PULL", True)])
+def test_linear_learners_match_reference_exactly(ref, cls, mode, protocol, faults):
+    """Ormandi 2013 learners: schedules and metric curves identical to the reference (1e-16 in practice).  The one
+    exception is UPDATE under message loss with two legs in flight, where the reference trains a cache entry that a
+    lost message leaked and a later message reuses (B9 + B10): only the schedule is compared there."""
+    def build(ns):
+        gen = torch.Generator().manual_seed(0)
+        X = torch.randn(480, 10, generator=gen)
+        y = torch.sign(X @ torch.randn(10, generator=gen))
+        dh = ns["data_handler"].ClassificationDataHandler(X[:400], y[:400], X[400:], y[400:])
+        disp = ns["data"].DataDispatcher(dh, n=8, eval_on_user=False, auto_assign=False)
+        disp.set_assignments(_assign(8), None)
+        proto = getattr(ns["handler"], cls)(net=ns["nn"].AdaLine(10), learning_rate=.01,
+                                            create_model_mode=getattr(ns["core"].CreateModelMode, mode))
+        nodes = ns["node"].GossipNode.generate(disp, ns["core"].StaticP2PNetwork(8, None), proto, round_len=10, sync=True)
+        kw = dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5) if faults else {}
+        sim = ns["simul"].GossipSimulator(nodes=nodes, data_dispatcher=disp, delta=10,
+                                          protocol=getattr(ns["core"].AntiEntropyProtocol, protocol), **kw)
+        rep = ns["simul"].SimulationReport()
+        sim.add_receiver(rep)
+        return sim, rep
+    ours, theirs = _run_both_built(ref, build)
+    _assert_same_run(ours, theirs, curves=not (mode == "UPDATE" and protocol == "PUSH_PULL" and faults))
