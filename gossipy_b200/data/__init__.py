@@ -226,6 +226,15 @@ class RecSysDataDispatcher(DataDispatcher):
         self.assignments: List[int] = list(range(self.n))
 
     def assign(self, seed: int = 42) -> None:
+        """User -> client permutation.  Default: a private generator (no side effects).  Under
+        ``reference_compat``: the reference's statement, which re-seeds torch's GLOBAL stream
+        (``data/__init__.py:534-536``)."""
+        from .. import GlobalSettings
+        if GlobalSettings().reference_compat:
+            import torch
+            torch.manual_seed(seed)
+            self.assignments = torch.randperm(self.data_handler.size()).tolist()
+            return
         self.assignments = np.random.default_rng(seed).permutation(self.n).tolist()
 
     def __getitem__(self, idx: int) -> Any:

@@ -112,13 +112,17 @@ class RecSysDataHandler(DataHandler):
     def __init__(self, ratings: Dict[int, List[Tuple[int, float]]], n_users: int, n_items: int,
                  test_size: float = 0.2, seed: int = 42) -> None:
         self.n_users, self.n_items = n_users, n_items
+        from .. import GlobalSettings
+        compat = GlobalSettings().reference_compat
+        if compat:
+            np.random.seed(seed)        # the reference re-seeds NumPy's GLOBAL stream here (data/handler.py:211)
         rng = np.random.default_rng(seed)
         self.ratings: Dict[int, np.ndarray] = {}
         self.test_id: List[int] = []
         for u in range(len(ratings)):
             arr = np.asarray(ratings[u], dtype=np.float64).reshape(-1, 2)
             self.test_id.append(max(1, int(len(arr) * (1 - test_size))))
-            self.ratings[u] = arr[rng.permutation(len(arr))]
+            self.ratings[u] = np.random.permutation(arr) if compat else arr[rng.permutation(len(arr))]
 
     def __getitem__(self, idx: int) -> np.ndarray:
         return self.ratings[idx][:self.test_id[idx]]

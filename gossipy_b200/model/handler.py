@@ -702,6 +702,9 @@ class TorchModelHandler(RowHandler):
         mod = self.model
         dev = self.device
         with _arena.on_stream(self._stream()):
+            if GlobalSettings().reference_compat:   # global torch stream, like the reference (placement dependent)
+                mod.init_weights()
+                return
             with torch.random.fork_rng(devices=[dev] if dev.type == "cuda" else []):
                 torch.manual_seed(_rng.derive(0x1217, self.owner if self.owner >= 0 else 0))
                 mod.init_weights()
@@ -1349,9 +1352,14 @@ class MFModelHandler(RowHandler):
             self._ensure_row()
             return
         X, b, Y, c = self._parts()
-        gen = torch.Generator().manual_seed(_rng.derive(0x3F, max(self.owner, 0)))
-        X.copy_(torch.rand(self.k, generator=gen) * mul)
-        Y.copy_(torch.rand(self.n_items, self.k, generator=gen) * mul)
+        if GlobalSettings().reference_compat:       # the reference's draws on the NumPy stream (handler.py:543-545)
+            mul64 = np.sqrt((r_max - r_min) / self.k)
+            X.copy_(torch.as_tensor(np.random.rand(1, self.k) * mul64, dtype=torch.float32).reshape(-1))
+            Y.copy_(torch.as_tensor(np.random.rand(self.n_items, self.k) * mul64, dtype=torch.float32))
+        else:
+            gen = torch.Generator().manual_seed(_rng.derive(0x3F, max(self.owner, 0)))
+            X.copy_(torch.rand(self.k, generator=gen) * mul)
+            Y.copy_(torch.rand(self.n_items, self.k, generator=gen) * mul)
         b.fill_(r_min / 2.0)
         c.fill_(r_min / 2.0)
 
@@ -1426,6 +1434,9 @@ class KMeansHandler(RowHandler):
         if not self._mine():
             self._ensure_row()
             self._version += 1
+            return
+        if GlobalSettings().reference_compat:       # the reference draws from the global torch stream (handler.py:595)
+            self.model = torch.rand(size=(self.k, self.dim))
             return
         gen = torch.Generator().manual_seed(_rng.derive(0x4B, max(self.owner, 0)))
         self.model = torch.rand(self.k, self.dim, generator=gen)

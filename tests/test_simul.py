@@ -392,3 +392,66 @@ def test_linear_learners_match_reference_exactly(ref, cls, mode, protocol, fault
         return sim, rep
     ours, theirs = _run_both_built(ref, build)
     _assert_same_run(ours, theirs, curves=not (mode == "UPDATE" and protocol == "PUSH_PULL" and faults))
+
+
+@pytest.mark.parametrize("matching", ["naive", "hungarian"])
+@pytest.mark.parametrize("protocol,faults", [("PUSH", False), ("PUSH", True), ("PUSH_PULL", False), ("PUSH_PULL", True)])
+def test_kmeans_matches_reference_exactly(ref, matching, protocol, faults):
+    """Berta 2014 under ``reference_compat`` (centroids drawn from the global torch stream like the reference).  The data
+    handler is the classification one on purpose: the reference's ClusteringDataHandler still splits 80/20 (B18)."""
+    g.GlobalSettings().reference_compat = True
+
+    def build(ns):
+        gen = torch.Generator().manual_seed(0)
+        X = torch.cat([torch.randn(120, 6, generator=gen) + 2, torch.randn(120, 6, generator=gen) - 2])
+        y = torch.cat([torch.zeros(120), torch.ones(120)]).long()
+        perm = torch.randperm(240, generator=gen)
+        X, y = X[perm], y[perm]
+        dh = ns["data_handler"].ClassificationDataHandler(X[:192], y[:192], X[192:], y[192:])
+        disp = ns["data"].DataDispatcher(dh, n=12, eval_on_user=False, auto_assign=False)
+        disp.set_assignments([np.arange(i * 16, (i + 1) * 16) for i in range(12)], None)
+        proto = ns["handler"].KMeansHandler(k=2, dim=6, alpha=.1, matching=matching,
+                                            create_model_mode=ns["core"].CreateModelMode.MERGE_UPDATE)
+        nodes = ns["node"].GossipNode.generate(disp, ns["core"].StaticP2PNetwork(12, None), proto, round_len=10, sync=True)
+        kw = dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5) if faults else {}
+        sim = ns["simul"].GossipSimulator(nodes=nodes, data_dispatcher=disp, delta=10,
+                                          protocol=getattr(ns["core"].AntiEntropyProtocol, protocol), **kw)
+        rep = ns["simul"].SimulationReport()
+        sim.add_receiver(rep)
+        return sim, rep
+    ours, theirs = _run_both_built(ref, build)
+    _assert_same_run(ours, theirs)
+
+
+@pytest.mark.parametrize("mode", ["MERGE_UPDATE", "UPDATE"])
+@pytest.mark.parametrize("protocol,faults", [("PUSH", False), ("PUSH", True), ("PUSH_PULL", False), ("PUSH_PULL", True)])
+def test_matrix_factorisation_matches_reference(ref, mode, protocol, faults):
+    """Hegedus 2020 under ``reference_compat`` (the reference's NumPy draws for the split, the user permutation and the
+    factor initialisation): same schedule, RMSE curves equal up to fp32 vs fp64 (B15's extra 1/2 in the merge is kept)."""
+    g.GlobalSettings().reference_compat = True
+
+    def build(ns):
+        rng = np.random.RandomState(0)
+        nu, ni = 10, 15
+        ratings = {u: [(int(i), float(rng.randint(1, 6))) for i in rng.choice(ni, 8, replace=False)] for u in range(nu)}
+        dh = ns["data_handler"].RecSysDataHandler(ratings, nu, ni, .2, seed=42)
+        disp = ns["data"].RecSysDataDispatcher(dh)
+        disp.assign(seed=42)
+        proto = ns["handler"].MFModelHandler(dim=3, n_items=ni, lam_reg=.1, learning_rate=.01,
+                                             create_model_mode=getattr(ns["core"].CreateModelMode, mode))
+        nodes = ns["node"].GossipNode.generate(disp, ns["core"].StaticP2PNetwork(nu, None), proto, round_len=10, sync=True)
+        kw = dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5) if faults else {}
+        sim = ns["simul"].GossipSimulator(nodes=nodes, data_dispatcher=disp, delta=10,
+                                          protocol=getattr(ns["core"].AntiEntropyProtocol, protocol), **kw)
+        rep = ns["simul"].SimulationReport()
+        sim.add_receiver(rep)
+        return sim, rep
+    ours, theirs = _run_both_built(ref, build)
+    assert (ours._sent_messages, ours._failed_messages, ours._total_size) == \
+        (theirs._sent_messages, theirs._failed_messages, theirs._total_size)
+    eo, er = ours.get_evaluation(True), theirs.get_evaluation(True)
+    assert [t for t, _ in eo] == [t for t, _ in er] and len(eo) == 3
+    if mode == "UPDATE" and protocol == "PUSH_PULL" and faults:
+        return      # B9 + B10: the reference trains a leaked, re-used cache entry in place
+    for (_, a), (_, b) in zip(eo, er):
+        assert a["rmse"] == pytest.approx(float(b["rmse"]), abs=1e-5)
