@@ -455,3 +455,48 @@ def test_matrix_factorisation_matches_reference(ref, mode, protocol, faults):
         return      # B9 + B10: the reference trains a leaked, re-used cache entry in place
     for (_, a), (_, b) in zip(eo, er):
         assert a["rmse"] == pytest.approx(float(b["rmse"]), abs=1e-5)
+
+
+@pytest.mark.parametrize("mixing", ["UniformMixing", "MetropolisHastingsMixing"])
+@pytest.mark.parametrize("topo_kind", ["clique", "ring"])
+@pytest.mark.parametrize("faults", [False, True])
+def test_all2all_matches_reference_exactly_in_compat_mode(ref, mixing, topo_kind, faults):
+    """Koloskova 2020 / main_all2all: with ``reference_compat`` (mixing weights paired with models by arrival order and
+    not renormalised, B17) schedules and curves are identical to the reference; the default pairs by peer id."""
+    g.GlobalSettings().reference_compat = True
+
+    def build(ns):
+        Xtr, ytr, Xte, yte = _dataset()
+        dh = ns["data_handler"].ClassificationDataHandler(Xtr, ytr, Xte, yte)
+        disp = ns["data"].DataDispatcher(dh, n=6, eval_on_user=False, auto_assign=False)
+        disp.set_assignments(_assign(6), None)
+        topo = None
+        if topo_kind == "ring":
+            topo = np.zeros((6, 6))
+            for i in range(6):
+                topo[i, (i + 1) % 6] = topo[i, (i - 1) % 6] = 1
+        net = ns["core"].StaticP2PNetwork(6, topo)
+        torch.manual_seed(0)
+        proto = ns["handler"].WeightedTMH(net=ns["nn"].LogisticRegression(10, 2), optimizer=torch.optim.SGD,
+                                          optimizer_params={"lr": .5}, criterion=CE, batch_size=0,
+                                          create_model_mode=ns["core"].CreateModelMode.MERGE_UPDATE)
+        nodes = ns["node"].All2AllGossipNode.generate(disp, net, proto, round_len=10, sync=True)
+        kw = dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5) if faults else {}
+        sim = ns["simul"].All2AllGossipSimulator(nodes=nodes, data_dispatcher=disp, delta=10,
+                                                 protocol=ns["core"].AntiEntropyProtocol.PUSH, **kw)
+        rep = ns["simul"].SimulationReport()
+        sim.add_receiver(rep)
+        sim._W = getattr(ns["core"], mixing)(net)
+        return sim, rep
+    out = []
+    for ns in (_ns(), _ns(ref)):
+        random.seed(5); np.random.seed(5); torch.manual_seed(5)
+        sim, rep = build(ns)
+        if hasattr(sim, "progress"):
+            sim.progress = False
+        random.seed(11); np.random.seed(11); torch.manual_seed(11)
+        sim.init_nodes(seed=42)
+        random.seed(12); np.random.seed(12)
+        sim.start(sim._W, n_rounds=3)
+        out.append(rep)
+    _assert_same_run(out[0], out[1])
