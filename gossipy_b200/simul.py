@@ -746,8 +746,13 @@ class TokenizedGossipSimulator(GossipSimulator):
         reaction = account.reactive(utility)
         if reaction:
             account.sub(reaction)
+            actor = receiver
+            if GlobalSettings().reference_compat:
+                # B4 mimicked: the reference issues the reactive sends from its stale loop variable `node`,
+                # i.e. the LAST node of this round's shuffled order, whoever received the message
+                actor = self.nodes[int(self._node_order[-1])]
             for _ in range(int(reaction)):
-                if not self._fire(receiver, t):
+                if not self._fire(actor, t):
                     break
 
     def __getstate__(self) -> Dict[str, Any]:

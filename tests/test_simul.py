@@ -500,3 +500,38 @@ def test_all2all_matches_reference_exactly_in_compat_mode(ref, mixing, topo_kind
         sim.start(sim._W, n_rounds=3)
         out.append(rep)
     _assert_same_run(out[0], out[1])
+
+
+_ACCOUNTS = {"proactive": lambda ns: ns["fc"].PurelyProactiveTokenAccount(),
+             "reactive": lambda ns: ns["fc"].PurelyReactiveTokenAccount(k=1),
+             "simple": lambda ns: ns["fc"].SimpleTokenAccount(C=2),
+             "generalized": lambda ns: ns["fc"].GeneralizedTokenAccount(C=4, A=2),
+             "randomized": lambda ns: ns["fc"].RandomizedTokenAccount(C=4, A=2)}
+
+
+@pytest.mark.parametrize("account", sorted(_ACCOUNTS))
+@pytest.mark.parametrize("protocol", ["PUSH", "PUSH_PULL"])
+@pytest.mark.parametrize("faults", [False, True])
+def test_tokenized_simulator_matches_reference_exactly_in_compat_mode(ref, account, protocol, faults):
+    """Danner 2018 flow control inside the round loop.  ``reference_compat`` mimics B4 (reactive sends leave from the
+    last node of the round's order instead of the receiver), which makes every account strategy comparable: schedules
+    under faults and metric curves are identical.  (Default behaviour: the receiver reacts, test above.)"""
+    g.GlobalSettings().reference_compat = True
+
+    def sim_kw(ns):
+        d = dict(token_account=_ACCOUNTS[account](ns), utility_fun=lambda a, b, m: 1)
+        if faults:
+            d.update(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5)
+        return d
+    ours, theirs = _run_both(ref, rounds=4, n_nodes=8, proto_fn=_logreg_proto(), sim_cls="TokenizedGossipSimulator",
+                             protocol=protocol, sim_kw=sim_kw)
+    _assert_same_run(ours, theirs)
+
+
+@pytest.mark.parametrize("faults", [False, True])
+def test_pens_matches_reference_exactly(ref, faults):
+    kw = (lambda ns: dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5)) if faults else None
+    ours, theirs = _run_both(ref, rounds=4, n_nodes=8, proto_fn=_logreg_proto(), node_cls="PENSNode", protocol="PUSH",
+                             node_kw={"n_sampled": 3, "m_top": 2, "step1_rounds": 2}, sim_kw=kw)
+    _assert_same_run(ours, theirs)
+    assert all(n.step == 2 for n in ours.sim.nodes.values())
