@@ -137,12 +137,21 @@ class ModelHandler(Sizeable, ABC):
         """Combine a received model with the local one according to ``self.mode``
         (ref ``handler.py:117-136``)."""
         mode = self.mode
+        compat = GlobalSettings().reference_compat
         if mode == CreateModelMode.UPDATE:
             # train the received model on local data and adopt it: adopting first and training
             # the local row is the same computation without mutating the in-flight snapshot
             self._adopt(recv_model)
             self.n_updates = copy.copy(recv_model.n_updates)
-            self._update(data)
+            if compat:
+                # B13 mimicked: the reference trains the received handler with the optimizer that travelled with it,
+                # which is detached if the SENDER had adopted a model before; afterwards this node's own optimizer
+                # is detached from the adopted model (it is what this node's later snapshots ship)
+                self._opt_detached = bool(recv_model.__dict__.get("_opt_detached", False))
+                self._update(data)
+                self._opt_detached = True
+            else:
+                self._update(data)
         elif mode == CreateModelMode.MERGE_UPDATE:
             if not (args or kwargs) and self._merge_update_fused(recv_model, data):
                 return
@@ -156,6 +165,8 @@ class ModelHandler(Sizeable, ABC):
             _dispose(tmp)
         elif mode == CreateModelMode.PASS:
             self._adopt(recv_model)
+            if compat:
+                self._opt_detached = True      # B13: ``self.model = deepcopy(...)`` leaves the optimizer on the old tensors
         else:
             raise ValueError("Unknown create model mode %s" % str(mode))
 
@@ -732,6 +743,18 @@ class TorchModelHandler(RowHandler):
 
     def _update(self, data: Tuple[torch.Tensor, torch.Tensor], merge_from: Any = None) -> None:
         self._version += 1
+        if self.__dict__.get("_opt_detached") and GlobalSettings().reference_compat and merge_from is None:
+            # B13 mimicked (differential tests only): the reference's optimizer still points at parameters that were
+            # replaced by an adoption, so its step changes nothing; the age still advances (handler.py:250-258)
+            self._next_key()
+            steps = self._n_local_steps(data)
+            if self._fused:
+                self._count_steps(steps)
+            else:
+                for _ in range(steps):
+                    self._pre_step()
+                self._count_steps(steps)
+            return
         if not self._mine():       # another rank trains this node: replay the bookkeeping only
             self._ensure_row()
             self._next_key()
@@ -772,6 +795,8 @@ class TorchModelHandler(RowHandler):
     def _merge_update_fused(self, recv_model: Any, data: Any) -> bool:
         if not (self._fused and FUSE_MERGE_UPDATE) or self.layout.int_buffers:
             return False
+        if self.__dict__.get("_opt_detached") and GlobalSettings().reference_compat:
+            return False       # B13 mimicked: merge, then an update whose optimizer step is lost (see _update)
         w = self._fused_merge_weights(recv_model)
         if w is None:
             return False

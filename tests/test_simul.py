@@ -284,6 +284,7 @@ def test_random_setups_match_reference(ref):
            samp=st.sampled_from([0., .4]), n_nodes=st.sampled_from([4, 8]), rounds=st.integers(2, 4))
     def check(protocol, mode, sync, drop, online, delay, samp, n_nodes, rounds):
         CACHE.clear()
+        g.GlobalSettings().reference_compat = True
         ours, theirs = _run_both(ref, rounds=rounds, n_nodes=n_nodes, proto_fn=_logreg_proto(mode=mode), protocol=protocol,
                                  sync=sync,
                                  sim_kw=lambda ns: dict(drop_prob=drop, online_prob=online, sampling_eval=samp,
@@ -293,19 +294,21 @@ def test_random_setups_match_reference(ref):
             (theirs._sent_messages, theirs._failed_messages, theirs._total_size)
         eo, er = ours.get_evaluation(False), theirs.get_evaluation(False)
         assert [t for t, _ in eo] == [t for t, _ in er]
-        # Where the reference's known bugs cannot fire, ages and curves must coincide too:
+        # Ages and curves must coincide too wherever the reference's cache aliasing cannot fire (B13 -- the optimizer that
+        # stays on replaced parameters after an adoption -- is mimicked under ``reference_compat``):
         #   B9  two in-flight messages of a node with the same (owner, age) key share ONE cached handler object, and UPDATE /
-        #       UPDATE_MERGE train the received handler in place: the second receiver gets an already trained, older-looking
-        #       snapshot.  B10 makes the sharing permanent in lossy runs (leaked entries), which also hits PASS (age never moves).
-        #   B13 (UPDATE) a node that adopted a model ships an optimizer that still points at the replaced parameters.
-        # MERGE_UPDATE never mutates a received handler and its key changes with every update: fully comparable.
+        #       UPDATE_MERGE train the received handler in place: the second receiver gets an already trained snapshot; PASS
+        #       never moves the age, so there the second message carries a stale model.  B10 makes the sharing permanent in
+        #       lossy runs (leaked entries).  One message per node and round (sync clocks, no delay, no loss) rules it out.
+        # MERGE_UPDATE never mutates a received handler and its key changes with every update: always comparable.
         lossy = drop > 0 or online < 1
-        one_in_flight = protocol == "PUSH" and delay == 0 and not lossy      # PASS never moves the age: B9 needs 2 in flight
-        if mode == "MERGE_UPDATE" or (mode == "PASS" and one_in_flight):
-            assert [int(ours.sim.nodes[i].model_handler.n_updates) for i in range(n_nodes)] == \
-                [int(theirs.sim.nodes[i].model_handler.n_updates) for i in range(n_nodes)]
-        else:
+        one_per_round = sync and not lossy and delay == 0
+        if mode in ("UPDATE", "UPDATE_MERGE"):
+            one_per_round = one_per_round and protocol == "PUSH"      # two pulls answered by one node in a round share a key
+        if not (mode == "MERGE_UPDATE" or one_per_round):
             return
+        assert [int(ours.sim.nodes[i].model_handler.n_updates) for i in range(n_nodes)] == \
+            [int(theirs.sim.nodes[i].model_handler.n_updates) for i in range(n_nodes)]
         for (_, a), (_, b) in zip(eo, er):
             for k in b:
                 assert a[k] == pytest.approx(float(b[k]), abs=2.5 / (80 * n_nodes)), (k, protocol, mode)   # <= 2 borderline samples
@@ -535,3 +538,34 @@ def test_pens_matches_reference_exactly(ref, faults):
                              node_kw={"n_sampled": 3, "m_top": 2, "step1_rounds": 2}, sim_kw=kw)
     _assert_same_run(ours, theirs)
     assert all(n.step == 2 for n in ours.sim.nodes.values())
+
+
+def _giaretta_topology():
+    ring = np.zeros((8, 8))
+    for i in range(8):
+        ring[i, (i + 1) % 8] = ring[i, (i - 1) % 8] = 1
+    ring[1, 4] = ring[4, 1] = 1
+    ring[0, 3] = ring[3, 0] = 1
+    return ring
+
+
+@pytest.mark.parametrize("topo", ["clique", "irregular"])
+@pytest.mark.parametrize("protocol,faults", [("PUSH", False), ("PUSH", True), ("PULL", False), ("PULL", True)])
+def test_pass_through_matches_reference_exactly_in_compat_mode(ref, topo, protocol, faults):
+    """Giaretta 2019: degree-aware pass-through on an irregular graph.  ``reference_compat`` mimics B1 (degree of node 0)
+    and B13 (an adopting node's optimizer stays on the replaced parameters: its later steps are lost), after which
+    schedules AND curves coincide.  (PUSH_PULL can put two messages with the same cache key in flight: B9.)"""
+    g.GlobalSettings().reference_compat = True
+    kw = (lambda ns: dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5)) if faults else None
+    ours, theirs = _run_both(ref, rounds=4, n_nodes=8, proto_fn=_logreg_proto(), node_cls="PassThroughNode",
+                             protocol=protocol, sim_kw=kw, topo=None if topo == "clique" else _giaretta_topology())
+    _assert_same_run(ours, theirs)
+
+
+@pytest.mark.parametrize("faults", [False, True])
+def test_cache_neigh_pull_matches_reference_exactly(ref, faults):
+    """CacheNeighNode: the reference only survives the PULL protocol on current Pythons (B11: ``random.choice(set)``)."""
+    kw = (lambda ns: dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5)) if faults else None
+    ours, theirs = _run_both(ref, rounds=4, n_nodes=8, proto_fn=_logreg_proto(), node_cls="CacheNeighNode",
+                             protocol="PULL", sim_kw=kw, topo=_giaretta_topology())
+    _assert_same_run(ours, theirs)
