@@ -569,3 +569,16 @@ def test_cache_neigh_pull_matches_reference_exactly(ref, faults):
     ours, theirs = _run_both(ref, rounds=4, n_nodes=8, proto_fn=_logreg_proto(), node_cls="CacheNeighNode",
                              protocol="PULL", sim_kw=kw, topo=_giaretta_topology())
     _assert_same_run(ours, theirs)
+
+
+@pytest.mark.parametrize("L", [0, 1, 5])
+@pytest.mark.parametrize("protocol", ["PUSH", "PULL", "PUSH_PULL"])
+@pytest.mark.parametrize("faults", [False, True])
+def test_limited_merge_matches_reference_exactly(ref, L, protocol, faults):
+    """Danner 2023 age-limited merge (keep / adopt / age-weighted average by the age gap), asynchronous clocks."""
+    kw = (lambda ns: dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5)) if faults else None
+    ours, theirs = _run_both(ref, rounds=4, n_nodes=8, proto_fn=_logreg_proto(cls="LimitedMergeTMH", age_diff_threshold=L),
+                             protocol=protocol, sim_kw=kw, sync=False)
+    _assert_same_run(ours, theirs)
+    assert [int(ours.sim.nodes[i].model_handler.n_updates) for i in range(8)] == \
+        [int(theirs.sim.nodes[i].model_handler.n_updates) for i in range(8)]
