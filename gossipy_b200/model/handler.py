@@ -768,9 +768,9 @@ class TorchModelHandler(RowHandler):
         x, y = self._to_device(data)
         s = self._stream()
         with _arena.on_stream(s):
-            if self._fused:
+            if self._fused and not (GlobalSettings().reference_compat and merge_from is None and self.batch_size):
                 steps = self._update_fused(x, y, merge_from)
-            else:
+            else:       # (compat + mini-batches: the reference's own shuffles, which only the autograd path can follow)
                 steps = self._update_generic(x, y)
         self._count_steps(steps)
 
@@ -795,8 +795,10 @@ class TorchModelHandler(RowHandler):
     def _merge_update_fused(self, recv_model: Any, data: Any) -> bool:
         if not (self._fused and FUSE_MERGE_UPDATE) or self.layout.int_buffers:
             return False
-        if self.__dict__.get("_opt_detached") and GlobalSettings().reference_compat:
-            return False       # B13 mimicked: merge, then an update whose optimizer step is lost (see _update)
+        if GlobalSettings().reference_compat and (self.__dict__.get("_opt_detached") or self.batch_size):
+            # B13 mimicked: merge, then an update whose optimizer step is lost (see _update); mini-batches: merge, then
+            # the autograd path with the reference's own shuffles (the fused kernels shuffle with the keyed permutation)
+            return False
         w = self._fused_merge_weights(recv_model)
         if w is None:
             return False
@@ -829,6 +831,21 @@ class TorchModelHandler(RowHandler):
         bs = n if not self.batch_size else self.batch_size
         gen_key = self._next_key()
         steps = 0
+        if GlobalSettings().reference_compat:
+            # the reference's shuffles, call for call on torch's global stream (handler.py:238-247): every epoch permutes
+            # the ALREADY permuted arrays
+            if self.local_epochs > 0:
+                for _ in range(self.local_epochs):
+                    perm = torch.randperm(n).to(x.device)
+                    x, y = x[perm], y[perm]
+                    for i in range(0, n, bs):
+                        self._local_step(mod, x[i:i + bs], y[i:i + bs])
+                        steps += 1
+            else:
+                perm = torch.randperm(n).to(x.device)
+                self._local_step(mod, x[perm][:bs], y[perm][:bs])
+                steps = 1
+            return steps
         if self.local_epochs > 0:
             for e in range(self.local_epochs):
                 perm = torch.from_numpy(ops.torch_ref.perm_indices(n, _rng.mix64(gen_key ^ e))).to(x.device)

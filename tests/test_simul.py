@@ -582,3 +582,30 @@ def test_limited_merge_matches_reference_exactly(ref, L, protocol, faults):
     _assert_same_run(ours, theirs)
     assert [int(ours.sim.nodes[i].model_handler.n_updates) for i in range(8)] == \
         [int(theirs.sim.nodes[i].model_handler.n_updates) for i in range(8)]
+
+
+@pytest.mark.parametrize("net_kind", ["logreg", "mlp"])
+@pytest.mark.parametrize("bs,epochs", [(16, 1), (7, 2), (16, 0)])
+@pytest.mark.parametrize("opt", ["sgd", "momentum", "adam"])
+@pytest.mark.parametrize("faults", [False, True])
+def test_minibatch_training_matches_reference_exactly(ref, net_kind, bs, epochs, opt, faults):
+    """Mini-batch local training inside a push-pull simulation.  Under ``reference_compat`` the shuffles are the
+    reference's own (``torch.randperm`` per epoch on the already permuted arrays); batch slicing, the short last batch,
+    ``local_epochs = 0`` (one random batch), and the flat SGD / momentum / Adam steps on the parameter row then reproduce
+    ``torch.optim`` on module parameters bit for bit: identical ages and curves."""
+    g.GlobalSettings().reference_compat = True
+
+    def proto(ns):
+        torch.manual_seed(0)
+        net = ns["nn"].LogisticRegression(10, 2) if net_kind == "logreg" else ns["nn"].TorchMLP(10, 2, (16,))
+        o, op = {"sgd": (torch.optim.SGD, {"lr": .1, "weight_decay": .01}),
+                 "momentum": (torch.optim.SGD, {"lr": .05, "momentum": .9}),
+                 "adam": (torch.optim.Adam, {"lr": .01})}[opt]
+        return ns["handler"].TorchModelHandler(net=net, optimizer=o, optimizer_params=op, criterion=CE, batch_size=bs,
+                                               local_epochs=epochs,
+                                               create_model_mode=ns["core"].CreateModelMode.MERGE_UPDATE)
+    kw = (lambda ns: dict(drop_prob=.2, online_prob=.8, delay=ns["core"].UniformDelay(0, 3), sampling_eval=.5)) if faults else None
+    ours, theirs = _run_both(ref, rounds=3, n_nodes=4, proto_fn=proto, protocol="PUSH_PULL", sim_kw=kw)
+    _assert_same_run(ours, theirs, tol=1e-9)
+    assert [int(ours.sim.nodes[i].model_handler.n_updates) for i in range(4)] == \
+        [int(theirs.sim.nodes[i].model_handler.n_updates) for i in range(4)]
