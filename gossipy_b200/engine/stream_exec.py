@@ -36,6 +36,9 @@ def eligible(sim: Any) -> Optional[str]:
     from ..model import handler as H
     from ..node import GossipNode
     from ..parallel import runtime as prt
+    from .. import GlobalSettings
+    if GlobalSettings().reference_compat:
+        return "reference_compat (bug-for-bug behaviours live in the Python handlers)"
     if type(sim).__name__ not in ("GossipSimulator", "TokenizedGossipSimulator"):
         return "simulator variant"
     if prt.active() and prt.transport() != "p2p":

@@ -761,6 +761,8 @@ class TokenizedGossipSimulator(GossipSimulator):
     def _native_supported(self) -> Optional[str]:
         if self.native_utility is None:
             return "utility_fun is a Python callback (set native_utility to a constant to go native)"
+        if GlobalSettings().reference_compat:
+            return "reference_compat mimics B4 in the Python loop only"
         return super()._native_supported()
 
     def _configure_scheduler(self, sch) -> None:
