@@ -60,16 +60,42 @@ def _labels_np(y: Any) -> np.ndarray:
     return y.detach().cpu().numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
 
 
+class _GlobalNumpyStream:
+    """The legacy global NumPy stream behind the few ``Generator`` methods the strategies use."""
+
+    permutation = staticmethod(np.random.permutation)
+    power = staticmethod(np.random.power)
+    shuffle = staticmethod(np.random.shuffle)
+    choice = staticmethod(np.random.choice)
+    dirichlet = staticmethod(np.random.dirichlet)
+
+    @staticmethod
+    def integers(low: int, high: int) -> int:
+        return int(np.random.randint(low, high))
+
+
 class AssignmentHandler:
     """Strategies mapping samples to ``n`` clients (ref ``data/__init__.py:164-373``).
 
     Every strategy returns a list of ``n`` index arrays.  Draws come from a private
     ``numpy`` Generator seeded with ``seed`` (the reference reseeds the *global* numpy/torch
-    RNGs as a side effect, which silently couples data assignment to the simulation's RNG).
+    RNGs as a side effect, which silently couples data assignment to the simulation's RNG);
+    with ``GlobalSettings().reference_compat`` the reference's draws are issued in the reference's
+    order on the global streams instead, which reproduces its index sets for a given seed.
     """
 
     def __init__(self, seed: int) -> None:
-        self.rng = np.random.default_rng(seed)
+        from .. import GlobalSettings
+        self.compat = bool(GlobalSettings().reference_compat)
+        if self.compat:
+            # the reference re-seeds the GLOBAL torch / NumPy streams here and draws from the global NumPy stream
+            # (``data/__init__.py:166-168``); under ``reference_compat`` the strategies below issue the same draws in the
+            # same order, so a given seed yields the reference's index sets
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            self.rng: Any = _GlobalNumpyStream()
+        else:
+            self.rng = np.random.default_rng(seed)
 
     # -- IID ------------------------------------------------------------------------
     def uniform(self, y: Any, n: int) -> List[np.ndarray]:
@@ -99,11 +125,12 @@ class AssignmentHandler:
         yy = _labels_np(y)
         assert min_quantity > 0 and min_quantity * n <= len(yy)
         out: List[List[int]] = [[] for _ in range(n)]
-        for c in np.unique(yy):
-            ids = np.flatnonzero(yy == c)
-            assert len(ids) >= n, "Under represented class!"
-            owner = np.concatenate([self._power_law_owner(len(ids) - n, n, alpha), np.arange(n)])
-            self.rng.shuffle(owner)
+        classes = [np.flatnonzero(yy == c) for c in np.unique(yy)]
+        assert all(len(ids) >= n for ids in classes), "Under represented class!"
+        skew = [self._power_law_owner(len(ids) - n, n, alpha) for ids in classes]     # all power-law draws first ...
+        for ids, sk in zip(classes, skew):
+            owner = np.concatenate([sk, np.arange(n)])
+            self.rng.shuffle(owner)                                                   # ... then one shuffle per class
             for i in range(n):
                 out[i].extend(ids[owner == i].tolist())
         return [np.array(o, dtype=int) for o in out]
@@ -124,6 +151,9 @@ class AssignmentHandler:
                 break
             for c in missing:
                 u = int(self.rng.integers(0, n))
+                if self.compat:      # the reference overwrites a random slot (may evict the only holder of another class)
+                    picks[u][int(self.rng.integers(0, class_per_client))] = c
+                    continue
                 free = [s for s in range(class_per_client) if c not in picks[u]]
                 picks[u][int(self.rng.choice(free))] = c
         owner = np.zeros(len(yy), dtype=int)
@@ -138,20 +168,22 @@ class AssignmentHandler:
         assert beta > 0, "beta must be > 0"
         yy = _labels_np(y)
         owner = np.zeros(len(yy), dtype=int)
-        for c in np.unique(yy):
+        classes = np.unique(yy)
+        props = [self.rng.dirichlet([beta] * n) for _ in classes]         # all proportions first (one draw per class)
+        for c, p in zip(classes, props):
             ids = np.flatnonzero(yy == c)
             self.rng.shuffle(ids)
-            p = self.rng.dirichlet([beta] * n)
-            owner[ids[:n]] = np.arange(n)[:len(ids[:n])]
+            self.rng.shuffle(p)                                           # (exchangeable; the reference does it too)
             if len(ids) > n:
                 owner[ids[n:]] = self.rng.choice(n, size=len(ids) - n, p=p)
+            owner[ids[:n]] = np.arange(n)[:len(ids[:n])]
         return [np.flatnonzero(owner == i) for i in range(n)]
 
     def label_pathological_skew(self, y: Any, n: int,
                                 shards_per_client: int = 2) -> List[np.ndarray]:
         """McMahan et al.: sort by label, cut into ``n*shards_per_client`` shards, deal them."""
         yy = _labels_np(y)
-        order = np.argsort(yy, kind="stable")
+        order = np.argsort(yy) if self.compat else np.argsort(yy, kind="stable")    # (ties: the reference's default sort)
         n_shards = int(shards_per_client * n)
         shard = int(np.ceil(len(yy) / n_shards))
         deal = self.rng.permutation(n_shards)

@@ -101,3 +101,30 @@ def test_recsys_and_loaders_offline():
     assert xtr.shape == (64, 3, 32, 32) and float(xtr.min()) >= 0 and float(xtr.max()) <= 1
     (mtr, _), (mte, _) = synthetic.mnist_like(100, 20)
     assert mtr.shape == (100, 784) and mte.shape == (20, 784)
+
+
+@pytest.mark.parametrize("name,kw", [("uniform", {}), ("quantity_skew", dict(min_quantity=2, alpha=4.)),
+                                     ("classwise_quantity_skew", dict(min_quantity=2, alpha=4.)),
+                                     ("label_quantity_skew", dict(class_per_client=2)),
+                                     ("label_dirichlet_skew", dict(beta=.5)),
+                                     ("label_pathological_skew", dict(shards_per_client=2))])
+@pytest.mark.parametrize("n,seed", [(7, 42), (10, 42), (10, 7)])
+def test_assignment_strategies_reproduce_the_reference_splits_in_compat_mode(ref, name, kw, n, seed):
+    """``reference_compat``: same seed -> the reference's index sets, element for element (and the same side effect
+    on the global streams); the default draws from a private generator instead."""
+    import gossipy.data as RD
+    import gossipy_b200 as g
+    import gossipy_b200.data as OD
+    y = torch.randint(0, 10, (1000,), generator=torch.Generator().manual_seed(0))
+    g.GlobalSettings().reference_compat = True
+    ours = getattr(OD.AssignmentHandler(seed), name)(y, n, **kw)
+    probe_o = (float(np.random.rand()), float(torch.rand(1)))
+    theirs = getattr(RD.AssignmentHandler(seed), name)(y, n, **kw)
+    probe_r = (float(np.random.rand()), float(torch.rand(1)))
+    assert len(ours) == len(theirs) == n
+    for a, b in zip(ours, theirs):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    assert probe_o == probe_r                      # the global streams end in the same state
+    g.GlobalSettings().reference_compat = False
+    other = getattr(OD.AssignmentHandler(seed), name)(y, n, **kw)
+    assert sorted(len(a) for a in other) != [] and sum(len(a) for a in other) <= 1000
