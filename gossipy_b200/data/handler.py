@@ -38,10 +38,22 @@ class ClassificationDataHandler(DataHandler):
         if test_size > 0 and (X_te is None or y_te is None):
             n = X.shape[0]
             n_te = int(round(n * test_size))
-            order = np.random.default_rng(seed).permutation(n)
-            tr_ids, te_ids = order[:n - n_te], order[n - n_te:]
-            self.Xtr, self.ytr = _take(X, tr_ids), _take(y, tr_ids)
-            self.Xte, self.yte = _take(X, te_ids), _take(y, te_ids)
+            from .. import GlobalSettings
+            if GlobalSettings().reference_compat and not isinstance(X, torch.Tensor):
+                # arrays: the reference delegates to scikit-learn (data/handler.py:69-72)
+                from sklearn.model_selection import train_test_split
+                self.Xtr, self.Xte, self.ytr, self.yte = train_test_split(X, y, test_size=test_size, random_state=seed,
+                                                                          shuffle=True)
+            else:
+                if GlobalSettings().reference_compat:
+                    # tensors: the reference re-seeds torch's GLOBAL stream and cuts a randperm (data/handler.py:60-67)
+                    torch.manual_seed(seed)
+                    order = torch.randperm(n).numpy()
+                else:
+                    order = np.random.default_rng(seed).permutation(n)
+                tr_ids, te_ids = order[:n - n_te], order[n - n_te:]
+                self.Xtr, self.ytr = _take(X, tr_ids), _take(y, tr_ids)
+                self.Xte, self.yte = _take(X, te_ids), _take(y, te_ids)
         else:
             self.Xtr, self.ytr = X, y
             self.Xte, self.yte = X_te, y_te

@@ -128,3 +128,27 @@ def test_assignment_strategies_reproduce_the_reference_splits_in_compat_mode(ref
     g.GlobalSettings().reference_compat = False
     other = getattr(OD.AssignmentHandler(seed), name)(y, n, **kw)
     assert sorted(len(a) for a in other) != [] and sum(len(a) for a in other) <= 1000
+
+
+def test_train_test_split_and_auto_assignment_reproduce_the_reference_in_compat_mode(ref):
+    import gossipy.data as RD
+    import gossipy.data.handler as RH
+    import gossipy_b200 as g
+    import gossipy_b200.data as OD
+    import gossipy_b200.data.handler as OH
+    gen = torch.Generator().manual_seed(0)
+    X = torch.randn(200, 5, generator=gen)
+    y = torch.randint(0, 3, (200,), generator=gen)
+    g.GlobalSettings().reference_compat = True
+    for ts, seed in ((.2, 42), (.3, 7)):
+        a = OH.ClassificationDataHandler(X, y, test_size=ts, seed=seed)
+        b = RH.ClassificationDataHandler(X, y, test_size=ts, seed=seed)
+        for p, q in ((a.Xtr, b.Xtr), (a.ytr, b.ytr), (a.Xte, b.Xte), (a.yte, b.yte)):
+            assert torch.equal(p, q)
+    a = OH.ClassificationDataHandler(X.numpy(), y.numpy(), test_size=.25, seed=3)
+    b = RH.ClassificationDataHandler(X.numpy(), y.numpy(), test_size=.25, seed=3)
+    assert np.array_equal(a.Xtr, b.Xtr) and np.array_equal(a.yte, b.yte)
+    a = OD.DataDispatcher(OH.ClassificationDataHandler(X, y, X[:40], y[:40]), n=7, eval_on_user=True, auto_assign=True)
+    b = RD.DataDispatcher(RH.ClassificationDataHandler(X, y, X[:40], y[:40]), n=7, eval_on_user=True, auto_assign=True)
+    for p, q in list(zip(a.tr_assignments, b.tr_assignments)) + list(zip(a.te_assignments, b.te_assignments)):
+        assert np.array_equal(np.asarray(p), np.asarray(q))
