@@ -7,7 +7,8 @@ of :mod:`gossipy_b200.data.synthetic` (``load_*`` fall back to them automaticall
 
 Environment: ``GOSSIPY_ROUNDS`` (override the number of rounds), ``GOSSIPY_NODES`` (cap the number
 of nodes), ``GOSSIPY_ENGINE=native|python`` (round-loop control plane), ``GOSSIPY_EXECUTOR=native``
-(with the native engine: enqueue eligible simulations from the C++ executor), ``GOSSIPY_DEVICE``.
+(with the native engine: enqueue eligible simulations from the C++ executor), ``GOSSIPY_DEVICE``,
+``GOSSIPY_COMPAT=1`` (``reference_compat``: reproduce the reference's numbers, Python engine).
 Multi-GPU: launch with ``python -m torch.distributed.run --nproc-per-node N examples/<script>.py``.
 """
 import os
@@ -31,6 +32,7 @@ def setup(seed: int):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dev = "cuda:%d" % torch.cuda.current_device()
     GlobalSettings().set_device(dev)
+    GlobalSettings().reference_compat = os.environ.get("GOSSIPY_COMPAT", "0") == "1"   # the reference's own numbers
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -609,3 +609,41 @@ def test_minibatch_training_matches_reference_exactly(ref, net_kind, bs, epochs,
     _assert_same_run(ours, theirs, tol=1e-9)
     assert [int(ours.sim.nodes[i].model_handler.n_updates) for i in range(4)] == \
         [int(theirs.sim.nodes[i].model_handler.n_updates) for i in range(4)]
+
+
+def test_whole_script_pipeline_matches_reference_in_compat_mode(ref):
+    """A reference-style experiment script end to end with NOTHING pinned by the test: ``set_seed``, the handler's own
+    train/test split, the dispatcher's auto-assignment, node clocks, weight initialisation, mini-batch shuffles, the
+    tokenized partitioned simulation of main_hegedus_2021 with churn.  Under ``reference_compat`` the two frameworks
+    print the same report."""
+    g.GlobalSettings().reference_compat = True
+    gen = torch.Generator().manual_seed(3)
+    X = torch.randn(600, 12, generator=gen)
+    y = (X @ torch.randn(12, 2, generator=gen)).argmax(1)
+    out = []
+    for ns, root in ((_ns(), g), (_ns(ref), ref)):
+        root.set_seed(98765)
+        dh = ns["data_handler"].ClassificationDataHandler(X, y, test_size=.1)
+        disp = ns["data"].DataDispatcher(dh, n=20, eval_on_user=False, auto_assign=True)
+        topo = ns["core"].StaticP2PNetwork(20, None)
+        net = ns["nn"].LogisticRegression(12, 2)
+        proto = ns["handler"].PartitionedTMH(net=net, tm_partition=ns["sampling"].TorchModelPartition(net, 4),
+                                             optimizer=torch.optim.SGD, optimizer_params={"lr": 1, "weight_decay": .001},
+                                             criterion=CE, batch_size=8, local_epochs=1,
+                                             create_model_mode=ns["core"].CreateModelMode.MERGE_UPDATE)
+        nodes = ns["node"].PartitioningBasedNode.generate(data_dispatcher=disp, p2p_net=topo, model_proto=proto,
+                                                          round_len=20, sync=False)
+        sim = ns["simul"].TokenizedGossipSimulator(nodes=nodes, data_dispatcher=disp,
+                                                   token_account=ns["fc"].RandomizedTokenAccount(C=20, A=10),
+                                                   utility_fun=lambda mh1, mh2, msg: 1, delta=20,
+                                                   protocol=ns["core"].AntiEntropyProtocol.PUSH,
+                                                   delay=ns["core"].UniformDelay(0, 5), online_prob=.6, drop_prob=.1,
+                                                   sampling_eval=.2)
+        if hasattr(sim, "progress"):
+            sim.progress = False
+        rep = ns["simul"].SimulationReport()
+        sim.add_receiver(rep)
+        sim.init_nodes(seed=42)
+        sim.start(n_rounds=6)
+        out.append(rep)
+    _assert_same_run(out[0], out[1], tol=1e-9)
