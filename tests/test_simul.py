@@ -36,12 +36,12 @@ def _assign(n_nodes, n=400):
 
 
 def _build(ns, n_nodes, proto_fn, node_cls="GossipNode", sim_cls="GossipSimulator", sync=True,
-           protocol="PUSH", sim_kw=None, node_kw=None, seed=5, topo=None):
+           protocol="PUSH", sim_kw=None, node_kw=None, seed=5, topo=None, eval_on_user=False):
     """Build the same experiment in namespace ``ns`` (ours or the reference)."""
     Xtr, ytr, Xte, yte = _dataset()
     dh = ns["data_handler"].ClassificationDataHandler(Xtr, ytr, Xte, yte)
-    disp = ns["data"].DataDispatcher(dh, n=n_nodes, eval_on_user=False, auto_assign=False)
-    disp.set_assignments(_assign(n_nodes), None)
+    disp = ns["data"].DataDispatcher(dh, n=n_nodes, eval_on_user=eval_on_user, auto_assign=False)
+    disp.set_assignments(_assign(n_nodes), _assign(n_nodes, 80) if eval_on_user else None)
     net = ns["core"].StaticP2PNetwork(n_nodes, topo)
     random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
     nodes = getattr(ns["node"], node_cls).generate(disp, net, proto_fn(ns), round_len=10, sync=sync,
@@ -281,15 +281,27 @@ def test_random_setups_match_reference(ref):
     @given(protocol=st.sampled_from(["PUSH", "PULL", "PUSH_PULL"]),
            mode=st.sampled_from(["MERGE_UPDATE", "UPDATE", "UPDATE_MERGE", "PASS"]), sync=st.booleans(),
            drop=st.sampled_from([0., .3]), online=st.sampled_from([1., .6]), delay=st.sampled_from([0, 4]),
-           samp=st.sampled_from([0., .4]), n_nodes=st.sampled_from([4, 8]), rounds=st.integers(2, 4))
-    def check(protocol, mode, sync, drop, online, delay, samp, n_nodes, rounds):
+           samp=st.sampled_from([0., .4]), n_nodes=st.sampled_from([4, 8]), rounds=st.integers(2, 4),
+           local_eval=st.booleans(), ring=st.booleans(), linear_delay=st.booleans())
+    def check(protocol, mode, sync, drop, online, delay, samp, n_nodes, rounds, local_eval, ring, linear_delay):
         CACHE.clear()
         g.GlobalSettings().reference_compat = True
+        topo = None
+        if ring:
+            topo = np.zeros((n_nodes, n_nodes))
+            for i in range(n_nodes):
+                topo[i, (i + 1) % n_nodes] = topo[i, (i - 1) % n_nodes] = 1
+
+        def delay_of(ns):
+            if not delay:
+                return ns["core"].ConstantDelay(0)
+            return ns["core"].LinearDelay(.1, 1) if linear_delay else ns["core"].UniformDelay(0, delay)
         ours, theirs = _run_both(ref, rounds=rounds, n_nodes=n_nodes, proto_fn=_logreg_proto(mode=mode), protocol=protocol,
-                                 sync=sync,
+                                 sync=sync, topo=topo, eval_on_user=local_eval,
                                  sim_kw=lambda ns: dict(drop_prob=drop, online_prob=online, sampling_eval=samp,
-                                                        delay=ns["core"].UniformDelay(0, delay) if delay
-                                                        else ns["core"].ConstantDelay(0)))
+                                                        delay=delay_of(ns)))
+        lo, lr_ = ours.get_evaluation(True), theirs.get_evaluation(True)
+        assert [t for t, _ in lo] == [t for t, _ in lr_]
         assert (ours._sent_messages, ours._failed_messages, ours._total_size) == \
             (theirs._sent_messages, theirs._failed_messages, theirs._total_size)
         eo, er = ours.get_evaluation(False), theirs.get_evaluation(False)
@@ -302,14 +314,14 @@ def test_random_setups_match_reference(ref):
         #       lossy runs (leaked entries).  One message per node and round (sync clocks, no delay, no loss) rules it out.
         # MERGE_UPDATE never mutates a received handler and its key changes with every update: always comparable.
         lossy = drop > 0 or online < 1
-        one_per_round = sync and not lossy and delay == 0
-        if mode in ("UPDATE", "UPDATE_MERGE"):
-            one_per_round = one_per_round and protocol == "PUSH"      # two pulls answered by one node in a round share a key
+        # (a reply is a second in-flight message of the responder: two pulls answered by one node share a key, and so do a
+        # node's own request and its reply within a tick)
+        one_per_round = sync and not lossy and delay == 0 and protocol == "PUSH"
         if not (mode == "MERGE_UPDATE" or one_per_round):
             return
         assert [int(ours.sim.nodes[i].model_handler.n_updates) for i in range(n_nodes)] == \
             [int(theirs.sim.nodes[i].model_handler.n_updates) for i in range(n_nodes)]
-        for (_, a), (_, b) in zip(eo, er):
+        for (_, a), (_, b) in list(zip(eo, er)) + list(zip(lo, lr_)):
             for k in b:
                 assert a[k] == pytest.approx(float(b[k]), abs=2.5 / (80 * n_nodes)), (k, protocol, mode)   # <= 2 borderline samples
     check()
