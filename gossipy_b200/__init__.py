@@ -300,7 +300,12 @@ class Cache:
 
     def clear(self) -> None:
         for item in self._cache.values():
-            _release(item.get())
+            value = item.get()
+            try:  # force: the entries die with the cache whatever their reference counts say
+                value._cache_refs = 0
+            except AttributeError:
+                pass
+            _release(value)
         self._cache.clear()
 
     def __getitem__(self, key: CacheKey) -> Any:

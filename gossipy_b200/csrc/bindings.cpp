@@ -341,6 +341,15 @@ at::Tensor tc_probe2(at::Tensor A, at::Tensor Bm, bool a_sw, bool b_sw) {
     return D;
 }
 
+std::vector<at::Tensor> tc_probe3(at::Tensor A, int64_t reps, int64_t cols) {
+    TORCH_CHECK(A.size(0) == 128 && A.size(1) == 8 && cols % 64 == 0 && cols <= 192);
+    auto D = at::zeros({128, 16}, A.options());
+    auto T = at::zeros({8}, A.options());
+    launch_tc_probe3(A.data_ptr<float>(), D.data_ptr<float>(), T.data_ptr<float>(), (int)reps, (int)cols, cur_stream());
+    GB_LAUNCH_CHECK();
+    return {D, T};
+}
+
 // ---- bank of linear learners ----------------------------------------------------------------------------
 static BankView bank_view(at::Tensor W, at::Tensor age, at::Tensor S, at::Tensor slot_age, at::Tensor X, at::Tensor y,
                           at::Tensor off, at::Tensor cnt, int64_t D, int64_t kind, int64_t mode, double lr) {
@@ -501,6 +510,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("bank_scores", &gb::bank_scores);
     m.def("tc_probe", &gb::tc_probe);
     m.def("tc_probe2", &gb::tc_probe2);
+    m.def("tc_probe3", &gb::tc_probe3);
     m.def("ipc_alloc", &gb::ipc_alloc);
     m.def("ipc_free", &gb::ipc_free);
     m.def("ipc_get_handle", &gb::ipc_get_handle);

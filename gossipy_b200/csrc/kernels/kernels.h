@@ -124,6 +124,8 @@ void launch_tc_probe(const float* A, const float* Bm, float* D, int K, int N, in
 void launch_tc_probe2(const float* A, const float* Bm, float* D, int M, int N, int K, int a_sw, int b_sw,
                       cudaStream_t stream);
 
+void launch_tc_probe3(const float* A, float* D, float* timing, int reps, int cols, cudaStream_t stream);
+
 int sm_count();
 // load every kernel of the extension on the current device (see merge.cu: preload_merge)
 void preload_merge(); void preload_optim(); void preload_small(); void preload_eval();

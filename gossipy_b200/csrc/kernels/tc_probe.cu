@@ -142,6 +142,96 @@ void launch_tc_probe2(const float* A, const float* Bm, float* D, int M, int N, i
     tc_probe2_kernel<<<1, 128, smem, stream>>>(A, Bm, D, M, N, K, a_sw, b_sw);
 }
 
+
+// Third probe (round 2): (a) how does a TS-mode kind::tf32 MMA narrow an fp32 A operand read from TMEM
+// (truncate or round)?  D[j][n] = tf32(A[j][n]) through an identity B;  (b) cycles of a TMEM -> registers ->
+// TMEM pass over `cols` columns per lane with 8 warps (the hi/lo re-split of the 3xTF32 training kernel).
+__global__ void __launch_bounds__(256, 1)
+tc_probe3_kernel(const float* __restrict__ A, float* __restrict__ D, float* __restrict__ timing, int reps, int cols) {
+    __shared__ __align__(1024) float b_s[16 * 8];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tslot;
+    const int tid = threadIdx.x, warp = tid >> 5, quad = warp & 3, half = warp >> 2, lane = tid & 31;
+    const int j = quad * 32 + lane;
+    if (warp == 0) tmem_alloc<512>(&tslot);
+    if (tid == 0) { mbar_init(&mbar, 1); mbar_fence_init(); }
+    if (tid < 128) { const int n = tid >> 3, k = tid & 7; b_s[((n / 8) * 2 + k / 4) * 32 + (n % 8) * 4 + (k % 4)] = (n == k) ? 1.f : 0.f; }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tslot, 0);
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    if (half == 0) {
+        float v[16];
+        for (int i = 0; i < 16; ++i) v[i] = i < 8 ? A[j * 8 + i] : 0.f;
+        tmem_st16(tlane + 0, v);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(kFmtTF32, kFmtTF32, 128, 16, false, false);
+            mma_tf32_ts(tmem + 32, tmem + 0, make_sdesc(smem_u32(b_s), 128u, 256u), idesc, false);
+            mma_commit(&mbar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&mbar, 0);
+    tc_fence_after();
+    if (half == 0) {
+        float v[16];
+        tmem_ld16(tlane + 32, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) D[j * 16 + i] = v[i];
+    }
+    __syncthreads();
+    // (b) timing: variant 0 = ld16 only, 1 = ld16 + lo + st16, 2 = ld32 + lo + 2 x st16
+    const int per = cols / 2;                       // columns per thread (half of the lane's columns)
+    for (int variant = 0; variant < 3; ++variant) {
+        __syncthreads();
+        const long long t0 = clock64();
+        float sink = 0.f;
+        for (int r = 0; r < reps; ++r) {
+            if (variant < 2) {
+                for (int c = 0; c < per; c += 16) {
+                    float v[16];
+                    tmem_ld16(tlane + 64 + half * per + c, v);
+                    tmem_ld_wait();
+                    if (variant == 0) { for (int i = 0; i < 16; ++i) sink += v[i]; }
+                    else {
+                        for (int i = 0; i < 16; ++i) v[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xffffe000u);
+                        tmem_st16(tlane + 64 + 208 + half * per + c, v);
+                    }
+                }
+            } else {
+                for (int c = 0; c < per; c += 32) {
+                    float v[32];
+                    tmem_ld32(tlane + 64 + half * per + c, v);
+                    tmem_ld_wait();
+                    for (int i = 0; i < 32; ++i) v[i] = v[i] - __uint_as_float(__float_as_uint(v[i]) & 0xffffe000u);
+                    tmem_st16(tlane + 64 + 208 + half * per + c, v);
+                    tmem_st16(tlane + 64 + 208 + half * per + c + 16, v + 16);
+                }
+            }
+            if (variant > 0) tmem_st_wait();
+        }
+        __syncthreads();
+        const long long t1 = clock64();
+        if (tid == 0) timing[variant] = (float)((double)(t1 - t0) / (double)reps);
+        if (sink == 123.456f) timing[7] = sink;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+void launch_tc_probe3(const float* A, float* D, float* timing, int reps, int cols, cudaStream_t stream) {
+    tc_probe3_kernel<<<1, 256, 0, stream>>>(A, D, timing, reps, cols);
+}
+
 // force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
 // on a cross-GPU flag could deadlock, so the extension loads everything up front)
 void preload_probe() {

@@ -28,7 +28,7 @@ class Row:
     """
 
     __slots__ = ("arena", "index", "tensor", "ready", "consumed", "stream", "rank", "gen",
-                 "remote_reads", "flag_ready", "flag_done", "_acked")
+                 "remote_reads", "flag_ready", "flag_done", "_acked", "in_use")
 
     def __init__(self, arena: "RowArena", index: int, tensor: Optional[torch.Tensor]) -> None:
         self.arena = arena
@@ -43,6 +43,7 @@ class Row:
         self.flag_ready = 0      # device address of the owner's `ready` flag (p2p transport)
         self.flag_done = 0       # device address of the owner's `done` counter
         self._acked = 0          # remote reads already waited for (owner side)
+        self.in_use = False      # set by alloc, cleared by free (double-free guard)
 
     def release(self) -> None:
         self.arena.free(self)
@@ -83,6 +84,7 @@ class RowArena:
         if not self._free:
             self._grow()
         row = self._free.pop(0)
+        row.in_use = True
         self.live += 1
         self.high_water = max(self.high_water, self.live)
         return row
@@ -90,6 +92,10 @@ class RowArena:
     def free(self, row: Row) -> None:
         if row.index < 0:
             return
+        if not row.in_use:
+            # a second free would put the row on the free list twice and hand it to two handlers
+            raise RuntimeError("arena row %d freed twice" % row.index)
+        row.in_use = False
         self.live -= 1
         self._free.append(row)  # FIFO reuse: pending readers have usually long finished
 

@@ -433,6 +433,9 @@ class RowHandler(ModelHandler):
     def _clone_shell(self) -> "RowHandler":
         new = object.__new__(self.__class__)
         new.__dict__.update(self.__dict__)
+        # the refcount stamped by CacheItem belongs to the in-flight snapshot, never to its clones
+        # (a clone that inherited it would refuse to release its row: unbounded arena growth)
+        new.__dict__.pop("_cache_refs", None)
         new._row = None
         new.n_updates = copy.copy(self.n_updates)
         return new

@@ -313,7 +313,13 @@ def kmeans_update(C: torch.Tensor, X: torch.Tensor, alpha: float) -> None:
     *incoming* centroids and, for samples sharing a centroid, the last one winning -- i.e. exactly
     the reference's batched indexing statement (``handler.py:604-615``)."""
     idx = kmeans_assign(C, X)
-    C[idx] = C[idx] * (1 - alpha) + alpha * X
+    # `C[idx] = C[idx] * (1 - alpha) + alpha * X` leaves the winner among duplicate indices to the
+    # indexing kernel (thread-count dependent on CPU); "last sample wins" is made explicit here
+    n, k = X.shape[0], C.shape[0]
+    winner = torch.full((k,), -1, dtype=torch.long, device=C.device)
+    winner.scatter_reduce_(0, idx, torch.arange(n, device=C.device), "amax")
+    sel = winner >= 0
+    C[sel] = C[sel] * (1 - alpha) + alpha * X[winner[sel]]
 
 
 @torch.no_grad()
