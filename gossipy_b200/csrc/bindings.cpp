@@ -24,8 +24,9 @@ static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream(); }
 // (ready flag address, generation, done counter address); zeros = no cross-GPU handshake
 using Sync = std::tuple<int64_t, int64_t, int64_t>;
 static PeerSync to_sync(const c10::optional<Sync>& s) {
-    PeerSync p{nullptr, 0u, nullptr};
+    PeerSync p{nullptr, 0u, nullptr, nullptr};
     if (s.has_value()) {
+        p.fault = device_fault_word();
         p.ready = reinterpret_cast<const uint32_t*>((uintptr_t)std::get<0>(*s));
         p.gen = (uint32_t)std::get<1>(*s);
         p.done = reinterpret_cast<uint32_t*>((uintptr_t)std::get<2>(*s));
@@ -153,7 +154,10 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
     }
     c10::cuda::CUDAGuard guard(row.device());
     const TrainImpl which = impl == "cluster" ? kTrainCluster : impl == "tc" ? kTrainTc
-                            : impl == "tc2" ? kTrainTc2 : impl == "tc3" ? kTrainTc3 : kTrainAuto;
+                            : impl == "tc2" ? kTrainTc2 : impl == "tc3" ? kTrainTc3
+                            : impl == "tc4" ? kTrainTc4 : impl == "tc4-tf32" ? kTrainTc4Tf32
+                            : impl == "tc8" ? kTrainTc8 : impl == "tc8-tf32" ? kTrainTc8Tf32 : kTrainAuto;
+    TORCH_CHECK(which != kTrainAuto || impl.empty() || impl == "auto", "unknown training kernel '", impl, "'");
     const char* why = "";
     const bool ok = launch_mlp1_train(p, which, cur_stream(), &why);
     TORCH_CHECK(ok, why, " (in=", p.IN, " hidden=", p.H, " out=", p.OUT, " batch=", p.B, ")");
@@ -463,9 +467,25 @@ void allreduce_mean(at::Tensor out, int64_t mc_ptr, std::vector<int64_t> buf_ptr
     GB_LAUNCH_CHECK();
 }
 int64_t device_sm_count() { return sm_count(); }
+// the current device's fault word (bits: kernels.h) -- read (and cleared) with one small D2H copy; the simulator
+// checks it whenever it reads a round's metrics
+int64_t device_fault(bool clear) {
+    uint32_t v = 0;
+    uint32_t* w = device_fault_word();
+    cudaMemcpy(&v, w, sizeof(v), cudaMemcpyDeviceToHost);
+    if (clear && v != 0) cudaMemset(w, 0, sizeof(v));
+    return (int64_t)v;
+}
+// pre-size the staging buffer of the CURRENT stream for the fused MLP training kernel (init_nodes)
+bool reserve_mlp1_staging(int64_t n, int64_t in_dim, int64_t batch_size, int64_t local_epochs, std::string impl) {
+    const int B = (int)(batch_size == 0 ? n : std::min<int64_t>(batch_size, n));
+    const int nc = (impl == "tc8" || impl == "tc8-tf32") ? 8 : 4;
+    const bool x3 = !(impl == "tc4-tf32" || impl == "tc8-tf32");
+    return reserve_train_staging((int)n, (int)in_dim, B, (int)local_epochs, nc, x3, cur_stream());
+}
 void preload() {
     preload_merge(); preload_optim(); preload_small(); preload_eval(); preload_train_cluster();
-    preload_train_tc(); preload_train_tc2(); preload_train_tc3(); preload_stage(); preload_probe(); preload_nvls(); preload_eval_tc(); preload_bank();
+    preload_train_tc(); preload_train_tc2(); preload_train_tc3(); preload_train_tc4(); preload_stage(); preload_probe(); preload_nvls(); preload_eval_tc(); preload_bank();
     cudaGetLastError();
 }
 
@@ -522,6 +542,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("flag_add", &gb::flag_add);
     m.def("device_sm_count", &gb::device_sm_count);
     m.def("preload", &gb::preload);
+    m.def("device_fault", &gb::device_fault, py::arg("clear") = true);
+    m.def("reserve_mlp1_staging", &gb::reserve_mlp1_staging);
     m.def("allreduce_mean", &gb::allreduce_mean);
     gb::bind_scheduler(m);
     gb::bind_executor(m);

@@ -240,7 +240,7 @@ private:
                 if (sl.has_reader) cuda_check(cudaStreamWaitEvent(nd.stream, sl.read, 0), "wait for the slot's last reader");
                 if (sl.written) cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the slot's last writer");
                 if (sl.remote_reads != sl.acked) launch_flag_wait(sl.done, sl.remote_reads, nd.stream);
-                launch_merge_pair(sl.data, nd.row, 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr}, nd.stream);
+                launch_merge_pair(sl.data, nd.row, 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr, nullptr}, nd.stream);
                 if (!sl.written) cuda_check(cudaEventCreateWithFlags(&sl.written, cudaEventDisableTiming), "event");
                 cuda_check(cudaEventRecord(sl.written, nd.stream), "record slot written");
                 if (world_ > 1) launch_flag_signal(sl.ready, sl.gen, nd.stream);
@@ -293,9 +293,9 @@ private:
         const bool exec = mine(node);
         const bool remote = world_ > 1 && rk != owner_[node];      // the snapshot lives on another rank than the reader
         if (remote) sl.remote_reads += 1;                           // replicated: the owner will wait for this many acks
-        PeerSync sync{nullptr, 0, nullptr};
+        PeerSync sync{nullptr, 0, nullptr, nullptr};
         if (exec && cuda_) {
-            if (remote) sync = PeerSync{sl.ready, sl.gen, sl.done};
+            if (remote) sync = PeerSync{sl.ready, sl.gen, sl.done, device_fault_word()};
             else if (sl.written)                                // (a slot restored from a checkpoint has no writer event)
                 cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
         }

@@ -82,6 +82,24 @@ GB_DEVICE uint32_t gb_ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
+// Bounded wait for a row's `ready` generation (cross-GPU handshake).  A lost publish must not hang the
+// GPU forever: after ~30 s the waiter records fault bit 1 in `fault` (host-visible, checked with the
+// metrics of every round) and carries on with whatever the row holds.
+GB_DEVICE uint64_t gb_globaltimer() { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+constexpr uint64_t GB_WAIT_NS = 30ull * 1000ull * 1000ull * 1000ull;
+GB_DEVICE void gb_wait_flag(const uint32_t* flag, uint32_t gen, uint32_t* fault, uint32_t code = 1u) {
+    if ((int32_t)(gb_ld_acquire_sys(flag) - gen) >= 0) return;
+    const uint64_t t0 = gb_globaltimer();
+    unsigned it = 0;
+    while ((int32_t)(gb_ld_acquire_sys(flag) - gen) < 0) {
+        __nanosleep(40);
+        if ((++it & 1023u) == 0u && gb_globaltimer() - t0 > GB_WAIT_NS) {
+            if (fault != nullptr) atomicOr(fault, code);
+            return;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // thread-block cluster helpers (raw PTX, no cooperative_groups dependency)
 // ---------------------------------------------------------------------------------------------

@@ -16,7 +16,11 @@ struct PeerSync {
     const uint32_t* ready;   // flag in the OWNER's memory (may be peer-mapped)
     uint32_t gen;
     uint32_t* done;          // read counter in the OWNER's memory (may be peer-mapped)
+    uint32_t* fault;         // this device's fault word (bounded waits report here; see device_fault_word())
 };
+// one word per device, zero-initialised; bit 1: a wait for a `ready` generation timed out, bit 2: an all-reduce
+// epoch wait timed out, bit 4: the ticket ring of the stand-alone flag operations overflowed
+uint32_t* device_fault_word();
 
 // ---- merge.cu ------------------------------------------------------------------------------------
 void launch_merge_pair(float* dst, const float* src, float w_dst, float w_src, int64_t lo, int64_t hi,
@@ -62,12 +66,17 @@ struct TrainParams {
     // (the peer row is pulled over NVLink while the weights are loaded on chip)
     const float* peer; float w_self, w_peer; PeerSync sync;
 };
-enum TrainImpl { kTrainAuto = 0, kTrainCluster = 1, kTrainTc = 2, kTrainTc2 = 3, kTrainTc3 = 4 };
+enum TrainImpl { kTrainAuto = 0, kTrainCluster = 1, kTrainTc = 2, kTrainTc2 = 3, kTrainTc3 = 4,
+                 kTrainTc4 = 5, kTrainTc4Tf32 = 6, kTrainTc8 = 7, kTrainTc8Tf32 = 8 };
 // returns false when the shape is outside the envelope of the requested implementation
 bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const char** why);
 bool mlp1_train_tc(const TrainParams& p, cudaStream_t stream);     // first generation (in-kernel gather)
 bool mlp1_train_tc2(const TrainParams& p, cudaStream_t stream);    // staged operands, 256 threads
 bool mlp1_train_tc3(const TrainParams& p, cudaStream_t stream);    // tc2 + second layer on the tensor core
+// fourth generation: nc-CTA cluster (4 or 8), x3 = error-compensated 3xTF32 products (fp32-equivalent)
+bool mlp1_train_tc4(const TrainParams& p, int nc, bool x3, cudaStream_t stream);
+bool reserve_train_staging(int n, int IN, int B, int epochs, int nc, bool x3, cudaStream_t stream);
+size_t mlp1_stage4_bytes(int n, int IN, int B, int epochs, int NC, bool x3, int* FPC_out, int* FP_out, int* steps_out);
 // device-side data loader of tc2: shuffled mini-batches in both UMMA operand layouts
 size_t mlp1_stage_bytes(int n, int IN, int B, int epochs, int* FPC_out, int* FP_out, int* steps_out);
 bool launch_mlp1_stage(const float* X, const int64_t* y, int n, int IN, int B, int epochs, uint64_t key,
@@ -129,7 +138,7 @@ void launch_tc_probe3(const float* A, float* D, float* timing, int reps, int col
 int sm_count();
 // load every kernel of the extension on the current device (see merge.cu: preload_merge)
 void preload_merge(); void preload_optim(); void preload_small(); void preload_eval();
-void preload_train_cluster(); void preload_train_tc(); void preload_train_tc2(); void preload_train_tc3(); void preload_stage();
+void preload_train_cluster(); void preload_train_tc(); void preload_train_tc2(); void preload_train_tc3(); void preload_train_tc4(); void preload_stage();
 void preload_probe();
 
 }  // namespace gb

@@ -22,26 +22,41 @@ constexpr int kMergeThreads = 256;
 constexpr int kUnroll = 4;  // 4 x 128-bit loads in flight per thread per operand (peer latency ~2 us)
 
 // ---- handshake helpers ---------------------------------------------------------------------------
-constexpr int kTickets = 4096;
+// Tickets: zero-initialised CTA-arrival counters, one per handshaking launch, returned to zero by the last
+// CTA.  The ring is far larger than the number of launches the host can run ahead (it waits for the metrics
+// of round r while it enqueues round r+1); should two in-flight launches ever share a ticket the arrival count
+// exceeds the grid size, which the kernels report as fault bit 4 instead of silently mis-acknowledging.
+constexpr int kTickets = 1 << 16;
 static uint32_t* g_tickets[16] = {nullptr};
 static uint32_t g_ticket_next[16] = {0};
+static uint32_t* g_fault[16] = {nullptr};
 
-// A zero-initialised CTA-arrival counter for one launch (returned to zero by the last CTA).
-static uint32_t* next_ticket() {
-    int dev = 0;
-    cudaGetDevice(&dev);
+// per-device scratch of the handshake protocol; allocated by preload_merge() (extension start-up), never on
+// the launch path: cudaMalloc is an implicit device-wide barrier and kernels of other GPUs may be spinning
+static void ensure_device_scratch(int dev) {
     if (g_tickets[dev] == nullptr) {
         cudaMalloc(&g_tickets[dev], kTickets * sizeof(uint32_t));
         cudaMemset(g_tickets[dev], 0, kTickets * sizeof(uint32_t));
+        cudaMalloc(&g_fault[dev], sizeof(uint32_t));
+        cudaMemset(g_fault[dev], 0, sizeof(uint32_t));
     }
+}
+static uint32_t* next_ticket() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    ensure_device_scratch(dev);
     return g_tickets[dev] + (g_ticket_next[dev]++ % kTickets);
+}
+uint32_t* device_fault_word() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    ensure_device_scratch(dev);
+    return g_fault[dev];
 }
 
 GB_DEVICE void peer_wait(const PeerSync& s) {
     if (s.ready != nullptr) {
-        if (threadIdx.x == 0) {
-            while ((int32_t)(gb_ld_acquire_sys(s.ready) - s.gen) < 0) __nanosleep(40);
-        }
+        if (threadIdx.x == 0) gb_wait_flag(s.ready, s.gen, s.fault);
         __syncthreads();
     }
 }
@@ -51,9 +66,12 @@ GB_DEVICE void peer_done(const PeerSync& s, uint32_t* ticket) {
         if (threadIdx.x == 0) {
             __threadfence();
             const uint32_t total = gridDim.x * gridDim.y;
-            if (atomicAdd(ticket, 1u) == total - 1u) {
+            const uint32_t seen = atomicAdd(ticket, 1u);
+            if (seen == total - 1u) {
                 *ticket = 0u;
                 gb_red_release_sys_add(s.done, 1u);
+            } else if (seen >= total && s.fault != nullptr) {
+                atomicOr(s.fault, 4u);               // ticket shared by two in-flight launches
             }
         }
     }
@@ -167,12 +185,13 @@ scatter_kernel(float* __restrict__ dst, const int64_t* __restrict__ idx, int64_t
 struct KwayArgs {
     const float* src[kMaxWay]; float w[kMaxWay]; float w0; int k;
     const uint32_t* ready[kMaxWay]; uint32_t gen[kMaxWay]; uint32_t* done[kMaxWay];
+    uint32_t* fault;
 };
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_kway_kernel(float* __restrict__ dst, const KwayArgs a, int64_t n, uint32_t* ticket) {
     if (threadIdx.x < a.k && a.ready[threadIdx.x] != nullptr) {
-        while ((int32_t)(gb_ld_acquire_sys(a.ready[threadIdx.x]) - a.gen[threadIdx.x]) < 0) __nanosleep(40);
+        gb_wait_flag(a.ready[threadIdx.x], a.gen[threadIdx.x], a.fault);
     }
     __syncthreads();
     const int64_t nvec = n / 4;
@@ -211,8 +230,8 @@ __global__ void flag_signal_kernel(uint32_t* flag, uint32_t value) {
     __threadfence_system();
     gb_st_release_sys(flag, value);
 }
-__global__ void flag_wait_kernel(const uint32_t* flag, uint32_t value) {
-    while ((int32_t)(gb_ld_acquire_sys(flag) - value) < 0) __nanosleep(64);   // flags only grow
+__global__ void flag_wait_kernel(const uint32_t* flag, uint32_t value, uint32_t* fault) {
+    gb_wait_flag(flag, value, fault);                                          // flags only grow
 }
 __global__ void flag_add_kernel(uint32_t* flag, uint32_t value) {
     __threadfence_system();
@@ -267,6 +286,7 @@ void launch_merge_kway(float* dst, const float* const* srcs, const float* weight
         KwayArgs a;
         a.k = std::min(kMaxWay, k - done);
         a.w0 = w0;
+        a.fault = device_fault_word();
         for (int j = 0; j < kMaxWay; ++j) { a.ready[j] = nullptr; a.done[j] = nullptr; a.gen[j] = 0; a.src[j] = nullptr; a.w[j] = 0.f; }
         for (int j = 0; j < a.k; ++j) {
             a.src[j] = srcs[done + j];
@@ -283,7 +303,7 @@ void launch_flag_signal(uint32_t* flag, uint32_t value, cudaStream_t stream) {
     flag_signal_kernel<<<1, 1, 0, stream>>>(flag, value);
 }
 void launch_flag_wait(const uint32_t* flag, uint32_t value, cudaStream_t stream) {
-    flag_wait_kernel<<<1, 1, 0, stream>>>(flag, value);
+    flag_wait_kernel<<<1, 1, 0, stream>>>(flag, value, device_fault_word());
 }
 void launch_flag_add(uint32_t* flag, uint32_t value, cudaStream_t stream) {
     flag_add_kernel<<<1, 1, 0, stream>>>(flag, value);
@@ -292,6 +312,7 @@ void launch_flag_add(uint32_t* flag, uint32_t value, cudaStream_t stream) {
 // force-load this file's kernels (CUDA loads functions lazily; loading one while another kernel spins
 // on a cross-GPU flag could deadlock, so the extension loads everything up front)
 void preload_merge() {
+    device_fault_word();
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, merge_pair_kernel);
     cudaFuncGetAttributes(&a, merge_segments_kernel);

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp1_train_cluster_kernel(const Tr
     // row being pulled (possibly over NVLink) while the weights are loaded on chip
     const bool merging = p.peer != nullptr;
     if (merging && p.sync.ready != nullptr) {
-        if (tid == 0) while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
+        if (tid == 0) gb_wait_flag(p.sync.ready, p.sync.gen, p.sync.fault);
         __syncthreads();
     }
     auto ldp = [&](size_t off) -> float {
@@ -337,22 +337,39 @@ static bool launch_cluster(const TrainParams& p, bool scaled, cudaStream_t strea
     return cudaLaunchKernelEx(&cfg, kern, q) == cudaSuccess;
 }
 
-static const bool g_default_tc3 = true;    // auto = tc3 -> tc2 -> tc -> cluster
-
+// auto = fp32-equivalent: tc4 (4-CTA cluster, 3xTF32 tcgen05) -> cluster kernel (fp32 CUDA cores).  The plain-tf32
+// variants (tc3, tc4-tf32, tc8-tf32) run only when asked for by name (GlobalSettings().allow_tf32 / impl=...).
 bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const char** why) {
     static const char* kNone = "";
     *why = kNone;
     const bool scaled = p.part_id != nullptr && p.ages != nullptr;
     if (scaled && p.n_parts > MAX_PARTS) { *why = "fused partitioned training supports <= 16 partitions"; return false; }
     if (impl != kTrainCluster && !scaled) {
-        if (impl == kTrainTc3 || (impl == kTrainAuto && g_default_tc3)) {
-            if (mlp1_train_tc3(p, stream)) return true;
-            if (impl == kTrainTc3) { *why = "tcgen05 (tc3) training kernel does not support this configuration"; return false; }
+        switch (impl) {
+        case kTrainTc4: case kTrainTc4Tf32: case kTrainTc8: case kTrainTc8Tf32: {
+            const int nc = (impl == kTrainTc8 || impl == kTrainTc8Tf32) ? 8 : 4;
+            const bool x3 = impl == kTrainTc8;
+            if (impl == kTrainTc4) { *why = "the fp32-equivalent tcgen05 kernel runs on 8-CTA clusters: use impl='tc8'"; return false; }
+            if (mlp1_train_tc4(p, nc, x3, stream)) return true;
+            *why = "tcgen05 (tc4) training kernel does not support this configuration";
+            return false;
         }
-        if (impl != kTrainTc && mlp1_train_tc2(p, stream)) return true;
-        if (impl == kTrainTc2) { *why = "tcgen05 (tc2) training kernel does not support this configuration"; return false; }
-        if (mlp1_train_tc(p, stream)) return true;
-        if (impl == kTrainTc) { *why = "tcgen05 training kernel does not support this configuration"; return false; }
+        case kTrainTc3:
+            if (mlp1_train_tc3(p, stream)) return true;
+            *why = "tcgen05 (tc3) training kernel does not support this configuration";
+            return false;
+        case kTrainTc2:
+            if (mlp1_train_tc2(p, stream)) return true;
+            *why = "tcgen05 (tc2) training kernel does not support this configuration";
+            return false;
+        case kTrainTc:
+            if (mlp1_train_tc(p, stream)) return true;
+            *why = "tcgen05 training kernel does not support this configuration";
+            return false;
+        default:
+            if (mlp1_train_tc4(p, 8, true, stream)) return true;
+            break;
+        }
     }
     if (!(p.IN % 4 == 0 && p.IN <= 1024 && p.OUT <= OUT_MAX && p.B <= 64 && p.H <= CMAX * SLOTS)) {
         *why = "mlp1_train(cluster): unsupported shape";

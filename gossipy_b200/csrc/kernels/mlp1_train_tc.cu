@@ -86,7 +86,7 @@ mlp1_train_tc_kernel(const TrainParams p, const int FPC /* real feature columns 
     // row being pulled (possibly over NVLink) while the master weights are loaded into TMEM
     const bool merging = p.peer != nullptr;
     if (merging && p.sync.ready != nullptr) {
-        if (tid == 0) while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
+        if (tid == 0) gb_wait_flag(p.sync.ready, p.sync.gen, p.sync.fault);
         __syncthreads();
     }
     auto ldp = [&](size_t off) -> float {

@@ -116,7 +116,7 @@ mlp1_train_tc3_kernel(const TrainParams p, const int FPC, const int FP, const in
     // acknowledges the read on the owner's `done` counter, and only then loads the weights on chip.
     if (p.peer != nullptr) {
         if (p.sync.ready != nullptr) {
-            if (tid == 0) while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
+            if (tid == 0) gb_wait_flag(p.sync.ready, p.sync.gen, p.sync.fault);
             __syncthreads();
         }
         const int64_t P = (int64_t)H * IN + H + (int64_t)OUT * H + OUT;

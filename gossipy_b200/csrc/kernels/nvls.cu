@@ -29,13 +29,12 @@ GB_DEVICE float4 multimem_ld_reduce_add(const float* mc_addr) {
 
 template <bool MULTICAST>
 __global__ void __launch_bounds__(kNvlsThreads)
-allreduce_mean_kernel(float* __restrict__ out, const AllReduceArgs a, int64_t n, uint32_t* ticket) {
+allreduce_mean_kernel(float* __restrict__ out, const AllReduceArgs a, int64_t n, uint32_t* ticket, uint32_t* fault) {
     const int tid = threadIdx.x;
     // ---- start barrier ------------------------------------------------------------------------------
     if (blockIdx.x == 0 && tid < a.world) gb_st_release_sys(a.flags[tid] + a.rank, a.epoch);        // ready[rank] @ peer tid
     if (tid < a.world) {
-        const uint32_t* mine = a.flags[a.rank] + tid;
-        while ((int32_t)(gb_ld_acquire_sys(mine) - a.epoch) < 0) __nanosleep(32);
+        gb_wait_flag(a.flags[a.rank] + tid, a.epoch, fault, 2u);
     }
     __syncthreads();
     // ---- reduce ---------------------------------------------------------------------------------------
@@ -65,8 +64,7 @@ allreduce_mean_kernel(float* __restrict__ out, const AllReduceArgs a, int64_t n,
             *ticket = 0u;
             for (int r = 0; r < a.world; ++r) gb_st_release_sys(a.flags[r] + a.world + a.rank, a.epoch);  // done[rank] @ peer r
             for (int r = 0; r < a.world; ++r) {
-                const uint32_t* d = a.flags[a.rank] + a.world + r;
-                while ((int32_t)(gb_ld_acquire_sys(d) - a.epoch) < 0) __nanosleep(32);
+                gb_wait_flag(a.flags[a.rank] + a.world + r, a.epoch, fault, 2u);
             }
         }
     }
@@ -87,13 +85,19 @@ bool launch_allreduce_mean(float* out, const AllReduceArgs& a, int64_t n, cudaSt
     int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((nvec + kNvlsThreads * 4 - 1) / (kNvlsThreads * 4),
                                                              (int64_t)sm_count()));
     if (a.mc != nullptr)
-        allreduce_mean_kernel<true><<<blocks, kNvlsThreads, 0, stream>>>(out, a, n, g_nvls_ticket[dev]);
+        allreduce_mean_kernel<true><<<blocks, kNvlsThreads, 0, stream>>>(out, a, n, g_nvls_ticket[dev], device_fault_word());
     else
-        allreduce_mean_kernel<false><<<blocks, kNvlsThreads, 0, stream>>>(out, a, n, g_nvls_ticket[dev]);
+        allreduce_mean_kernel<false><<<blocks, kNvlsThreads, 0, stream>>>(out, a, n, g_nvls_ticket[dev], device_fault_word());
     return true;
 }
 
 void preload_nvls() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_nvls_ticket[dev] == nullptr) {                 // not on the launch path (see merge.cu)
+        cudaMalloc(&g_nvls_ticket[dev], sizeof(uint32_t));
+        cudaMemset(g_nvls_ticket[dev], 0, sizeof(uint32_t));
+    }
     cudaFuncAttributes at;
     cudaFuncGetAttributes(&at, allreduce_mean_kernel<true>);
     cudaFuncGetAttributes(&at, allreduce_mean_kernel<false>);

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(LR_THREADS) logreg_train_kernel(const LogregPa
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = LR_THREADS / 32;
     if (p.peer != nullptr) {            // fused MERGE_UPDATE: start from w_self*row + w_peer*peer
         if (p.sync.ready != nullptr && tid == 0)
-            while ((int32_t)(gb_ld_acquire_sys(p.sync.ready) - p.sync.gen) < 0) __nanosleep(40);
+            gb_wait_flag(p.sync.ready, p.sync.gen, p.sync.fault);
         __syncthreads();
         for (int i = tid; i < P; i += LR_THREADS) W[i] = p.w_self * p.row[i] + p.w_peer * gb_ld_stream1(p.peer + i);
         __syncthreads();
