@@ -18,12 +18,13 @@
 // the receiver's mbarrier):
 //   RS: CTA c receives every CTA's partial sums of ITS 32/NC samples, adds them in a fixed order, applies bias + ReLU
 //       and -- owning complete hidden activations of those samples -- computes their logits, softmax and dz2;
-//   AG: h and dz2 of the owned samples go to all CTAs; every CTA then forms dh, the ReLU mask, dz1 and the operand
-//       images of the update MMA for all 32 samples (redundantly, bit-identical) and updates its b1 / W2 / b2 replicas.
-// The second layer (32 x 100 x 10) runs on the CUDA cores in exact fp32: as tf32 MMAs it is 19 M64/M128 K8
-// instructions of ~45 cycles each per step, 57 with error compensation, for 0.1 MFLOP.  Shared-memory broadcast
-// reads cost one LSU cycle per value and warp, so dh / gW2 are register tiled (4 samples x 4 hidden units per
-// thread: 12 LDS.128 of dz2 per step instead of 96).
+//       then dh = dz2 . W2, the ReLU mask and dz1 of those samples;
+//   AG: dz1 and dz2 of the owned samples go to all CTAs, which write the operand images of the update MMA;
+//   the hidden activations of the owned samples additionally go, sliced by hidden unit, to the CTA that owns that
+//   slice of W2: CTA c forms gW2[:, 16c .. 16c+15] over all 32 samples, applies the SGD step and all-gathers its
+//   slice of the new W2 (4-byte st.async, off the critical path) -- every CTA holds identical b1 / W2 / b2 replicas.
+// The second layer (32 x 100 x 10) therefore runs DISTRIBUTED on the CUDA cores in exact fp32, ~15 kFLOP per CTA and
+// step: as tf32 MMAs it is 19 M64/M128 K8 instructions of ~45 cycles each, 57 with error compensation.
 // Warp roles: warps 0-7 compute, warp 8 issues all MMAs and bulk copies and never touches data.
 // Operand tiles (hi and lo images of X in both K-major layouts) are written ahead of time by mlp1_stage4_kernel.
 #include "tc_common.cuh"
@@ -39,7 +40,7 @@ constexpr int T4_HP = 128;
 constexpr int T4_OUTV = 10;               // classes handled (padding classes: weights 0, bias -3e38)
 constexpr int T4_DZP = 12;                // floats per dz2 row in shared memory (3 x float4)
 constexpr int T4_WCB = 64, T4_WLD = 65;   // TMEM fill / write-back scratch: 64-column blocks, odd pitch
-constexpr int T4_NPROF = 12;
+constexpr int T4_NPROF = 14;   // phase counters (compute thread 0, warp 4 lane 0 and the issuer lane)
 
 template <int NC, bool X3> struct T4Cfg {
     static_assert(!X3 || NC == 8, "the error-compensated path needs W, Wlo and G in TMEM: 3 x FP <= 384 columns");
@@ -56,19 +57,21 @@ template <int NC, bool X3> struct T4Cfg {
     static constexpr int a2 = xt + NIMG * tile_max;              // update A operand [128 x 32] K-major, hi (+ lo)
     static constexpr int rs = a2 + NIMG * T4_HP * T4_B * 4;      // [NC src][GPO][128][4]
     static constexpr int ag = rs + 8 * T4_HP * 16;               // [8 sample groups][128][4]
-    static constexpr int gw2p = ag + 8 * T4_HP * 16;             // [8 warps][10][128] partial gW2
-    static constexpr int w2s = gw2p + 8 * T4_OUTV * T4_HP * 4;   // W2 [10][128]
-    static constexpr int gb1p = w2s + T4_OUTV * T4_HP * 4;       // [8 warps][128]
-    static constexpr int dzb = gb1p + 8 * T4_HP * 4;             // dz2 [32][12]
-    static constexpr int red = dzb + T4_B * T4_DZP * 4;          // [8 warps][40]
+    static constexpr int JS = T4_HP / NC;                        // hidden units per W2 slice
+    static constexpr int hsl = ag + 8 * T4_HP * 16;              // h of my W2 slice: [8 sample groups][JS][4]
+    static constexpr int w2s = hsl + 8 * JS * 16;                // W2 [10][128]
+    static constexpr int gb1p = w2s + T4_OUTV * T4_HP * 4;       // [2 halves][128]
+    static constexpr int dzb = gb1p + 2 * T4_HP * 4;             // dz2 [32][12] (all samples, via the all-gather)
+    static constexpr int dzo = dzb + T4_B * T4_DZP * 4;          // dz2 of my own samples [S][12]
+    static constexpr int red = dzo + 8 * T4_DZP * 4;             // [8 warps][40]
     static constexpr int b2 = red + 8 * 40 * 4;
     static constexpr int ys = b2 + 16 * 4;                       // [2][32] int
-    static constexpr int mbar = ys + 2 * T4_B * 4;               // 9 x uint64
+    static constexpr int mbar = ys + 2 * T4_B * 4;               // 10 x uint64
     static constexpr int tslot = mbar + 128;
     static constexpr int total = tslot + 16;
     static_assert(t_d1 + (X3 ? 96 : 32) <= 512, "TMEM budget");
     static_assert(total + 1024 <= 227 * 1024, "shared memory budget");
-    static_assert(T4_HP * T4_WLD * 4 <= gw2p - a2, "fill / write-back scratch must fit in a2 + rs + ag");
+    static_assert(T4_HP * T4_WLD * 4 <= hsl - a2, "fill / write-back scratch must fit in a2 + rs + ag");
     static_assert(NC * GPO == 8, "8 float4 sample groups");
 };
 
@@ -80,6 +83,10 @@ GB_DEVICE void mbar_arrive(uint64_t* mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(mbar)) : "memory");
 }
 GB_DEVICE void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+GB_DEVICE void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+                 :: "r"(remote_addr), "f"(v), "r"(remote_mbar) : "memory");
+}
 GB_DEVICE float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // sum 40 per-lane values over the warp with 45 shuffles: afterwards every lane whose bits 2..4 are g holds the
@@ -139,14 +146,16 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
     float* a2 = reinterpret_cast<float*>(smem + C::a2);
     float* rsb = reinterpret_cast<float*>(smem + C::rs);
     float* agb = reinterpret_cast<float*>(smem + C::ag);
-    float* gw2p = reinterpret_cast<float*>(smem + C::gw2p);
+    float* hsl = reinterpret_cast<float*>(smem + C::hsl);
     float* w2s = reinterpret_cast<float*>(smem + C::w2s);
     float* gb1p = reinterpret_cast<float*>(smem + C::gb1p);
     float* dzb = reinterpret_cast<float*>(smem + C::dzb);
+    float* dzo = reinterpret_cast<float*>(smem + C::dzo);
     float* red = reinterpret_cast<float*>(smem + C::red);
     float* b2s = reinterpret_cast<float*>(smem + C::b2);
     int* ysm = reinterpret_cast<int*>(smem + C::ys);
-    // 0 xf landed, 1 xt landed, 2 forward done, 3 update done, 4 (spare), 5 RS, 6 AG, 7 a2 ready (256), 8 Wlo ready (256)
+    // 0 xf landed, 1 xt landed, 2 forward done, 3 update done, 4 W2 all-gather, 5 RS, 6 AG, 7 a2 ready (256), 8 W/Wlo ready (256),
+    // 9 h slices of my W2 columns
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::mbar);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + C::tslot);
 
@@ -197,8 +206,9 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
     if (warp == 0) tmem_alloc<512>(tslot);
     if (tid == 0) {
         for (int i = 0; i < 7; ++i) mbar_init(&mbar[i], 1);
-        mbar_init(&mbar[7], T4_CTHREADS);
-        mbar_init(&mbar[8], T4_CTHREADS);
+        mbar_init(&mbar[7], T4Cfg<NC, X3>::GPO == 1 ? 4 : 8);      // one arrival per writing warp
+        mbar_init(&mbar[8], 8);
+        mbar_init(&mbar[9], 1);
         mbar_fence_init();
     }
     float b1r = (warp < T4_ISSUER && j < H) ? p.row[off_b1 + j] : 0.f;       // both threads of hidden unit j carry b1[j]
@@ -270,7 +280,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
 #pragma unroll
     for (int i = 0; i < T4_NPROF; ++i) prof[i] = 0u;
     unsigned tprev = 0u;
-#define T4_STAMP(i) do { if (profiling && lane == 0 && (warp == 0 || warp == T4_ISSUER)) { const unsigned t_ = (unsigned)clock(); prof[i] += t_ - tprev; tprev = t_; } } while (0)
+#define T4_STAMP(i) do { if (profiling && lane == 0 && (warp == 0 || warp == 4 || warp == T4_ISSUER)) { const unsigned t_ = (unsigned)clock(); prof[i] += t_ - tprev; tprev = t_; } } while (0)
 
     const uint32_t rs_bytes = 8u * (uint32_t)H * 16u;
     const uint32_t ag_bytes = rs_bytes + (uint32_t)T4_B * T4_DZP * 4u;
@@ -282,26 +292,22 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
         const uint32_t x_sbo = (uint32_t)nchunk * 128u;
         const uint32_t d1 = tmem_u + C::t_d1, w1 = tmem_u + C::t_w1, wlo = tmem_u + C::t_wlo;
         const uint32_t gacc = tmem_u + (X3 ? C::t_g : C::t_w1);
-        const int ksteps = FP >> 3;
+        const int ksteps = (FPC + 7) >> 3;                    // columns beyond FPC are zero padding
+        const uint32_t idesc_fwd2 = make_idesc(kFmtTF32, kFmtTF32, 128, 2 * T4_B, false, false);
         // forward chains of step s that only need the master weights: D1a = W . Xhi^T (and D1b = W . Xlo^T)
         auto fwd_ab = [&](int s) {
             mbar_wait(&mbar[0], (uint32_t)(s & 1));               // X tile(s) of step s have landed
             tc_fence_after();
             if (elect_one()) {
-                mbar_expect_tx(&mbar[5], rs_bytes);               // this step's exchanges
+                mbar_expect_tx(&mbar[5], rs_bytes);               // this step's exchanges (4 and 9 are armed by their consumers)
                 mbar_expect_tx(&mbar[6], ag_bytes);
+                // the lo image follows the hi image at 4 row groups x SBO, so [Xhi; Xlo] is ONE 64-row K-major operand:
+                // D1a | D1b = W . [Xhi; Xlo]^T with half the instructions (N = 64; issue cost ~32 cycles per MMA)
                 const uint64_t bhi = make_sdesc(smem_u32(xf), 128u, x_sbo);
 #pragma unroll 4
                 for (int k = 0; k < ksteps; ++k)                   // +256 B per K step = +16 in the address field
-                    mma_tf32_ts(d1, w1 + (uint32_t)k * 8u, bhi + (uint64_t)(k * 16), idesc_fwd, k > 0);
-                if (X3) {
-                    const uint64_t blo = make_sdesc(smem_u32(xf) + tile_bytes, 128u, x_sbo);
-#pragma unroll 4
-                    for (int k = 0; k < ksteps; ++k)
-                        mma_tf32_ts(d1 + 32u, w1 + (uint32_t)k * 8u, blo + (uint64_t)(k * 16), idesc_fwd, k > 0);
-                } else {
-                    mma_commit(&mbar[2]);
-                }
+                    mma_tf32_ts(d1, w1 + (uint32_t)k * 8u, bhi + (uint64_t)(k * 16), X3 ? idesc_fwd2 : idesc_fwd, k > 0);
+                if (!X3) mma_commit(&mbar[2]);
             }
             __syncwarp();
         };
@@ -332,9 +338,10 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             }
             T4_STAMP(1);
             mbar_wait(&mbar[7], ph);                              // dz1 operand images written by the compute warps
+            T4_STAMP(2);
             mbar_wait(&mbar[1], ph);                              // X^T tile(s) landed
             tc_fence_after();
-            T4_STAMP(2);
+            T4_STAMP(6);
             if (elect_one()) {
                 const uint64_t ahi = make_sdesc(smem_u32(a2), 128u, 1024u);
                 const uint64_t bhi = make_sdesc(smem_u32(xt), 128u, 1024u);
@@ -387,7 +394,9 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
         }
     } else {
         // =========================== compute warps ===============================================================
+        constexpr int JS = C::JS;
         float sscale = 1.f;                                  // W_true = sscale * W_tmem (lazy weight decay)
+        const bool reducer = half < GPO;                     // owns (hidden unit j, samples rank*S + 4*half .. +3)
         // loop-invariant DSMEM addresses
         uint32_t rs_dst[4], rs_bar[4];
 #pragma unroll
@@ -397,25 +406,34 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             rs_dst[q] = gb_map_shared(rsb + (((size_t)rank * GPO + (sg % GPO)) * T4_HP + j) * 4, owner);
             rs_bar[q] = gb_map_shared(&mbar[5], owner);
         }
+        const int my_g = (int)rank * GPO + (reducer ? half : 0);  // global float4 sample group of my owned samples
         uint32_t ag_dst[NC], ag_bar[NC];
 #pragma unroll
         for (int d = 0; d < NC; ++d) {
-            ag_dst[d] = gb_map_shared(agb + (((size_t)rank * GPO + (half < GPO ? half : 0)) * T4_HP + j) * 4, (uint32_t)d);
+            ag_dst[d] = gb_map_shared(agb + ((size_t)my_g * T4_HP + j) * 4, (uint32_t)d);
             ag_bar[d] = gb_map_shared(&mbar[6], (uint32_t)d);
         }
+        const uint32_t hs_dst = gb_map_shared(hsl + ((size_t)my_g * JS + (j % JS)) * 4, (uint32_t)(j / JS));
+        const uint32_t hs_bar = gb_map_shared(&mbar[9], (uint32_t)(j / JS));
         // softmax lanes (warp 0): owned sample si -> destination CTA sd
         const int sm_si = lane / NC, sm_d = lane % NC;
         const uint32_t dz_dst = gb_map_shared(dzb + (size_t)((int)rank * S + sm_si) * T4_DZP, (uint32_t)sm_d);
         const uint32_t dz_bar = gb_map_shared(&mbar[6], (uint32_t)sm_d);
-        // register tile of the second-layer backward: samples 4*warp .. 4*warp+3, hidden units lane + 32 i
-        const int tb0 = 4 * warp;
+        // my slice of W2: hidden units rank*JS .. rank*JS + JS-1
+        const int js_valid = max(0, min(JS, H - (int)rank * JS));
+        const uint32_t hs_bytes = (uint32_t)js_valid * 8u * 16u;
+        const uint32_t w2_bytes = (uint32_t)T4_OUTV * (uint32_t)H * 4u;
+        if (tid == 0) {
+            mbar_expect_tx(&mbar[9], hs_bytes);
+            mbar_expect_tx(&mbar[4], w2_bytes);
+        }
 
         for (int s = 0; s < total_steps; ++s) {
             const int par = s & 1;
             const uint32_t ph = (uint32_t)(s & 1);
             const int pos = p.epochs > 0 ? (s % spe) * B : 0;
             const int bcur = min(B, n - pos);
-            if (profiling && tid == 0) tprev = (unsigned)clock();
+            if (profiling && lane == 0) tprev = (unsigned)clock();
 
             // (1) partial z1 of my feature slice -> registers; reduce-scatter over the cluster
             mbar_wait(&mbar[2], ph);
@@ -441,11 +459,16 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                 }
             }
             T4_STAMP(1);
+            if (s > 0) {                                         // this step's W2 (all-gathered slices of step s-1)
+                mbar_wait_cluster(&mbar[4], (uint32_t)((s - 1) & 1));
+                if (tid == 0) mbar_expect_tx(&mbar[4], w2_bytes);
+            }
             mbar_wait_cluster(&mbar[5], ph);                     // every CTA's partial sums of my samples landed
             T4_STAMP(2);
-            // (2) owner work: h of my S samples (all hidden units), their logits / softmax / dz2
-            if (half < GPO) {
-                float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            // (2) owner work: h of my S samples (all hidden units), their logits / softmax / dz2 / dz1
+            float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float w2r[T4_OUTV];
+            if (reducer) {
                 float v[40];
                 if (j < H) {
                     float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -456,15 +479,14 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                     }
                     h4 = make_float4(fmaxf(fmaf(sscale, z.x, b1r), 0.f), fmaxf(fmaf(sscale, z.y, b1r), 0.f),
                                      fmaxf(fmaf(sscale, z.z, b1r), 0.f), fmaxf(fmaf(sscale, z.w, b1r), 0.f));
-#pragma unroll
-                    for (int d = 0; d < NC; ++d) st_async_v4(ag_dst[d], h4, ag_bar[d]);
+                    st_async_v4(hs_dst, h4, hs_bar);               // -> the CTA that owns column j of W2
                 }
                 const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
                 for (int o = 0; o < T4_OUTV; ++o) {
-                    const float w = w2s[o * T4_HP + j];
+                    w2r[o] = w2s[o * T4_HP + j];
 #pragma unroll
-                    for (int bl = 0; bl < 4; ++bl) v[bl * T4_OUTV + o] = hv[bl] * w;
+                    for (int bl = 0; bl < 4; ++bl) v[bl * T4_OUTV + o] = hv[bl] * w2r[o];
                 }
                 warp_reduce40(v, lane);
                 if ((lane & 3) == 0) {
@@ -498,106 +520,80 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
 #pragma unroll
                     for (int o = 0; o < T4_OUTV; ++o) dzv[o] = (z[o] * inv - (o == yy ? 1.f : 0.f)) * invb;
                 }
+                if (sm_d == 0) {                                 // local copy for the dh of my own samples
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        *reinterpret_cast<float4*>(dzo + sm_si * T4_DZP + 4 * q) = make_float4(dzv[4 * q], dzv[4 * q + 1], dzv[4 * q + 2], dzv[4 * q + 3]);
+                }
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     st_async_v4(dz_dst + (uint32_t)(q * 16), make_float4(dzv[4 * q], dzv[4 * q + 1], dzv[4 * q + 2], dzv[4 * q + 3]), dz_bar);
             }
             T4_STAMP(4);
-            // (3) all-gather landed: h and dz2 of all 32 samples.  Register tile: 4 samples x 4 hidden units per thread
-            mbar_wait_cluster(&mbar[6], ph);
-            T4_STAMP(5);
-            float ht[4][4];                                      // [i: hidden lane+32i][bl: sample tb0+bl]
-            float dzr[4][T4_DZP];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int jj = lane + 32 * i;
-                const float4 hv = (jj < H) ? *reinterpret_cast<const float4*>(agb + ((size_t)warp * T4_HP + jj) * 4)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                ht[i][0] = hv.x; ht[i][1] = hv.y; ht[i][2] = hv.z; ht[i][3] = hv.w;
-            }
-#pragma unroll
-            for (int bl = 0; bl < 4; ++bl) {
-                const float4* dr = reinterpret_cast<const float4*>(dzb + (size_t)(tb0 + bl) * T4_DZP);   // warp-wide broadcast
-                const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2];
-                dzr[bl][0] = d0.x; dzr[bl][1] = d0.y; dzr[bl][2] = d0.z; dzr[bl][3] = d0.w;
-                dzr[bl][4] = d1.x; dzr[bl][5] = d1.y; dzr[bl][6] = d1.z; dzr[bl][7] = d1.w;
-                dzr[bl][8] = d2.x; dzr[bl][9] = d2.y; dzr[bl][10] = d2.z; dzr[bl][11] = d2.w;
-            }
-            if (p.dbg != nullptr && !profiling && s == 0 && rank == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int bl = 0; bl < 4; ++bl) p.dbg[(lane + 32 * i) * T4_B + tb0 + bl] = ht[i][bl];
-            }
-            const float s_next = sscale * decay;
-            {
-                float dh[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int bl = 0; bl < 4; ++bl) dh[i][bl] = 0.f;
-#pragma unroll
-                for (int o = 0; o < T4_OUTV; ++o) {
-                    float w[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) w[i] = w2s[o * T4_HP + lane + 32 * i];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int bl = 0; bl < 4; ++bl) dh[i][bl] = fmaf(dzr[bl][o], w[i], dh[i][bl]);
-                }
-                const float ascale = -p.lr / s_next;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int jj = lane + 32 * i;
-                    float outv[4], gb1 = 0.f;
-#pragma unroll
-                    for (int bl = 0; bl < 4; ++bl) {
-                        const float dz1 = (ht[i][bl] > 0.f) ? dh[i][bl] : 0.f;
-                        gb1 += dz1;
-                        outv[bl] = ascale * dz1;
-                    }
-                    gb1p[warp * T4_HP + jj] = gb1;
-                    // A2[hid = jj][batch] K-major core matrices: ((jj/8)*8 + b/4)*128 B + (jj%8)*16 B + (b%4)*4 B
-                    float* arow = a2 + (size_t)(jj >> 3) * (8 * 32) + (jj & 7) * 4 + warp * 32;
-                    if (X3) {
-                        float lo[4];
-#pragma unroll
-                        for (int bl = 0; bl < 4; ++bl) { const float hi = tf32_hi(outv[bl]); lo[bl] = outv[bl] - hi; outv[bl] = hi; }
-                        *reinterpret_cast<float4*>(arow + T4_HP * T4_B) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    }
-                    *reinterpret_cast<float4*>(arow) = make_float4(outv[0], outv[1], outv[2], outv[3]);
-                }
-            }
-            fence_proxy_async();
-            mbar_arrive(&mbar[7]);                               // -> the issuer starts the update MMAs
-            T4_STAMP(6);
-            // (4) off the critical path: second-layer gradients and parameter replicas
-#pragma unroll
-            for (int o = 0; o < T4_OUTV; ++o)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float g = ht[i][0] * dzr[0][o];
-                    g = fmaf(ht[i][1], dzr[1][o], g); g = fmaf(ht[i][2], dzr[2][o], g); g = fmaf(ht[i][3], dzr[3][o], g);
-                    gw2p[(warp * T4_OUTV + o) * T4_HP + lane + 32 * i] = g;
-                }
-            if (tid >= 64 && tid < 96 && s + 1 < total_steps)                // labels of the next step
-                ysm[(par ^ 1) * T4_B + (tid - 64)] = stage_ys[(size_t)(s + 1) * T4_B + (tid - 64)];
             bar_compute();
+            if (reducer && j < H) {                              // dh = dz2 . W2[:, j], ReLU mask -> dz1 of my samples, to all CTAs
+                const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+                float dz1[4];
 #pragma unroll
-            for (int k = 0; k < (T4_OUTV * T4_HP) / T4_CTHREADS; ++k) {      // 1280 entries of W2, 5 per thread
-                const int e = tid + T4_CTHREADS * k;
-                float g = 0.f;
+                for (int bl = 0; bl < 4; ++bl) {
+                    const float4* dr = reinterpret_cast<const float4*>(dzo + (4 * half + bl) * T4_DZP);   // warp-wide broadcast
+                    const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2];
+                    float dh = d0.x * w2r[0];
+                    dh = fmaf(d0.y, w2r[1], dh); dh = fmaf(d0.z, w2r[2], dh); dh = fmaf(d0.w, w2r[3], dh);
+                    dh = fmaf(d1.x, w2r[4], dh); dh = fmaf(d1.y, w2r[5], dh); dh = fmaf(d1.z, w2r[6], dh);
+                    dh = fmaf(d1.w, w2r[7], dh); dh = fmaf(d2.x, w2r[8], dh); dh = fmaf(d2.y, w2r[9], dh);
+                    dz1[bl] = (hv[bl] > 0.f) ? dh : 0.f;
+                }
+                const float4 dv = make_float4(dz1[0], dz1[1], dz1[2], dz1[3]);
 #pragma unroll
-                for (int w = 0; w < 8; ++w) g += gw2p[w * T4_OUTV * T4_HP + e];      // fixed order
-                w2s[e] = fmaf(-p.lr, g, w2s[e] * decay);
+                for (int d = 0; d < NC; ++d) st_async_v4(ag_dst[d], dv, ag_bar[d]);
             }
-            {
-                float g = 0.f;
+            T4_STAMP(5);
+            // (3) all-gather landed: dz1 and dz2 of all 32 samples -> operand images of the update MMA
+            mbar_wait_cluster(&mbar[6], ph);
+            T4_STAMP(6);
+            const float s_next = sscale * decay;
+            // With one sample group per owner (NC = 8) only half 0 reduces and sends; half 1 writes the operand images
+            // of all 32 samples.
+            constexpr bool kSplitRoles = (GPO == 1);
+            if (!kSplitRoles || half == 1) {
+                const float ascale = -p.lr / s_next;
+                float gb1 = 0.f;
+                constexpr int NQ = kSplitRoles ? 8 : 4;
+                const int q0 = kSplitRoles ? 0 : 4 * half;
+                // A2[hid = j][batch] K-major core matrices: ((j/8)*8 + b/4)*128 B + (j%8)*16 B + (b%4)*4 B
+                float* arow = a2 + (size_t)(j >> 3) * (8 * 32) + (j & 7) * 4 + q0 * 32;
+                float4 d[NQ];
 #pragma unroll
-                for (int w = 0; w < 8; ++w) g += gb1p[w * T4_HP + j];
-                b1r = fmaf(-p.lr, g, b1r * decay);
+                for (int q = 0; q < NQ; ++q)
+                    d[q] = (j < H) ? *reinterpret_cast<const float4*>(agb + ((size_t)(q0 + q) * T4_HP + j) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    gb1 += (d[q].x + d[q].y) + (d[q].z + d[q].w);
+                    float4 a = make_float4(ascale * d[q].x, ascale * d[q].y, ascale * d[q].z, ascale * d[q].w);
+                    if (p.dbg != nullptr && !profiling && s == 0 && rank == 0) {     // bring-up: dz1 of the first step
+                        float* o = p.dbg + j * T4_B + 4 * (q0 + q);
+                        o[0] = d[q].x; o[1] = d[q].y; o[2] = d[q].z; o[3] = d[q].w;
+                    }
+                    if (X3) {
+                        const float4 hi = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
+                        *reinterpret_cast<float4*>(arow + T4_HP * T4_B + q * 32) = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
+                        a = hi;
+                    }
+                    *reinterpret_cast<float4*>(arow + q * 32) = a;
+                }
+                gb1p[(kSplitRoles ? 0 : half) * T4_HP + j] = gb1;
+                if (kSplitRoles) gb1p[T4_HP + j] = 0.f;
+                T4_STAMP(12);
+                fence_proxy_async();
+                T4_STAMP(13);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&mbar[7]);            // -> the issuer starts the update MMAs
             }
+            T4_STAMP(7);
+            // (4) off the critical path: my slice of W2 (all samples), db2, labels of the next step
+            if (tid >= 64 && tid < 96 && s + 1 < total_steps)
+                ysm[(par ^ 1) * T4_B + (tid - 64)] = stage_ys[(size_t)(s + 1) * T4_B + (tid - 64)];
             if (warp == 5) {                                     // db2[o] = sum_b dz2[b][o]: lane = sample
                 const float4* dr = reinterpret_cast<const float4*>(dzb + (size_t)lane * T4_DZP);
                 const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2];
@@ -611,36 +607,78 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                     b2s[lane] = fmaf(-p.lr, g, b2s[lane] * decay);
                 }
             }
-            sscale = s_next;
-            T4_STAMP(7);
+            if (js_valid > 0) {
+                mbar_wait_cluster(&mbar[9], ph);                 // h of my W2 columns, all 32 samples
+                for (int e = tid; e < js_valid * T4_OUTV; e += T4_CTHREADS) {
+                    const int jj = e / T4_OUTV, o = e - jj * T4_OUTV;
+                    float g = 0.f;
+#pragma unroll
+                    for (int g8 = 0; g8 < 8; ++g8) {                // fixed order
+                        const float4 hv4 = *reinterpret_cast<const float4*>(hsl + ((size_t)g8 * JS + jj) * 4);
+                        g = fmaf(hv4.x, dzb[(4 * g8) * T4_DZP + o], g);
+                        g = fmaf(hv4.y, dzb[(4 * g8 + 1) * T4_DZP + o], g);
+                        g = fmaf(hv4.z, dzb[(4 * g8 + 2) * T4_DZP + o], g);
+                        g = fmaf(hv4.w, dzb[(4 * g8 + 3) * T4_DZP + o], g);
+                    }
+                    const int jg = (int)rank * JS + jj;
+                    const float wn = fmaf(-p.lr, g, w2s[o * T4_HP + jg] * decay);
+                    float* slot = w2s + o * T4_HP + jg;
+#pragma unroll
+                    for (int d = 0; d < NC; ++d)
+                        st_async_f32(gb_map_shared(slot, (uint32_t)d), wn, gb_map_shared(&mbar[4], (uint32_t)d));
+                }
+            }
+            T4_STAMP(8);
             // (5) update retired: W += G (round to nearest) and re-split into hi / lo for the next forward pass
             mbar_wait(&mbar[3], ph);
             tc_fence_after();
-            T4_STAMP(8);
+            T4_STAMP(9);
             if (X3) {
                 const int ngrp = FP >> 4;                        // 16-column groups; this thread takes g = half, half+2, ...
                 const bool more = s + 1 < total_steps;
-                for (int g = half; g < ngrp; g += 2) {
-                    float wv[16], gv[16];
+                for (int g = half; g < ngrp; g += 4) {               // two groups per round: four loads in flight
+                    const bool two = g + 2 < ngrp;
+                    float wv[16], gv[16], wv2[16], gv2[16];
                     tmem_ld16(tlane + C::t_w1 + g * 16, wv);
                     tmem_ld16(tlane + C::t_g + g * 16, gv);
+                    if (two) {
+                        tmem_ld16(tlane + C::t_w1 + (g + 2) * 16, wv2);
+                        tmem_ld16(tlane + C::t_g + (g + 2) * 16, gv2);
+                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; ++i) wv[i] += gv[i];
                     tmem_st16(tlane + C::t_w1 + g * 16, wv);
                     if (more) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) wv[i] = wv[i] - tf32_hi(wv[i]);
-                        tmem_st16(tlane + C::t_wlo + g * 16, wv);
+                        for (int i = 0; i < 16; ++i) gv[i] = wv[i] - tf32_hi(wv[i]);
+                        tmem_st16(tlane + C::t_wlo + g * 16, gv);
+                    }
+                    if (two) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) wv2[i] += gv2[i];
+                        tmem_st16(tlane + C::t_w1 + (g + 2) * 16, wv2);
+                        if (more) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) gv2[i] = wv2[i] - tf32_hi(wv2[i]);
+                            tmem_st16(tlane + C::t_wlo + (g + 2) * 16, gv2);
+                        }
                     }
                 }
                 tmem_st_wait();
                 tc_fence_before();
-                if (more) mbar_arrive(&mbar[8]);
+                __syncwarp();
+                if (more && lane == 0) mbar_arrive(&mbar[8]);
             }
-            T4_STAMP(9);
-            bar_compute();                                       // W2 / b2 of this step are visible to every warp
+            T4_STAMP(10);
+            bar_compute();                                       // end of step: gb1p complete, buffers of this step consumed
+            T4_STAMP(11);
+            if (tid == 0) mbar_expect_tx(&mbar[9], hs_bytes);    // next step's h slices
+            b1r = fmaf(-p.lr, gb1p[j] + gb1p[T4_HP + j], b1r * decay);
+            sscale = s_next;
         }
+        // the last step's W2 all-gather
+        mbar_wait_cluster(&mbar[4], (uint32_t)((total_steps - 1) & 1));
         if (tid == 0) red[0] = sscale;
         if (rank == 0 && j < H && half == 0) b1g[j] = b1r;
     }
@@ -683,9 +721,9 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
         for (int i = tid; i < OUT * H; i += T4_THREADS) W2g[i] = w2s[(i / H) * T4_HP + (i % H)];
         if (tid < OUT) b2g[tid] = b2s[tid];
     }
-    if (profiling && lane == 0 && (warp == 0 || warp == T4_ISSUER)) {
+    if (profiling && lane == 0 && (warp == 0 || warp == 4 || warp == T4_ISSUER)) {
         for (int i = 0; i < T4_NPROF; ++i)
-            p.dbg[rank * 64 + (warp == 0 ? 0 : 32) + i] = (float)((double)prof[i] / (double)total_steps);
+            p.dbg[rank * 64 + (warp == 0 ? 0 : warp == 4 ? 16 : 32) + i] = (float)((double)prof[i] / (double)total_steps);
     }
     tc_fence_before();
     __syncthreads();
