@@ -82,6 +82,10 @@ GB_DEVICE void bulk_g2s4(void* smem_dst, const void* gsrc, uint32_t bytes, uint6
 GB_DEVICE void mbar_arrive(uint64_t* mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(mbar)) : "memory");
 }
+// wait for st.async traffic from other CTAs of the cluster (acquire at cluster scope).  Measured alternatives that
+// did not change the step time: CTA-scope acquire (no CCTL.IVALL), a suspend-time hint, one polling lane per warp
+// (4x slower) -- the shared-memory port is busy with ~32 KB of DSMEM traffic per step at ~20 B/cycle instead.
+GB_DEVICE void mbar_wait_dsm(uint64_t* mbar, uint32_t parity) { mbar_wait_cluster(mbar, parity); }
 GB_DEVICE void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 GB_DEVICE void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
@@ -422,7 +426,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
         // my slice of W2: hidden units rank*JS .. rank*JS + JS-1
         const int js_valid = max(0, min(JS, H - (int)rank * JS));
         const uint32_t hs_bytes = (uint32_t)js_valid * 8u * 16u;
-        const uint32_t w2_bytes = (uint32_t)T4_OUTV * (uint32_t)H * 4u;
+        const uint32_t w2_bytes = (uint32_t)T4_OUTV * (uint32_t)((H + 3) >> 2) * 16u;   // every group of 4 hidden units, all classes
         if (tid == 0) {
             mbar_expect_tx(&mbar[9], hs_bytes);
             mbar_expect_tx(&mbar[4], w2_bytes);
@@ -460,10 +464,10 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             }
             T4_STAMP(1);
             if (s > 0) {                                         // this step's W2 (all-gathered slices of step s-1)
-                mbar_wait_cluster(&mbar[4], (uint32_t)((s - 1) & 1));
+                mbar_wait_dsm(&mbar[4], (uint32_t)((s - 1) & 1));
                 if (tid == 0) mbar_expect_tx(&mbar[4], w2_bytes);
             }
-            mbar_wait_cluster(&mbar[5], ph);                     // every CTA's partial sums of my samples landed
+            mbar_wait_dsm(&mbar[5], ph);                     // every CTA's partial sums of my samples landed
             T4_STAMP(2);
             // (2) owner work: h of my S samples (all hidden units), their logits / softmax / dz2 / dz1
             float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -550,7 +554,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             }
             T4_STAMP(5);
             // (3) all-gather landed: dz1 and dz2 of all 32 samples -> operand images of the update MMA
-            mbar_wait_cluster(&mbar[6], ph);
+            mbar_wait_dsm(&mbar[6], ph);
             T4_STAMP(6);
             const float s_next = sscale * decay;
             // With one sample group per owner (NC = 8) only half 0 reduces and sends; half 1 writes the operand images
@@ -568,8 +572,12 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                 for (int q = 0; q < NQ; ++q)
                     d[q] = (j < H) ? *reinterpret_cast<const float4*>(agb + ((size_t)(q0 + q) * T4_HP + j) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
+                for (int q = 0; q < NQ; ++q) gb1 += (d[q].x + d[q].y) + (d[q].z + d[q].w);
+                gb1p[(kSplitRoles ? 0 : half) * T4_HP + j] = gb1;
+                if (kSplitRoles) gb1p[T4_HP + j] = 0.f;
+                T4_STAMP(12);
+#pragma unroll
                 for (int q = 0; q < NQ; ++q) {
-                    gb1 += (d[q].x + d[q].y) + (d[q].z + d[q].w);
                     float4 a = make_float4(ascale * d[q].x, ascale * d[q].y, ascale * d[q].z, ascale * d[q].w);
                     if (p.dbg != nullptr && !profiling && s == 0 && rank == 0) {     // bring-up: dz1 of the first step
                         float* o = p.dbg + j * T4_B + 4 * (q0 + q);
@@ -582,11 +590,8 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                     }
                     *reinterpret_cast<float4*>(arow + q * 32) = a;
                 }
-                gb1p[(kSplitRoles ? 0 : half) * T4_HP + j] = gb1;
-                if (kSplitRoles) gb1p[T4_HP + j] = 0.f;
-                T4_STAMP(12);
-                fence_proxy_async();
                 T4_STAMP(13);
+                fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&mbar[7]);            // -> the issuer starts the update MMAs
             }
@@ -608,24 +613,34 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                 }
             }
             if (js_valid > 0) {
-                mbar_wait_cluster(&mbar[9], ph);                 // h of my W2 columns, all 32 samples
-                for (int e = tid; e < js_valid * T4_OUTV; e += T4_CTHREADS) {
-                    const int jj = e / T4_OUTV, o = e - jj * T4_OUTV;
-                    float g = 0.f;
+                mbar_wait_dsm(&mbar[9], ph);                 // h of my W2 columns, all 32 samples
+                // 4 hidden units x 1 class per thread: the new W2 entries travel as 16-byte st.async (4-byte ones cost
+                // 4x the DSMEM transactions and mbarrier updates, which slow every shared-memory access of the cluster)
+                const int ngr = (js_valid + 3) >> 2;
+                for (int e = tid; e < ngr * T4_OUTV; e += T4_CTHREADS) {
+                    const int jq = e / T4_OUTV, o = e - jq * T4_OUTV;
+                    float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int g8 = 0; g8 < 8; ++g8) {                // fixed order
-                        const float4 hv4 = *reinterpret_cast<const float4*>(hsl + ((size_t)g8 * JS + jj) * 4);
-                        g = fmaf(hv4.x, dzb[(4 * g8) * T4_DZP + o], g);
-                        g = fmaf(hv4.y, dzb[(4 * g8 + 1) * T4_DZP + o], g);
-                        g = fmaf(hv4.z, dzb[(4 * g8 + 2) * T4_DZP + o], g);
-                        g = fmaf(hv4.w, dzb[(4 * g8 + 3) * T4_DZP + o], g);
+                        const float dz0 = dzb[(4 * g8) * T4_DZP + o], dz1v = dzb[(4 * g8 + 1) * T4_DZP + o];
+                        const float dz2v = dzb[(4 * g8 + 2) * T4_DZP + o], dz3 = dzb[(4 * g8 + 3) * T4_DZP + o];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 hv4 = *reinterpret_cast<const float4*>(hsl + ((size_t)g8 * JS + 4 * jq + u) * 4);
+                            g[u] = fmaf(hv4.x, dz0, g[u]); g[u] = fmaf(hv4.y, dz1v, g[u]);
+                            g[u] = fmaf(hv4.z, dz2v, g[u]); g[u] = fmaf(hv4.w, dz3, g[u]);
+                        }
                     }
-                    const int jg = (int)rank * JS + jj;
-                    const float wn = fmaf(-p.lr, g, w2s[o * T4_HP + jg] * decay);
+                    const int jg = (int)rank * JS + 4 * jq;
                     float* slot = w2s + o * T4_HP + jg;
+                    const float4 wo = *reinterpret_cast<const float4*>(slot);
+                    const float4 wn = make_float4(jg < H ? fmaf(-p.lr, g[0], wo.x * decay) : 0.f,
+                                                  jg + 1 < H ? fmaf(-p.lr, g[1], wo.y * decay) : 0.f,
+                                                  jg + 2 < H ? fmaf(-p.lr, g[2], wo.z * decay) : 0.f,
+                                                  jg + 3 < H ? fmaf(-p.lr, g[3], wo.w * decay) : 0.f);
 #pragma unroll
                     for (int d = 0; d < NC; ++d)
-                        st_async_f32(gb_map_shared(slot, (uint32_t)d), wn, gb_map_shared(&mbar[4], (uint32_t)d));
+                        st_async_v4(gb_map_shared(slot, (uint32_t)d), wn, gb_map_shared(&mbar[4], (uint32_t)d));
                 }
             }
             T4_STAMP(8);
@@ -678,7 +693,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             sscale = s_next;
         }
         // the last step's W2 all-gather
-        mbar_wait_cluster(&mbar[4], (uint32_t)((total_steps - 1) & 1));
+        mbar_wait_dsm(&mbar[4], (uint32_t)((total_steps - 1) & 1));
         if (tid == 0) red[0] = sscale;
         if (rank == 0 && j < H && half == 0) b1g[j] = b1r;
     }
