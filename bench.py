@@ -30,6 +30,18 @@ if ROOT not in sys.path:
 N_NODES, D_IN, D_H, D_OUT = 8, 784, 100, 10
 N_TRAIN, N_TEST, BATCH, DELTA, LR = 60000, 10000, 32, 100, 0.1
 BASELINE_ROUNDS_PER_S = 0.44   # reference as-is on the survey box (CPU); no published GPU number
+METRIC = "gossip rounds/sec (8-node MLP 784-100-10, push-pull, synthetic MNIST-shape non-IID)"
+
+
+def common_config(world: int):
+    """The benchmark configuration, identical in both arms (arm-specific notes go to "details")."""
+    return {"model": "TorchMLP(784,10,(100,)) P=79510", "nodes": N_NODES, "global_batch": BATCH * N_NODES,
+            "batch_per_node": BATCH, "seq_len": None, "samples_per_node": N_TRAIN // N_NODES, "local_epochs": 1,
+            "optimizer": "SGD lr 0.1", "protocol": "PUSH_PULL", "mode": "MERGE_UPDATE", "delta": DELTA,
+            "eval": "all 8 nodes on the 10000-sample global test set every round",
+            "sgd_steps_per_round": 16 * ((N_TRAIN // N_NODES + BATCH - 1) // BATCH),
+            "parallelism": "gossip-dp8 (8 nodes over %d GPU(s))" % world,
+            "l2": "inputs (219 MB of shards + 31 MB test set) exceed the 126 MB L2"}
 
 
 def parse():
@@ -38,13 +50,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--train-impl", default="", help="force a training kernel: cluster | tc")
+    ap.add_argument("--train-impl", default="", help="training kernel: '' = fp32-equivalent default (tc8, 3xTF32), "
+                    "cluster (fp32 CUDA cores), tc8-tf32 | tc3 (plain tf32)")
     ap.add_argument("--engine", default="native", choices=["native", "python"],
                     help="control plane of the round loop: C++ scheduler or the Python loop")
-    ap.add_argument("--executor", default="python", choices=["native", "python"],
+    ap.add_argument("--executor", default="native", choices=["native", "python"],
                     help="native engine only: C++ executor (csrc/exec) or the per-event Python executor")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--curve", action="store_true", help="also print accuracy per round")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the secondary plain-tf32 measurement")
+    ap.add_argument("--curve", action="store_true", help="(kept for compatibility: the curve is always printed)")
     return ap.parse_args()
 
 
@@ -182,7 +196,7 @@ def build_native(world: int, rank: int, train_impl: str, engine: str = "native",
     dh = ClassificationDataHandler(Xtr, ytr, Xte, yte)
     disp = DataDispatcher(dh, n=N_NODES, eval_on_user=False, auto_assign=False)
     disp.set_assignments(AssignmentHandler(42).label_pathological_skew(ytr, N_NODES, 2), None)
-    ops.TRAIN_IMPL = train_impl or ""
+    ops.set_train_impl(train_impl or "")
     proto = TorchModelHandler(net=TorchMLP(D_IN, D_OUT, (D_H,)), optimizer=torch.optim.SGD,
                               optimizer_params={"lr": LR}, criterion=torch.nn.CrossEntropyLoss(),
                               local_epochs=1, batch_size=BATCH,
@@ -265,28 +279,34 @@ def run_native(args, rank, world):
         h2d = sum(int(n.data[0][0].numel()) * 4 + int(n.data[0][1].numel()) * 8 for n in sim.nodes.values())
         e2e = {"value": K / (ms_e / 1e3), "unit": "rounds/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": N_NODES * D_OUT * D_OUT * 4, "ms_per_step": ms_e / K}
+    dtype = ops.train_dtype()
+    n_main = len(acc)
+    tf32 = None
+    if not args.no_tf32 and torch.cuda.is_available() and ops.TRAIN_IMPL in ("", "tc8"):
+        # secondary number: the same rounds with plain tf32 tensor-core products (GlobalSettings().allow_tf32)
+        import gossipy_b200 as g
+        g.GlobalSettings().allow_tf32 = True
+        K2 = max(10, K // 4)
+        time_rounds(sim, 2, world)
+        ms_t = max_over_ranks(time_rounds(sim, K2, world), world)
+        g.GlobalSettings().allow_tf32 = False
+        ops.set_train_impl(args.train_impl or "")
+        tf32 = {"value": K2 / (ms_t / 1e3), "unit": "rounds/s", "steps": K2,
+                "dtype": "tf32 (operands truncated to 10 mantissa bits; NOT the headline: below the reference's fp32)"}
     if rank == 0:
-        out = {"metric": "gossip rounds/sec (8-node MLP 784-100-10, push-pull, synthetic MNIST-shape non-IID)",
+        out = {"metric": METRIC,
                "value": value, "unit": "rounds/s", "n_gpus": world, "steps": K, "warmup": W,
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
-               "vs_baseline": value / BASELINE_ROUNDS_PER_S,
-               "dtype": "fp32" if args.train_impl == "cluster" else "tf32 (fp32 master weights + fp32 accumulate)",
-               "data": "synthetic", "impl": "native",
-               "config": {"model": "TorchMLP(784,10,(100,)) P=79510", "nodes": N_NODES,
-                          "global_batch": BATCH * N_NODES, "batch_per_node": BATCH, "seq_len": None,
-                          "samples_per_node": N_TRAIN // N_NODES, "local_epochs": 1,
-                          "protocol": "PUSH_PULL", "mode": "MERGE_UPDATE", "delta": DELTA,
-                          "eval": "all 8 nodes on the 10000-sample global test set every round",
-                          "sgd_steps_per_round": 16 * ((N_TRAIN // N_NODES + BATCH - 1) // BATCH),
-                          "parallelism": "gossip-dp: %d nodes over %d GPU(s)" % (N_NODES, world),
-                          "l2": "192 MB flush buffer rewritten every round (and at N=1 the inputs, 219 MB, exceed the 126 MB L2)",
-                          "placement": "block (node i on rank i*N//8), peer rows pulled over NVLink by the fused merge+train kernel",
-                          "train_kernel": args.train_impl or "auto", "engine": args.engine,
-                          "executor": ("c++ (csrc/exec)" if "_stream_exec" in sim.__dict__ else "python (per event)")},
+               "vs_baseline": value / BASELINE_ROUNDS_PER_S, "dtype": dtype,
+               "data": "synthetic", "impl": "native", "config": common_config(world),
+               "details": {"l2_flush": "192 MB buffer rewritten every round inside the timed region",
+                           "placement": "block (node i on rank i*N//8), peer rows pulled over NVLink by the fused merge+train kernel",
+                           "train_kernel": args.train_impl or "auto (tc8: 3xTF32 tcgen05, 8-CTA cluster)",
+                           "engine": args.engine,
+                           "executor": ("c++ (csrc/exec)" if "_stream_exec" in sim.__dict__ else "python (per event)")},
                "clocks": clk.summary(), "gpu_launches": launches,
-               "test_acc_by_round_tail": acc[-5:], "e2e": e2e}
-        if args.curve:
-            out["test_acc_by_round"] = acc
+               "test_acc_by_round_tail": acc[n_main - 5:n_main], "test_acc_by_round": acc[:n_main], "e2e": e2e,
+               "tf32": tf32}
         print(json.dumps(out))
 
 
@@ -390,18 +410,14 @@ def run_reference(args, rank, world):
         h2d = steps_round * (BATCH * D_IN * 4 + BATCH * 8) + 16 * p_bytes + 8 * (N_TEST * D_IN * 4 + p_bytes)
         d2h = 16 * p_bytes + 8 * (p_bytes + N_TEST * 8 * 2)
         print(json.dumps({
-            "metric": "gossip rounds/sec (8-node MLP 784-100-10, push-pull, synthetic MNIST-shape non-IID)",
+            "metric": METRIC,
             "value": value, "unit": "rounds/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": value / BASELINE_ROUNDS_PER_S, "dtype": "fp32", "data": "synthetic",
             "impl": "reference",
-            "config": {"model": "TorchMLP(784,10,(100,)) P=79510", "nodes": N_NODES,
-                       "global_batch": BATCH * N_NODES, "seq_len": None, "protocol": "PUSH_PULL",
-                       "samples_per_node": N_TRAIN // N_NODES,
-                       "parallelism": "single process, single device (the reference has no multi-GPU mode; "
-                                      "ranks > 0 idle)",
-                       "l2": "inputs larger than L2"},
-            "clocks": clocks, "gpu_launches": 0, "test_acc_by_round_tail": acc[-5:],
+            "config": common_config(world),
+            "details": {"parallelism": "single process, single device (the reference has no multi-GPU mode; ranks > 0 idle)"},
+            "clocks": clocks, "gpu_launches": 0, "test_acc_by_round_tail": acc[-5:], "test_acc_by_round": acc,
             "e2e": {"value": value, "unit": "rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "the reference's stock path already moves every mini-batch and the model "
                             "host<->device inside the timed region"}}))

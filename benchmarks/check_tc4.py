@@ -1,6 +1,6 @@
 """GPU bring-up / accuracy / timing of the fp32-equivalent training kernel (mlp1_train_tc4.cu).
 
-    python benchmarks/check_tc4.py [impl ...]      (default: tc4 tc4-tf32 tc8 tc8-tf32 tc3 cluster)
+    python benchmarks/check_tc4.py [impl ...]      (default: tc8 tc8-tf32 tc3 cluster)
 
 Prints one JSON line per check: first-step activations vs an fp64 oracle, whole updates vs the fp64 oracle next
 to the error of the plain fp32 PyTorch oracle, kernel time and phase counters."""
@@ -12,7 +12,7 @@ from gossipy_b200.engine import rng
 from gossipy_b200.ops import torch_ref as ref
 from gossipy_b200.ops.native import native
 
-IMPLS = sys.argv[1:] or ["tc8", "tc8-tf32", "tc4-tf32", "tc3", "cluster"]
+IMPLS = sys.argv[1:] or ["tc8", "tc8-tf32", "tc3", "cluster"]
 
 
 def problem(n, d_in, d_h, d_out, seed=0):

@@ -102,6 +102,22 @@ class GlobalSettings(metaclass=_SingletonMeta):
         self.rank = 0
         self.world_size = 1
         self.reference_compat = False  # mimic selected reference quirks (see docs/QUIRKS.md)
+        self._allow_tf32 = False
+
+    # -- numerics -----------------------------------------------------------------------
+    @property
+    def allow_tf32(self) -> bool:
+        """``False`` (default): the fused GPU kernels compute like the reference's fp32 -- tensor-core products are
+        error compensated (3xTF32).  ``True``: plain tf32 products (operands truncated to 10 mantissa bits, the
+        analogue of ``torch.backends.cuda.matmul.allow_tf32``), ~25 % faster per local update."""
+        return self._allow_tf32
+
+    @allow_tf32.setter
+    def allow_tf32(self, on: bool) -> None:
+        self._allow_tf32 = bool(on)
+        from . import ops
+        ops.set_train_impl("tc8-tf32" if on else "")
+        ops.set_eval_tf32(bool(on))
 
     # -- device -------------------------------------------------------------------------
     def auto_device(self) -> torch.device:

@@ -124,6 +124,16 @@ void adam_step(at::Tensor p, at::Tensor g, int64_t n, at::Tensor m, at::Tensor v
 // ---- fused local updates -----------------------------------------------------------------------------
 static thread_local float* g_debug_ptr = nullptr;
 
+static TrainImpl parse_train_impl(const std::string& impl) {
+    const TrainImpl which = impl == "cluster" ? kTrainCluster : impl == "tc3" ? kTrainTc3
+                            : impl == "tc8" ? kTrainTc8 : impl == "tc8-tf32" ? kTrainTc8Tf32 : kTrainAuto;
+    TORCH_CHECK(which != kTrainAuto || impl.empty() || impl == "auto", "unknown training kernel '", impl,
+                "' (cluster | tc8 | tc8-tf32 | tc3)");
+    return which;
+}
+// what the automatic choice means for this process (also used by the C++ executor)
+void set_train_impl(std::string impl) { set_default_train_impl(parse_train_impl(impl)); }
+
 int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
                    int64_t batch_size, int64_t local_epochs, double lr, double wd, int64_t key,
                    c10::optional<at::Tensor> part_id, c10::optional<at::Tensor> ages, std::string impl,
@@ -153,11 +163,7 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
         p.sync = to_sync(sync);
     }
     c10::cuda::CUDAGuard guard(row.device());
-    const TrainImpl which = impl == "cluster" ? kTrainCluster : impl == "tc" ? kTrainTc
-                            : impl == "tc2" ? kTrainTc2 : impl == "tc3" ? kTrainTc3
-                            : impl == "tc4" ? kTrainTc4 : impl == "tc4-tf32" ? kTrainTc4Tf32
-                            : impl == "tc8" ? kTrainTc8 : impl == "tc8-tf32" ? kTrainTc8Tf32 : kTrainAuto;
-    TORCH_CHECK(which != kTrainAuto || impl.empty() || impl == "auto", "unknown training kernel '", impl, "'");
+    const TrainImpl which = parse_train_impl(impl);
     const char* why = "";
     const bool ok = launch_mlp1_train(p, which, cur_stream(), &why);
     TORCH_CHECK(ok, why, " (in=", p.IN, " hidden=", p.H, " out=", p.OUT, " batch=", p.B, ")");
@@ -324,36 +330,6 @@ void mf_update(at::Tensor X, at::Tensor b, at::Tensor Y, at::Tensor c, at::Tenso
     GB_LAUNCH_CHECK();
 }
 
-at::Tensor tc_probe(at::Tensor A, at::Tensor Bm, int64_t variant) {
-    const int K = (int)A.size(1), N = (int)Bm.size(1);
-    TORCH_CHECK(A.size(0) == 128 && Bm.size(0) == K && K % 8 == 0 && N % 16 == 0 && N <= 256);
-    TORCH_CHECK(!(variant & 4) || N % 32 == 0); TORCH_CHECK(!(variant & 8) || K % 32 == 0);
-    auto D = at::zeros({128, N}, A.options());
-    launch_tc_probe(A.data_ptr<float>(), Bm.data_ptr<float>(), D.data_ptr<float>(), K, N, (int)variant, cur_stream());
-    GB_LAUNCH_CHECK();
-    return D;
-}
-
-at::Tensor tc_probe2(at::Tensor A, at::Tensor Bm, bool a_sw, bool b_sw) {
-    // D[M x N] = A[M x K] . Bm[N x K]^T on the tensor core (bring-up of operand layouts)
-    const int M = (int)A.size(0), K = (int)A.size(1), N = (int)Bm.size(0);
-    TORCH_CHECK((M == 64 || M == 128) && Bm.size(1) == K && K % 8 == 0 && N % 16 == 0 && N <= 256);
-    TORCH_CHECK((!a_sw && !b_sw) || K % 32 == 0);
-    auto D = at::zeros({M, N}, A.options());
-    launch_tc_probe2(A.data_ptr<float>(), Bm.data_ptr<float>(), D.data_ptr<float>(), M, N, K, a_sw, b_sw, cur_stream());
-    GB_LAUNCH_CHECK();
-    return D;
-}
-
-std::vector<at::Tensor> tc_probe3(at::Tensor A, int64_t reps, int64_t cols) {
-    TORCH_CHECK(A.size(0) == 128 && A.size(1) == 8 && cols % 64 == 0 && cols <= 192);
-    auto D = at::zeros({128, 16}, A.options());
-    auto T = at::zeros({8}, A.options());
-    launch_tc_probe3(A.data_ptr<float>(), D.data_ptr<float>(), T.data_ptr<float>(), (int)reps, (int)cols, cur_stream());
-    GB_LAUNCH_CHECK();
-    return {D, T};
-}
-
 // ---- bank of linear learners ----------------------------------------------------------------------------
 static BankView bank_view(at::Tensor W, at::Tensor age, at::Tensor S, at::Tensor slot_age, at::Tensor X, at::Tensor y,
                           at::Tensor off, at::Tensor cnt, int64_t D, int64_t kind, int64_t mode, double lr) {
@@ -479,13 +455,13 @@ int64_t device_fault(bool clear) {
 // pre-size the staging buffer of the CURRENT stream for the fused MLP training kernel (init_nodes)
 bool reserve_mlp1_staging(int64_t n, int64_t in_dim, int64_t batch_size, int64_t local_epochs, std::string impl) {
     const int B = (int)(batch_size == 0 ? n : std::min<int64_t>(batch_size, n));
-    const int nc = (impl == "tc8" || impl == "tc8-tf32") ? 8 : 4;
-    const bool x3 = !(impl == "tc4-tf32" || impl == "tc8-tf32");
+    const int nc = 8;
+    const bool x3 = impl != "tc8-tf32";
     return reserve_train_staging((int)n, (int)in_dim, B, (int)local_epochs, nc, x3, cur_stream());
 }
 void preload() {
     preload_merge(); preload_optim(); preload_small(); preload_eval(); preload_train_cluster();
-    preload_train_tc(); preload_train_tc2(); preload_train_tc3(); preload_train_tc4(); preload_stage(); preload_probe(); preload_nvls(); preload_eval_tc(); preload_bank();
+    preload_train_tc3(); preload_train_tc4(); preload_stage(); preload_nvls(); preload_eval_tc(); preload_bank();
     cudaGetLastError();
 }
 
@@ -528,9 +504,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("bank_deliver", &gb::bank_deliver);
     m.def("bank_update", &gb::bank_update);
     m.def("bank_scores", &gb::bank_scores);
-    m.def("tc_probe", &gb::tc_probe);
-    m.def("tc_probe2", &gb::tc_probe2);
-    m.def("tc_probe3", &gb::tc_probe3);
     m.def("ipc_alloc", &gb::ipc_alloc);
     m.def("ipc_free", &gb::ipc_free);
     m.def("ipc_get_handle", &gb::ipc_get_handle);
@@ -543,6 +516,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("device_sm_count", &gb::device_sm_count);
     m.def("preload", &gb::preload);
     m.def("device_fault", &gb::device_fault, py::arg("clear") = true);
+    m.def("set_train_impl", &gb::set_train_impl);
+    m.def("set_eval_tf32", &gb::set_eval_tf32);
     m.def("reserve_mlp1_staging", &gb::reserve_mlp1_staging);
     m.def("allreduce_mean", &gb::allreduce_mean);
     gb::bind_scheduler(m);

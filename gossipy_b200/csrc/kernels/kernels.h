@@ -66,13 +66,13 @@ struct TrainParams {
     // (the peer row is pulled over NVLink while the weights are loaded on chip)
     const float* peer; float w_self, w_peer; PeerSync sync;
 };
-enum TrainImpl { kTrainAuto = 0, kTrainCluster = 1, kTrainTc = 2, kTrainTc2 = 3, kTrainTc3 = 4,
-                 kTrainTc4 = 5, kTrainTc4Tf32 = 6, kTrainTc8 = 7, kTrainTc8Tf32 = 8 };
+// auto = fp32-equivalent: tc8 (3xTF32 on an 8-CTA cluster) -> cluster (fp32 CUDA cores).  Plain-tf32 kernels only by name:
+// tc3 (CTA pair, whole step on the tensor core), tc8-tf32 (8-CTA cluster).
+enum TrainImpl { kTrainAuto = 0, kTrainCluster = 1, kTrainTc3 = 4, kTrainTc8 = 7, kTrainTc8Tf32 = 8 };
 // returns false when the shape is outside the envelope of the requested implementation
 bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const char** why);
-bool mlp1_train_tc(const TrainParams& p, cudaStream_t stream);     // first generation (in-kernel gather)
-bool mlp1_train_tc2(const TrainParams& p, cudaStream_t stream);    // staged operands, 256 threads
-bool mlp1_train_tc3(const TrainParams& p, cudaStream_t stream);    // tc2 + second layer on the tensor core
+void set_default_train_impl(TrainImpl impl);   // meaning of kTrainAuto for this process
+bool mlp1_train_tc3(const TrainParams& p, cudaStream_t stream);    // CTA pair, plain tf32, second layer on the tensor core too
 // fourth generation: nc-CTA cluster (4 or 8), x3 = error-compensated 3xTF32 products (fp32-equivalent)
 bool mlp1_train_tc4(const TrainParams& p, int nc, bool x3, cudaStream_t stream);
 bool reserve_train_staging(int n, int IN, int B, int epochs, int nc, bool x3, cudaStream_t stream);
@@ -89,6 +89,7 @@ void launch_mlp1_eval_pretile(const float* X, int n, int IN, float* out, cudaStr
 bool launch_mlp1_eval_tc(const float* row, const float* xt, const int64_t* y, int n, int IN, int H, int OUT,
                          int n_classes, int* cm, cudaStream_t stream);
 void preload_eval_tc();
+void set_eval_tf32(bool on);            // plain tf32 products instead of the fp32-equivalent 3xTF32 default
 
 // ---- small.cu --------------------------------------------------------------------------------------
 struct LogregParams {
@@ -126,19 +127,9 @@ void launch_bank_scores(const BankView& b, const int* nodes, int n_nodes, const 
                         cudaStream_t st);
 void preload_bank();
 
-// ---- tc_probe.cu -----------------------------------------------------------------------------------
-void launch_tc_probe(const float* A, const float* Bm, float* D, int K, int N, int variant,
-                     cudaStream_t stream);
-
-void launch_tc_probe2(const float* A, const float* Bm, float* D, int M, int N, int K, int a_sw, int b_sw,
-                      cudaStream_t stream);
-
-void launch_tc_probe3(const float* A, float* D, float* timing, int reps, int cols, cudaStream_t stream);
-
 int sm_count();
 // load every kernel of the extension on the current device (see merge.cu: preload_merge)
 void preload_merge(); void preload_optim(); void preload_small(); void preload_eval();
-void preload_train_cluster(); void preload_train_tc(); void preload_train_tc2(); void preload_train_tc3(); void preload_train_tc4(); void preload_stage();
-void preload_probe();
+void preload_train_cluster(); void preload_train_tc3(); void preload_train_tc4(); void preload_stage();
 
 }  // namespace gb

@@ -1,10 +1,15 @@
 // Evaluation of a Linear-ReLU-Linear network on the tensor cores: one CTA per 128-sample
-// tile, a 3-stage bulk-copy pipeline feeding tcgen05.mma (tf32, fp32 accumulate in TMEM), and an
+// tile, a 3-stage bulk-copy pipeline feeding tcgen05.mma (fp32 accumulate in TMEM), and an
 // epilogue that finishes the network (bias + ReLU + second layer + argmax) and reduces the tile to a
 // confusion matrix -- only C*C integers leave the SM.  Reference: gossipy/model/handler.py:282-334
 // (full-test-set forward on the device, predictions shipped to scikit-learn on the host).
 //
-//   z1[128 x NP] = Xtile[128 x IN] . W1[NP x IN]^T        NP = hidden units padded to 16, K in stages of 64
+//   z1[128 x NP] = Xtile[128 x IN] . W1[NP x IN]^T        NP = hidden units padded to 16, K in stages of 32
+//
+// Default (X3): fp32-equivalent products, a.b ~= a_hi.b_hi + a_hi.b_lo + a_lo.b_hi (kind::tf32 truncates its
+// operands, so the raw tiles ARE the hi operands).  The lo images (x - trunc(x), exact) are produced in shared
+// memory by the six otherwise idle warps while the tensor core works on the hi product of the same stage: no
+// second copy of the test set, no extra HBM traffic.  Plain tf32 (GlobalSettings().allow_tf32) skips them.
 //
 // Both operands are read from PRE-TILED images (K-major core matrices, one contiguous block per
 // pipeline stage, so a stage is two cp.async.bulk copies): the test set is tiled once and cached
@@ -17,21 +22,23 @@
 namespace gb {
 
 constexpr int EV_TM = 128;             // samples per tile (MMA M)
-constexpr int EV_KS = 64;              // features per pipeline stage
+constexpr int EV_KS = 32;              // features per pipeline stage
 constexpr int EV_STAGES = 3;
 constexpr int EV_THREADS_TC = 256;
 constexpr int EV_NP_MAX = 128;
-constexpr int EV_A_BYTES = EV_TM * EV_KS * 4;                 // 32768
+constexpr int EV_A_BYTES = EV_TM * EV_KS * 4;                 // 16384
+constexpr int EV_CH = EV_KS / 4;                              // 16-byte chunks per row and stage
+constexpr int EV_SPLIT_WARPS = 6;                             // warps 2..7 write the lo images
 
-// rows x IN (row-major) -> [tile][stage][row group][16 chunks][8 rows][4 floats], zero padded
+// rows x IN (row-major) -> [tile][stage][row group][EV_CH chunks][8 rows][4 floats], zero padded
 __global__ void __launch_bounds__(256)
 eval_pretile_kernel(const float* __restrict__ src, int rows, int IN, int rows_per_tile, int nstage,
                     float* __restrict__ dst, int64_t total_chunks) {
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_chunks;
          q += (int64_t)gridDim.x * blockDim.x) {
         const int r8 = (int)(q & 7);
-        const int c = (int)((q >> 3) & 15);
-        int64_t rest = q >> 7;
+        const int c = (int)((q >> 3) % EV_CH);
+        int64_t rest = (q >> 3) / EV_CH;
         const int groups = rows_per_tile >> 3;
         const int g = (int)(rest % groups); rest /= groups;
         const int s = (int)(rest % nstage);
@@ -53,14 +60,16 @@ eval_pretile_kernel(const float* __restrict__ src, int rows, int IN, int rows_pe
 }
 
 struct EvSmem {
-    static constexpr int a = 0;                                        // [3][32768]
-    static constexpr int b = a + EV_STAGES * EV_A_BYTES;               // [3][NP_MAX*64*4 = 32768]
-    static constexpr int w2 = b + EV_STAGES * EV_NP_MAX * EV_KS * 4;   // [128][12]
+    static constexpr int a = 0;                                        // [3][16384]
+    static constexpr int b = a + EV_STAGES * EV_A_BYTES;               // [3][NP_MAX*32*4 = 16384]
+    static constexpr int alo = b + EV_STAGES * EV_NP_MAX * EV_KS * 4;  // lo images of the same stages
+    static constexpr int blo = alo + EV_STAGES * EV_A_BYTES;
+    static constexpr int w2 = blo + EV_STAGES * EV_NP_MAX * EV_KS * 4; // [128][12]
     static constexpr int b1 = w2 + EV_NP_MAX * 12 * 4;
     static constexpr int part = b1 + EV_NP_MAX * 4;                    // [128][12] partial logits of the second half
     static constexpr int cm = part + EV_TM * 12 * 4;                   // [16*16] int
-    static constexpr int mbar = cm + 256 * 4;                          // full[3], empty[3], done
-    static constexpr int tslot = mbar + 64;
+    static constexpr int mbar = cm + 256 * 4;                          // full[3], empty[3], split[3], done
+    static constexpr int tslot = mbar + 96;
     static constexpr int total = tslot + 16;
 };
 
@@ -69,6 +78,7 @@ GB_DEVICE void ev_bulk(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_
                  :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
+template <bool X3>
 __global__ void __launch_bounds__(EV_THREADS_TC, 1)
 mlp1_eval_tc_kernel(const float* __restrict__ row, const float* __restrict__ xt /* pre-tiled test set */,
                     const float* __restrict__ w1t /* pre-tiled W1 */, const int64_t* __restrict__ y, int n,
@@ -89,7 +99,9 @@ mlp1_eval_tc_kernel(const float* __restrict__ row, const float* __restrict__ xt 
 
     if (warp == 2) tmem_alloc<128>(tslot);
     if (tid == 0) {
-        for (int i = 0; i < 2 * EV_STAGES + 1; ++i) mbar_init(&mbar[i], 1);
+        for (int i = 0; i < 2 * EV_STAGES; ++i) mbar_init(&mbar[i], 1);
+        for (int i = 0; i < EV_STAGES; ++i) mbar_init(&mbar[2 * EV_STAGES + i], EV_SPLIT_WARPS);
+        mbar_init(&mbar[3 * EV_STAGES], 1);
         mbar_fence_init();
     }
     for (int i = tid; i < EV_NP_MAX * 12; i += EV_THREADS_TC) {
@@ -104,7 +116,7 @@ mlp1_eval_tc_kernel(const float* __restrict__ row, const float* __restrict__ xt 
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tslot, 0);
     const int tile = blockIdx.x;
     const float* a_src = xt + (size_t)tile * nstage * (EV_TM * EV_KS);
-    uint64_t* full = mbar, *empty = mbar + EV_STAGES, *done = mbar + 2 * EV_STAGES;
+    uint64_t* full = mbar, *empty = mbar + EV_STAGES, *split = mbar + 2 * EV_STAGES, *done = mbar + 3 * EV_STAGES;
 
     if (warp == 0) {                    // ---- producer: two bulk copies per stage ----
         if (elect_one()) {
@@ -124,16 +136,51 @@ mlp1_eval_tc_kernel(const float* __restrict__ row, const float* __restrict__ xt 
                 const int st = s % EV_STAGES;
                 mbar_wait(&full[st], (uint32_t)((s / EV_STAGES) & 1));
                 tc_fence_after();
-                const uint64_t ad = make_sdesc(smem_u32(smem + EvSmem::a + st * EV_A_BYTES), 128u, 16u * 128u);
-                const uint64_t bd = make_sdesc(smem_u32(smem + EvSmem::b + st * (EV_NP_MAX * EV_KS * 4)), 128u, 16u * 128u);
+                const uint64_t ad = make_sdesc(smem_u32(smem + EvSmem::a + st * EV_A_BYTES), 128u, EV_CH * 128u);
+                const uint64_t bd = make_sdesc(smem_u32(smem + EvSmem::b + st * (EV_NP_MAX * EV_KS * 4)), 128u, EV_CH * 128u);
 #pragma unroll
                 for (int k = 0; k < EV_KS / 8; ++k)
                     mma_tf32_ss(tmem, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), idesc, (s | k) != 0);
+                if (X3) {
+                    mbar_wait(&split[st], (uint32_t)((s / EV_STAGES) & 1));      // lo images of this stage written
+                    tc_fence_after();
+                    const uint64_t al = make_sdesc(smem_u32(smem + EvSmem::alo + st * EV_A_BYTES), 128u, EV_CH * 128u);
+                    const uint64_t bl = make_sdesc(smem_u32(smem + EvSmem::blo + st * (EV_NP_MAX * EV_KS * 4)), 128u, EV_CH * 128u);
+#pragma unroll
+                    for (int k = 0; k < EV_KS / 8; ++k)
+                        mma_tf32_ss(tmem, ad + (uint64_t)(k * 16), bl + (uint64_t)(k * 16), idesc, true);
+#pragma unroll
+                    for (int k = 0; k < EV_KS / 8; ++k)
+                        mma_tf32_ss(tmem, al + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), idesc, true);
+                }
                 mma_commit(&empty[st]);                 // stage is free again when these MMAs retire
             }
             mma_commit(done);
         }
         __syncwarp();
+    }
+    else if (X3) {                      // ---- warps 2..7: lo = x - trunc(x) of both operand tiles of every stage ----
+        const int t2 = tid - 64, n2 = EV_SPLIT_WARPS * 32;
+        const int a4 = EV_A_BYTES / 16, b4 = (int)(b_bytes / 16u);
+        for (int s = 0; s < nstage; ++s) {
+            const int st = s % EV_STAGES;
+            mbar_wait(&full[st], (uint32_t)((s / EV_STAGES) & 1));
+            const float4* as = reinterpret_cast<const float4*>(smem + EvSmem::a + st * EV_A_BYTES);
+            const float4* bs = reinterpret_cast<const float4*>(smem + EvSmem::b + st * (EV_NP_MAX * EV_KS * 4));
+            float4* ad = reinterpret_cast<float4*>(smem + EvSmem::alo + st * EV_A_BYTES);
+            float4* bd = reinterpret_cast<float4*>(smem + EvSmem::blo + st * (EV_NP_MAX * EV_KS * 4));
+            for (int i = t2; i < a4 + b4; i += n2) {
+                const float4 v = i < a4 ? as[i] : bs[i - a4];
+                const float4 lo = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u),
+                                              v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                                              v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u),
+                                              v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+                if (i < a4) ad[i] = lo; else bd[i - a4] = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&split[st])) : "memory");
+        }
     }
     // ---- epilogue: thread (sample = 32*quad + lane, half) finishes its half of the hidden units ----
     mbar_wait(done, 0u);
@@ -210,6 +257,9 @@ void launch_mlp1_eval_pretile(const float* X, int n, int IN, float* out, cudaStr
 struct W1Slot { float* ptr; cudaStream_t stream; int dev; };
 static W1Slot g_w1slots[256] = {};
 
+static bool g_eval_tf32 = false;        // GlobalSettings().allow_tf32: plain tf32 products in the evaluation kernel
+void set_eval_tf32(bool on) { g_eval_tf32 = on; }
+
 bool launch_mlp1_eval_tc(const float* row, const float* xt, const int64_t* y, int n, int IN, int H, int OUT,
                          int n_classes, int* cm, cudaStream_t stream) {
     if (H > EV_NP_MAX || OUT > 10 || n_classes > 16 || n <= 0 || IN % 4 != 0) return false;
@@ -228,7 +278,7 @@ bool launch_mlp1_eval_tc(const float* row, const float* xt, const int64_t* y, in
     if (slot != nullptr && w1_floats > slot_floats) return false;       // shape grew: let the simt kernel handle it
     if (slot == nullptr) {
         if (free_i < 0) return false;
-        const size_t want = std::max(w1_floats, (size_t)16 * EV_NP_MAX * EV_KS);   // room for IN <= 1024
+        const size_t want = std::max(w1_floats, (size_t)(1024 / EV_KS) * EV_NP_MAX * EV_KS);   // room for IN <= 1024
         if (cudaMalloc(&slot, want * 4) != cudaSuccess) { cudaGetLastError(); return false; }
         slot_floats = std::max(slot_floats, want);
         if (w1_floats > want) return false;
@@ -238,20 +288,24 @@ bool launch_mlp1_eval_tc(const float* row, const float* xt, const int64_t* y, in
     eval_pretile_kernel<<<(int)((chunks + 255) / 256), 256, 0, stream>>>(row, H, IN, NP, nstage, slot, chunks);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(mlp1_eval_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EvSmem::total) != cudaSuccess)
+        if (cudaFuncSetAttribute(mlp1_eval_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EvSmem::total) != cudaSuccess ||
+            cudaFuncSetAttribute(mlp1_eval_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EvSmem::total) != cudaSuccess)
             return false;
         configured = true;
     }
     const int ntile = (n + EV_TM - 1) / EV_TM;
-    mlp1_eval_tc_kernel<<<ntile, EV_THREADS_TC, EvSmem::total, stream>>>(row, xt, slot, y, n, IN, H, OUT, NP, nstage,
-                                                                       n_classes, cm);
+    if (g_eval_tf32)
+        mlp1_eval_tc_kernel<false><<<ntile, EV_THREADS_TC, EvSmem::total, stream>>>(row, xt, slot, y, n, IN, H, OUT, NP, nstage, n_classes, cm);
+    else
+        mlp1_eval_tc_kernel<true><<<ntile, EV_THREADS_TC, EvSmem::total, stream>>>(row, xt, slot, y, n, IN, H, OUT, NP, nstage, n_classes, cm);
     return cudaGetLastError() == cudaSuccess;
 }
 
 void preload_eval_tc() {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, eval_pretile_kernel);
-    cudaFuncGetAttributes(&a, mlp1_eval_tc_kernel);
+    cudaFuncGetAttributes(&a, mlp1_eval_tc_kernel<true>);
+    cudaFuncGetAttributes(&a, mlp1_eval_tc_kernel<false>);
 }
 
 }  // namespace gb

@@ -1,4 +1,4 @@
-// Device-side data loader of the tcgen05 training kernel (mlp1_train_tc2.cu).
+// Device-side data loader of the CTA-pair tcgen05 training kernel (mlp1_train_tc3.cu).
 //
 // One local update visits the node's shard in a keyed pseudo-random order (the engine's Feistel
 // permutation, one key per epoch).  Instead of gathering 32 random rows per SGD step INSIDE the

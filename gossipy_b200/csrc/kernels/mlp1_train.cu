@@ -338,33 +338,25 @@ static bool launch_cluster(const TrainParams& p, bool scaled, cudaStream_t strea
 }
 
 // auto = fp32-equivalent: tc4 (4-CTA cluster, 3xTF32 tcgen05) -> cluster kernel (fp32 CUDA cores).  The plain-tf32
-// variants (tc3, tc4-tf32, tc8-tf32) run only when asked for by name (GlobalSettings().allow_tf32 / impl=...).
+// variants (tc3, tc8-tf32) run only when asked for by name (GlobalSettings().allow_tf32 / impl=...).
+static TrainImpl g_auto_impl = kTrainAuto;     // what "auto" means for this process (ops.set_train_impl / allow_tf32)
+void set_default_train_impl(TrainImpl impl) { g_auto_impl = impl; }
+
 bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const char** why) {
     static const char* kNone = "";
     *why = kNone;
+    if (impl == kTrainAuto) impl = g_auto_impl;
     const bool scaled = p.part_id != nullptr && p.ages != nullptr;
     if (scaled && p.n_parts > MAX_PARTS) { *why = "fused partitioned training supports <= 16 partitions"; return false; }
     if (impl != kTrainCluster && !scaled) {
         switch (impl) {
-        case kTrainTc4: case kTrainTc4Tf32: case kTrainTc8: case kTrainTc8Tf32: {
-            const int nc = (impl == kTrainTc8 || impl == kTrainTc8Tf32) ? 8 : 4;
-            const bool x3 = impl == kTrainTc8;
-            if (impl == kTrainTc4) { *why = "the fp32-equivalent tcgen05 kernel runs on 8-CTA clusters: use impl='tc8'"; return false; }
-            if (mlp1_train_tc4(p, nc, x3, stream)) return true;
+        case kTrainTc8: case kTrainTc8Tf32:
+            if (mlp1_train_tc4(p, 8, impl == kTrainTc8, stream)) return true;
             *why = "tcgen05 (tc4) training kernel does not support this configuration";
             return false;
-        }
         case kTrainTc3:
             if (mlp1_train_tc3(p, stream)) return true;
             *why = "tcgen05 (tc3) training kernel does not support this configuration";
-            return false;
-        case kTrainTc2:
-            if (mlp1_train_tc2(p, stream)) return true;
-            *why = "tcgen05 (tc2) training kernel does not support this configuration";
-            return false;
-        case kTrainTc:
-            if (mlp1_train_tc(p, stream)) return true;
-            *why = "tcgen05 training kernel does not support this configuration";
             return false;
         default:
             if (mlp1_train_tc4(p, 8, true, stream)) return true;

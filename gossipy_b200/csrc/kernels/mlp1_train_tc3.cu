@@ -1,4 +1,5 @@
-// tcgen05 / TMEM training kernel, third generation ("tc3"): mlp1_train_tc3.cu with the SECOND LAYER on
+// tcgen05 / TMEM training kernel, CTA-pair variant ("tc3", plain tf32 products: opt-in, see mlp1_train_tc4.cu for the
+// fp32-equivalent default): the whole SGD step incl. the SECOND LAYER on
 // the tensor core as well.  Per SGD step the CTA pair issues five GEMMs:
 //
 //   fwd   z1^T[128 x 32]  = W1(TMEM, fp32 master) . X^T                       (M128 N32  K392, TS mode)
@@ -12,7 +13,7 @@
 // (j, half) reads row j of dh^T / gW2^T straight out of TMEM.  Operand images in shared memory:
 // h (b-major, 128-byte swizzle so the 16 per-thread stores are conflict free), h^T, W2 (K = j, swizzled),
 // W2^T (K = o), dz2 and dz2^T (no-swizzle core matrices).  Everything else (loader, bulk copies,
-// st.async exchange, lazy weight decay, fused MERGE_UPDATE) is as in tc2.
+// st.async exchange, lazy weight decay, fused MERGE_UPDATE): see the sections below.
 // Reference semantics: gossipy/model/handler.py:235-258.  tf32 products, fp32 accumulation/master.
 #include "tc_common.cuh"
 #include "kernels.h"

@@ -923,8 +923,8 @@ static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
 
 // nc in {4, 8}; x3 = error-compensated (fp32-equivalent) products, otherwise plain tf32
 bool mlp1_train_tc4(const TrainParams& p, int nc, bool x3, cudaStream_t stream) {
-    if (x3) return nc == 8 && tc4_launch<8, true>(p, stream);
-    return nc == 8 ? tc4_launch<8, false>(p, stream) : tc4_launch<4, false>(p, stream);
+    if (nc != 8) return false;      // (the kernel is written for NC in {4, 8}; only the 8-CTA form is validated and shipped)
+    return x3 ? tc4_launch<8, true>(p, stream) : tc4_launch<8, false>(p, stream);
 }
 
 // allocate the staging buffer of `stream` ahead of time (init_nodes): no cudaMalloc -- an implicit device-wide
@@ -938,7 +938,6 @@ bool reserve_train_staging(int n, int IN, int B, int epochs, int nc, bool x3, cu
 // on a cross-GPU flag could deadlock, so the extension loads everything up front)
 void preload_train_tc4() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<4, false>);
     cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, true>);
     cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, false>);
     cudaFuncGetAttributes(&a, mlp1_stage4_kernel<true>);

@@ -163,7 +163,32 @@ def adam_step(p, g, n, m, v, step, lr, beta1, beta2, eps, weight_decay=0.0,
 
 
 MergeFrom = Tuple[torch.Tensor, float, float, Optional[RowSync]]   # (peer row, w_self, w_peer, sync)
-TRAIN_IMPL = ""   # "", "cluster" or "tc": process-wide override of the MLP training kernel choice
+TRAIN_IMPL = ""   # process-wide choice of the fused MLP training kernel, see set_train_impl()
+TRAIN_IMPLS = ("", "auto", "tc8", "cluster", "tc8-tf32", "tc3")
+
+
+def set_train_impl(name: str = "") -> None:
+    """Choose the fused MLP training kernel for this process (Python handlers and the C++ executor).
+
+    ``""`` / ``"auto"`` (default): fp32-equivalent -- ``tc8`` (error-compensated 3xTF32 tcgen05 kernel on an 8-CTA
+    cluster) with the fp32 CUDA-core ``cluster`` kernel as fall-back.  The plain-tf32 kernels (``tc8-tf32``, ``tc3``) truncate operands to 10 mantissa bits -- below the reference's fp32 -- and run only when
+    asked for by name or through ``GlobalSettings().allow_tf32 = True``."""
+    global TRAIN_IMPL
+    if name not in TRAIN_IMPLS:
+        raise ValueError("unknown training kernel %r (one of %s)" % (name, ", ".join(repr(t) for t in TRAIN_IMPLS)))
+    TRAIN_IMPL = "" if name == "auto" else name
+    from .native import native_available, _try_import
+    if native_available():
+        _try_import().set_train_impl(TRAIN_IMPL)
+
+
+def train_dtype() -> str:
+    """Human-readable arithmetic of the fused MLP training path in use (bench / reports)."""
+    if TRAIN_IMPL in ("tc8-tf32", "tc3"):
+        return "tf32 (operands truncated to 10 mantissa bits, fp32 accumulate and master weights)"
+    if TRAIN_IMPL == "cluster":
+        return "fp32"
+    return "fp32-equivalent (3xTF32 error-compensated tcgen05 products, fp32 accumulate; second layer exact fp32)"
 
 
 def _cpu_premerge(row, merge_from: Optional[MergeFrom]) -> None:
@@ -198,6 +223,12 @@ def mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, key,
 
 
 EVAL_IMPL = ""          # "", "tc" or "simt": evaluation kernel choice ("" = tensor cores when the shape fits)
+
+
+def set_eval_tf32(on: bool) -> None:
+    from .native import native_available, _try_import
+    if native_available():
+        _try_import().set_eval_tf32(bool(on))
 _PRETILED: dict = {}     # id(X) -> (X, pre-tiled copy): the test set is tiled once for the tcgen05 kernel
 
 

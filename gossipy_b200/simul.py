@@ -101,6 +101,21 @@ class SimulationEventSender(ABC):
             r.update_end()
 
 
+def _check_device_fault() -> None:
+    """Bounded device-side waits (cross-GPU ``ready`` flags, all-reduce epochs) report a timeout in a per-device
+    fault word instead of hanging the GPU; surface it where the host synchronises anyway."""
+    if GlobalSettings().get_device().type != "cuda":
+        return
+    from .ops.native import native_available, native
+    if not native_available():
+        return
+    bits = int(native().device_fault(True))
+    if bits:
+        raise RuntimeError("gossipy_b200: device fault word = %d (1: a wait for a peer's model timed out, 2: an "
+                           "all-reduce epoch timed out, 4: handshake ticket shared by two launches) -- results "
+                           "of this round are invalid" % bits)
+
+
 class SimulationReport(SimulationEventReceiver):
     """Message counters and per-round mean metrics (ref ``simul.py:180-270``)."""
 
@@ -323,6 +338,8 @@ class GossipSimulator(SimulationEventSender):
                 self.notify_evaluation(t, True, _prt.share_metrics([p.result() for p in local]))
             if glob:
                 self.notify_evaluation(t, False, _prt.share_metrics([p.result() for p in glob]))
+            if (local or glob) and _prt.active():
+                _check_device_fault()
         if defer:
             return finish
         finish()
@@ -542,7 +559,8 @@ class GossipSimulator(SimulationEventSender):
     # native engine: execute bankable set-ups (linear learners) many nodes per launch.  "auto" = on a GPU, or from
     # 512 nodes on the CPU (where the bank's vectorised-over-nodes update loses to per-node calls for a few big shards)
     batched: Any = "auto"
-    native_executor = False   # native engine: enqueue eligible set-ups from C++ (engine/stream_exec.py); opt-in
+    native_executor = True    # native engine: eligible set-ups are enqueued from C++ (engine/stream_exec.py);
+                              # everything else (other node / handler types) goes through the per-event Python executor
 
     def _run_native_streamed(self, sch, n_rounds: int) -> None:
         """Rounds of an eligible simulation (``engine.stream_exec.eligible``): the scheduler's event list
