@@ -106,6 +106,12 @@ def timing(impl):
     print(json.dumps(out))
 
 
+if IMPLS == ["ncuonly"]:          # a handful of flagship updates for ncu to capture
+    X, y, row = problem(7500, 784, 100, 10)
+    for _ in range(4):
+        ops.mlp1_train(row, X, y, (784, 100, 10), 32, 1, 0.1, 0.0, 1234)
+    torch.cuda.synchronize()
+    IMPLS = []
 for impl in IMPLS:
     try:
         if impl != "cluster":

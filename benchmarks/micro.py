@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Micro-benchmarks of the hot ops (CUDA events, warm-up, L2 flush between iterations).
 
-    python benchmarks/micro.py train|eval|merge|overlap|all [--impl cluster|tc]
+    python benchmarks/micro.py train|eval|merge|overlap|all [--impl cluster|tc8|tc8-tf32|tc3]
 """
 from __future__ import annotations
 
@@ -74,9 +74,9 @@ def bench_train(impl):
     per_step = (med - med10) / (steps - 10)
     print(json.dumps({"op": "mlp1_train fixed cost", "impl": impl or "auto", "ms_10_steps": med10,
                       "us_per_step_marginal": per_step * 1e3, "fixed_us_per_launch": (med10 - 10 * per_step) * 1e3}))
-    if impl in ("", "tc2", "tc3"):   # per-phase cycle counters of the tc2/tc3 kernel (thread 0 of CTA 0)
+    if impl == "tc3":   # per-phase cycle counters of the CTA-pair kernel (thread 0 of both CTAs); tc8: benchmarks/check_tc4.py
         from gossipy_b200.ops.native import native
-        dbg = native().mlp1_train_tc_debug(row, X, y, DIMS, 32, 1, 0.1, 0.0, 1234, impl or "tc2")
+        dbg = native().mlp1_train_tc_debug(row, X, y, DIMS, 32, 1, 0.1, 0.0, 1234, impl)
         raw = dbg[0, :17].tolist()
         raw1 = dbg[1, :17].tolist()          # CTA 1 of the pair (tc3)
         names = ["A+B issue fwd MMA (+wait X tile, +wait upd(s-1), request X^T)", "C wait fwd MMA + tmem_ld",
@@ -101,13 +101,15 @@ def bench_train(impl):
 def bench_eval():
     X, y, row = problem(10000)
     flops = 10000 * 2 * (784 * 100 + 100 * 10)
-    for impl in ("simt", "tc"):
-        ops.EVAL_IMPL = impl
+    for impl in ("simt", "tc", "tc-tf32"):
+        ops.EVAL_IMPL = "tc" if impl == "tc-tf32" else impl
+        ops.set_eval_tf32(impl == "tc-tf32")       # "tc": fp32-equivalent (3xTF32, the default); "tc-tf32": plain tf32
         med, best = timeit(lambda: ops.mlp1_eval(row, X, y, DIMS, 10), iters=10)
         print(json.dumps({"op": "mlp1_eval", "impl": impl, "ms": med, "best_ms": best, "tflops": flops / med / 1e9,
                           "x_read_gbs": 10000 * 784 * 4 / med / 1e6,
                           "frac_of_measured_hbm": 10000 * 784 * 4 / med / 1e6 / PEAKS["hbm_gbs"]}))
     ops.EVAL_IMPL = ""
+    ops.set_eval_tf32(False)
 
 
 def bench_merge():

@@ -348,6 +348,10 @@ bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const
     if (impl == kTrainAuto) impl = g_auto_impl;
     const bool scaled = p.part_id != nullptr && p.ages != nullptr;
     if (scaled && p.n_parts > MAX_PARTS) { *why = "fused partitioned training supports <= 16 partitions"; return false; }
+    if (scaled && (impl == kTrainAuto || impl == kTrainTc8)) {     // K3 on the tensor-core kernel (<= 16 partitions)
+        if (mlp1_train_tc4(p, 8, true, stream)) return true;
+        if (impl == kTrainTc8) { *why = "tcgen05 (tc8) training kernel does not support this partitioned configuration"; return false; }
+    }
     if (impl != kTrainCluster && !scaled) {
         switch (impl) {
         case kTrainTc8: case kTrainTc8Tf32:

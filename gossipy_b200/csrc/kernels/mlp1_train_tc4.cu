@@ -25,6 +25,10 @@
 //   slice of the new W2 (4-byte st.async, off the critical path) -- every CTA holds identical b1 / W2 / b2 replicas.
 // The second layer (32 x 100 x 10) therefore runs DISTRIBUTED on the CUDA cores in exact fp32, ~15 kFLOP per CTA and
 // step: as tf32 MMAs it is 19 M64/M128 K8 instructions of ~45 cycles each, 57 with error compensation.
+// K3 (SC = true): PartitionedTMH divides the gradient of every parameter by the age of its partition
+// (reference model/handler.py:497-520).  Because the update reaches the master through registers anyway (W += G),
+// the per-element factor 1/age[part(j, k)] is applied there -- partition ids of a thread's 56 weights are packed
+// into 7 registers at kernel start -- and to the b1 / W2 / b2 steps; the tensor-core work is unchanged.
 // Warp roles: warps 0-7 compute, warp 8 issues all MMAs and bulk copies and never touches data.
 // Operand tiles (hi and lo images of X in both K-major layouts) are written ahead of time by mlp1_stage4_kernel.
 #include "tc_common.cuh"
@@ -65,7 +69,8 @@ template <int NC, bool X3> struct T4Cfg {
     static constexpr int dzo = dzb + T4_B * T4_DZP * 4;          // dz2 of my own samples [S][12]
     static constexpr int red = dzo + 8 * T4_DZP * 4;             // [8 warps][40]
     static constexpr int b2 = red + 8 * 40 * 4;
-    static constexpr int ys = b2 + 16 * 4;                       // [2][32] int
+    static constexpr int inva = b2 + 16 * 4;                     // [2][16] 1/age of every partition, this / next step
+    static constexpr int ys = inva + 2 * 16 * 4;                 // [2][32] int
     static constexpr int mbar = ys + 2 * T4_B * 4;               // 10 x uint64
     static constexpr int tslot = mbar + 128;
     static constexpr int total = tslot + 16;
@@ -127,7 +132,7 @@ GB_DEVICE void warp_reduce40(float (&v)[40], int lane) {
     }
 }
 
-template <int NC, bool X3>
+template <int NC, bool X3, bool SC>
 __global__ void __launch_bounds__(T4_THREADS, 1)
 mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const int total_steps,
                       const float* __restrict__ stage, const int* __restrict__ stage_ys) {
@@ -157,6 +162,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
     float* dzo = reinterpret_cast<float*>(smem + C::dzo);
     float* red = reinterpret_cast<float*>(smem + C::red);
     float* b2s = reinterpret_cast<float*>(smem + C::b2);
+    float* inva = reinterpret_cast<float*>(smem + C::inva);
     int* ysm = reinterpret_cast<int*>(smem + C::ys);
     // 0 xf landed, 1 xt landed, 2 forward done, 3 update done, 4 W2 all-gather, 5 RS, 6 AG, 7 a2 ready (256), 8 W/Wlo ready (256),
     // 9 h slices of my W2 columns
@@ -221,6 +227,10 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
         w2s[i] = (o < OUT && jj < H) ? p.row[off_w2 + (size_t)o * H + jj] : 0.f;
     }
     if (tid < 16) b2s[tid] = (tid < OUT) ? p.row[off_b2 + tid] : -3.0e38f;   // padding classes: probability 0
+    if (SC && tid < 16) {        // ages are incremented before the step (reference handler.py:506)
+        inva[tid] = tid < p.n_parts ? 1.f / (float)(p.ages[tid] + 1) : 1.f;
+        inva[16 + tid] = 1.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -431,6 +441,34 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             mbar_expect_tx(&mbar[9], hs_bytes);
             mbar_expect_tx(&mbar[4], w2_bytes);
         }
+        // K3: partition ids (4 bits each) of the master-weight entries this thread adds G to, and of its small parameters
+        uint32_t pidw[SC ? 8 : 1];
+        uint32_t pid_b1 = 0u, pid_b2 = 0u, pid_w2 = 0u;
+        if (SC) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pidw[q] = 0u;
+            const int ngrp = FP >> 4;
+            int gi = 0;
+            for (int g = half; g < ngrp; g += 2, ++gi) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int col = g * 16 + i;
+                    uint32_t pid = 0u;
+                    if (j < H && col < fcnt) pid = (uint32_t)p.part_id[(size_t)j * IN + f0 + col] & 15u;
+                    if (gi < 4) pidw[2 * gi + (i >> 3)] |= pid << (4 * (i & 7));
+                }
+            }
+            if (j < H) pid_b1 = (uint32_t)p.part_id[off_b1 + j] & 15u;
+            if (warp == 5 && lane < OUT) pid_b2 = (uint32_t)p.part_id[off_b2 + lane] & 15u;
+            if (tid < ((js_valid + 3) >> 2) * T4_OUTV) {
+                const int jq = tid / T4_OUTV, o = tid - jq * T4_OUTV;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int jg = (int)rank * JS + 4 * jq + u;
+                    if (jg < H && o < OUT) pid_w2 |= ((uint32_t)p.part_id[off_w2 + (size_t)o * H + jg] & 15u) << (4 * u);
+                }
+            }
+        }
 
         for (int s = 0; s < total_steps; ++s) {
             const int par = s & 1;
@@ -599,6 +637,8 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             // (4) off the critical path: my slice of W2 (all samples), db2, labels of the next step
             if (tid >= 64 && tid < 96 && s + 1 < total_steps)
                 ysm[(par ^ 1) * T4_B + (tid - 64)] = stage_ys[(size_t)(s + 1) * T4_B + (tid - 64)];
+            if (SC && tid >= 96 && tid < 96 + p.n_parts)          // 1/age of the next step (ages grow by one per step)
+                inva[16 * (par ^ 1) + (tid - 96)] = 1.f / (float)(p.ages[tid - 96] + (int64_t)s + 2);
             if (warp == 5) {                                     // db2[o] = sum_b dz2[b][o]: lane = sample
                 const float4* dr = reinterpret_cast<const float4*>(dzb + (size_t)lane * T4_DZP);
                 const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2];
@@ -609,7 +649,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                     float g = dv[0];
 #pragma unroll
                     for (int o = 1; o < T4_OUTV; ++o) g = (lane == o) ? dv[o] : g;
-                    b2s[lane] = fmaf(-p.lr, g, b2s[lane] * decay);
+                    b2s[lane] = fmaf(SC ? -p.lr * inva[16 * par + pid_b2] : -p.lr, g, b2s[lane] * decay);
                 }
             }
             if (js_valid > 0) {
@@ -634,10 +674,15 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                     const int jg = (int)rank * JS + 4 * jq;
                     float* slot = w2s + o * T4_HP + jg;
                     const float4 wo = *reinterpret_cast<const float4*>(slot);
-                    const float4 wn = make_float4(jg < H ? fmaf(-p.lr, g[0], wo.x * decay) : 0.f,
-                                                  jg + 1 < H ? fmaf(-p.lr, g[1], wo.y * decay) : 0.f,
-                                                  jg + 2 < H ? fmaf(-p.lr, g[2], wo.z * decay) : 0.f,
-                                                  jg + 3 < H ? fmaf(-p.lr, g[3], wo.w * decay) : 0.f);
+                    float l0 = -p.lr, l1 = -p.lr, l2 = -p.lr, l3 = -p.lr;
+                    if (SC) {          // (one W2 group per thread: e == tid, see the packing above)
+                        const float* ia = inva + 16 * par;
+                        l0 *= ia[pid_w2 & 15u]; l1 *= ia[(pid_w2 >> 4) & 15u]; l2 *= ia[(pid_w2 >> 8) & 15u]; l3 *= ia[(pid_w2 >> 12) & 15u];
+                    }
+                    const float4 wn = make_float4(jg < H ? fmaf(l0, g[0], wo.x * decay) : 0.f,
+                                                  jg + 1 < H ? fmaf(l1, g[1], wo.y * decay) : 0.f,
+                                                  jg + 2 < H ? fmaf(l2, g[2], wo.z * decay) : 0.f,
+                                                  jg + 3 < H ? fmaf(l3, g[3], wo.w * decay) : 0.f);
 #pragma unroll
                     for (int d = 0; d < NC; ++d)
                         st_async_v4(gb_map_shared(slot, (uint32_t)d), wn, gb_map_shared(&mbar[4], (uint32_t)d));
@@ -661,8 +706,16 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                         tmem_ld16(tlane + C::t_g + (g + 2) * 16, gv2);
                     }
                     tmem_ld_wait();
+                    if (SC) {
+                        const float* ia = inva + 16 * par;
+                        const int gi = (g - half) >> 1;
+                        const uint32_t pa = gi == 0 ? pidw[0] : gi == 2 ? pidw[4] : 0u, pb = gi == 0 ? pidw[1] : gi == 2 ? pidw[5] : 0u;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) wv[i] += gv[i];
+                        for (int i = 0; i < 16; ++i) wv[i] = fmaf(gv[i], ia[((i < 8 ? pa : pb) >> (4 * (i & 7))) & 15u], wv[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) wv[i] += gv[i];
+                    }
                     tmem_st16(tlane + C::t_w1 + g * 16, wv);
                     if (more) {
 #pragma unroll
@@ -670,8 +723,16 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                         tmem_st16(tlane + C::t_wlo + g * 16, gv);
                     }
                     if (two) {
+                        if (SC) {
+                            const float* ia = inva + 16 * par;
+                            const int gi = ((g - half) >> 1) + 1;
+                            const uint32_t pa = gi == 1 ? pidw[2] : gi == 3 ? pidw[6] : 0u, pb = gi == 1 ? pidw[3] : gi == 3 ? pidw[7] : 0u;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) wv2[i] += gv2[i];
+                            for (int i = 0; i < 16; ++i) wv2[i] = fmaf(gv2[i], ia[((i < 8 ? pa : pb) >> (4 * (i & 7))) & 15u], wv2[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) wv2[i] += gv2[i];
+                        }
                         tmem_st16(tlane + C::t_w1 + (g + 2) * 16, wv2);
                         if (more) {
 #pragma unroll
@@ -689,7 +750,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             bar_compute();                                       // end of step: gb1p complete, buffers of this step consumed
             T4_STAMP(11);
             if (tid == 0) mbar_expect_tx(&mbar[9], hs_bytes);    // next step's h slices
-            b1r = fmaf(-p.lr, gb1p[j] + gb1p[T4_HP + j], b1r * decay);
+            b1r = fmaf(SC ? -p.lr * inva[16 * par + pid_b1] : -p.lr, gb1p[j] + gb1p[T4_HP + j], b1r * decay);
             sscale = s_next;
         }
         // the last step's W2 all-gather
@@ -882,7 +943,7 @@ static void* stage_buffer_for4(cudaStream_t stream, size_t bytes, bool may_alloc
     return ptr;
 }
 
-template <int NC, bool X3>
+template <int NC, bool X3, bool SC>
 static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
     using C = T4Cfg<NC, X3>;
     if (p.H > T4_HP || p.OUT > T4_OUTV || p.B > T4_B || p.IN % 4 != 0) return false;
@@ -906,7 +967,8 @@ static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
         }
         mlp1_stage4_kernel<X3><<<dim3(steps, NC), 256, smem, stream>>>(p.X, p.y, p.n, p.IN, p.B, p.epochs, p.key, NC, FPC, FP, out, ys);
     }
-    auto kern = mlp1_train_tc4_kernel<NC, X3>;
+    if (SC && (p.n_parts > 16 || p.part_id == nullptr || p.ages == nullptr)) return false;
+    auto kern = mlp1_train_tc4_kernel<NC, X3, SC>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::total + 1024) != cudaSuccess) return false;
@@ -924,7 +986,9 @@ static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
 // nc in {4, 8}; x3 = error-compensated (fp32-equivalent) products, otherwise plain tf32
 bool mlp1_train_tc4(const TrainParams& p, int nc, bool x3, cudaStream_t stream) {
     if (nc != 8) return false;      // (the kernel is written for NC in {4, 8}; only the 8-CTA form is validated and shipped)
-    return x3 ? tc4_launch<8, true>(p, stream) : tc4_launch<8, false>(p, stream);
+    const bool scaled = p.part_id != nullptr && p.ages != nullptr;
+    if (scaled) return x3 && tc4_launch<8, true, true>(p, stream);      // K3 rides on the W += G pass of the X3 form
+    return x3 ? tc4_launch<8, true, false>(p, stream) : tc4_launch<8, false, false>(p, stream);
 }
 
 // allocate the staging buffer of `stream` ahead of time (init_nodes): no cudaMalloc -- an implicit device-wide
@@ -938,8 +1002,9 @@ bool reserve_train_staging(int n, int IN, int B, int epochs, int nc, bool x3, cu
 // on a cross-GPU flag could deadlock, so the extension loads everything up front)
 void preload_train_tc4() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, true>);
-    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, true, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, true, true>);
+    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, false, false>);
     cudaFuncGetAttributes(&a, mlp1_stage4_kernel<true>);
     cudaFuncGetAttributes(&a, mlp1_stage4_kernel<false>);
 }

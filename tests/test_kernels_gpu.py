@@ -136,18 +136,30 @@ def test_mlp1_train_cluster_matches_oracle(dims, n, bs, ep, wd):
     assert not torch.equal(row, _mlp_problem(n, *dims)[2])
 
 
-def test_mlp1_train_partition_scaled_matches_oracle():
+@pytest.mark.parametrize("impl,n_parts", [("cluster", 4), ("tc8", 4), ("tc8", 7), ("", 4)])
+def test_mlp1_train_partition_scaled_matches_oracle(impl, n_parts):
+    """K3: per-partition 1/age gradient scaling (PartitionedTMH) inside the fused kernels; the tensor-core kernel applies
+    it where the update meets the master weights (W += G / age) and is held to fp32 accuracy."""
     ops, ref = _ops()
     from gossipy_b200.model.nn import TorchMLP
     from gossipy_b200.model.sampling import TorchModelPartition
     dims = (784, 100, 10)
     X, y, row = _mlp_problem(200, *dims)
-    part = TorchModelPartition(TorchMLP(*dims[::2], (dims[1],)), 4)
-    pid = part.part_id.cuda(); ages = torch.tensor([3, 0, 7, 1], device="cuda")
+    part = TorchModelPartition(TorchMLP(*dims[::2], (dims[1],)), n_parts)
+    pid = part.part_id.cuda(); ages = torch.tensor([3, 0, 7, 1, 12, 2, 5][:n_parts], device="cuda")
     want = row.clone()
     ref.mlp1_train(want, X, y, dims, 32, 1, 1., .001, 99, (pid, ages))
-    ops.mlp1_train(row, X, y, dims, 32, 1, 1., .001, 99, (pid, ages), impl="cluster")
-    torch.testing.assert_close(row, want, rtol=2e-3, atol=2e-4)
+    ops.mlp1_train(row, X, y, dims, 32, 1, 1., .001, 99, (pid, ages), impl=impl)
+    if impl == "cluster":
+        torch.testing.assert_close(row, want, rtol=2e-3, atol=2e-4)
+    else:
+        w64 = _mlp_problem(200, *dims)[2].double()
+        ref.mlp1_train(w64, X.double(), y, dims, 32, 1, 1., .001, 99, (pid, ages))
+        P = 79510
+        e_k = float((row[:P].double() - w64[:P]).norm() / w64[:P].norm())
+        e_32 = float((want[:P].double() - w64[:P]).norm() / w64[:P].norm())
+        assert e_k < 4 * e_32 + 1e-7, (e_k, e_32)
+        torch.testing.assert_close(row, want, rtol=1e-4, atol=2e-6)
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc", "tc-tf32"])
