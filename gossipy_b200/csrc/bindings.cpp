@@ -124,6 +124,16 @@ void adam_step(at::Tensor p, at::Tensor g, int64_t n, at::Tensor m, at::Tensor v
 // ---- fused local updates -----------------------------------------------------------------------------
 static thread_local float* g_debug_ptr = nullptr;
 
+// partition ages: a device tensor is passed by pointer, a host tensor (<= 16 partitions) by value in the launch
+// parameters -- no H2D copy, nothing for the host to wait for
+template <class P> static void set_ages(P& p, const at::Tensor& ages) {
+    p.n_parts = (int)ages.numel();
+    if (ages.is_cuda()) { p.ages = ages.data_ptr<int64_t>(); return; }
+    TORCH_CHECK(p.n_parts <= kMaxPartsByValue && ages.is_contiguous(), "host-side partition ages: at most 16 partitions");
+    p.ages = nullptr; p.use_ages_val = true;
+    for (int i = 0; i < p.n_parts; ++i) p.ages_val[i] = ages.data_ptr<int64_t>()[i];
+}
+
 static TrainImpl parse_train_impl(const std::string& impl) {
     const TrainImpl which = impl == "cluster" ? kTrainCluster : impl == "tc3" ? kTrainTc3
                             : impl == "tc8" ? kTrainTc8 : impl == "tc8-tf32" ? kTrainTc8Tf32 : kTrainAuto;
@@ -152,10 +162,9 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
     p.row = row.data_ptr<float>(); p.X = X.data_ptr<float>(); p.y = y.data_ptr<int64_t>();
     p.dbg = g_debug_ptr;
     if (part_id.has_value() && ages.has_value()) {
-        TORCH_CHECK(part_id->is_cuda() && part_id->scalar_type() == at::kLong && ages->is_cuda() &&
-                    ages->scalar_type() == at::kLong);
-        p.part_id = part_id->data_ptr<int64_t>(); p.ages = ages->data_ptr<int64_t>();
-        p.n_parts = (int)ages->numel();
+        TORCH_CHECK(part_id->is_cuda() && part_id->scalar_type() == at::kLong && ages->scalar_type() == at::kLong);
+        p.part_id = part_id->data_ptr<int64_t>();
+        set_ages(p, *ages);
     }
     if (peer.has_value()) {
         TORCH_CHECK(peer->is_cuda() && peer->scalar_type() == at::kFloat && peer->numel() >= P);
@@ -258,8 +267,8 @@ int64_t logreg_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int6
     p.epochs = (int)local_epochs; p.lr = (float)lr; p.wd = (float)wd; p.key = (uint64_t)key;
     p.row = row.data_ptr<float>(); p.X = X.data_ptr<float>(); p.y = y.data_ptr<int64_t>();
     if (part_id.has_value() && ages.has_value()) {
-        p.part_id = part_id->data_ptr<int64_t>(); p.ages = ages->data_ptr<int64_t>();
-        p.n_parts = (int)ages->numel();
+        p.part_id = part_id->data_ptr<int64_t>();
+        set_ages(p, *ages);
     }
     if (peer.has_value()) {
         TORCH_CHECK(peer->is_cuda() && peer->scalar_type() == at::kFloat);

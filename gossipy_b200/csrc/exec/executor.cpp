@@ -10,6 +10,10 @@
 //   SEND / REPLY_SEND  snapshot kernel  slot <- sender's row            on the SENDER's stream
 //   DELIVER / REPLY    MERGE_UPDATE: fused merge + local-update kernel (reads the slot)
 //                      UPDATE: adopt (copy) + local-update kernel;  PASS: adopt     on the RECEIVER's stream
+//   partitioned models (PartitioningBasedNode + PartitionedTMH, reference node.py:566-659, handler.py:455-525):
+//                      SEND also draws the partition id (keyed, like node.py does under the native engine) and
+//                      carries the sender's per-partition ages; DELIVER = segment merge of that partition with
+//                      age weights + local update with per-partition 1/age gradient scaling (ages by value)
 //
 // with two CUDA events per snapshot slot ordering the streams (slot written -> reader may start; slot
 // read -> slot may be overwritten).  Disjoint node pairs therefore overlap on the device, and the host
@@ -58,10 +62,13 @@ enum : int32_t { MT_PUSH = 1, MT_PULL = 2, MT_REPLY = 3, MT_PUSH_PULL = 4 };
 struct Node {
     float* row = nullptr; const float* X = nullptr; const int64_t* y = nullptr;
     int n = 0; int64_t age = 0, counter = 0; cudaStream_t stream = nullptr;
+    std::vector<int64_t> ages_v;            // partitioned models: one age per partition (age = their sum)
+    int64_t model_msgs = 0;                 // model-carrying messages sent so far (keys the partition draw)
 };
 
 struct Slot {
     int64_t age = 0;
+    std::vector<int64_t> ages_v; int pid = 0;
     cudaEvent_t written = nullptr, read = nullptr; bool has_reader = false;      // same-rank ordering
     float* data = nullptr;                                                        // peer-mapped when the slot lives on another rank
     uint32_t* ready = nullptr; uint32_t* done = nullptr;                          // cross-rank handshake words (owner's memory)
@@ -141,6 +148,25 @@ public:
     void set_callbacks(py::function snapshot, py::function train, py::function adopt) {
         cb_snapshot_ = snapshot; cb_train_ = train; cb_adopt_ = adopt;
     }
+    // partitioned models: partition table of every parameter (device, int64) and the strided blocks of every
+    // partition (device int64 [S, 4] each, model/sampling.py::segments); CPU mode: callbacks instead
+    void set_partition(int n_parts, uintptr_t part_id, const std::vector<uintptr_t>& seg_ptrs, const std::vector<int>& seg_counts) {
+        if (n_parts < 1 || n_parts > kMaxPartsByValue) throw std::invalid_argument("1..16 partitions supported by the native executor");
+        if ((int)seg_ptrs.size() != n_parts || (int)seg_counts.size() != n_parts) throw std::invalid_argument("one segment table per partition");
+        if (mode_ != 2) throw std::invalid_argument("partitioned models run MERGE_UPDATE in the native executor");
+        n_parts_ = n_parts; part_id_ = reinterpret_cast<const int64_t*>(part_id);
+        seg_ptrs_ = seg_ptrs; seg_counts_ = seg_counts;
+        for (Node& nd : nodes_) nd.ages_v.assign(n_parts, 0);
+    }
+    void set_partition_callbacks(py::function merge_part, py::function train_part) { cb_merge_part_ = merge_part; cb_train_part_ = train_part; }
+    void set_node_ages(int i, const std::vector<int64_t>& ages, int64_t model_msgs) {
+        Node& nd = nodes_.at(i);
+        if ((int)ages.size() != n_parts_) throw std::invalid_argument("one age per partition");
+        nd.ages_v = ages; nd.model_msgs = model_msgs;
+        nd.age = 0; for (int64_t a : ages) nd.age += a;
+    }
+    std::vector<std::vector<int64_t>> ages_v() const { std::vector<std::vector<int64_t>> v; for (const Node& n : nodes_) v.push_back(n.ages_v); return v; }
+    std::vector<int64_t> model_msgs() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.model_msgs); return v; }
     int free_slots() const { return (int)free_[world_ > 1 ? rank_ : 0].size(); }
 
     // Executes one round's events [n, 6] = (kind, tick, a, b, slot, aux) from index `start`.  Returns the nodes to
@@ -188,11 +214,15 @@ public:
     std::vector<int64_t> ages() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.age); return v; }
     std::vector<int64_t> counters() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.counter); return v; }
     int64_t launches() const { return launches_; }
-    // messages on the wire: (message id, rank, slot, age) -- checkpointing
+    // messages on the wire: (message id, rank, slot, age [, partition id, age of every partition]) -- checkpointing
     std::vector<std::vector<int64_t>> inflight() const {
         std::vector<std::vector<int64_t>> v;
-        for (const auto& kv : inflight_)
-            v.push_back({kv.first, kv.second.first, kv.second.second, pools_[kv.second.first][kv.second.second].age});
+        for (const auto& kv : inflight_) {
+            const Slot& sl = pools_[kv.second.first][kv.second.second];
+            std::vector<int64_t> r{kv.first, kv.second.first, kv.second.second, sl.age};
+            if (n_parts_ > 0) { r.push_back(sl.pid); r.insert(r.end(), sl.ages_v.begin(), sl.ages_v.end()); }
+            v.push_back(r);
+        }
         std::sort(v.begin(), v.end());
         return v;
     }
@@ -203,7 +233,9 @@ public:
             auto it = std::find(fl.begin(), fl.end(), s);
             if (it == fl.end()) throw std::invalid_argument("slot is not free");
             fl.erase(it);
-            pools_.at(rk).at(s).age = r.at(3);
+            Slot& sl = pools_.at(rk).at(s);
+            sl.age = r.at(3);
+            if (n_parts_ > 0) { sl.pid = (int)r.at(4); sl.ages_v.assign(r.begin() + 5, r.begin() + 5 + n_parts_); }
             inflight_[(int32_t)r.at(0)] = {rk, s};
         }
     }
@@ -232,6 +264,14 @@ private:
         Node& nd = nodes_.at(node);
         Slot& sl = pools_[rk][s];
         sl.age = nd.age;
+        if (n_parts_ > 0) {                               // node.py::PartitioningBasedNode._payload_extras (keyed form)
+            sl.ages_v = nd.ages_v;
+            uint64_t h = mix64(seed_);
+            const uint64_t parts[3] = {0x9A57ull, (uint64_t)node, (uint64_t)nd.model_msgs};
+            for (uint64_t p : parts) h = mix64(h ^ p);
+            sl.pid = (int)((h & ((1ull << 63) - 1)) % (uint64_t)n_parts_);
+            nd.model_msgs += 1;
+        }
         sl.gen += 1;                                      // replicated: every rank knows which generation a reader expects
         if (mine(node)) {
             if (cuda_) {
@@ -264,17 +304,25 @@ private:
         ws = (float)((double)a / (double)tot); wp = (float)((double)b / (double)tot);
     }
 
-    void train(Node& nd, const float* peer, float ws, float wp, uint64_t key, PeerSync sync) {
+    void train(Node& nd, const float* peer, float ws, float wp, uint64_t key, PeerSync sync,
+               const std::vector<int64_t>* part_ages = nullptr) {
         bool ok;
         const char* why = "";
+        auto scaled = [&](auto& p) {
+            if (part_ages == nullptr) return;
+            p.part_id = part_id_; p.ages = nullptr; p.use_ages_val = true; p.n_parts = n_parts_;
+            for (int i = 0; i < n_parts_; ++i) p.ages_val[i] = (*part_ages)[i];
+        };
         if (family_ == 0) {
             TrainParams p{};
+            scaled(p);
             p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.H = H_; p.OUT = OUT_;
             p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
             if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; p.sync = sync; }
             ok = launch_mlp1_train(p, kTrainAuto, nd.stream, &why);
         } else {
             LogregParams p{};
+            scaled(p);
             p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.OUT = OUT_;
             p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
             if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; p.sync = sync; }
@@ -299,7 +347,29 @@ private:
             else if (sl.written)                                // (a slot restored from a checkpoint has no writer event)
                 cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
         }
-        if (mode_ == 4) {                                  // PASS: adopt the received model, age unchanged
+        if (n_parts_ > 0) {                                // partitioned MERGE_UPDATE: merge one partition, then train
+            const int pid = sl.pid;
+            const int64_t a = nd.ages_v[pid], b = sl.ages_v[pid];
+            float w1 = .5f, w2 = .5f;                      // sampling.py::mixing_weights: (0, 0) -> (1, 1)
+            if (a + b > 0) { w1 = (float)((double)a / (double)(a + b)); w2 = (float)((double)b / (double)(a + b)); }
+            if (exec) {
+                if (cuda_) launch_merge_segments(nd.row, sl.data, reinterpret_cast<const int64_t*>(seg_ptrs_[pid]), seg_counts_[pid], w1, w2, sync, nd.stream);
+                else cb_merge_part_(node, rk, s, pid, w1, w2, (int64_t)sl.gen);
+                ++launches_;
+            }
+            nd.ages_v[pid] = std::max(a, b);
+            nd.age = 0; for (int64_t v : nd.ages_v) nd.age += v;
+            nd.counter += 1;
+            const uint64_t key = key_of(node, nd);
+            if (exec) {
+                if (cuda_) train(nd, nullptr, 1.f, 0.f, key, PeerSync{nullptr, 0, nullptr, nullptr}, &nd.ages_v);
+                else cb_train_part_(node, (int64_t)key, nd.ages_v);
+                ++launches_;
+            }
+            const int st = steps_of(nd);
+            for (int64_t& v : nd.ages_v) v += st;
+            nd.age += (int64_t)st * n_parts_;
+        } else if (mode_ == 4) {                           // PASS: adopt the received model, age unchanged
             if (exec) {
                 if (cuda_) launch_merge_pair(nd.row, sl.data, 0.f, 1.f, 0, row_floats_, sync, nd.stream);
                 else cb_adopt_(node, rk, s, (int64_t)sl.gen);
@@ -349,7 +419,9 @@ private:
     std::vector<std::vector<Slot>> pools_;          // per owner rank
     std::vector<std::deque<int>> free_;             // FIFO: a slot is reused as late as possible (see snapshot())
     std::unordered_map<int32_t, std::pair<int, int>> inflight_;     // message id -> (rank, slot)
-    py::function cb_snapshot_, cb_train_, cb_adopt_;
+    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_;
+    int n_parts_ = 0; const int64_t* part_id_ = nullptr;
+    std::vector<uintptr_t> seg_ptrs_; std::vector<int> seg_counts_;
     int64_t launches_ = 0, resume_at_ = -1;
 };
 
@@ -365,6 +437,11 @@ void bind_executor(py::module_& m) {
         .def("set_node_data", &StreamExecutor::set_node_data)
         .def("set_slots", &StreamExecutor::set_slots)
         .def("set_callbacks", &StreamExecutor::set_callbacks)
+        .def("set_partition", &StreamExecutor::set_partition)
+        .def("set_partition_callbacks", &StreamExecutor::set_partition_callbacks)
+        .def("set_node_ages", &StreamExecutor::set_node_ages)
+        .def("ages_v", &StreamExecutor::ages_v)
+        .def("model_msgs", &StreamExecutor::model_msgs)
         .def("run", &StreamExecutor::run, py::arg("events"), py::arg("start") = 0)
         .def_property_readonly("resume_at", &StreamExecutor::resume_at)
         .def_property_readonly("free_slots", &StreamExecutor::free_slots)

@@ -55,11 +55,17 @@ void launch_adam(float* p, const float* g, int64_t n, float* m, float* v, int64_
                  float beta1, float beta2, float eps, float wd, bool decoupled, cudaStream_t stream);
 
 // ---- mlp1_train*.cu / mlp1_eval.cu ---------------------------------------------------------------
+constexpr int kMaxPartsByValue = 16;
 struct TrainParams {
     float* row; const float* X; const int64_t* y;
     int n, IN, H, OUT, B, epochs;
     float lr, wd; uint64_t key;
+    // K3 (PartitionedTMH): part_id = partition of every parameter (device), ages = age of every partition -- either a
+    // device array (`ages`) or, when that is null and use_ages_val is set, by value (<= 16 partitions; no H2D copy)
     const int64_t* part_id; const int64_t* ages; int n_parts;
+    int64_t ages_val[kMaxPartsByValue]; bool use_ages_val;
+    __host__ __device__ bool scaled() const { return part_id != nullptr && (ages != nullptr || use_ages_val); }
+    __host__ __device__ int64_t age_of(int part) const { return ages != nullptr ? ages[part] : ages_val[part]; }
     int Hs, C, nbuf;
     float* dbg;                 // optional debug dump (tests)
     // fused MERGE_UPDATE: when `peer` is set the kernel starts from w_self*row + w_peer*peer
@@ -95,6 +101,9 @@ void set_eval_tf32(bool on);            // plain tf32 products instead of the fp
 struct LogregParams {
     float* row; const float* X; const int64_t* y; int n, IN, OUT, B, epochs; float lr, wd; uint64_t key;
     const int64_t* part_id; const int64_t* ages; int n_parts;
+    int64_t ages_val[kMaxPartsByValue]; bool use_ages_val;
+    __host__ __device__ bool scaled() const { return part_id != nullptr && (ages != nullptr || use_ages_val); }
+    __host__ __device__ int64_t age_of(int part) const { return ages != nullptr ? ages[part] : ages_val[part]; }
     const float* peer; float w_self, w_peer; PeerSync sync;
 };
 bool launch_logreg_train(LogregParams p, cudaStream_t stream);

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NW * 32, 1) mlp1_train_cluster_kernel(const Tr
         const float inv_b = 1.f / (float)bcur;
 
         if (SCALED && tid < p.n_parts)     // ages are incremented before the step (ref :506)
-            coef[tid] = p.lr / (float)(p.ages[tid] + (int64_t)s + 1);
+            coef[tid] = p.lr / (float)(p.age_of(tid) + (int64_t)s + 1);
 
         // ---- forward, layer 1: z1 = x W1^T + b1 ; h = relu(z1) -------------------------------
         if (warp * UPW < nslots) {
@@ -346,7 +346,7 @@ bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const
     static const char* kNone = "";
     *why = kNone;
     if (impl == kTrainAuto) impl = g_auto_impl;
-    const bool scaled = p.part_id != nullptr && p.ages != nullptr;
+    const bool scaled = p.scaled();
     if (scaled && p.n_parts > MAX_PARTS) { *why = "fused partitioned training supports <= 16 partitions"; return false; }
     if (scaled && (impl == kTrainAuto || impl == kTrainTc8)) {     // K3 on the tensor-core kernel (<= 16 partitions)
         if (mlp1_train_tc4(p, 8, true, stream)) return true;

@@ -228,7 +228,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
     }
     if (tid < 16) b2s[tid] = (tid < OUT) ? p.row[off_b2 + tid] : -3.0e38f;   // padding classes: probability 0
     if (SC && tid < 16) {        // ages are incremented before the step (reference handler.py:506)
-        inva[tid] = tid < p.n_parts ? 1.f / (float)(p.ages[tid] + 1) : 1.f;
+        inva[tid] = tid < p.n_parts ? 1.f / (float)(p.age_of(tid) + 1) : 1.f;
         inva[16 + tid] = 1.f;
     }
     tc_fence_before();
@@ -638,7 +638,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             if (tid >= 64 && tid < 96 && s + 1 < total_steps)
                 ysm[(par ^ 1) * T4_B + (tid - 64)] = stage_ys[(size_t)(s + 1) * T4_B + (tid - 64)];
             if (SC && tid >= 96 && tid < 96 + p.n_parts)          // 1/age of the next step (ages grow by one per step)
-                inva[16 * (par ^ 1) + (tid - 96)] = 1.f / (float)(p.ages[tid - 96] + (int64_t)s + 2);
+                inva[16 * (par ^ 1) + (tid - 96)] = 1.f / (float)(p.age_of(tid - 96) + (int64_t)s + 2);
             if (warp == 5) {                                     // db2[o] = sum_b dz2[b][o]: lane = sample
                 const float4* dr = reinterpret_cast<const float4*>(dzb + (size_t)lane * T4_DZP);
                 const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2];
@@ -967,7 +967,7 @@ static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
         }
         mlp1_stage4_kernel<X3><<<dim3(steps, NC), 256, smem, stream>>>(p.X, p.y, p.n, p.IN, p.B, p.epochs, p.key, NC, FPC, FP, out, ys);
     }
-    if (SC && (p.n_parts > 16 || p.part_id == nullptr || p.ages == nullptr)) return false;
+    if (SC && (p.n_parts > 16 || !p.scaled())) return false;
     auto kern = mlp1_train_tc4_kernel<NC, X3, SC>;
     static bool configured = false;
     if (!configured) {
@@ -986,7 +986,7 @@ static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
 // nc in {4, 8}; x3 = error-compensated (fp32-equivalent) products, otherwise plain tf32
 bool mlp1_train_tc4(const TrainParams& p, int nc, bool x3, cudaStream_t stream) {
     if (nc != 8) return false;      // (the kernel is written for NC in {4, 8}; only the 8-CTA form is validated and shipped)
-    const bool scaled = p.part_id != nullptr && p.ages != nullptr;
+    const bool scaled = p.scaled();
     if (scaled) return x3 && tc4_launch<8, true, true>(p, stream);      // K3 rides on the W += G pass of the X3 form
     return x3 ? tc4_launch<8, true, false>(p, stream) : tc4_launch<8, false, false>(p, stream);
 }

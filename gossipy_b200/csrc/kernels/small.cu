@@ -41,14 +41,14 @@ __global__ void __launch_bounds__(LR_THREADS) logreg_train_kernel(const LogregPa
     const int n = p.n, B = p.B;
     const int spe = (n + B - 1) / B;
     const int total = p.epochs > 0 ? p.epochs * spe : 1;
-    const bool scaled = p.part_id != nullptr;
+    const bool scaled = p.scaled();
     for (int s = 0; s < total; ++s) {
         const int e = p.epochs > 0 ? s / spe : 0;
         const int pos = p.epochs > 0 ? (s % spe) * B : 0;
         const int bcur = min(B, n - pos);
         GbPerm perm; perm.init((uint32_t)n, gb_mix64(p.key ^ (uint64_t)e));
         for (int i = tid; i < P; i += LR_THREADS) G[i] = 0.f;
-        if (scaled && tid < p.n_parts) coef[tid] = 1.f / (float)(p.ages[tid] + (int64_t)s + 1);
+        if (scaled && tid < p.n_parts) coef[tid] = 1.f / (float)(p.age_of(tid) + (int64_t)s + 1);
         for (int c0 = 0; c0 < bcur; c0 += LR_BMAX) {           // passes over the mini-batch
             const int cb = min(LR_BMAX, bcur - c0);
             __syncthreads();

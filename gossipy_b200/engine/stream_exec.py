@@ -48,23 +48,30 @@ def eligible(sim: Any) -> Optional[str]:
     ids = sorted(sim.nodes)
     if ids != list(range(len(ids))):
         return "node ids must be 0..N-1"
+    from ..node import PartitioningBasedNode
     ref = None
     for i in ids:
         node = sim.nodes[i]
         h = node.model_handler
-        if type(node) is not GossipNode:
+        partitioned = type(node) is PartitioningBasedNode and type(h) is H.PartitionedTMH
+        if type(node) is not GossipNode and not partitioned:
             return "node class %s" % type(node).__name__
-        if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH):
+        if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH) and not partitioned:
             return "handler class %s" % type(h).__name__
         if not h._fused or h.layout.int_buffers:
             return "handler is not on the fused kernel path"
-        if h.mode not in (CreateModelMode.MERGE_UPDATE, CreateModelMode.UPDATE, CreateModelMode.PASS):
+        if partitioned:
+            if h.mode != CreateModelMode.MERGE_UPDATE:
+                return "partitioned models: mode %s" % h.mode.name
+            if h.tm_partition.n_parts > 16:
+                return "more than 16 partitions"
+        elif h.mode not in (CreateModelMode.MERGE_UPDATE, CreateModelMode.UPDATE, CreateModelMode.PASS):
             return "mode %s" % h.mode.name
-        if not isinstance(h.n_updates, (int, np.integer)):
+        elif not isinstance(h.n_updates, (int, np.integer)):
             return "vector-valued model age"
         sig = (h._family, h.batch_size, h.local_epochs, float(h.optimizer_params.get("lr", 1e-3)),
                float(h.optimizer_params.get("weight_decay", 0.0)), h._row_numel, type(h), h.mode,
-               getattr(h, "L", None))
+               getattr(h, "L", None), h.tm_partition.n_parts if partitioned else 0)
         if ref is None:
             ref = sig
         elif sig != ref:
@@ -99,6 +106,18 @@ class StreamExec:
         limited = int(h0.L) if hasattr(h0, "L") else -1          # LimitedMergeTMH: age-limited merge weights
         self.ex = self.C.StreamExecutor(len(ids), 0 if fam == "mlp1" else 1, IN, Hd, OUT, self.bs, self.epochs,
                                         self.lr, self.wd, _rng.base_seed(), self.cuda, int(h0.mode.value), limited)
+        self.n_parts = 0
+        if type(h0).__name__ == "PartitionedTMH":       # per-partition ages, segment merges, 1/age gradient scaling (K3)
+            part = h0.tm_partition
+            self.n_parts = int(part.n_parts)
+            self._part_id = part.part_id.to(self.device)
+            self._segs = [part.segments(p).to(self.device).contiguous() for p in range(self.n_parts)]
+            if self.cuda:
+                self.ex.set_partition(self.n_parts, self._part_id.data_ptr(), [t.data_ptr() for t in self._segs],
+                                      [int(t.shape[0]) for t in self._segs])
+            else:
+                self.ex.set_partition(self.n_parts, 0, [0] * self.n_parts, [int(t.shape[0]) for t in self._segs])
+                self.ex.set_partition_callbacks(self._cb_merge_part, self._cb_train_part)
         from ..parallel import runtime as prt
         self.multi = prt.active()
         self.rank = prt.rank() if self.multi else 0
@@ -152,14 +171,17 @@ class StreamExec:
         """(Re)read rows, data, ages, counters and streams from the handlers (start of every ``start``)."""
         for i, node in self.sim.nodes.items():
             h = node.model_handler
+            age = int(np.sum(h.n_updates))
             if not self._mine(i):      # another rank runs this node: only its sample count and counters matter here
-                self.ex.set_node(i, 0, 0, 0, int(node.data[0][0].shape[0]), int(h.n_updates), int(h._update_counter), 0)
-                continue
-            row = h.row
-            x, y = self._node_data(i)
-            s = h._stream()
-            self.ex.set_node(i, row.data_ptr(), x.data_ptr(), y.data_ptr(), int(x.shape[0]), int(h.n_updates),
-                             int(h._update_counter), int(s.cuda_stream) if s is not None else 0)
+                self.ex.set_node(i, 0, 0, 0, int(node.data[0][0].shape[0]), age, int(h._update_counter), 0)
+            else:
+                row = h.row
+                x, y = self._node_data(i)
+                s = h._stream()
+                self.ex.set_node(i, row.data_ptr(), x.data_ptr(), y.data_ptr(), int(x.shape[0]), age,
+                                 int(h._update_counter), int(s.cuda_stream) if s is not None else 0)
+            if self.n_parts:
+                self.ex.set_node_ages(i, [int(a) for a in h.n_updates], int(getattr(node, "_model_msgs", 0)))
 
     def refresh_data(self) -> None:
         """Streamed inputs: the resident buffers alternate every round."""
@@ -170,6 +192,17 @@ class StreamExec:
 
     def sync_back(self) -> None:
         ages, counters = self.ex.ages(), self.ex.counters()
+        if self.n_parts:
+            ages_v, msgs = self.ex.ages_v(), self.ex.model_msgs()
+            for i, node in self.sim.nodes.items():
+                h = node.model_handler
+                new = np.asarray(ages_v[i], dtype=h.n_updates.dtype)
+                if not np.array_equal(new, h.n_updates) or h._update_counter != counters[i]:
+                    h._version += 1
+                h.n_updates = new
+                h._update_counter = int(counters[i])
+                node._model_msgs = int(msgs[i])
+            return
         for i, node in self.sim.nodes.items():
             h = node.model_handler
             if int(h.n_updates) != ages[i] or h._update_counter != counters[i]:
@@ -215,6 +248,17 @@ class StreamExec:
             merge = (src, float(w_self), float(w_peer), sync)
         fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key), None, merge_from=merge)
 
+    def _cb_merge_part(self, node: int, rank: int, slot: int, pid: int, w1: float, w2: float, gen: int) -> None:
+        src, sync = self._slot(rank, slot, gen)
+        ops.merge_segments(self.sim.nodes[node].model_handler.row, src, self._segs[pid], float(w1), float(w2), sync)
+
+    def _cb_train_part(self, node: int, key: int, ages: List[int]) -> None:
+        h = self.sim.nodes[node].model_handler
+        x, y = self._data[node]
+        fn = ops.mlp1_train if self.family == "mlp1" else ops.logreg_train
+        fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key),
+           (self._part_id, torch.as_tensor(ages, dtype=torch.int64)))
+
     # -- one round -------------------------------------------------------------------------------------------
     def run_round(self, events: np.ndarray) -> List[int]:
         before = self.ex.launches
@@ -251,7 +295,7 @@ class StreamExec:
             raise NotImplementedError("checkpointing the C++ executor with several ranks")
         rows = self.ex.inflight()
         idx = torch.as_tensor([r[2] for r in rows], dtype=torch.int64, device=self.device)
-        return {"ids": [int(r[0]) for r in rows], "ages": [int(r[3]) for r in rows],
+        return {"ids": [int(r[0]) for r in rows], "ages": [int(r[3]) for r in rows], "extra": [list(map(int, r[4:])) for r in rows],
                 "rows": self.slots[idx].cpu() if rows else torch.zeros(0, self.row_numel)}
 
     def import_inflight(self, st: Dict[str, Any]) -> None:
@@ -265,4 +309,5 @@ class StreamExec:
         self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = st["rows"].to(self.device)
         if self.cuda:
             torch.cuda.synchronize(self.device)     # the node streams read these slots without a writer event
-        self.ex.import_inflight([[int(m), 0, int(s), int(a)] for m, s, a in zip(st["ids"], free, st["ages"])])
+        extra = st.get("extra") or [[] for _ in range(n)]
+        self.ex.import_inflight([[int(m), 0, int(s), int(a)] + list(e) for m, s, a, e in zip(st["ids"], free, st["ages"], extra)])

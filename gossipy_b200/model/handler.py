@@ -1211,11 +1211,12 @@ class PartitionedTMH(TorchModelHandler):
     def _elem_scale(self) -> Tuple[torch.Tensor, torch.Tensor]:
         ages = torch.as_tensor(np.asarray(self.n_updates, dtype=np.int64))
         dev = self.row.device
-        if dev.type == "cuda":
+        if dev.type == "cuda" and ages.numel() > 16:
             # through pinned memory, asynchronously on the node's stream: a pageable H2D copy would block the host
             # until everything queued on that stream has finished (the caching host allocator keeps the staging
             # buffer alive until the copy has run)
             ages = ages.pin_memory().to(dev, non_blocking=True)
+        # (<= 16 partitions: the ages stay on the host and travel by value in the kernel's launch parameters)
         return (self._part_ids(), ages)
 
     def _count_steps(self, steps: int) -> None:

@@ -241,7 +241,15 @@ class PartitioningBasedNode(GossipNode):
     (ref ``node.py:566-659``); replies draw a fresh one."""
 
     def _payload_extras(self) -> Tuple[Any, ...]:
-        return (int(np.random.randint(0, self.model_handler.tm_partition.n_parts)),)
+        n_parts = self.model_handler.tm_partition.n_parts
+        if getattr(self, "_keyed_draws", False):
+            # native engine: a counter-based draw (node id, number of model messages sent so far) that the C++ executor
+            # reproduces (csrc/exec/executor.cpp::snapshot) -- the host NumPy stream is not consumed
+            from .engine import rng as _rng
+            k = int(getattr(self, "_model_msgs", 0))
+            self._model_msgs = k + 1
+            return (int(_rng.derive(0x9A57, self.idx, k) % n_parts),)
+        return (int(np.random.randint(0, n_parts)),)
 
     def _model_message(self, t: int, peer: int, mtype: MessageType) -> Message:
         extras = self._payload_extras()  # the reference draws the pid before snapshotting

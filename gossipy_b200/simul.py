@@ -477,6 +477,9 @@ class GossipSimulator(SimulationEventSender):
         LOG.info("Simulation started (native scheduler).")
         from .ops.native import _try_import
         C = _try_import()
+        if not GlobalSettings().reference_compat:
+            for node in self.nodes.values():      # node-side random draws (partition ids) come from keyed streams that
+                node._keyed_draws = True          # the C++ executor reproduces, not from the host NumPy generator
         sch = self.__dict__.get("_scheduler")
         saved = self.__dict__.pop("_scheduler_state", None)
         if resume and sch is None and saved is not None:

@@ -75,6 +75,21 @@ def build(kind, device):
         sim = All2AllGossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
         start_args = (UniformMixing(net),)
         sim._mr_kwargs = {"synchronous": True}
+    elif kind in ("x_part_mlp", "x_part_logreg"):
+        # partitioned models through the C++ executor: keyed partition draws, ages per partition, segment merges
+        if kind == "x_part_mlp":
+            (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
+            n, bs, net, prt_ = 4, 32, TorchMLP(784, 10, (100,)), AntiEntropyProtocol.PUSH_PULL
+        else:
+            (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+            n, bs, net, prt_ = 6, 16, LogisticRegression(57, 2), AntiEntropyProtocol.PUSH
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
+        proto = PartitionedTMH(net, TorchModelPartition(net, 4), torch.optim.SGD, {"lr": .5, "weight_decay": .001},
+                               torch.nn.CrossEntropyLoss(), batch_size=bs, create_model_mode=CreateModelMode.MERGE_UPDATE)
+        nodes = PartitioningBasedNode.generate(disp, StaticP2PNetwork(n), proto, 10, True)
+        sim = GossipSimulator(nodes, disp, 10, prt_, delay=UniformDelay(0, 2))
+        sim.engine = "native"
+        sim.native_executor = True
     elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull"):
         # native engine + the C++ executor (csrc/exec): one executor per rank over the same event list
         if kind == "x_mlp_pushpull":

@@ -12,14 +12,16 @@ pytestmark = pytest.mark.skipif(not native_available(), reason="extension not bu
 
 
 def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=4, device="cpu", sync=True, start=True,
-         mode="MERGE_UPDATE", limited=None, tokenized=False):
+         mode="MERGE_UPDATE", limited=None, tokenized=False, partitioned=0):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork, UniformDelay
     from gossipy_b200.data import DataDispatcher, synthetic
     from gossipy_b200.data.handler import ClassificationDataHandler
     from gossipy_b200.core import CreateModelMode
     from gossipy_b200.flow_control import RandomizedTokenAccount
-    from gossipy_b200.model.handler import LimitedMergeTMH, TorchModelHandler
+    from gossipy_b200.model.handler import LimitedMergeTMH, PartitionedTMH, TorchModelHandler
+    from gossipy_b200.model.sampling import TorchModelPartition
+    from gossipy_b200.node import PartitioningBasedNode
     from gossipy_b200.simul import TokenizedGossipSimulator
     from gossipy_b200.model.nn import LogisticRegression, TorchMLP
     from gossipy_b200.node import GossipNode
@@ -35,12 +37,17 @@ def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=
         net, bs = LogisticRegression(57, 2), 16
     disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
     kwh = dict(batch_size=bs, create_model_mode=getattr(CreateModelMode, mode))
-    if limited is not None:
+    node_cls = GossipNode
+    if partitioned:
+        proto = PartitionedTMH(net, TorchModelPartition(net, partitioned), torch.optim.SGD, {"lr": .5, "weight_decay": .001},
+                               torch.nn.CrossEntropyLoss(), **kwh)
+        node_cls = PartitioningBasedNode
+    elif limited is not None:
         proto = LimitedMergeTMH(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(),
                                 age_diff_threshold=limited, **kwh)
     else:
         proto = TorchModelHandler(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), **kwh)
-    nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, sync)
+    nodes = node_cls.generate(disp, StaticP2PNetwork(n), proto, 10, sync)
     kw = dict(drop_prob=.15, online_prob=.8, delay=UniformDelay(0, 4), sampling_eval=.5) if faults else {}
     if tokenized:
         sim = TokenizedGossipSimulator(nodes, disp, RandomizedTokenAccount(C=4, A=2), lambda a, b, m: 1, 10,
@@ -61,7 +68,7 @@ def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=
 def _state(sim):
     n = len(sim.nodes)
     rows = torch.stack([sim.nodes[i].model_handler.row.detach().cpu().clone() for i in range(n)])
-    ages = [int(sim.nodes[i].model_handler.n_updates) for i in range(n)]
+    ages = [np.asarray(sim.nodes[i].model_handler.n_updates).tolist() for i in range(n)]
     ctr = [int(sim.nodes[i].model_handler._update_counter) for i in range(n)]
     return rows, ages, ctr
 
@@ -106,6 +113,22 @@ def test_native_executor_modes_and_variants(kw):
     sim_b, rep_b = _sim(True, **kw)
     assert "_stream_exec" in sim_b.__dict__ and "_stream_exec" not in sim_a.__dict__
     _same(sim_a, rep_a, sim_b, rep_b)
+    g.CACHE.clear()
+
+
+@pytest.mark.parametrize("kw", [dict(model="logreg", protocol="PUSH", partitioned=4, faults=True),
+                                dict(model="mlp", protocol="PUSH_PULL", partitioned=3),
+                                dict(model="logreg", protocol="PULL", partitioned=7, faults=True, sync=False)])
+def test_native_executor_partitioned_models(kw):
+    """PartitioningBasedNode + PartitionedTMH (reference node.py:566-659, handler.py:455-525) from C++: keyed partition
+    draw, per-partition ages on the wire, segment merge with age weights, 1/age-scaled local update."""
+    import gossipy_b200 as g
+    sim_a, rep_a = _sim(False, **kw)
+    sim_b, rep_b = _sim(True, **kw)
+    assert "_stream_exec" in sim_b.__dict__ and "_stream_exec" not in sim_a.__dict__
+    _same(sim_a, rep_a, sim_b, rep_b)
+    assert [getattr(nd, "_model_msgs", 0) for nd in sim_a.nodes.values()] == [getattr(nd, "_model_msgs", 0) for nd in sim_b.nodes.values()]
+    assert sum(getattr(nd, "_model_msgs", 0) for nd in sim_b.nodes.values()) > 0
     g.CACHE.clear()
 
 
