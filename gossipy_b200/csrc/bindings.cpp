@@ -216,8 +216,10 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, int64_t> mlp1_stage_debug(at::Ten
     return {xf, xt, ys, (int64_t)FP};
 }
 
-at::Tensor mlp1_eval(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
-                     int64_t n_classes, c10::optional<at::Tensor> X_lp) {
+std::tuple<at::Tensor, c10::optional<at::Tensor>> mlp1_eval(at::Tensor row, at::Tensor X, at::Tensor y,
+                                                            std::tuple<int64_t, int64_t, int64_t> dims, int64_t n_classes,
+                                                            c10::optional<at::Tensor> X_lp, bool want_score1) {
+    // confusion matrix [C, C] (int32) and, on request, the class-1 logit of every sample (AUC of 2-output networks)
     check_row(row, "row"); check_row(X, "X");
     TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.is_contiguous());
     const int IN = (int)std::get<0>(dims), H = (int)std::get<1>(dims), OUT = (int)std::get<2>(dims);
@@ -225,20 +227,23 @@ at::Tensor mlp1_eval(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int6
     TORCH_CHECK(X.size(1) == IN && y.numel() == n);
     c10::cuda::CUDAGuard guard(row.device());
     auto cm = at::zeros({n_classes, n_classes}, row.options().dtype(at::kInt));
+    c10::optional<at::Tensor> sc;
+    float* scp = nullptr;
+    if (want_score1) { sc = at::empty({n}, row.options()); scp = sc->data_ptr<float>(); }
     if (X_lp.has_value()) {      // pre-tiled test set -> tensor-core kernel
         TORCH_CHECK(X_lp->is_cuda() && X_lp->scalar_type() == at::kFloat && X_lp->is_contiguous() &&
                     X_lp->numel() == mlp1_eval_pretile_floats(n, IN), "X_lp must come from mlp1_eval_pretile(X)");
         if (launch_mlp1_eval_tc(row.data_ptr<float>(), X_lp->data_ptr<float>(), y.data_ptr<int64_t>(), n, IN, H,
-                                OUT, (int)n_classes, cm.data_ptr<int>(), cur_stream())) {
+                                OUT, (int)n_classes, cm.data_ptr<int>(), scp, cur_stream())) {
             GB_LAUNCH_CHECK();
-            return cm;
+            return {cm, sc};
         }
     }
     TORCH_CHECK(launch_mlp1_eval(row.data_ptr<float>(), X.data_ptr<float>(), y.data_ptr<int64_t>(), n, IN, H,
-                                 OUT, (int)n_classes, cm.data_ptr<int>(), cur_stream()),
+                                 OUT, (int)n_classes, cm.data_ptr<int>(), scp, cur_stream()),
                 "mlp1_eval: hidden <= 128 and out <= 16 supported");
     GB_LAUNCH_CHECK();
-    return cm;
+    return {cm, sc};
 }
 
 at::Tensor mlp1_eval_pretile(at::Tensor X) {
@@ -337,6 +342,20 @@ void mf_update(at::Tensor X, at::Tensor b, at::Tensor Y, at::Tensor c, at::Tenso
     launch_mf_update(X.data_ptr<float>(), b.data_ptr<float>(), Y.data_ptr<float>(), c.data_ptr<float>(),
                      rc.data_ptr<float>(), m, k, (float)reg, (float)lr, cur_stream());
     GB_LAUNCH_CHECK();
+}
+
+at::Tensor kmeans_match_merge(at::Tensor C, at::Tensor P, int64_t k, int64_t dim, double w_own, double w_peer,
+                              c10::optional<Sync> sync) {
+    // C[:k*dim] = w_own * C + w_peer * P[perm] with the optimal (min total distance) matching, k <= 8; returns perm
+    check_row(C, "C");
+    TORCH_CHECK(P.is_cuda() && P.scalar_type() == at::kFloat && C.numel() >= k * dim && P.numel() >= k * dim);
+    c10::cuda::CUDAGuard guard(C.device());
+    auto perm = at::empty({k}, C.options().dtype(at::kLong));
+    TORCH_CHECK(launch_kmeans_match_merge(C.data_ptr<float>(), P.data_ptr<float>(), (int)k, (int)dim, (float)w_own,
+                                          (float)w_peer, to_sync(sync), perm.data_ptr<int64_t>(), cur_stream()),
+                "kmeans_match_merge: 1 <= k <= 8");
+    GB_LAUNCH_CHECK();
+    return perm;
 }
 
 // ---- bank of linear learners ----------------------------------------------------------------------------
@@ -498,7 +517,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("dims"), py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"),
           py::arg("key"), py::arg("impl") = "tc");
     m.def("mlp1_stage_debug", &gb::mlp1_stage_debug);
-    m.def("mlp1_eval", &gb::mlp1_eval);
+    m.def("mlp1_eval", &gb::mlp1_eval, py::arg("row"), py::arg("X"), py::arg("y"), py::arg("dims"), py::arg("n_classes"),
+          py::arg("X_lp") = py::none(), py::arg("want_score1") = false);
     m.def("mlp1_eval_pretile", &gb::mlp1_eval_pretile);
     m.def("logreg_train", &gb::logreg_train, py::arg("row"), py::arg("X"), py::arg("y"), py::arg("dims"),
           py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"), py::arg("key"),
@@ -509,6 +529,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kmeans_update", &gb::kmeans_update);
     m.def("kmeans_assign", &gb::kmeans_assign);
     m.def("mf_update", &gb::mf_update);
+    m.def("kmeans_match_merge", &gb::kmeans_match_merge, py::arg("C"), py::arg("P"), py::arg("k"), py::arg("dim"),
+          py::arg("w_own"), py::arg("w_peer"), py::arg("sync") = py::none());
     m.def("bank_snapshot", &gb::bank_snapshot);
     m.def("bank_deliver", &gb::bank_deliver);
     m.def("bank_update", &gb::bank_update);

@@ -87,13 +87,14 @@ size_t mlp1_stage4_bytes(int n, int IN, int B, int epochs, int NC, bool x3, int*
 size_t mlp1_stage_bytes(int n, int IN, int B, int epochs, int* FPC_out, int* FP_out, int* steps_out);
 bool launch_mlp1_stage(const float* X, const int64_t* y, int n, int IN, int B, int epochs, uint64_t key,
                        void* staging, cudaStream_t stream);
+// score1 (optional, [n]): the class-1 logit of every sample, for the AUC of 2-output networks
 bool launch_mlp1_eval(const float* row, const float* X, const int64_t* y, int n, int IN, int H, int OUT,
-                      int n_classes, int* cm, cudaStream_t stream);
+                      int n_classes, int* cm, float* score1, cudaStream_t stream);
 // tcgen05 evaluation on a PRE-TILED copy of the test set (mlp1_eval_tc.cu)
 int64_t mlp1_eval_pretile_floats(int n, int IN);
 void launch_mlp1_eval_pretile(const float* X, int n, int IN, float* out, cudaStream_t stream);
 bool launch_mlp1_eval_tc(const float* row, const float* xt, const int64_t* y, int n, int IN, int H, int OUT,
-                         int n_classes, int* cm, cudaStream_t stream);
+                         int n_classes, int* cm, float* score1, cudaStream_t stream);
 void preload_eval_tc();
 void set_eval_tf32(bool on);            // plain tf32 products instead of the fp32-equivalent 3xTF32 default
 
@@ -115,6 +116,9 @@ void launch_kmeans_assign(const float* C, const float* X, int n, int k, int dim,
                           cudaStream_t stream);
 void launch_kmeans_apply(float* C, const float* X, const int64_t* asg, int n, int k, int dim, float alpha,
                          cudaStream_t stream);
+// optimal centroid matching (k <= 8, exhaustive) fused with the weighted merge; perm_out (optional, [k]) = assignment
+bool launch_kmeans_match_merge(float* C, const float* P, int k, int dim, float w_own, float w_peer, PeerSync sync,
+                               int64_t* perm_out, cudaStream_t stream);
 void launch_mf_update(float* Xu, float* bu, float* Y, float* c, const float* ratings, int m, int k,
                       float reg, float lr, cudaStream_t stream);
 

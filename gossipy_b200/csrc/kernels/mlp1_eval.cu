@@ -18,7 +18,7 @@ constexpr int EV_THREADS = 256;
 __global__ void __launch_bounds__(EV_THREADS)
 mlp1_eval_simt_kernel(const float* __restrict__ row, const float* __restrict__ X,
                       const int64_t* __restrict__ y, int n, int IN, int H, int OUT, int n_classes,
-                      int* __restrict__ cm) {
+                      int* __restrict__ cm, float* __restrict__ score1) {
     __shared__ float xs[EV_TS][EV_KC + 1];
     __shared__ float ws[EV_HMAX][EV_KC + 1];
     __shared__ float hs[EV_TS][EV_HMAX + 1];
@@ -69,14 +69,15 @@ mlp1_eval_simt_kernel(const float* __restrict__ row, const float* __restrict__ X
         for (int o = 1; o < OUT; ++o) if (zs[tid][o] > bv) { bv = zs[tid][o]; best = o; }
         const int t = (int)y[s0 + tid];
         if (t >= 0 && t < n_classes && best < n_classes) atomicAdd(&cm[t * n_classes + best], 1);
+        if (score1 != nullptr) score1[s0 + tid] = OUT > 1 ? zs[tid][1] : zs[tid][0];      // class-1 logit (AUC of 2-output nets)
     }
 }
 
 bool launch_mlp1_eval(const float* row, const float* X, const int64_t* y, int n, int IN, int H, int OUT,
-                      int n_classes, int* cm, cudaStream_t stream) {
+                      int n_classes, int* cm, float* score1, cudaStream_t stream) {
     if (H > EV_HMAX || OUT > 16 || n <= 0) return false;
     mlp1_eval_simt_kernel<<<(n + EV_TS - 1) / EV_TS, EV_THREADS, 0, stream>>>(row, X, y, n, IN, H, OUT,
-                                                                             n_classes, cm);
+                                                                             n_classes, cm, score1);
     return true;
 }
 

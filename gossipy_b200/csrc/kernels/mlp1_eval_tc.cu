@@ -82,7 +82,8 @@ template <bool X3>
 __global__ void __launch_bounds__(EV_THREADS_TC, 1)
 mlp1_eval_tc_kernel(const float* __restrict__ row, const float* __restrict__ xt /* pre-tiled test set */,
                     const float* __restrict__ w1t /* pre-tiled W1 */, const int64_t* __restrict__ y, int n,
-                    int IN, int H, int OUT, int NP, int nstage, int n_classes, int* __restrict__ cm_out) {
+                    int IN, int H, int OUT, int NP, int nstage, int n_classes, int* __restrict__ cm_out,
+                    float* __restrict__ score1) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quad = warp & 3, half = warp >> 2;
@@ -223,6 +224,7 @@ mlp1_eval_tc_kernel(const float* __restrict__ row, const float* __restrict__ xt 
             for (int o = 0; o < 10; ++o) {
                 const float v = logit[o] + part[sidx * 12 + o] + (o < OUT ? b2g[o] : 0.f);
                 if (o < OUT && v > bv) { bv = v; best = o; }
+                if (score1 != nullptr && o == (OUT > 1 ? 1 : 0)) score1[gs] = v;       // class-1 logit (AUC of 2-output nets)
             }
             const int t = (int)y[gs];
             if (t >= 0 && t < n_classes && best < n_classes) atomicAdd(&cms[t * 16 + best], 1);
@@ -261,7 +263,7 @@ static bool g_eval_tf32 = false;        // GlobalSettings().allow_tf32: plain tf
 void set_eval_tf32(bool on) { g_eval_tf32 = on; }
 
 bool launch_mlp1_eval_tc(const float* row, const float* xt, const int64_t* y, int n, int IN, int H, int OUT,
-                         int n_classes, int* cm, cudaStream_t stream) {
+                         int n_classes, int* cm, float* score1, cudaStream_t stream) {
     if (H > EV_NP_MAX || OUT > 10 || n_classes > 16 || n <= 0 || IN % 4 != 0) return false;
     const int NP = (H + 15) & ~15;
     const int nstage = (IN + EV_KS - 1) / EV_KS;
@@ -295,9 +297,9 @@ bool launch_mlp1_eval_tc(const float* row, const float* xt, const int64_t* y, in
     }
     const int ntile = (n + EV_TM - 1) / EV_TM;
     if (g_eval_tf32)
-        mlp1_eval_tc_kernel<false><<<ntile, EV_THREADS_TC, EvSmem::total, stream>>>(row, xt, slot, y, n, IN, H, OUT, NP, nstage, n_classes, cm);
+        mlp1_eval_tc_kernel<false><<<ntile, EV_THREADS_TC, EvSmem::total, stream>>>(row, xt, slot, y, n, IN, H, OUT, NP, nstage, n_classes, cm, score1);
     else
-        mlp1_eval_tc_kernel<true><<<ntile, EV_THREADS_TC, EvSmem::total, stream>>>(row, xt, slot, y, n, IN, H, OUT, NP, nstage, n_classes, cm);
+        mlp1_eval_tc_kernel<true><<<ntile, EV_THREADS_TC, EvSmem::total, stream>>>(row, xt, slot, y, n, IN, H, OUT, NP, nstage, n_classes, cm, score1);
     return cudaGetLastError() == cudaSuccess;
 }
 

@@ -223,6 +223,71 @@ kmeans_apply_kernel(float* __restrict__ C, const float* __restrict__ X, const in
     }
 }
 
+// Matched merge of two sets of k <= 8 centroids (KMeansHandler "hungarian", reference handler.py:617-630 with the
+// column assignment actually applied): the optimal assignment minimising the summed Euclidean distance
+// is found by enumerating all k! <= 40 320 permutations (factoradic decode, 256 threads, packed atomicMin -- ties go
+// to the lexicographically smallest permutation), then C = w_own * C + w_peer * C_peer[perm] in the same kernel.
+// No host round trip (the reference's path is cdist -> CPU -> scipy.linear_sum_assignment -> GPU).
+__global__ void __launch_bounds__(256)
+kmeans_match_merge_kernel(float* __restrict__ C, const float* __restrict__ P, int k, int dim, float w_own, float w_peer,
+                          PeerSync sync, int64_t* __restrict__ perm_out) {
+    __shared__ float cost[64];
+    __shared__ unsigned long long best;
+    __shared__ int perm[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (sync.ready != nullptr) { if (tid == 0) gb_wait_flag(sync.ready, sync.gen, sync.fault); __syncthreads(); }
+    if (tid == 0) best = ~0ull;
+    for (int e = warp; e < k * k; e += 8) {                 // cost[i][j] = || C[i] - P[j] ||
+        const int i = e / k, j = e % k;
+        float acc = 0.f;
+        for (int d = lane; d < dim; d += 32) { const float df = C[i * dim + d] - gb_ld_stream1(P + j * dim + d); acc = fmaf(df, df, acc); }
+        acc = gb_warp_sum(acc);
+        if (lane == 0) cost[i * 8 + j] = sqrtf(acc);
+    }
+    __syncthreads();
+    int nperm = 1;
+    for (int i = 2; i <= k; ++i) nperm *= i;
+    for (int pi = tid; pi < nperm; pi += 256) {
+        int avail[8], idx = pi, fact = nperm;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) avail[i] = i;
+        float total = 0.f;
+        for (int i = 0; i < k; ++i) {                        // factoradic digits, most significant first: lexicographic order
+            fact /= (k - i);
+            const int dgt = idx / fact; idx -= dgt * fact;
+            int col = avail[dgt];
+            for (int t = dgt; t < k - i - 1; ++t) avail[t] = avail[t + 1];
+            total += cost[i * 8 + col];
+        }
+        atomicMin(&best, ((unsigned long long)__float_as_uint(total) << 32) | (unsigned)pi);     // costs >= 0: bit order = value order
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int avail[8], idx = (int)(best & 0xffffffffull), fact = nperm;
+        for (int i = 0; i < 8; ++i) avail[i] = i;
+        for (int i = 0; i < k; ++i) {
+            fact /= (k - i);
+            const int dgt = idx / fact; idx -= dgt * fact;
+            perm[i] = avail[dgt];
+            for (int t = dgt; t < k - i - 1; ++t) avail[t] = avail[t + 1];
+            if (perm_out != nullptr) perm_out[i] = perm[i];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < k * dim; e += 256) {
+        const int i = e / dim, d = e - i * dim;
+        C[e] = w_own * C[e] + w_peer * gb_ld_stream1(P + perm[i] * dim + d);
+    }
+    if (sync.done != nullptr) { __syncthreads(); if (tid == 0) { __threadfence(); gb_red_release_sys_add(sync.done, 1u); } }
+}
+
+bool launch_kmeans_match_merge(float* C, const float* P, int k, int dim, float w_own, float w_peer, PeerSync sync,
+                               int64_t* perm_out, cudaStream_t stream) {
+    if (k < 1 || k > 8 || dim < 1) return false;
+    kmeans_match_merge_kernel<<<1, 256, 0, stream>>>(C, P, k, dim, w_own, w_peer, sync, perm_out);
+    return true;
+}
+
 void launch_kmeans_assign(const float* C, const float* X, int n, int k, int dim, int64_t* out,
                           cudaStream_t stream) {
     if (n <= 0) return;
@@ -289,6 +354,7 @@ void preload_small() {
     cudaFuncGetAttributes(&a, linear_seq_kernel);
     cudaFuncGetAttributes(&a, kmeans_assign_kernel);
     cudaFuncGetAttributes(&a, kmeans_apply_kernel);
+    cudaFuncGetAttributes(&a, kmeans_match_merge_kernel);
     cudaFuncGetAttributes(&a, mf_update_kernel);
 }
 

@@ -997,10 +997,8 @@ class TorchModelHandler(RowHandler):
             if fam is not None and fam[0] == "mlp1":
                 n_out = fam[1][2]
                 xx = x.reshape(x.shape[0], -1) if x.dim() > 2 else x
-                if n_out == 2:
-                    scores = ops.torch_ref.mlp1_logits(self.row, xx, fam[1])
-                    cm = ops.torch_ref.confusion_matrix(y, scores.argmax(1), 2)
-                    auc_in = scores[:, 1]
+                if n_out == 2:       # the evaluation kernel also writes the class-1 logit (AUC), no eager forward pass
+                    cm, auc_in = ops.mlp1_eval(self.row, xx, y, fam[1], n_out, want_scores=True)
                 else:
                     cm = ops.mlp1_eval(self.row, xx, y, fam[1], n_out)
             else:
@@ -1508,18 +1506,10 @@ class KMeansHandler(RowHandler):
         if self.matching == "naive" or GlobalSettings().reference_compat:
             self._weighted_merge(other_model_handler, 0.5, 0.5)
             return
-        from scipy.optimize import linear_sum_assignment
-
         def run(src, sync):
-            if sync is not None:     # cross-rank: stage the peer's centroids with the handshake
-                staged = torch.empty_like(self.row)
-                ops.snapshot(staged, src, sync)
-                src = staged
-            theirs = src[:self.k * self.dim].view(self.k, self.dim)
-            cost = torch.cdist(self.model, theirs).cpu().numpy()
-            cols = linear_sum_assignment(cost)[1]
-            perm = torch.as_tensor(cols, device=self.row.device)
-            self.model.copy_((self.model + theirs[perm]) / 2)
+            # k <= 8 on a GPU: exhaustive optimal matching + merge in ONE kernel (cross-rank handshake included);
+            # otherwise cdist -> scipy.linear_sum_assignment on the host
+            ops.kmeans_match_merge(self.row, src, self.k, self.dim, 0.5, 0.5, sync)
         self._pull(other_model_handler, run)
         self._version += 1
 

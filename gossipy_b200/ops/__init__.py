@@ -242,18 +242,20 @@ def _pretiled(X: torch.Tensor) -> torch.Tensor:
     return hit[1]
 
 
-def mlp1_eval(row, X, y, dims, n_classes: int, X_lp=None) -> torch.Tensor:
-    """Confusion matrix ``[C,C]`` (int32/int64 tensor on the row's device) of the MLP on (X, y)."""
+def mlp1_eval(row, X, y, dims, n_classes: int, X_lp=None, want_scores: bool = False):
+    """Confusion matrix ``[C,C]`` (int32/int64 tensor on the row's device) of the MLP on (X, y); with
+    ``want_scores`` also the class-1 logit of every sample (for the AUC of 2-output networks) as a second value."""
     if _use_native(row):
         d = tuple(int(v) for v in dims)
         if (X_lp is None and EVAL_IMPL != "simt" and d[0] % 4 == 0 and d[1] <= 128 and d[2] <= 10 and n_classes <= 16
                 and X.shape[0] >= 512):
             X_lp = _pretiled(X)
-        cm = native().mlp1_eval(row, X, y, d, int(n_classes), X_lp)
+        cm, sc = native().mlp1_eval(row, X, y, d, int(n_classes), X_lp, bool(want_scores))
         _count(2 if X_lp is not None else 1)
-        return cm
-    pred = torch_ref.mlp1_logits(row, X, dims).argmax(dim=1)
-    return torch_ref.confusion_matrix(y, pred, n_classes)
+        return (cm, sc) if want_scores else cm
+    logits = torch_ref.mlp1_logits(row, X, dims)
+    cm = torch_ref.confusion_matrix(y, logits.argmax(dim=1), n_classes)
+    return (cm, logits[:, 1 if logits.shape[1] > 1 else 0]) if want_scores else cm
 
 
 def logreg_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, key,
@@ -270,6 +272,25 @@ def logreg_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, ke
     _cpu_premerge(row, merge_from)
     return torch_ref.logreg_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, key,
                                   elem_scale_ages)
+
+
+def kmeans_match_merge(C_row, P_row, k: int, dim: int, w_own: float = .5, w_peer: float = .5, sync=None) -> torch.Tensor:
+    """Optimal-matching merge of two centroid sets in place (k <= 8 on the GPU: exhaustive search in one kernel);
+    returns the assignment ``perm`` (peer centroid matched to each own centroid)."""
+    if _use_native(C_row) and k <= 8:
+        perm = native().kmeans_match_merge(C_row, P_row, int(k), int(dim), float(w_own), float(w_peer), _st(sync))
+        _count()
+        return perm
+    if sync is not None:
+        sync.host_wait()
+    own, theirs = C_row[:k * dim].view(k, dim), P_row[:k * dim].view(k, dim)
+    from scipy.optimize import linear_sum_assignment
+    cols = linear_sum_assignment(torch.cdist(own, theirs).cpu().numpy())[1]
+    perm = torch.as_tensor(cols, device=C_row.device)
+    own.copy_(w_own * own + w_peer * theirs[perm])
+    if sync is not None:
+        sync.host_done()
+    return perm
 
 
 def logreg_scores(row, X, dims) -> torch.Tensor:

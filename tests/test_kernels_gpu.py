@@ -189,6 +189,23 @@ def test_mlp1_eval_confusion_matrix(impl, dims, n):
     assert int((cm.long() - want).abs().sum()) <= 2 * close_calls + (2 if impl == "tc-tf32" else 0)
 
 
+def test_mlp1_eval_scores_for_two_output_networks():
+    """2-output MLPs (AUC): the evaluation kernels also emit the class-1 logit -- no eager forward pass."""
+    ops, ref = _ops()
+    dims = (256, 128, 2)
+    X, y, row = _mlp_problem(1500, *dims)
+    y = y % 2
+    want = ref.mlp1_logits(row, X, dims)
+    for impl in ("simt", "tc"):
+        ops.EVAL_IMPL = impl
+        try:
+            cm, sc = ops.mlp1_eval(row, X, y, dims, 2, want_scores=True)
+        finally:
+            ops.EVAL_IMPL = ""
+        torch.testing.assert_close(sc, want[:, 1], rtol=1e-4, atol=1e-5)
+        assert int(cm.sum()) == 1500
+
+
 def test_logreg_train_and_scores():
     ops, ref = _ops()
     gen = torch.Generator().manual_seed(0)
@@ -227,6 +244,23 @@ def test_sequential_learners_kmeans_mf():
     ref.mf_update(Xu, b, Y, c, ratings, .1, .01); ops.mf_update(*dev, ratings.cuda(), .1, .01)
     for got, want in zip(dev, (Xu, b, Y, c)):
         torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("k,dim", [(1, 5), (3, 57), (5, 20), (8, 64)])
+def test_kmeans_matched_merge_equals_hungarian(k, dim):
+    """In-kernel exhaustive optimal matching (k <= 8) + merge vs scipy.linear_sum_assignment."""
+    from scipy.optimize import linear_sum_assignment
+    ops, _ = _ops()
+    gen = torch.Generator().manual_seed(k * 100 + dim)
+    A = torch.rand(k, dim, generator=gen)
+    B = A[torch.randperm(k, generator=gen)] + .05 * torch.randn(k, dim, generator=gen)      # a shuffled, perturbed copy
+    cols = linear_sum_assignment(torch.cdist(A, B).numpy())[1]
+    want = .25 * A + .75 * B[torch.as_tensor(cols)]
+    rowA = torch.zeros(max(32, (k * dim + 31) // 32 * 32), device="cuda"); rowA[:k * dim] = A.reshape(-1).cuda()
+    rowB = torch.zeros_like(rowA); rowB[:k * dim] = B.reshape(-1).cuda()
+    perm = ops.kmeans_match_merge(rowA, rowB, k, dim, .25, .75)
+    assert perm.cpu().tolist() == cols.tolist()
+    torch.testing.assert_close(rowA[:k * dim].view(k, dim).cpu(), want, rtol=1e-6, atol=1e-6)
 
 
 def test_keyed_permutation_device_matches_host():
