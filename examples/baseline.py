@@ -11,7 +11,7 @@ from gossipy_b200.model.handler import TorchModelHandler
 from gossipy_b200.model.nn import LogisticRegression, TorchMLP
 
 rank, world = setup(98765)
-X, y = load_classification_dataset("spambase", as_tensor=True)
+X, y = load_classification_dataset("spambase", as_tensor=True, synthetic_fallback=True)  # (no network: same-shape synthetic data)
 data_handler = ClassificationDataHandler(X, y, test_size=.1)
 dim = data_handler.Xtr.shape[1]
 for name, net, lr in (("logistic regression", LogisticRegression(dim, 2), 1.0),

@@ -15,7 +15,7 @@ from gossipy_b200.simul import All2AllGossipSimulator, SimulationReport
 
 rank, world = setup(98765)
 sync_rounds = os.environ.get("GOSSIPY_SYNC", "0") == "1"
-X, y = load_classification_dataset("spambase", as_tensor=True)
+X, y = load_classification_dataset("spambase", as_tensor=True, synthetic_fallback=True)  # (no network: same-shape synthetic data)
 data_handler = ClassificationDataHandler(X, y, test_size=.1)
 n_nodes = cap_nodes(8 if sync_rounds else 100)
 dispatcher = DataDispatcher(data_handler, n=n_nodes, eval_on_user=False, auto_assign=True)

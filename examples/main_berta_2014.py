@@ -9,7 +9,7 @@ from gossipy_b200.node import GossipNode
 from gossipy_b200.simul import GossipSimulator, SimulationReport
 
 rank, world = setup(98765)
-X, y = load_classification_dataset("spambase", as_tensor=True)
+X, y = load_classification_dataset("spambase", as_tensor=True, synthetic_fallback=True)  # (no network: same-shape synthetic data)
 n = cap_nodes(X.shape[0])
 data_handler = ClusteringDataHandler(X[:n], y[:n])
 dispatcher = DataDispatcher(data_handler, eval_on_user=False, auto_assign=True)

@@ -11,7 +11,7 @@ from gossipy_b200.node import GossipNode
 from gossipy_b200.simul import GossipSimulator, SimulationReport
 
 rank, world = setup(98765)
-X, y = load_classification_dataset("spambase", as_tensor=True)
+X, y = load_classification_dataset("spambase", as_tensor=True, synthetic_fallback=True)  # (no network: same-shape synthetic data)
 data_handler = ClassificationDataHandler(X, y, test_size=.1)
 n_nodes = cap_nodes(100)
 dispatcher = DataDispatcher(data_handler, n=n_nodes, eval_on_user=False, auto_assign=True)

@@ -34,7 +34,7 @@ def barabasi_albert(n: int, m: int, seed: int = 42) -> np.ndarray:
 
 
 rank, world = setup(98765)
-X, y = load_classification_dataset("spambase", as_tensor=True)
+X, y = load_classification_dataset("spambase", as_tensor=True, synthetic_fallback=True)  # (no network: same-shape synthetic data)
 y = 2 * y - 1
 n_train = cap_nodes(int(X.shape[0] * .9))
 n_test = X.shape[0] // 10

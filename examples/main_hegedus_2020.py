@@ -9,7 +9,7 @@ from gossipy_b200.node import GossipNode
 from gossipy_b200.simul import GossipSimulator, SimulationReport
 
 rank, world = setup(98765)
-ratings, n_users, n_items = load_recsys_dataset("ml-1m")
+ratings, n_users, n_items = load_recsys_dataset("ml-1m", synthetic_fallback=True)  # (no network: same-shape synthetic data)
 n_users = cap_nodes(n_users)
 ratings = {u: r for u, r in ratings.items() if u < n_users}
 data_handler = RecSysDataHandler(ratings, n_users, n_items, test_size=.1, seed=42)

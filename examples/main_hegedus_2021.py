@@ -24,7 +24,7 @@ if os.environ.get("GOSSIPY_MODEL", "logreg") == "mlp":
     net = TorchMLP(784, 10, (100,))
     opt = {"lr": .1, "weight_decay": .001}
 else:
-    X, y = load_classification_dataset("spambase", as_tensor=True)
+    X, y = load_classification_dataset("spambase", as_tensor=True, synthetic_fallback=True)  # (no network: same-shape synthetic data)
     data_handler = ClassificationDataHandler(X, y, test_size=.1)
     net = LogisticRegression(data_handler.Xtr.shape[1], 2)
     opt = {"lr": 1, "weight_decay": .001}

@@ -17,7 +17,7 @@ from gossipy_b200.simul import GossipSimulator, SimulationReport
 rank, world = setup(98765)
 n_nodes = cap_nodes(8)
 n_keep = int(os.environ.get("GOSSIPY_SAMPLES", 4000))
-(Xtr, ytr), (Xte, yte) = get_CIFAR10()
+(Xtr, ytr), (Xte, yte) = get_CIFAR10(synthetic_fallback=True)  # (no network: same-shape synthetic data)
 Xtr, ytr, Xte, yte = Xtr[:n_keep], torch.as_tensor(ytr[:n_keep]), Xte[:n_keep // 5], torch.as_tensor(yte[:n_keep // 5])
 half_tr, half_te = Xtr.shape[0] // 2, Xte.shape[0] // 2
 Xtr[half_tr:] = torch.rot90(Xtr[half_tr:], 2, (2, 3))   # second half of the clients sees rotated images

@@ -11,7 +11,7 @@ from gossipy_b200.node import GossipNode
 from gossipy_b200.simul import GossipSimulator, SimulationReport
 
 rank, world = setup(98765)
-X, y = load_classification_dataset("spambase", as_tensor=True)
+X, y = load_classification_dataset("spambase", as_tensor=True, synthetic_fallback=True)  # (no network: same-shape synthetic data)
 y = 2 * y - 1                                            # labels in {-1, +1}
 n_train = cap_nodes(int(X.shape[0] * .9))
 data_handler = ClassificationDataHandler(X[:n_train + X.shape[0] // 10], y[:n_train + X.shape[0] // 10],

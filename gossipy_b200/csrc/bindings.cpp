@@ -147,7 +147,9 @@ void set_train_impl(std::string impl) { set_default_train_impl(parse_train_impl(
 int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_t, int64_t, int64_t> dims,
                    int64_t batch_size, int64_t local_epochs, double lr, double wd, int64_t key,
                    c10::optional<at::Tensor> part_id, c10::optional<at::Tensor> ages, std::string impl,
-                   c10::optional<at::Tensor> peer, double w_self, double w_peer, c10::optional<Sync> sync) {
+                   c10::optional<at::Tensor> peer, double w_self, double w_peer, c10::optional<Sync> sync,
+                   double momentum = 0.0, double dampening = 0.0, bool nesterov = false,
+                   c10::optional<at::Tensor> mom = c10::nullopt, bool mom_first = false) {
     check_row(row, "row"); check_row(X, "X");
     TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.is_contiguous() && X.dim() == 2);
     TrainParams p{};
@@ -170,6 +172,12 @@ int64_t mlp1_train(at::Tensor row, at::Tensor X, at::Tensor y, std::tuple<int64_
         TORCH_CHECK(peer->is_cuda() && peer->scalar_type() == at::kFloat && peer->numel() >= P);
         p.peer = peer->data_ptr<float>(); p.w_self = (float)w_self; p.w_peer = (float)w_peer;
         p.sync = to_sync(sync);
+    }
+    if (momentum != 0.0) {
+        TORCH_CHECK(mom.has_value() && mom->is_cuda() && mom->scalar_type() == at::kFloat && mom->is_contiguous() &&
+                    mom->numel() >= P, "momentum needs the momentum-buffer row");
+        p.momentum = (float)momentum; p.dampening = (float)dampening; p.nesterov = nesterov;
+        p.mom = mom->data_ptr<float>(); p.mom_first = mom_first;
     }
     c10::cuda::CUDAGuard guard(row.device());
     const TrainImpl which = parse_train_impl(impl);
@@ -512,7 +520,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"), py::arg("key"),
           py::arg("part_id") = py::none(), py::arg("ages") = py::none(), py::arg("impl") = "",
           py::arg("peer") = py::none(), py::arg("w_self") = 1.0, py::arg("w_peer") = 0.0,
-          py::arg("sync") = py::none());
+          py::arg("sync") = py::none(), py::arg("momentum") = 0.0, py::arg("dampening") = 0.0, py::arg("nesterov") = false,
+          py::arg("mom") = py::none(), py::arg("mom_first") = false);
     m.def("mlp1_train_tc_debug", &gb::mlp1_train_tc_debug, py::arg("row"), py::arg("X"), py::arg("y"),
           py::arg("dims"), py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"),
           py::arg("key"), py::arg("impl") = "tc");

@@ -33,6 +33,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <deque>
 #include <stdexcept>
 #include <string>
@@ -69,6 +70,7 @@ struct Node {
 struct Slot {
     int64_t age = 0;
     std::vector<int64_t> ages_v; int pid = 0;
+    int state = 0;                          // debug mode: 0 free, 1 written (on the wire), checked on every transition
     cudaEvent_t written = nullptr, read = nullptr; bool has_reader = false;      // same-rank ordering
     float* data = nullptr;                                                        // peer-mapped when the slot lives on another rank
     uint32_t* ready = nullptr; uint32_t* done = nullptr;                          // cross-rank handshake words (owner's memory)
@@ -97,6 +99,8 @@ public:
           lr_((float)lr), wd_((float)wd), seed_(base_seed), cuda_(use_cuda), mode_(mode), L_(limited_merge),
           pools_(1), free_(1) {
         if (n_nodes <= 0) throw std::invalid_argument("n_nodes must be positive");
+        const char* dbg = std::getenv("GOSSIPY_EXEC_DEBUG");
+        debug_ = dbg != nullptr && dbg[0] != '\0' && dbg[0] != '0';
         if (mode != 1 && mode != 2 && mode != 4) throw std::invalid_argument("mode must be UPDATE, MERGE_UPDATE or PASS");
     }
     ~StreamExecutor() {
@@ -191,7 +195,10 @@ public:
                     break;
                 case EV_DROP: {
                     auto it = inflight_.find(id);
-                    if (it != inflight_.end()) { free_[it->second.first].push_back(it->second.second); inflight_.erase(it); }
+                    if (it != inflight_.end()) {
+                        if (debug_) pools_[it->second.first][it->second.second].state = 0;
+                        free_[it->second.first].push_back(it->second.second); inflight_.erase(it);
+                    }
                     break;
                 }
                 case EV_DELIVER:
@@ -214,6 +221,7 @@ public:
     std::vector<int64_t> ages() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.age); return v; }
     std::vector<int64_t> counters() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.counter); return v; }
     int64_t launches() const { return launches_; }
+    bool debug() const { return debug_; }
     // messages on the wire: (message id, rank, slot, age [, partition id, age of every partition]) -- checkpointing
     std::vector<std::vector<int64_t>> inflight() const {
         std::vector<std::vector<int64_t>> v;
@@ -263,6 +271,14 @@ private:
         const int s = fl.front(); fl.pop_front();
         Node& nd = nodes_.at(node);
         Slot& sl = pools_[rk][s];
+        if (debug_) {       // race-debug mode (GOSSIPY_EXEC_DEBUG=1): every slot has ONE writer and ONE reader per life
+            if (sl.state != 0) throw std::logic_error("executor debug: snapshot into a slot that is still on the wire");
+            for (const auto& kv : inflight_)
+                if (kv.second.first == rk && kv.second.second == s) throw std::logic_error("executor debug: free list and in-flight table share a slot");
+            if (inflight_.count(msg_id)) throw std::logic_error("executor debug: message id sent twice");
+            if (world_ > 1 && sl.acked > sl.remote_reads) throw std::logic_error("executor debug: more acknowledgements than remote reads");
+            sl.state = 1;
+        }
         sl.age = nd.age;
         if (n_parts_ > 0) {                               // node.py::PartitioningBasedNode._payload_extras (keyed form)
             sl.ages_v = nd.ages_v;
@@ -338,6 +354,12 @@ private:
         inflight_.erase(it);
         Node& nd = nodes_.at(node);
         Slot& sl = pools_[rk][s];
+        if (debug_) {
+            if (sl.state != 1) throw std::logic_error("executor debug: delivery of a slot that holds no snapshot");
+            if (cuda_ && mine(node) && !(world_ > 1 && rk != owner_[node]) && sl.written == nullptr && sl.gen == 0)
+                throw std::logic_error("executor debug: local reader without a writer event");
+            sl.state = 0;
+        }
         const bool exec = mine(node);
         const bool remote = world_ > 1 && rk != owner_[node];      // the snapshot lives on another rank than the reader
         if (remote) sl.remote_reads += 1;                           // replicated: the owner will wait for this many acks
@@ -423,6 +445,7 @@ private:
     int n_parts_ = 0; const int64_t* part_id_ = nullptr;
     std::vector<uintptr_t> seg_ptrs_; std::vector<int> seg_counts_;
     int64_t launches_ = 0, resume_at_ = -1;
+    bool debug_ = false;
 };
 
 void bind_executor(py::module_& m) {
@@ -446,6 +469,7 @@ void bind_executor(py::module_& m) {
         .def_property_readonly("resume_at", &StreamExecutor::resume_at)
         .def_property_readonly("free_slots", &StreamExecutor::free_slots)
         .def_property_readonly("launches", &StreamExecutor::launches)
+        .def_property_readonly("debug", &StreamExecutor::debug)
         .def("ages", &StreamExecutor::ages)
         .def("counters", &StreamExecutor::counters)
         .def("inflight", &StreamExecutor::inflight)

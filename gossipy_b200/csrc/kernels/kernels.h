@@ -68,6 +68,9 @@ struct TrainParams {
     __host__ __device__ int64_t age_of(int part) const { return ages != nullptr ? ages[part] : ages_val[part]; }
     int Hs, C, nbuf;
     float* dbg;                 // optional debug dump (tests)
+    // torch.optim.SGD momentum (fused tcgen05 kernel only): `mom` = momentum-buffer row (same layout as `row`),
+    // mom_first = the buffer holds no state yet (torch initialises it with the first gradient)
+    float momentum, dampening; bool nesterov; float* mom; bool mom_first;
     // fused MERGE_UPDATE: when `peer` is set the kernel starts from w_self*row + w_peer*peer
     // (the peer row is pulled over NVLink while the weights are loaded on chip)
     const float* peer; float w_self, w_peer; PeerSync sync;

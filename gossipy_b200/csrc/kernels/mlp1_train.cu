@@ -348,6 +348,11 @@ bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const
     if (impl == kTrainAuto) impl = g_auto_impl;
     const bool scaled = p.scaled();
     if (scaled && p.n_parts > MAX_PARTS) { *why = "fused partitioned training supports <= 16 partitions"; return false; }
+    if (p.momentum != 0.f) {                                       // fused momentum-SGD: the tcgen05 kernel only
+        if ((impl == kTrainAuto || impl == kTrainTc8) && mlp1_train_tc4(p, 8, true, stream)) return true;
+        *why = "fused momentum-SGD needs the tcgen05 (tc8) kernel: 32 <= in <= 896 (multiple of 4), hidden <= 128, out <= 10, batch <= 32";
+        return false;
+    }
     if (scaled && (impl == kTrainAuto || impl == kTrainTc8)) {     // K3 on the tensor-core kernel (<= 16 partitions)
         if (mlp1_train_tc4(p, 8, true, stream)) return true;
         if (impl == kTrainTc8) { *why = "tcgen05 (tc8) training kernel does not support this partitioned configuration"; return false; }

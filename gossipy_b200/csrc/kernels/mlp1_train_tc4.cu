@@ -29,6 +29,10 @@
 // (reference model/handler.py:497-520).  Because the update reaches the master through registers anyway (W += G),
 // the per-element factor 1/age[part(j, k)] is applied there -- partition ids of a thread's 56 weights are packed
 // into 7 registers at kernel start -- and to the b1 / W2 / b2 steps; the tensor-core work is unchanged.
+// Momentum (MOM = true): torch.optim.SGD with momentum / dampening / nesterov / weight decay.  The momentum buffer of
+// W1 lives in a fourth TMEM tile V next to W, Wlo and G (4 x 112 columns + 64 accumulator columns = 512), and the
+// W += G pass becomes  d = G + wd*W;  V = mu*V + (1-tau)*d;  W -= lr*(nesterov ? d + mu*V : V)  in registers; the
+// buffers of b1 / W2 / b2 sit with their owners.  State is loaded from / stored to the handler's momentum row.
 // Warp roles: warps 0-7 compute, warp 8 issues all MMAs and bulk copies and never touches data.
 // Operand tiles (hi and lo images of X in both K-major layouts) are written ahead of time by mlp1_stage4_kernel.
 #include "tc_common.cuh"
@@ -46,14 +50,16 @@ constexpr int T4_DZP = 12;                // floats per dz2 row in shared memory
 constexpr int T4_WCB = 64, T4_WLD = 65;   // TMEM fill / write-back scratch: 64-column blocks, odd pitch
 constexpr int T4_NPROF = 14;   // phase counters (compute thread 0, warp 4 lane 0 and the issuer lane)
 
-template <int NC, bool X3> struct T4Cfg {
+template <int NC, bool X3, bool MOM = false> struct T4Cfg {
     static_assert(!X3 || NC == 8, "the error-compensated path needs W, Wlo and G in TMEM: 3 x FP <= 384 columns");
+    static_assert(!MOM || X3, "momentum rides on the W += G pass of the error-compensated form");
     static constexpr int NIMG = X3 ? 2 : 1;
-    static constexpr int FP_MAX = NC == 4 ? 240 : 128;          // feature columns per CTA (multiple of 16)
+    static constexpr int FP_MAX = NC == 4 ? 240 : (MOM ? 112 : 128);   // feature columns per CTA (multiple of 16)
     static constexpr int S = T4_B / NC;                         // samples owned per CTA
     static constexpr int GPO = S / 4;                           // float4 sample groups per owner
-    static constexpr int t_w1 = 0, t_wlo = FP_MAX, t_g = 2 * FP_MAX;
-    static constexpr int t_d1 = X3 ? 3 * FP_MAX : FP_MAX;       // X3: three 32-column accumulators
+    static constexpr int t_w1 = 0, t_wlo = FP_MAX, t_g = 2 * FP_MAX, t_v = 3 * FP_MAX;
+    static constexpr int t_d1 = MOM ? 4 * FP_MAX : X3 ? 3 * FP_MAX : FP_MAX;
+    static constexpr int d1_cols = MOM ? 64 : X3 ? 96 : 32;     // X3: three accumulators; MOM: chain c shares chain a's
     // shared memory (byte offsets; base rounded up to 1024 B)
     static constexpr int tile_max = T4_B * FP_MAX * 4;
     static constexpr int xf = 0;
@@ -74,7 +80,7 @@ template <int NC, bool X3> struct T4Cfg {
     static constexpr int mbar = ys + 2 * T4_B * 4;               // 10 x uint64
     static constexpr int tslot = mbar + 128;
     static constexpr int total = tslot + 16;
-    static_assert(t_d1 + (X3 ? 96 : 32) <= 512, "TMEM budget");
+    static_assert(t_d1 + d1_cols <= 512, "TMEM budget");
     static_assert(total + 1024 <= 227 * 1024, "shared memory budget");
     static_assert(T4_HP * T4_WLD * 4 <= hsl - a2, "fill / write-back scratch must fit in a2 + rs + ag");
     static_assert(NC * GPO == 8, "8 float4 sample groups");
@@ -132,11 +138,12 @@ GB_DEVICE void warp_reduce40(float (&v)[40], int lane) {
     }
 }
 
-template <int NC, bool X3, bool SC>
+template <int NC, bool X3, bool SC, bool MOM>
 __global__ void __launch_bounds__(T4_THREADS, 1)
 mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const int total_steps,
                       const float* __restrict__ stage, const int* __restrict__ stage_ys) {
-    using C = T4Cfg<NC, X3>;
+    using C = T4Cfg<NC, X3, MOM>;
+    static_assert(!(MOM && SC), "momentum and partition scaling are not combined");
     constexpr int NIMG = C::NIMG, GPO = C::GPO, S = C::S;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // round up on the SHARED-window address: going through uintptr_t would lose the address space
@@ -281,13 +288,39 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             }
             __syncthreads();
         }
+        if (MOM) {                // momentum buffer of W1 -> TMEM tile V (zeros when there is no state yet)
+            for (int cb = 0; cb * T4_WCB < FP; ++cb) {
+                const int c0 = cb * T4_WCB;
+                for (int idx = tid; idx < H * (T4_WCB / 4); idx += T4_THREADS) {
+                    const int rr = idx >> 4, c = c0 + ((idx & 15) << 2);
+                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < fcnt && !p.mom_first) w = *reinterpret_cast<const float4*>(p.mom + (size_t)rr * IN + f0 + c);
+                    float* d = wbuf + rr * T4_WLD + (c - c0);
+                    d[0] = w.x; d[1] = w.y; d[2] = w.z; d[3] = w.w;
+                }
+                __syncthreads();
+                if (warp < T4_ISSUER) {
+#pragma unroll
+                    for (int gl = 0; gl < 2; ++gl) {
+                        const int g = cb * 4 + half * 2 + gl;
+                        if (g * 16 < FP) {
+                            float v[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = (j < H) ? wbuf[j * T4_WLD + (half * 2 + gl) * 16 + i] : 0.f;
+                            tmem_st16(tlane + C::t_v + g * 16, v);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
         tmem_st_wait();
     }
     tc_fence_before();
     gb_cluster_sync();            // peers are running: their shared memory may be written from here on
     tc_fence_after();
 
-    const float decay = 1.f - p.lr * p.wd;
+    const float decay = MOM ? 1.f : 1.f - p.lr * p.wd;     // momentum: weight decay enters the buffer (d = g + wd*w), no lazy scale
     const int spe = (n + B - 1) / B;
     const bool profiling = p.dbg != nullptr && p.lr != 0.f;
     unsigned prof[T4_NPROF];
@@ -336,7 +369,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                     const uint64_t bhi = make_sdesc(smem_u32(xf), 128u, x_sbo);
 #pragma unroll 4
                     for (int k = 0; k < ksteps; ++k)
-                        mma_tf32_ts(d1 + 64u, wlo + (uint32_t)k * 8u, bhi + (uint64_t)(k * 16), idesc_fwd, k > 0);
+                        mma_tf32_ts(d1 + (MOM ? 0u : 64u), wlo + (uint32_t)k * 8u, bhi + (uint64_t)(k * 16), idesc_fwd, MOM ? true : k > 0);
                     mma_commit(&mbar[2]);
                 }
                 __syncwarp();
@@ -441,6 +474,26 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             mbar_expect_tx(&mbar[9], hs_bytes);
             mbar_expect_tx(&mbar[4], w2_bytes);
         }
+        // momentum buffers of the small parameters: b1 (every thread of hidden unit j), my W2 group, b2 (warp 5)
+        float vb1 = 0.f, vb2 = 0.f;
+        float4 vw2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MOM && !p.mom_first) {
+            if (j < H) vb1 = p.mom[off_b1 + j];
+            if (warp == 5 && lane < OUT) vb2 = p.mom[off_b2 + lane];
+            if (tid < ((js_valid + 3) >> 2) * T4_OUTV) {
+                const int jq = tid / T4_OUTV, o = tid - jq * T4_OUTV, jg = (int)rank * JS + 4 * jq;
+                if (o < OUT) {
+                    const float* mp = p.mom + off_w2 + (size_t)o * H + jg;
+                    vw2 = make_float4(jg < H ? mp[0] : 0.f, jg + 1 < H ? mp[1] : 0.f, jg + 2 < H ? mp[2] : 0.f, jg + 3 < H ? mp[3] : 0.f);
+                }
+            }
+        }
+        // one scalar SGD step with torch.optim.SGD semantics: returns the new parameter, updates the buffer
+        auto sgd_mom = [&](float w, float g, float& v, bool first) -> float {
+            const float d = fmaf(p.wd, w, g);
+            v = first ? d : fmaf(p.momentum, v, (1.f - p.dampening) * d);
+            return w - p.lr * (p.nesterov ? fmaf(p.momentum, v, d) : v);
+        };
         // K3: partition ids (4 bits each) of the master-weight entries this thread adds G to, and of its small parameters
         uint32_t pidw[SC ? 8 : 1];
         uint32_t pid_b1 = 0u, pid_b2 = 0u, pid_w2 = 0u;
@@ -484,7 +537,13 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             {
                 float acc[16];
                 tmem_ld16(tlane + C::t_d1 + 16 * half, acc);
-                if (X3) {
+                if (X3 && MOM) {
+                    float accb[16];
+                    tmem_ld16(tlane + C::t_d1 + 32 + 16 * half, accb);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] += accb[i];
+                } else if (X3) {
                     float accb[16], accc[16];
                     tmem_ld16(tlane + C::t_d1 + 32 + 16 * half, accb);
                     tmem_ld16(tlane + C::t_d1 + 64 + 16 * half, accc);
@@ -599,7 +658,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             // of all 32 samples.
             constexpr bool kSplitRoles = (GPO == 1);
             if (!kSplitRoles || half == 1) {
-                const float ascale = -p.lr / s_next;
+                const float ascale = MOM ? 1.f : -p.lr / s_next;      // momentum: G is the raw gradient
                 float gb1 = 0.f;
                 constexpr int NQ = kSplitRoles ? 8 : 4;
                 const int q0 = kSplitRoles ? 0 : 4 * half;
@@ -649,7 +708,8 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                     float g = dv[0];
 #pragma unroll
                     for (int o = 1; o < T4_OUTV; ++o) g = (lane == o) ? dv[o] : g;
-                    b2s[lane] = fmaf(SC ? -p.lr * inva[16 * par + pid_b2] : -p.lr, g, b2s[lane] * decay);
+                    if (MOM) b2s[lane] = sgd_mom(b2s[lane], g, vb2, p.mom_first && s == 0);
+                    else b2s[lane] = fmaf(SC ? -p.lr * inva[16 * par + pid_b2] : -p.lr, g, b2s[lane] * decay);
                 }
             }
             if (js_valid > 0) {
@@ -679,10 +739,17 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                         const float* ia = inva + 16 * par;
                         l0 *= ia[pid_w2 & 15u]; l1 *= ia[(pid_w2 >> 4) & 15u]; l2 *= ia[(pid_w2 >> 8) & 15u]; l3 *= ia[(pid_w2 >> 12) & 15u];
                     }
-                    const float4 wn = make_float4(jg < H ? fmaf(l0, g[0], wo.x * decay) : 0.f,
-                                                  jg + 1 < H ? fmaf(l1, g[1], wo.y * decay) : 0.f,
-                                                  jg + 2 < H ? fmaf(l2, g[2], wo.z * decay) : 0.f,
-                                                  jg + 3 < H ? fmaf(l3, g[3], wo.w * decay) : 0.f);
+                    float4 wn;
+                    if (MOM) {
+                        const bool first = p.mom_first && s == 0;
+                        wn = make_float4(jg < H ? sgd_mom(wo.x, g[0], vw2.x, first) : 0.f, jg + 1 < H ? sgd_mom(wo.y, g[1], vw2.y, first) : 0.f,
+                                         jg + 2 < H ? sgd_mom(wo.z, g[2], vw2.z, first) : 0.f, jg + 3 < H ? sgd_mom(wo.w, g[3], vw2.w, first) : 0.f);
+                    } else {
+                        wn = make_float4(jg < H ? fmaf(l0, g[0], wo.x * decay) : 0.f,
+                                         jg + 1 < H ? fmaf(l1, g[1], wo.y * decay) : 0.f,
+                                         jg + 2 < H ? fmaf(l2, g[2], wo.z * decay) : 0.f,
+                                         jg + 3 < H ? fmaf(l3, g[3], wo.w * decay) : 0.f);
+                    }
 #pragma unroll
                     for (int d = 0; d < NC; ++d)
                         st_async_v4(gb_map_shared(slot, (uint32_t)d), wn, gb_map_shared(&mbar[4], (uint32_t)d));
@@ -706,7 +773,15 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                         tmem_ld16(tlane + C::t_g + (g + 2) * 16, gv2);
                     }
                     tmem_ld_wait();
-                    if (SC) {
+                    if (MOM) {
+                        float vv[16];
+                        tmem_ld16(tlane + C::t_v + g * 16, vv);
+                        tmem_ld_wait();
+                        const bool first = p.mom_first && s == 0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) wv[i] = sgd_mom(wv[i], gv[i], vv[i], first);
+                        tmem_st16(tlane + C::t_v + g * 16, vv);
+                    } else if (SC) {
                         const float* ia = inva + 16 * par;
                         const int gi = (g - half) >> 1;
                         const uint32_t pa = gi == 0 ? pidw[0] : gi == 2 ? pidw[4] : 0u, pb = gi == 0 ? pidw[1] : gi == 2 ? pidw[5] : 0u;
@@ -723,7 +798,15 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                         tmem_st16(tlane + C::t_wlo + g * 16, gv);
                     }
                     if (two) {
-                        if (SC) {
+                        if (MOM) {
+                            float vv[16];
+                            tmem_ld16(tlane + C::t_v + (g + 2) * 16, vv);
+                            tmem_ld_wait();
+                            const bool first = p.mom_first && s == 0;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) wv2[i] = sgd_mom(wv2[i], gv2[i], vv[i], first);
+                            tmem_st16(tlane + C::t_v + (g + 2) * 16, vv);
+                        } else if (SC) {
                             const float* ia = inva + 16 * par;
                             const int gi = ((g - half) >> 1) + 1;
                             const uint32_t pa = gi == 1 ? pidw[2] : gi == 3 ? pidw[6] : 0u, pb = gi == 1 ? pidw[3] : gi == 3 ? pidw[7] : 0u;
@@ -750,13 +833,28 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
             bar_compute();                                       // end of step: gb1p complete, buffers of this step consumed
             T4_STAMP(11);
             if (tid == 0) mbar_expect_tx(&mbar[9], hs_bytes);    // next step's h slices
-            b1r = fmaf(SC ? -p.lr * inva[16 * par + pid_b1] : -p.lr, gb1p[j] + gb1p[T4_HP + j], b1r * decay);
+            if (MOM) b1r = sgd_mom(b1r, gb1p[j] + gb1p[T4_HP + j], vb1, p.mom_first && s == 0);
+            else b1r = fmaf(SC ? -p.lr * inva[16 * par + pid_b1] : -p.lr, gb1p[j] + gb1p[T4_HP + j], b1r * decay);
             sscale = s_next;
         }
         // the last step's W2 all-gather
         mbar_wait_dsm(&mbar[4], (uint32_t)((total_steps - 1) & 1));
         if (tid == 0) red[0] = sscale;
         if (rank == 0 && j < H && half == 0) b1g[j] = b1r;
+        if (MOM) {                                           // momentum buffers of the small parameters -> the handler's row
+            if (rank == 0 && j < H && half == 0) p.mom[off_b1 + j] = vb1;
+            if (rank == 0 && warp == 5 && lane < OUT) p.mom[off_b2 + lane] = vb2;
+            if (tid < ((js_valid + 3) >> 2) * T4_OUTV) {
+                const int jq = tid / T4_OUTV, o = tid - jq * T4_OUTV, jg = (int)rank * JS + 4 * jq;
+                if (o < OUT) {
+                    float* mp = p.mom + off_w2 + (size_t)o * H + jg;
+                    if (jg < H) mp[0] = vw2.x;
+                    if (jg + 1 < H) mp[1] = vw2.y;
+                    if (jg + 2 < H) mp[2] = vw2.z;
+                    if (jg + 3 < H) mp[3] = vw2.w;
+                }
+            }
+        }
     }
 
     // ---- every MMA has retired (all compute threads waited for the last update): write everything back -----------
@@ -788,6 +886,36 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                 if (c < fcnt) {
                     const float* sp = wbuf + rr * T4_WLD + (c - c0);
                     *reinterpret_cast<float4*>(p.row + (size_t)rr * IN + f0 + c) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (MOM) {                                               // TMEM tile V -> the momentum row (same path as W)
+        float* wbuf = a2;
+        for (int cb = 0; cb * T4_WCB < FP; ++cb) {
+            const int c0 = cb * T4_WCB;
+            if (warp < T4_ISSUER) {
+#pragma unroll
+                for (int gl = 0; gl < 2; ++gl) {
+                    const int g = cb * 4 + half * 2 + gl;
+                    if (g * 16 < FP) {
+                        float v[16];
+                        tmem_ld16(tlane + C::t_v + g * 16, v);
+                        tmem_ld_wait();
+                        if (j < H) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) wbuf[j * T4_WLD + (half * 2 + gl) * 16 + i] = v[i];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < H * (T4_WCB / 4); idx += T4_THREADS) {
+                const int rr = idx >> 4, c = c0 + ((idx & 15) << 2);
+                if (c < fcnt) {
+                    const float* sp = wbuf + rr * T4_WLD + (c - c0);
+                    *reinterpret_cast<float4*>(p.mom + (size_t)rr * IN + f0 + c) = make_float4(sp[0], sp[1], sp[2], sp[3]);
                 }
             }
             __syncthreads();
@@ -943,9 +1071,10 @@ static void* stage_buffer_for4(cudaStream_t stream, size_t bytes, bool may_alloc
     return ptr;
 }
 
-template <int NC, bool X3, bool SC>
+template <int NC, bool X3, bool SC, bool MOM = false>
 static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
-    using C = T4Cfg<NC, X3>;
+    using C = T4Cfg<NC, X3, MOM>;
+    if (MOM && (p.mom == nullptr || p.momentum <= 0.f)) return false;
     if (p.H > T4_HP || p.OUT > T4_OUTV || p.B > T4_B || p.IN % 4 != 0) return false;
     int FPC, FP, steps;
     const size_t bytes = mlp1_stage4_bytes(p.n, p.IN, p.B, p.epochs, NC, X3, &FPC, &FP, &steps);
@@ -968,7 +1097,7 @@ static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
         mlp1_stage4_kernel<X3><<<dim3(steps, NC), 256, smem, stream>>>(p.X, p.y, p.n, p.IN, p.B, p.epochs, p.key, NC, FPC, FP, out, ys);
     }
     if (SC && (p.n_parts > 16 || !p.scaled())) return false;
-    auto kern = mlp1_train_tc4_kernel<NC, X3, SC>;
+    auto kern = mlp1_train_tc4_kernel<NC, X3, SC, MOM>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::total + 1024) != cudaSuccess) return false;
@@ -987,6 +1116,7 @@ static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
 bool mlp1_train_tc4(const TrainParams& p, int nc, bool x3, cudaStream_t stream) {
     if (nc != 8) return false;      // (the kernel is written for NC in {4, 8}; only the 8-CTA form is validated and shipped)
     const bool scaled = p.scaled();
+    if (p.momentum != 0.f) return x3 && !scaled && tc4_launch<8, true, false, true>(p, stream);
     if (scaled) return x3 && tc4_launch<8, true, true>(p, stream);      // K3 rides on the W += G pass of the X3 form
     return x3 ? tc4_launch<8, true, false>(p, stream) : tc4_launch<8, false, false>(p, stream);
 }
@@ -1002,9 +1132,10 @@ bool reserve_train_staging(int n, int IN, int B, int epochs, int nc, bool x3, cu
 // on a cross-GPU flag could deadlock, so the extension loads everything up front)
 void preload_train_tc4() {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, true, false>);
-    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, true, true>);
-    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, false, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, true, false, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, true, true, false>);
+    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, true, false, true>);
+    cudaFuncGetAttributes(&a, mlp1_train_tc4_kernel<8, false, false, false>);
     cudaFuncGetAttributes(&a, mlp1_stage4_kernel<true>);
     cudaFuncGetAttributes(&a, mlp1_stage4_kernel<false>);
 }

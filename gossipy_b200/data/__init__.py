@@ -154,8 +154,12 @@ class AssignmentHandler:
                 if self.compat:      # the reference overwrites a random slot (may evict the only holder of another class)
                     picks[u][int(self.rng.integers(0, class_per_client))] = c
                     continue
-                free = [s for s in range(class_per_client) if c not in picks[u]]
-                picks[u][int(self.rng.choice(free))] = c
+                # only overwrite a slot whose class some OTHER client holds too: covering c must not uncover another
+                # class (class_per_client * n >= L guarantees such a slot exists somewhere; retry with another client)
+                holders = np.bincount(np.concatenate(picks), minlength=L)
+                free = [s for s in range(class_per_client) if holders[picks[u][s]] > 1]
+                if free:
+                    picks[u][int(self.rng.choice(free))] = c
         owner = np.zeros(len(yy), dtype=int)
         for ci, lbl in enumerate(labels):
             users = [u for u in range(n) if ci in picks[u]]
@@ -295,12 +299,14 @@ def _standardize(X: np.ndarray) -> np.ndarray:
 
 
 def load_classification_dataset(name_or_path: str, normalize: bool = True,
-                                as_tensor: bool = True, synthetic_fallback: bool = True):
+                                as_tensor: bool = True, synthetic_fallback: bool = False):
     """Load a classification data set by name or svmlight path (ref ``data/__init__.py:561-624``).
 
     sklearn's bundled sets (iris, breast, digits, wine) load offline.  The UCI / reuters sets
-    need a download; when that fails and ``synthetic_fallback`` is set, synthetic data of the
-    same shape is returned (with a warning) so that scripts still run on air-gapped GPU boxes.
+    need a download; when that fails the error is raised, like in the reference.  Only with an explicit
+    ``synthetic_fallback=True`` is synthetic data of the same shape returned instead (with a warning), so
+    that scripts still run on air-gapped GPU boxes -- results on real and synthetic data cannot be mixed up
+    silently (the examples opt in).
     """
     from . import synthetic
     X = y = None
@@ -352,7 +358,7 @@ def _download_named(name: str):
     return X, y
 
 
-def load_recsys_dataset(name: str, path: str = ".", synthetic_fallback: bool = True):
+def load_recsys_dataset(name: str, path: str = ".", synthetic_fallback: bool = False):
     """MovieLens ratings as ``{user: [(item, rating), ...]}`` (ref ``data/__init__.py:628-681``)."""
     from . import synthetic
     if name.startswith("synthetic:"):
@@ -395,7 +401,7 @@ def _torchvision_pair(cls_name: str, path: str):
         return cls(root=path, train=True, download=True), cls(root=path, train=False, download=True)
 
 
-def get_CIFAR10(path: str = "./data", as_tensor: bool = True, synthetic_fallback: bool = True):
+def get_CIFAR10(path: str = "./data", as_tensor: bool = True, synthetic_fallback: bool = False):
     """CIFAR-10 as ``((Xtr, ytr), (Xte, yte))``, images NCHW in [0,1] (ref ``:684-722``)."""
     from . import synthetic
     try:
@@ -411,7 +417,7 @@ def get_CIFAR10(path: str = "./data", as_tensor: bool = True, synthetic_fallback
     return (tr.data, tr.targets), (te.data, te.targets)
 
 
-def get_FashionMNIST(path: str = "./data", as_tensor: bool = True, synthetic_fallback: bool = True):
+def get_FashionMNIST(path: str = "./data", as_tensor: bool = True, synthetic_fallback: bool = False):
     """Fashion-MNIST as ``((Xtr, ytr), (Xte, yte))`` in [0,1] (ref ``:725-762``)."""
     from . import synthetic
     try:

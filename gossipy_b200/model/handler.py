@@ -611,6 +611,11 @@ class TorchModelHandler(RowHandler):
         self._opt_kind = self._classify_optimizer()
         self._fused = (self._family is not None and self._family[0] in ("mlp1", "logreg")
                        and self._opt_kind == "sgd_plain" and _is_plain_ce(criterion))
+        # torch.optim.SGD with momentum: fused as well for the MLP family inside the tensor-core kernel's envelope
+        # (momentum buffer of W1 in a TMEM tile); checked per update against the shard's shape
+        self._fused_momentum = (self._family is not None and self._family[0] == "mlp1"
+                                and self._opt_kind == "sgd_momentum" and _is_plain_ce(criterion)
+                                and type(self)._elem_scale is TorchModelHandler._elem_scale)
         self._grad_row: Optional[torch.Tensor] = None
         self._opt_rows: Dict[str, torch.Tensor] = {}
         self._opt_steps = 0
@@ -773,17 +778,29 @@ class TorchModelHandler(RowHandler):
         with _arena.on_stream(s):
             if self._fused and not (GlobalSettings().reference_compat and merge_from is None and self.batch_size):
                 steps = self._update_fused(x, y, merge_from)
+            elif (self.__dict__.get("_fused_momentum") and not GlobalSettings().reference_compat and not self.layout.int_buffers
+                  and ops.mlp1_momentum_supported(self._family[1], self.batch_size, int(x.shape[0]))):
+                steps = self._update_fused(x, y, merge_from, momentum=True)
             else:       # (compat + mini-batches: the reference's own shuffles, which only the autograd path can follow)
                 steps = self._update_generic(x, y)
         self._count_steps(steps)
 
-    def _update_fused(self, x: torch.Tensor, y: torch.Tensor, merge_from: Any = None) -> int:
+    def _update_fused(self, x: torch.Tensor, y: torch.Tensor, merge_from: Any = None, momentum: bool = False) -> int:
         fam, dims = self._family
-        lr = float(self.optimizer_params.get("lr", 1e-3))
-        wd = float(self.optimizer_params.get("weight_decay", 0.0))
+        p = self.optimizer_params
+        lr = float(p.get("lr", 1e-3))
+        wd = float(p.get("weight_decay", 0.0))
         fn = ops.mlp1_train if fam == "mlp1" else ops.logreg_train
         if x.dim() > 2:
             x = x.reshape(x.shape[0], -1)
+        if momentum:          # torch.optim.SGD(momentum=...): the buffer row is the one the flat optimizer kernel uses
+            buf = self._opt_rows.get("momentum")
+            first = buf is None
+            if first:
+                buf = self._opt_rows["momentum"] = torch.zeros_like(self.row)
+            mom = (float(p.get("momentum", 0.0)), float(p.get("dampening", 0.0)), bool(p.get("nesterov", False)), buf, first)
+            return fn(self.row, x, y, dims, self.batch_size, self.local_epochs, lr, wd, self._next_key(), None,
+                      merge_from=merge_from, momentum=mom)
         return fn(self.row, x, y, dims, self.batch_size, self.local_epochs, lr, wd,
                   self._next_key(), self._elem_scale(), merge_from=merge_from)
 

@@ -201,25 +201,36 @@ def _cpu_premerge(row, merge_from: Optional[MergeFrom]) -> None:
             sync.host_done()
 
 
+def mlp1_momentum_supported(dims, batch_size: int, n_samples: int) -> bool:
+    """Envelope of the fused momentum-SGD kernel (tcgen05, 8-CTA cluster; momentum buffer of W1 in a TMEM tile)."""
+    d_in, d_h, d_out = (int(v) for v in dims)
+    bs = n_samples if not batch_size else min(int(batch_size), n_samples)
+    return d_in % 4 == 0 and 32 <= d_in <= 896 and d_h <= 128 and d_out <= 10 and bs <= 32
+
+
 def mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, key,
                elem_scale_ages=None, impl: Optional[str] = None,
-               merge_from: Optional[MergeFrom] = None) -> int:
+               merge_from: Optional[MergeFrom] = None, momentum=None) -> int:
     """Fused local update of a 1-hidden-layer ReLU MLP; returns the number of SGD steps.
 
     ``merge_from = (peer_row, w_self, w_peer, sync)`` fuses the preceding merge into the same
-    launch (MERGE_UPDATE): training starts from ``w_self*row + w_peer*peer_row``."""
+    launch (MERGE_UPDATE): training starts from ``w_self*row + w_peer*peer_row``.
+    ``momentum = (mu, dampening, nesterov, buffer_row, first)``: torch.optim.SGD's momentum inside the kernel."""
     if _use_native(row):
         peer, ws, wp, sync = merge_from if merge_from is not None else (None, 1.0, 0.0, None)
+        mu, damp, nest, buf, first = momentum if momentum is not None else (0.0, 0.0, False, None, False)
         n = native().mlp1_train(row, X, y, tuple(int(d) for d in dims), int(batch_size),
                                 int(local_epochs), float(lr), float(weight_decay), int(key),
                                 None if elem_scale_ages is None else elem_scale_ages[0],
                                 None if elem_scale_ages is None else elem_scale_ages[1],
-                                impl or TRAIN_IMPL, peer, float(ws), float(wp), _st(sync))
+                                ("" if momentum is not None and (impl or TRAIN_IMPL) != "tc8" else impl or TRAIN_IMPL),
+                                peer, float(ws), float(wp), _st(sync),
+                                float(mu), float(damp), bool(nest), buf, bool(first))
         _count()
         return n
     _cpu_premerge(row, merge_from)
     return torch_ref.mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, weight_decay, key,
-                                elem_scale_ages)
+                                elem_scale_ages, momentum)
 
 
 EVAL_IMPL = ""          # "", "tc" or "simt": evaluation kernel choice ("" = tensor cores when the shape fits)

@@ -182,13 +182,16 @@ def mlp1_unpack(row: torch.Tensor, dims: Tuple[int, int, int]):
 @torch.no_grad()
 def mlp1_train(row: torch.Tensor, X: torch.Tensor, y: torch.Tensor, dims: Tuple[int, int, int],
                batch_size: int, local_epochs: int, lr: float, weight_decay: float, key: int,
-               elem_scale_ages: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> int:
+               elem_scale_ages: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               momentum: Optional[Tuple[float, float, bool, torch.Tensor, bool]] = None) -> int:
     """One ``_update`` of a ``Linear-ReLU-Linear`` net with mean cross-entropy and plain SGD
     (ref ``handler.py:235-258``), done with explicit fp32 forward/backward on the flat row.
 
     ``elem_scale_ages = (part_id[int64, P], ages[int64, n_parts])``: PartitionedTMH semantics --
     before every step all ages are incremented and the gradient of element e is divided by
-    ``ages[part_id[e]]`` (ref ``handler.py:503-520``).  Returns the number of SGD steps.
+    ``ages[part_id[e]]`` (ref ``handler.py:503-520``).  ``momentum = (mu, dampening, nesterov, buffer row,
+    first)``: torch.optim.SGD's momentum update on the flat buffer (``first``: the buffer holds no state
+    yet).  Returns the number of SGD steps.
     """
     W1, b1, W2, b2 = mlp1_unpack(row, dims)
     n = X.shape[0]
@@ -218,7 +221,17 @@ def mlp1_train(row: torch.Tensor, X: torch.Tensor, y: torch.Tensor, dims: Tuple[
             ages += 1
             g = g / ages[part_id].to(g.dtype)
         pr = row[:P]
-        pr.add_(g + weight_decay * pr, alpha=-lr)
+        if momentum is not None:
+            mu, damp, nesterov, buf, first = momentum
+            d = g + weight_decay * pr
+            b = buf[:P]
+            if first and steps == 0:
+                b.copy_(d)
+            else:
+                b.mul_(mu).add_(d, alpha=1 - damp)
+            pr.add_(d.add(b, alpha=mu) if nesterov else b, alpha=-lr)
+        else:
+            pr.add_(g + weight_decay * pr, alpha=-lr)
         steps += 1
     return steps
 

@@ -95,7 +95,9 @@ def test_recsys_and_loaders_offline():
     assert tr.shape[1] == 2 and len(tr) + len(te) == 30 and not disp.has_test()
     X, y = load_classification_dataset("iris")
     assert X.shape == (150, 4) and abs(float(X.mean())) < 1e-5
-    Xs, ys = load_classification_dataset("spambase")              # no network -> synthetic shape
+    with pytest.raises(Exception):                                 # no network: the default is to fail loudly, like the reference
+        load_classification_dataset("spambase")
+    Xs, ys = load_classification_dataset("spambase", synthetic_fallback=True)   # explicit opt-in -> synthetic data of that shape
     assert Xs.shape == (4601, 57) and set(ys.tolist()) == {0, 1}
     (xtr, ytr), (xte, yte) = synthetic.images_like("cifar10", n_train=64, n_test=16)
     assert xtr.shape == (64, 3, 32, 32) and float(xtr.min()) >= 0 and float(xtr.max()) <= 1

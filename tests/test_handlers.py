@@ -311,3 +311,27 @@ def test_snapshot_dedupe_and_release():
     h._update((X, y))
     assert h.caching(0) != k1
     CACHE.clear()
+
+
+def test_momentum_oracle_equals_torch_optim_sgd():
+    """The explicit momentum update of the fused-path oracle (ops.torch_ref.mlp1_train) is torch.optim.SGD's."""
+    import torch
+    from gossipy_b200.ops import torch_ref as ref
+    from gossipy_b200.model.nn import TorchMLP
+    torch.manual_seed(3)
+    dims = (20, 7, 3)
+    net = TorchMLP(20, 3, (7,)).double()
+    X = torch.randn(48, 20, dtype=torch.float64); y = torch.randint(0, 3, (48,))
+    for kw in (dict(momentum=.9), dict(momentum=.9, nesterov=True), dict(momentum=.5, dampening=.2, weight_decay=.01)):
+        m = __import__("copy").deepcopy(net)
+        row = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).clone()
+        buf = torch.zeros_like(row)
+        opt = torch.optim.SGD(m.parameters(), lr=.1, **kw)
+        idx_all = list(ref._batches(48, 16, 2, 99))
+        for idx in idx_all:
+            loss = torch.nn.functional.cross_entropy(m(X[idx]), y[idx])
+            opt.zero_grad(); loss.backward(); opt.step()
+        ref.mlp1_train(row, X, y, dims, 16, 2, .1, kw.get("weight_decay", 0.), 99, None,
+                       (kw["momentum"], kw.get("dampening", 0.), kw.get("nesterov", False), buf, True))
+        want = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+        torch.testing.assert_close(row, want, rtol=1e-10, atol=1e-12)

@@ -408,6 +408,31 @@ def test_flagship_update_235_steps_is_fp32_accurate(lr):
     assert e_t > 50 * e_k
 
 
+@pytest.mark.parametrize("kw", [dict(mu=.9), dict(mu=.9, nesterov=True), dict(mu=.5, damp=.1, wd=.01), dict(mu=.9, n=7500, lr=.02)])
+def test_fused_momentum_sgd_matches_torch_semantics(kw):
+    """torch.optim.SGD(momentum, dampening, nesterov, weight_decay) inside the tcgen05 kernel (momentum buffer of W1 in
+    a TMEM tile), two consecutive updates (buffer state carried through the handler's momentum row) vs the fp64 oracle."""
+    ops, ref = _ops()
+    dims = (784, 100, 10)
+    n, lr = kw.get("n", 320), kw.get("lr", .05)
+    mu, damp, nest, wd = kw["mu"], kw.get("damp", 0.), kw.get("nesterov", False), kw.get("wd", 0.)
+    X, y, row = _mlp_problem(n, *dims)
+    r64, r32, got = row.double().clone(), row.clone(), row.clone()
+    b64, b32, bk = torch.zeros_like(r64), torch.zeros_like(r32), torch.zeros_like(got)
+    for upd in range(2):
+        first = upd == 0
+        ref.mlp1_train(r64, X.double(), y, dims, 32, 1, lr, wd, 77 + upd, None, (mu, damp, nest, b64, first))
+        ref.mlp1_train(r32, X, y, dims, 32, 1, lr, wd, 77 + upd, None, (mu, damp, nest, b32, first))
+        ops.mlp1_train(got, X, y, dims, 32, 1, lr, wd, 77 + upd, momentum=(mu, damp, nest, bk, first))
+    P = 79510
+    nrm = float(r64[:P].norm())
+    e_k = float((got[:P].double() - r64[:P]).norm()) / nrm
+    e_32 = float((r32[:P].double() - r64[:P]).norm()) / nrm
+    assert e_k < 4 * e_32 + 1e-7, (e_k, e_32)
+    torch.testing.assert_close(got[:P], r32[:P], rtol=2e-4, atol=5e-6)
+    torch.testing.assert_close(bk[:P], b32[:P], rtol=2e-3, atol=1e-5)          # the momentum buffers agree as well
+
+
 def test_training_kernels_are_deterministic():
     ops, _ = _ops()
     dims = (784, 100, 10)

@@ -132,6 +132,26 @@ def test_native_executor_partitioned_models(kw):
     g.CACHE.clear()
 
 
+def test_executor_race_debug_mode(monkeypatch):
+    """GOSSIPY_EXEC_DEBUG=1: slot life-cycle assertions (one writer, one reader per life; no slot both free and on the
+    wire; no message id twice) hold on a faulty run and fire on a forged event list."""
+    import gossipy_b200 as g
+    from gossipy_b200.ops.native import _try_import
+    monkeypatch.setenv("GOSSIPY_EXEC_DEBUG", "1")
+    sim, rep = _sim(True, "logreg", "PUSH_PULL", True, n=7, rounds=5)
+    assert sim._stream_exec.ex.debug
+    C = _try_import()
+    ex = C.StreamExecutor(2, 1, 4, 0, 2, 2, 1, .1, 0., 5, False, 2, -1)
+    for i in range(2):
+        ex.set_node(i, 0, 0, 0, 6, 0, 0, 0)
+    ex.set_callbacks(lambda *a: None, lambda *a: None, lambda *a: None)
+    ex.set_slots(0, 4, 8, 8)
+    ev = np.array([[C.EV_SEND, 0, 0, 1, 100, 1], [C.EV_SEND, 0, 0, 1, 100, 1]], dtype=np.int32)      # the same message id twice
+    with pytest.raises(Exception, match="executor debug"):
+        ex.run(ev, 0)
+    g.CACHE.clear()
+
+
 def test_slot_pool_grows_and_resume_is_exact(tmp_path):
     import gossipy_b200 as g
     from gossipy_b200.simul import GossipSimulator
