@@ -56,6 +56,9 @@ def parse():
                     help="control plane of the round loop: C++ scheduler or the Python loop")
     ap.add_argument("--executor", default="native", choices=["native", "python"],
                     help="native engine only: C++ executor (csrc/exec) or the per-event Python executor")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="several GPUs: p2p = fused kernels read peer memory over NVLink (default); nccl = the same engine "
+                         "with ncclSend/ncclRecv of every model into a staging row (the NCCL-only baseline)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tf32", action="store_true", help="skip the secondary plain-tf32 measurement")
     ap.add_argument("--curve", action="store_true", help="(kept for compatibility: the curve is always printed)")
@@ -174,7 +177,7 @@ def barrier(world: int):
 # --------------------------------------------------------------------------------------------
 # this framework
 # --------------------------------------------------------------------------------------------
-def build_native(world: int, rank: int, train_impl: str, engine: str = "native", executor: str = "python"):
+def build_native(world: int, rank: int, train_impl: str, engine: str = "native", executor: str = "python", transport: str = "p2p"):
     import torch
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork
@@ -190,7 +193,7 @@ def build_native(world: int, rank: int, train_impl: str, engine: str = "native",
     g.GlobalSettings().set_device(dev)
     if world > 1:
         from gossipy_b200.parallel import runtime as prt
-        prt.init(rank, world)
+        prt.init(rank, world, transport=transport)
     g.set_seed(98765)
     Xtr, ytr, Xte, yte = make_data()
     dh = ClassificationDataHandler(Xtr, ytr, Xte, yte)
@@ -260,7 +263,7 @@ def run_native(args, rank, world):
     K = args.steps if args.steps is not None else 100
     W = args.warmup if args.warmup is not None else 3
     W = max(W, 3)
-    sim, rep = build_native(world, rank, args.train_impl, args.engine, args.executor)
+    sim, rep = build_native(world, rank, args.train_impl, args.engine, args.executor, args.transport)
     time_rounds(sim, W, world, resume=False)
     launches0 = ops.launch_count
     with ClockSampler(torch.cuda.current_device() if torch.cuda.is_available() else 0) as clk:
@@ -302,7 +305,7 @@ def run_native(args, rank, world):
                "details": {"l2_flush": "192 MB buffer rewritten every round inside the timed region",
                            "placement": "block (node i on rank i*N//8), peer rows pulled over NVLink by the fused merge+train kernel",
                            "train_kernel": args.train_impl or "auto (tc8: 3xTF32 tcgen05, 8-CTA cluster)",
-                           "engine": args.engine,
+                           "engine": args.engine, "transport": args.transport if world > 1 else "none",
                            "executor": ("c++ (csrc/exec)" if "_stream_exec" in sim.__dict__ else "python (per event)")},
                "clocks": clk.summary(), "gpu_launches": launches,
                "test_acc_by_round_tail": acc[n_main - 5:n_main], "test_acc_by_round": acc[:n_main], "e2e": e2e,

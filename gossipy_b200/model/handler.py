@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import copy
 from abc import ABC, abstractmethod
-from typing import Any, Callable, Dict, Iterable, Optional, Sequence, Tuple, Union
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -390,7 +390,7 @@ class RowHandler(ModelHandler):
             self._row = _arena.arena_for(dev, self._row_numel, self._rank()).alloc()
             self._claim_row()
             self._on_new_row(None)
-        elif self._row.tensor.device.type != dev.type:
+        elif self._row.tensor is not None and self._row.tensor.device.type != dev.type:      # (ghost rows of other ranks carry no tensor)
             old = self._row
             self._row = _arena.arena_for(dev, self._row_numel, self._rank()).alloc()
             self._claim_row()
@@ -500,6 +500,9 @@ class RowHandler(ModelHandler):
         hs = [others] if single else list(others)
         rows = [o._ensure_row() for o in hs]
         my_rank = self._rank()
+        if _prt.active() and _prt.transport() == "nccl":
+            self._pull_nccl(rows, fn, single)
+            return
         syncs = [_arena.read_sync(r, my_rank) for r in rows]
         if not self._mine():
             return
@@ -513,6 +516,53 @@ class RowHandler(ModelHandler):
             fn(srcs[0] if single else srcs, syncs[0] if single else syncs)
             for r in local:
                 _arena.after_read(r, cur)
+
+    def _pull_nccl(self, rows: List[Any], fn: Callable, single: bool) -> None:
+        """``transport="nccl"`` (the NCCL-only baseline of the same engine): a row that lives on
+        another rank is SENT by its owner (``ncclSend``, ordered after the row's last writer) and RECEIVED by
+        the reader into a staging tensor, on which the same merge / training kernel then runs -- no peer
+        memory, no flags.  Every rank replays the same event sequence, so sends and receives pair up."""
+        import torch.distributed as dist
+        me, dst = _prt.rank(), self._rank()
+        mine = self._mine()
+        cuda = self.device.type == "cuda"
+        cur = _arena.current(self.device) if cuda else None
+        srcs: List[Any] = []
+        staged = False
+        for r in rows:
+            if r.rank == dst:
+                srcs.append(r.tensor)
+                continue
+            if me == r.rank:                    # my row: ship it (other ranks that own neither end do nothing)
+                _arena.before_read(r, cur)
+                dist.send(r.tensor, dst=dst)
+                _arena.after_read(r, cur)
+            if mine:
+                stage = torch.empty(r.tensor.shape if r.tensor is not None else (self._row_numel,), dtype=torch.float32,
+                                    device=self.device)
+                dist.recv(stage, src=r.rank)
+                srcs.append(stage)
+                staged = True
+        if not mine:
+            return
+        s = self._stream()
+        if cuda and staged and s is not None:   # the node's stream consumes what arrived on the communication stream
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            s.wait_event(ev)
+        with _arena.on_stream(s):
+            c = s if s is not None else cur
+            local = [r for r in rows if r.rank == dst]
+            for r in local:
+                _arena.before_read(r, c)
+            none = [None] * len(rows)
+            fn(srcs[0] if single else srcs, None if single else none)
+            for r in local:
+                _arena.after_read(r, c)
+            if cuda and staged and s is not None:
+                for t in srcs:
+                    if t is not None:
+                        t.record_stream(s)
 
     def _adopt(self, other: "RowHandler") -> None:
         self._pull(other, lambda src, sync: ops.merge_pair(self.row, src, 0.0, 1.0, sync=sync))

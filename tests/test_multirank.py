@@ -24,8 +24,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(world, device, rounds=3, kinds=KINDS):
+def _run(world, device, rounds=3, kinds=KINDS, transport=None):
     env = dict(os.environ, OMP_NUM_THREADS="1")
+    if transport:
+        env["GOSSIPY_B200_TRANSPORT"] = transport
     if world == 1:
         cmd = [sys.executable, WORKER, kinds, device, str(rounds)]
     else:
@@ -62,6 +64,15 @@ def test_two_ranks_cpu_equal_single_process():
     _compare(single, multi, rel=1e-5)
 
 
+def test_nccl_transport_two_and_three_ranks_cpu_equal_single_process():
+    """``transport="nccl"`` (send / recv of the row + the same kernels on a staging copy: the NCCL-only baseline of the
+    engine, here over gloo) gives the results of the shared-arena transport and of a single process."""
+    kinds = "mlp_pushpull,limited_pull,partitioned"
+    single = _run(1, "cpu", kinds=kinds)
+    for world in (2, 3):
+        _compare(single, _run(world, "cpu", kinds=kinds, transport="nccl"), rel=1e-5)
+
+
 def test_pens_two_and_three_ranks_cpu_equal_single_process():
     """PENS: the top-m choice is made on the owner from device results and broadcast; both steps run."""
     single = _run(1, "cpu", rounds=9, kinds="pens")
@@ -92,6 +103,14 @@ def test_two_ranks_cuda_equal_single_gpu():
     single = _run(1, "cuda:0")
     multi = _run(2, "cuda")
     _compare(single, multi, rel=2e-3)
+
+
+@pytest.mark.gpu
+def test_nccl_transport_two_ranks_cuda_equal_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    kinds = "mlp_pushpull,limited_pull,partitioned"
+    _compare(_run(1, "cuda:0", kinds=kinds), _run(2, "cuda", kinds=kinds, transport="nccl"), rel=2e-3)
 
 
 @pytest.mark.gpu
