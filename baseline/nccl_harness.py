@@ -33,7 +33,7 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import BATCH, D_H, D_IN, D_OUT, LR, METRIC, N_NODES, common_config, make_data  # noqa: E402
+from bench import BATCH, D_H, D_IN, D_OUT, LR, METRIC, N_NODES, common_config, make_data, make_split  # noqa: E402
 
 
 class Node:
@@ -94,7 +94,7 @@ def main():
         dist.init_process_group("nccl")
     from gossipy_b200.data import AssignmentHandler
     Xtr, ytr, Xte, yte = make_data()
-    parts = AssignmentHandler(42).label_pathological_skew(ytr, N_NODES, 2)
+    parts = make_split(ytr)
     owner = [i * world // N_NODES for i in range(N_NODES)]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     nodes = {i: Node(i, Xtr[parts[i]], ytr[parts[i]], gen, dev) for i in range(N_NODES) if owner[i] == rank}

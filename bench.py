@@ -77,6 +77,21 @@ def make_data(seed: int = 0):
     return X[:N_TRAIN], y[:N_TRAIN], X[N_TRAIN:], y[N_TRAIN:]
 
 
+def make_split(y, n_nodes: int = N_NODES, shards_per_client: int = 2, seed: int = 42):
+    """McMahan's pathological non-IID split, computed HERE (NumPy only) so that both arms train on identical shards:
+    samples sorted by label, cut into n_nodes * shards_per_client contiguous shards, shards dealt to the nodes at
+    random.  (Each framework's own AssignmentHandler draws from a different random stream: with only 16 shards of 10
+    classes the particular deal moves the accuracy curve by several points, which is not what a comparison of the two
+    implementations should measure.)"""
+    import numpy as np
+    yy = np.asarray(y)
+    order = np.argsort(yy, kind="stable")
+    shards = np.array_split(order, n_nodes * shards_per_client)
+    deal = np.random.RandomState(seed).permutation(len(shards))
+    return [np.sort(np.concatenate([shards[k] for k in deal[i * shards_per_client:(i + 1) * shards_per_client]]))
+            for i in range(n_nodes)]
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -198,7 +213,7 @@ def build_native(world: int, rank: int, train_impl: str, engine: str = "native",
     Xtr, ytr, Xte, yte = make_data()
     dh = ClassificationDataHandler(Xtr, ytr, Xte, yte)
     disp = DataDispatcher(dh, n=N_NODES, eval_on_user=False, auto_assign=False)
-    disp.set_assignments(AssignmentHandler(42).label_pathological_skew(ytr, N_NODES, 2), None)
+    disp.set_assignments(make_split(ytr), None)
     ops.set_train_impl(train_impl or "")
     proto = TorchModelHandler(net=TorchMLP(D_IN, D_OUT, (D_H,)), optimizer=torch.optim.SGD,
                               optimizer_params={"lr": LR}, criterion=torch.nn.CrossEntropyLoss(),
@@ -373,7 +388,7 @@ def run_reference(args, rank, world):
         Xtr, ytr, Xte, yte = make_data()
         dh = ClassificationDataHandler(Xtr, ytr, Xte, yte)
         disp = DataDispatcher(dh, n=N_NODES, eval_on_user=False, auto_assign=False)
-        disp.set_assignments(AssignmentHandler(42).label_pathological_skew(ytr, N_NODES, 2), None)
+        disp.set_assignments(make_split(ytr), None)
         proto = TorchModelHandler(net=TorchMLP(D_IN, D_OUT, (D_H,)), optimizer=torch.optim.SGD,
                                   optimizer_params={"lr": LR}, criterion=torch.nn.CrossEntropyLoss(),
                                   local_epochs=1, batch_size=BATCH,

@@ -49,7 +49,7 @@ def run_ours(seed: int, rounds: int, small: bool, train_impl: str = ""):
     g.set_seed(1000 + seed)
     Xtr, ytr, Xte, yte = data(small, 0)
     disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=8, eval_on_user=False, auto_assign=False)
-    disp.set_assignments(AssignmentHandler(42).label_pathological_skew(ytr, 8, 2), None)
+    disp.set_assignments(bench.make_split(ytr), None)      # identical shards in both arms
     proto = TorchModelHandler(net=TorchMLP(784, 10, (100,)), optimizer=torch.optim.SGD, optimizer_params={"lr": .1},
                               criterion=torch.nn.CrossEntropyLoss(), local_epochs=1, batch_size=32,
                               create_model_mode=CreateModelMode.MERGE_UPDATE)
@@ -101,7 +101,7 @@ def run_reference(seed: int, rounds: int, small: bool):
     set_seed(1000 + seed)
     Xtr, ytr, Xte, yte = data(small, 0)
     disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=8, eval_on_user=False, auto_assign=False)
-    disp.set_assignments(AssignmentHandler(42).label_pathological_skew(ytr, 8, 2), None)
+    disp.set_assignments(bench.make_split(ytr), None)      # identical shards in both arms
     proto = TorchModelHandler(net=TorchMLP(784, 10, (100,)), optimizer=torch.optim.SGD, optimizer_params={"lr": .1},
                               criterion=torch.nn.CrossEntropyLoss(), local_epochs=1, batch_size=32,
                               create_model_mode=CreateModelMode.MERGE_UPDATE)

@@ -13,6 +13,16 @@ try:
 except Exception as e:
     print('bad json', e)
 "; grep -i "error\|Traceback" gpurun_out/bench_n${N}.err | head -3
+for tr in p2p nccl; do
+  run 300 29871 bench.py --gpus $N --steps 30 --warmup 3 --executor python --transport $tr --no-e2e --no-tf32 > gpurun_out/bench_n${N}_py_$tr.json 2> gpurun_out/bench_n${N}_py_$tr.err; echo "bench N=$N python executor, transport $tr rc=$?"
+  tail -1 gpurun_out/bench_n${N}_py_$tr.json | python -c "
+import sys, json
+try:
+    d = json.loads(sys.stdin.read()); print({k: d[k] for k in ('value', 'ms_per_step')}, d['details']['transport'], d['test_acc_by_round_tail'][-2:])
+except Exception as e:
+    print('bad json', e)
+"
+done
 : > gpurun_out/baseline_configs_n$N.jsonl
 p=29890
 for c in 3 4 6; do
