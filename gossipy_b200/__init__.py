@@ -103,6 +103,9 @@ class GlobalSettings(metaclass=_SingletonMeta):
         self.world_size = 1
         self.reference_compat = False  # mimic selected reference quirks (see docs/QUIRKS.md)
         self._allow_tf32 = False
+        # replay the forward + backward of generic (autograd) models from a CUDA graph per handler and batch shape
+        # instead of launching every layer's kernels from Python (model/handler.py: _graph_fwd_bwd)
+        self.cuda_graphs = os.environ.get("GOSSIPY_CUDA_GRAPHS", "1") != "0"
 
     # -- numerics -----------------------------------------------------------------------
     @property

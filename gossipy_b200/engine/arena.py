@@ -118,7 +118,6 @@ class SymmetricArenas:
     """
 
     def __init__(self, device: torch.device, row_numel: int) -> None:
-        import torch.distributed as dist
         from ..parallel import runtime as prt
         self.device = torch.device(device)
         self.row_numel = int(row_numel)
@@ -127,83 +126,92 @@ class SymmetricArenas:
         cap = prt.arena_capacity()
         if cap is None:
             cap = int(max(64, min(8192, (256 << 20) // row_bytes)))
-        self.capacity = cap
-        self.flags_off = self.capacity * row_bytes
+        self.capacity = cap               # rows per segment
         self.cuda = self.device.type == "cuda"
         self.flag_words = 2 if self.cuda else 1 + self.world
-        total = self.flags_off + self.capacity * 4 * self.flag_words
+        self.n_segments = 0
+        self._shm: List = []
         self.mirrors: List[RowArena] = []
+        for r in range(self.world):
+            mirror = RowArena(self.device, row_numel, rank=r, ghost=True)
+            mirror._grow = self.grow  # type: ignore[assignment]
+            self.mirrors.append(mirror)
+        self.grow()
+
+    def grow(self) -> None:
+        """Add one segment of ``capacity`` rows (+ flags) on EVERY rank.  Collective -- and safe to call from the
+        allocation path: all ranks replay the same alloc / free sequence on every mirror, so they all run out of rows
+        of a mirror at the same point of the replicated bookkeeping.  Rows keep their addresses (earlier segments are
+        never moved), so captured pointers, in-flight reads and the executor's slot tables stay valid."""
+        import torch.distributed as dist
+        from ..parallel import runtime as prt
+        row_bytes = self.row_numel * 4
+        flags_off = self.capacity * row_bytes
+        total = flags_off + self.capacity * 4 * self.flag_words
+        seg = self.n_segments
+        first = seg * self.capacity
         if self.cuda:
             from ..ops.native import native
             nat = native()
             torch.cuda.set_device(self.device)
-            self.base = nat.ipc_alloc(total)
+            base = nat.ipc_alloc(total)
             handles: List = [None] * self.world
-            dist.all_gather_object(handles, nat.ipc_get_handle(self.base))
-            self.bases = [self.base if r == prt.rank() else nat.ipc_open_handle(handles[r])
-                          for r in range(self.world)]
+            dist.all_gather_object(handles, nat.ipc_get_handle(base))
+            bases = [base if r == prt.rank() else nat.ipc_open_handle(handles[r]) for r in range(self.world)]
             dist.barrier()
             dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-            for r in range(self.world):
-                mirror = RowArena(self.device, row_numel, rank=r, ghost=True)
-                mirror._n_rows = self.capacity
+            for r, mirror in enumerate(self.mirrors):
                 for i in range(self.capacity):
-                    t = nat.tensor_from_ptr(self.bases[r] + i * row_bytes, [self.row_numel], dev_index, False)
-                    row = Row(mirror, i, t)
-                    row.flag_ready = self.bases[r] + self.flags_off + 8 * i
-                    row.flag_done = self.bases[r] + self.flags_off + 8 * i + 4
+                    t = nat.tensor_from_ptr(bases[r] + i * row_bytes, [self.row_numel], dev_index, False)
+                    row = Row(mirror, first + i, t)
+                    row.flag_ready = bases[r] + flags_off + 8 * i
+                    row.flag_done = bases[r] + flags_off + 8 * i + 4
                     mirror._free.append(row)
-                mirror._grow = _no_growth  # type: ignore[assignment]
-                self.mirrors.append(mirror)
+                mirror._n_rows += self.capacity
         else:
             import numpy as np
             from multiprocessing import shared_memory
             tag = prt.session_tag()
-            names = ["gb200_%s_%d_%d" % (tag, self.row_numel, r) for r in range(self.world)]
+            names = ["gb200_%s_%d_%d_%d" % (tag, self.row_numel, seg, r) for r in range(self.world)]
             mine = shared_memory.SharedMemory(name=names[prt.rank()], create=True, size=total)
             np.frombuffer(mine.buf, dtype=np.uint8)[:] = 0
             dist.barrier()
-            self._shm = [mine if r == prt.rank() else shared_memory.SharedMemory(name=names[r])
-                         for r in range(self.world)]
+            shms = [mine if r == prt.rank() else shared_memory.SharedMemory(name=names[r])
+                    for r in range(self.world)]
             dist.barrier()
-            _SHM_KEEPALIVE.extend(self._shm)
-            for r in range(self.world):
-                buf = self._shm[r].buf
+            self._shm.append(shms)
+            _SHM_KEEPALIVE.extend(shms)
+            for r, mirror in enumerate(self.mirrors):
+                buf = shms[r].buf
                 data = torch.frombuffer(buf, dtype=torch.float32, count=self.capacity * self.row_numel)
-                flags = np.frombuffer(buf, dtype=np.int32, offset=self.flags_off,
+                flags = np.frombuffer(buf, dtype=np.int32, offset=flags_off,
                                       count=self.capacity * self.flag_words)
-                mirror = RowArena(self.device, row_numel, rank=r, ghost=True)
-                mirror._n_rows = self.capacity
                 for i in range(self.capacity):
-                    row = Row(mirror, i, data[i * self.row_numel:(i + 1) * self.row_numel])
+                    row = Row(mirror, first + i, data[i * self.row_numel:(i + 1) * self.row_numel])
                     row.flag_ready = (flags, i * self.flag_words)
                     row.flag_done = (flags, i * self.flag_words + 1)     # + reader rank
                     mirror._free.append(row)
-                mirror._grow = _no_growth  # type: ignore[assignment]
-                self.mirrors.append(mirror)
+                mirror._n_rows += self.capacity
+        self.n_segments += 1
 
     def close(self) -> None:
         from ..parallel import runtime as prt
         if self.cuda:
             return
-        for r, shm in enumerate(self._shm):
-            if r == prt.rank():
+        for shms in self._shm:
+            for r, shm in enumerate(shms):
+                if r == prt.rank():
+                    try:
+                        shm.unlink()
+                    except Exception:
+                        pass
                 try:
-                    shm.unlink()
-                except Exception:
+                    shm.close()
+                except Exception:      # tensors created with torch.frombuffer may still reference the mapping
                     pass
-            try:
-                shm.close()
-            except Exception:      # tensors created with torch.frombuffer may still reference the mapping
-                pass
 
 
 _SHM_KEEPALIVE: List = []
-
-
-def _no_growth() -> None:
-    raise RuntimeError("symmetric arena exhausted: too many models in flight for the p2p transport "
-                       "(raise it with parallel.runtime.init(arena_capacity=...))")
 
 
 _ARENAS: Dict[tuple, RowArena] = {}

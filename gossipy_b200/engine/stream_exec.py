@@ -128,15 +128,8 @@ class StreamExec:
             # a rank's slots are rows of ITS symmetric arena (mapped everywhere); every rank performs the same
             # allocations on every mirror, so (rank, slot) means the same row in all processes
             per_rank = max(self.owner.count(r) for r in range(prt.world()))
-            k = max(8, 6 * per_rank)
-            self.pool_rows = [[_arena.arena_for(self.device, self.row_numel, r).alloc() for _ in range(k)]
-                              for r in range(prt.world())]
-            for r, rows in enumerate(self.pool_rows):
-                for row in rows:
-                    ready = row.flag_ready if self.cuda else 0
-                    done = row.flag_done if self.cuda else 0
-                    self.ex.add_slot(r, row.tensor.data_ptr(), int(ready), int(done), self.row_numel, int(row.gen),
-                                     int(row.remote_reads), int(getattr(row, "_acked", 0)))
+            self.pool_rows = [[] for _ in range(prt.world())]
+            self._add_pool_rows(max(8, 6 * per_rank))
             self.slots = None
         else:
             self.owner = [0] * len(ids)
@@ -145,6 +138,18 @@ class StreamExec:
         if not self.cuda:
             self.ex.set_callbacks(self._cb_snapshot, self._cb_train, self._cb_adopt)
         self.bind_nodes()
+
+    def _add_pool_rows(self, k: int) -> None:
+        """``k`` more snapshot slots per rank (replicated: every rank allocates the same rows on every mirror; the
+        symmetric arenas add a segment collectively when they run out)."""
+        for r, rows in enumerate(self.pool_rows):
+            for _ in range(k):
+                row = _arena.arena_for(self.device, self.row_numel, r).alloc()
+                rows.append(row)
+                ready = row.flag_ready if self.cuda else 0
+                done = row.flag_done if self.cuda else 0
+                self.ex.add_slot(r, row.tensor.data_ptr(), int(ready), int(done), self.row_numel, int(row.gen),
+                                 int(row.remote_reads), int(getattr(row, "_acked", 0)))
 
     # -- state shared with the handlers ---------------------------------------------------------------
     def _publish_slots(self) -> None:
@@ -277,9 +282,9 @@ class StreamExec:
         return evals
 
     def _grow(self) -> None:
-        if self.multi:
-            raise RuntimeError("out of snapshot slots: the symmetric arenas do not grow "
-                               "(raise parallel.runtime.init(arena_capacity=...))")
+        if self.multi:          # replicated books: every rank runs out of the same pool at the same event
+            self._add_pool_rows(len(self.pool_rows[0]))
+            return
         if self.cuda:
             torch.cuda.synchronize(self.device)
         bigger = torch.zeros(2 * int(self.slots.shape[0]), self.row_numel, dtype=torch.float32, device=self.device)

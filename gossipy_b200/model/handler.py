@@ -229,7 +229,7 @@ def _dispose(h: Any) -> None:
 
 
 def _state_eq(a: Dict[str, Any], b: Dict[str, Any]) -> bool:
-    skip = {"_row", "_module", "_proto", "_grad_row", "_opt_rows", "_torch_opt", "owner", "_size_cache",
+    skip = {"_row", "_module", "_proto", "_grad_row", "_opt_rows", "_torch_opt", "owner", "_size_cache", "_graphs",
             "_version", "_is_snapshot", "_bound_to", "_grad_bound", "_update_counter",
             "_part_id_dev", "_seg_dev", "layout"}
     for k in a.keys() | b.keys():
@@ -436,6 +436,7 @@ class RowHandler(ModelHandler):
         # the refcount stamped by CacheItem belongs to the in-flight snapshot, never to its clones
         # (a clone that inherited it would refuse to release its row: unbounded arena growth)
         new.__dict__.pop("_cache_refs", None)
+        new.__dict__.pop("_graphs", None)       # captured steps are bound to MY row's addresses
         new._row = None
         new.n_updates = copy.copy(self.n_updates)
         return new
@@ -588,6 +589,7 @@ class RowHandler(ModelHandler):
         st["_row"] = None if self._row is None else self._row.tensor.detach().cpu().clone()
         st.pop("_module", None)
         st.pop("_torch_opt", None)
+        st.pop("_graphs", None)
         st["_grad_row"] = None
         opt = st.get("_opt_rows")
         if opt:
@@ -620,6 +622,38 @@ def _is_plain_ce(criterion: Any) -> bool:
                 and getattr(criterion, "label_smoothing", 0.0) == 0.0
                 and criterion.ignore_index == -100)
     return False
+
+
+class _GraphStep:
+    """One captured forward + backward (``TorchModelHandler._graph_fwd_bwd``): static inputs + the graph."""
+
+    __slots__ = ("graph", "x", "y", "seen", "failed")
+
+    def __init__(self) -> None:
+        self.graph = None
+        self.x = self.y = None
+        self.seen = 0
+        self.failed = False
+
+    def fill(self, x: torch.Tensor, y: torch.Tensor, idx: Optional[torch.Tensor]) -> None:
+        if idx is not None:
+            torch.index_select(x, 0, idx, out=self.x)
+            torch.index_select(y, 0, idx, out=self.y)
+        else:
+            self.x.copy_(x)
+            self.y.copy_(y)
+
+
+_GRAPH_POOLS: Dict[Tuple[int, int], Any] = {}
+
+
+def _graph_pool(device: torch.device):
+    """The graph memory pool of the current stream of ``device`` (shared by the handlers that run on that stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    pool = _GRAPH_POOLS.get(key)
+    if pool is None:
+        pool = _GRAPH_POOLS[key] = torch.cuda.graph_pool_handle()
+    return pool
 
 
 class TorchModelHandler(RowHandler):
@@ -920,25 +954,84 @@ class TorchModelHandler(RowHandler):
             for e in range(self.local_epochs):
                 perm = torch.from_numpy(ops.torch_ref.perm_indices(n, _rng.mix64(gen_key ^ e))).to(x.device)
                 for i in range(0, n, bs):
-                    idx = perm[i:i + bs]
-                    self._local_step(mod, x[idx], y[idx])
+                    self._local_step(mod, x, y, perm[i:i + bs])
                     steps += 1
         else:
             perm = torch.from_numpy(ops.torch_ref.perm_indices(n, _rng.mix64(gen_key))).to(x.device)
-            idx = perm[:bs]
-            self._local_step(mod, x[idx], y[idx])
+            self._local_step(mod, x, y, perm[:bs])
             steps = 1
         return steps
 
-    def _local_step(self, mod: TorchModel, x: torch.Tensor, y: torch.Tensor) -> None:
-        """forward / loss / backward / optimizer step (ref ``handler.py:250-258``)."""
+    def _local_step(self, mod: TorchModel, x: torch.Tensor, y: torch.Tensor,
+                    idx: Optional[torch.Tensor] = None) -> None:
+        """forward / loss / backward / optimizer step (ref ``handler.py:250-258``) on the mini-batch ``x[idx], y[idx]``
+        (``idx = None``: all of ``x, y``).  On a GPU the forward + backward is replayed from a CUDA graph."""
         mod.train()
         g = self._ensure_grad()
-        g.zero_()
-        loss = self.criterion(mod(x), y)
-        loss.backward()
+        if not self._graph_fwd_bwd(mod, g, x, y, idx):
+            if idx is not None:
+                x, y = x[idx], y[idx]
+            g.zero_()
+            loss = self.criterion(mod(x), y)
+            loss.backward()
         self._pre_step()
         self._apply_optimizer(g)
+
+    #: eager steps of a (handler, batch shape) before its graph is captured: cuDNN / cuBLAS handles, workspaces and
+    #: autotuned algorithms must exist before a capture starts
+    _GRAPH_WARMUP = 2
+
+    def _graph_fwd_bwd(self, mod: TorchModel, g: torch.Tensor, x: torch.Tensor, y: torch.Tensor,
+                       idx: Optional[torch.Tensor]) -> bool:
+        """Zero the gradient row, forward, loss, backward of one mini-batch as ONE graph launch.
+
+        A generic model's step is a few hundred small kernels (ResNet-20: ~600) whose launches from Python, not
+        their execution, bound the update on a B200.  The parameters are views of the handler's arena row and the
+        gradients views of its gradient row, so every address in the step is fixed: after ``_GRAPH_WARMUP`` eager
+        steps the step is captured per (row, gradient row, module, batch shape) with the mini-batch gathered into
+        static input buffers (one ``index_select`` per tensor), and replayed afterwards.  The optimizer stays outside
+        (one fused launch, host-side step counters / hooks keep working).  Graphs of the handlers of one stream share
+        a memory pool -- replays on a stream are ordered and nothing allocated under capture outlives the step.
+        Returns ``False`` when the step has to run eagerly."""
+        if not (g.is_cuda and GlobalSettings().cuda_graphs) or torch.cuda.is_current_stream_capturing():
+            return False
+        nb = int(idx.numel()) if idx is not None else int(x.size(0))
+        key = (self.row.data_ptr(), g.data_ptr(), id(mod), nb, tuple(x.shape[1:]), x.dtype, tuple(y.shape[1:]),
+               y.dtype, x.device.index)
+        cache = self.__dict__.get("_graphs")
+        if cache is None:
+            cache = self.__dict__["_graphs"] = {}
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) >= 4:          # the row moved / the batch size changed: drop the stale captures
+                cache.clear()
+            ent = cache[key] = _GraphStep()
+        if ent.failed:
+            return False
+        if ent.graph is None:
+            ent.seen += 1
+            if ent.seen <= self._GRAPH_WARMUP:
+                return False
+            ent.x = torch.empty((nb,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+            ent.y = torch.empty((nb,) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)
+            ent.fill(x, y, idx)
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph, pool=_graph_pool(x.device), capture_error_mode="thread_local"):
+                    g.zero_()
+                    loss = self.criterion(mod(ent.x), ent.y)
+                    loss.backward()
+                    del loss
+            except Exception as err:            # an op that cannot be captured (host sync, CPU tensors, ...)
+                ent.failed = True
+                ent.x = ent.y = None
+                LOG.debug("CUDA-graph capture of %s failed, running eagerly: %s", type(mod).__name__, err)
+                return False
+            ent.graph = graph
+        else:
+            ent.fill(x, y, idx)
+        ent.graph.replay()
+        return True
 
     def _pre_step(self) -> None:
         """Hook between backward and the optimizer step (gradient adjustment)."""

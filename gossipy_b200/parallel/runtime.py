@@ -46,6 +46,8 @@ def init(rank: Optional[int] = None, world: Optional[int] = None,
     if not transport:
         transport = "p2p"
     _state["transport"] = transport if world > 1 else "none"
+    if arena_capacity is None and os.environ.get("GOSSIPY_B200_ARENA_ROWS"):
+        arena_capacity = int(os.environ["GOSSIPY_B200_ARENA_ROWS"])     # rows per segment of the symmetric arenas
     _state["arena_capacity"] = arena_capacity
     if world > 1:
         assert dist.is_initialized(), "initialise torch.distributed before parallel.runtime.init"

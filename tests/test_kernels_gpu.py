@@ -661,3 +661,61 @@ def test_bank_kernels_equal_per_event_kernels(protocol, mode, handler):
         for k in m1:
             assert m1[k] == pytest.approx(m2[k], abs=2e-2), k
     g.CACHE.clear()
+
+
+# ---------------------------------------------------------------------------------------------
+# generic (autograd) models: the forward + backward is replayed from a CUDA graph per handler and batch shape
+# ---------------------------------------------------------------------------------------------
+class _ConvBN(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.c1 = torch.nn.Conv2d(3, 8, 3, padding=1)
+        self.bn = torch.nn.BatchNorm2d(8)
+        self.c2 = torch.nn.Conv2d(8, 8, 3, padding=1)
+        self.fc = torch.nn.Linear(8 * 8 * 8, 10)
+
+    def forward(self, x):
+        x = torch.relu(self.bn(self.c1(x)))
+        x = torch.nn.functional.max_pool2d(torch.relu(self.c2(x)), 2)
+        return self.fc(x.flatten(1))
+
+
+@pytest.mark.parametrize("opt,params", [(torch.optim.SGD, {"lr": .05, "momentum": .9, "weight_decay": 1e-4}),
+                                        (torch.optim.Adam, {"lr": 1e-3}), (torch.optim.SGD, {"lr": .05})])
+def test_generic_step_replayed_from_cuda_graph_equals_eager(opt, params):
+    import gossipy_b200 as g
+    from gossipy_b200.model.handler import TorchModelHandler
+    from gossipy_b200.model.nn import TorchModel
+
+    class Net(_ConvBN, TorchModel):
+        def init_weights(self):
+            pass
+
+        def __str__(self):
+            return "ConvBN"
+
+    gen = torch.Generator().manual_seed(5)
+    X = torch.randn(200, 3, 16, 16, generator=gen)
+    y = torch.randint(0, 10, (200,), generator=gen)
+
+    def run(graphs):
+        g.GlobalSettings().cuda_graphs = graphs
+        g.set_seed(11)
+        torch.manual_seed(11)
+        h = TorchModelHandler(Net(), opt, dict(params), torch.nn.CrossEntropyLoss(), local_epochs=1, batch_size=32)
+        h.init()
+        for _ in range(3):                      # 7 steps each: 6 full batches + one of 8 samples
+            h._update((X, y))
+        ev = h.evaluate((X, y))
+        used = sum(1 for e in h.__dict__.get("_graphs", {}).values() if e.graph is not None)
+        nbt = int(h.model.bn.num_batches_tracked)
+        return h.row.clone(), ev, used, nbt
+    try:
+        r_eager, ev_eager, used_eager, nbt_eager = run(False)
+        r_graph, ev_graph, used_graph, nbt_graph = run(True)
+    finally:
+        g.GlobalSettings().cuda_graphs = True
+    assert used_eager == 0 and used_graph == 2          # the full batch and the trailing partial batch
+    assert nbt_eager == nbt_graph == 21
+    assert torch.allclose(r_graph, r_eager, rtol=1e-4, atol=1e-5), float((r_graph - r_eager).abs().max())
+    assert ev_graph["accuracy"] == pytest.approx(ev_eager["accuracy"], abs=.011)

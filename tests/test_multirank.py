@@ -24,10 +24,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(world, device, rounds=3, kinds=KINDS, transport=None):
+def _run(world, device, rounds=3, kinds=KINDS, transport=None, arena_rows=None):
     env = dict(os.environ, OMP_NUM_THREADS="1")
     if transport:
         env["GOSSIPY_B200_TRANSPORT"] = transport
+    if arena_rows:
+        env["GOSSIPY_B200_ARENA_ROWS"] = str(arena_rows)
     if world == 1:
         cmd = [sys.executable, WORKER, kinds, device, str(rounds)]
     else:
@@ -96,6 +98,14 @@ def test_cpp_executor_two_and_three_ranks_cpu_equal_single_process():
         _compare(single, multi, rel=1e-5)
 
 
+def test_symmetric_arenas_grow_when_they_run_out():
+    """Segments of 4 rows: the shared arenas (and the C++ executor's snapshot pools on them) must add segments
+    collectively, in the middle of a round, without changing the results."""
+    kinds = "mlp_pushpull,x_mlp_pushpull"
+    single = _run(1, "cpu", kinds=kinds)
+    _compare(single, _run(2, "cpu", kinds=kinds, arena_rows=4), rel=1e-5)
+
+
 @pytest.mark.gpu
 def test_two_ranks_cuda_equal_single_gpu():
     if torch.cuda.device_count() < 2:
@@ -130,3 +140,5 @@ def test_cpp_executor_two_ranks_cuda_equal_single_gpu():
     multi = _run(2, "cuda", rounds=4, kinds=XKINDS)
     assert all(v["cpp_executor"] for v in multi.values())
     _compare(single, multi, rel=2e-3)
+    # tiny arena segments: CUDA-IPC segments are added collectively mid-run
+    _compare(single, _run(2, "cuda", rounds=4, kinds=XKINDS, arena_rows=8), rel=2e-3)
