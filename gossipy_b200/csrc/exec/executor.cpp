@@ -65,10 +65,12 @@ struct Node {
     int n = 0; int64_t age = 0, counter = 0; cudaStream_t stream = nullptr;
     std::vector<int64_t> ages_v;            // partitioned models: one age per partition (age = their sum)
     int64_t model_msgs = 0;                 // model-carrying messages sent so far (keys the partition draw)
+    float* scratch = nullptr;               // UPDATE_MERGE: private trainable copy of a received model
 };
 
 struct Slot {
     int64_t age = 0;
+    int64_t counter = 0;                    // the sender's update counter at send time (UPDATE_MERGE keys the copy's update with it)
     std::vector<int64_t> ages_v; int pid = 0;
     int state = 0;                          // debug mode: 0 free, 1 written (on the wire), checked on every transition
     cudaEvent_t written = nullptr, read = nullptr; bool has_reader = false;      // same-rank ordering
@@ -101,7 +103,7 @@ public:
         if (n_nodes <= 0) throw std::invalid_argument("n_nodes must be positive");
         const char* dbg = std::getenv("GOSSIPY_EXEC_DEBUG");
         debug_ = dbg != nullptr && dbg[0] != '\0' && dbg[0] != '0';
-        if (mode != 1 && mode != 2 && mode != 4) throw std::invalid_argument("mode must be UPDATE, MERGE_UPDATE or PASS");
+        if (mode < 1 || mode > 4) throw std::invalid_argument("mode must be UPDATE, MERGE_UPDATE, UPDATE_MERGE or PASS");
     }
     ~StreamExecutor() {
         for (auto& pool : pools_)
@@ -123,6 +125,8 @@ public:
         nd.y = reinterpret_cast<const int64_t*>(y); nd.n = n; nd.age = age; nd.counter = counter;
         nd.stream = reinterpret_cast<cudaStream_t>(stream);
     }
+    void set_node_scratch(int i, uintptr_t scratch) { nodes_.at(i).scratch = reinterpret_cast<float*>(scratch); }
+    void set_update_merge_callback(py::function f) { cb_update_merge_ = std::move(f); }
     void set_node_data(int i, uintptr_t X, uintptr_t y, int n) {       // streamed inputs: the buffers alternate per round
         Node& nd = nodes_.at(i);
         nd.X = reinterpret_cast<const float*>(X); nd.y = reinterpret_cast<const int64_t*>(y); nd.n = n;
@@ -229,6 +233,7 @@ public:
             const Slot& sl = pools_[kv.second.first][kv.second.second];
             std::vector<int64_t> r{kv.first, kv.second.first, kv.second.second, sl.age};
             if (n_parts_ > 0) { r.push_back(sl.pid); r.insert(r.end(), sl.ages_v.begin(), sl.ages_v.end()); }
+            else if (mode_ == 3) r.push_back(sl.counter);
             v.push_back(r);
         }
         std::sort(v.begin(), v.end());
@@ -244,6 +249,7 @@ public:
             Slot& sl = pools_.at(rk).at(s);
             sl.age = r.at(3);
             if (n_parts_ > 0) { sl.pid = (int)r.at(4); sl.ages_v.assign(r.begin() + 5, r.begin() + 5 + n_parts_); }
+            else if (mode_ == 3) sl.counter = r.at(4);
             inflight_[(int32_t)r.at(0)] = {rk, s};
         }
     }
@@ -254,12 +260,13 @@ private:
         const int bs = B_ == 0 ? nd.n : std::min(B_, nd.n);
         return epochs_ > 0 ? epochs_ * ((nd.n + bs - 1) / bs) : 1;
     }
-    uint64_t key_of(int node, const Node& nd) const {     // model/handler.py::_next_key -> engine/rng.py::derive
+    uint64_t key_of(int node, int64_t counter, int64_t age) const {     // model/handler.py::_next_key -> engine/rng.py::derive
         uint64_t h = mix64(seed_);
-        const uint64_t parts[4] = {0x5EEDull, (uint64_t)node, (uint64_t)nd.counter, (uint64_t)nd.age};
+        const uint64_t parts[4] = {0x5EEDull, (uint64_t)node, (uint64_t)counter, (uint64_t)age};
         for (uint64_t p : parts) h = mix64(h ^ p);
         return h & ((1ull << 63) - 1);
     }
+    uint64_t key_of(int node, const Node& nd) const { return key_of(node, nd.counter, nd.age); }
 
     bool snapshot(int node, int32_t msg_id) {
         const int rk = world_ > 1 ? owner_[node] : 0;
@@ -280,6 +287,7 @@ private:
             sl.state = 1;
         }
         sl.age = nd.age;
+        sl.counter = nd.counter;
         if (n_parts_ > 0) {                               // node.py::PartitioningBasedNode._payload_extras (keyed form)
             sl.ages_v = nd.ages_v;
             uint64_t h = mix64(seed_);
@@ -391,6 +399,32 @@ private:
             const int st = steps_of(nd);
             for (int64_t& v : nd.ages_v) v += st;
             nd.age += (int64_t)st * n_parts_;
+        } else if (mode_ == 3) {
+            // UPDATE_MERGE (model/handler.py::__call__, reference handler.py:129-132): update the own model, update a
+            // private copy of the received one on the own data (keyed like the Python scratch copy: this node, the
+            // sender's counter + 1, the sender's age), then merge the two
+            const int st = steps_of(nd);
+            nd.counter += 1;
+            const uint64_t key_own = key_of(node, nd);
+            const uint64_t key_tmp = key_of(node, sl.counter + 1, sl.age);
+            const int64_t age_own = nd.age + st, age_tmp = sl.age + st;
+            float ws, wp;
+            merge_weights(age_own, age_tmp, ws, wp);
+            if (exec) {
+                if (cuda_) {
+                    if (nd.scratch == nullptr) throw std::runtime_error("UPDATE_MERGE needs a scratch row per node (set_node_scratch)");
+                    const PeerSync none{nullptr, 0, nullptr, nullptr};
+                    train(nd, nullptr, 1.f, 0.f, key_own, none);
+                    launch_merge_pair(nd.scratch, sl.data, 0.f, 1.f, 0, row_floats_, sync, nd.stream);
+                    Node tmp = nd; tmp.row = nd.scratch;
+                    train(tmp, nullptr, 1.f, 0.f, key_tmp, none);
+                    if (wp != 0.f) launch_merge_pair(nd.row, nd.scratch, ws, wp, 0, row_floats_, none, nd.stream);
+                } else {
+                    cb_update_merge_(node, rk, s, (int64_t)key_own, (int64_t)key_tmp, ws, wp, (int64_t)sl.gen);
+                }
+                launches_ += 4;
+            }
+            nd.age = std::max(age_own, age_tmp);
         } else if (mode_ == 4) {                           // PASS: adopt the received model, age unchanged
             if (exec) {
                 if (cuda_) launch_merge_pair(nd.row, sl.data, 0.f, 1.f, 0, row_floats_, sync, nd.stream);
@@ -441,7 +475,7 @@ private:
     std::vector<std::vector<Slot>> pools_;          // per owner rank
     std::vector<std::deque<int>> free_;             // FIFO: a slot is reused as late as possible (see snapshot())
     std::unordered_map<int32_t, std::pair<int, int>> inflight_;     // message id -> (rank, slot)
-    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_;
+    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_merge_;
     int n_parts_ = 0; const int64_t* part_id_ = nullptr;
     std::vector<uintptr_t> seg_ptrs_; std::vector<int> seg_counts_;
     int64_t launches_ = 0, resume_at_ = -1;
@@ -458,6 +492,8 @@ void bind_executor(py::module_& m) {
         .def("add_slot", &StreamExecutor::add_slot)
         .def("set_node", &StreamExecutor::set_node)
         .def("set_node_data", &StreamExecutor::set_node_data)
+        .def("set_node_scratch", &StreamExecutor::set_node_scratch)
+        .def("set_update_merge_callback", &StreamExecutor::set_update_merge_callback)
         .def("set_slots", &StreamExecutor::set_slots)
         .def("set_callbacks", &StreamExecutor::set_callbacks)
         .def("set_partition", &StreamExecutor::set_partition)

@@ -65,7 +65,8 @@ def eligible(sim: Any) -> Optional[str]:
                 return "partitioned models: mode %s" % h.mode.name
             if h.tm_partition.n_parts > 16:
                 return "more than 16 partitions"
-        elif h.mode not in (CreateModelMode.MERGE_UPDATE, CreateModelMode.UPDATE, CreateModelMode.PASS):
+        elif h.mode not in (CreateModelMode.MERGE_UPDATE, CreateModelMode.UPDATE, CreateModelMode.UPDATE_MERGE,
+                            CreateModelMode.PASS):
             return "mode %s" % h.mode.name
         elif not isinstance(h.n_updates, (int, np.integer)):
             return "vector-valued model age"
@@ -137,6 +138,15 @@ class StreamExec:
             self._publish_slots()
         if not self.cuda:
             self.ex.set_callbacks(self._cb_snapshot, self._cb_train, self._cb_adopt)
+        self._scratch = None
+        if h0.mode == CreateModelMode.UPDATE_MERGE:      # one private row per node of this rank for the copy that is trained
+            mine = [i for i in ids if self.owner[i] == self.rank]
+            self._scratch = torch.zeros(max(1, len(mine)), self.row_numel, dtype=torch.float32, device=self.device)
+            self._scratch_of = {i: k for k, i in enumerate(mine)}
+            for i, k in self._scratch_of.items():
+                self.ex.set_node_scratch(i, self._scratch[k].data_ptr())
+            if not self.cuda:
+                self.ex.set_update_merge_callback(self._cb_update_merge)
         self.bind_nodes()
 
     def _add_pool_rows(self, k: int) -> None:
@@ -252,6 +262,19 @@ class StreamExec:
             src, sync = self._slot(rank, slot, gen)
             merge = (src, float(w_self), float(w_peer), sync)
         fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key), None, merge_from=merge)
+
+    def _cb_update_merge(self, node: int, rank: int, slot: int, key_own: int, key_tmp: int, w_self: float, w_peer: float,
+                         gen: int) -> None:
+        h = self.sim.nodes[node].model_handler
+        x, y = self._data[node]
+        fn = ops.mlp1_train if self.family == "mlp1" else ops.logreg_train
+        fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key_own), None)
+        tmp = self._scratch[self._scratch_of[node]]
+        src, sync = self._slot(rank, slot, gen)
+        ops.merge_pair(tmp, src, 0.0, 1.0, sync=sync)
+        fn(tmp, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key_tmp), None)
+        if w_peer != 0.0:
+            ops.merge_pair(h.row, tmp, float(w_self), float(w_peer))
 
     def _cb_merge_part(self, node: int, rank: int, slot: int, pid: int, w1: float, w2: float, gen: int) -> None:
         src, sync = self._slot(rank, slot, gen)

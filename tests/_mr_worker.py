@@ -90,7 +90,7 @@ def build(kind, device):
         sim = GossipSimulator(nodes, disp, 10, prt_, delay=UniformDelay(0, 2))
         sim.engine = "native"
         sim.native_executor = True
-    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull"):
+    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge"):
         # native engine + the C++ executor (csrc/exec): one executor per rank over the same event list
         if kind == "x_mlp_pushpull":
             (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
@@ -99,6 +99,10 @@ def build(kind, device):
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
             n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), LimitedMergeTMH, {"age_diff_threshold": 2}
             proto_, kws = AntiEntropyProtocol.PUSH, dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 2), sampling_eval=.5)
+        elif kind == "x_update_merge":
+            (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(480, 200)
+            n, bs, net, cls = 5, 32, TorchMLP(784, 10, (100,)), TorchModelHandler
+            kwh, proto_, kws = {"create_model_mode": CreateModelMode.UPDATE_MERGE}, AntiEntropyProtocol.PUSH_PULL, dict(delay=UniformDelay(0, 2))
         else:
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(500, 200)
             n, bs, net, cls = 5, 16, LogisticRegression(57, 2), TorchModelHandler

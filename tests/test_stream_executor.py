@@ -105,7 +105,9 @@ def test_native_executor_equals_python_executor(model, protocol, faults, sync):
 
 @pytest.mark.parametrize("kw", [dict(mode="UPDATE", protocol="PUSH"), dict(mode="PASS", protocol="PUSH_PULL", faults=True),
                                 dict(limited=20, protocol="PULL", faults=True), dict(limited=0, protocol="PUSH_PULL"),
-                                dict(tokenized=True, protocol="PUSH", faults=True), dict(mode="UPDATE", model="mlp", faults=True)])
+                                dict(tokenized=True, protocol="PUSH", faults=True), dict(mode="UPDATE", model="mlp", faults=True),
+                                dict(mode="UPDATE_MERGE", protocol="PUSH_PULL", faults=True), dict(mode="UPDATE_MERGE", model="mlp", protocol="PUSH"),
+                                dict(mode="UPDATE_MERGE", limited=3, protocol="PULL", faults=True)])
 def test_native_executor_modes_and_variants(kw):
     import gossipy_b200 as g
     kw = dict(dict(model="logreg", sync=False), **kw)
@@ -186,8 +188,14 @@ def test_eligibility():
     assert eligible(sim) is not None
     for nd in sim.nodes.values():
         nd.model_handler.mode = CreateModelMode.UPDATE_MERGE
-    assert eligible(sim) is not None
-    sim.start(1)                                   # falls back to the per-event executor
+    assert eligible(sim) is None                   # all four modes run natively
+    import gossipy_b200 as g
+    g.GlobalSettings().reference_compat = True     # bug-for-bug behaviours live in the Python handlers
+    try:
+        assert eligible(sim) is not None
+        sim.start(1)                               # falls back to the per-event executor
+    finally:
+        g.GlobalSettings().reference_compat = False
     assert "_stream_exec" not in sim.__dict__
 
 
@@ -221,6 +229,14 @@ def test_native_executor_cuda_equals_python_executor():
         assert "_stream_exec" in sim_b.__dict__
         _same(sim_a, rep_a, sim_b, rep_b, tol=1e-6)
         g.CACHE.clear()
+    for kw in (dict(model="mlp", protocol="PUSH_PULL", mode="UPDATE_MERGE"), dict(model="logreg", protocol="PUSH", mode="UPDATE_MERGE", limited=3, faults=True),
+               dict(model="mlp", protocol="PUSH", partitioned=4, faults=True)):
+        sim_a, rep_a = _sim(False, n=8, rounds=4, device="cuda:0", **kw)
+        sim_b, rep_b = _sim(True, n=8, rounds=4, device="cuda:0", **kw)
+        torch.cuda.synchronize()
+        assert "_stream_exec" in sim_b.__dict__
+        _same(sim_a, rep_a, sim_b, rep_b, tol=1e-5)
+        g.CACHE.clear()
     g.GlobalSettings().set_device("cpu")
 
 
@@ -232,7 +248,7 @@ def test_native_executor_equals_python_executor_random_setups():
 
     @settings(max_examples=int(os.environ.get("EXEC_EXAMPLES", "12")), deadline=None, derandomize=True, database=None,
               suppress_health_check=list(HealthCheck))
-    @given(protocol=st.sampled_from(["PUSH", "PULL", "PUSH_PULL"]), mode=st.sampled_from(["MERGE_UPDATE", "UPDATE", "PASS"]),
+    @given(protocol=st.sampled_from(["PUSH", "PULL", "PUSH_PULL"]), mode=st.sampled_from(["MERGE_UPDATE", "UPDATE", "UPDATE_MERGE", "PASS"]),
            faults=st.booleans(), sync=st.booleans(), limited=st.sampled_from([None, 0, 3, 50]), tokenized=st.booleans(),
            n=st.integers(2, 9), rounds=st.integers(1, 4))
     def check(protocol, mode, faults, sync, limited, tokenized, n, rounds):
