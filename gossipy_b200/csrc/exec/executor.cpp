@@ -328,8 +328,10 @@ private:
         ws = (float)((double)a / (double)tot); wp = (float)((double)b / (double)tot);
     }
 
-    void train(Node& nd, const float* peer, float ws, float wp, uint64_t key, PeerSync sync,
-               const std::vector<int64_t>* part_ages = nullptr) {
+    // stage_mode (kernels.h): 1 = issue only the operand loader (returns whether anything was staged), 2 = the
+    // training kernel on operands staged by an earlier call, 0 = both
+    bool train(Node& nd, const float* peer, float ws, float wp, uint64_t key, PeerSync sync,
+               const std::vector<int64_t>* part_ages = nullptr, int stage_mode = 0) {
         bool ok;
         const char* why = "";
         auto scaled = [&](auto& p) {
@@ -343,8 +345,11 @@ private:
             p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.H = H_; p.OUT = OUT_;
             p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
             if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; p.sync = sync; }
+            p.stage_mode = stage_mode;
             ok = launch_mlp1_train(p, kTrainAuto, nd.stream, &why);
+            if (stage_mode == 1) return ok;
         } else {
+            if (stage_mode == 1) return false;
             LogregParams p{};
             scaled(p);
             p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.OUT = OUT_;
@@ -353,6 +358,7 @@ private:
             ok = launch_logreg_train(p, nd.stream);
         }
         if (!ok) throw std::runtime_error(std::string("training kernel rejected the shape: ") + why);
+        return true;
     }
 
     void consume(int node, int32_t msg_id) {
@@ -372,9 +378,12 @@ private:
         const bool remote = world_ > 1 && rk != owner_[node];      // the snapshot lives on another rank than the reader
         if (remote) sl.remote_reads += 1;                           // replicated: the owner will wait for this many acks
         PeerSync sync{nullptr, 0, nullptr, nullptr};
+        // fused MERGE_UPDATE of the MLP: the operand loader of the training kernel does not depend on the incoming model,
+        // so it is issued BEFORE this stream waits for the snapshot (off the critical path of a gossip chain)
+        const bool hoist = exec && cuda_ && !remote && sl.written && n_parts_ == 0 && mode_ == 2 && family_ == 0;
         if (exec && cuda_) {
             if (remote) sync = PeerSync{sl.ready, sl.gen, sl.done, device_fault_word()};
-            else if (sl.written)                                // (a slot restored from a checkpoint has no writer event)
+            else if (sl.written && !hoist)                      // (a slot restored from a checkpoint has no writer event)
                 cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
         }
         if (n_parts_ > 0) {                                // partitioned MERGE_UPDATE: merge one partition, then train
@@ -448,7 +457,11 @@ private:
             nd.counter += 1;
             const uint64_t key = key_of(node, nd);
             if (exec) {
-                if (cuda_) train(nd, fused_merge ? sl.data : nullptr, ws, wp, key, sync);
+                if (hoist) {
+                    const bool staged = train(nd, sl.data, ws, wp, key, sync, nullptr, 1);
+                    cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
+                    train(nd, sl.data, ws, wp, key, sync, nullptr, staged ? 2 : 0);
+                } else if (cuda_) train(nd, fused_merge ? sl.data : nullptr, ws, wp, key, sync);
                 else cb_train_(node, rk, fused_merge ? s : -1, (int64_t)key, ws, wp, (int64_t)sl.gen);
                 ++launches_;
             }

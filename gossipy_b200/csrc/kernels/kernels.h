@@ -74,6 +74,10 @@ struct TrainParams {
     // fused MERGE_UPDATE: when `peer` is set the kernel starts from w_self*row + w_peer*peer
     // (the peer row is pulled over NVLink while the weights are loaded on chip)
     const float* peer; float w_self, w_peer; PeerSync sync;
+    // the tcgen05 kernel's operands are staged by a loader kernel that depends on (X, y, key) only, not on the model:
+    // 0 = loader + training kernel, 1 = loader only (issued BEFORE the stream waits for the incoming snapshot, so it
+    // is off the critical path of a gossip chain), 2 = training kernel only (operands already staged on this stream)
+    int stage_mode;
 };
 // auto = fp32-equivalent: tc8 (3xTF32 on an 8-CTA cluster) -> cluster (fp32 CUDA cores).  Plain-tf32 kernels only by name:
 // tc3 (CTA pair, whole step on the tensor core), tc8-tf32 (8-CTA cluster).

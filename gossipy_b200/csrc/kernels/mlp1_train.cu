@@ -348,6 +348,10 @@ bool launch_mlp1_train(TrainParams p, TrainImpl impl, cudaStream_t stream, const
     if (impl == kTrainAuto) impl = g_auto_impl;
     const bool scaled = p.scaled();
     if (scaled && p.n_parts > MAX_PARTS) { *why = "fused partitioned training supports <= 16 partitions"; return false; }
+    if (p.stage_mode == 1) {        // loader only: meaningful for the tcgen05 (tc8) kernels; false = nothing was staged
+        const bool tc8 = impl == kTrainAuto || impl == kTrainTc8 || (impl == kTrainTc8Tf32 && !scaled && p.momentum == 0.f);
+        return tc8 && mlp1_train_tc4(p, 8, impl != kTrainTc8Tf32, stream);
+    }
     if (p.momentum != 0.f) {                                       // fused momentum-SGD: the tcgen05 kernel only
         if ((impl == kTrainAuto || impl == kTrainTc8) && mlp1_train_tc4(p, 8, true, stream)) return true;
         *why = "fused momentum-SGD needs the tcgen05 (tc8) kernel: 32 <= in <= 896 (multiple of 4), hidden <= 128, out <= 10, batch <= 32";

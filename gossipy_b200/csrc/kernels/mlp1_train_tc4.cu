@@ -1094,9 +1094,11 @@ static bool tc4_launch(const TrainParams& p, cudaStream_t stream) {
                 return false;
             configured = smem;
         }
-        mlp1_stage4_kernel<X3><<<dim3(steps, NC), 256, smem, stream>>>(p.X, p.y, p.n, p.IN, p.B, p.epochs, p.key, NC, FPC, FP, out, ys);
+        if (p.stage_mode != 2)
+            mlp1_stage4_kernel<X3><<<dim3(steps, NC), 256, smem, stream>>>(p.X, p.y, p.n, p.IN, p.B, p.epochs, p.key, NC, FPC, FP, out, ys);
     }
     if (SC && (p.n_parts > 16 || !p.scaled())) return false;
+    if (p.stage_mode == 1) return cudaGetLastError() == cudaSuccess;
     auto kern = mlp1_train_tc4_kernel<NC, X3, SC, MOM>;
     static bool configured = false;
     if (!configured) {

@@ -287,6 +287,11 @@ class PENSNode(GossipNode):
         self.step = 1
         self.best_nodes: Optional[List[int]] = None
 
+    def __getstate__(self) -> Dict[str, Any]:
+        st = dict(self.__dict__)       # checkpoints carry the scores, not the device-side pending reads
+        st["cache"] = {s: (k, v.result() if hasattr(v, "result") else v) for s, (k, v) in self.cache.items()}
+        return st
+
     def _select_neighbors(self) -> None:
         thr = self.m_top / self.n_sampled
         self.best_nodes = [i for i, cnt in self.neigh_counter.items() if cnt > self.selected[i] * thr]
@@ -322,12 +327,18 @@ class PENSNode(GossipNode):
             self.model_handler(recv, self.data[0])
             _release(recv)
             return None
-        accuracy = CACHE[key].evaluate(self.data[0])["accuracy"]
+        # the candidate is scored on the device right away (its kernels queue behind the sender's snapshot), but the
+        # score is only READ when the selection needs it: one host synchronisation per n_sampled models instead of one
+        # per message (the reference evaluates synchronously in every receive, node.py:764-785)
+        cand = CACHE[key]
+        score = cand.evaluate_async(self.data[0]) if hasattr(cand, "evaluate_async") else cand.evaluate(self.data[0])
         stale = self.cache.get(msg.sender)
         if stale is not None:
             CACHE.drop(stale[0])
-        self.cache[msg.sender] = (key, -accuracy)  # newest model per sender
+        self.cache[msg.sender] = (key, score)  # newest model per sender
         if len(self.cache) >= self.n_sampled:
+            self.cache = {s: (k, -float((v.result() if hasattr(v, "result") else v)["accuracy"]))
+                          for s, (k, v) in self.cache.items()}
             top = sorted(self.cache, key=lambda s: self.cache[s][1])[:self.m_top]
             models = [CACHE.pop(self.cache[s][0]) for s in top]
             self.model_handler(models, self.data[0])
@@ -354,18 +365,22 @@ class PENSNode(GossipNode):
         snap = CACHE.pop(msg.value[0])
         local = self.model_handler._scratch_copy(snap)
         _release(snap)
-        res = local.evaluate(self.data[0])
-        score = -float(res["accuracy"]) if res is not None else 0.0
+        pending = local.evaluate_async(self.data[0])     # read at selection time only (see receive)
         stale = self.cache.get(msg.sender)
         if stale is not None:
             stale[0].release()
-        self.cache[msg.sender] = (local, score)      # newest model per sender
+        self.cache[msg.sender] = (local, pending)    # newest model per sender
         if len(self.cache) < self.n_sampled:
             return None
         owner = _prt.rank_of(self.idx)
         top = None
         if _prt.rank() == owner:
-            top = sorted(self.cache, key=lambda s: self.cache[s][1])[:self.m_top]
+            def neg_acc(s):
+                res = self.cache[s][1]
+                res = res.result() if hasattr(res, "result") else res
+                return -float(res["accuracy"]) if res is not None else 0.0
+            scores = {s: neg_acc(s) for s in self.cache}
+            top = sorted(self.cache, key=lambda s: scores[s])[:self.m_top]
         top = _prt.share_ints(top, owner, min(self.m_top, len(self.cache)))
         self.model_handler([self.cache[s][0] for s in top], self.data[0])
         for s in self.cache:                          # canonical release order: same free lists everywhere
