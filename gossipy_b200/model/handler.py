@@ -1590,19 +1590,26 @@ class MFModelHandler(RowHandler):
         den = 2.0 * (a + b)
         self._weighted_merge(other_model_handler, a / den, b / den, 0, self._n_shared)
 
-    def evaluate(self, ratings: Any) -> Dict[str, float]:
+    def evaluate_async(self, ratings: Any) -> PendingEval:
+        """RMSE on the node's ratings (ref ``handler.py:569-573``); the scalar stays on the device until ``result()``."""
         if not self._mine():
-            return None
+            return _NOT_MINE
         r = self._to_device(ratings)
         if not isinstance(r, torch.Tensor):
             r = torch.as_tensor(np.asarray(r), dtype=torch.float32, device=self.device)
         r = r.to(torch.float32).reshape(-1, 2)
         X, b, Y, c = self._parts()
-        with _arena.on_stream(self._stream()):
+        s = self._stream()
+        with _arena.on_stream(s):
+            _arena.before_read(self._ensure_row(), s if s is not None else _arena.current(self.device))
             idx = r[:, 0].long()
             pred = Y[idx] @ X + b + c[idx]
-            rmse = float(torch.sqrt(torch.mean((r[:, 1] - pred) ** 2)))   # syncs the node's stream
-        return {"rmse": rmse}
+            mse = torch.mean((r[:, 1] - pred) ** 2)
+            ev = _mark(self.device)
+        return PendingEval(lambda: {"rmse": float(torch.sqrt(mse))}, ev)
+
+    def evaluate(self, ratings: Any) -> Dict[str, float]:
+        return self.evaluate_async(ratings).result()
 
     def get_size(self) -> int:
         return self.k * (self.n_items + 1)
@@ -1673,17 +1680,28 @@ class KMeansHandler(RowHandler):
         self._pull(other_model_handler, run)
         self._version += 1
 
-    def evaluate(self, data: Tuple[torch.Tensor, torch.Tensor]) -> Dict[str, float]:
+    def evaluate_async(self, data: Tuple[torch.Tensor, torch.Tensor]) -> PendingEval:
+        """NMI of the cluster assignment (ref ``handler.py:632-636``): the contingency table is built on the device and
+        read when the result is asked for."""
         if not self._mine():
-            return None
+            return _NOT_MINE
         X, y = self._to_device(data)
-        with _arena.on_stream(self._stream()):
+        yl = y.long().reshape(-1)
+        y_host = data[1]
+        if isinstance(y_host, torch.Tensor) and y_host.is_cuda:
+            n_true = int(yl.max()) + 1 if yl.numel() else 1       # labels only exist on the device: one read
+        else:                                                     # number of classes from the host copy: no device read
+            n_true = int(np.asarray(y_host).max()) + 1 if yl.numel() else 1
+        s = self._stream()
+        with _arena.on_stream(s):
+            _arena.before_read(self._ensure_row(), s if s is not None else _arena.current(self.device))
             pred = ops.kmeans_assign(self.model, X.float().reshape(-1, self.dim))
-            yl = y.long().reshape(-1)
-            n_true = int(yl.max()) + 1 if yl.numel() else 1
-            ct = torch.bincount(yl * self.k + pred.long(), minlength=n_true * self.k)
-            ct = ct.view(n_true, self.k).cpu().numpy()                    # syncs the node's stream
-        return {"nmi": _metrics.nmi_from_contingency(ct)}
+            ct = torch.bincount(yl * self.k + pred.long(), minlength=n_true * self.k).view(n_true, self.k)
+            ev = _mark(self.device)
+        return PendingEval(lambda: {"nmi": _metrics.nmi_from_contingency(ct.cpu().numpy())}, ev)
+
+    def evaluate(self, data: Tuple[torch.Tensor, torch.Tensor]) -> Dict[str, float]:
+        return self.evaluate_async(data).result()
 
     def get_size(self) -> int:
         return self.k * self.dim
