@@ -393,6 +393,28 @@ void bank_snapshot(BANK_ARGS, at::Tensor sender, at::Tensor slot) {
     launch_bank_snapshot(bank_view(BANK_PASS), sender.data_ptr<int>(), slot.data_ptr<int>(), (int)sender.numel(), cur_stream());
     GB_LAUNCH_CHECK();
 }
+void bank_snapshot_push(BANK_ARGS, std::vector<int64_t> peer_S, std::vector<int64_t> peer_age, at::Tensor sender,
+                        at::Tensor slot, at::Tensor dst_rank) {
+    check_idx(sender); check_idx(slot); check_idx(dst_rank);
+    TORCH_CHECK(peer_S.size() == peer_age.size() && (int)peer_S.size() <= kMaxRanks && sender.numel() == dst_rank.numel());
+    BankPeers pr{};
+    for (size_t r = 0; r < peer_S.size(); ++r) {
+        pr.S[r] = reinterpret_cast<float*>((uintptr_t)peer_S[r]);
+        pr.slot_age[r] = reinterpret_cast<long long*>((uintptr_t)peer_age[r]);
+    }
+    c10::cuda::CUDAGuard guard(W.device());
+    launch_bank_snapshot_push(bank_view(BANK_PASS), pr, sender.data_ptr<int>(), slot.data_ptr<int>(), dst_rank.data_ptr<int>(),
+                              (int)sender.numel(), cur_stream());
+    GB_LAUNCH_CHECK();
+}
+void rank_barrier(std::vector<int64_t> flags, int64_t rank, int64_t gen) {
+    TORCH_CHECK((int)flags.size() <= kMaxRanks && rank >= 0 && rank < (int64_t)flags.size());
+    RankBarrier rb{};
+    for (size_t r = 0; r < flags.size(); ++r) rb.flags[r] = reinterpret_cast<uint32_t*>((uintptr_t)flags[r]);
+    rb.rank = (int)rank; rb.world = (int)flags.size(); rb.gen = (uint32_t)gen;
+    launch_rank_barrier(rb, cur_stream());
+    GB_LAUNCH_CHECK();
+}
 void bank_deliver(BANK_ARGS, at::Tensor recv, at::Tensor slot) {
     check_idx(recv); check_idx(slot);
     c10::cuda::CUDAGuard guard(W.device());
@@ -550,6 +572,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("ipc_open_handle", &gb::ipc_open_handle);
     m.def("ipc_close_handle", &gb::ipc_close_handle);
     m.def("tensor_from_ptr", &gb::tensor_from_ptr);
+    m.def("bank_snapshot_push", &gb::bank_snapshot_push);
+    m.def("rank_barrier", &gb::rank_barrier);
     m.def("flag_signal", &gb::flag_signal);
     m.def("flag_wait", &gb::flag_wait);
     m.def("flag_add", &gb::flag_add);

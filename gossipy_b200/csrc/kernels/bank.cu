@@ -58,6 +58,29 @@ bank_snapshot_kernel(const BankView b, const int* __restrict__ sender, const int
     if (lane == 0) b.slot_age[d] = b.age[s];
 }
 
+// several ranks: S[slot] of the RECEIVER's rank = W[sender] (stores travel over NVLink / NVSwitch; the next
+// rank_barrier_kernel publishes them)
+__global__ void __launch_bounds__(BK_WARPS * 32)
+bank_snapshot_push_kernel(const BankView b, const BankPeers peers, const int* __restrict__ sender,
+                          const int* __restrict__ slot, const int* __restrict__ dst_rank, int n) {
+    const int item = blockIdx.x * BK_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= n) return;
+    const int s = sender[item], d = slot[item];
+    if (d < 0) return;
+    float* S = peers.S[dst_rank[item]];
+    for (int k = lane; k < b.Dp; k += 32) S[(size_t)d * b.Dp + k] = b.W[(size_t)s * b.Dp + k];
+    if (lane == 0) peers.slot_age[dst_rank[item]][d] = b.age[s];
+}
+
+// barrier across the ranks of the job, stream ordered: everything this rank's earlier kernels wrote (also into peers'
+// memory) is visible to every rank's later kernels.  One generation word per (rank, peer); bounded wait (fault bit 8).
+__global__ void rank_barrier_kernel(const RankBarrier rb, uint32_t* fault) {
+    const int t = threadIdx.x;
+    __threadfence_system();
+    if (t < rb.world) gb_st_release_sys(rb.flags[t] + rb.rank, rb.gen);
+    if (t < rb.world) gb_wait_flag(rb.flags[rb.rank] + t, rb.gen, fault, 8u);
+}
+
 // deliver: node recv[i] consumes snapshot slot[i] according to the CreateModelMode
 template <int KPL>
 __global__ void __launch_bounds__(BK_WARPS * 32)
@@ -156,6 +179,14 @@ void launch_bank_snapshot(const BankView& b, const int* sender, const int* slot,
     if (n <= 0) return;
     bank_snapshot_kernel<<<(n + BK_WARPS - 1) / BK_WARPS, BK_WARPS * 32, 0, st>>>(b, sender, slot, n);
 }
+void launch_bank_snapshot_push(const BankView& b, const BankPeers& peers, const int* sender, const int* slot,
+                               const int* dst_rank, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    bank_snapshot_push_kernel<<<(n + BK_WARPS - 1) / BK_WARPS, BK_WARPS * 32, 0, st>>>(b, peers, sender, slot, dst_rank, n);
+}
+void launch_rank_barrier(const RankBarrier& rb, cudaStream_t st) {
+    rank_barrier_kernel<<<1, 32, 0, st>>>(rb, device_fault_word());
+}
 bool launch_bank_deliver(const BankView& b, const int* recv, const int* slot, int n, cudaStream_t st) {
     if (n <= 0) return true;
     if (b.D <= 64) deliver_t<2>(b, recv, slot, n, st);
@@ -183,6 +214,8 @@ void launch_bank_scores(const BankView& b, const int* nodes, int n_nodes, const 
 void preload_bank() {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, bank_snapshot_kernel);
+    cudaFuncGetAttributes(&a, bank_snapshot_push_kernel);
+    cudaFuncGetAttributes(&a, rank_barrier_kernel);
     cudaFuncGetAttributes(&a, bank_deliver_kernel<2>); cudaFuncGetAttributes(&a, bank_deliver_kernel<4>);
     cudaFuncGetAttributes(&a, bank_deliver_kernel<8>); cudaFuncGetAttributes(&a, bank_deliver_kernel<32>);
     cudaFuncGetAttributes(&a, bank_update_kernel<2>); cudaFuncGetAttributes(&a, bank_update_kernel<4>);

@@ -140,6 +140,13 @@ struct BankView {
     int mode;                            // CreateModelMode value (1 UPDATE, 2 MERGE_UPDATE, 3 UPDATE_MERGE, 4 PASS)
     float lr;
 };
+// several ranks: a snapshot is PUSHED into the slot bank of the receiver's GPU (remote stores over NVLink), so the
+// delivery kernels only read local memory; phases are separated by a flag barrier across the ranks
+struct BankPeers { float* S[kMaxRanks]; long long* slot_age[kMaxRanks]; };
+struct RankBarrier { uint32_t* flags[kMaxRanks]; int rank, world; uint32_t gen; };   // flags[r][q] = generation rank q reached
+void launch_bank_snapshot_push(const BankView& b, const BankPeers& peers, const int* sender, const int* slot,
+                               const int* dst_rank, int n, cudaStream_t st);
+void launch_rank_barrier(const RankBarrier& rb, cudaStream_t st);
 void launch_bank_snapshot(const BankView& b, const int* sender, const int* slot, int n, cudaStream_t st);
 bool launch_bank_deliver(const BankView& b, const int* recv, const int* slot, int n, cudaStream_t st);
 bool launch_bank_update(const BankView& b, const int* nodes, int n, cudaStream_t st);

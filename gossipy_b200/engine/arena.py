@@ -242,6 +242,8 @@ def arena_for(device: torch.device, row_numel: int, rank: Optional[int] = None) 
 
 
 def reset_arenas() -> None:
+    from . import bank as _bank
+    _bank.close_all()
     for sym in _SYMMETRIC.values():
         sym.close()
     _ARENAS.clear()

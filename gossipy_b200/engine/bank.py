@@ -36,13 +36,23 @@ _MODE = {CreateModelMode.UPDATE: 1, CreateModelMode.MERGE_UPDATE: 2, CreateModel
          CreateModelMode.PASS: 4}
 
 
+_OPEN: List["LinearBank"] = []      # banks holding shared-memory segments (closed by parallel.runtime.shutdown)
+
+
+def close_all() -> None:
+    while _OPEN:
+        _OPEN.pop().close()
+
+
 def bankable(sim) -> Optional[str]:
     """``None`` if :class:`LinearBank` can execute ``sim``; otherwise the reason it cannot."""
     from ..model.handler import AdaLineHandler
     from ..node import GossipNode
     from ..parallel import runtime as prt
-    if prt.active():
-        return "multi-rank run"
+    if prt.active() and prt.transport() != "p2p":
+        return "several ranks without shared memory"
+    if prt.active() and prt.world() > 16:
+        return "more than 16 ranks"
     nodes = list(sim.nodes.values())
     h0 = nodes[0].model_handler
     if not isinstance(h0, AdaLineHandler):
@@ -76,12 +86,20 @@ class LinearBank:
         self.mode = _MODE[h0.mode]
         self.lr = float(h0.learning_rate)
         dev = self.device
+        from ..parallel import runtime as prt
+        self.multi = prt.active()
+        self.world = prt.world() if self.multi else 1
+        self.rank = prt.rank() if self.multi else 0
+        # several ranks: every rank keeps the whole index space (N x Dp floats is small) but only the rows of ITS nodes
+        # are live; the event list and all slot bookkeeping are replicated, the launches cover the own nodes
+        self.owner = np.asarray([prt.rank_of(i) if self.multi else 0 for i in ids], dtype=np.int64)
         # models and ages
         self.W = torch.zeros(self.n, self.Dp, dtype=torch.float32, device=dev)
         self.age = torch.zeros(self.n, dtype=torch.int64, device=dev)
         for i in ids:
             h = sim.nodes[i].model_handler
-            self.W[i, :self.D].copy_(h.row[:self.D])
+            if self.owner[i] == self.rank:
+                self.W[i, :self.D].copy_(h.row[:self.D])
             self.age[i] = int(h.n_updates)
         # data: all shards concatenated
         xs, ys, off, cnt = [], [], [], []
@@ -100,11 +118,14 @@ class LinearBank:
         self.max_cnt = int(max(cnt)) if cnt else 0
         # snapshot slots
         self.cap = max(64, 4 * self.n)
-        self.S = torch.zeros(self.cap, self.Dp, dtype=torch.float32, device=dev)
-        self.slot_age = torch.zeros(self.cap, dtype=torch.int64, device=dev)
-        self.free = np.arange(self.cap - 1, -1, -1, dtype=np.int64)   # stack of free slots
-        self.n_free = self.cap
         self.slot_map = np.full(_RING, -1, dtype=np.int64)            # message id (mod ring) -> slot
+        if self.multi:
+            self._init_shared_slots()
+        else:
+            self.S = torch.zeros(self.cap, self.Dp, dtype=torch.float32, device=dev)
+            self.slot_age = torch.zeros(self.cap, dtype=torch.int64, device=dev)
+            self.free = np.arange(self.cap - 1, -1, -1, dtype=np.int64)   # stack of free slots
+            self.n_free = self.cap
         # evaluation set
         self.Xte = self.yte = None
         if sim.data_dispatcher.has_test():
@@ -112,6 +133,137 @@ class LinearBank:
             self.Xte = torch.as_tensor(Xte, dtype=torch.float32).reshape(-1, self.D).contiguous().to(dev)
             self.yte = torch.as_tensor(yte).reshape(-1).to(dev)
         self.size_model = int(h0.get_size())
+
+    # -- several ranks: slot banks in shared memory, snapshots pushed to the receiver's rank ----------------------
+    def _init_shared_slots(self) -> None:
+        """One allocation per rank, mapped into every process (CUDA IPC; POSIX shared memory on CPU):
+        ``S[cap][Dp]`` fp32 | ``slot_age[cap]`` int64 | barrier generations ``[16]`` uint32.  A message's snapshot lives in
+        the bank of the RECEIVER's rank: the sender's rank pushes it there (stores over NVLink), deliveries read local
+        memory only.  Slots are allocated from per-rank pools by replicated bookkeeping (identical on every rank)."""
+        import torch.distributed as dist
+        from ..parallel import runtime as prt
+        cap, Dp, W = self.cap, self.Dp, self.world
+        off_age = cap * Dp * 4
+        off_flag = off_age + cap * 8
+        total = off_flag + 64
+        self._gen = 0
+        self.slot_rank = np.zeros(_RING, dtype=np.int64)              # message id (mod ring) -> rank of its slot
+        self.free_r = [np.arange(cap - 1, -1, -1, dtype=np.int64) for _ in range(W)]
+        self.n_free_r = [cap] * W
+        self.pending_r: List[List[np.ndarray]] = [[] for _ in range(W)]   # released, reusable after the next barrier
+        if self.device.type == "cuda":
+            from ..ops.native import native
+            nat = native()
+            torch.cuda.set_device(self.device)
+            base = nat.ipc_alloc(total)
+            dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            nat.tensor_from_ptr(base, [total // 4], dev_index, True).zero_()
+            torch.cuda.synchronize(self.device)
+            handles: List = [None] * W
+            dist.all_gather_object(handles, nat.ipc_get_handle(base))
+            bases = [base if r == self.rank else nat.ipc_open_handle(handles[r]) for r in range(W)]
+            dist.barrier()
+            self._peer_S = [int(bptr) for bptr in bases]
+            self._peer_age = [int(bptr) + off_age for bptr in bases]
+            self._peer_flags = [int(bptr) + off_flag for bptr in bases]
+            self.S = nat.tensor_from_ptr(base, [cap, Dp], dev_index, False)
+            self.slot_age = nat.tensor_from_ptr(base + off_age, [2 * cap], dev_index, True).view(torch.int64)
+        else:
+            from multiprocessing import shared_memory
+            names = ["gb200_bank_%s_%d" % (prt.session_tag(), r) for r in range(W)]
+            mine = shared_memory.SharedMemory(name=names[self.rank], create=True, size=total)
+            np.frombuffer(mine.buf, dtype=np.uint8)[:] = 0
+            dist.barrier()
+            self._shm = [mine if r == self.rank else shared_memory.SharedMemory(name=names[r]) for r in range(W)]
+            dist.barrier()
+            _OPEN.append(self)
+            self._S_of = [torch.frombuffer(sh.buf, dtype=torch.float32, count=cap * Dp).view(cap, Dp) for sh in self._shm]
+            self._age_of = [torch.frombuffer(sh.buf, dtype=torch.int64, count=cap, offset=off_age) for sh in self._shm]
+            self.S, self.slot_age = self._S_of[self.rank], self._age_of[self.rank]
+
+    def close(self) -> None:
+        """Release the shared-memory mappings (CPU runs; CUDA IPC allocations live until the process ends)."""
+        shm = self.__dict__.pop("_shm", None)
+        if shm is None:
+            return
+        self.__dict__.pop("_S_of", None)
+        self.__dict__.pop("_age_of", None)
+        self.S = self.slot_age = None
+        for r, sh in enumerate(shm):
+            if r == self.rank:
+                try:
+                    sh.unlink()
+                except Exception:
+                    pass
+            try:
+                sh.close()
+            except Exception:      # tensors created with torch.frombuffer may still reference the mapping
+                pass
+
+    def _barrier(self) -> None:
+        """All ranks: what was pushed before is visible, what was read before may be overwritten.  On a GPU a
+        stream-ordered flag barrier over NVLink (one small kernel, no host synchronisation)."""
+        if self.device.type == "cuda":
+            from ..ops.native import native
+            self._gen += 1
+            native().rank_barrier(self._peer_flags, self.rank, self._gen)
+            ops._count()
+        else:
+            import torch.distributed as dist
+            dist.barrier()
+        for r in range(self.world):                       # slots released before the barrier may be written again
+            for sl in self.pending_r[r]:
+                k = sl.size
+                if self.n_free_r[r] + k > self.free_r[r].size:
+                    self.free_r[r] = np.concatenate([self.free_r[r], np.empty(self.n_free_r[r] + k - self.free_r[r].size, dtype=np.int64)])
+                self.free_r[r][self.n_free_r[r]:self.n_free_r[r] + k] = sl
+                self.n_free_r[r] += k
+            self.pending_r[r] = []
+
+    def _alloc_multi(self, dst: np.ndarray) -> np.ndarray:
+        out = np.empty(dst.size, dtype=np.int64)
+        for r in np.unique(dst):
+            sel = dst == r
+            k = int(sel.sum())
+            if self.n_free_r[r] < k:
+                self._barrier()                           # (replicated decision) recycle what was released since
+            if self.n_free_r[r] < k:
+                raise RuntimeError("banked engine: more than %d messages in flight towards rank %d" % (self.cap, r))
+            out[sel] = self.free_r[r][self.n_free_r[r] - k:self.n_free_r[r]]
+            self.n_free_r[r] -= k
+        return out
+
+    def _release_multi(self, slots: np.ndarray, ranks: np.ndarray) -> None:
+        keep = slots >= 0
+        slots, ranks = slots[keep], ranks[keep]
+        for r in np.unique(ranks):
+            self.pending_r[r].append(slots[ranks == r].copy())
+
+    def _snapshot_multi(self, senders: np.ndarray, slots: np.ndarray, dst: np.ndarray) -> bool:
+        """Push the snapshots of MY senders into the banks of their receivers' ranks; returns whether the phase has
+        cross-rank traffic (a replicated fact: then every rank runs the barrier)."""
+        carries = slots >= 0
+        cross = bool(np.any(carries & (self.owner[senders] != dst)))
+        mine = carries & (self.owner[senders] == self.rank)
+        if mine.any():
+            s, d, r = senders[mine], slots[mine], dst[mine]
+            if self.device.type == "cuda":
+                from ..ops.native import native
+                native().bank_snapshot_push(*self._args(), self._peer_S, self._peer_age, self._idx(s), self._idx(d), self._idx(r))
+                ops._count()
+            else:
+                st = torch.as_tensor(s, dtype=torch.int64)
+                for q in np.unique(r):
+                    sel = r == q
+                    dd = torch.as_tensor(d[sel], dtype=torch.int64)
+                    self._S_of[q][dd] = self.W[st[torch.as_tensor(sel)]]
+                    self._age_of[q][dd] = self.age[st[torch.as_tensor(sel)]]
+        return cross
+
+    def _deliver_multi(self, recvs: np.ndarray, slots: np.ndarray) -> None:
+        mine = self.owner[recvs] == self.rank
+        if mine.any():
+            self._deliver(recvs[mine], slots[mine])
 
     # -- low level ops (CUDA kernels / torch on CPU) ---------------------------------------------
     def _args(self):
@@ -240,6 +392,8 @@ class LinearBank:
 
     def run_round(self, events: np.ndarray, C: Any) -> Tuple[List[int], Dict[str, int]]:
         """Execute one round's event list; returns (nodes to evaluate, message counters)."""
+        if self.multi:
+            return self._run_round_multi(events, C)
         kind, tick, a, b, slot, aux = (events[:, i] for i in range(6))
         counters = {"sent": 0, "sent_size": 0, "failed": 0}
         evals: List[int] = []
@@ -306,12 +460,92 @@ class LinearBank:
                 evals.extend(ea[m].tolist())
         return evals, counters
 
+    def _run_round_multi(self, events: np.ndarray, C: Any) -> Tuple[List[int], Dict[str, int]]:
+        """``run_round`` with the nodes spread over several ranks: same phases, every rank launches the work of its own
+        nodes; a phase that pushed snapshots across ranks ends with a barrier."""
+        kind, tick, a, b, slot, aux = (events[:, i] for i in range(6))
+        counters = {"sent": 0, "sent_size": 0, "failed": 0}
+        evals: List[int] = []
+        if events.shape[0] == 0:
+            return evals, counters
+        own = self.owner
+        bounds = np.flatnonzero(np.r_[True, tick[1:] != tick[:-1], True])
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            k, ea, eb, es, ex = kind[lo:hi], a[lo:hi], b[lo:hi], slot[lo:hi], aux[lo:hi]
+            m = k == C.EV_SEND
+            if m.any():
+                senders, recvs, mids, mtypes = ea[m], eb[m], es[m], ex[m]
+                carries = mtypes != 2
+                dst = own[recvs]
+                slots = np.full(senders.size, -1, dtype=np.int64)
+                if carries.any():
+                    slots[carries] = self._alloc_multi(dst[carries])
+                self.slot_map[mids % _RING] = slots
+                self.slot_rank[mids % _RING] = dst
+                if self._snapshot_multi(senders, slots, dst):
+                    self._barrier()
+                counters["sent"] += int(senders.size)
+                counters["sent_size"] += int(carries.sum()) * self.size_model + int((~carries).sum())
+            m = k == C.EV_DELIVER
+            if m.any():
+                origin, recv, mids = ea[m], eb[m], es[m]
+                rs = k == C.EV_REPLY_SEND
+                req_ids, rep_ids = es[rs], ex[rs]
+                has_reply = np.isin(mids, req_ids) if req_ids.size else np.zeros(mids.size, dtype=bool)
+                rep_of = None
+                if req_ids.size:
+                    srt = np.argsort(req_ids)
+                    pos_in = np.searchsorted(req_ids[srt], mids[has_reply])
+                    rep_of = np.full(mids.size, -1, dtype=np.int64)
+                    rep_of[has_reply] = rep_ids[srt][pos_in]
+                for idx in self._waves(recv):
+                    r_w, mid_w = recv[idx], mids[idx]
+                    s_w = self.slot_map[mid_w % _RING].copy()
+                    self._deliver_multi(r_w, s_w)
+                    self._release_multi(s_w, own[r_w])
+                    if rep_of is not None:
+                        sel = has_reply[idx]
+                        if sel.any():
+                            dst = own[origin[idx][sel]]
+                            rslots = self._alloc_multi(dst)
+                            self.slot_map[rep_of[idx][sel] % _RING] = rslots
+                            self.slot_rank[rep_of[idx][sel] % _RING] = dst
+                            if self._snapshot_multi(r_w[sel], rslots, dst):
+                                self._barrier()
+            m = k == C.EV_REPLY_DELIVER
+            if m.any():
+                recv, mids = ea[m], es[m]
+                counters["sent"] += int(recv.size)
+                counters["sent_size"] += int(recv.size) * self.size_model
+                for idx in self._waves(recv):
+                    s_w = self.slot_map[mids[idx] % _RING].copy()
+                    self._deliver_multi(recv[idx], s_w)
+                    self._release_multi(s_w, own[recv[idx]])
+            m = k == C.EV_DROP
+            if m.any():
+                counters["failed"] += int(m.sum())
+                dropped = self.slot_map[es[m] % _RING].copy()
+                self.slot_map[es[m] % _RING] = -1
+                self._release_multi(dropped, self.slot_rank[es[m] % _RING])
+            m = k == C.EV_EVAL
+            if m.any():
+                evals.extend(ea[m].tolist())
+        return evals, counters
+
     # -- evaluation ------------------------------------------------------------------------------------
     def evaluate(self, nodes: List[int]) -> List[Dict[str, float]]:
         """Metric dicts of ``nodes`` on the global evaluation set: one scores launch, metrics (incl. the
         rank-based AUC with average ranks for ties) vectorised over the nodes on the device, one read-back."""
         if not nodes or self.Xte is None:
             return []
+        if self.multi:                      # every rank scores its own nodes; one small all-reduce merges the dicts
+            from ..parallel import runtime as prt
+            mine = [i for i in nodes if self.owner[i] == self.rank]
+            part = dict(zip(mine, self._evaluate_local(mine))) if mine else {}
+            return prt.share_metrics([part.get(i) for i in nodes])
+        return self._evaluate_local(nodes)
+
+    def _evaluate_local(self, nodes: List[int]) -> List[Dict[str, float]]:
         scores = self._scores(nodes)                                   # [E, T]
         E, T = scores.shape
         pos = (self.yte > 0)
@@ -360,6 +594,8 @@ class LinearBank:
     # -- checkpointing -----------------------------------------------------------------------------
     def export_inflight(self, message_ids: List[int]) -> Dict[str, Any]:
         """Snapshots of the messages that are still on the wire (ids from the scheduler's queues)."""
+        if self.multi:
+            raise NotImplementedError("checkpointing the banked engine with several ranks")
         ids = np.asarray(message_ids, dtype=np.int64)
         slots = self.slot_map[ids % _RING] if ids.size else np.zeros(0, dtype=np.int64)
         keep = slots >= 0
@@ -379,9 +615,18 @@ class LinearBank:
 
     def writeback(self) -> None:
         W = self.W[:, :self.D]
-        ages = self.age.cpu().tolist()
+        age = self.age
+        if self.multi:                      # ages of the other ranks' nodes (device results): one all-reduce per run
+            import torch.distributed as dist
+            mask = torch.as_tensor(self.owner == self.rank, device=age.device)
+            age = torch.where(mask, age, torch.zeros_like(age))
+            dist.all_reduce(age)
+        ages = age.cpu().tolist()
         for i, node in self.sim.nodes.items():
             h = node.model_handler
-            h.row[:self.D].copy_(W[i])
+            if self.owner[i] == self.rank:
+                h.row[:self.D].copy_(W[i])
             h.n_updates = int(ages[i])
             h._version += 1
+        if self.multi:
+            self.age.copy_(age)

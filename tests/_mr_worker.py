@@ -34,6 +34,24 @@ def build(kind, device):
         nodes = GossipNode.generate(disp, StaticP2PNetwork(8), proto, 20, False)
         sim = GossipSimulator(nodes, disp, 20, AntiEntropyProtocol.PUSH, drop_prob=.1, online_prob=.8,
                               delay=UniformDelay(0, 3), sampling_eval=.5)
+    elif kind in ("bank_pegasos", "bank_adaline_pushpull"):
+        # the banked engine (engine/bank.py): one node per few samples, many nodes per launch; several ranks push
+        # snapshots into the receiver rank's slot bank
+        from gossipy_b200.model.handler import AdaLineHandler
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(90, 120)
+        ytr, yte = 2 * ytr - 1, 2 * yte - 1
+        n = 45 if kind == "bank_pegasos" else 30
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
+        if kind == "bank_pegasos":
+            proto = PegasosHandler(AdaLine(57), 0.01, CreateModelMode.MERGE_UPDATE)
+            kws, prt_ = dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 3), sampling_eval=.3), AntiEntropyProtocol.PUSH
+        else:
+            proto = AdaLineHandler(AdaLine(57), 0.01, CreateModelMode.UPDATE_MERGE)
+            kws, prt_ = dict(delay=UniformDelay(0, 2)), AntiEntropyProtocol.PUSH_PULL
+        nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, kind == "bank_pegasos")
+        sim = GossipSimulator(nodes, disp, 10, prt_, **kws)
+        sim.engine = "native"
+        sim.batched = True
     elif kind == "mlp_pushpull":
         (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
         disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=4, eval_on_user=False)
@@ -155,7 +173,7 @@ def run(kind, device, rounds):
             "sums": {str(k): sums[k] for k in sorted(sums)}, "ages": {str(k): ages[k] for k in sorted(ages)},
             "cache_left": len(g.CACHE),
             "best": {str(i): getattr(n, "best_nodes", None) for i, n in sim.nodes.items()},
-            "cpp_executor": "_stream_exec" in sim.__dict__}
+            "cpp_executor": "_stream_exec" in sim.__dict__, "banked": "_bank" in sim.__dict__}
 
 
 def main():

@@ -106,6 +106,30 @@ def test_symmetric_arenas_grow_when_they_run_out():
     _compare(single, _run(2, "cpu", kinds=kinds, arena_rows=4), rel=1e-5)
 
 
+BKINDS = "bank_pegasos,bank_adaline_pushpull"
+
+
+def test_banked_engine_two_and_three_ranks_cpu_equal_single_process():
+    """engine/bank.py with several ranks: snapshots pushed into the slot bank of the receiver's rank, replicated slot
+    pools, a barrier after every phase with cross-rank pushes."""
+    single = _run(1, "cpu", rounds=5, kinds=BKINDS)
+    assert all(v["banked"] for v in single.values())
+    for world in (2, 3):
+        multi = _run(world, "cpu", rounds=5, kinds=BKINDS)
+        assert all(v["banked"] for v in multi.values())
+        _compare(single, multi, rel=1e-5)
+
+
+@pytest.mark.gpu
+def test_banked_engine_two_ranks_cuda_equal_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    single = _run(1, "cuda:0", rounds=5, kinds=BKINDS)
+    multi = _run(2, "cuda", rounds=5, kinds=BKINDS)
+    assert all(v["banked"] for v in multi.values())
+    _compare(single, multi, rel=1e-4)
+
+
 @pytest.mark.gpu
 def test_two_ranks_cuda_equal_single_gpu():
     if torch.cuda.device_count() < 2:
