@@ -60,14 +60,6 @@ inline uint64_t mix64(uint64_t x) {          // engine/rng.py::mix64
 enum : int32_t { EV_SEND = 0, EV_DROP = 1, EV_DELIVER = 2, EV_REPLY_SEND = 3, EV_REPLY_DELIVER = 4, EV_EVAL = 5 };
 enum : int32_t { MT_PUSH = 1, MT_PULL = 2, MT_REPLY = 3, MT_PUSH_PULL = 4 };
 
-struct Node {
-    float* row = nullptr; const float* X = nullptr; const int64_t* y = nullptr;
-    int n = 0; int64_t age = 0, counter = 0; cudaStream_t stream = nullptr;
-    std::vector<int64_t> ages_v;            // partitioned models: one age per partition (age = their sum)
-    int64_t model_msgs = 0;                 // model-carrying messages sent so far (keys the partition draw)
-    float* scratch = nullptr;               // UPDATE_MERGE: private trainable copy of a received model
-};
-
 struct Slot {
     int64_t age = 0;
     int64_t counter = 0;                    // the sender's update counter at send time (UPDATE_MERGE keys the copy's update with it)
@@ -77,6 +69,17 @@ struct Slot {
     float* data = nullptr;                                                        // peer-mapped when the slot lives on another rank
     uint32_t* ready = nullptr; uint32_t* done = nullptr;                          // cross-rank handshake words (owner's memory)
     uint32_t gen = 0, remote_reads = 0, acked = 0;                                // replicated bookkeeping of the handshake
+};
+
+struct Node {
+    float* row = nullptr; const float* X = nullptr; const int64_t* y = nullptr;
+    int n = 0; int64_t age = 0, counter = 0; cudaStream_t stream = nullptr;
+    std::vector<int64_t> ages_v;            // partitioned models: one age per partition (age = their sum)
+    int64_t model_msgs = 0;                 // model-carrying messages sent so far (keys the partition draw)
+    float* scratch = nullptr;               // UPDATE_MERGE: private trainable copy of a received model
+    // snapshot elision: a message whose delivery provably precedes this node's next write travels as a reference to the
+    // LIVE row (`alias.data == row`), no copy.  0 = none, 1 = on the wire, 2 = read: the next write waits for `alias.read`
+    Slot alias; int alias_state = 0;
 };
 
 void cuda_check(cudaError_t e, const char* what) {
@@ -103,6 +106,8 @@ public:
         if (n_nodes <= 0) throw std::invalid_argument("n_nodes must be positive");
         const char* dbg = std::getenv("GOSSIPY_EXEC_DEBUG");
         debug_ = dbg != nullptr && dbg[0] != '\0' && dbg[0] != '0';
+        const char* el = std::getenv("GOSSIPY_EXEC_ELIDE");
+        elide_ = !(el != nullptr && el[0] == '0');
         if (mode < 1 || mode > 4) throw std::invalid_argument("mode must be UPDATE, MERGE_UPDATE, UPDATE_MERGE or PASS");
     }
     ~StreamExecutor() {
@@ -111,6 +116,10 @@ public:
                 if (s.written) cudaEventDestroy(s.written);
                 if (s.read) cudaEventDestroy(s.read);
             }
+        for (Node& nd : nodes_) {
+            if (nd.alias.written) cudaEventDestroy(nd.alias.written);
+            if (nd.alias.read) cudaEventDestroy(nd.alias.read);
+        }
     }
 
     void set_ranks(int my_rank, int world, const std::vector<int>& owner) {
@@ -192,16 +201,22 @@ public:
             const int32_t kind = ev(i, 0), a = ev(i, 2), b = ev(i, 3), id = ev(i, 4), aux = ev(i, 5);
             switch (kind) {
                 case EV_SEND:
-                    if (aux != MT_PULL) { if (!snapshot(a, id)) { resume_at_ = i; return evals; } }
+                    if (aux != MT_PULL) { if (!snapshot(a, id, can_alias(ev, i, a, b, id, false))) { resume_at_ = i; return evals; } }
                     break;
                 case EV_REPLY_SEND:                       // b answers with its (just updated) model; reply id in aux
-                    if (!snapshot(b, aux)) { resume_at_ = i; return evals; }
+                    if (!snapshot(b, aux, can_alias(ev, i, b, a, aux, true))) { resume_at_ = i; return evals; }
                     break;
                 case EV_DROP: {
                     auto it = inflight_.find(id);
                     if (it != inflight_.end()) {
-                        if (debug_) pools_[it->second.first][it->second.second].state = 0;
-                        free_[it->second.first].push_back(it->second.second); inflight_.erase(it);
+                        if (it->second.first < 0) {       // an elided snapshot that was never read
+                            Node& snd = nodes_[-1 - it->second.first];
+                            snd.alias_state = 0; snd.alias.state = 0;
+                        } else {
+                            if (debug_) pools_[it->second.first][it->second.second].state = 0;
+                            free_[it->second.first].push_back(it->second.second);
+                        }
+                        inflight_.erase(it);
                     }
                     break;
                 }
@@ -221,6 +236,7 @@ public:
         return evals;
     }
     int64_t resume_at() const { return resume_at_; }
+    int64_t elided() const { return elided_; }
 
     std::vector<int64_t> ages() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.age); return v; }
     std::vector<int64_t> counters() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back(n.counter); return v; }
@@ -230,6 +246,7 @@ public:
     std::vector<std::vector<int64_t>> inflight() const {
         std::vector<std::vector<int64_t>> v;
         for (const auto& kv : inflight_) {
+            if (kv.second.first < 0) throw std::logic_error("an elided snapshot outlived its round");
             const Slot& sl = pools_[kv.second.first][kv.second.second];
             std::vector<int64_t> r{kv.first, kv.second.first, kv.second.second, sl.age};
             if (n_parts_ > 0) { r.push_back(sl.pid); r.insert(r.end(), sl.ages_v.begin(), sl.ages_v.end()); }
@@ -247,6 +264,7 @@ public:
             if (it == fl.end()) throw std::invalid_argument("slot is not free");
             fl.erase(it);
             Slot& sl = pools_.at(rk).at(s);
+            sl.state = 1;                                   // (debug mode) holds a snapshot again
             sl.age = r.at(3);
             if (n_parts_ > 0) { sl.pid = (int)r.at(4); sl.ages_v.assign(r.begin() + 5, r.begin() + 5 + n_parts_); }
             else if (mode_ == 3) sl.counter = r.at(4);
@@ -268,24 +286,7 @@ private:
     }
     uint64_t key_of(int node, const Node& nd) const { return key_of(node, nd.counter, nd.age); }
 
-    bool snapshot(int node, int32_t msg_id) {
-        const int rk = world_ > 1 ? owner_[node] : 0;
-        auto& fl = free_[rk];
-        if (fl.empty()) return false;
-        // oldest free slot first: its last reader is a whole training kernel (~1 ms) on another node's
-        // stream, and the WAR wait below would serialise unrelated nodes if a just-freed slot were reused
-        // (LIFO reuse measured 74 instead of 190 rounds/s on the headline benchmark)
-        const int s = fl.front(); fl.pop_front();
-        Node& nd = nodes_.at(node);
-        Slot& sl = pools_[rk][s];
-        if (debug_) {       // race-debug mode (GOSSIPY_EXEC_DEBUG=1): every slot has ONE writer and ONE reader per life
-            if (sl.state != 0) throw std::logic_error("executor debug: snapshot into a slot that is still on the wire");
-            for (const auto& kv : inflight_)
-                if (kv.second.first == rk && kv.second.second == s) throw std::logic_error("executor debug: free list and in-flight table share a slot");
-            if (inflight_.count(msg_id)) throw std::logic_error("executor debug: message id sent twice");
-            if (world_ > 1 && sl.acked > sl.remote_reads) throw std::logic_error("executor debug: more acknowledgements than remote reads");
-            sl.state = 1;
-        }
+    void fill_meta(Slot& sl, int node, Node& nd) {         // what travels with the model: age(s), counter, partition id
         sl.age = nd.age;
         sl.counter = nd.counter;
         if (n_parts_ > 0) {                               // node.py::PartitioningBasedNode._payload_extras (keyed form)
@@ -296,6 +297,77 @@ private:
             sl.pid = (int)((h & ((1ull << 63) - 1)) % (uint64_t)n_parts_);
             nd.model_msgs += 1;
         }
+    }
+
+    // Snapshot elision ("zero-copy live read when provably safe"): the message sent at event i by `sender` to `dst` may
+    // travel as a reference to the sender's live row iff, in this round's event list, (1) it is delivered (or dropped)
+    // before any event writes the sender's row, and (2) the sender's next write after the delivery is either the
+    // delivery of the reply to this very message (which waits for the reader's kernel anyway) or does not happen in
+    // this round -- otherwise the write would have to wait for the reader's whole training kernel.  Same rank only
+    // (a peer reads a live row of another GPU through the published snapshot protocol, not directly).
+    template <class Ev>
+    bool can_alias(const Ev& ev, int64_t i, int sender, int dst, int32_t msg_id, bool is_reply) const {
+        if (!elide_ || nodes_[sender].alias_state != 0) return false;
+        if (world_ > 1 && owner_[sender] != owner_[dst]) return false;
+        const int64_t n = ev.shape(0), window = std::min<int64_t>(n, i + 1 + 512);
+        auto writes_sender = [&](int64_t j) {
+            const int32_t kind = ev(j, 0);
+            if (kind == EV_DELIVER) return ev(j, 3) == sender && (ev(j, 5) == MT_PUSH || ev(j, 5) == MT_PUSH_PULL);
+            if (kind == EV_REPLY_DELIVER) return ev(j, 2) == sender;
+            return false;
+        };
+        int64_t j = i + 1;
+        bool found = false;
+        for (; j < window; ++j) {
+            const int32_t kind = ev(j, 0);
+            if (kind == EV_DROP && ev(j, 4) == msg_id) return true;
+            if ((!is_reply && kind == EV_DELIVER && ev(j, 4) == msg_id) || (is_reply && kind == EV_REPLY_DELIVER && ev(j, 4) == msg_id)) { found = true; break; }
+            if (writes_sender(j)) return false;
+        }
+        if (!found) return false;
+        int32_t reply_id = -1;                              // the reply this delivery triggers (PUSH_PULL): slot = request id
+        for (int64_t q = j + 1; q < n; ++q) {
+            const int32_t kind = ev(q, 0);
+            if (!is_reply && kind == EV_REPLY_SEND && ev(q, 4) == msg_id) reply_id = ev(q, 5);
+            if (writes_sender(q)) return kind == EV_REPLY_DELIVER && reply_id >= 0 && ev(q, 4) == reply_id;
+            if (q - j > 4096) return false;
+        }
+        return true;
+    }
+
+    bool snapshot(int node, int32_t msg_id, bool alias = false) {
+        Node& nd = nodes_.at(node);
+        if (alias) {
+            Slot& sl = nd.alias;
+            if (debug_ && (sl.state != 0 || nd.alias_state != 0)) throw std::logic_error("executor debug: second elided snapshot of a live row");
+            sl.state = 1; nd.alias_state = 1;
+            fill_meta(sl, node, nd);
+            sl.data = nd.row;
+            if (mine(node) && cuda_) {                      // "written" = the sender's stream has reached this point
+                if (!sl.written) cuda_check(cudaEventCreateWithFlags(&sl.written, cudaEventDisableTiming), "event");
+                cuda_check(cudaEventRecord(sl.written, nd.stream), "record live row ready");
+            }
+            inflight_[msg_id] = {-1 - node, 0};
+            ++elided_;
+            return true;
+        }
+        const int rk = world_ > 1 ? owner_[node] : 0;
+        auto& fl = free_[rk];
+        if (fl.empty()) return false;
+        // oldest free slot first: its last reader is a whole training kernel (~1 ms) on another node's
+        // stream, and the WAR wait below would serialise unrelated nodes if a just-freed slot were reused
+        // (LIFO reuse measured 74 instead of 190 rounds/s on the headline benchmark)
+        const int s = fl.front(); fl.pop_front();
+        Slot& sl = pools_[rk][s];
+        if (debug_) {       // race-debug mode (GOSSIPY_EXEC_DEBUG=1): every slot has ONE writer and ONE reader per life
+            if (sl.state != 0) throw std::logic_error("executor debug: snapshot into a slot that is still on the wire");
+            for (const auto& kv : inflight_)
+                if (kv.second.first == rk && kv.second.second == s) throw std::logic_error("executor debug: free list and in-flight table share a slot");
+            if (inflight_.count(msg_id)) throw std::logic_error("executor debug: message id sent twice");
+            if (world_ > 1 && sl.acked > sl.remote_reads) throw std::logic_error("executor debug: more acknowledgements than remote reads");
+            sl.state = 1;
+        }
+        fill_meta(sl, node, nd);
         sl.gen += 1;                                      // replicated: every rank knows which generation a reader expects
         if (mine(node)) {
             if (cuda_) {
@@ -367,7 +439,14 @@ private:
         const int rk = it->second.first, s = it->second.second;
         inflight_.erase(it);
         Node& nd = nodes_.at(node);
-        Slot& sl = pools_[rk][s];
+        const bool aliased = rk < 0;                        // elided snapshot: the "slot" is the sender's live row
+        Slot& sl = aliased ? nodes_[-1 - rk].alias : pools_[rk][s];
+        if (nd.alias_state == 1) throw std::logic_error("a node is written while its live row is on the wire (elision look-ahead violated)");
+        if (nd.alias_state == 2) {                          // my live row was read by a peer's kernel: it must finish first
+            if (mine(node) && cuda_ && nd.alias.has_reader)
+                cuda_check(cudaStreamWaitEvent(nd.stream, nd.alias.read, 0), "wait for the reader of the live row");
+            nd.alias_state = 0;
+        }
         if (debug_) {
             if (sl.state != 1) throw std::logic_error("executor debug: delivery of a slot that holds no snapshot");
             if (cuda_ && mine(node) && !(world_ > 1 && rk != owner_[node]) && sl.written == nullptr && sl.gen == 0)
@@ -375,7 +454,7 @@ private:
             sl.state = 0;
         }
         const bool exec = mine(node);
-        const bool remote = world_ > 1 && rk != owner_[node];      // the snapshot lives on another rank than the reader
+        const bool remote = !aliased && world_ > 1 && rk != owner_[node];      // the snapshot lives on another rank than the reader
         if (remote) sl.remote_reads += 1;                           // replicated: the owner will wait for this many acks
         PeerSync sync{nullptr, 0, nullptr, nullptr};
         // fused MERGE_UPDATE of the MLP: the operand loader of the training kernel does not depend on the incoming model,
@@ -473,7 +552,8 @@ private:
             sl.has_reader = true;
         }
         if (exec && cuda_) cuda_check(cudaGetLastError(), "consume launch");
-        free_[rk].push_back(s);
+        if (aliased) nodes_[-1 - rk].alias_state = 2;
+        else free_[rk].push_back(s);
     }
 
     std::vector<Node> nodes_;
@@ -492,7 +572,8 @@ private:
     int n_parts_ = 0; const int64_t* part_id_ = nullptr;
     std::vector<uintptr_t> seg_ptrs_; std::vector<int> seg_counts_;
     int64_t launches_ = 0, resume_at_ = -1;
-    bool debug_ = false;
+    bool debug_ = false, elide_ = true;
+    int64_t elided_ = 0;
 };
 
 void bind_executor(py::module_& m) {
@@ -516,6 +597,7 @@ void bind_executor(py::module_& m) {
         .def("model_msgs", &StreamExecutor::model_msgs)
         .def("run", &StreamExecutor::run, py::arg("events"), py::arg("start") = 0)
         .def_property_readonly("resume_at", &StreamExecutor::resume_at)
+        .def_property_readonly("elided", &StreamExecutor::elided)
         .def_property_readonly("free_slots", &StreamExecutor::free_slots)
         .def_property_readonly("launches", &StreamExecutor::launches)
         .def_property_readonly("debug", &StreamExecutor::debug)

@@ -228,6 +228,8 @@ class StreamExec:
     # -- CPU callbacks (the same handshakes the kernels perform on a GPU, on the shared-memory flags) ----------
     def _slot(self, rank: int, slot: int, gen: int):
         """(tensor, cross-rank handshake or None) of a snapshot slot as seen by THIS rank."""
+        if rank < 0:                    # elided snapshot: the sender's live row (same rank by construction)
+            return self.sim.nodes[-1 - rank].model_handler.row, None
         if not self.multi:
             return self.slots[slot], None
         row = self.pool_rows[rank][slot]

@@ -199,9 +199,10 @@ def test_eligibility():
     assert "_stream_exec" not in sim.__dict__
 
 
-def test_executor_runs_out_of_slots_gracefully():
+def test_executor_runs_out_of_slots_gracefully(monkeypatch):
     """Direct use of the C++ class: `run` stops at the event it cannot serve and resumes after the pool grew."""
     from gossipy_b200.ops.native import _try_import
+    monkeypatch.setenv("GOSSIPY_EXEC_ELIDE", "0")       # (with elision these two messages need no slot at all)
     C = _try_import()
     log = []
     ex = C.StreamExecutor(3, 1, 4, 0, 2, 2, 1, .1, 0., 5, False, 2, -1)
@@ -217,6 +218,48 @@ def test_executor_runs_out_of_slots_gracefully():
     assert list(ex.run(ev, 1)) == [1] and ex.resume_at == -1
     assert [e[0] for e in log] == ["snap", "snap", "train", "train"]
     assert ex.ages() == [0, 20 + 3, 20] and ex.counters() == [0, 2, 0] and ex.inflight() == []
+
+
+def test_snapshot_elision_only_when_provably_safe(monkeypatch):
+    """A message travels as a reference to the sender's live row iff it is delivered before the sender's next write and
+    that write does not have to wait for the reader (csrc/exec/executor.cpp::can_alias)."""
+    from gossipy_b200.ops.native import _try_import
+    C = _try_import()
+
+    def run(ev, n=3):
+        log = []
+        ex = C.StreamExecutor(n, 1, 4, 0, 2, 2, 1, .1, 0., 5, False, 2, -1)
+        for i in range(n):
+            ex.set_node(i, 0, 0, 0, 6, 10 * i, 0, 0)
+        ex.set_callbacks(lambda nd, r, s, g, rr: log.append(("snap", nd)), lambda nd, r, s, k, ws, wp, g: log.append(("train", nd, r)),
+                         lambda nd, r, s, g: log.append(("adopt", nd)))
+        ex.set_slots(0, 4, 8, 8)
+        ex.run(np.asarray(ev, dtype=np.int32), 0)
+        return ex, log
+    PUSH, PUSH_PULL, REPLY = 0, 3, 2          # message types (core.MessageType values)
+    from gossipy_b200.core import MessageType
+    PUSH, PUSH_PULL, REPLY = MessageType.PUSH.value, MessageType.PUSH_PULL.value, MessageType.REPLY.value
+    # push-pull, no delay: the request is read live (the reply's delivery waits for the reader anyway), the reply is read
+    # live too (node 1 is not written again in this round)
+    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH_PULL], [C.EV_DELIVER, 0, 0, 1, 100, PUSH_PULL], [C.EV_REPLY_SEND, 0, 0, 1, 100, 101],
+                   [C.EV_REPLY_DELIVER, 0, 0, 1, 101, REPLY]])
+    assert ex.elided == 2 and [e[0] for e in log] == ["train", "train"] and log[0][2] == -1 and log[1][2] == -2
+    # the sender is written (a delivery from node 2) before its own message arrives: a real snapshot is taken
+    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH], [C.EV_SEND, 0, 2, 0, 101, PUSH], [C.EV_DELIVER, 0, 2, 0, 101, PUSH],
+                   [C.EV_DELIVER, 0, 0, 1, 100, PUSH]])
+    assert [e for e in log if e[0] == "snap"][0] == ("snap", 0) and ex.elided == 1          # (only node 2's message is read live)
+    # delivered first, but the sender's next write is an unrelated delivery that would have to wait for the reader: snapshot
+    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH], [C.EV_DELIVER, 0, 0, 1, 100, PUSH], [C.EV_SEND, 0, 2, 0, 101, PUSH],
+                   [C.EV_DELIVER, 0, 2, 0, 101, PUSH]])
+    assert ("snap", 0) in log and ex.elided == 1
+    # not delivered in this round (delay): snapshot; dropped: nothing is ever read, no copy
+    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH]])
+    assert log == [("snap", 0)] and ex.elided == 0 and len(ex.inflight()) == 1
+    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH], [C.EV_DROP, 0, 0, 1, 100, PUSH]])
+    assert log == [] and ex.elided == 1 and ex.inflight() == []
+    monkeypatch.setenv("GOSSIPY_EXEC_ELIDE", "0")
+    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH], [C.EV_DELIVER, 0, 0, 1, 100, PUSH]])
+    assert ex.elided == 0 and log[0] == ("snap", 0)
 
 
 @pytest.mark.gpu
