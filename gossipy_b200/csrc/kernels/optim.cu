@@ -74,4 +74,15 @@ void preload_optim() {
     cudaFuncGetAttributes(&a, adam_kernel);
 }
 
+// the keyed sample order of one epoch as an index vector (generic autograd path: the mini-batches are gathered on the
+// device with it; producing it here instead of copying a host-built vector keeps the host free to run ahead)
+__global__ void keyed_perm_kernel(int64_t* __restrict__ out, int n, uint64_t key) {
+    GbPerm perm; perm.init((uint32_t)n, key);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int64_t)perm((uint32_t)i);
+}
+void launch_keyed_perm(int64_t* out, int n, uint64_t key, cudaStream_t stream) {
+    if (n <= 0) return;
+    keyed_perm_kernel<<<std::min(1024, (n + 255) / 256), 256, 0, stream>>>(out, n, key);
+}
+
 }  // namespace gb

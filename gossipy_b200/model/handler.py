@@ -952,12 +952,12 @@ class TorchModelHandler(RowHandler):
             return steps
         if self.local_epochs > 0:
             for e in range(self.local_epochs):
-                perm = torch.from_numpy(ops.torch_ref.perm_indices(n, _rng.mix64(gen_key ^ e))).to(x.device)
+                perm = ops.keyed_perm(n, _rng.mix64(gen_key ^ e), x.device)
                 for i in range(0, n, bs):
                     self._local_step(mod, x, y, perm[i:i + bs])
                     steps += 1
         else:
-            perm = torch.from_numpy(ops.torch_ref.perm_indices(n, _rng.mix64(gen_key))).to(x.device)
+            perm = ops.keyed_perm(n, _rng.mix64(gen_key), x.device)
             self._local_step(mod, x, y, perm[:bs])
             steps = 1
         return steps
@@ -1385,7 +1385,10 @@ class PartitionedTMH(TorchModelHandler):
         self.n_updates = self.n_updates + 1
 
     def _grad_scale(self) -> torch.Tensor:
-        inv = 1.0 / torch.as_tensor(self.n_updates, dtype=torch.float32, device=self.row.device)
+        ages = torch.as_tensor(self.n_updates, dtype=torch.float32)
+        if self.row.is_cuda:        # through pinned memory: a pageable upload would block the host until this stream drained
+            ages = ages.pin_memory().to(self.row.device, non_blocking=True)
+        inv = 1.0 / ages
         scale = torch.ones_like(self.row)
         scale[:self.layout.n_params] = inv[self._part_ids()]
         return scale

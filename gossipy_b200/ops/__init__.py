@@ -162,6 +162,19 @@ def adam_step(p, g, n, m, v, step, lr, beta1, beta2, eps, weight_decay=0.0,
         torch_ref.adam_step(p, g, n, m, v, step, lr, beta1, beta2, eps, weight_decay, decoupled)
 
 
+def keyed_perm(n: int, key: int, device: Any) -> torch.Tensor:
+    """The keyed permutation of ``range(n)`` (``torch_ref.perm_indices``) as an int64 tensor on ``device``: written by a
+    kernel on a GPU (no host-built vector, no H2D copy -- a pageable copy would block the host until the node's stream
+    has drained, i.e. serialise the nodes)."""
+    device = torch.device(device)
+    if device.type == "cuda" and native_available():
+        k = int(key) & ((1 << 64) - 1)
+        out = native().keyed_perm(int(n), k - (1 << 64) if k >= (1 << 63) else k, device)     # two's complement for int64
+        _count()
+        return out
+    return torch.from_numpy(torch_ref.perm_indices(n, key)).to(device)
+
+
 MergeFrom = Tuple[torch.Tensor, float, float, Optional[RowSync]]   # (peer row, w_self, w_peer, sync)
 TRAIN_IMPL = ""   # process-wide choice of the fused MLP training kernel, see set_train_impl()
 TRAIN_IMPLS = ("", "auto", "tc8", "cluster", "tc8-tf32", "tc3")

@@ -275,6 +275,15 @@ def test_keyed_permutation_device_matches_host():
     torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
 
 
+@pytest.mark.parametrize("n", [1, 2, 37, 1000, 7500, 65537])
+def test_keyed_perm_kernel_equals_host_permutation(n):
+    ops, ref = _ops()
+    for key in (0, 777, (1 << 63) + 12345, (1 << 64) - 1):
+        dev = ops.keyed_perm(n, key, "cuda:0")
+        assert dev.dtype == torch.int64 and dev.is_cuda
+        assert np.array_equal(dev.cpu().numpy(), ref.perm_indices(n, key))
+
+
 def test_handlers_and_simulation_on_gpu_match_cpu_curve():
     import gossipy_b200 as g
     from gossipy_b200 import ops
