@@ -239,26 +239,30 @@ def test_snapshot_elision_only_when_provably_safe(monkeypatch):
     PUSH, PUSH_PULL, REPLY = 0, 3, 2          # message types (core.MessageType values)
     from gossipy_b200.core import MessageType
     PUSH, PUSH_PULL, REPLY = MessageType.PUSH.value, MessageType.PUSH_PULL.value, MessageType.REPLY.value
-    # push-pull, no delay: the request is read live (the reply's delivery waits for the reader anyway), the reply is read
-    # live too (node 1 is not written again in this round)
-    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH_PULL], [C.EV_DELIVER, 0, 0, 1, 100, PUSH_PULL], [C.EV_REPLY_SEND, 0, 0, 1, 100, 101],
-                   [C.EV_REPLY_DELIVER, 0, 0, 1, 101, REPLY]])
-    assert ex.elided == 2 and [e[0] for e in log] == ["train", "train"] and log[0][2] == -1 and log[1][2] == -2
+    # push-pull, no delay: the request is read live (the sender's next write is the delivery of the reply, which waits
+    # for the reader anyway); the reply travels as a snapshot (node 1's next write must not wait for node 0's kernel)
+    pp = [[C.EV_SEND, 0, 0, 1, 100, PUSH_PULL], [C.EV_DELIVER, 0, 0, 1, 100, PUSH_PULL], [C.EV_REPLY_SEND, 0, 0, 1, 100, 101],
+          [C.EV_REPLY_DELIVER, 0, 0, 1, 101, REPLY]]
+    ex, log = run(pp)
+    assert ex.elided == 1 and log == [("train", 1, -1), ("snap", 1), ("train", 0, 0)]
     # the sender is written (a delivery from node 2) before its own message arrives: a real snapshot is taken
-    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH], [C.EV_SEND, 0, 2, 0, 101, PUSH], [C.EV_DELIVER, 0, 2, 0, 101, PUSH],
-                   [C.EV_DELIVER, 0, 0, 1, 100, PUSH]])
-    assert [e for e in log if e[0] == "snap"][0] == ("snap", 0) and ex.elided == 1          # (only node 2's message is read live)
-    # delivered first, but the sender's next write is an unrelated delivery that would have to wait for the reader: snapshot
+    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH_PULL], [C.EV_SEND, 0, 2, 0, 101, PUSH], [C.EV_DELIVER, 0, 2, 0, 101, PUSH],
+                   [C.EV_DELIVER, 0, 0, 1, 100, PUSH_PULL], [C.EV_REPLY_SEND, 0, 0, 1, 100, 102], [C.EV_REPLY_DELIVER, 0, 0, 1, 102, REPLY]])
+    assert ex.elided == 0 and [e for e in log if e[0] == "snap"][0] == ("snap", 0)
+    # plain PUSH: the sender's next write (if any) is unrelated to the reader -> it must not wait for the reader's kernel
     ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH], [C.EV_DELIVER, 0, 0, 1, 100, PUSH], [C.EV_SEND, 0, 2, 0, 101, PUSH],
                    [C.EV_DELIVER, 0, 2, 0, 101, PUSH]])
-    assert ("snap", 0) in log and ex.elided == 1
+    assert ex.elided == 0 and ("snap", 0) in log and ("snap", 2) in log
+    # an unrelated delivery reaches the sender between the request and its reply: snapshot
+    ex, log = run(pp[:2] + [[C.EV_SEND, 0, 2, 0, 103, PUSH], [C.EV_DELIVER, 0, 2, 0, 103, PUSH]] + pp[2:])
+    assert ex.elided == 0
     # not delivered in this round (delay): snapshot; dropped: nothing is ever read, no copy
     ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH]])
     assert log == [("snap", 0)] and ex.elided == 0 and len(ex.inflight()) == 1
     ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH], [C.EV_DROP, 0, 0, 1, 100, PUSH]])
     assert log == [] and ex.elided == 1 and ex.inflight() == []
     monkeypatch.setenv("GOSSIPY_EXEC_ELIDE", "0")
-    ex, log = run([[C.EV_SEND, 0, 0, 1, 100, PUSH], [C.EV_DELIVER, 0, 0, 1, 100, PUSH]])
+    ex, log = run(pp)
     assert ex.elided == 0 and log[0] == ("snap", 0)
 
 
