@@ -445,11 +445,14 @@ private:
         const bool aliased = rk < 0;                        // elided snapshot: the "slot" is the sender's live row
         Slot& sl = aliased ? nodes_[-1 - rk].alias : pools_[rk][s];
         if (nd.alias_state == 1) throw std::logic_error("a node is written while its live row is on the wire (elision look-ahead violated)");
-        if (nd.alias_state == 2) {                          // my live row was read by a peer's kernel: it must finish first
-            if (mine(node) && cuda_ && nd.alias.has_reader)
-                cuda_check(cudaStreamWaitEvent(nd.stream, nd.alias.read, 0), "wait for the reader of the live row");
-            nd.alias_state = 0;
-        }
+        // my live row was read by a peer's kernel: that kernel must finish before this stream WRITES the row (the operand
+        // loader below does not touch the row and is issued first)
+        bool wait_reader = false;
+        if (nd.alias_state == 2) { wait_reader = mine(node) && cuda_ && nd.alias.has_reader; nd.alias_state = 0; }
+        auto reader_done = [&]() {
+            if (wait_reader) cuda_check(cudaStreamWaitEvent(nd.stream, nd.alias.read, 0), "wait for the reader of the live row");
+            wait_reader = false;
+        };
         if (debug_) {
             if (sl.state != 1) throw std::logic_error("executor debug: delivery of a slot that holds no snapshot");
             if (cuda_ && mine(node) && !(world_ > 1 && rk != owner_[node]) && sl.written == nullptr && sl.gen == 0)
@@ -463,6 +466,7 @@ private:
         // fused MERGE_UPDATE of the MLP: the operand loader of the training kernel does not depend on the incoming model,
         // so it is issued BEFORE this stream waits for the snapshot (off the critical path of a gossip chain)
         const bool hoist = exec && cuda_ && !remote && sl.written && n_parts_ == 0 && mode_ == 2 && family_ == 0;
+        if (!hoist) reader_done();
         if (exec && cuda_) {
             if (remote) sync = PeerSync{sl.ready, sl.gen, sl.done, device_fault_word()};
             else if (sl.written && !hoist)                      // (a slot restored from a checkpoint has no writer event)
@@ -541,6 +545,7 @@ private:
             if (exec) {
                 if (hoist) {
                     const bool staged = train(nd, sl.data, ws, wp, key, sync, nullptr, 1);
+                    reader_done();
                     cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
                     train(nd, sl.data, ws, wp, key, sync, nullptr, staged ? 2 : 0);
                 } else if (cuda_) train(nd, fused_merge ? sl.data : nullptr, ws, wp, key, sync);
