@@ -495,8 +495,20 @@ class GossipSimulator(SimulationEventSender):
             self.__dict__.pop("_bank_inflight", None)
             if resume and getattr(self, "_clock", 0):
                 # checkpoint taken under the Python engine: keep the clock (and the evaluation phase
-                # of sync nodes) but the pending Python queues are not transferable
+                # of sync nodes) but the pending Python queues are not transferable: their messages are
+                # lost (like drops) and the snapshots they reference are returned to the arenas
                 sch.clock = int(self._clock)
+                lost = 0
+                for queues in (self._msg_queues, self._rep_queues):
+                    for msgs in queues.values():
+                        for msg in msgs:
+                            lost += 1
+                            if msg.value and isinstance(msg.value[0], CacheKey):
+                                CACHE.drop(msg.value[0])
+                    queues.clear()
+                if lost:
+                    LOG.warning("Resuming a Python-engine checkpoint under the native engine: %d pending messages "
+                                "were discarded." % lost)
             else:
                 self._clock = 0
         use_bank = self.batched is True or (self.batched == "auto" and (

@@ -258,3 +258,32 @@ def test_scheduler_state_roundtrip():
     assert c.token_balances() == a.token_balances()
     with pytest.raises(Exception):
         C.GossipScheduler(5, 10, 3, 0., 1., 0., 1).set_state(st)
+
+
+def test_python_checkpoint_resumed_under_native_engine_returns_pending_snapshots(tmp_path):
+    """The pending queues of a Python-engine checkpoint cannot be continued by the C++ scheduler: the messages are
+    discarded WITH their snapshots (arena rows must not leak)."""
+    import gossipy_b200 as g
+    from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork, UniformDelay
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import TorchModelHandler
+    from gossipy_b200.model.nn import LogisticRegression
+    from gossipy_b200.node import GossipNode
+    from gossipy_b200.simul import GossipSimulator
+    g.CACHE.clear()
+    g.set_seed(3)
+    (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(300, 100)
+    disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=6, eval_on_user=False)
+    proto = TorchModelHandler(LogisticRegression(57, 2), torch.optim.SGD, {"lr": .1}, torch.nn.CrossEntropyLoss(), batch_size=16)
+    nodes = GossipNode.generate(disp, StaticP2PNetwork(6), proto, 10, True)
+    sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH, delay=UniformDelay(5, 30))
+    sim.progress = False
+    sim.init_nodes(seed=1)
+    sim.start(2)                                   # Python engine; long delays leave messages on the wire
+    assert len(g.CACHE) > 0
+    sim.engine = "native"
+    sim.start(1, resume=True)
+    sim.engine = "python"
+    assert sum(len(q) for q in sim._msg_queues.values()) == 0
+    g.CACHE.clear()
