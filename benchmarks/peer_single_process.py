@@ -17,9 +17,10 @@ n = int(os.environ.get("PEER_FLOATS", 1 << 26))
 dst = torch.randn(n, device="cuda:0")
 srcs = [torch.randn(n, device="cuda:%d" % d) for d in range(1, n_dev)]
 probe = torch.empty(16, device="cuda:0")
-for s in srcs:                      # a cross-device copy makes torch enable peer access between the two devices
-    probe.copy_(s[:16])
+for s in srcs:                      # kernels on cuda:0 dereference the other GPUs' memory directly
     assert torch.cuda.can_device_access_peer(0, s.device.index)
+    nat.enable_peer_access(0, s.device.index)
+    probe.copy_(s[:16])
 torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
 

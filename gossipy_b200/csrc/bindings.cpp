@@ -474,6 +474,17 @@ int64_t ipc_open_handle(pybind11::bytes handle) {
     C10_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     return (int64_t)(uintptr_t)p;
 }
+// one process, several visible GPUs (benchmarks / ncu captures of the peer kernels): let kernels on `dev` dereference
+// cudaMalloc'ed memory of `peer`
+void enable_peer_access(int64_t dev, int64_t peer) {
+    c10::cuda::CUDAGuard guard((c10::DeviceIndex)dev);
+    int can = 0;
+    C10_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, (int)dev, (int)peer));
+    TORCH_CHECK(can, "device ", dev, " cannot access device ", peer);
+    cudaError_t e = cudaDeviceEnablePeerAccess((int)peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else C10_CUDA_CHECK(e);
+}
 void ipc_close_handle(int64_t ptr) { C10_CUDA_CHECK(cudaIpcCloseMemHandle((void*)(uintptr_t)ptr)); }
 at::Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> sizes, int64_t device, bool as_int32) {
     auto opts = at::TensorOptions().device(at::kCUDA, (c10::DeviceIndex)device)
@@ -581,6 +592,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("ipc_get_handle", &gb::ipc_get_handle);
     m.def("ipc_open_handle", &gb::ipc_open_handle);
     m.def("ipc_close_handle", &gb::ipc_close_handle);
+    m.def("enable_peer_access", &gb::enable_peer_access);
     m.def("tensor_from_ptr", &gb::tensor_from_ptr);
     m.def("bank_snapshot_push", &gb::bank_snapshot_push);
     m.def("rank_barrier", &gb::rank_barrier);
