@@ -627,13 +627,14 @@ def _is_plain_ce(criterion: Any) -> bool:
 class _GraphStep:
     """One captured forward + backward (``TorchModelHandler._graph_fwd_bwd``): static inputs + the graph."""
 
-    __slots__ = ("graph", "x", "y", "seen", "failed")
+    __slots__ = ("graph", "x", "y", "seen", "failed", "error")
 
     def __init__(self) -> None:
         self.graph = None
         self.x = self.y = None
         self.seen = 0
         self.failed = False
+        self.error = ""
 
     def fill(self, x: torch.Tensor, y: torch.Tensor, idx: Optional[torch.Tensor]) -> None:
         if idx is not None:
@@ -1024,8 +1025,10 @@ class TorchModelHandler(RowHandler):
                     del loss
             except Exception as err:            # an op that cannot be captured (host sync, CPU tensors, ...)
                 ent.failed = True
+                ent.error = "%s: %s" % (type(err).__name__, err)
                 ent.x = ent.y = None
-                LOG.debug("CUDA-graph capture of %s failed, running eagerly: %s", type(mod).__name__, err)
+                LOG.warning("CUDA-graph capture of a %s step failed, this batch shape runs eagerly: %s"
+                            % (type(mod).__name__, ent.error))
                 return False
             ent.graph = graph
         else:

@@ -716,9 +716,11 @@ def test_generic_step_replayed_from_cuda_graph_equals_eager(opt, params):
         for _ in range(3):                      # 7 steps each: 6 full batches + one of 8 samples
             h._update((X, y))
         ev = h.evaluate((X, y))
-        used = sum(1 for e in h.__dict__.get("_graphs", {}).values() if e.graph is not None)
+        ents = list(h.__dict__.get("_graphs", {}).values())
+        used = sum(1 for e in ents if e.graph is not None)
+        assert not [e.error for e in ents if e.failed], [e.error for e in ents if e.failed]
         nbt = int(h.model.bn.num_batches_tracked)
-        return h.row.clone(), ev, used, nbt
+        return h.row.clone(), ev, used, (nbt, [(e.seen, e.graph is not None) for e in ents])
     # cuDNN's default convolution algorithms are not run-to-run reproducible (two EAGER runs of this test differ by 5e-3
     # after 21 steps, profiles/r2d/check_graph_step.jsonl); with deterministic fp32 algorithms the replayed step must
     # reproduce the eagerly launched one exactly
@@ -730,7 +732,7 @@ def test_generic_step_replayed_from_cuda_graph_equals_eager(opt, params):
     finally:
         g.GlobalSettings().cuda_graphs = True
         torch.backends.cudnn.deterministic, torch.backends.cudnn.allow_tf32 = saved
-    assert used_eager == 0 and used_graph == 2          # the full batch and the trailing partial batch
-    assert nbt_eager == nbt_graph == 21
+    assert used_eager == 0 and used_graph == 2, (nbt_eager, nbt_graph)      # the full batch and the trailing partial batch
+    assert nbt_eager[0] == nbt_graph[0] == 21
     assert torch.allclose(r_graph, r_eager, rtol=1e-6, atol=1e-7), float((r_graph - r_eager).abs().max())
     assert ev_graph["accuracy"] == pytest.approx(ev_eager["accuracy"], abs=1e-6)
