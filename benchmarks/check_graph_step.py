@@ -88,21 +88,10 @@ def resnet_timing():
             h.owner = i
             h.init()
             hs.append(h)
-        def shard_loss(h):
-            with torch.no_grad():
-                m = h.model
-                m.eval()
-                Xd, yd = X[:512].cuda(), y[:512].cuda()
-                out_ = m(Xd)
-                return round(float(torch.nn.functional.cross_entropy(out_, yd)), 4), round(float((out_.argmax(1) == yd).float().mean()), 4)
-        loss0 = shard_loss(hs[0])
         for h in hs:                       # warm-up + capture
             h._update((X, y))
-        for _ in range(4):                 # does the path learn?  (loss / accuracy of node 0 on its own shard, random labels)
-            hs[0]._update((X, y))
         torch.cuda.synchronize()
-        out = {"resnet20_batch64": True, "cuda_graphs": graphs, "node0_train_loss_acc_before": loss0,
-               "node0_train_loss_acc_after_5_epochs": shard_loss(hs[0])}
+        out = {"resnet20_batch64": True, "cuda_graphs": graphs}
         for k in (1, 8):
             t0 = time.perf_counter()
             for h in hs[:k]:
