@@ -106,6 +106,16 @@ def timing(impl):
     print(json.dumps(out))
 
 
+def timing_momentum():
+    """The fused momentum-SGD form of tc8 (velocity tile in TMEM)."""
+    dims = (784, 100, 10)
+    X, y, row = problem(7500, *dims)
+    buf = torch.zeros_like(row)
+    med, best = timeit(lambda: ops.mlp1_train(row, X, y, dims, 32, 1, 0.01, 0.0, 1234, momentum=(0.9, 0.0, False, buf, False)))
+    print(json.dumps({"check": "timing 235 steps", "impl": "tc8 + fused momentum", "ms_per_update": med, "best_ms": best,
+                      "us_per_step": med / 235 * 1e3}))
+
+
 if IMPLS == ["ncuonly"]:          # a handful of flagship updates for ncu to capture
     X, y, row = problem(7500, 784, 100, 10)
     for _ in range(4):
@@ -123,3 +133,8 @@ for impl in IMPLS:
         timing(impl)
     except Exception as e:                                   # keep going: one JSON line per failure
         print(json.dumps({"impl": impl, "error": str(e)[:300]}))
+if "tc8" in IMPLS:
+    try:
+        timing_momentum()
+    except Exception as e:
+        print(json.dumps({"impl": "tc8 + fused momentum", "error": str(e)[:300]}))
