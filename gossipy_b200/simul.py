@@ -872,6 +872,7 @@ class All2AllGossipSimulator(GossipSimulator):
         mean = None if len(mine) == 1 else torch.zeros(numel, dtype=torch.float32, device=dev)
         size = int(h0.get_size())
         LOG.info("Synchronous all-to-all rounds (%s all-reduce)." % coll.kind)
+        prev_finish = None
         try:
             for r in range(n_rounds):
                 t = self._clock + self.delta - 1
@@ -916,10 +917,16 @@ class All2AllGossipSimulator(GossipSimulator):
                                 ops.merge_pair(h.row, mean, 0.0, 1.0, 0, numel)
                     h._update(self.nodes[i].data[0])
                 self._clock += self.delta
-                self._evaluate_nodes(t, self._eval_sample())
+                # read round r's metrics after round r+1 is enqueued (the host-side read blocks; the GPUs stay busy)
+                finish = self._evaluate_nodes(t, self._eval_sample(), defer=self.pipeline_eval)
+                if prev_finish is not None:
+                    prev_finish()
+                prev_finish = finish
                 self.notify_timestep(t)
         except KeyboardInterrupt:
             LOG.warning("Simulation interrupted by user.")
+        if prev_finish is not None:
+            prev_finish()
         self.notify_end()
 
 
