@@ -424,10 +424,12 @@ void rank_barrier(std::vector<int64_t> flags, int64_t rank, int64_t gen) {
     launch_rank_barrier(rb, cur_stream());
     GB_LAUNCH_CHECK();
 }
-void bank_deliver(BANK_ARGS, at::Tensor recv, at::Tensor slot) {
+void bank_deliver(BANK_ARGS, at::Tensor recv, at::Tensor slot, c10::optional<at::Tensor> item_mode) {
     check_idx(recv); check_idx(slot);
+    if (item_mode.has_value()) { check_idx(*item_mode); TORCH_CHECK(item_mode->numel() == recv.numel()); }
     c10::cuda::CUDAGuard guard(W.device());
-    TORCH_CHECK(launch_bank_deliver(bank_view(BANK_PASS), recv.data_ptr<int>(), slot.data_ptr<int>(), (int)recv.numel(),
+    TORCH_CHECK(launch_bank_deliver(bank_view(BANK_PASS), recv.data_ptr<int>(), slot.data_ptr<int>(),
+                                    item_mode.has_value() ? item_mode->data_ptr<int>() : nullptr, (int)recv.numel(),
                                     cur_stream()), "bank: dim <= 1024 supported");
     GB_LAUNCH_CHECK();
 }
@@ -584,7 +586,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kmeans_match_merge", &gb::kmeans_match_merge, py::arg("C"), py::arg("P"), py::arg("k"), py::arg("dim"),
           py::arg("w_own"), py::arg("w_peer"), py::arg("sync") = py::none());
     m.def("bank_snapshot", &gb::bank_snapshot);
-    m.def("bank_deliver", &gb::bank_deliver);
+    m.def("bank_deliver", &gb::bank_deliver, py::arg("W"), py::arg("age"), py::arg("S"), py::arg("slot_age"), py::arg("X"), py::arg("y"),
+          py::arg("off"), py::arg("cnt"), py::arg("D"), py::arg("kind"), py::arg("mode"), py::arg("lr"), py::arg("recv"), py::arg("slot"),
+          py::arg("item_mode") = py::none());
     m.def("bank_update", &gb::bank_update);
     m.def("bank_scores", &gb::bank_scores);
     m.def("ipc_alloc", &gb::ipc_alloc);

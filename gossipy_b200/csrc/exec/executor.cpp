@@ -63,6 +63,7 @@ enum : int32_t { MT_PUSH = 1, MT_PULL = 2, MT_REPLY = 3, MT_PUSH_PULL = 4 };
 struct Slot {
     int64_t age = 0;
     int64_t counter = 0;                    // the sender's update counter at send time (UPDATE_MERGE keys the copy's update with it)
+    int sender = -1;                        // PassThroughNode: the sender's degree rides along
     std::vector<int64_t> ages_v; int pid = 0;
     int state = 0;                          // debug mode: 0 free, 1 written (on the wire), checked on every transition
     cudaEvent_t written = nullptr, read = nullptr; bool has_reader = false;      // same-rank ordering
@@ -77,6 +78,7 @@ struct Node {
     std::vector<int64_t> ages_v;            // partitioned models: one age per partition (age = their sum)
     int64_t model_msgs = 0;                 // model-carrying messages sent so far (keys the partition draw)
     float* scratch = nullptr;               // UPDATE_MERGE: private trainable copy of a received model
+    uint64_t pt_draws = 0;                  // PassThroughNode: accept draws made so far (keys the next one)
     // snapshot elision: a message whose delivery provably precedes this node's next write travels as a reference to the
     // LIVE row (`alias.data == row`), no copy.  0 = none, 1 = on the wire, 2 = read: the next write waits for `alias.read`
     Slot alias; int alias_state = 0;
@@ -134,6 +136,13 @@ public:
         nd.y = reinterpret_cast<const int64_t*>(y); nd.n = n; nd.age = age; nd.counter = counter;
         nd.stream = reinterpret_cast<cudaStream_t>(stream);
     }
+    // PassThroughNode (node.py::_accepts): degrees of all nodes and the accept draws made so far
+    void set_passthrough(const std::vector<int64_t>& degrees, const std::vector<int64_t>& draws) {
+        if (degrees.size() != nodes_.size() || draws.size() != nodes_.size()) throw std::invalid_argument("one degree / counter per node expected");
+        deg_.assign(degrees.begin(), degrees.end());
+        for (size_t i = 0; i < nodes_.size(); ++i) nodes_[i].pt_draws = (uint64_t)draws[i];
+    }
+    std::vector<int64_t> pt_draws() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back((int64_t)n.pt_draws); return v; }
     void set_node_scratch(int i, uintptr_t scratch) { nodes_.at(i).scratch = reinterpret_cast<float*>(scratch); }
     void set_update_merge_callback(py::function f) { cb_update_merge_ = std::move(f); }
     void set_node_data(int i, uintptr_t X, uintptr_t y, int n) {       // streamed inputs: the buffers alternate per round
@@ -251,6 +260,7 @@ public:
             std::vector<int64_t> r{kv.first, kv.second.first, kv.second.second, sl.age};
             if (n_parts_ > 0) { r.push_back(sl.pid); r.insert(r.end(), sl.ages_v.begin(), sl.ages_v.end()); }
             else if (mode_ == 3) r.push_back(sl.counter);
+            if (!deg_.empty()) r.push_back(sl.sender);
             v.push_back(r);
         }
         std::sort(v.begin(), v.end());
@@ -268,6 +278,7 @@ public:
             sl.age = r.at(3);
             if (n_parts_ > 0) { sl.pid = (int)r.at(4); sl.ages_v.assign(r.begin() + 5, r.begin() + 5 + n_parts_); }
             else if (mode_ == 3) sl.counter = r.at(4);
+            if (!deg_.empty()) sl.sender = (int)r.back();
             inflight_[(int32_t)r.at(0)] = {rk, s};
         }
     }
@@ -289,6 +300,7 @@ private:
     void fill_meta(Slot& sl, int node, Node& nd) {         // what travels with the model: age(s), counter, partition id
         sl.age = nd.age;
         sl.counter = nd.counter;
+        sl.sender = node;
         if (n_parts_ > 0) {                               // node.py::PartitioningBasedNode._payload_extras (keyed form)
             sl.ages_v = nd.ages_v;
             uint64_t h = mix64(seed_);
@@ -463,9 +475,18 @@ private:
         const bool remote = !aliased && world_ > 1 && rk != owner_[node];      // the snapshot lives on another rank than the reader
         if (remote) sl.remote_reads += 1;                           // replicated: the owner will wait for this many acks
         PeerSync sync{nullptr, 0, nullptr, nullptr};
+        int mode = mode_;
+        if (!deg_.empty()) {                                // PassThroughNode: merge with probability min(1, deg_sender / deg_self),
+            const uint64_t k = nd.pt_draws++;               // else adopt untouched (PASS); keyed draw, integer comparison
+            uint64_t h = mix64(seed_);
+            const uint64_t parts[3] = {0x9A55ull, (uint64_t)node, k};
+            for (uint64_t p : parts) h = mix64(h ^ p);
+            const uint64_t u = (h & ((1ull << 63) - 1)) >> 20;
+            if (!(u * (uint64_t)deg_[node] < ((uint64_t)deg_[sl.sender] << 43))) mode = 4;
+        }
         // fused MERGE_UPDATE of the MLP: the operand loader of the training kernel does not depend on the incoming model,
         // so it is issued BEFORE this stream waits for the snapshot (off the critical path of a gossip chain)
-        const bool hoist = exec && cuda_ && !remote && sl.written && n_parts_ == 0 && mode_ == 2 && family_ == 0;
+        const bool hoist = exec && cuda_ && !remote && sl.written && n_parts_ == 0 && mode == 2 && family_ == 0;
         if (!hoist) reader_done();
         if (exec && cuda_) {
             if (remote) sync = PeerSync{sl.ready, sl.gen, sl.done, device_fault_word()};
@@ -494,7 +515,7 @@ private:
             const int st = steps_of(nd);
             for (int64_t& v : nd.ages_v) v += st;
             nd.age += (int64_t)st * n_parts_;
-        } else if (mode_ == 3) {
+        } else if (mode == 3) {
             // UPDATE_MERGE (model/handler.py::__call__, reference handler.py:129-132): update the own model, update a
             // private copy of the received one on the own data (keyed like the Python scratch copy: this node, the
             // sender's counter + 1, the sender's age), then merge the two
@@ -520,7 +541,7 @@ private:
                 launches_ += 4;
             }
             nd.age = std::max(age_own, age_tmp);
-        } else if (mode_ == 4) {                           // PASS: adopt the received model, age unchanged
+        } else if (mode == 4) {                            // PASS: adopt the received model, age unchanged
             if (exec) {
                 if (cuda_) launch_merge_pair(nd.row, sl.data, 0.f, 1.f, 0, row_floats_, sync, nd.stream);
                 else cb_adopt_(node, rk, s, (int64_t)sl.gen);
@@ -528,7 +549,7 @@ private:
             }
         } else {
             float ws = 0.f, wp = 1.f;
-            const bool fused_merge = mode_ == 2;           // MERGE_UPDATE: the merge rides on the training kernel
+            const bool fused_merge = mode == 2;            // MERGE_UPDATE: the merge rides on the training kernel
             if (fused_merge) {
                 merge_weights(nd.age, sl.age, ws, wp);
                 nd.age = std::max(nd.age, sl.age);
@@ -578,6 +599,7 @@ private:
     std::unordered_map<int32_t, std::pair<int, int>> inflight_;     // message id -> (rank, slot)
     py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_merge_;
     int n_parts_ = 0; const int64_t* part_id_ = nullptr;
+    std::vector<int64_t> deg_;                       // PassThroughNode: node degrees (empty = plain nodes)
     std::vector<uintptr_t> seg_ptrs_; std::vector<int> seg_counts_;
     int64_t launches_ = 0, resume_at_ = -1;
     bool debug_ = false, elide_ = true;
@@ -595,6 +617,8 @@ void bind_executor(py::module_& m) {
         .def("set_node", &StreamExecutor::set_node)
         .def("set_node_data", &StreamExecutor::set_node_data)
         .def("set_node_scratch", &StreamExecutor::set_node_scratch)
+        .def("set_passthrough", &StreamExecutor::set_passthrough)
+        .def("pt_draws", &StreamExecutor::pt_draws)
         .def("set_update_merge_callback", &StreamExecutor::set_update_merge_callback)
         .def("set_slots", &StreamExecutor::set_slots)
         .def("set_callbacks", &StreamExecutor::set_callbacks)

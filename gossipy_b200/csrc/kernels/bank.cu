@@ -84,11 +84,15 @@ __global__ void rank_barrier_kernel(const RankBarrier rb, uint32_t* fault) {
 // deliver: node recv[i] consumes snapshot slot[i] according to the CreateModelMode
 template <int KPL>
 __global__ void __launch_bounds__(BK_WARPS * 32)
-bank_deliver_kernel(const BankView b, const int* __restrict__ recv, const int* __restrict__ slot, int n) {
+bank_deliver_kernel(const BankView b, const int* __restrict__ recv, const int* __restrict__ slot,
+                    const int* __restrict__ item_mode, int n) {
     const int item = blockIdx.x * BK_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (item >= n) return;
     const int r = recv[item], s = slot[item];
     if (s < 0) return;                          // PULL request delivered: the receiver only replies
+    // PassThroughNode: the receiver either merges (the bank's mode) or adopts the model untouched (PASS), decided per
+    // message by a keyed draw on the host
+    const int mode = item_mode != nullptr ? item_mode[item] : b.mode;
     float w[KPL], sv[KPL];
 #pragma unroll
     for (int q = 0; q < KPL; ++q) {
@@ -97,7 +101,7 @@ bank_deliver_kernel(const BankView b, const int* __restrict__ recv, const int* _
         sv[q] = k < b.D ? b.S[(size_t)s * b.Dp + k] : 0.f;
     }
     long long aw = b.age[r], as = b.slot_age[s];
-    switch (b.mode) {
+    switch (mode) {
         case 1:                                 // UPDATE: train the received model and adopt it
 #pragma unroll
             for (int q = 0; q < KPL; ++q) w[q] = sv[q];
@@ -167,8 +171,8 @@ bank_scores_kernel(const BankView b, const int* __restrict__ nodes, int n_nodes,
 }
 
 template <int KPL>
-static void deliver_t(const BankView& b, const int* recv, const int* slot, int n, cudaStream_t st) {
-    bank_deliver_kernel<KPL><<<(n + BK_WARPS - 1) / BK_WARPS, BK_WARPS * 32, 0, st>>>(b, recv, slot, n);
+static void deliver_t(const BankView& b, const int* recv, const int* slot, const int* item_mode, int n, cudaStream_t st) {
+    bank_deliver_kernel<KPL><<<(n + BK_WARPS - 1) / BK_WARPS, BK_WARPS * 32, 0, st>>>(b, recv, slot, item_mode, n);
 }
 template <int KPL>
 static void update_t(const BankView& b, const int* nodes, int n, cudaStream_t st) {
@@ -187,12 +191,12 @@ void launch_bank_snapshot_push(const BankView& b, const BankPeers& peers, const 
 void launch_rank_barrier(const RankBarrier& rb, cudaStream_t st) {
     rank_barrier_kernel<<<1, 32, 0, st>>>(rb, device_fault_word());
 }
-bool launch_bank_deliver(const BankView& b, const int* recv, const int* slot, int n, cudaStream_t st) {
+bool launch_bank_deliver(const BankView& b, const int* recv, const int* slot, const int* item_mode, int n, cudaStream_t st) {
     if (n <= 0) return true;
-    if (b.D <= 64) deliver_t<2>(b, recv, slot, n, st);
-    else if (b.D <= 128) deliver_t<4>(b, recv, slot, n, st);
-    else if (b.D <= 256) deliver_t<8>(b, recv, slot, n, st);
-    else if (b.D <= 1024) deliver_t<32>(b, recv, slot, n, st);
+    if (b.D <= 64) deliver_t<2>(b, recv, slot, item_mode, n, st);
+    else if (b.D <= 128) deliver_t<4>(b, recv, slot, item_mode, n, st);
+    else if (b.D <= 256) deliver_t<8>(b, recv, slot, item_mode, n, st);
+    else if (b.D <= 1024) deliver_t<32>(b, recv, slot, item_mode, n, st);
     else return false;
     return true;
 }

@@ -150,7 +150,7 @@ void launch_bank_snapshot_push(const BankView& b, const BankPeers& peers, const 
                                const int* dst_rank, int n, cudaStream_t st);
 void launch_rank_barrier(const RankBarrier& rb, cudaStream_t st);
 void launch_bank_snapshot(const BankView& b, const int* sender, const int* slot, int n, cudaStream_t st);
-bool launch_bank_deliver(const BankView& b, const int* recv, const int* slot, int n, cudaStream_t st);
+bool launch_bank_deliver(const BankView& b, const int* recv, const int* slot, const int* item_mode, int n, cudaStream_t st);
 bool launch_bank_update(const BankView& b, const int* nodes, int n, cudaStream_t st);
 void launch_bank_scores(const BankView& b, const int* nodes, int n_nodes, const float* Xte, int n_te, float* scores,
                         cudaStream_t st);

@@ -47,7 +47,7 @@ def close_all() -> None:
 def bankable(sim) -> Optional[str]:
     """``None`` if :class:`LinearBank` can execute ``sim``; otherwise the reason it cannot."""
     from ..model.handler import AdaLineHandler
-    from ..node import GossipNode
+    from ..node import GossipNode, PassThroughNode
     from ..parallel import runtime as prt
     if prt.active() and prt.transport() != "p2p":
         return "several ranks without shared memory"
@@ -57,9 +57,12 @@ def bankable(sim) -> Optional[str]:
     h0 = nodes[0].model_handler
     if not isinstance(h0, AdaLineHandler):
         return "handler is not AdaLine/Pegasos"
+    cls = type(nodes[0])
+    if cls is PassThroughNode and not getattr(nodes[0], "_keyed_draws", False):
+        return "pass-through nodes with host-stream draws"
     for n in nodes:
         h = n.model_handler
-        if type(n) is not GossipNode:
+        if type(n) is not cls or cls not in (GossipNode, PassThroughNode):
             return "node subclass"
         if type(h) is not type(h0) or h.learning_rate != h0.learning_rate or h.dim != h0.dim or h.mode != h0.mode:
             return "heterogeneous handlers"
@@ -133,6 +136,30 @@ class LinearBank:
             self.Xte = torch.as_tensor(Xte, dtype=torch.float32).reshape(-1, self.D).contiguous().to(dev)
             self.yte = torch.as_tensor(yte).reshape(-1).to(dev)
         self.size_model = int(h0.get_size())
+        # PassThroughNode (Giaretta 2019): the sender's degree rides along; the receiver merges with probability
+        # min(1, deg_sender / deg_self), else adopts the model untouched -- a keyed draw per delivery (node.py::_accepts)
+        from ..node import PassThroughNode
+        self.passthrough = type(sim.nodes[ids[0]]) is PassThroughNode
+        if self.passthrough:
+            self.deg = np.asarray([int(sim.nodes[i].n_neighs) for i in ids], dtype=np.uint64)
+            self.pt_count = np.asarray([int(getattr(sim.nodes[i], "_pt_draws", 0)) for i in ids], dtype=np.uint64)
+            self.size_model += 1                    # the degree is one more atom on the wire
+
+    def _item_modes(self, recvs: np.ndarray, senders: np.ndarray, slots: np.ndarray) -> Optional[np.ndarray]:
+        """Per delivered message: the bank's mode (merge) or 4 (PASS), from the receivers' keyed draws."""
+        if not self.passthrough:
+            return None
+        from ..ops.torch_ref import _mix64_np
+        from . import rng as _rng
+        carries = slots >= 0
+        r = recvs.astype(np.int64)
+        k = self.pt_count[r]
+        h = np.uint64(_rng.mix64(_rng.mix64(_rng.base_seed()) ^ 0x9A55))
+        u = _mix64_np(_mix64_np(h ^ r.astype(np.uint64)) ^ k)
+        u = (u & np.uint64((1 << 63) - 1)) >> np.uint64(20)
+        accept = u * self.deg[r] < (self.deg[senders.astype(np.int64)] << np.uint64(43))
+        self.pt_count[r[carries]] += np.uint64(1)   # (a receiver appears once per wave)
+        return np.where(accept, self.mode, 4).astype(np.int32)
 
     # -- several ranks: slot banks in shared memory, snapshots pushed to the receiver's rank ----------------------
     def _init_shared_slots(self) -> None:
@@ -260,10 +287,10 @@ class LinearBank:
                     self._age_of[q][dd] = self.age[st[torch.as_tensor(sel)]]
         return cross
 
-    def _deliver_multi(self, recvs: np.ndarray, slots: np.ndarray) -> None:
+    def _deliver_multi(self, recvs: np.ndarray, slots: np.ndarray, modes=None) -> None:
         mine = self.owner[recvs] == self.rank
         if mine.any():
-            self._deliver(recvs[mine], slots[mine])
+            self._deliver(recvs[mine], slots[mine], None if modes is None else modes[mine])
 
     # -- low level ops (CUDA kernels / torch on CPU) ---------------------------------------------
     def _args(self):
@@ -313,13 +340,25 @@ class LinearBank:
             w[live] = wl
         return w, age
 
-    def _deliver(self, recvs, slots) -> None:
+    def _deliver(self, recvs, slots, modes=None) -> None:
         if len(recvs) == 0:
             return
         if self.device.type == "cuda":
             from ..ops.native import native
-            native().bank_deliver(*self._args(), self._idx(recvs), self._idx(slots))
+            native().bank_deliver(*self._args(), self._idx(recvs), self._idx(slots),
+                                  None if modes is None else self._idx(modes))
             ops._count()
+            return
+        if modes is not None:                       # per-message modes: one vectorised pass per mode
+            modes = np.asarray(modes)
+            saved = self.mode
+            try:
+                for m in np.unique(modes):
+                    sel = modes == m
+                    self.mode = int(m)
+                    self._deliver(np.asarray(recvs)[sel], np.asarray(slots)[sel])
+            finally:
+                self.mode = saved
             return
         r = torch.as_tensor(np.asarray(recvs), dtype=torch.int64)
         s = torch.as_tensor(np.asarray(slots), dtype=torch.int64)
@@ -416,7 +455,7 @@ class LinearBank:
             # ---- phase B: deliveries (+ the replies they trigger), conflict-free waves ---------------
             m = k == C.EV_DELIVER
             if m.any():
-                recv, mids = eb[m], es[m]
+                origin, recv, mids = ea[m], eb[m], es[m]
                 # replies: EV_REPLY_SEND(slot = request id, aux = reply id) follows its delivery
                 rs = k == C.EV_REPLY_SEND
                 req_ids, rep_ids = es[rs], ex[rs]
@@ -430,7 +469,7 @@ class LinearBank:
                 for idx in self._waves(recv):
                     r_w, mid_w = recv[idx], mids[idx]
                     s_w = self.slot_map[mid_w % _RING].copy()
-                    self._deliver(r_w, s_w)
+                    self._deliver(r_w, s_w, self._item_modes(r_w, origin[idx], s_w))
                     self._release(s_w)
                     if rep_of is not None:
                         sel = has_reply[idx]
@@ -441,12 +480,12 @@ class LinearBank:
             # ---- phase C: replies delivered ------------------------------------------------------------
             m = k == C.EV_REPLY_DELIVER
             if m.any():
-                recv, mids = ea[m], es[m]
+                recv, repl, mids = ea[m], eb[m], es[m]
                 counters["sent"] += int(recv.size)
                 counters["sent_size"] += int(recv.size) * self.size_model
                 for idx in self._waves(recv):
                     s_w = self.slot_map[mids[idx] % _RING].copy()
-                    self._deliver(recv[idx], s_w)
+                    self._deliver(recv[idx], s_w, self._item_modes(recv[idx], repl[idx], s_w))
                     self._release(s_w)
             # ---- losses: free the snapshot -------------------------------------------------------------
             m = k == C.EV_DROP
@@ -501,7 +540,7 @@ class LinearBank:
                 for idx in self._waves(recv):
                     r_w, mid_w = recv[idx], mids[idx]
                     s_w = self.slot_map[mid_w % _RING].copy()
-                    self._deliver_multi(r_w, s_w)
+                    self._deliver_multi(r_w, s_w, self._item_modes(r_w, origin[idx], s_w))
                     self._release_multi(s_w, own[r_w])
                     if rep_of is not None:
                         sel = has_reply[idx]
@@ -514,12 +553,12 @@ class LinearBank:
                                 self._barrier()
             m = k == C.EV_REPLY_DELIVER
             if m.any():
-                recv, mids = ea[m], es[m]
+                recv, repl, mids = ea[m], eb[m], es[m]
                 counters["sent"] += int(recv.size)
                 counters["sent_size"] += int(recv.size) * self.size_model
                 for idx in self._waves(recv):
                     s_w = self.slot_map[mids[idx] % _RING].copy()
-                    self._deliver_multi(recv[idx], s_w)
+                    self._deliver_multi(recv[idx], s_w, self._item_modes(recv[idx], repl[idx], s_w))
                     self._release_multi(s_w, own[recv[idx]])
             m = k == C.EV_DROP
             if m.any():
@@ -628,5 +667,7 @@ class LinearBank:
                 h.row[:self.D].copy_(W[i])
             h.n_updates = int(ages[i])
             h._version += 1
+            if self.passthrough:
+                node._pt_draws = int(self.pt_count[i])
         if self.multi:
             self.age.copy_(age)

@@ -48,14 +48,19 @@ def eligible(sim: Any) -> Optional[str]:
     ids = sorted(sim.nodes)
     if ids != list(range(len(ids))):
         return "node ids must be 0..N-1"
-    from ..node import PartitioningBasedNode
+    from ..node import PartitioningBasedNode, PassThroughNode
     ref = None
+    cls0 = type(sim.nodes[ids[0]])
     for i in ids:
         node = sim.nodes[i]
         h = node.model_handler
         partitioned = type(node) is PartitioningBasedNode and type(h) is H.PartitionedTMH
-        if type(node) is not GossipNode and not partitioned:
+        if type(node) is not cls0:
+            return "mixed node classes"
+        if type(node) not in (GossipNode, PassThroughNode) and not partitioned:
             return "node class %s" % type(node).__name__
+        if type(node) is PassThroughNode and not getattr(node, "_keyed_draws", False):
+            return "pass-through nodes with host-stream draws"
         if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH) and not partitioned:
             return "handler class %s" % type(h).__name__
         if not h._fused or h.layout.int_buffers:
@@ -138,6 +143,8 @@ class StreamExec:
             self._publish_slots()
         if not self.cuda:
             self.ex.set_callbacks(self._cb_snapshot, self._cb_train, self._cb_adopt)
+        from ..node import PassThroughNode
+        self.passthrough = type(sim.nodes[ids[0]]) is PassThroughNode
         self._scratch = None
         if h0.mode == CreateModelMode.UPDATE_MERGE:      # one private row per node of this rank for the copy that is trained
             mine = [i for i in ids if self.owner[i] == self.rank]
@@ -197,6 +204,10 @@ class StreamExec:
                                  int(h._update_counter), int(s.cuda_stream) if s is not None else 0)
             if self.n_parts:
                 self.ex.set_node_ages(i, [int(a) for a in h.n_updates], int(getattr(node, "_model_msgs", 0)))
+        if self.passthrough:
+            ids = sorted(self.sim.nodes)
+            self.ex.set_passthrough([int(self.sim.nodes[i].n_neighs) for i in ids],
+                                    [int(getattr(self.sim.nodes[i], "_pt_draws", 0)) for i in ids])
 
     def refresh_data(self) -> None:
         """Streamed inputs: the resident buffers alternate every round."""
@@ -218,12 +229,15 @@ class StreamExec:
                 h._update_counter = int(counters[i])
                 node._model_msgs = int(msgs[i])
             return
+        draws = self.ex.pt_draws() if self.passthrough else None
         for i, node in self.sim.nodes.items():
             h = node.model_handler
             if int(h.n_updates) != ages[i] or h._update_counter != counters[i]:
                 h._version += 1
             h.n_updates = int(ages[i])
             h._update_counter = int(counters[i])
+            if draws is not None:
+                node._pt_draws = int(draws[i])
 
     # -- CPU callbacks (the same handshakes the kernels perform on a GPU, on the shared-memory flags) ----------
     def _slot(self, rank: int, slot: int, gen: int):

@@ -167,9 +167,21 @@ class PassThroughNode(GossipNode):
     def _payload_extras(self) -> Tuple[Any, ...]:
         return (self.n_neighs,)
 
+    def _accepts(self, deg: int) -> bool:
+        """Merge with probability ``min(1, deg_sender / deg_self)``.  Under the native engine the draw is keyed by
+        (node, number of draws so far) and compared in integer arithmetic, so that the C++ executor and the banked engine
+        reproduce it (``u < 2**43``; accept iff ``u * deg_self < deg_sender * 2**43``)."""
+        if getattr(self, "_keyed_draws", False):
+            from .engine import rng as _rng
+            k = int(getattr(self, "_pt_draws", 0))
+            self._pt_draws = k + 1
+            u = _rng.derive(0x9A55, self.idx, k) >> 20
+            return u * int(self.n_neighs) < (int(deg) << 43)
+        return np.random.rand() < min(1, deg / self.n_neighs)
+
     def _consume(self, msg: Message, recv_model: ModelHandler, extras: Tuple[Any, ...]) -> None:
         deg = extras[0]
-        if np.random.rand() < min(1, deg / self.n_neighs):
+        if self._accepts(deg):
             self.model_handler(recv_model, self.data[0])
         else:
             prev = self.model_handler.mode

@@ -34,7 +34,7 @@ def build(kind, device):
         nodes = GossipNode.generate(disp, StaticP2PNetwork(8), proto, 20, False)
         sim = GossipSimulator(nodes, disp, 20, AntiEntropyProtocol.PUSH, drop_prob=.1, online_prob=.8,
                               delay=UniformDelay(0, 3), sampling_eval=.5)
-    elif kind in ("bank_pegasos", "bank_adaline_pushpull"):
+    elif kind in ("bank_pegasos", "bank_adaline_pushpull", "bank_passthrough"):
         # the banked engine (engine/bank.py): one node per few samples, many nodes per launch; several ranks push
         # snapshots into the receiver rank's slot bank
         from gossipy_b200.model.handler import AdaLineHandler
@@ -42,13 +42,22 @@ def build(kind, device):
         ytr, yte = 2 * ytr - 1, 2 * yte - 1
         n = 45 if kind == "bank_pegasos" else 30
         disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
-        if kind == "bank_pegasos":
+        if kind in ("bank_pegasos", "bank_passthrough"):
             proto = PegasosHandler(AdaLine(57), 0.01, CreateModelMode.MERGE_UPDATE)
             kws, prt_ = dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 3), sampling_eval=.3), AntiEntropyProtocol.PUSH
         else:
             proto = AdaLineHandler(AdaLine(57), 0.01, CreateModelMode.UPDATE_MERGE)
             kws, prt_ = dict(delay=UniformDelay(0, 2)), AntiEntropyProtocol.PUSH_PULL
-        nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, kind == "bank_pegasos")
+        if kind == "bank_passthrough":       # degree-aware pass-through (ring + hub: unequal degrees)
+            from gossipy_b200.node import PassThroughNode
+            A = np.zeros((n, n), dtype=int)
+            for i in range(n):
+                A[i, (i + 1) % n] = A[(i + 1) % n, i] = 1
+                if i % 3 == 0 and i:
+                    A[i, 0] = A[0, i] = 1
+            nodes = PassThroughNode.generate(disp, StaticP2PNetwork(n, A), proto, 10, True)
+        else:
+            nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, kind == "bank_pegasos")
         sim = GossipSimulator(nodes, disp, 10, prt_, **kws)
         sim.engine = "native"
         sim.batched = True
@@ -108,7 +117,7 @@ def build(kind, device):
         sim = GossipSimulator(nodes, disp, 10, prt_, delay=UniformDelay(0, 2))
         sim.engine = "native"
         sim.native_executor = True
-    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge"):
+    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge", "x_passthrough"):
         # native engine + the C++ executor (csrc/exec): one executor per rank over the same event list
         if kind == "x_mlp_pushpull":
             (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
@@ -117,6 +126,10 @@ def build(kind, device):
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
             n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), LimitedMergeTMH, {"age_diff_threshold": 2}
             proto_, kws = AntiEntropyProtocol.PUSH, dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 2), sampling_eval=.5)
+        elif kind == "x_passthrough":
+            (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+            n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), TorchModelHandler, {}
+            proto_, kws = AntiEntropyProtocol.PUSH_PULL, dict(delay=UniformDelay(0, 2))
         elif kind == "x_update_merge":
             (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(480, 200)
             n, bs, net, cls = 5, 32, TorchMLP(784, 10, (100,)), TorchModelHandler
@@ -127,7 +140,16 @@ def build(kind, device):
             kwh, proto_, kws = {"create_model_mode": CreateModelMode.UPDATE}, AntiEntropyProtocol.PULL, dict(delay=UniformDelay(0, 3))
         disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
         proto = cls(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), batch_size=bs, **kwh)
-        nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, kind != "x_limited_push")
+        if kind == "x_passthrough":
+            from gossipy_b200.node import PassThroughNode
+            A = np.zeros((n, n), dtype=int)
+            for i in range(n):
+                A[i, (i + 1) % n] = A[(i + 1) % n, i] = 1
+                if i > 1:
+                    A[i, 0] = A[0, i] = 1
+            nodes = PassThroughNode.generate(disp, StaticP2PNetwork(n, A), proto, 10, True)
+        else:
+            nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, kind != "x_limited_push")
         sim = GossipSimulator(nodes, disp, 10, proto_, **kws)
         sim.engine = "native"
         sim.native_executor = True

@@ -141,7 +141,8 @@ def test_scheduler_event_stream_invariants():
 # batched execution of the linear learners (engine.bank.LinearBank): same schedule, same results as
 # the per-event executor
 # ---------------------------------------------------------------------------------------------
-def _linear_sim(batched, protocol, mode, handler="pegasos", n=40, rounds=6, device="cpu", faults=True, sync=False):
+def _linear_sim(batched, protocol, mode, handler="pegasos", n=40, rounds=6, device="cpu", faults=True, sync=False,
+                passthrough=False):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork, UniformDelay
     from gossipy_b200.data import DataDispatcher, synthetic
@@ -157,7 +158,16 @@ def _linear_sim(batched, protocol, mode, handler="pegasos", n=40, rounds=6, devi
     disp = DataDispatcher(ClassificationDataHandler(Xtr, 2 * ytr - 1, Xte, 2 * yte - 1), n=n, eval_on_user=False)
     cls = PegasosHandler if handler == "pegasos" else AdaLineHandler
     proto = cls(AdaLine(57), .01 if handler == "pegasos" else .001, getattr(CreateModelMode, mode))
-    nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, sync)
+    if passthrough:                 # degree-aware pass-through on a topology with unequal degrees (ring + hub)
+        from gossipy_b200.node import PassThroughNode
+        A = np.zeros((n, n), dtype=int)
+        for i in range(n):
+            A[i, (i + 1) % n] = A[(i + 1) % n, i] = 1
+            if i % 3 == 0 and i:
+                A[i, 0] = A[0, i] = 1
+        nodes = PassThroughNode.generate(disp, StaticP2PNetwork(n, A), proto, 10, sync)
+    else:
+        nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, sync)
     kw = dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 3), sampling_eval=.3) if faults else {}
     sim = GossipSimulator(nodes, disp, 10, getattr(AntiEntropyProtocol, protocol), **kw)
     sim.progress = False
@@ -190,6 +200,22 @@ def test_banked_execution_equals_per_event_execution(protocol, mode, handler):
         assert t1 == t2
         for k in m1:
             assert m1[k] == pytest.approx(m2[k], abs=1e-4), k
+    g.CACHE.clear()
+
+
+@pytest.mark.parametrize("protocol,mode", [("PUSH", "MERGE_UPDATE"), ("PUSH_PULL", "UPDATE"), ("PULL", "MERGE_UPDATE")])
+def test_banked_pass_through_nodes_equal_per_event_execution(protocol, mode):
+    """PassThroughNode (reference node.py:289-392) in the banked engine: keyed accept draws, per-message PASS / merge."""
+    import gossipy_b200 as g
+    rep_a, rows_a, ages_a, sim_a = _linear_sim(False, protocol, mode, passthrough=True)
+    rep_b, rows_b, ages_b, sim_b = _linear_sim(True, protocol, mode, passthrough=True)
+    assert "_bank" not in sim_a.__dict__ and "_bank" in sim_b.__dict__
+    assert (rep_a._sent_messages, rep_a._failed_messages, rep_a._total_size) == \
+        (rep_b._sent_messages, rep_b._failed_messages, rep_b._total_size)
+    draws_a = [getattr(nd, "_pt_draws", 0) for nd in sim_a.nodes.values()]
+    assert draws_a == [getattr(nd, "_pt_draws", 0) for nd in sim_b.nodes.values()] and sum(draws_a) > 0
+    assert ages_a == ages_b
+    torch.testing.assert_close(rows_a, rows_b, rtol=1e-4, atol=1e-5)
     g.CACHE.clear()
 
 

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.skipif(not native_available(), reason="extension not bu
 
 
 def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=4, device="cpu", sync=True, start=True,
-         mode="MERGE_UPDATE", limited=None, tokenized=False, partitioned=0):
+         mode="MERGE_UPDATE", limited=None, tokenized=False, partitioned=0, passthrough=False):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork, UniformDelay
     from gossipy_b200.data import DataDispatcher, synthetic
@@ -47,7 +47,17 @@ def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=
                                 age_diff_threshold=limited, **kwh)
     else:
         proto = TorchModelHandler(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), **kwh)
-    nodes = node_cls.generate(disp, StaticP2PNetwork(n), proto, 10, sync)
+    topo = StaticP2PNetwork(n)
+    if passthrough:                 # degree-aware pass-through needs unequal degrees: a ring plus a hub
+        from gossipy_b200.node import PassThroughNode
+        node_cls = PassThroughNode
+        A = np.zeros((n, n), dtype=int)
+        for i in range(n):
+            A[i, (i + 1) % n] = A[(i + 1) % n, i] = 1
+            if i > 1:
+                A[i, 0] = A[0, i] = 1
+        topo = StaticP2PNetwork(n, A)
+    nodes = node_cls.generate(disp, topo, proto, 10, sync)
     kw = dict(drop_prob=.15, online_prob=.8, delay=UniformDelay(0, 4), sampling_eval=.5) if faults else {}
     if tokenized:
         sim = TokenizedGossipSimulator(nodes, disp, RandomizedTokenAccount(C=4, A=2), lambda a, b, m: 1, 10,
@@ -131,6 +141,21 @@ def test_native_executor_partitioned_models(kw):
     _same(sim_a, rep_a, sim_b, rep_b)
     assert [getattr(nd, "_model_msgs", 0) for nd in sim_a.nodes.values()] == [getattr(nd, "_model_msgs", 0) for nd in sim_b.nodes.values()]
     assert sum(getattr(nd, "_model_msgs", 0) for nd in sim_b.nodes.values()) > 0
+    g.CACHE.clear()
+
+
+@pytest.mark.parametrize("kw", [dict(model="logreg", protocol="PUSH", passthrough=True, faults=True),
+                                dict(model="mlp", protocol="PUSH_PULL", passthrough=True),
+                                dict(model="logreg", protocol="PULL", passthrough=True, mode="UPDATE", sync=False)])
+def test_native_executor_pass_through_nodes(kw):
+    """PassThroughNode (reference node.py:289-392) from C++: keyed accept draw against the degrees, PASS or merge."""
+    import gossipy_b200 as g
+    sim_a, rep_a = _sim(False, n=7, **kw)
+    sim_b, rep_b = _sim(True, n=7, **kw)
+    assert "_stream_exec" in sim_b.__dict__ and "_stream_exec" not in sim_a.__dict__
+    _same(sim_a, rep_a, sim_b, rep_b)
+    draws = [getattr(nd, "_pt_draws", 0) for nd in sim_a.nodes.values()]
+    assert draws == [getattr(nd, "_pt_draws", 0) for nd in sim_b.nodes.values()] and sum(draws) > 0
     g.CACHE.clear()
 
 
