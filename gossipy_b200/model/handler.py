@@ -649,12 +649,26 @@ _GRAPH_POOLS: Dict[Tuple[int, int], Any] = {}
 
 
 def _graph_pool(device: torch.device):
-    """The graph memory pool of the current stream of ``device`` (shared by the handlers that run on that stream)."""
+    """The graph memory pool of the current stream of ``device`` (shared by the handlers that run on that stream).
+
+    The pool is owned by a ``torch.cuda.MemPool`` object that lives as long as the process: a bare pool handle dies with
+    the last graph captured into it, and capturing into a dead handle trips an internal assertion of the caching allocator
+    (met when handlers -- and their graphs -- of an earlier simulation had been collected).  ``None`` (a private pool per
+    graph) when the API is missing."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    pool = _GRAPH_POOLS.get(key)
-    if pool is None:
-        pool = _GRAPH_POOLS[key] = torch.cuda.graph_pool_handle()
-    return pool
+    ent = _GRAPH_POOLS.get(key)
+    if ent is None:
+        mem_pool = getattr(torch.cuda, "MemPool", None)
+        ent = (None, None)
+        if mem_pool is not None:
+            try:
+                with torch.cuda.device(device):
+                    owner = mem_pool()
+                ent = (owner.id, owner)
+            except Exception:              # pragma: no cover - depends on the torch build
+                ent = (None, None)
+        _GRAPH_POOLS[key] = ent
+    return ent[0]
 
 
 class TorchModelHandler(RowHandler):
