@@ -106,6 +106,10 @@ class GlobalSettings(metaclass=_SingletonMeta):
         # replay the forward + backward of generic (autograd) models from a CUDA graph per handler and batch shape
         # instead of launching every layer's kernels from Python (model/handler.py: _graph_fwd_bwd)
         self.cuda_graphs = os.environ.get("GOSSIPY_CUDA_GRAPHS", "1") != "0"
+        # rows of convolutional models keep their filters in channels-last order and feed NHWC batches (cuDNN's tensor-core
+        # kernels run without layout conversions): "auto" = handlers created while the device is a GPU, True = always
+        # (also on CPU: tests), False = never
+        self.channels_last = {"0": False, "1": True}.get(os.environ.get("GOSSIPY_CHANNELS_LAST", ""), "auto")
 
     # -- numerics -----------------------------------------------------------------------
     @property

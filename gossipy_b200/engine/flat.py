@@ -23,7 +23,12 @@ ROW_ALIGN = 32  # floats
 class FlatLayout:
     """Offsets of every parameter / float buffer of a module inside a flat row."""
 
-    def __init__(self, module: nn.Module) -> None:
+    def __init__(self, module: nn.Module, channels_last: bool = False) -> None:
+        # channels_last: 4-D parameters (convolution filters [O, I, kh, kw]) are stored in the row as [O, kh, kw, I] and
+        # bound as permuted views, i.e. as ``torch.channels_last`` tensors -- cuDNN then runs its NHWC tensor-core
+        # kernels without converting filters and activations back and forth on every call.  Which element sits at
+        # which row index is a private matter of the layout: merges, snapshots and optimizers are element-wise.
+        self.channels_last = bool(channels_last) and any(p.dim() == 4 for p in module.parameters())
         self.param_names: List[str] = []
         self.entries: List[Tuple[str, torch.Size, int, int]] = []  # name, shape, offset, numel
         off = 0
@@ -46,6 +51,13 @@ class FlatLayout:
         self.padded = max(ROW_ALIGN, (off + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN)
         self.requires_grad = [bool(p.requires_grad) for p in module.parameters()]
 
+    def _view(self, flat: torch.Tensor, shape: torch.Size) -> torch.Tensor:
+        """The tensor of ``shape`` stored in the 1-D row slice ``flat``."""
+        if self.__dict__.get("channels_last", False) and len(shape) == 4:
+            o, i, kh, kw = shape
+            return flat.view(o, kh, kw, i).permute(0, 3, 1, 2)
+        return flat.view(shape)
+
     # -- moving data between a module and a row ------------------------------------------
     @torch.no_grad()
     def gather(self, module: nn.Module, row: torch.Tensor) -> None:
@@ -53,7 +65,7 @@ class FlatLayout:
         sd = dict(module.named_parameters())
         sd.update(dict(module.named_buffers()))
         for name, shape, off, n in self.entries + self.float_buffers:
-            row[off:off + n].copy_(sd[name].detach().reshape(-1))
+            self._view(row[off:off + n], shape).copy_(sd[name].detach())
         if self.padded > self.numel:
             row[self.numel:self.padded].zero_()
 
@@ -64,9 +76,9 @@ class FlatLayout:
         params = dict(module.named_parameters())
         for name, shape, off, n in self.entries:
             p = params[name]
-            p.data = row[off:off + n].view(shape)
+            p.data = self._view(row[off:off + n], shape)
             if grad_row is not None and p.requires_grad:
-                p.grad = grad_row[off:off + n].view(shape)
+                p.grad = self._view(grad_row[off:off + n], shape)
         if self.float_buffers:
             owners = _buffer_owners(module)
             for name, shape, off, n in self.float_buffers:
@@ -75,7 +87,7 @@ class FlatLayout:
 
     def views(self, row: torch.Tensor) -> Dict[str, torch.Tensor]:
         """``{name: view}`` for ``torch.func.functional_call`` on a snapshot row."""
-        return {name: row[off:off + n].view(shape)
+        return {name: self._view(row[off:off + n], shape)
                 for name, shape, off, n in self.entries + self.float_buffers}
 
     # -- index helpers used by partitioned / sampled merges -------------------------------

@@ -698,7 +698,9 @@ class TorchModelHandler(RowHandler):
         # `_module` is this handler's live module whose tensors are views of the row (lazy).
         self._proto = copy.deepcopy(net)
         self._module = None if copy_model else net
-        self.layout = FlatLayout(self._proto)
+        cl = GlobalSettings().channels_last
+        self.layout = FlatLayout(self._proto, channels_last=self._ROW_CHANNELS_LAST_OK and (
+            cl is True or (cl == "auto" and GlobalSettings().is_cuda())))
         self._row_numel = self.layout.padded
         self._size_cache = int(self._proto.get_size())
         self.optimizer_cls = optimizer
@@ -946,6 +948,11 @@ class TorchModelHandler(RowHandler):
 
     def _update_generic(self, x: torch.Tensor, y: torch.Tensor) -> int:
         mod = self.model
+        nhwc = False
+        if self.layout.channels_last and x.dim() == 4 and not GlobalSettings().reference_compat:
+            # the shard as [N, H, W, C] (one pass per update): a gathered mini-batch viewed back as [B, C, H, W] is a
+            # channels-last tensor, so no layer has to convert layouts
+            x, nhwc = x.permute(0, 2, 3, 1).contiguous(), True
         n = x.size(0)
         bs = n if not self.batch_size else self.batch_size
         gen_key = self._next_key()
@@ -969,25 +976,28 @@ class TorchModelHandler(RowHandler):
             for e in range(self.local_epochs):
                 perm = ops.keyed_perm(n, _rng.mix64(gen_key ^ e), x.device)
                 for i in range(0, n, bs):
-                    self._local_step(mod, x, y, perm[i:i + bs])
+                    self._local_step(mod, x, y, perm[i:i + bs], nhwc)
                     steps += 1
         else:
             perm = ops.keyed_perm(n, _rng.mix64(gen_key), x.device)
-            self._local_step(mod, x, y, perm[:bs])
+            self._local_step(mod, x, y, perm[:bs], nhwc)
             steps = 1
         return steps
 
+    #: whole-model merges only: handlers that address parameters by flat index (sampling, partitions) keep the plain order
+    _ROW_CHANNELS_LAST_OK = True
+
     def _local_step(self, mod: TorchModel, x: torch.Tensor, y: torch.Tensor,
-                    idx: Optional[torch.Tensor] = None) -> None:
+                    idx: Optional[torch.Tensor] = None, nhwc: bool = False) -> None:
         """forward / loss / backward / optimizer step (ref ``handler.py:250-258``) on the mini-batch ``x[idx], y[idx]``
         (``idx = None``: all of ``x, y``).  On a GPU the forward + backward is replayed from a CUDA graph."""
         mod.train()
         g = self._ensure_grad()
-        if not self._graph_fwd_bwd(mod, g, x, y, idx):
+        if not self._graph_fwd_bwd(mod, g, x, y, idx, nhwc):
             if idx is not None:
                 x, y = x[idx], y[idx]
             g.zero_()
-            loss = self.criterion(mod(x), y)
+            loss = self.criterion(mod(x.permute(0, 3, 1, 2) if nhwc else x), y)
             loss.backward()
         self._pre_step()
         self._apply_optimizer(g)
@@ -997,7 +1007,7 @@ class TorchModelHandler(RowHandler):
     _GRAPH_WARMUP = 2
 
     def _graph_fwd_bwd(self, mod: TorchModel, g: torch.Tensor, x: torch.Tensor, y: torch.Tensor,
-                       idx: Optional[torch.Tensor]) -> bool:
+                       idx: Optional[torch.Tensor], nhwc: bool = False) -> bool:
         """Zero the gradient row, forward, loss, backward of one mini-batch as ONE graph launch.
 
         A generic model's step is a few hundred small kernels (ResNet-20: ~600) whose launches from Python, not
@@ -1012,7 +1022,7 @@ class TorchModelHandler(RowHandler):
             return False
         nb = int(idx.numel()) if idx is not None else int(x.size(0))
         key = (self.row.data_ptr(), g.data_ptr(), id(mod), nb, tuple(x.shape[1:]), x.dtype, tuple(y.shape[1:]),
-               y.dtype, x.device.index)
+               y.dtype, x.device.index, nhwc)
         cache = self.__dict__.get("_graphs")
         if cache is None:
             cache = self.__dict__["_graphs"] = {}
@@ -1034,7 +1044,7 @@ class TorchModelHandler(RowHandler):
             try:
                 with torch.cuda.graph(graph, pool=_graph_pool(x.device), capture_error_mode="thread_local"):
                     g.zero_()
-                    loss = self.criterion(mod(ent.x), ent.y)
+                    loss = self.criterion(mod(ent.x.permute(0, 3, 1, 2) if nhwc else ent.x), ent.y)
                     loss.backward()
                     del loss
             except Exception as err:            # an op that cannot be captured (host sync, CPU tensors, ...)
@@ -1141,6 +1151,8 @@ class TorchModelHandler(RowHandler):
 
     # -- evaluation -----------------------------------------------------------------------------
     def _forward_scores(self, x: torch.Tensor) -> torch.Tensor:
+        if self.layout.channels_last and x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)
         mod = self._module
         if mod is not None:
             self._bind()
@@ -1326,6 +1338,7 @@ class PegasosHandler(AdaLineHandler):
 # sampled / partitioned / weighted / limited merges
 # --------------------------------------------------------------------------------------
 class SamplingTMH(TorchModelHandler):
+    _ROW_CHANNELS_LAST_OK = False
     """Merge only a random subset of coordinates (ref ``handler.py:426-452``)."""
 
     def __init__(self, sample_size: float, *args, **kwargs) -> None:
@@ -1359,6 +1372,7 @@ class SamplingTMH(TorchModelHandler):
 
 
 class PartitionedTMH(TorchModelHandler):
+    _ROW_CHANNELS_LAST_OK = False
     """Per-partition ages and merges (ref ``handler.py:455-525``).
 
     ``n_updates`` is an int array with one age per partition.  Every local step increments all

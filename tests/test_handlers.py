@@ -335,3 +335,51 @@ def test_momentum_oracle_equals_torch_optim_sgd():
                        (kw["momentum"], kw.get("dampening", 0.), kw.get("nesterov", False), buf, True))
         want = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
         torch.testing.assert_close(row, want, rtol=1e-10, atol=1e-12)
+
+
+def test_channels_last_rows_are_a_private_layout_choice():
+    """``GlobalSettings().channels_last``: conv filters live in the row as [O, kh, kw, I] and are bound as channels-last
+    views, mini-batches are gathered as NHWC -- training, merging, evaluation, pickling and the model setter give the
+    results of the plain layout."""
+    import copy
+    import pickle
+    import gossipy_b200 as g
+    from gossipy_b200.model.handler import PartitionedTMH, TorchModelHandler
+    from gossipy_b200.model.nn import CIFAR10Net
+    from gossipy_b200.model.sampling import TorchModelPartition
+
+    def run(cl):
+        g.GlobalSettings().channels_last = cl
+        g.set_seed(3)
+        torch.manual_seed(3)
+        X, y = torch.rand(96, 3, 32, 32), torch.randint(0, 10, (96,))
+        h = TorchModelHandler(CIFAR10Net(), torch.optim.SGD, {"lr": .05, "momentum": .9}, torch.nn.CrossEntropyLoss(), batch_size=32)
+        h.init()
+        h2 = h.copy()
+        for _ in range(2):
+            h._update((X, y))
+        h2._update((X[:64], y[:64]))
+        h._merge(h2)
+        ev = h.evaluate((X, y))
+        sd = {k: v.detach().clone() for k, v in h.model.state_dict().items()}
+        h3 = pickle.loads(pickle.dumps(h))
+        assert all(torch.equal(sd[k], v) for k, v in h3.model.state_dict().items())
+        h4 = h.copy()
+        h4.model = copy.deepcopy(h.model)
+        assert all(torch.equal(a, b) for a, b in zip(h4.model.state_dict().values(), sd.values()))
+        return h, sd, ev
+    try:
+        h0, sd0, ev0 = run(False)
+        h1, sd1, ev1 = run(True)
+        assert not h0.layout.channels_last and h1.layout.channels_last
+        w = next(v for v in h1.model.parameters() if v.dim() == 4)
+        assert w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous()
+        for k in sd0:
+            torch.testing.assert_close(sd0[k].float(), sd1[k].float(), rtol=1e-5, atol=1e-6)
+        assert ev0 == pytest.approx(ev1, abs=1e-6)
+        # handlers that address parameters by flat index keep the plain order
+        net = CIFAR10Net()
+        hp = PartitionedTMH(net, TorchModelPartition(net, 4), torch.optim.SGD, {"lr": .1}, torch.nn.CrossEntropyLoss())
+        assert not hp.layout.channels_last
+    finally:
+        g.GlobalSettings().channels_last = "auto"

@@ -736,3 +736,46 @@ def test_generic_step_replayed_from_cuda_graph_equals_eager(opt, params):
     assert nbt_eager[0] == nbt_graph[0] == 21
     assert torch.allclose(r_graph, r_eager, rtol=1e-6, atol=1e-7), float((r_graph - r_eager).abs().max())
     assert ev_graph["accuracy"] == pytest.approx(ev_eager["accuracy"], abs=1e-6)
+
+
+def test_channels_last_rows_on_gpu_match_plain_rows():
+    """Default on a GPU: conv filters are channels-last views of the row, batches NHWC; same training as the plain layout
+    (deterministic fp32 cuDNN; different algorithms => tolerance, not equality)."""
+    import gossipy_b200 as g
+    from gossipy_b200.model.handler import TorchModelHandler
+    from gossipy_b200.model.nn import TorchModel
+
+    class Net(_ConvBN, TorchModel):
+        def init_weights(self):
+            pass
+
+        def __str__(self):
+            return "ConvBN"
+
+    gen = torch.Generator().manual_seed(5)
+    X = torch.randn(200, 3, 16, 16, generator=gen)
+    y = torch.randint(0, 10, (200,), generator=gen)
+
+    def run(cl):
+        g.GlobalSettings().channels_last = cl
+        g.set_seed(11)
+        torch.manual_seed(11)
+        h = TorchModelHandler(Net(), torch.optim.SGD, {"lr": .05, "momentum": .9}, torch.nn.CrossEntropyLoss(), local_epochs=1, batch_size=32)
+        h.init()
+        for _ in range(3):
+            h._update((X, y))
+        return h, {k: v.detach().float().clone() for k, v in h.model.state_dict().items()}, h.evaluate((X, y))
+    saved = (torch.backends.cudnn.deterministic, torch.backends.cudnn.allow_tf32)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.allow_tf32 = True, False
+    try:
+        h0, sd0, ev0 = run(False)
+        h1, sd1, ev1 = run("auto")
+    finally:
+        g.GlobalSettings().channels_last = "auto"
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.allow_tf32 = saved
+    assert not h0.layout.channels_last and h1.layout.channels_last
+    assert h1.model.c1.weight.is_contiguous(memory_format=torch.channels_last)
+    assert sum(1 for e in h1.__dict__.get("_graphs", {}).values() if e.graph is not None) == 2
+    for k in sd0:
+        torch.testing.assert_close(sd0[k], sd1[k], rtol=2e-3, atol=2e-4)
+    assert ev0["accuracy"] == pytest.approx(ev1["accuracy"], abs=.02)
