@@ -32,17 +32,24 @@ class FlatLayout:
         self.param_names: List[str] = []
         self.entries: List[Tuple[str, torch.Size, int, int]] = []  # name, shape, offset, numel
         off = 0
+        # channels-last rows: every tensor starts on a 32-byte boundary (cuDNN's NHWC kernels use 128-bit accesses on the
+        # filter / gradient pointers; a filter that starts at an odd float offset faults with "misaligned address").
+        # The pads are ordinary row elements that stay zero (zero gradient); plain rows stay densely packed -- the
+        # fused MLP / logreg kernels address [W1 | b1 | W2 | b2] directly.
+        align = 8 if self.channels_last else 1
         for name, p in module.named_parameters():
+            off = (off + align - 1) // align * align
             self.param_names.append(name)
             self.entries.append((name, p.shape, off, p.numel()))
             off += p.numel()
-        self.n_params = off  # == model.get_size() for ordinary models
+        self.n_params = off  # == model.get_size() for ordinary models (channels-last rows: plus alignment pads)
         self.float_buffers: List[Tuple[str, torch.Size, int, int]] = []
         self.int_buffers: List[str] = []
         for name, b in module.named_buffers():
             if b is None:
                 continue
             if b.dtype.is_floating_point:
+                off = (off + align - 1) // align * align
                 self.float_buffers.append((name, b.shape, off, b.numel()))
                 off += b.numel()
             else:
@@ -64,6 +71,8 @@ class FlatLayout:
         """Copy the module's current values into ``row``."""
         sd = dict(module.named_parameters())
         sd.update(dict(module.named_buffers()))
+        if self.__dict__.get("channels_last", False):
+            row[:self.numel].zero_()            # alignment pads between the tensors
         for name, shape, off, n in self.entries + self.float_buffers:
             self._view(row[off:off + n], shape).copy_(sd[name].detach())
         if self.padded > self.numel:
