@@ -47,7 +47,7 @@ def close_all() -> None:
 def bankable(sim) -> Optional[str]:
     """``None`` if :class:`LinearBank` can execute ``sim``; otherwise the reason it cannot."""
     from ..model.handler import AdaLineHandler
-    from ..node import GossipNode, PassThroughNode
+    from ..node import CacheNeighNode, GossipNode, PassThroughNode
     from ..parallel import runtime as prt
     if prt.active() and prt.transport() != "p2p":
         return "several ranks without shared memory"
@@ -58,11 +58,13 @@ def bankable(sim) -> Optional[str]:
     if not isinstance(h0, AdaLineHandler):
         return "handler is not AdaLine/Pegasos"
     cls = type(nodes[0])
-    if cls is PassThroughNode and not getattr(nodes[0], "_keyed_draws", False):
-        return "pass-through nodes with host-stream draws"
+    if cls in (PassThroughNode, CacheNeighNode) and not getattr(nodes[0], "_keyed_draws", False):
+        return "node-side draws from the host stream"
+    if cls is CacheNeighNode and "_bank" not in sim.__dict__ and any(n.local_cache for n in nodes):
+        return "neighbour caches filled by another executor"
     for n in nodes:
         h = n.model_handler
-        if type(n) is not cls or cls not in (GossipNode, PassThroughNode):
+        if type(n) is not cls or cls not in (GossipNode, PassThroughNode, CacheNeighNode):
             return "node subclass"
         if type(h) is not type(h0) or h.learning_rate != h0.learning_rate or h.dim != h0.dim or h.mode != h0.mode:
             return "heterogeneous handlers"
@@ -144,6 +146,42 @@ class LinearBank:
             self.deg = np.asarray([int(sim.nodes[i].n_neighs) for i in ids], dtype=np.uint64)
             self.pt_count = np.asarray([int(getattr(sim.nodes[i], "_pt_draws", 0)) for i in ids], dtype=np.uint64)
             self.size_model += 1                    # the degree is one more atom on the wire
+        # CacheNeighNode (Giaretta 2019): received models are only stored, newest per sender; at a PUSH / PUSH_PULL send one
+        # cached model (keyed choice among the senders in the cache) is consumed before the snapshot (node.py::CacheNeighNode)
+        from ..node import CacheNeighNode
+        self.cacheneigh = type(sim.nodes[ids[0]]) is CacheNeighNode
+        if self.cacheneigh:
+            self.cn_cache: List[Dict[int, int]] = [dict() for _ in ids]      # node -> {sender: slot}
+            self.cn_count = [int(getattr(sim.nodes[i], "_cn_draws", 0)) for i in ids]
+
+    def _cn_store(self, recvs: np.ndarray, senders: np.ndarray, slots: np.ndarray) -> np.ndarray:
+        """Deliveries to cache-neighbour nodes: remember the slot, return the slots of the models they replace."""
+        stale, owners = [], []
+        for r, s, sl in zip(recvs.tolist(), senders.tolist(), slots.tolist()):
+            if sl < 0:
+                continue
+            old = self.cn_cache[r].get(s)
+            if old is not None:
+                stale.append(old)
+                owners.append(r)
+            self.cn_cache[r][s] = sl
+        self._cn_stale_nodes = np.asarray(owners, dtype=np.int64)      # (several ranks: a slot lives on its receiver's rank)
+        return np.asarray(stale, dtype=np.int64)
+
+    def _cn_pick(self, senders: np.ndarray, mtypes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Sends of cache-neighbour nodes: (nodes, slots) of the cached models consumed before the snapshots."""
+        from . import rng as _rng
+        nodes, slots = [], []
+        for a, mt in zip(senders.tolist(), mtypes.tolist()):
+            cache = self.cn_cache[a]
+            if mt == 2 or not cache:            # PULL requests do not consume
+                continue
+            keys = sorted(cache)
+            k = keys[_rng.derive(0x9A59, a, self.cn_count[a]) % len(keys)]
+            self.cn_count[a] += 1
+            nodes.append(a)
+            slots.append(cache.pop(k))
+        return np.asarray(nodes, dtype=np.int64), np.asarray(slots, dtype=np.int64)
 
     def _item_modes(self, recvs: np.ndarray, senders: np.ndarray, slots: np.ndarray) -> Optional[np.ndarray]:
         """Per delivered message: the bank's mode (merge) or 4 (PASS), from the receivers' keyed draws."""
@@ -446,6 +484,10 @@ class LinearBank:
             if m.any():
                 senders, mids, mtypes = ea[m], es[m], ex[m]
                 carries = mtypes != 2                                   # 2 = PULL request
+                if self.cacheneigh:                                     # consume one cached model before the snapshot
+                    cn_nodes, cn_slots = self._cn_pick(senders, mtypes)
+                    self._deliver(cn_nodes, cn_slots)
+                    self._release(cn_slots)
                 slots = np.full(senders.size, -1, dtype=np.int64)
                 slots[carries] = self._alloc(int(carries.sum()))
                 self.slot_map[mids % _RING] = slots
@@ -466,11 +508,14 @@ class LinearBank:
                     pos_in = np.searchsorted(req_ids[srt], mids[has_reply])
                     rep_of = np.full(mids.size, -1, dtype=np.int64)
                     rep_of[has_reply] = rep_ids[srt][pos_in]
-                for idx in self._waves(recv):
+                for idx in ([np.arange(recv.size)] if self.cacheneigh else self._waves(recv)):
                     r_w, mid_w = recv[idx], mids[idx]
                     s_w = self.slot_map[mid_w % _RING].copy()
-                    self._deliver(r_w, s_w, self._item_modes(r_w, origin[idx], s_w))
-                    self._release(s_w)
+                    if self.cacheneigh:                                 # only stored (newest per sender)
+                        self._release(self._cn_store(r_w, origin[idx], s_w))
+                    else:
+                        self._deliver(r_w, s_w, self._item_modes(r_w, origin[idx], s_w))
+                        self._release(s_w)
                     if rep_of is not None:
                         sel = has_reply[idx]
                         if sel.any():
@@ -483,10 +528,13 @@ class LinearBank:
                 recv, repl, mids = ea[m], eb[m], es[m]
                 counters["sent"] += int(recv.size)
                 counters["sent_size"] += int(recv.size) * self.size_model
-                for idx in self._waves(recv):
+                for idx in ([np.arange(recv.size)] if self.cacheneigh else self._waves(recv)):
                     s_w = self.slot_map[mids[idx] % _RING].copy()
-                    self._deliver(recv[idx], s_w, self._item_modes(recv[idx], repl[idx], s_w))
-                    self._release(s_w)
+                    if self.cacheneigh:
+                        self._release(self._cn_store(recv[idx], repl[idx], s_w))
+                    else:
+                        self._deliver(recv[idx], s_w, self._item_modes(recv[idx], repl[idx], s_w))
+                        self._release(s_w)
             # ---- losses: free the snapshot -------------------------------------------------------------
             m = k == C.EV_DROP
             if m.any():
@@ -515,6 +563,11 @@ class LinearBank:
             if m.any():
                 senders, recvs, mids, mtypes = ea[m], eb[m], es[m], ex[m]
                 carries = mtypes != 2
+                if self.cacheneigh:
+                    cn_nodes, cn_slots = self._cn_pick(senders, mtypes)
+                    if cn_nodes.size:
+                        self._deliver_multi(cn_nodes, cn_slots)
+                        self._release_multi(cn_slots, own[cn_nodes])
                 dst = own[recvs]
                 slots = np.full(senders.size, -1, dtype=np.int64)
                 if carries.any():
@@ -537,11 +590,15 @@ class LinearBank:
                     pos_in = np.searchsorted(req_ids[srt], mids[has_reply])
                     rep_of = np.full(mids.size, -1, dtype=np.int64)
                     rep_of[has_reply] = rep_ids[srt][pos_in]
-                for idx in self._waves(recv):
+                for idx in ([np.arange(recv.size)] if self.cacheneigh else self._waves(recv)):
                     r_w, mid_w = recv[idx], mids[idx]
                     s_w = self.slot_map[mid_w % _RING].copy()
-                    self._deliver_multi(r_w, s_w, self._item_modes(r_w, origin[idx], s_w))
-                    self._release_multi(s_w, own[r_w])
+                    if self.cacheneigh:
+                        stale = self._cn_store(r_w, origin[idx], s_w)
+                        self._release_multi(stale, own[self._cn_stale_nodes])
+                    else:
+                        self._deliver_multi(r_w, s_w, self._item_modes(r_w, origin[idx], s_w))
+                        self._release_multi(s_w, own[r_w])
                     if rep_of is not None:
                         sel = has_reply[idx]
                         if sel.any():
@@ -556,10 +613,14 @@ class LinearBank:
                 recv, repl, mids = ea[m], eb[m], es[m]
                 counters["sent"] += int(recv.size)
                 counters["sent_size"] += int(recv.size) * self.size_model
-                for idx in self._waves(recv):
+                for idx in ([np.arange(recv.size)] if self.cacheneigh else self._waves(recv)):
                     s_w = self.slot_map[mids[idx] % _RING].copy()
-                    self._deliver_multi(recv[idx], s_w, self._item_modes(recv[idx], repl[idx], s_w))
-                    self._release_multi(s_w, own[recv[idx]])
+                    if self.cacheneigh:
+                        stale = self._cn_store(recv[idx], repl[idx], s_w)
+                        self._release_multi(stale, own[self._cn_stale_nodes])
+                    else:
+                        self._deliver_multi(recv[idx], s_w, self._item_modes(recv[idx], repl[idx], s_w))
+                        self._release_multi(s_w, own[recv[idx]])
             m = k == C.EV_DROP
             if m.any():
                 counters["failed"] += int(m.sum())
@@ -640,9 +701,23 @@ class LinearBank:
         keep = slots >= 0
         ids, slots = ids[keep], slots[keep]
         idx = torch.as_tensor(slots, dtype=torch.int64, device=self.device)
-        return {"ids": ids, "rows": self.S[idx].cpu(), "ages": self.slot_age[idx].cpu()}
+        out = {"ids": ids, "rows": self.S[idx].cpu(), "ages": self.slot_age[idx].cpu()}
+        if self.cacheneigh:                 # models waiting in the neighbour caches are state as well
+            ent = [(n, s, sl) for n, cache in enumerate(self.cn_cache) for s, sl in sorted(cache.items())]
+            cidx = torch.as_tensor([e[2] for e in ent], dtype=torch.int64, device=self.device)
+            out["cn"] = {"nodes": [e[0] for e in ent], "senders": [e[1] for e in ent],
+                         "rows": self.S[cidx].cpu(), "ages": self.slot_age[cidx].cpu()}
+        return out
 
     def import_inflight(self, st: Dict[str, Any]) -> None:
+        cn = st.get("cn")
+        if cn is not None and len(cn["nodes"]):
+            slots = self._alloc(len(cn["nodes"]))
+            idx = torch.as_tensor(slots, dtype=torch.int64, device=self.device)
+            self.S[idx] = cn["rows"].to(self.device)
+            self.slot_age[idx] = cn["ages"].to(self.device)
+            for n, s, sl in zip(cn["nodes"], cn["senders"], slots.tolist()):
+                self.cn_cache[n][s] = sl
         ids = np.asarray(st["ids"], dtype=np.int64)
         if ids.size == 0:
             return
@@ -669,5 +744,7 @@ class LinearBank:
             h._version += 1
             if self.passthrough:
                 node._pt_draws = int(self.pt_count[i])
+            if self.cacheneigh:
+                node._cn_draws = int(self.cn_count[i])
         if self.multi:
             self.age.copy_(age)

@@ -211,7 +211,15 @@ class CacheNeighNode(GossipNode):
 
     def send(self, t: int, peer: int, protocol: AntiEntropyProtocol) -> Message:
         if protocol in (AntiEntropyProtocol.PUSH, AntiEntropyProtocol.PUSH_PULL) and self.local_cache:
-            k = random.choice(sorted(self.local_cache.keys()))
+            keys = sorted(self.local_cache.keys())
+            if getattr(self, "_keyed_draws", False):
+                # native engine: keyed by (node, number of choices so far) so that the banked engine reproduces it
+                from .engine import rng as _rng
+                n_draws = int(getattr(self, "_cn_draws", 0))
+                self._cn_draws = n_draws + 1
+                k = keys[_rng.derive(0x9A59, self.idx, n_draws) % len(keys)]
+            else:
+                k = random.choice(keys)
             cached = CACHE.pop(self.local_cache.pop(k))
             self.model_handler(cached, self.data[0])
             _release(cached)

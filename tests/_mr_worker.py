@@ -34,7 +34,7 @@ def build(kind, device):
         nodes = GossipNode.generate(disp, StaticP2PNetwork(8), proto, 20, False)
         sim = GossipSimulator(nodes, disp, 20, AntiEntropyProtocol.PUSH, drop_prob=.1, online_prob=.8,
                               delay=UniformDelay(0, 3), sampling_eval=.5)
-    elif kind in ("bank_pegasos", "bank_adaline_pushpull", "bank_passthrough"):
+    elif kind in ("bank_pegasos", "bank_adaline_pushpull", "bank_passthrough", "bank_cacheneigh"):
         # the banked engine (engine/bank.py): one node per few samples, many nodes per launch; several ranks push
         # snapshots into the receiver rank's slot bank
         from gossipy_b200.model.handler import AdaLineHandler
@@ -42,7 +42,7 @@ def build(kind, device):
         ytr, yte = 2 * ytr - 1, 2 * yte - 1
         n = 45 if kind == "bank_pegasos" else 30
         disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
-        if kind in ("bank_pegasos", "bank_passthrough"):
+        if kind in ("bank_pegasos", "bank_passthrough", "bank_cacheneigh"):
             proto = PegasosHandler(AdaLine(57), 0.01, CreateModelMode.MERGE_UPDATE)
             kws, prt_ = dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 3), sampling_eval=.3), AntiEntropyProtocol.PUSH
         else:
@@ -56,6 +56,9 @@ def build(kind, device):
                 if i % 3 == 0 and i:
                     A[i, 0] = A[0, i] = 1
             nodes = PassThroughNode.generate(disp, StaticP2PNetwork(n, A), proto, 10, True)
+        elif kind == "bank_cacheneigh":      # one cache slot per neighbour, consumed at send time
+            from gossipy_b200.node import CacheNeighNode
+            nodes = CacheNeighNode.generate(disp, StaticP2PNetwork(n), proto, 10, True)
         else:
             nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, kind == "bank_pegasos")
         sim = GossipSimulator(nodes, disp, 10, prt_, **kws)

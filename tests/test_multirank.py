@@ -106,7 +106,7 @@ def test_symmetric_arenas_grow_when_they_run_out():
     _compare(single, _run(2, "cpu", kinds=kinds, arena_rows=4), rel=1e-5)
 
 
-BKINDS = "bank_pegasos,bank_adaline_pushpull,bank_passthrough"
+BKINDS = "bank_pegasos,bank_adaline_pushpull,bank_passthrough,bank_cacheneigh"
 
 
 def test_banked_engine_two_and_three_ranks_cpu_equal_single_process():

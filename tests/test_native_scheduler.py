@@ -142,7 +142,7 @@ def test_scheduler_event_stream_invariants():
 # the per-event executor
 # ---------------------------------------------------------------------------------------------
 def _linear_sim(batched, protocol, mode, handler="pegasos", n=40, rounds=6, device="cpu", faults=True, sync=False,
-                passthrough=False):
+                passthrough=False, cacheneigh=False):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork, UniformDelay
     from gossipy_b200.data import DataDispatcher, synthetic
@@ -158,7 +158,10 @@ def _linear_sim(batched, protocol, mode, handler="pegasos", n=40, rounds=6, devi
     disp = DataDispatcher(ClassificationDataHandler(Xtr, 2 * ytr - 1, Xte, 2 * yte - 1), n=n, eval_on_user=False)
     cls = PegasosHandler if handler == "pegasos" else AdaLineHandler
     proto = cls(AdaLine(57), .01 if handler == "pegasos" else .001, getattr(CreateModelMode, mode))
-    if passthrough:                 # degree-aware pass-through on a topology with unequal degrees (ring + hub)
+    if cacheneigh:
+        from gossipy_b200.node import CacheNeighNode
+        nodes = CacheNeighNode.generate(disp, StaticP2PNetwork(n), proto, 10, sync)
+    elif passthrough:               # degree-aware pass-through on a topology with unequal degrees (ring + hub)
         from gossipy_b200.node import PassThroughNode
         A = np.zeros((n, n), dtype=int)
         for i in range(n):
@@ -219,6 +222,27 @@ def test_banked_pass_through_nodes_equal_per_event_execution(protocol, mode):
     g.CACHE.clear()
 
 
+@pytest.mark.parametrize("protocol,mode", [("PUSH", "MERGE_UPDATE"), ("PUSH_PULL", "MERGE_UPDATE"), ("PUSH", "UPDATE")])
+def test_banked_cache_neighbour_nodes_equal_per_event_execution(protocol, mode):
+    """CacheNeighNode (reference node.py:395-496) in the banked engine: deliveries are stored per sender, one cached
+    model (keyed choice) is consumed before every PUSH / PUSH_PULL send."""
+    import gossipy_b200 as g
+    rep_a, rows_a, ages_a, sim_a = _linear_sim(False, protocol, mode, cacheneigh=True)
+    rep_b, rows_b, ages_b, sim_b = _linear_sim(True, protocol, mode, cacheneigh=True)
+    assert "_bank" not in sim_a.__dict__ and "_bank" in sim_b.__dict__
+    assert (rep_a._sent_messages, rep_a._failed_messages, rep_a._total_size) == \
+        (rep_b._sent_messages, rep_b._failed_messages, rep_b._total_size)
+    draws_a = [getattr(nd, "_cn_draws", 0) for nd in sim_a.nodes.values()]
+    assert draws_a == [getattr(nd, "_cn_draws", 0) for nd in sim_b.nodes.values()] and sum(draws_a) > 0
+    assert ages_a == ages_b
+    torch.testing.assert_close(rows_a, rows_b, rtol=1e-4, atol=1e-5)
+    ev_a, ev_b = rep_a.get_evaluation(False), rep_b.get_evaluation(False)
+    for (t1, m1), (t2, m2) in zip(ev_a, ev_b):
+        for k in m1:
+            assert m1[k] == pytest.approx(m2[k], abs=1e-4), k
+    g.CACHE.clear()
+
+
 def test_bank_falls_back_when_not_bankable():
     from gossipy_b200.engine.bank import bankable
     rep, _, sim = _sim("native", __import__("gossipy_b200").core.AntiEntropyProtocol.PUSH, n=5, rounds=2)
@@ -229,13 +253,13 @@ def test_bank_falls_back_when_not_bankable():
 # checkpoint / resume under the native engine: the scheduler's dynamic state and the in-flight
 # snapshots are part of the checkpoint, so an interrupted run continues on the identical schedule
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("batched", [False, True])
-def test_native_checkpoint_resume_is_exact(batched, tmp_path):
+@pytest.mark.parametrize("batched,variant", [(False, {}), (True, {}), (True, {"cacheneigh": True}), (True, {"passthrough": True})])
+def test_native_checkpoint_resume_is_exact(batched, variant, tmp_path):
     import gossipy_b200 as g
     from gossipy_b200.simul import GossipSimulator
-    rep_full, rows_full, ages_full, _ = _linear_sim(batched, "PUSH_PULL", "MERGE_UPDATE", rounds=6)
+    rep_full, rows_full, ages_full, _ = _linear_sim(batched, "PUSH_PULL", "MERGE_UPDATE", rounds=6, **variant)
     g.CACHE.clear()
-    rep_a, _, _, sim = _linear_sim(batched, "PUSH_PULL", "MERGE_UPDATE", rounds=3)
+    rep_a, _, _, sim = _linear_sim(batched, "PUSH_PULL", "MERGE_UPDATE", rounds=3, **variant)
     assert sim._scheduler.pending > 0          # delays up to 3 ticks: messages are on the wire at the cut
     path = str(tmp_path / "ckpt.pkl")
     sim.save(path)
