@@ -34,7 +34,7 @@ def ours(a):
     from gossipy_b200.data.handler import ClassificationDataHandler
     from gossipy_b200.model.handler import PegasosHandler
     from gossipy_b200.model.nn import AdaLine
-    from gossipy_b200.node import GossipNode
+    from gossipy_b200.node import CacheNeighNode, GossipNode, PassThroughNode
     from gossipy_b200.simul import GossipSimulator, SimulationReport
     g.LOG.setLevel(50)
     dev = a.device
@@ -43,7 +43,24 @@ def ours(a):
     Xtr, ytr, Xte, yte = data(a.nodes)
     disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), eval_on_user=False, auto_assign=True)
     proto = PegasosHandler(AdaLine(57), .01, CreateModelMode.MERGE_UPDATE)
-    nodes = GossipNode.generate(disp, StaticP2PNetwork(disp.size()), proto, 100, False)
+    node_cls = {"gossip": GossipNode, "passthrough": PassThroughNode, "cacheneigh": CacheNeighNode}[a.node]
+    topo = StaticP2PNetwork(disp.size())
+    if a.node == "passthrough":             # main_giaretta_2019: Barabasi-Albert graph (unequal degrees), m = 10
+        rng = np.random.default_rng(7)
+        n, m_ = disp.size(), 10
+        A = np.zeros((n, n), dtype=np.int8)
+        deg = np.zeros(n)
+        for i in range(m_ + 1):
+            for j in range(i):
+                A[i, j] = A[j, i] = 1
+        deg[:m_ + 1] = m_
+        for i in range(m_ + 1, n):
+            tgt = rng.choice(i, size=m_, replace=False, p=deg[:i] / deg[:i].sum())
+            A[i, tgt] = A[tgt, i] = 1
+            deg[tgt] += 1
+            deg[i] = m_
+        topo = StaticP2PNetwork(n, A)
+    nodes = node_cls.generate(disp, topo, proto, 100, False)
     sim = GossipSimulator(nodes, disp, 100, AntiEntropyProtocol.PUSH, delay=UniformDelay(0, 10), online_prob=.2,
                           drop_prob=.1, sampling_eval=.1)
     sim.progress = False
@@ -61,7 +78,7 @@ def ours(a):
     sec = time.perf_counter() - t0
     from gossipy_b200 import ops
     ev = rep.get_evaluation(False)
-    return {"impl": a.impl, "device": dev, "nodes": disp.size(), "rounds": a.rounds, "rounds_per_s": a.rounds / sec,
+    return {"impl": a.impl, "node_class": a.node, "banked": "_bank" in sim.__dict__, "device": dev, "nodes": disp.size(), "rounds": a.rounds, "rounds_per_s": a.rounds / sec,
             "ms_per_round": sec / a.rounds * 1e3, "last_eval": {k: round(v, 4) for k, v in ev[-1][1].items()},
             "sent": rep._sent_messages, "failed": rep._failed_messages, "native_launches": ops.launch_count}
 
@@ -124,5 +141,7 @@ if __name__ == "__main__":
     ap.add_argument("--rounds", type=int, default=20)
     ap.add_argument("--impl", default="banked", choices=["banked", "events", "python", "reference"])
     ap.add_argument("--device", default="cuda:0" if torch.cuda.is_available() else "cpu")
+    ap.add_argument("--node", default="gossip", choices=["gossip", "passthrough", "cacheneigh"],
+                    help="node class (the three variants of the reference's main_giaretta_2019.py)")
     a = ap.parse_args()
     print(json.dumps(reference(a) if a.impl == "reference" else ours(a)))
