@@ -121,6 +121,15 @@ at::Tensor keyed_perm(int64_t n, int64_t key, at::Device device) {
     return out;
 }
 
+at::Tensor keyed_randint(int64_t k, int64_t n, int64_t key, at::Device device) {
+    TORCH_CHECK(device.is_cuda() && k >= 0 && n > 0);
+    c10::cuda::CUDAGuard guard(device);
+    at::Tensor out = at::empty({k}, at::TensorOptions().device(device).dtype(at::kLong));
+    launch_keyed_randint(out.data_ptr<int64_t>(), k, n, (uint64_t)key, cur_stream());
+    GB_LAUNCH_CHECK();
+    return out;
+}
+
 void adam_step(at::Tensor p, at::Tensor g, int64_t n, at::Tensor m, at::Tensor v, int64_t step,
                double lr, double beta1, double beta2, double eps, double wd, bool decoupled) {
     check_row(p, "p"); check_row(g, "g"); check_row(m, "m"); check_row(v, "v");
@@ -561,6 +570,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgd_step", &gb::sgd_step);
     m.def("adam_step", &gb::adam_step);
     m.def("keyed_perm", &gb::keyed_perm);
+    m.def("keyed_randint", &gb::keyed_randint);
     m.def("mlp1_train", &gb::mlp1_train, py::arg("row"), py::arg("X"), py::arg("y"), py::arg("dims"),
           py::arg("batch_size"), py::arg("local_epochs"), py::arg("lr"), py::arg("wd"), py::arg("key"),
           py::arg("part_id") = py::none(), py::arg("ages") = py::none(), py::arg("impl") = "",

@@ -79,6 +79,7 @@ struct Node {
     int64_t model_msgs = 0;                 // model-carrying messages sent so far (keys the partition draw)
     float* scratch = nullptr;               // UPDATE_MERGE: private trainable copy of a received model
     uint64_t pt_draws = 0;                  // PassThroughNode: accept draws made so far (keys the next one)
+    int64_t* sample_idx = nullptr; float* sample_val = nullptr;   // SamplingTMH: the coordinate sample and its merged values
     // snapshot elision: a message whose delivery provably precedes this node's next write travels as a reference to the
     // LIVE row (`alias.data == row`), no copy.  0 = none, 1 = on the wire, 2 = read: the next write waits for `alias.read`
     Slot alias; int alias_state = 0;
@@ -143,6 +144,13 @@ public:
         for (size_t i = 0; i < nodes_.size(); ++i) nodes_[i].pt_draws = (uint64_t)draws[i];
     }
     std::vector<int64_t> pt_draws() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back((int64_t)n.pt_draws); return v; }
+    // SamplingBasedNode + SamplingTMH (MERGE_UPDATE): the receiver draws k coordinates (keyed, with replacement), merges only
+    // those, then trains (model/handler.py::SamplingTMH, node.py::SamplingBasedNode)
+    void set_sampling(int64_t k, int64_t n_params) { sample_k_ = k; n_params_ = n_params; }
+    void set_node_sample_buffers(int i, uintptr_t idx, uintptr_t val) {
+        nodes_.at(i).sample_idx = reinterpret_cast<int64_t*>(idx); nodes_.at(i).sample_val = reinterpret_cast<float*>(val);
+    }
+    void set_sample_merge_callback(py::function f) { cb_sample_merge_ = std::move(f); }
     void set_node_scratch(int i, uintptr_t scratch) { nodes_.at(i).scratch = reinterpret_cast<float*>(scratch); }
     void set_update_merge_callback(py::function f) { cb_update_merge_ = std::move(f); }
     void set_node_data(int i, uintptr_t X, uintptr_t y, int n) {       // streamed inputs: the buffers alternate per round
@@ -486,7 +494,7 @@ private:
         }
         // fused MERGE_UPDATE of the MLP: the operand loader of the training kernel does not depend on the incoming model,
         // so it is issued BEFORE this stream waits for the snapshot (off the critical path of a gossip chain)
-        const bool hoist = exec && cuda_ && !remote && sl.written && n_parts_ == 0 && mode == 2 && family_ == 0;
+        const bool hoist = exec && cuda_ && !remote && sl.written && n_parts_ == 0 && sample_k_ == 0 && mode == 2 && family_ == 0;
         if (!hoist) reader_done();
         if (exec && cuda_) {
             if (remote) sync = PeerSync{sl.ready, sl.gen, sl.done, device_fault_word()};
@@ -515,6 +523,30 @@ private:
             const int st = steps_of(nd);
             for (int64_t& v : nd.ages_v) v += st;
             nd.age += (int64_t)st * n_parts_;
+        } else if (sample_k_ > 0) {                        // sampled MERGE_UPDATE: merge k keyed coordinates, then train
+            nd.counter += 1;                               // SamplingTMH.draw_sample consumes one update key ...
+            uint64_t h = mix64(seed_);
+            const uint64_t parts[3] = {0x5A3Full, (uint64_t)node, key_of(node, nd) & 0xFFFFFFFFull};
+            for (uint64_t p : parts) h = mix64(h ^ p);
+            const uint64_t key_s = h & ((1ull << 63) - 1);
+            if (exec) {
+                if (cuda_) {
+                    if (nd.sample_idx == nullptr) throw std::runtime_error("sampling needs per-node sample buffers");
+                    launch_keyed_randint(nd.sample_idx, sample_k_, n_params_, key_s, nd.stream);
+                    launch_merge_indexed(nd.row, sl.data, nd.sample_idx, sample_k_, .5f, .5f, nd.sample_val, sync, nd.stream);
+                } else {
+                    cb_sample_merge_(node, rk, s, (int64_t)key_s, (int64_t)sl.gen);
+                }
+                launches_ += 3;
+            }
+            nd.counter += 1;                               // ... and the local update the next one
+            const uint64_t key = key_of(node, nd);
+            if (exec) {
+                if (cuda_) train(nd, nullptr, 1.f, 0.f, key, PeerSync{nullptr, 0, nullptr, nullptr});
+                else cb_train_(node, rk, -1, (int64_t)key, 1.f, 0.f, (int64_t)sl.gen);
+                ++launches_;
+            }
+            nd.age += steps_of(nd);
         } else if (mode == 3) {
             // UPDATE_MERGE (model/handler.py::__call__, reference handler.py:129-132): update the own model, update a
             // private copy of the received one on the own data (keyed like the Python scratch copy: this node, the
@@ -597,7 +629,8 @@ private:
     std::vector<std::vector<Slot>> pools_;          // per owner rank
     std::vector<std::deque<int>> free_;             // FIFO: a slot is reused as late as possible (see snapshot())
     std::unordered_map<int32_t, std::pair<int, int>> inflight_;     // message id -> (rank, slot)
-    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_merge_;
+    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_merge_, cb_sample_merge_;
+    int64_t sample_k_ = 0, n_params_ = 0;            // SamplingTMH: sample size (0 = whole-model merges)
     int n_parts_ = 0; const int64_t* part_id_ = nullptr;
     std::vector<int64_t> deg_;                       // PassThroughNode: node degrees (empty = plain nodes)
     std::vector<uintptr_t> seg_ptrs_; std::vector<int> seg_counts_;
@@ -617,6 +650,9 @@ void bind_executor(py::module_& m) {
         .def("set_node", &StreamExecutor::set_node)
         .def("set_node_data", &StreamExecutor::set_node_data)
         .def("set_node_scratch", &StreamExecutor::set_node_scratch)
+        .def("set_sampling", &StreamExecutor::set_sampling)
+        .def("set_node_sample_buffers", &StreamExecutor::set_node_sample_buffers)
+        .def("set_sample_merge_callback", &StreamExecutor::set_sample_merge_callback)
         .def("set_passthrough", &StreamExecutor::set_passthrough)
         .def("pt_draws", &StreamExecutor::pt_draws)
         .def("set_update_merge_callback", &StreamExecutor::set_update_merge_callback)

@@ -51,6 +51,8 @@ void preload_nvls();
 // ---- optim.cu ------------------------------------------------------------------------------------
 // out[i] = keyed permutation of range(n) at i (the order in which the fused kernels and the oracle visit the samples)
 void launch_keyed_perm(int64_t* out, int n, uint64_t key, cudaStream_t stream);
+// out[i] = mix64(key ^ i) % n, i < k: k keyed draws from range(n) WITH replacement (SamplingTMH's coordinate sample)
+void launch_keyed_randint(int64_t* out, int64_t k, int64_t n, uint64_t key, cudaStream_t stream);
 void launch_sgd(float* p, const float* g, int64_t n, float lr, float wd, float momentum, float* buf,
                 float dampening, bool nesterov, bool first, const float* scale, cudaStream_t stream);
 void launch_adam(float* p, const float* g, int64_t n, float* m, float* v, int64_t step, float lr,

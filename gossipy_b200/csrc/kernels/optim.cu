@@ -80,6 +80,15 @@ __global__ void keyed_perm_kernel(int64_t* __restrict__ out, int n, uint64_t key
     GbPerm perm; perm.init((uint32_t)n, key);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (int64_t)perm((uint32_t)i);
 }
+// k keyed draws from range(n) with replacement (model/handler.py::SamplingTMH.draw_sample, ops/torch_ref.py::keyed_randint)
+__global__ void keyed_randint_kernel(int64_t* __restrict__ out, int64_t k, uint64_t n, uint64_t key) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (int64_t)(gb_mix64(key ^ (uint64_t)i) % n);
+}
+void launch_keyed_randint(int64_t* out, int64_t k, int64_t n, uint64_t key, cudaStream_t stream) {
+    if (k <= 0 || n <= 0) return;
+    keyed_randint_kernel<<<(int)std::min<int64_t>(1024, (k + 255) / 256), 256, 0, stream>>>(out, k, (uint64_t)n, key);
+}
 void launch_keyed_perm(int64_t* out, int n, uint64_t key, cudaStream_t stream) {
     if (n <= 0) return;
     keyed_perm_kernel<<<std::min(1024, (n + 255) / 256), 256, 0, stream>>>(out, n, key);

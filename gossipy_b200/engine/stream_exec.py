@@ -48,21 +48,24 @@ def eligible(sim: Any) -> Optional[str]:
     ids = sorted(sim.nodes)
     if ids != list(range(len(ids))):
         return "node ids must be 0..N-1"
-    from ..node import PartitioningBasedNode, PassThroughNode
+    from ..node import PartitioningBasedNode, PassThroughNode, SamplingBasedNode
     ref = None
     cls0 = type(sim.nodes[ids[0]])
     for i in ids:
         node = sim.nodes[i]
         h = node.model_handler
         partitioned = type(node) is PartitioningBasedNode and type(h) is H.PartitionedTMH
+        sampled = type(node) is SamplingBasedNode and type(h) is H.SamplingTMH
         if type(node) is not cls0:
             return "mixed node classes"
-        if type(node) not in (GossipNode, PassThroughNode) and not partitioned:
+        if type(node) not in (GossipNode, PassThroughNode) and not partitioned and not sampled:
             return "node class %s" % type(node).__name__
         if type(node) is PassThroughNode and not getattr(node, "_keyed_draws", False):
             return "pass-through nodes with host-stream draws"
-        if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH) and not partitioned:
+        if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH) and not partitioned and not sampled:
             return "handler class %s" % type(h).__name__
+        if sampled and h.mode != CreateModelMode.MERGE_UPDATE:
+            return "sampled models: mode %s" % h.mode.name
         if not h._fused or h.layout.int_buffers:
             return "handler is not on the fused kernel path"
         if partitioned:
@@ -77,7 +80,7 @@ def eligible(sim: Any) -> Optional[str]:
             return "vector-valued model age"
         sig = (h._family, h.batch_size, h.local_epochs, float(h.optimizer_params.get("lr", 1e-3)),
                float(h.optimizer_params.get("weight_decay", 0.0)), h._row_numel, type(h), h.mode,
-               getattr(h, "L", None), h.tm_partition.n_parts if partitioned else 0)
+               getattr(h, "L", None), h.tm_partition.n_parts if partitioned else 0, getattr(h, "sample_size", None))
         if ref is None:
             ref = sig
         elif sig != ref:
@@ -145,6 +148,19 @@ class StreamExec:
             self.ex.set_callbacks(self._cb_snapshot, self._cb_train, self._cb_adopt)
         from ..node import PassThroughNode
         self.passthrough = type(sim.nodes[ids[0]]) is PassThroughNode
+        self.sample_k = 0
+        if type(h0).__name__ == "SamplingTMH":          # the receiver merges k keyed coordinates (with replacement), then trains
+            from ..model.sampling import TorchModelSampling
+            self.n_params = int(h0.layout.n_params)
+            self.sample_k = int(TorchModelSampling.sample_size(h0.sample_size, self.n_params))
+            self.ex.set_sampling(self.sample_k, self.n_params)
+            mine = [i for i in ids if self.owner[i] == self.rank]
+            self._samp_idx = torch.zeros(max(1, len(mine)), self.sample_k, dtype=torch.int64, device=self.device)
+            self._samp_val = torch.zeros(max(1, len(mine)), self.sample_k, dtype=torch.float32, device=self.device)
+            for k_, i in enumerate(mine):
+                self.ex.set_node_sample_buffers(i, self._samp_idx[k_].data_ptr(), self._samp_val[k_].data_ptr())
+            if not self.cuda:
+                self.ex.set_sample_merge_callback(self._cb_sample_merge)
         self._scratch = None
         if h0.mode == CreateModelMode.UPDATE_MERGE:      # one private row per node of this rank for the copy that is trained
             mine = [i for i in ids if self.owner[i] == self.rank]
@@ -291,6 +307,11 @@ class StreamExec:
         fn(tmp, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key_tmp), None)
         if w_peer != 0.0:
             ops.merge_pair(h.row, tmp, float(w_self), float(w_peer))
+
+    def _cb_sample_merge(self, node: int, rank: int, slot: int, key: int, gen: int) -> None:
+        src, sync = self._slot(rank, slot, gen)
+        idx = ops.keyed_randint(self.sample_k, self.n_params, int(key), self.device)
+        ops.merge_indexed(self.sim.nodes[node].model_handler.row, src, idx, 0.5, 0.5, sync)
 
     def _cb_merge_part(self, node: int, rank: int, slot: int, pid: int, w1: float, w2: float, gen: int) -> None:
         src, sync = self._slot(rank, slot, gen)

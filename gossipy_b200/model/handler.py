@@ -1347,10 +1347,11 @@ class SamplingTMH(TorchModelHandler):
 
     def draw_sample(self) -> torch.Tensor:
         """Flat positions to merge, generated on the handler's device."""
-        gen = torch.Generator(device=self.device)
-        gen.manual_seed(_rng.derive(0x5A3F, max(self.owner, 0), self._next_key() & 0xFFFFFFFF))
-        return TorchModelSampling.sample_flat(self.sample_size, self.layout.n_params,
-                                              device=self.device, generator=gen)
+        key = _rng.derive(0x5A3F, max(self.owner, 0), self._next_key() & 0xFFFFFFFF)
+        k = TorchModelSampling.sample_size(self.sample_size, self.layout.n_params)
+        # counter-based draws (uniform with replacement, like ``sample_flat``): the same sample on every device, and
+        # reproducible by the C++ executor
+        return ops.keyed_randint(k, self.layout.n_params, key, self.device)
 
     def _merge(self, other_model_handler: "SamplingTMH", sample: Any) -> None:
         if isinstance(sample, dict):

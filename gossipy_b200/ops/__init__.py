@@ -175,6 +175,18 @@ def keyed_perm(n: int, key: int, device: Any) -> torch.Tensor:
     return torch.from_numpy(torch_ref.perm_indices(n, key)).to(device)
 
 
+def keyed_randint(k: int, n: int, key: int, device: Any) -> torch.Tensor:
+    """``k`` keyed draws from ``range(n)`` with replacement (the coordinate sample of ``SamplingTMH``), on ``device``;
+    the same values on every device and in the C++ executor."""
+    device = torch.device(device)
+    if device.type == "cuda" and native_available():
+        kk = int(key) & ((1 << 64) - 1)
+        out = native().keyed_randint(int(k), int(n), kk - (1 << 64) if kk >= (1 << 63) else kk, device)
+        _count()
+        return out
+    return torch.from_numpy(torch_ref.keyed_randint(int(k), int(n), int(key))).to(device)
+
+
 MergeFrom = Tuple[torch.Tensor, float, float, Optional[RowSync]]   # (peer row, w_self, w_peer, sync)
 TRAIN_IMPL = ""   # process-wide choice of the fused MLP training kernel, see set_train_impl()
 TRAIN_IMPLS = ("", "auto", "tc8", "cluster", "tc8-tf32", "tc3")

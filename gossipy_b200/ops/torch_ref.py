@@ -53,6 +53,12 @@ def perm_indices(n: int, key: int) -> np.ndarray:
     return out.astype(np.int64)
 
 
+def keyed_randint(k: int, n: int, key: int) -> np.ndarray:
+    """``k`` keyed draws from ``range(n)`` with replacement: ``mix64(key ^ i) % n`` (mirrors ``keyed_randint_kernel``)."""
+    key = _U64(key & ((1 << 64) - 1))
+    return (_mix64_np(key ^ np.arange(k, dtype=np.uint64)) % _U64(n)).astype(np.int64)
+
+
 # --------------------------------------------------------------------------------------
 # merges on flat rows
 # --------------------------------------------------------------------------------------

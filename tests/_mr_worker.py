@@ -120,7 +120,7 @@ def build(kind, device):
         sim = GossipSimulator(nodes, disp, 10, prt_, delay=UniformDelay(0, 2))
         sim.engine = "native"
         sim.native_executor = True
-    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge", "x_passthrough"):
+    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge", "x_passthrough", "x_sampled"):
         # native engine + the C++ executor (csrc/exec): one executor per rank over the same event list
         if kind == "x_mlp_pushpull":
             (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
@@ -129,6 +129,12 @@ def build(kind, device):
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
             n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), LimitedMergeTMH, {"age_diff_threshold": 2}
             proto_, kws = AntiEntropyProtocol.PUSH, dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 2), sampling_eval=.5)
+        elif kind == "x_sampled":
+            from gossipy_b200.model.handler import SamplingTMH
+            from gossipy_b200.node import SamplingBasedNode
+            (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+            n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), (lambda *a, **k: SamplingTMH(.3, *a, **k)), {}
+            proto_, kws = AntiEntropyProtocol.PUSH_PULL, dict(delay=UniformDelay(0, 2))
         elif kind == "x_passthrough":
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
             n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), TorchModelHandler, {}
@@ -151,6 +157,8 @@ def build(kind, device):
                 if i > 1:
                     A[i, 0] = A[0, i] = 1
             nodes = PassThroughNode.generate(disp, StaticP2PNetwork(n, A), proto, 10, True)
+        elif kind == "x_sampled":
+            nodes = SamplingBasedNode.generate(disp, StaticP2PNetwork(n), proto, 10, True)
         else:
             nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, kind != "x_limited_push")
         sim = GossipSimulator(nodes, disp, 10, proto_, **kws)

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.skipif(not native_available(), reason="extension not bu
 
 
 def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=4, device="cpu", sync=True, start=True,
-         mode="MERGE_UPDATE", limited=None, tokenized=False, partitioned=0, passthrough=False):
+         mode="MERGE_UPDATE", limited=None, tokenized=False, partitioned=0, passthrough=False, sampled=0.0):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork, UniformDelay
     from gossipy_b200.data import DataDispatcher, synthetic
@@ -42,6 +42,11 @@ def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=
         proto = PartitionedTMH(net, TorchModelPartition(net, partitioned), torch.optim.SGD, {"lr": .5, "weight_decay": .001},
                                torch.nn.CrossEntropyLoss(), **kwh)
         node_cls = PartitioningBasedNode
+    elif sampled:
+        from gossipy_b200.model.handler import SamplingTMH
+        from gossipy_b200.node import SamplingBasedNode
+        proto = SamplingTMH(sampled, net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), **kwh)
+        node_cls = SamplingBasedNode
     elif limited is not None:
         proto = LimitedMergeTMH(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(),
                                 age_diff_threshold=limited, **kwh)
@@ -156,6 +161,20 @@ def test_native_executor_pass_through_nodes(kw):
     _same(sim_a, rep_a, sim_b, rep_b)
     draws = [getattr(nd, "_pt_draws", 0) for nd in sim_a.nodes.values()]
     assert draws == [getattr(nd, "_pt_draws", 0) for nd in sim_b.nodes.values()] and sum(draws) > 0
+    g.CACHE.clear()
+
+
+@pytest.mark.parametrize("kw", [dict(model="logreg", protocol="PUSH", sampled=.3, faults=True),
+                                dict(model="mlp", protocol="PUSH_PULL", sampled=.1),
+                                dict(model="logreg", protocol="PULL", sampled=.5, faults=True, sync=False)])
+def test_native_executor_sampled_models(kw):
+    """SamplingBasedNode + SamplingTMH (reference node.py:499-562, handler.py:426-452) from C++: the receiver's keyed
+    coordinate sample (with replacement), indexed merge, local update."""
+    import gossipy_b200 as g
+    sim_a, rep_a = _sim(False, **kw)
+    sim_b, rep_b = _sim(True, **kw)
+    assert "_stream_exec" in sim_b.__dict__ and "_stream_exec" not in sim_a.__dict__
+    _same(sim_a, rep_a, sim_b, rep_b)
     g.CACHE.clear()
 
 
@@ -302,7 +321,8 @@ def test_native_executor_cuda_equals_python_executor():
         _same(sim_a, rep_a, sim_b, rep_b, tol=1e-6)
         g.CACHE.clear()
     for kw in (dict(model="mlp", protocol="PUSH_PULL", mode="UPDATE_MERGE"), dict(model="logreg", protocol="PUSH", mode="UPDATE_MERGE", limited=3, faults=True),
-               dict(model="mlp", protocol="PUSH", partitioned=4, faults=True)):
+               dict(model="mlp", protocol="PUSH", partitioned=4, faults=True), dict(model="mlp", protocol="PUSH_PULL", sampled=.2),
+               dict(model="logreg", protocol="PUSH", passthrough=True, faults=True)):
         sim_a, rep_a = _sim(False, n=8, rounds=4, device="cuda:0", **kw)
         sim_b, rep_b = _sim(True, n=8, rounds=4, device="cuda:0", **kw)
         torch.cuda.synchronize()
