@@ -57,13 +57,15 @@ inline uint64_t mix64(uint64_t x) {          // engine/rng.py::mix64
 }
 
 // event kinds / message types of csrc/sched/scheduler.cpp
-enum : int32_t { EV_SEND = 0, EV_DROP = 1, EV_DELIVER = 2, EV_REPLY_SEND = 3, EV_REPLY_DELIVER = 4, EV_EVAL = 5 };
+enum : int32_t { EV_SEND = 0, EV_DROP = 1, EV_DELIVER = 2, EV_REPLY_SEND = 3, EV_REPLY_DELIVER = 4, EV_EVAL = 5, EV_TIMEOUT = 7 };
 enum : int32_t { MT_PUSH = 1, MT_PULL = 2, MT_REPLY = 3, MT_PUSH_PULL = 4 };
 
 struct Slot {
     int64_t age = 0;
     int64_t counter = 0;                    // the sender's update counter at send time (UPDATE_MERGE keys the copy's update with it)
     int sender = -1;                        // PassThroughNode: the sender's degree rides along
+    int refs = 0;                           // all-to-all mode: messages in flight + cache entries that reference this snapshot
+    std::vector<cudaEvent_t> reads; int n_reads = 0;     // all-to-all mode: one event per same-rank reader of this life
     std::vector<int64_t> ages_v; int pid = 0;
     int state = 0;                          // debug mode: 0 free, 1 written (on the wire), checked on every transition
     cudaEvent_t written = nullptr, read = nullptr; bool has_reader = false;      // same-rank ordering
@@ -80,6 +82,11 @@ struct Node {
     float* scratch = nullptr;               // UPDATE_MERGE: private trainable copy of a received model
     uint64_t pt_draws = 0;                  // PassThroughNode: accept draws made so far (keys the next one)
     int64_t* sample_idx = nullptr; float* sample_val = nullptr;   // SamplingTMH: the coordinate sample and its merged values
+    // All2AllGossipNode: newest model per sender in first-arrival order (a Python dict's order), mixing weights ([0] = self,
+    // then one per peer in get_peers() order), and the snapshot shared by the pushes of one timeout
+    std::vector<std::pair<int, std::pair<int, int>>> cache;
+    std::vector<double> mix_w; std::vector<int> peers;
+    int64_t version = 0, snap_version = -1; int snap_rk = -1, snap_slot = -1;
     // snapshot elision: a message whose delivery provably precedes this node's next write travels as a reference to the
     // LIVE row (`alias.data == row`), no copy.  0 = none, 1 = on the wire, 2 = read: the next write waits for `alias.read`
     Slot alias; int alias_state = 0;
@@ -118,6 +125,7 @@ public:
             for (Slot& s : pool) {
                 if (s.written) cudaEventDestroy(s.written);
                 if (s.read) cudaEventDestroy(s.read);
+                for (cudaEvent_t e : s.reads) cudaEventDestroy(e);
             }
         for (Node& nd : nodes_) {
             if (nd.alias.written) cudaEventDestroy(nd.alias.written);
@@ -151,6 +159,33 @@ public:
         nodes_.at(i).sample_idx = reinterpret_cast<int64_t*>(idx); nodes_.at(i).sample_val = reinterpret_cast<float*>(val);
     }
     void set_sample_merge_callback(py::function f) { cb_sample_merge_ = std::move(f); }
+    // All2AllGossipNode + WeightedTMH (node.py:406-462, handler.py::WeightedTMH): deliveries are cached per sender; on timeout the
+    // cached models are merged with the mixing weights (k-way kernel) and the node trains; its pushes share one snapshot
+    void set_all2all(bool on) { a2a_ = on; }
+    void set_node_mixing(int i, const std::vector<int>& peers, const std::vector<double>& weights) {
+        nodes_.at(i).peers = peers; nodes_.at(i).mix_w = weights;
+    }
+    void set_kway_callback(py::function f) { cb_kway_ = std::move(f); }
+    // (node, sender, rank, slot, age) of every cached model -- checkpointing
+    std::vector<std::vector<int64_t>> caches() const {
+        std::vector<std::vector<int64_t>> v;
+        for (size_t i = 0; i < nodes_.size(); ++i)
+            for (const auto& e : nodes_[i].cache)
+                v.push_back({(int64_t)i, e.first, e.second.first, e.second.second, pools_[e.second.first][e.second.second].age});
+        return v;
+    }
+    void import_cache(const std::vector<std::vector<int64_t>>& rows) {        // slots already filled by Python
+        for (const auto& r : rows) {
+            const int rk = 0, s = (int)r.at(2);
+            auto& fl = free_.at(rk);
+            auto it = std::find(fl.begin(), fl.end(), s);
+            if (it == fl.end()) throw std::invalid_argument("slot is not free");
+            fl.erase(it);
+            Slot& sl = pools_.at(rk).at(s);
+            sl.state = 1; sl.refs = 1; sl.age = r.at(3);
+            nodes_.at((size_t)r.at(0)).cache.push_back({(int)r.at(1), {rk, s}});
+        }
+    }
     void set_node_scratch(int i, uintptr_t scratch) { nodes_.at(i).scratch = reinterpret_cast<float*>(scratch); }
     void set_update_merge_callback(py::function f) { cb_update_merge_ = std::move(f); }
     void set_node_data(int i, uintptr_t X, uintptr_t y, int n) {       // streamed inputs: the buffers alternate per round
@@ -218,7 +253,11 @@ public:
             const int32_t kind = ev(i, 0), a = ev(i, 2), b = ev(i, 3), id = ev(i, 4), aux = ev(i, 5);
             switch (kind) {
                 case EV_SEND:
+                    if (a2a_) { if (!snapshot_shared(a, id)) { resume_at_ = i; return evals; } break; }
                     if (aux != MT_PULL) { if (!snapshot(a, id, can_alias(ev, i, a, b, id, false))) { resume_at_ = i; return evals; } }
+                    break;
+                case EV_TIMEOUT:
+                    if (a2a_) on_timeout(a);
                     break;
                 case EV_REPLY_SEND:                       // b answers with its (just updated) model; reply id in aux
                     if (!snapshot(b, aux, can_alias(ev, i, b, a, aux, true))) { resume_at_ = i; return evals; }
@@ -226,7 +265,9 @@ public:
                 case EV_DROP: {
                     auto it = inflight_.find(id);
                     if (it != inflight_.end()) {
-                        if (it->second.first < 0) {       // an elided snapshot that was never read
+                        if (a2a_) {
+                            release_ref(it->second.first, it->second.second);
+                        } else if (it->second.first < 0) {       // an elided snapshot that was never read
                             Node& snd = nodes_[-1 - it->second.first];
                             snd.alias_state = 0; snd.alias.state = 0;
                         } else {
@@ -238,6 +279,7 @@ public:
                     break;
                 }
                 case EV_DELIVER:
+                    if (a2a_) { if (aux == MT_PUSH) store(b, a, id); break; }
                     if (aux == MT_PUSH || aux == MT_PUSH_PULL) consume(b, id);
                     break;
                 case EV_REPLY_DELIVER:
@@ -283,6 +325,7 @@ public:
             fl.erase(it);
             Slot& sl = pools_.at(rk).at(s);
             sl.state = 1;                                   // (debug mode) holds a snapshot again
+            sl.refs = 1;
             sl.age = r.at(3);
             if (n_parts_ > 0) { sl.pid = (int)r.at(4); sl.ages_v.assign(r.begin() + 5, r.begin() + 5 + n_parts_); }
             else if (mode_ == 3) sl.counter = r.at(4);
@@ -330,7 +373,7 @@ private:
     // that are dropped.  Same rank only (a peer GPU reads through the published-snapshot protocol).
     template <class Ev>
     bool can_alias(const Ev& ev, int64_t i, int sender, int dst, int32_t msg_id, bool is_reply) const {
-        if (!elide_ || nodes_[sender].alias_state != 0) return false;
+        if (!elide_ || a2a_ || nodes_[sender].alias_state != 0) return false;
         if (world_ > 1 && owner_[sender] != owner_[dst]) return false;
         const int64_t n = ev.shape(0), window = std::min<int64_t>(n, i + 1 + 512);
         auto writes_sender = [&](int64_t j) {
@@ -397,6 +440,8 @@ private:
                 // the slot's previous life: its reader (WAR) and -- for a dropped message nobody read -- its writer (WAW);
                 // readers on other ranks acknowledge through the slot's `done` counter
                 if (sl.has_reader) cuda_check(cudaStreamWaitEvent(nd.stream, sl.read, 0), "wait for the slot's last reader");
+                for (int q = 0; q < sl.n_reads; ++q) cuda_check(cudaStreamWaitEvent(nd.stream, sl.reads[q], 0), "wait for the slot's readers");
+                sl.n_reads = 0;
                 if (sl.written) cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the slot's last writer");
                 if (sl.remote_reads != sl.acked) launch_flag_wait(sl.done, sl.remote_reads, nd.stream);
                 launch_merge_pair(sl.data, nd.row, 0.f, 1.f, 0, row_floats_, PeerSync{nullptr, 0, nullptr, nullptr}, nd.stream);
@@ -412,6 +457,105 @@ private:
         sl.acked = sl.remote_reads;
         inflight_[msg_id] = {rk, s};
         return true;
+    }
+
+    // ---- All2AllGossipNode --------------------------------------------------------------------------------------------
+    void release_ref(int rk, int s) {
+        Slot& sl = pools_[rk][s];
+        if (--sl.refs <= 0) { sl.refs = 0; sl.state = 0; free_[rk].push_back(s); }
+    }
+    // the pushes of one timeout carry the same model: one snapshot, one reference per message (model/handler.py::caching)
+    bool snapshot_shared(int node, int32_t msg_id) {
+        Node& nd = nodes_.at(node);
+        if (nd.snap_slot >= 0 && nd.snap_version == nd.version && pools_[nd.snap_rk][nd.snap_slot].refs > 0) {
+            pools_[nd.snap_rk][nd.snap_slot].refs += 1;
+            if (debug_ && inflight_.count(msg_id)) throw std::logic_error("executor debug: message id sent twice");
+            inflight_[msg_id] = {nd.snap_rk, nd.snap_slot};
+            return true;
+        }
+        if (!snapshot(node, msg_id, false)) return false;
+        const auto where = inflight_.at(msg_id);
+        pools_[where.first][where.second].refs = 1;
+        nd.snap_rk = where.first; nd.snap_slot = where.second; nd.snap_version = nd.version;
+        return true;
+    }
+    void store(int node, int sender, int32_t msg_id) {          // node.py::All2AllGossipNode.receive: newest model per sender
+        auto it = inflight_.find(msg_id);
+        if (it == inflight_.end()) throw std::runtime_error("delivery of an unknown message");
+        const std::pair<int, int> where = it->second;
+        inflight_.erase(it);
+        Node& nd = nodes_.at(node);
+        for (auto& e : nd.cache)
+            if (e.first == sender) { release_ref(e.second.first, e.second.second); e.second = where; return; }
+        nd.cache.push_back({sender, where});
+    }
+    void on_timeout(int node) {                                   // node.py::All2AllGossipNode.on_timeout + WeightedTMH MERGE_UPDATE
+        Node& nd = nodes_.at(node);
+        if (nd.cache.empty()) return;
+        const int k = (int)nd.cache.size();
+        std::vector<double> use(1, nd.mix_w.empty() ? 0.0 : nd.mix_w[0]);
+        for (const auto& e : nd.cache) {
+            double w = 0.0;
+            for (size_t q = 0; q < nd.peers.size(); ++q)
+                if (nd.peers[q] == e.first) { if (q + 1 < nd.mix_w.size()) w = nd.mix_w[q + 1]; break; }
+            use.push_back(w);
+        }
+        if (k < (int)nd.peers.size()) {                           // fewer models than neighbours: renormalise (sequential sum,
+            double sum = 0.0;                                     // like the Python side)
+            for (double u : use) sum += u;
+            if (sum > 0.0) for (double& u : use) u /= sum;
+        }
+        const bool exec = mine(node);
+        int64_t age = nd.age;
+        std::vector<const float*> srcs; std::vector<PeerSync> syncs; bool any_remote = false;
+        std::vector<std::vector<int64_t>> cpu_srcs;
+        for (const auto& e : nd.cache) {
+            Slot& sl = pools_[e.second.first][e.second.second];
+            age = std::max(age, sl.age);
+            const bool remote = world_ > 1 && e.second.first != owner_[node];
+            if (remote) sl.remote_reads += 1;                     // replicated: the owner waits for this many acknowledgements
+            if (exec && cuda_) {
+                srcs.push_back(sl.data);
+                if (remote) { syncs.push_back(PeerSync{sl.ready, sl.gen, sl.done, device_fault_word()}); any_remote = true; }
+                else {
+                    syncs.push_back(PeerSync{nullptr, 0, nullptr, nullptr});
+                    if (sl.written) cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for a cached snapshot");
+                }
+            } else if (exec) {
+                cpu_srcs.push_back({e.second.first, e.second.second, (int64_t)sl.gen});
+            }
+        }
+        if (exec) {
+            if (cuda_) {
+                std::vector<float> wf(use.begin(), use.end());
+                launch_merge_kway(nd.row, srcs.data(), wf.data(), k, row_floats_, any_remote ? syncs.data() : nullptr, nd.stream);
+                for (const auto& e : nd.cache) {                  // same-rank readers: the slot's next writer waits for this kernel
+                    if (world_ > 1 && e.second.first != owner_[node]) continue;
+                    Slot& sl = pools_[e.second.first][e.second.second];
+                    if ((int)sl.reads.size() <= sl.n_reads) {
+                        cudaEvent_t ev; cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+                        sl.reads.push_back(ev);
+                    }
+                    cuda_check(cudaEventRecord(sl.reads[sl.n_reads++], nd.stream), "record slot read");
+                }
+            } else {
+                cb_kway_(node, cpu_srcs, use);
+            }
+            ++launches_;
+        }
+        nd.age = age;
+        nd.counter += 1;
+        const uint64_t key = key_of(node, nd);
+        if (exec) {
+            if (cuda_) train(nd, nullptr, 1.f, 0.f, key, PeerSync{nullptr, 0, nullptr, nullptr});
+            else cb_train_(node, 0, -1, (int64_t)key, 1.f, 0.f, (int64_t)0);
+            ++launches_;
+            if (cuda_) cuda_check(cudaGetLastError(), "timeout launch");
+        }
+        nd.age += steps_of(nd);
+        nd.version += 1;
+        for (const auto& e : nd.cache) release_ref(e.second.first, e.second.second);
+        nd.cache.clear();
     }
 
     void merge_weights(int64_t a, int64_t b, float& ws, float& wp) const {   // model/handler.py: _fused_merge_weights
@@ -629,7 +773,8 @@ private:
     std::vector<std::vector<Slot>> pools_;          // per owner rank
     std::vector<std::deque<int>> free_;             // FIFO: a slot is reused as late as possible (see snapshot())
     std::unordered_map<int32_t, std::pair<int, int>> inflight_;     // message id -> (rank, slot)
-    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_merge_, cb_sample_merge_;
+    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_merge_, cb_sample_merge_, cb_kway_;
+    bool a2a_ = false;                               // All2AllGossipNode mode
     int64_t sample_k_ = 0, n_params_ = 0;            // SamplingTMH: sample size (0 = whole-model merges)
     int n_parts_ = 0; const int64_t* part_id_ = nullptr;
     std::vector<int64_t> deg_;                       // PassThroughNode: node degrees (empty = plain nodes)
@@ -650,6 +795,11 @@ void bind_executor(py::module_& m) {
         .def("set_node", &StreamExecutor::set_node)
         .def("set_node_data", &StreamExecutor::set_node_data)
         .def("set_node_scratch", &StreamExecutor::set_node_scratch)
+        .def("set_all2all", &StreamExecutor::set_all2all)
+        .def("set_node_mixing", &StreamExecutor::set_node_mixing)
+        .def("set_kway_callback", &StreamExecutor::set_kway_callback)
+        .def("caches", &StreamExecutor::caches)
+        .def("import_cache", &StreamExecutor::import_cache)
         .def("set_sampling", &StreamExecutor::set_sampling)
         .def("set_node_sample_buffers", &StreamExecutor::set_node_sample_buffers)
         .def("set_sample_merge_callback", &StreamExecutor::set_sample_merge_callback)

@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..core import CreateModelMode
+from ..core import AntiEntropyProtocol, CreateModelMode
 from . import arena as _arena
 from . import rng as _rng
 
@@ -39,7 +39,8 @@ def eligible(sim: Any) -> Optional[str]:
     from .. import GlobalSettings
     if GlobalSettings().reference_compat:
         return "reference_compat (bug-for-bug behaviours live in the Python handlers)"
-    if type(sim).__name__ not in ("GossipSimulator", "TokenizedGossipSimulator"):
+    a2a = type(sim).__name__ == "All2AllGossipSimulator"
+    if type(sim).__name__ not in ("GossipSimulator", "TokenizedGossipSimulator") and not a2a:
         return "simulator variant"
     if prt.active() and prt.transport() != "p2p":
         return "several ranks without shared arenas"
@@ -48,7 +49,12 @@ def eligible(sim: Any) -> Optional[str]:
     ids = sorted(sim.nodes)
     if ids != list(range(len(ids))):
         return "node ids must be 0..N-1"
-    from ..node import PartitioningBasedNode, PassThroughNode, SamplingBasedNode
+    from ..node import All2AllGossipNode, PartitioningBasedNode, PassThroughNode, SamplingBasedNode
+    if a2a:
+        if sim.protocol != AntiEntropyProtocol.PUSH:
+            return "all-to-all: protocol %s" % sim.protocol.name
+        if getattr(sim, "_W", None) is None:
+            return "all-to-all: no mixing matrix"
     ref = None
     cls0 = type(sim.nodes[ids[0]])
     for i in ids:
@@ -56,13 +62,18 @@ def eligible(sim: Any) -> Optional[str]:
         h = node.model_handler
         partitioned = type(node) is PartitioningBasedNode and type(h) is H.PartitionedTMH
         sampled = type(node) is SamplingBasedNode and type(h) is H.SamplingTMH
+        weighted = a2a and type(node) is All2AllGossipNode and type(h) is H.WeightedTMH
         if type(node) is not cls0:
             return "mixed node classes"
-        if type(node) not in (GossipNode, PassThroughNode) and not partitioned and not sampled:
+        if a2a != weighted:
+            return "all-to-all needs All2AllGossipNode + WeightedTMH"
+        if weighted and (h.mode != CreateModelMode.MERGE_UPDATE or node.local_cache and "_stream_exec" not in sim.__dict__):
+            return "all-to-all: mode %s / caches filled by another executor" % h.mode.name
+        if type(node) not in (GossipNode, PassThroughNode) and not partitioned and not sampled and not weighted:
             return "node class %s" % type(node).__name__
         if type(node) is PassThroughNode and not getattr(node, "_keyed_draws", False):
             return "pass-through nodes with host-stream draws"
-        if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH) and not partitioned and not sampled:
+        if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH) and not partitioned and not sampled and not weighted:
             return "handler class %s" % type(h).__name__
         if sampled and h.mode != CreateModelMode.MERGE_UPDATE:
             return "sampled models: mode %s" % h.mode.name
@@ -161,6 +172,11 @@ class StreamExec:
                 self.ex.set_node_sample_buffers(i, self._samp_idx[k_].data_ptr(), self._samp_val[k_].data_ptr())
             if not self.cuda:
                 self.ex.set_sample_merge_callback(self._cb_sample_merge)
+        self.a2a = type(sim).__name__ == "All2AllGossipSimulator"
+        if self.a2a:                    # cached neighbourhood + k-way merge on timeout; the pushes of a timeout share a snapshot
+            self.ex.set_all2all(True)
+            if not self.cuda:
+                self.ex.set_kway_callback(self._cb_kway)
         self._scratch = None
         if h0.mode == CreateModelMode.UPDATE_MERGE:      # one private row per node of this rank for the copy that is trained
             mine = [i for i in ids if self.owner[i] == self.rank]
@@ -220,6 +236,10 @@ class StreamExec:
                                  int(h._update_counter), int(s.cuda_stream) if s is not None else 0)
             if self.n_parts:
                 self.ex.set_node_ages(i, [int(a) for a in h.n_updates], int(getattr(node, "_model_msgs", 0)))
+        if self.a2a:
+            for i, node in self.sim.nodes.items():
+                self.ex.set_node_mixing(i, [int(p) for p in node.p2p_net.get_peers(i)],
+                                        [float(w) for w in np.asarray(self.sim._W[i], dtype=float)])
         if self.passthrough:
             ids = sorted(self.sim.nodes)
             self.ex.set_passthrough([int(self.sim.nodes[i].n_neighs) for i in ids],
@@ -308,6 +328,15 @@ class StreamExec:
         if w_peer != 0.0:
             ops.merge_pair(h.row, tmp, float(w_self), float(w_peer))
 
+    def _cb_kway(self, node: int, srcs: List[List[int]], weights: List[float]) -> None:
+        rows, syncs = [], []
+        for rank, slot, gen in srcs:
+            t, sync = self._slot(int(rank), int(slot), int(gen))
+            rows.append(t)
+            syncs.append(sync)
+        ops.merge_kway(self.sim.nodes[node].model_handler.row, rows, [float(w) for w in weights],
+                       syncs if any(s is not None for s in syncs) else None)
+
     def _cb_sample_merge(self, node: int, rank: int, slot: int, key: int, gen: int) -> None:
         src, sync = self._slot(rank, slot, gen)
         idx = ops.keyed_randint(self.sample_k, self.n_params, int(key), self.device)
@@ -360,16 +389,34 @@ class StreamExec:
             raise NotImplementedError("checkpointing the C++ executor with several ranks")
         rows = self.ex.inflight()
         idx = torch.as_tensor([r[2] for r in rows], dtype=torch.int64, device=self.device)
-        return {"ids": [int(r[0]) for r in rows], "ages": [int(r[3]) for r in rows], "extra": [list(map(int, r[4:])) for r in rows],
-                "rows": self.slots[idx].cpu() if rows else torch.zeros(0, self.row_numel)}
+        out = {"ids": [int(r[0]) for r in rows], "ages": [int(r[3]) for r in rows], "extra": [list(map(int, r[4:])) for r in rows],
+               "rows": self.slots[idx].cpu() if rows else torch.zeros(0, self.row_numel)}
+        if self.a2a:                    # models waiting in the neighbour caches are state as well
+            ent = self.ex.caches()
+            cidx = torch.as_tensor([e[3] for e in ent], dtype=torch.int64, device=self.device)
+            out["cache"] = {"nodes": [int(e[0]) for e in ent], "senders": [int(e[1]) for e in ent], "ages": [int(e[4]) for e in ent],
+                            "rows": self.slots[cidx].cpu() if ent else torch.zeros(0, self.row_numel)}
+        return out
 
     def import_inflight(self, st: Dict[str, Any]) -> None:
+        cache = st.get("cache")
+        if cache is not None and len(cache["nodes"]):
+            m = len(cache["nodes"])
+            while int(self.slots.shape[0]) < m or self.ex.free_slots < m:
+                self._grow()
+            taken = {int(r[2]) for r in self.ex.inflight()} | {int(e[3]) for e in self.ex.caches()}
+            free = [s for s in range(int(self.slots.shape[0])) if s not in taken][:m]
+            self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = cache["rows"].to(self.device)
+            self.ex.import_cache([[int(nd), int(sd), int(s), int(a)] for nd, sd, s, a in
+                                  zip(cache["nodes"], cache["senders"], free, cache["ages"])])
         n = len(st["ids"])
         if n == 0:
+            if self.cuda:
+                torch.cuda.synchronize(self.device)
             return
         while int(self.slots.shape[0]) < n or self.ex.free_slots < n:
             self._grow()
-        taken = {int(r[2]) for r in self.ex.inflight()}
+        taken = {int(r[2]) for r in self.ex.inflight()} | ({int(e[3]) for e in self.ex.caches()} if self.a2a else set())
         free = [s for s in range(int(self.slots.shape[0])) if s not in taken][:n]
         self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = st["rows"].to(self.device)
         if self.cuda:

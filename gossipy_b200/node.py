@@ -446,8 +446,12 @@ class All2AllGossipNode(GossipNode):
                 pos = {p: i + 1 for i, p in enumerate(peers)}
                 use = np.array([w[0]] + [w[pos[s]] if s in pos and pos[s] < len(w) else 0.0
                                          for s in senders])
-                if len(models) < len(peers) and use.sum() > 0:
-                    use = use / use.sum()
+                if len(models) < len(peers):
+                    total = 0.0
+                    for u in use.tolist():           # sequential sum: the C++ executor reproduces it bit for bit
+                        total += u
+                    if total > 0:
+                        use = use / total
             self.model_handler(models, self.data[0], use)
             for m in models:
                 _release(m)

@@ -519,7 +519,7 @@ class GossipSimulator(SimulationEventSender):
             if why is None:
                 self._run_native_banked(sch, n_rounds, C)
                 return
-        if self.native_executor and type(self) in (GossipSimulator, TokenizedGossipSimulator):
+        if self.native_executor and type(self) in (GossipSimulator, TokenizedGossipSimulator, All2AllGossipSimulator):
             from .engine import stream_exec as _sx
             if _sx.eligible(self) is None:
                 self._run_native_streamed(sch, n_rounds)

@@ -105,6 +105,19 @@ def build(kind, device):
         sim = All2AllGossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
         start_args = (UniformMixing(net),)
         sim._mr_kwargs = {"synchronous": True}
+    elif kind == "x_all2all":
+        # asynchronous all-to-all (cached neighbourhood, k-way merge on timeout) through the C++ executor; snapshots
+        # shared by the pushes of a timeout, read by several ranks
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=6, eval_on_user=False)
+        net = StaticP2PNetwork(6)
+        proto = WeightedTMH(LogisticRegression(57, 2), torch.optim.SGD, {"lr": .1, "weight_decay": .001},
+                            torch.nn.CrossEntropyLoss(), batch_size=16, create_model_mode=CreateModelMode.MERGE_UPDATE)
+        nodes = All2AllGossipNode.generate(disp, net, proto, 10, False)
+        sim = All2AllGossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH, drop_prob=.1, delay=UniformDelay(0, 3))
+        sim.engine = "native"
+        sim.native_executor = True
+        start_args = (UniformMixing(net),)
     elif kind in ("x_part_mlp", "x_part_logreg"):
         # partitioned models through the C++ executor: keyed partition draws, ages per partition, segment merges
         if kind == "x_part_mlp":

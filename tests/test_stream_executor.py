@@ -329,6 +329,13 @@ def test_native_executor_cuda_equals_python_executor():
         assert "_stream_exec" in sim_b.__dict__
         _same(sim_a, rep_a, sim_b, rep_b, tol=1e-5)
         g.CACHE.clear()
+    for kw in (dict(model="mlp", n=8, sync=True), dict(model="logreg", n=6, faults=True, mixing="ring")):
+        sim_a, rep_a = _a2a_sim(False, device="cuda:0", **kw)
+        sim_b, rep_b = _a2a_sim(True, device="cuda:0", **kw)
+        torch.cuda.synchronize()
+        assert "_stream_exec" in sim_b.__dict__
+        _same(sim_a, rep_a, sim_b, rep_b, tol=1e-5)
+        g.CACHE.clear()
     g.GlobalSettings().set_device("cpu")
 
 
@@ -356,3 +363,74 @@ def test_native_executor_equals_python_executor_random_setups():
             (rep_b._sent_messages, rep_b._failed_messages, rep_b._total_size)
         g.CACHE.clear()
     check()
+
+
+def _a2a_sim(streamed, model="logreg", n=6, rounds=4, device="cpu", faults=False, sync=False, mixing="uniform", start=True):
+    import gossipy_b200 as g
+    from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork, UniformDelay, UniformMixing
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import WeightedTMH
+    from gossipy_b200.model.nn import LogisticRegression, TorchMLP
+    from gossipy_b200.node import All2AllGossipNode
+    from gossipy_b200.simul import All2AllGossipSimulator, SimulationReport
+    g.GlobalSettings().set_device(device)
+    g.CACHE.clear()
+    g.set_seed(7)
+    if model == "mlp":
+        (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(96 * n, 120)
+        net, bs = TorchMLP(784, 10, (100,)), 32
+    else:
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(50 * n + 3, 150)
+        net, bs = LogisticRegression(57, 2), 16
+    disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
+    proto = WeightedTMH(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), batch_size=bs,
+                        create_model_mode=CreateModelMode.MERGE_UPDATE)
+    if mixing == "ring":            # sparse topology: each node hears from two neighbours only
+        A = np.zeros((n, n), dtype=int)
+        for i in range(n):
+            A[i, (i + 1) % n] = A[(i + 1) % n, i] = 1
+        topo = StaticP2PNetwork(n, A)
+    else:
+        topo = StaticP2PNetwork(n)
+    nodes = All2AllGossipNode.generate(disp, topo, proto, 10, sync)
+    kw = dict(drop_prob=.2, online_prob=.8, delay=UniformDelay(0, 4), sampling_eval=.5) if faults else {}
+    sim = All2AllGossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH, **kw)
+    sim.progress = False
+    sim.engine = "native"
+    sim.native_executor = streamed
+    rep = SimulationReport(); sim.add_receiver(rep)
+    sim.init_nodes(seed=11)
+    sim._mix = UniformMixing(topo)
+    if start:
+        sim.start(sim._mix, rounds)
+    return sim, rep
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(faults=True), dict(model="mlp", sync=True), dict(mixing="ring", faults=True, n=7)])
+def test_native_executor_all_to_all_nodes(kw):
+    """All2AllGossipNode + WeightedTMH (reference node.py:789-870, handler.py:642-688) from C++: per-sender caches, shared
+    snapshot of a timeout's pushes (reference counts), k-way merge with renormalised mixing weights on timeout, update."""
+    import gossipy_b200 as g
+    sim_a, rep_a = _a2a_sim(False, **kw)
+    sim_b, rep_b = _a2a_sim(True, **kw)
+    assert "_stream_exec" in sim_b.__dict__ and "_stream_exec" not in sim_a.__dict__
+    _same(sim_a, rep_a, sim_b, rep_b)
+    g.CACHE.clear()
+
+
+def test_all_to_all_executor_checkpoint_keeps_the_caches(tmp_path):
+    import gossipy_b200 as g
+    from gossipy_b200.simul import All2AllGossipSimulator
+    sim_full, rep_full = _a2a_sim(True, faults=True, rounds=6)
+    sim, rep = _a2a_sim(True, faults=True, start=False)
+    sim.start(sim._mix, 3)
+    assert len(sim._stream_exec.ex.caches()) > 0
+    path = str(tmp_path / "ck.pkl")
+    sim.save(path)
+    g.CACHE.clear()
+    sim2 = All2AllGossipSimulator.load(path)
+    rep2 = [r for r in sim2._receivers if type(r).__name__ == "SimulationReport"][0]
+    sim2.start(sim._mix, 3, resume=True)
+    _same(sim_full, rep_full, sim2, rep2)
+    g.CACHE.clear()
