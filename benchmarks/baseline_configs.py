@@ -10,6 +10,8 @@
 4  main_giaretta_2019  partitioned-model merge, 64 nodes over 8 GPUs (8 nodes per GPU)
 5  main_onoszko_2021   ResNet-20 on CIFAR-shape data, 8 nodes, TokenAccount flow control
 6  weak scaling        config 2 with 8 nodes PER GPU (8 x world nodes, 7 500 samples each): aggregate node-rounds/s
+7  main_all2all as the reference runs it: ASYNCHRONOUS all-to-all (nodes fire at their own ticks, cache their neighbours'
+   models, merge them with the mixing weights on timeout) -- the C++ executor's all-to-all mode; `--no-executor` = per-event
 
 Rank 0 prints one JSON line: rounds/s (device time, max over ranks), metric curve tail, message counters.
 ``--scale`` shrinks the data sets (1.0 = the sizes named above)."""
@@ -33,6 +35,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
     ap.add_argument("--engine", default="native")
+    ap.add_argument("--no-executor", action="store_true", help="per-event Python executor instead of the C++ one")
     a = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     dev = a.device
@@ -70,7 +73,7 @@ def main():
         sim = GossipSimulator(nodes, disp, 100, AEP.PUSH, drop_prob=.1, online_prob=.2, delay=UniformDelay(0, 10),
                               sampling_eval=.1)
         desc = "Pegasos, 8 nodes, PUSH, churn"
-    elif a.config in (2, 3):
+    elif a.config in (2, 3, 7):
         (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(int(60000 * sc), int(10000 * sc))
         disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=8, eval_on_user=False, auto_assign=False)
         disp.set_assignments(AssignmentHandler(42).label_pathological_skew(ytr, 8, 2), None)
@@ -86,8 +89,13 @@ def main():
                                 torch.nn.CrossEntropyLoss(), batch_size=32)
             nodes = All2AllGossipNode.generate(disp, net, proto, 100, True)
             sim = All2AllGossipSimulator(nodes, disp, 100, AEP.PUSH)
-            start_extra, start_kw = (UniformMixing(net),), {"synchronous": True}
-            desc = "MLP all-to-all averaging, 8 nodes, one-shot all-reduce per round"
+            if a.config == 3:
+                start_extra, start_kw = (UniformMixing(net),), {"synchronous": True}
+                desc = "MLP all-to-all averaging, 8 nodes, one-shot all-reduce per round"
+            else:
+                start_extra = (UniformMixing(net),)
+                desc = "MLP asynchronous all-to-all (reference semantics), 8 nodes, %s" % (
+                    "per-event Python executor" if a.no_executor else "C++ executor")
     elif a.config == 4:
         n_nodes = 64
         (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(int(60000 * sc), int(10000 * sc))
@@ -130,6 +138,8 @@ def main():
         raise SystemExit("config must be 1..6")
     sim.progress = False
     sim.engine = a.engine
+    if a.no_executor:
+        sim.native_executor = False
     rep = SimulationReport()
     sim.add_receiver(rep)
     sim.init_nodes(seed=42)
