@@ -52,13 +52,22 @@ def spambase_like(n_train: int = 4141, n_test: int = 460, seed: int = 0):
 
 def images_like(name: str, as_tensor: bool = True, seed: int = 0, n_train: int = None,
                 n_test: int = None):
-    """CIFAR-10 (3x32x32) / Fashion-MNIST (28x28) shaped images in [0,1] with teacher labels."""
+    """CIFAR-10 (3x32x32) / Fashion-MNIST (28x28) shaped images in [0,1], ten classes.
+
+    Every class has a smooth prototype image (a random 4x4 field per channel, bilinearly upsampled); a sample is its
+    class prototype plus white noise, squashed to [0, 1].  The class signal is spatially structured, so convolutional
+    nets with global pooling (ResNet-20) learn it as readily as fully connected ones -- a pixel-wise linear teacher, the
+    previous generator, is invisible to them."""
     shape = {"cifar10": (3, 32, 32), "fashionmnist": (28, 28)}[name]
     ntr = n_train or {"cifar10": 50000, "fashionmnist": 60000}[name]
     nte = n_test or 10000
-    d = int(np.prod(shape))
-    X, y = teacher_classification(ntr + nte, d, 10, seed=seed, noise=0.3)
-    X = torch.sigmoid(X).reshape(ntr + nte, *shape)
+    g = torch.Generator().manual_seed(seed)
+    chans = shape[0] if len(shape) == 3 else 1
+    hw = shape[-2:]
+    proto = torch.nn.functional.interpolate(torch.randn(10, chans, 4, 4, generator=g), size=hw, mode="bilinear",
+                                            align_corners=False)
+    y = torch.randint(0, 10, (ntr + nte,), generator=g)
+    X = torch.sigmoid(1.5 * proto[y] + torch.randn(ntr + nte, chans, *hw, generator=g)).reshape(ntr + nte, *shape)
     if not as_tensor:
         return (X[:ntr].numpy(), y[:ntr].tolist()), (X[ntr:].numpy(), y[ntr:].tolist())
     return (X[:ntr], y[:ntr]), (X[ntr:], y[ntr:])
