@@ -646,6 +646,7 @@ class _GraphStep:
 
 
 _GRAPH_POOLS: Dict[Tuple[int, int], Any] = {}
+CAPTURE_WINDOW = [False]       # several ranks: True while the simulator initialises the nodes (see _graph_fwd_bwd)
 
 
 def _graph_pool(device: torch.device):
@@ -1036,6 +1037,11 @@ class TorchModelHandler(RowHandler):
         if ent.graph is None:
             ent.seen += 1
             if ent.seen <= self._GRAPH_WARMUP:
+                return False
+            if _prt.active() and not CAPTURE_WINDOW[0]:
+                # several ranks: a capture synchronises the device and frees cached blocks; if a kernel of this GPU is
+                # spinning on a peer's flag while the peer's host is in the same situation, neither publishes -- captures
+                # are confined to ``init_nodes`` (no cross-GPU dependency exists yet), later shapes run eagerly
                 return False
             ent.x = torch.empty((nb,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
             ent.y = torch.empty((nb,) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)

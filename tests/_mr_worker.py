@@ -64,6 +64,38 @@ def build(kind, device):
         sim = GossipSimulator(nodes, disp, 10, prt_, **kws)
         sim.engine = "native"
         sim.batched = True
+    elif kind == "cnn_pushpull":
+        # a generic (autograd) model: conv + BatchNorm; on a GPU its steps are replayed from CUDA graphs captured during
+        # init_nodes (several ranks: captures are confined to that window) and its rows are channels-last
+        from gossipy_b200.model.nn import TorchModel
+
+        class SmallCNN(TorchModel):
+            def __init__(self):
+                super().__init__()
+                self.c1 = torch.nn.Conv2d(1, 4, 3, padding=1)
+                self.bn = torch.nn.BatchNorm2d(4)
+                self.fc = torch.nn.Linear(4 * 4 * 4, 3)
+
+            def forward(self, x):
+                x = torch.nn.functional.max_pool2d(torch.relu(self.bn(self.c1(x))), 2)
+                return self.fc(x.flatten(1))
+
+            def init_weights(self):
+                pass
+
+            def __str__(self):
+                return "SmallCNN"
+        gen = torch.Generator().manual_seed(3)
+        yall = torch.randint(0, 3, (420,), generator=gen)
+        proto_img = torch.randn(3, 1, 8, 8, generator=gen)
+        Xall = torch.sigmoid(1.5 * proto_img[yall] + torch.randn(420, 1, 8, 8, generator=gen))
+        disp = DataDispatcher(ClassificationDataHandler(Xall[:320], yall[:320], Xall[320:], yall[320:]), n=4, eval_on_user=False)
+        torch.manual_seed(5)
+        proto = TorchModelHandler(SmallCNN(), torch.optim.SGD, {"lr": .05, "momentum": .9}, torch.nn.CrossEntropyLoss(),
+                                  batch_size=16)
+        nodes = GossipNode.generate(disp, StaticP2PNetwork(4), proto, 10, True)
+        sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH_PULL)
+        sim.engine = "native"
     elif kind == "mlp_pushpull":
         (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
         disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=4, eval_on_user=False)

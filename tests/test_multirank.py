@@ -120,6 +120,21 @@ def test_banked_engine_two_and_three_ranks_cpu_equal_single_process():
         _compare(single, multi, rel=1e-5)
 
 
+def test_generic_conv_model_two_ranks_cpu_equal_single_process():
+    single = _run(1, "cpu", rounds=4, kinds="cnn_pushpull")
+    _compare(single, _run(2, "cpu", rounds=4, kinds="cnn_pushpull"), rel=1e-4)
+
+
+@pytest.mark.gpu
+def test_generic_conv_model_two_ranks_cuda_equal_single_gpu():
+    """Generic models across GPUs: CUDA-graph captures happen inside init_nodes only (a capture synchronises the device,
+    which must not happen while kernels of both GPUs wait for each other's flags), channels-last rows."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    single = _run(1, "cuda:0", rounds=5, kinds="cnn_pushpull")
+    _compare(single, _run(2, "cuda", rounds=5, kinds="cnn_pushpull"), rel=5e-2)
+
+
 @pytest.mark.gpu
 def test_banked_engine_two_ranks_cuda_equal_single_gpu():
     if torch.cuda.device_count() < 2:
