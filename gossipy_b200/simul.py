@@ -237,6 +237,21 @@ class GossipSimulator(SimulationEventSender):
             eval_set = self.data_dispatcher.get_eval_set() if self.data_dispatcher.has_test() else None
         except Exception:
             eval_set = None
+        # generic (autograd) models also use library kernels on their snapshot / merge path (integer-buffer max, clones,
+        # gathers) that CUDA would otherwise load lazily at the first exchange -- loading a module can need a device-wide
+        # synchronisation, which must not happen while kernels wait on other GPUs' flags: exercise that path once here
+        # (a snapshot merged back into its own model with weights 1/2 + 1/2 leaves every value unchanged)
+        for node in self.nodes.values():
+            h = node.model_handler
+            if getattr(h, "_fused", True) or not hasattr(h, "_snapshot") or not hasattr(h, "layout"):
+                continue
+            try:
+                snap = h._snapshot()
+                h._weighted_merge(snap, 0.5, 0.5)
+                h._merge_int_buffers(snap)
+                snap.release()
+            except Exception as err:           # priming is best effort
+                LOG.debug("priming the exchange path of node %s failed: %s" % (getattr(node, "idx", "?"), err))
         pend = []
         for node in self.nodes.values():
             fn = getattr(node, "evaluate_async", None)
