@@ -231,7 +231,7 @@ __global__ void flag_signal_kernel(uint32_t* flag, uint32_t value) {
     gb_st_release_sys(flag, value);
 }
 __global__ void flag_wait_kernel(const uint32_t* flag, uint32_t value, uint32_t* fault) {
-    gb_wait_flag(flag, value, fault);                                          // flags only grow
+    gb_wait_flag(flag, value, fault, 16u);                                     // flags only grow; 16 = a stream-ordered wait (acks of a row's readers)
 }
 __global__ void flag_add_kernel(uint32_t* flag, uint32_t value) {
     __threadfence_system();

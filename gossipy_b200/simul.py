@@ -113,7 +113,8 @@ def _check_device_fault() -> None:
     if bits:
         raise RuntimeError("gossipy_b200: device fault word = %d (1: a wait for a peer's model timed out, 2: an "
                            "all-reduce epoch timed out, 4: handshake ticket shared by two launches, 8: a rank barrier of the "
-                           "banked engine timed out) -- results "
+                           "banked engine timed out, 16: a wait for the acknowledgements of a row's remote readers timed "
+                           "out) -- results "
                            "of this round are invalid" % bits)
 
 
