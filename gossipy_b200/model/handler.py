@@ -700,8 +700,12 @@ class TorchModelHandler(RowHandler):
         self._proto = copy.deepcopy(net)
         self._module = None if copy_model else net
         cl = GlobalSettings().channels_last
+        # "auto": on a GPU, one rank.  With several ranks cuDNN's NHWC BatchNorm kernels are off limits: they are persistent
+        # (cooperative: all CTAs must be co-resident), so one of them queues behind the kernels that spin on a peer's
+        # flag while the snapshot the peer is waiting for queues behind it -- on both GPUs at once (measured: config 5 on
+        # 2 GPUs timed out in the bounded waits with channels-last rows, not with NCHW rows)
         self.layout = FlatLayout(self._proto, channels_last=self._ROW_CHANNELS_LAST_OK and (
-            cl is True or (cl == "auto" and GlobalSettings().is_cuda())))
+            cl is True or (cl == "auto" and GlobalSettings().is_cuda() and not _prt.active())))
         self._row_numel = self.layout.padded
         self._size_cache = int(self._proto.get_size())
         self.optimizer_cls = optimizer
