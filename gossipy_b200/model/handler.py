@@ -646,7 +646,6 @@ class _GraphStep:
 
 
 _GRAPH_POOLS: Dict[Tuple[int, int], Any] = {}
-CAPTURE_WINDOW = [False]       # several ranks: True while the simulator initialises the nodes (see _graph_fwd_bwd)
 
 
 def _graph_pool(device: torch.device):
@@ -1025,6 +1024,13 @@ class TorchModelHandler(RowHandler):
         Returns ``False`` when the step has to run eagerly."""
         if not (g.is_cuda and GlobalSettings().cuda_graphs) or torch.cuda.is_current_stream_capturing():
             return False
+        if _prt.active():
+            # One rank only.  With several ranks a node's stream may hold a kernel that waits on another GPU's flag; the
+            # replayed steps keep the GPU full of cuDNN kernels, some of them persistent (all CTAs co-resident), which then
+            # queue behind the waiting kernels while the snapshot the peer needs queues behind them -- on both GPUs at once.
+            # Measured on 2 GPUs (BASELINE config 5): replayed steps run into the bounded waits, eager steps (the GPU is
+            # mostly idle between the host's launches) do not.  A capture would also synchronise the device.
+            return False
         nb = int(idx.numel()) if idx is not None else int(x.size(0))
         key = (self.row.data_ptr(), g.data_ptr(), id(mod), nb, tuple(x.shape[1:]), x.dtype, tuple(y.shape[1:]),
                y.dtype, x.device.index, nhwc)
@@ -1042,11 +1048,7 @@ class TorchModelHandler(RowHandler):
             ent.seen += 1
             if ent.seen <= self._GRAPH_WARMUP:
                 return False
-            if _prt.active() and not CAPTURE_WINDOW[0]:
-                # several ranks: a capture synchronises the device and frees cached blocks; if a kernel of this GPU is
-                # spinning on a peer's flag while the peer's host is in the same situation, neither publishes -- captures
-                # are confined to ``init_nodes`` (no cross-GPU dependency exists yet), later shapes run eagerly
-                return False
+
             ent.x = torch.empty((nb,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
             ent.y = torch.empty((nb,) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)
             ent.fill(x, y, idx)

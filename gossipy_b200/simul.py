@@ -214,18 +214,9 @@ class GossipSimulator(SimulationEventSender):
         from .parallel import runtime as _prt
         if _prt.active():
             _prt.set_num_nodes(self.n_nodes)
-        from .model import handler as _mh
-        _mh.CAPTURE_WINDOW[0] = True       # no cross-GPU dependency exists yet: CUDA-graph captures are safe
-        try:
-            for node in self.nodes.values():
-                node.init_model()
-            self._prime_device_paths()
-        finally:
-            _mh.CAPTURE_WINDOW[0] = False
-        if _prt.active() and GlobalSettings().get_device().type == "cuda":
-            import torch
-            torch.cuda.synchronize()
-            _prt.barrier()                 # every rank has left its capture window before any exchange starts
+        for node in self.nodes.values():
+            node.init_model()
+        self._prime_device_paths()
 
     def _prime_device_paths(self) -> None:
         """Run every node's evaluation once, before any cross-GPU dependency exists, and discard the

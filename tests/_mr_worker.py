@@ -65,8 +65,8 @@ def build(kind, device):
         sim.engine = "native"
         sim.batched = True
     elif kind == "cnn_pushpull":
-        # a generic (autograd) model: conv + BatchNorm; on a GPU its steps are replayed from CUDA graphs captured during
-        # init_nodes (several ranks: captures are confined to that window) and its rows are channels-last
+        # a generic (autograd) model: conv + BatchNorm (one rank on a GPU: steps replayed from CUDA graphs, channels-last rows;
+        # several ranks: eager steps, plain rows)
         from gossipy_b200.model.nn import TorchModel
 
         class SmallCNN(TorchModel):

@@ -127,8 +127,7 @@ def test_generic_conv_model_two_ranks_cpu_equal_single_process():
 
 @pytest.mark.gpu
 def test_generic_conv_model_two_ranks_cuda_equal_single_gpu():
-    """Generic models across GPUs: CUDA-graph captures happen inside init_nodes only (a capture synchronises the device,
-    which must not happen while kernels of both GPUs wait for each other's flags), channels-last rows."""
+    """Generic models across GPUs (eager steps: graph replay and channels-last rows are single-rank features)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     single = _run(1, "cuda:0", rounds=5, kinds="cnn_pushpull")
