@@ -77,7 +77,7 @@ template <int NC, bool X3, bool MOM = false> struct T4Cfg {
     static constexpr int b2 = red + 8 * 40 * 4;
     static constexpr int inva = b2 + 16 * 4;                     // [2][16] 1/age of every partition, this / next step
     static constexpr int ys = inva + 2 * 16 * 4;                 // [2][32] int
-    static constexpr int mbar = ys + 2 * T4_B * 4;               // 10 x uint64
+    static constexpr int mbar = ys + 2 * T4_B * 4;               // 11 x uint64 (16 reserved)
     static constexpr int tslot = mbar + 128;
     static constexpr int total = tslot + 16;
     static_assert(t_d1 + d1_cols <= 512, "TMEM budget");
@@ -226,6 +226,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
         mbar_init(&mbar[7], T4Cfg<NC, X3>::GPO == 1 ? 4 : 8);      // one arrival per writing warp
         mbar_init(&mbar[8], 8);
         mbar_init(&mbar[9], 1);
+        mbar_init(&mbar[10], 8);                                     // first 64 columns of W / Wlo rewritten (pipelined forward)
         mbar_fence_init();
     }
     float b1r = (warp < T4_ISSUER && j < H) ? p.row[off_b1 + j] : 0.f;       // both threads of hidden unit j carry b1[j]
@@ -362,8 +363,7 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
         for (int s = 0; s < total_steps; ++s) {
             const uint32_t ph = (uint32_t)(s & 1);
             if (profiling && lane == 0) tprev = (unsigned)clock();
-            if (X3) {
-                if (s > 0) mbar_wait(&mbar[8], (uint32_t)((s - 1) & 1));   // W and Wlo of this step are in TMEM
+            if (X3 && s == 0) {                                   // (steps s > 0: the whole forward was issued at the end of step s-1)
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t bhi = make_sdesc(smem_u32(xf), 128u, x_sbo);
@@ -419,10 +419,39 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                         bulk_g2s4(xt, my_stage + (size_t)(s + 1) * NC * blk + NIMG * tile_floats, NIMG * tile_bytes, &mbar[1]);
                     }
                     __syncwarp();
-                    mbar_wait(&mbar[8], ph);                      // W, Wlo of step s+1 written
+                    // forward of step s+1, pipelined with the W += G pass: the compute warps rewrite the first 64 columns of
+                    // W / Wlo first (mbar[10]) and the rest afterwards (mbar[8]); the MMAs of a K range are issued as soon as
+                    // its columns are in place, so the tensor pipe works on the first half while the pass finishes the second
+                    mbar_wait(&mbar[0], (uint32_t)((s + 1) & 1));  // X tile(s) of step s+1 have landed
+                    // (the momentum variant adds its third chain onto the first chain's accumulator: interleaving the two K
+                    // ranges would change the order of that sum, so it keeps the unpipelined order: kh = 0)
+                    const int kh = MOM ? 0 : (ksteps < 8 ? ksteps : 8);
+                    mbar_wait(&mbar[10], ph);
                     tc_fence_after();
                     T4_STAMP(4);
-                    fwd_ab(s + 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&mbar[5], rs_bytes);
+                        mbar_expect_tx(&mbar[6], ag_bytes);
+                        const uint64_t bhi = make_sdesc(smem_u32(xf), 128u, x_sbo);
+#pragma unroll 4
+                        for (int k = 0; k < kh; ++k)
+                            mma_tf32_ts(d1, w1 + (uint32_t)k * 8u, bhi + (uint64_t)(k * 16), idesc_fwd2, k > 0);
+#pragma unroll 4
+                        for (int k = 0; k < kh; ++k)
+                            mma_tf32_ts(d1 + (MOM ? 0u : 64u), wlo + (uint32_t)k * 8u, bhi + (uint64_t)(k * 16), idesc_fwd, MOM ? true : k > 0);
+                    }
+                    __syncwarp();
+                    mbar_wait(&mbar[8], ph);                      // all of W, Wlo of step s+1 written
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t bhi = make_sdesc(smem_u32(xf), 128u, x_sbo);
+                        for (int k = kh; k < ksteps; ++k)
+                            mma_tf32_ts(d1, w1 + (uint32_t)k * 8u, bhi + (uint64_t)(k * 16), idesc_fwd2, k > 0);
+                        for (int k = kh; k < ksteps; ++k)
+                            mma_tf32_ts(d1 + (MOM ? 0u : 64u), wlo + (uint32_t)k * 8u, bhi + (uint64_t)(k * 16), idesc_fwd, MOM ? true : k > 0);
+                        mma_commit(&mbar[2]);
+                    }
+                    __syncwarp();
                 }
                 T4_STAMP(5);
             } else {
@@ -764,6 +793,12 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                 const int ngrp = FP >> 4;                        // 16-column groups; this thread takes g = half, half+2, ...
                 const bool more = s + 1 < total_steps;
                 for (int g = half; g < ngrp; g += 4) {               // two groups per round: four loads in flight
+                    if (g >= 4 && g < 8) {                           // round 1 rewrote columns 0..63: the issuer may start
+                        tmem_st_wait();                              // the forward MMAs of that K range (pipelined forward)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (more && lane == 0) mbar_arrive(&mbar[10]);
+                    }
                     const bool two = g + 2 < ngrp;
                     float wv[16], gv[16], wv2[16], gv2[16];
                     tmem_ld16(tlane + C::t_w1 + g * 16, wv);
@@ -827,7 +862,10 @@ mlp1_train_tc4_kernel(const TrainParams p, const int FPC, const int FP, const in
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (more && lane == 0) mbar_arrive(&mbar[8]);
+                if (more && lane == 0) {
+                    if (half + 4 >= ngrp) mbar_arrive(&mbar[10]);     // this warp had a single round (FP <= 64 or the last odd group)
+                    mbar_arrive(&mbar[8]);
+                }
             }
             T4_STAMP(10);
             bar_compute();                                       // end of step: gb1p complete, buffers of this step consumed
