@@ -81,6 +81,7 @@ struct Node {
     int64_t model_msgs = 0;                 // model-carrying messages sent so far (keys the partition draw)
     float* scratch = nullptr;               // UPDATE_MERGE: private trainable copy of a received model
     uint64_t pt_draws = 0;                  // PassThroughNode: accept draws made so far (keys the next one)
+    uint64_t cn_draws = 0;                  // CacheNeighNode: cache choices made so far (keys the next one)
     int64_t* sample_idx = nullptr; float* sample_val = nullptr;   // SamplingTMH: the coordinate sample and its merged values
     // All2AllGossipNode: newest model per sender in first-arrival order (a Python dict's order), mixing weights ([0] = self,
     // then one per peer in get_peers() order), and the snapshot shared by the pushes of one timeout
@@ -166,6 +167,14 @@ public:
         nodes_.at(i).peers = peers; nodes_.at(i).mix_w = weights;
     }
     void set_kway_callback(py::function f) { cb_kway_ = std::move(f); }
+    // CacheNeighNode (node.py:196-226): deliveries are only stored (newest per sender); a PUSH / PUSH_PULL send first consumes
+    // one cached model, chosen among the senders in the cache (sorted) by a keyed draw
+    void set_cache_neigh(const std::vector<int64_t>& draws) {
+        if (draws.size() != nodes_.size()) throw std::invalid_argument("one draw counter per node expected");
+        cn_ = true;
+        for (size_t i = 0; i < nodes_.size(); ++i) nodes_[i].cn_draws = (uint64_t)draws[i];
+    }
+    std::vector<int64_t> cn_draws() const { std::vector<int64_t> v; for (const Node& n : nodes_) v.push_back((int64_t)n.cn_draws); return v; }
     // (node, sender, rank, slot, age) of every cached model -- checkpointing
     std::vector<std::vector<int64_t>> caches() const {
         std::vector<std::vector<int64_t>> v;
@@ -254,6 +263,10 @@ public:
             switch (kind) {
                 case EV_SEND:
                     if (a2a_) { if (!snapshot_shared(a, id)) { resume_at_ = i; return evals; } break; }
+                    if (cn_ && aux != MT_PULL) {
+                        if (free_[world_ > 1 ? owner_[a] : 0].empty()) { resume_at_ = i; return evals; }   // (before the cache is touched)
+                        consume_cached(a);
+                    }
                     if (aux != MT_PULL) { if (!snapshot(a, id, can_alias(ev, i, a, b, id, false))) { resume_at_ = i; return evals; } }
                     break;
                 case EV_TIMEOUT:
@@ -280,10 +293,11 @@ public:
                 }
                 case EV_DELIVER:
                     if (a2a_) { if (aux == MT_PUSH) store(b, a, id); break; }
+                    if (cn_) { if (aux == MT_PUSH || aux == MT_PUSH_PULL) store(b, a, id); break; }
                     if (aux == MT_PUSH || aux == MT_PUSH_PULL) consume(b, id);
                     break;
                 case EV_REPLY_DELIVER:
-                    consume(a, id);
+                    if (cn_) store(a, b, id); else consume(a, id);
                     break;
                 case EV_EVAL:
                     evals.push_back(a);
@@ -373,7 +387,7 @@ private:
     // that are dropped.  Same rank only (a peer GPU reads through the published-snapshot protocol).
     template <class Ev>
     bool can_alias(const Ev& ev, int64_t i, int sender, int dst, int32_t msg_id, bool is_reply) const {
-        if (!elide_ || a2a_ || nodes_[sender].alias_state != 0) return false;
+        if (!elide_ || a2a_ || cn_ || nodes_[sender].alias_state != 0) return false;
         if (world_ > 1 && owner_[sender] != owner_[dst]) return false;
         const int64_t n = ev.shape(0), window = std::min<int64_t>(n, i + 1 + 512);
         auto writes_sender = [&](int64_t j) {
@@ -488,6 +502,25 @@ private:
         for (auto& e : nd.cache)
             if (e.first == sender) { release_ref(e.second.first, e.second.second); e.second = where; return; }
         nd.cache.push_back({sender, where});
+    }
+    void consume_cached(int node) {                               // node.py::CacheNeighNode.send: one cached model, keyed choice
+        Node& nd = nodes_.at(node);
+        if (nd.cache.empty()) return;
+        std::vector<int> keys;
+        for (const auto& e : nd.cache) keys.push_back(e.first);
+        std::sort(keys.begin(), keys.end());
+        uint64_t h = mix64(seed_);
+        const uint64_t parts[3] = {0x9A59ull, (uint64_t)node, nd.cn_draws++};
+        for (uint64_t p : parts) h = mix64(h ^ p);
+        const int pick = keys[(size_t)((h & ((1ull << 63) - 1)) % (uint64_t)keys.size())];
+        for (size_t q = 0; q < nd.cache.size(); ++q)
+            if (nd.cache[q].first == pick) {
+                const std::pair<int, int> where = nd.cache[q].second;
+                nd.cache.erase(nd.cache.begin() + (long)q);
+                pools_[where.first][where.second].refs = 0;
+                consume_at(node, where.first, where.second);
+                return;
+            }
     }
     void on_timeout(int node) {                                   // node.py::All2AllGossipNode.on_timeout + WeightedTMH MERGE_UPDATE
         Node& nd = nodes_.at(node);
@@ -605,6 +638,10 @@ private:
         if (it == inflight_.end()) throw std::runtime_error("delivery of an unknown message");
         const int rk = it->second.first, s = it->second.second;
         inflight_.erase(it);
+        consume_at(node, rk, s);
+    }
+    // node `node` consumes the snapshot in slot (rk, s) according to the CreateModelMode (rk < 0: an elided snapshot)
+    void consume_at(int node, int rk, int s) {
         Node& nd = nodes_.at(node);
         const bool aliased = rk < 0;                        // elided snapshot: the "slot" is the sender's live row
         Slot& sl = aliased ? nodes_[-1 - rk].alias : pools_[rk][s];
@@ -775,6 +812,7 @@ private:
     std::unordered_map<int32_t, std::pair<int, int>> inflight_;     // message id -> (rank, slot)
     py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_merge_, cb_sample_merge_, cb_kway_;
     bool a2a_ = false;                               // All2AllGossipNode mode
+    bool cn_ = false;                                // CacheNeighNode mode
     int64_t sample_k_ = 0, n_params_ = 0;            // SamplingTMH: sample size (0 = whole-model merges)
     int n_parts_ = 0; const int64_t* part_id_ = nullptr;
     std::vector<int64_t> deg_;                       // PassThroughNode: node degrees (empty = plain nodes)
@@ -798,6 +836,8 @@ void bind_executor(py::module_& m) {
         .def("set_all2all", &StreamExecutor::set_all2all)
         .def("set_node_mixing", &StreamExecutor::set_node_mixing)
         .def("set_kway_callback", &StreamExecutor::set_kway_callback)
+        .def("set_cache_neigh", &StreamExecutor::set_cache_neigh)
+        .def("cn_draws", &StreamExecutor::cn_draws)
         .def("caches", &StreamExecutor::caches)
         .def("import_cache", &StreamExecutor::import_cache)
         .def("set_sampling", &StreamExecutor::set_sampling)

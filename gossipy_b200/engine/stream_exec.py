@@ -49,7 +49,7 @@ def eligible(sim: Any) -> Optional[str]:
     ids = sorted(sim.nodes)
     if ids != list(range(len(ids))):
         return "node ids must be 0..N-1"
-    from ..node import All2AllGossipNode, PartitioningBasedNode, PassThroughNode, SamplingBasedNode
+    from ..node import All2AllGossipNode, CacheNeighNode, PartitioningBasedNode, PassThroughNode, SamplingBasedNode
     if a2a:
         if sim.protocol != AntiEntropyProtocol.PUSH:
             return "all-to-all: protocol %s" % sim.protocol.name
@@ -69,10 +69,12 @@ def eligible(sim: Any) -> Optional[str]:
             return "all-to-all needs All2AllGossipNode + WeightedTMH"
         if weighted and (h.mode != CreateModelMode.MERGE_UPDATE or node.local_cache and "_stream_exec" not in sim.__dict__):
             return "all-to-all: mode %s / caches filled by another executor" % h.mode.name
-        if type(node) not in (GossipNode, PassThroughNode) and not partitioned and not sampled and not weighted:
+        if type(node) not in (GossipNode, PassThroughNode, CacheNeighNode) and not partitioned and not sampled and not weighted:
             return "node class %s" % type(node).__name__
-        if type(node) is PassThroughNode and not getattr(node, "_keyed_draws", False):
-            return "pass-through nodes with host-stream draws"
+        if type(node) in (PassThroughNode, CacheNeighNode) and not getattr(node, "_keyed_draws", False):
+            return "node-side draws from the host stream"
+        if type(node) is CacheNeighNode and node.local_cache and "_stream_exec" not in sim.__dict__:
+            return "neighbour caches filled by another executor"
         if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH) and not partitioned and not sampled and not weighted:
             return "handler class %s" % type(h).__name__
         if sampled and h.mode != CreateModelMode.MERGE_UPDATE:
@@ -172,6 +174,8 @@ class StreamExec:
                 self.ex.set_node_sample_buffers(i, self._samp_idx[k_].data_ptr(), self._samp_val[k_].data_ptr())
             if not self.cuda:
                 self.ex.set_sample_merge_callback(self._cb_sample_merge)
+        from ..node import CacheNeighNode
+        self.cacheneigh = type(sim.nodes[ids[0]]) is CacheNeighNode
         self.a2a = type(sim).__name__ == "All2AllGossipSimulator"
         if self.a2a:                    # cached neighbourhood + k-way merge on timeout; the pushes of a timeout share a snapshot
             self.ex.set_all2all(True)
@@ -240,6 +244,8 @@ class StreamExec:
             for i, node in self.sim.nodes.items():
                 self.ex.set_node_mixing(i, [int(p) for p in node.p2p_net.get_peers(i)],
                                         [float(w) for w in np.asarray(self.sim._W[i], dtype=float)])
+        if self.cacheneigh:
+            self.ex.set_cache_neigh([int(getattr(self.sim.nodes[i], "_cn_draws", 0)) for i in sorted(self.sim.nodes)])
         if self.passthrough:
             ids = sorted(self.sim.nodes)
             self.ex.set_passthrough([int(self.sim.nodes[i].n_neighs) for i in ids],
@@ -266,6 +272,9 @@ class StreamExec:
                 node._model_msgs = int(msgs[i])
             return
         draws = self.ex.pt_draws() if self.passthrough else None
+        if self.cacheneigh:
+            for i, c in enumerate(self.ex.cn_draws()):
+                self.sim.nodes[i]._cn_draws = int(c)
         for i, node in self.sim.nodes.items():
             h = node.model_handler
             if int(h.n_updates) != ages[i] or h._update_counter != counters[i]:
@@ -391,7 +400,7 @@ class StreamExec:
         idx = torch.as_tensor([r[2] for r in rows], dtype=torch.int64, device=self.device)
         out = {"ids": [int(r[0]) for r in rows], "ages": [int(r[3]) for r in rows], "extra": [list(map(int, r[4:])) for r in rows],
                "rows": self.slots[idx].cpu() if rows else torch.zeros(0, self.row_numel)}
-        if self.a2a:                    # models waiting in the neighbour caches are state as well
+        if self.a2a or self.cacheneigh:  # models waiting in the neighbour caches are state as well
             ent = self.ex.caches()
             cidx = torch.as_tensor([e[3] for e in ent], dtype=torch.int64, device=self.device)
             out["cache"] = {"nodes": [int(e[0]) for e in ent], "senders": [int(e[1]) for e in ent], "ages": [int(e[4]) for e in ent],
@@ -416,7 +425,7 @@ class StreamExec:
             return
         while int(self.slots.shape[0]) < n or self.ex.free_slots < n:
             self._grow()
-        taken = {int(r[2]) for r in self.ex.inflight()} | ({int(e[3]) for e in self.ex.caches()} if self.a2a else set())
+        taken = {int(r[2]) for r in self.ex.inflight()} | {int(e[3]) for e in self.ex.caches()}
         free = [s for s in range(int(self.slots.shape[0])) if s not in taken][:n]
         self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = st["rows"].to(self.device)
         if self.cuda:

@@ -165,7 +165,7 @@ def build(kind, device):
         sim = GossipSimulator(nodes, disp, 10, prt_, delay=UniformDelay(0, 2))
         sim.engine = "native"
         sim.native_executor = True
-    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge", "x_passthrough", "x_sampled"):
+    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge", "x_passthrough", "x_sampled", "x_cacheneigh"):
         # native engine + the C++ executor (csrc/exec): one executor per rank over the same event list
         if kind == "x_mlp_pushpull":
             (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
@@ -180,6 +180,10 @@ def build(kind, device):
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
             n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), (lambda *a, **k: SamplingTMH(.3, *a, **k)), {}
             proto_, kws = AntiEntropyProtocol.PUSH_PULL, dict(delay=UniformDelay(0, 2))
+        elif kind == "x_cacheneigh":
+            (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
+            n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), TorchModelHandler, {}
+            proto_, kws = AntiEntropyProtocol.PUSH_PULL, dict(delay=UniformDelay(0, 2), drop_prob=.1)
         elif kind == "x_passthrough":
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
             n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), TorchModelHandler, {}
@@ -204,6 +208,9 @@ def build(kind, device):
             nodes = PassThroughNode.generate(disp, StaticP2PNetwork(n, A), proto, 10, True)
         elif kind == "x_sampled":
             nodes = SamplingBasedNode.generate(disp, StaticP2PNetwork(n), proto, 10, True)
+        elif kind == "x_cacheneigh":
+            from gossipy_b200.node import CacheNeighNode
+            nodes = CacheNeighNode.generate(disp, StaticP2PNetwork(n), proto, 10, True)
         else:
             nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, kind != "x_limited_push")
         sim = GossipSimulator(nodes, disp, 10, proto_, **kws)

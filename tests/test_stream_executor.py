@@ -12,7 +12,7 @@ pytestmark = pytest.mark.skipif(not native_available(), reason="extension not bu
 
 
 def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=4, device="cpu", sync=True, start=True,
-         mode="MERGE_UPDATE", limited=None, tokenized=False, partitioned=0, passthrough=False, sampled=0.0):
+         mode="MERGE_UPDATE", limited=None, tokenized=False, partitioned=0, passthrough=False, sampled=0.0, cacheneigh=False):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork, UniformDelay
     from gossipy_b200.data import DataDispatcher, synthetic
@@ -53,6 +53,9 @@ def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=
     else:
         proto = TorchModelHandler(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), **kwh)
     topo = StaticP2PNetwork(n)
+    if cacheneigh:
+        from gossipy_b200.node import CacheNeighNode
+        node_cls = CacheNeighNode
     if passthrough:                 # degree-aware pass-through needs unequal degrees: a ring plus a hub
         from gossipy_b200.node import PassThroughNode
         node_cls = PassThroughNode
@@ -175,6 +178,41 @@ def test_native_executor_sampled_models(kw):
     sim_b, rep_b = _sim(True, **kw)
     assert "_stream_exec" in sim_b.__dict__ and "_stream_exec" not in sim_a.__dict__
     _same(sim_a, rep_a, sim_b, rep_b)
+    g.CACHE.clear()
+
+
+@pytest.mark.parametrize("kw", [dict(model="logreg", protocol="PUSH", cacheneigh=True, faults=True),
+                                dict(model="mlp", protocol="PUSH_PULL", cacheneigh=True),
+                                dict(model="logreg", protocol="PUSH_PULL", cacheneigh=True, mode="UPDATE", limited=None, faults=True, sync=False)])
+def test_native_executor_cache_neighbour_nodes(kw):
+    """CacheNeighNode (reference node.py:395-496) from C++: deliveries are stored per sender, one cached model (keyed
+    choice) is consumed before every PUSH / PUSH_PULL snapshot."""
+    import gossipy_b200 as g
+    sim_a, rep_a = _sim(False, n=7, **kw)
+    sim_b, rep_b = _sim(True, n=7, **kw)
+    assert "_stream_exec" in sim_b.__dict__ and "_stream_exec" not in sim_a.__dict__
+    draws = [getattr(nd, "_cn_draws", 0) for nd in sim_a.nodes.values()]
+    assert draws == [getattr(nd, "_cn_draws", 0) for nd in sim_b.nodes.values()] and sum(draws) > 0
+    _same(sim_a, rep_a, sim_b, rep_b)
+    g.CACHE.clear()
+
+
+def test_cache_neighbour_executor_checkpoint_keeps_the_caches(tmp_path):
+    import gossipy_b200 as g
+    from gossipy_b200.simul import GossipSimulator
+    kw = dict(model="logreg", protocol="PUSH", cacheneigh=True, faults=True, n=7)
+    sim_full, rep_full = _sim(True, rounds=6, **kw)
+    sim, rep = _sim(True, start=False, **kw)
+    sim.start(3)
+    assert len(sim._stream_exec.ex.caches()) > 0
+    path = str(tmp_path / "ck.pkl")
+    sim.save(path)
+    g.CACHE.clear()
+    sim2 = GossipSimulator.load(path)
+    rep2 = [r for r in sim2._receivers if type(r).__name__ == "SimulationReport"][0]
+    sim2.start(3, resume=True)
+    assert "_stream_exec" in sim2.__dict__
+    _same(sim_full, rep_full, sim2, rep2)
     g.CACHE.clear()
 
 
@@ -322,7 +360,7 @@ def test_native_executor_cuda_equals_python_executor():
         g.CACHE.clear()
     for kw in (dict(model="mlp", protocol="PUSH_PULL", mode="UPDATE_MERGE"), dict(model="logreg", protocol="PUSH", mode="UPDATE_MERGE", limited=3, faults=True),
                dict(model="mlp", protocol="PUSH", partitioned=4, faults=True), dict(model="mlp", protocol="PUSH_PULL", sampled=.2),
-               dict(model="logreg", protocol="PUSH", passthrough=True, faults=True)):
+               dict(model="logreg", protocol="PUSH", passthrough=True, faults=True), dict(model="mlp", protocol="PUSH_PULL", cacheneigh=True)):
         sim_a, rep_a = _sim(False, n=8, rounds=4, device="cuda:0", **kw)
         sim_b, rep_b = _sim(True, n=8, rounds=4, device="cuda:0", **kw)
         torch.cuda.synchronize()
