@@ -82,6 +82,7 @@ struct Node {
     float* scratch = nullptr;               // UPDATE_MERGE: private trainable copy of a received model
     uint64_t pt_draws = 0;                  // PassThroughNode: accept draws made so far (keys the next one)
     uint64_t cn_draws = 0;                  // CacheNeighNode: cache choices made so far (keys the next one)
+    float* mom = nullptr; bool mom_first = false;   // fused momentum-SGD: the momentum-buffer row, still without state?
     int64_t* sample_idx = nullptr; float* sample_val = nullptr;   // SamplingTMH: the coordinate sample and its merged values
     // All2AllGossipNode: newest model per sender in first-arrival order (a Python dict's order), mixing weights ([0] = self,
     // then one per peer in get_peers() order), and the snapshot shared by the pushes of one timeout
@@ -167,6 +168,12 @@ public:
         nodes_.at(i).peers = peers; nodes_.at(i).mix_w = weights;
     }
     void set_kway_callback(py::function f) { cb_kway_ = std::move(f); }
+    // torch.optim.SGD with momentum inside the tensor-core kernel (MERGE_UPDATE: plain pair merge, then the momentum kernel --
+    // what model/handler.py does for these handlers)
+    void set_momentum(double mu, double dampening, bool nesterov) { momentum_ = (float)mu; dampening_ = (float)dampening; nesterov_ = nesterov; }
+    void set_node_momentum(int i, uintptr_t buf, bool first) { nodes_.at(i).mom = reinterpret_cast<float*>(buf); nodes_.at(i).mom_first = first; }
+    std::vector<int> mom_first() const { std::vector<int> v; for (const Node& n : nodes_) v.push_back(n.mom_first ? 1 : 0); return v; }
+    void set_merge_pair_callback(py::function f) { cb_merge_pair_ = std::move(f); }
     // CacheNeighNode (node.py:196-226): deliveries are only stored (newest per sender); a PUSH / PUSH_PULL send first consumes
     // one cached model, chosen among the senders in the cache (sorted) by a keyed draw
     void set_cache_neigh(const std::vector<int64_t>& draws) {
@@ -617,9 +624,14 @@ private:
             p.row = nd.row; p.X = nd.X; p.y = nd.y; p.n = nd.n; p.IN = IN_; p.H = H_; p.OUT = OUT_;
             p.B = B_ == 0 ? nd.n : std::min(B_, nd.n); p.epochs = epochs_; p.lr = lr_; p.wd = wd_; p.key = key;
             if (peer) { p.peer = peer; p.w_self = ws; p.w_peer = wp; p.sync = sync; }
+            if (momentum_ != 0.f) {
+                if (nd.mom == nullptr) throw std::runtime_error("fused momentum-SGD needs a momentum row per node (set_node_momentum)");
+                p.momentum = momentum_; p.dampening = dampening_; p.nesterov = nesterov_; p.mom = nd.mom; p.mom_first = nd.mom_first;
+            }
             p.stage_mode = stage_mode;
             ok = launch_mlp1_train(p, kTrainAuto, nd.stream, &why);
             if (stage_mode == 1) return ok;
+            nd.mom_first = false;
         } else {
             if (stage_mode == 1) return false;
             LogregParams p{};
@@ -675,7 +687,7 @@ private:
         }
         // fused MERGE_UPDATE of the MLP: the operand loader of the training kernel does not depend on the incoming model,
         // so it is issued BEFORE this stream waits for the snapshot (off the critical path of a gossip chain)
-        const bool hoist = exec && cuda_ && !remote && sl.written && n_parts_ == 0 && sample_k_ == 0 && mode == 2 && family_ == 0;
+        const bool hoist = exec && cuda_ && !remote && sl.written && n_parts_ == 0 && sample_k_ == 0 && mode == 2 && family_ == 0 && momentum_ == 0.f;
         if (!hoist) reader_done();
         if (exec && cuda_) {
             if (remote) sync = PeerSync{sl.ready, sl.gen, sl.done, device_fault_word()};
@@ -762,10 +774,20 @@ private:
             }
         } else {
             float ws = 0.f, wp = 1.f;
-            const bool fused_merge = mode == 2;            // MERGE_UPDATE: the merge rides on the training kernel
+            const bool fused_merge = mode == 2 && momentum_ == 0.f;   // MERGE_UPDATE: the merge rides on the training kernel
             if (fused_merge) {
                 merge_weights(nd.age, sl.age, ws, wp);
                 nd.age = std::max(nd.age, sl.age);
+            } else if (mode == 2) {                        // momentum-SGD: pair merge, then the momentum kernel (handler.py: _merge, _update)
+                merge_weights(nd.age, sl.age, ws, wp);
+                nd.age = std::max(nd.age, sl.age);
+                if (wp == 0.f) {                           // the own model is much older: nothing is read (nor acknowledged)
+                    if (remote) sl.remote_reads -= 1;
+                } else if (exec) {
+                    if (cuda_) launch_merge_pair(nd.row, sl.data, ws, wp, 0, row_floats_, sync, nd.stream);
+                    else cb_merge_pair_(node, rk, s, ws, wp, (int64_t)sl.gen);
+                    ++launches_;
+                }
             } else {                                       // UPDATE: adopt (a true copy: heals a diverged model), then train
                 if (exec) {
                     if (cuda_) launch_merge_pair(nd.row, sl.data, 0.f, 1.f, 0, row_floats_, sync, nd.stream);
@@ -813,6 +835,8 @@ private:
     py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_merge_, cb_sample_merge_, cb_kway_;
     bool a2a_ = false;                               // All2AllGossipNode mode
     bool cn_ = false;                                // CacheNeighNode mode
+    float momentum_ = 0.f, dampening_ = 0.f; bool nesterov_ = false;     // fused momentum-SGD (0 = plain SGD)
+    py::function cb_merge_pair_;
     int64_t sample_k_ = 0, n_params_ = 0;            // SamplingTMH: sample size (0 = whole-model merges)
     int n_parts_ = 0; const int64_t* part_id_ = nullptr;
     std::vector<int64_t> deg_;                       // PassThroughNode: node degrees (empty = plain nodes)
@@ -836,6 +860,10 @@ void bind_executor(py::module_& m) {
         .def("set_all2all", &StreamExecutor::set_all2all)
         .def("set_node_mixing", &StreamExecutor::set_node_mixing)
         .def("set_kway_callback", &StreamExecutor::set_kway_callback)
+        .def("set_momentum", &StreamExecutor::set_momentum)
+        .def("set_node_momentum", &StreamExecutor::set_node_momentum)
+        .def("mom_first", &StreamExecutor::mom_first)
+        .def("set_merge_pair_callback", &StreamExecutor::set_merge_pair_callback)
         .def("set_cache_neigh", &StreamExecutor::set_cache_neigh)
         .def("cn_draws", &StreamExecutor::cn_draws)
         .def("caches", &StreamExecutor::caches)

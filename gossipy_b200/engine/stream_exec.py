@@ -79,7 +79,13 @@ def eligible(sim: Any) -> Optional[str]:
             return "handler class %s" % type(h).__name__
         if sampled and h.mode != CreateModelMode.MERGE_UPDATE:
             return "sampled models: mode %s" % h.mode.name
-        if not h._fused or h.layout.int_buffers:
+        momentum = bool(h.__dict__.get("_fused_momentum")) and not h._fused
+        if momentum:            # torch.optim.SGD with momentum inside the tensor-core kernel: plain nodes, MERGE_UPDATE
+            n_i = int(node.data[0][0].shape[0]) if isinstance(node.data[0], (tuple, list)) else 0
+            if (partitioned or sampled or weighted or h.mode != CreateModelMode.MERGE_UPDATE
+                    or not ops.mlp1_momentum_supported(h._family[1], h.batch_size, n_i)):
+                return "momentum-SGD outside the fused envelope"
+        if not (h._fused or momentum) or h.layout.int_buffers:
             return "handler is not on the fused kernel path"
         if partitioned:
             if h.mode != CreateModelMode.MERGE_UPDATE:
@@ -93,7 +99,9 @@ def eligible(sim: Any) -> Optional[str]:
             return "vector-valued model age"
         sig = (h._family, h.batch_size, h.local_epochs, float(h.optimizer_params.get("lr", 1e-3)),
                float(h.optimizer_params.get("weight_decay", 0.0)), h._row_numel, type(h), h.mode,
-               getattr(h, "L", None), h.tm_partition.n_parts if partitioned else 0, getattr(h, "sample_size", None))
+               getattr(h, "L", None), h.tm_partition.n_parts if partitioned else 0, getattr(h, "sample_size", None),
+               (float(h.optimizer_params.get("momentum", 0.0)), float(h.optimizer_params.get("dampening", 0.0)),
+                bool(h.optimizer_params.get("nesterov", False))) if momentum else None)
         if ref is None:
             ref = sig
         elif sig != ref:
@@ -176,6 +184,13 @@ class StreamExec:
                 self.ex.set_sample_merge_callback(self._cb_sample_merge)
         from ..node import CacheNeighNode
         self.cacheneigh = type(sim.nodes[ids[0]]) is CacheNeighNode
+        self.momentum = None
+        if h0.__dict__.get("_fused_momentum") and not h0._fused:
+            p0 = h0.optimizer_params
+            self.momentum = (float(p0.get("momentum", 0.0)), float(p0.get("dampening", 0.0)), bool(p0.get("nesterov", False)))
+            self.ex.set_momentum(*self.momentum)
+            if not self.cuda:
+                self.ex.set_merge_pair_callback(self._cb_merge_pair)
         self.a2a = type(sim).__name__ == "All2AllGossipSimulator"
         if self.a2a:                    # cached neighbourhood + k-way merge on timeout; the pushes of a timeout share a snapshot
             self.ex.set_all2all(True)
@@ -244,6 +259,18 @@ class StreamExec:
             for i, node in self.sim.nodes.items():
                 self.ex.set_node_mixing(i, [int(p) for p in node.p2p_net.get_peers(i)],
                                         [float(w) for w in np.asarray(self.sim._W[i], dtype=float)])
+        if self.momentum is not None:
+            self._mom_first = {}
+            for i, node in self.sim.nodes.items():
+                if not self._mine(i):
+                    continue
+                h = node.model_handler
+                buf = h._opt_rows.get("momentum")
+                first = buf is None or bool(h.__dict__.get("_mom_pending"))
+                if buf is None:
+                    buf = h._opt_rows["momentum"] = torch.zeros_like(h.row)
+                self.ex.set_node_momentum(i, buf.data_ptr(), first)
+                self._mom_first[i] = first          # (CPU: the callback trains, so the flag is kept here)
         if self.cacheneigh:
             self.ex.set_cache_neigh([int(getattr(self.sim.nodes[i], "_cn_draws", 0)) for i in sorted(self.sim.nodes)])
         if self.passthrough:
@@ -271,6 +298,10 @@ class StreamExec:
                 h._update_counter = int(counters[i])
                 node._model_msgs = int(msgs[i])
             return
+        if self.momentum is not None:       # a buffer the executor created but never used still has no state
+            for i, first in enumerate(self.ex.mom_first()):
+                if self._mine(i):
+                    self.sim.nodes[i].model_handler._mom_pending = bool(first if self.cuda else self._mom_first.get(i, False))
         draws = self.ex.pt_draws() if self.passthrough else None
         if self.cacheneigh:
             for i, c in enumerate(self.ex.cn_draws()):
@@ -314,6 +345,10 @@ class StreamExec:
         src, sync = self._slot(rank, slot, gen)
         ops.merge_pair(self.sim.nodes[node].model_handler.row, src, 0.0, 1.0, sync=sync)
 
+    def _cb_merge_pair(self, node: int, rank: int, slot: int, w_self: float, w_peer: float, gen: int) -> None:
+        src, sync = self._slot(rank, slot, gen)
+        ops.merge_pair(self.sim.nodes[node].model_handler.row, src, float(w_self), float(w_peer), sync=sync)
+
     def _cb_train(self, node: int, rank: int, slot: int, key: int, w_self: float, w_peer: float, gen: int) -> None:
         h = self.sim.nodes[node].model_handler
         x, y = self._data[node]
@@ -322,6 +357,12 @@ class StreamExec:
         if slot >= 0:
             src, sync = self._slot(rank, slot, gen)
             merge = (src, float(w_self), float(w_peer), sync)
+        if self.momentum is not None:
+            first = bool(self._mom_first.get(node, False))
+            self._mom_first[node] = False
+            fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key), None, merge_from=merge,
+               momentum=self.momentum + (h._opt_rows["momentum"], first))
+            return
         fn(h.row, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key), None, merge_from=merge)
 
     def _cb_update_merge(self, node: int, rank: int, slot: int, key_own: int, key_tmp: int, w_self: float, w_peer: float,

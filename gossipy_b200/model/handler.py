@@ -900,8 +900,8 @@ class TorchModelHandler(RowHandler):
             x = x.reshape(x.shape[0], -1)
         if momentum:          # torch.optim.SGD(momentum=...): the buffer row is the one the flat optimizer kernel uses
             buf = self._opt_rows.get("momentum")
-            first = buf is None
-            if first:
+            first = buf is None or bool(self.__dict__.pop("_mom_pending", False))   # (a buffer the C++ executor created but never used)
+            if buf is None:
                 buf = self._opt_rows["momentum"] = torch.zeros_like(self.row)
             mom = (float(p.get("momentum", 0.0)), float(p.get("dampening", 0.0)), bool(p.get("nesterov", False)), buf, first)
             return fn(self.row, x, y, dims, self.batch_size, self.local_epochs, lr, wd, self._next_key(), None,

@@ -165,7 +165,7 @@ def build(kind, device):
         sim = GossipSimulator(nodes, disp, 10, prt_, delay=UniformDelay(0, 2))
         sim.engine = "native"
         sim.native_executor = True
-    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge", "x_passthrough", "x_sampled", "x_cacheneigh"):
+    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge", "x_passthrough", "x_sampled", "x_cacheneigh", "x_momentum"):
         # native engine + the C++ executor (csrc/exec): one executor per rank over the same event list
         if kind == "x_mlp_pushpull":
             (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
@@ -179,6 +179,10 @@ def build(kind, device):
             from gossipy_b200.node import SamplingBasedNode
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
             n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), (lambda *a, **k: SamplingTMH(.3, *a, **k)), {}
+            proto_, kws = AntiEntropyProtocol.PUSH_PULL, dict(delay=UniformDelay(0, 2))
+        elif kind == "x_momentum":
+            (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(480, 200)
+            n, bs, net, cls, kwh = 5, 32, TorchMLP(784, 10, (100,)), TorchModelHandler, {}
             proto_, kws = AntiEntropyProtocol.PUSH_PULL, dict(delay=UniformDelay(0, 2))
         elif kind == "x_cacheneigh":
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
@@ -197,7 +201,8 @@ def build(kind, device):
             n, bs, net, cls = 5, 16, LogisticRegression(57, 2), TorchModelHandler
             kwh, proto_, kws = {"create_model_mode": CreateModelMode.UPDATE}, AntiEntropyProtocol.PULL, dict(delay=UniformDelay(0, 3))
         disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
-        proto = cls(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), batch_size=bs, **kwh)
+        opt_kw = {"lr": .05, "momentum": .9} if kind == "x_momentum" else {"lr": .1, "weight_decay": .001}
+        proto = cls(net, torch.optim.SGD, opt_kw, torch.nn.CrossEntropyLoss(), batch_size=bs, **kwh)
         if kind == "x_passthrough":
             from gossipy_b200.node import PassThroughNode
             A = np.zeros((n, n), dtype=int)

@@ -84,7 +84,7 @@ def test_pens_two_and_three_ranks_cpu_equal_single_process():
     _compare(single, _run(3, "cpu", rounds=9, kinds="pens"), rel=1e-5, skip=("cache_left",))
 
 
-XKINDS = "x_mlp_pushpull,x_limited_push,x_update_pull,x_update_merge,x_passthrough,x_sampled,x_cacheneigh,x_all2all,x_part_mlp,x_part_logreg"
+XKINDS = "x_mlp_pushpull,x_limited_push,x_update_pull,x_update_merge,x_passthrough,x_sampled,x_cacheneigh,x_momentum,x_all2all,x_part_mlp,x_part_logreg"
 
 
 def test_cpp_executor_two_and_three_ranks_cpu_equal_single_process():

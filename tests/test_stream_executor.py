@@ -12,7 +12,7 @@ pytestmark = pytest.mark.skipif(not native_available(), reason="extension not bu
 
 
 def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=4, device="cpu", sync=True, start=True,
-         mode="MERGE_UPDATE", limited=None, tokenized=False, partitioned=0, passthrough=False, sampled=0.0, cacheneigh=False):
+         mode="MERGE_UPDATE", limited=None, tokenized=False, partitioned=0, passthrough=False, sampled=0.0, cacheneigh=False, momentum=None):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, StaticP2PNetwork, UniformDelay
     from gossipy_b200.data import DataDispatcher, synthetic
@@ -50,6 +50,8 @@ def _sim(streamed, model="mlp", protocol="PUSH_PULL", faults=False, n=6, rounds=
     elif limited is not None:
         proto = LimitedMergeTMH(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(),
                                 age_diff_threshold=limited, **kwh)
+    elif momentum is not None:
+        proto = TorchModelHandler(net, torch.optim.SGD, dict({"lr": .05, "weight_decay": .001}, **momentum), torch.nn.CrossEntropyLoss(), **kwh)
     else:
         proto = TorchModelHandler(net, torch.optim.SGD, {"lr": .1, "weight_decay": .001}, torch.nn.CrossEntropyLoss(), **kwh)
     topo = StaticP2PNetwork(n)
@@ -216,6 +218,25 @@ def test_cache_neighbour_executor_checkpoint_keeps_the_caches(tmp_path):
     g.CACHE.clear()
 
 
+@pytest.mark.parametrize("kw", [dict(momentum={"momentum": .9}, protocol="PUSH_PULL"), dict(momentum={"momentum": .8, "nesterov": True}, protocol="PUSH", faults=True),
+                                dict(momentum={"momentum": .9, "dampening": .1}, protocol="PULL", cacheneigh=False, passthrough=True)])
+def test_native_executor_momentum_sgd(kw):
+    """torch.optim.SGD with momentum (fused into the tensor-core kernel on a GPU) from C++: pair merge, then the momentum
+    update with the node's own buffer row (MERGE_UPDATE keeps the optimizer state at the node)."""
+    import gossipy_b200 as g
+    sim_a, rep_a = _sim(False, model="mlp", **kw)
+    sim_b, rep_b = _sim(True, model="mlp", **kw)
+    assert "_stream_exec" in sim_b.__dict__ and "_stream_exec" not in sim_a.__dict__
+    _same(sim_a, rep_a, sim_b, rep_b)
+    for i in sim_a.nodes:                       # the momentum buffers carry the same state
+        ba, bb = sim_a.nodes[i].model_handler._opt_rows.get("momentum"), sim_b.nodes[i].model_handler._opt_rows.get("momentum")
+        if ba is not None:
+            assert bb is not None and torch.equal(ba, bb)
+        else:                                   # never updated: the executor's buffer exists but is marked as stateless
+            assert bb is None or sim_b.nodes[i].model_handler.__dict__.get("_mom_pending")
+    g.CACHE.clear()
+
+
 def test_executor_race_debug_mode(monkeypatch):
     """GOSSIPY_EXEC_DEBUG=1: slot life-cycle assertions (one writer, one reader per life; no slot both free and on the
     wire; no message id twice) hold on a faulty run and fire on a forged event list."""
@@ -360,7 +381,8 @@ def test_native_executor_cuda_equals_python_executor():
         g.CACHE.clear()
     for kw in (dict(model="mlp", protocol="PUSH_PULL", mode="UPDATE_MERGE"), dict(model="logreg", protocol="PUSH", mode="UPDATE_MERGE", limited=3, faults=True),
                dict(model="mlp", protocol="PUSH", partitioned=4, faults=True), dict(model="mlp", protocol="PUSH_PULL", sampled=.2),
-               dict(model="logreg", protocol="PUSH", passthrough=True, faults=True), dict(model="mlp", protocol="PUSH_PULL", cacheneigh=True)):
+               dict(model="logreg", protocol="PUSH", passthrough=True, faults=True), dict(model="mlp", protocol="PUSH_PULL", cacheneigh=True),
+               dict(model="mlp", protocol="PUSH_PULL", momentum={"momentum": .9})):
         sim_a, rep_a = _sim(False, n=8, rounds=4, device="cuda:0", **kw)
         sim_b, rep_b = _sim(True, n=8, rounds=4, device="cuda:0", **kw)
         torch.cuda.synchronize()
