@@ -409,10 +409,11 @@ def test_native_executor_equals_python_executor_random_setups():
               suppress_health_check=list(HealthCheck))
     @given(protocol=st.sampled_from(["PUSH", "PULL", "PUSH_PULL"]), mode=st.sampled_from(["MERGE_UPDATE", "UPDATE", "UPDATE_MERGE", "PASS"]),
            faults=st.booleans(), sync=st.booleans(), limited=st.sampled_from([None, 0, 3, 50]), tokenized=st.booleans(),
-           n=st.integers(2, 9), rounds=st.integers(1, 4))
-    def check(protocol, mode, faults, sync, limited, tokenized, n, rounds):
+           n=st.integers(2, 9), rounds=st.integers(1, 4), node=st.sampled_from(["gossip", "gossip", "passthrough", "cacheneigh"]))
+    def check(protocol, mode, faults, sync, limited, tokenized, n, rounds, node):
         kw = dict(model="logreg", protocol=protocol, mode=mode, faults=faults, sync=sync, limited=limited,
-                  tokenized=tokenized, n=n, rounds=rounds)
+                  tokenized=tokenized, n=max(n, 3) if node == "passthrough" else n, rounds=rounds,
+                  passthrough=node == "passthrough", cacheneigh=node == "cacheneigh")
         sim_a, rep_a = _sim(False, **kw)
         sim_b, rep_b = _sim(True, **kw)
         assert "_stream_exec" in sim_b.__dict__
