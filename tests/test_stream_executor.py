@@ -495,3 +495,37 @@ def test_all_to_all_executor_checkpoint_keeps_the_caches(tmp_path):
     sim2.start(sim._mix, 3, resume=True)
     _same(sim_full, rep_full, sim2, rep2)
     g.CACHE.clear()
+
+
+def test_native_executor_variants_random_setups():
+    """Derandomised sweep over the executor's other modes (all-to-all, sampled, partitioned, momentum) x protocol x faults x
+    clocks x sizes; EXEC_EXAMPLES to stress (1 500 random set-ups pass, also with GOSSIPY_EXEC_DEBUG=1)."""
+    import os
+    import gossipy_b200 as g
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=int(os.environ.get("EXEC_EXAMPLES", "10")), deadline=None, derandomize=True, database=None,
+              suppress_health_check=list(HealthCheck))
+    @given(kind=st.sampled_from(["a2a", "sampled", "part", "momentum"]), model=st.sampled_from(["logreg", "mlp"]),
+           protocol=st.sampled_from(["PUSH", "PULL", "PUSH_PULL"]), faults=st.booleans(), sync=st.booleans(), n=st.integers(2, 8),
+           rounds=st.integers(1, 4), tokenized=st.booleans(), frac=st.sampled_from([.05, .3, 1.0]), parts=st.sampled_from([2, 4, 7]),
+           ring=st.booleans(), nesterov=st.booleans())
+    def check(kind, model, protocol, faults, sync, n, rounds, tokenized, frac, parts, ring, nesterov):
+        if kind == "a2a":
+            kw = dict(model=model, n=max(n, 3) if ring else n, rounds=rounds, faults=faults, sync=sync, mixing="ring" if ring else "uniform")
+            sim_a, rep_a = _a2a_sim(False, **kw)
+            sim_b, rep_b = _a2a_sim(True, **kw)
+        else:
+            kw = dict(model=model, protocol=protocol, faults=faults, sync=sync, n=n, rounds=rounds, tokenized=tokenized)
+            if kind == "sampled":
+                kw["sampled"] = frac
+            elif kind == "part":
+                kw["partitioned"] = parts
+            else:
+                kw.update(model="mlp", momentum={"momentum": .9, "nesterov": nesterov})
+            sim_a, rep_a = _sim(False, **kw)
+            sim_b, rep_b = _sim(True, **kw)
+        assert "_stream_exec" in sim_b.__dict__, (kind, kw)
+        _same(sim_a, rep_a, sim_b, rep_b)
+        g.CACHE.clear()
+    check()
