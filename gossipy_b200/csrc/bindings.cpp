@@ -211,7 +211,7 @@ at::Tensor mlp1_train_tc_debug(at::Tensor row, at::Tensor X, at::Tensor y,
                                std::tuple<int64_t, int64_t, int64_t> dims, int64_t batch_size,
                                int64_t local_epochs, double lr, double wd, int64_t key, std::string impl) {
     // runs a tcgen05 kernel with its debug buffer attached: lr == 0 -> relu(z1) [128, 32] of the first
-    // step (bring-up test); lr != 0 (tc2) -> average cycles per step of each phase in the first 6 floats
+    // step (bring-up test); lr != 0 -> average cycles per step of each phase in the first 6 floats
     auto dbg = at::zeros({128, 32}, row.options());
     g_debug_ptr = dbg.data_ptr<float>();
     mlp1_train(row, X, y, dims, batch_size, local_epochs, lr, wd, key, c10::nullopt, c10::nullopt, impl,
@@ -223,7 +223,7 @@ at::Tensor mlp1_train_tc_debug(at::Tensor row, at::Tensor X, at::Tensor y,
 std::tuple<at::Tensor, at::Tensor, at::Tensor, int64_t> mlp1_stage_debug(at::Tensor X, at::Tensor y,
                                                                          int64_t batch_size, int64_t local_epochs,
                                                                          int64_t key) {
-    // runs the device-side loader of the tc2 training kernel and returns (XF, XT, YS, FP)
+    // runs the device-side loader of the tc3 training kernel and returns (XF, XT, YS, FP)
     check_row(X, "X");
     TORCH_CHECK(y.is_cuda() && y.scalar_type() == at::kLong && y.is_contiguous());
     const int n = (int)X.size(0), IN = (int)X.size(1);

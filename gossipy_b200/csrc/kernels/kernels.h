@@ -94,7 +94,7 @@ bool mlp1_train_tc3(const TrainParams& p, cudaStream_t stream);    // CTA pair, 
 bool mlp1_train_tc4(const TrainParams& p, int nc, bool x3, cudaStream_t stream);
 bool reserve_train_staging(int n, int IN, int B, int epochs, int nc, bool x3, cudaStream_t stream);
 size_t mlp1_stage4_bytes(int n, int IN, int B, int epochs, int NC, bool x3, int* FPC_out, int* FP_out, int* steps_out);
-// device-side data loader of tc2: shuffled mini-batches in both UMMA operand layouts
+// device-side data loader of the tc3 training kernel: shuffled mini-batches in both UMMA operand layouts
 size_t mlp1_stage_bytes(int n, int IN, int B, int epochs, int* FPC_out, int* FP_out, int* steps_out);
 bool launch_mlp1_stage(const float* X, const int64_t* y, int n, int IN, int B, int epochs, uint64_t key,
                        void* staging, cudaStream_t stream);
