@@ -191,8 +191,8 @@ public:
         return v;
     }
     void import_cache(const std::vector<std::vector<int64_t>>& rows) {        // slots already filled by Python
-        for (const auto& r : rows) {
-            const int rk = 0, s = (int)r.at(2);
+        for (const auto& r : rows) {                                            // (node, sender, slot, age [, rank])
+            const int rk = r.size() > 4 ? (int)r.at(4) : 0, s = (int)r.at(2);
             auto& fl = free_.at(rk);
             auto it = std::find(fl.begin(), fl.end(), s);
             if (it == fl.end()) throw std::invalid_argument("slot is not free");

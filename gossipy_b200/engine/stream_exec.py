@@ -434,42 +434,78 @@ class StreamExec:
         self._publish_slots()
 
     # -- checkpointing -----------------------------------------------------------------------------------------
+    def _slot_rows(self, where: List[Any]) -> torch.Tensor:
+        """The contents of the slots ``[(rank, slot), ...]`` as one CPU tensor.  Several ranks: every owner contributes its
+        slots (one small all-gather), so the checkpoint of every rank is complete."""
+        if not where:
+            return torch.zeros(0, self.row_numel)
+        if not self.multi:
+            idx = torch.as_tensor([s for _, s in where], dtype=torch.int64, device=self.device)
+            return self.slots[idx].cpu()
+        import torch.distributed as dist
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
+        local = {(int(r), int(s)): self.pool_rows[int(r)][int(s)].tensor.detach().cpu().clone()
+                 for r, s in where if int(r) == self.rank}
+        gathered: List[Any] = [None] * len(self.pool_rows)
+        dist.all_gather_object(gathered, local)
+        merged = {k: v for part in gathered for k, v in part.items()}
+        return torch.stack([merged[(int(r), int(s))] for r, s in where])
+
     def export_inflight(self) -> Dict[str, Any]:
-        if self.multi:
-            raise NotImplementedError("checkpointing the C++ executor with several ranks")
         rows = self.ex.inflight()
-        idx = torch.as_tensor([r[2] for r in rows], dtype=torch.int64, device=self.device)
-        out = {"ids": [int(r[0]) for r in rows], "ages": [int(r[3]) for r in rows], "extra": [list(map(int, r[4:])) for r in rows],
-               "rows": self.slots[idx].cpu() if rows else torch.zeros(0, self.row_numel)}
+        out = {"ids": [int(r[0]) for r in rows], "ranks": [int(r[1]) for r in rows], "ages": [int(r[3]) for r in rows],
+               "extra": [list(map(int, r[4:])) for r in rows], "rows": self._slot_rows([(r[1], r[2]) for r in rows])}
         if self.a2a or self.cacheneigh:  # models waiting in the neighbour caches are state as well
             ent = self.ex.caches()
-            cidx = torch.as_tensor([e[3] for e in ent], dtype=torch.int64, device=self.device)
-            out["cache"] = {"nodes": [int(e[0]) for e in ent], "senders": [int(e[1]) for e in ent], "ages": [int(e[4]) for e in ent],
-                            "rows": self.slots[cidx].cpu() if ent else torch.zeros(0, self.row_numel)}
+            out["cache"] = {"nodes": [int(e[0]) for e in ent], "senders": [int(e[1]) for e in ent], "ranks": [int(e[2]) for e in ent],
+                            "ages": [int(e[4]) for e in ent], "rows": self._slot_rows([(e[2], e[3]) for e in ent])}
         return out
+
+    def _restore_slots(self, ranks: List[int], rows: torch.Tensor) -> List[int]:
+        """Free slots (one per entry, in the pool of the entry's rank -- the same choice on every rank) filled with ``rows``
+        by their owners."""
+        n = len(ranks)
+        if not self.multi:
+            while int(self.slots.shape[0]) < n or self.ex.free_slots < n:
+                self._grow()
+            taken = {int(r[2]) for r in self.ex.inflight()} | {int(e[3]) for e in self.ex.caches()}
+            free = [s for s in range(int(self.slots.shape[0])) if s not in taken][:n]
+            self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = rows.to(self.device)
+            return free
+        taken = {(int(r[1]), int(r[2])) for r in self.ex.inflight()} | {(int(e[2]), int(e[3])) for e in self.ex.caches()}
+        chosen: List[int] = []
+        for i, rk in enumerate(ranks):
+            while True:
+                free = [s for s in range(len(self.pool_rows[rk])) if (rk, s) not in taken]
+                if free:
+                    break
+                self._add_pool_rows(len(self.pool_rows[0]))
+            taken.add((rk, free[0]))
+            chosen.append(free[0])
+            if rk == self.rank:
+                self.pool_rows[rk][free[0]].tensor.copy_(rows[i].to(self.device))
+        return chosen
+
+    def _after_restore(self) -> None:
+        if self.cuda:
+            torch.cuda.synchronize(self.device)     # the node streams read these slots without a writer event
+        if self.multi:
+            from ..parallel import runtime as prt
+            prt.barrier()                           # ... and no rank reads a peer's slot before its owner has filled it
 
     def import_inflight(self, st: Dict[str, Any]) -> None:
         cache = st.get("cache")
         if cache is not None and len(cache["nodes"]):
-            m = len(cache["nodes"])
-            while int(self.slots.shape[0]) < m or self.ex.free_slots < m:
-                self._grow()
-            taken = {int(r[2]) for r in self.ex.inflight()} | {int(e[3]) for e in self.ex.caches()}
-            free = [s for s in range(int(self.slots.shape[0])) if s not in taken][:m]
-            self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = cache["rows"].to(self.device)
-            self.ex.import_cache([[int(nd), int(sd), int(s), int(a)] for nd, sd, s, a in
-                                  zip(cache["nodes"], cache["senders"], free, cache["ages"])])
+            ranks = [int(r) for r in cache.get("ranks", [0] * len(cache["nodes"]))]
+            free = self._restore_slots(ranks, cache["rows"])
+            self.ex.import_cache([[int(nd), int(sd), int(s), int(a), int(rk)] for nd, sd, s, a, rk in
+                                  zip(cache["nodes"], cache["senders"], free, cache["ages"], ranks)])
         n = len(st["ids"])
-        if n == 0:
-            if self.cuda:
-                torch.cuda.synchronize(self.device)
-            return
-        while int(self.slots.shape[0]) < n or self.ex.free_slots < n:
-            self._grow()
-        taken = {int(r[2]) for r in self.ex.inflight()} | {int(e[3]) for e in self.ex.caches()}
-        free = [s for s in range(int(self.slots.shape[0])) if s not in taken][:n]
-        self.slots[torch.as_tensor(free, dtype=torch.int64, device=self.device)] = st["rows"].to(self.device)
-        if self.cuda:
-            torch.cuda.synchronize(self.device)     # the node streams read these slots without a writer event
-        extra = st.get("extra") or [[] for _ in range(n)]
-        self.ex.import_inflight([[int(m), 0, int(s), int(a)] + list(e) for m, s, a, e in zip(st["ids"], free, st["ages"], extra)])
+        if n:
+            ranks = [int(r) for r in st.get("ranks", [0] * n)]
+            free = self._restore_slots(ranks, st["rows"])
+            extra = st.get("extra") or [[] for _ in range(n)]
+            self.ex.import_inflight([[int(m), int(rk), int(s), int(a)] + list(e)
+                                     for m, rk, s, a, e in zip(st["ids"], ranks, free, st["ages"], extra)])
+        self._after_restore()

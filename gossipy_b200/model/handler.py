@@ -602,7 +602,9 @@ class RowHandler(ModelHandler):
         self._row = None
         self._restore_members()
         if saved is not None:
-            self._ensure_row().tensor.copy_(saved)
+            row = self._ensure_row()            # (several ranks: every rank replays the allocation ...)
+            if self._mine():                    # ... but only the owner restores the values: a peer's copy may be older
+                row.tensor.copy_(saved)
         opt = self.__dict__.get("_opt_rows")
         if opt:
             self._opt_rows = {k: v.to(self.device) for k, v in opt.items()}

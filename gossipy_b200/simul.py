@@ -485,7 +485,13 @@ class GossipSimulator(SimulationEventSender):
 
     def _configure_scheduler(self, sch) -> None:
         node = self.nodes[0]
-        extras = len(node._payload_extras())
+        counters = {k: node.__dict__.get(k) for k in ("_model_msgs", "_pt_draws", "_cn_draws")}
+        extras = len(node._payload_extras())        # only the NUMBER of extras matters here ...
+        for k, v in counters.items():               # ... a keyed draw it may have made must not count (exact resume)
+            if v is None:
+                node.__dict__.pop(k, None)
+            else:
+                node.__dict__[k] = v
         sch.set_message_sizes(int(node.model_handler.get_size()) + extras, 1)
 
     def _run_native(self, n_rounds: int, resume: bool = False) -> None:
@@ -716,6 +722,12 @@ class GossipSimulator(SimulationEventSender):
         with open(filename, "rb") as f:
             loaded = _pickler.load(f)
         CACHE.load(loaded["cache"])
+        from .parallel import runtime as _prt
+        if _prt.active():                   # every owner has restored its rows before any rank reads a peer's
+            if GlobalSettings().get_device().type == "cuda":
+                import torch
+                torch.cuda.synchronize()
+            _prt.barrier()
         return loaded["simul"]
 
     def __getstate__(self) -> Dict[str, Any]:
@@ -733,7 +745,7 @@ class GossipSimulator(SimulationEventSender):
             if bank is not None:
                 pending = [int(r[1]) for r in state["msg_q"] if int(r[4]) != 2] + [int(r[1]) for r in state["rep_q"]]
                 st["_bank_inflight"] = bank.export_inflight(pending)
-            if sx is not None and not sx.multi:      # (several ranks: in-flight snapshots live in other processes)
+            if sx is not None:                       # (several ranks: the owners' slots are gathered, every rank saves all)
                 st["_exec_inflight"] = sx.export_inflight()
         return st
 

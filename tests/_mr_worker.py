@@ -243,7 +243,20 @@ def run(kind, device, rounds):
     from gossipy_b200.parallel import runtime as prt
     sim, rep, start_args = build(kind, device)
     sim.init_nodes(seed=5)
-    sim.start(*start_args, rounds, **getattr(sim, "_mr_kwargs", {}))
+    if os.environ.get("MR_CHECKPOINT"):
+        # interrupted run: half of the rounds, checkpoint (every rank writes its own file), reload, resume
+        import tempfile
+        first = max(1, rounds // 2)
+        sim.start(*start_args, first, **getattr(sim, "_mr_kwargs", {}))
+        path = os.path.join(tempfile.gettempdir(), "gb200_mr_ckpt_%d_%d.pkl" % (os.getpid(), prt.rank() if prt.active() else 0))
+        sim.save(path)
+        g.CACHE.clear()
+        sim = type(sim).load(path)
+        os.remove(path)
+        rep = [r for r in sim._receivers if type(r).__name__ == "SimulationReport"][0]
+        sim.start(*start_args, rounds - first, resume=True)
+    else:
+        sim.start(*start_args, rounds, **getattr(sim, "_mr_kwargs", {}))
     if device.startswith("cuda"):
         torch.cuda.synchronize()
     sums = {}

@@ -24,8 +24,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(world, device, rounds=3, kinds=KINDS, transport=None, arena_rows=None):
+def _run(world, device, rounds=3, kinds=KINDS, transport=None, arena_rows=None, checkpoint=False):
     env = dict(os.environ, OMP_NUM_THREADS="1")
+    if checkpoint:
+        env["MR_CHECKPOINT"] = "1"
     if transport:
         env["GOSSIPY_B200_TRANSPORT"] = transport
     if arena_rows:
@@ -98,6 +100,16 @@ def test_cpp_executor_two_and_three_ranks_cpu_equal_single_process():
         _compare(single, multi, rel=1e-5)
 
 
+def test_checkpoint_with_several_ranks_resumes_exactly():
+    """save / load with two ranks: every rank writes a complete checkpoint (the owners' in-flight snapshot slots and cached
+    models are gathered), only owners restore row values, a barrier separates restoring from reading; the interrupted run
+    equals the uninterrupted single-process run -- Python executor and C++ executor (delays, caches, partitioned models)."""
+    kinds = "mlp_pushpull,limited_pull,x_update_pull,x_limited_push,x_all2all,x_cacheneigh,x_part_logreg"
+    single = _run(1, "cpu", rounds=6, kinds=kinds)
+    _compare(single, _run(1, "cpu", rounds=6, kinds=kinds, checkpoint=True), rel=1e-5)
+    _compare(single, _run(2, "cpu", rounds=6, kinds=kinds, checkpoint=True), rel=1e-5)
+
+
 def test_symmetric_arenas_grow_when_they_run_out():
     """Segments of 4 rows: the shared arenas (and the C++ executor's snapshot pools on them) must add segments
     collectively, in the middle of a round, without changing the results."""
@@ -123,6 +135,15 @@ def test_banked_engine_two_and_three_ranks_cpu_equal_single_process():
 def test_generic_conv_model_two_ranks_cpu_equal_single_process():
     single = _run(1, "cpu", rounds=4, kinds="cnn_pushpull")
     _compare(single, _run(2, "cpu", rounds=4, kinds="cnn_pushpull"), rel=1e-4)
+
+
+@pytest.mark.gpu
+def test_checkpoint_with_two_ranks_cuda_resumes_exactly():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    kinds = "x_update_pull,x_all2all"
+    single = _run(1, "cuda:0", rounds=6, kinds=kinds)
+    _compare(single, _run(2, "cuda", rounds=6, kinds=kinds, checkpoint=True), rel=2e-3)
 
 
 @pytest.mark.gpu

@@ -199,6 +199,26 @@ def test_native_executor_cache_neighbour_nodes(kw):
     g.CACHE.clear()
 
 
+@pytest.mark.parametrize("kw", [dict(model="logreg", protocol="PUSH", partitioned=4, faults=True), dict(model="logreg", protocol="PUSH_PULL", sampled=.3, faults=True),
+                                dict(model="logreg", protocol="PUSH", passthrough=True, faults=True, n=7)])
+def test_executor_checkpoint_of_keyed_node_classes_is_exact(kw, tmp_path):
+    """Node classes with keyed draws (partition ids, samples, accept draws): building the scheduler again after a load must not
+    consume a draw (it used to: the partitioned resume was off by one message counter)."""
+    import gossipy_b200 as g
+    from gossipy_b200.simul import GossipSimulator
+    sim_full, rep_full = _sim(True, rounds=6, **kw)
+    sim, rep = _sim(True, start=False, **kw)
+    sim.start(3)
+    path = str(tmp_path / "ck.pkl")
+    sim.save(path)
+    g.CACHE.clear()
+    sim2 = GossipSimulator.load(path)
+    rep2 = [r for r in sim2._receivers if type(r).__name__ == "SimulationReport"][0]
+    sim2.start(3, resume=True)
+    _same(sim_full, rep_full, sim2, rep2)
+    g.CACHE.clear()
+
+
 def test_cache_neighbour_executor_checkpoint_keeps_the_caches(tmp_path):
     import gossipy_b200 as g
     from gossipy_b200.simul import GossipSimulator
