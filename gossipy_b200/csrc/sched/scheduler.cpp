@@ -140,12 +140,27 @@ public:
         tokenized_ = kind != TK_NONE; utility_ = utility;
     }
     void set_broadcast(bool all_peers) { broadcast_ = all_peers; emit_timeouts_ = all_peers; }   // All2All
+    // Restrict node i's peer choice to `peers` (empty = back to its neighbourhood): PENS step 2 gossips only with
+    // the peers its selection phase preferred (gossipy/node.py:729-741).  Part of the CONFIGURATION: the caller
+    // re-applies it after set_state (the lists are derived from node state that is checkpointed with the nodes).
+    void set_peer_list(int i, const std::vector<int32_t>& peers) {
+        if (i < 0 || i >= n_) throw std::invalid_argument("node index out of range");
+        for (int32_t p : peers)
+            if (p < 0 || p >= n_) throw std::invalid_argument("peer index out of range");
+        if (peer_list_.empty()) peer_list_.resize(n_);
+        peer_list_[i] = peers;
+    }
 
     // Simulate `rounds` rounds starting at the internal clock; returns the events as an int32 array
     // [n_events, 6] = (kind, tick, a, b, slot, aux).
-    py::array_t<int32_t> run(int rounds) {
+    py::array_t<int32_t> run(int rounds) { return run_ticks((int64_t)rounds * delta_); }
+    // Same, for `ticks` timesteps (a round may be simulated in pieces when the caller has to change the
+    // configuration at a tick inside it, e.g. the PENS step switch; shuffles and evaluations stay tied to the
+    // absolute clock, so run_ticks(a) + run_ticks(b) produce the events of run_ticks(a + b)).
+    py::array_t<int32_t> run_ticks(int64_t ticks) {
+        if (ticks < 0) throw std::invalid_argument("ticks must be non-negative");
         events_.clear();
-        const int64_t first = clock_, last = clock_ + (int64_t)rounds * delta_;
+        const int64_t first = clock_, last = clock_ + ticks;
         for (int64_t t = first; t < last; ++t) {
             if (t % delta_ == 0) shuffle();
             for (int idx = 0; idx < n_; ++idx) tick_node(order_[idx], t);
@@ -273,6 +288,11 @@ private:
             for (int k = 0; k < deg; ++k) send_to(i, peer_at(i, k), t);
             return true;
         }
+        if (!peer_list_.empty() && !peer_list_[i].empty()) {
+            const std::vector<int32_t>& pl = peer_list_[i];
+            send_to(i, pl[(size_t)r_peer_.below((uint64_t)pl.size())], t);
+            return true;
+        }
         send_to(i, peer_at(i, (int)r_peer_.below((uint64_t)deg)), t);
         return true;
     }
@@ -341,6 +361,7 @@ private:
     Stream r_order_, r_peer_, r_drop_, r_online_, r_delay_, r_eval_, r_token_;
     std::vector<int> sync_, offset_, round_len_, order_;
     std::vector<int64_t> indptr_; std::vector<int32_t> indices_; bool clique_ = true;
+    std::vector<std::vector<int32_t>> peer_list_;          // per-node restriction of the peer choice (empty = none)
     int delay_kind_ = DELAY_CONST; double delay_a_ = 0, delay_b_ = 0;
     int64_t size_model_ = 1, size_pull_ = 1;
     std::vector<TokenAccount> accounts_; bool tokenized_ = false; int64_t utility_ = 1;
@@ -364,7 +385,9 @@ void bind_scheduler(py::module_& m) {
         .def("set_message_sizes", &GossipScheduler::set_message_sizes)
         .def("set_token_account", &GossipScheduler::set_token_account)
         .def("set_broadcast", &GossipScheduler::set_broadcast)
+        .def("set_peer_list", &GossipScheduler::set_peer_list)
         .def("run", &GossipScheduler::run, py::arg("rounds") = 1)
+        .def("run_ticks", &GossipScheduler::run_ticks, py::arg("ticks"))
         .def_property("clock", &GossipScheduler::clock, &GossipScheduler::set_clock)
         .def_property_readonly("sent", &GossipScheduler::sent)
         .def_property_readonly("failed", &GossipScheduler::failed)

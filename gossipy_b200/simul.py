@@ -32,7 +32,7 @@ from .core import (AntiEntropyProtocol, ConstantDelay, Delay, Message, MessageTy
 from .data import DataDispatcher
 from .flow_control import TokenAccount
 from .model.handler import ModelHandler, PendingEval
-from .node import All2AllGossipNode, GossipNode
+from .node import All2AllGossipNode, GossipNode, PENSNode
 from .utils import StringEncoder
 from .utils.profiling import nvtx_range
 
@@ -440,6 +440,8 @@ class GossipSimulator(SimulationEventSender):
             return "extension not built"
         for node in self.nodes.values():
             cls = type(node)
+            if cls is PENSNode:          # its step switch and peer choice are driven from _run_native (_pens_switch)
+                continue
             if cls.timed_out is not GossipNode.timed_out and not isinstance(node, All2AllGossipNode):
                 return "node class overrides timed_out"
             if cls.get_peer is not GossipNode.get_peer:
@@ -546,40 +548,41 @@ class GossipSimulator(SimulationEventSender):
             if _sx.eligible(self) is None:
                 self._run_native_streamed(sch, n_rounds)
                 return
-        SEND, DROP, DELIVER, RSEND, RDELIVER, EVAL, TIMEOUT = (C.EV_SEND, C.EV_DROP, C.EV_DELIVER,
-                                                              C.EV_REPLY_SEND, C.EV_REPLY_DELIVER, C.EV_EVAL,
-                                                              C.EV_TIMEOUT)
         msgs = self._native_msgs
         prev_finish = None
+        pens = [n for n in self.nodes.values() if type(n) is PENSNode]
+        for node in pens:                  # resumed run: the restricted peer lists are configuration, not scheduler state
+            if node.step == 2 and node.best_nodes:
+                sch.set_peer_list(node.idx, [int(p) for p in node.best_nodes])
         try:
             for _ in range(n_rounds):
                 if self.stream_inputs:
                     self._stream_round_inputs()
-                with nvtx_range("schedule"):
-                    events = sch.run(1)
-                pending_reply: Optional[Message] = None
                 eval_nodes: List[GossipNode] = []
+                if not pens:
+                    with nvtx_range("schedule"):
+                        events = sch.run(1).tolist()
+                    eval_nodes = self._native_execute(events, msgs)
+                else:
+                    # PENS (ref node.py:716-741): a node leaves step 1 at the first tick of round `step1_rounds`.  The
+                    # round is simulated in pieces so that the switch (peer list of the scheduler, `step` of the node,
+                    # which decides how a delivery is consumed) falls between two pieces, each executed before the next
+                    t_end = int(sch.clock) + self.delta
+                    while int(sch.clock) < t_end:
+                        t0, nxt = int(sch.clock), t_end
+                        for node in pens:
+                            if node.step == 1:
+                                t_sw = int(node.step1_rounds) * int(node.round_len)
+                                if t_sw <= t0:
+                                    node.step = 2
+                                    node._select_neighbors()
+                                    sch.set_peer_list(node.idx, [int(p) for p in node.best_nodes])
+                                elif t_sw < nxt:
+                                    nxt = t_sw
+                        with nvtx_range("schedule"):
+                            events = sch.run_ticks(nxt - t0).tolist()
+                        eval_nodes += self._native_execute(events, msgs)
                 t_last = int(sch.clock) - 1
-                for kind, t, a, b, slot, aux in events.tolist():
-                    if kind == SEND:
-                        msg = self._native_send(self.nodes[a], t, b)
-                        msgs[slot] = msg
-                        self.notify_message(False, msg)
-                    elif kind == DROP:
-                        self._lost(msgs.pop(slot, None))
-                    elif kind == DELIVER:
-                        pending_reply = self.nodes[b].receive(t, msgs.pop(slot))
-                    elif kind == RSEND:
-                        msgs[aux] = pending_reply
-                        pending_reply = None
-                    elif kind == RDELIVER:
-                        reply = msgs.pop(slot)
-                        self.notify_message(False, reply)
-                        self.nodes[a].receive(t, reply)
-                    elif kind == EVAL:
-                        eval_nodes.append(self.nodes[a])
-                    elif kind == TIMEOUT:
-                        self._native_timeout(self.nodes[a], t)
                 # software pipelining of the host: the metrics of round r are read back only after
                 # round r+1 has been enqueued (evaluation snapshots the statistics on the device)
                 finish = self._evaluate_nodes(t_last, eval_nodes, defer=self.pipeline_eval)
@@ -701,7 +704,41 @@ class GossipSimulator(SimulationEventSender):
         bank.writeback()
         self.notify_end()
 
+    def _native_execute(self, events: List[List[int]], msgs: Dict[int, Message]) -> List[GossipNode]:
+        """Per-event executor of the native control plane: turns the scheduler's events (rows of
+        ``kind, tick, a, b, slot, aux``) into node calls; returns the nodes to evaluate."""
+        from .ops.native import _try_import
+        C = _try_import()
+        SEND, DROP, DELIVER, RSEND, RDELIVER, EVAL, TIMEOUT = (C.EV_SEND, C.EV_DROP, C.EV_DELIVER,
+                                                              C.EV_REPLY_SEND, C.EV_REPLY_DELIVER, C.EV_EVAL,
+                                                              C.EV_TIMEOUT)
+        pending_reply: Optional[Message] = None
+        eval_nodes: List[GossipNode] = []
+        for kind, t, a, b, slot, aux in events:
+            if kind == SEND:
+                msg = self._native_send(self.nodes[a], t, b)
+                msgs[slot] = msg
+                self.notify_message(False, msg)
+            elif kind == DROP:
+                self._lost(msgs.pop(slot, None))
+            elif kind == DELIVER:
+                pending_reply = self.nodes[b].receive(t, msgs.pop(slot))
+            elif kind == RSEND:
+                msgs[aux] = pending_reply
+                pending_reply = None
+            elif kind == RDELIVER:
+                reply = msgs.pop(slot)
+                self.notify_message(False, reply)
+                self.nodes[a].receive(t, reply)
+            elif kind == EVAL:
+                eval_nodes.append(self.nodes[a])
+            elif kind == TIMEOUT:
+                self._native_timeout(self.nodes[a], t)
+        return eval_nodes
+
     def _native_send(self, node: GossipNode, t: int, peer: int) -> Message:
+        if type(node) is PENSNode and node.step == 1:      # what PENSNode.get_peer counts (ref node.py:733-737)
+            node.selected[peer] += 1
         return node.send(t, peer, self.protocol)
 
     def _native_timeout(self, node: GossipNode, t: int) -> None:

@@ -221,7 +221,7 @@ def build(kind, device):
         sim = GossipSimulator(nodes, disp, 10, proto_, **kws)
         sim.engine = "native"
         sim.native_executor = True
-    elif kind == "pens":              # performance-based neighbour selection: data-dependent top-m, then step 2
+    elif kind in ("pens", "pens_native"):              # performance-based neighbour selection: data-dependent top-m, then step 2
         from gossipy_b200.node import PENSNode
         (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
         disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=6, eval_on_user=False)
@@ -230,6 +230,8 @@ def build(kind, device):
                                   create_model_mode=CreateModelMode.MERGE_UPDATE)
         nodes = PENSNode.generate(disp, StaticP2PNetwork(6), proto, 10, True, n_sampled=2, m_top=1, step1_rounds=5)
         sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
+        if kind == "pens_native":      # C++ control plane: step switch and restricted peer lists in the scheduler
+            sim.engine = "native"
     else:
         raise ValueError(kind)
     sim.progress = False

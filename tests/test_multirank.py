@@ -182,6 +182,14 @@ def test_nccl_transport_two_ranks_cuda_equal_single_gpu():
     _compare(_run(1, "cuda:0", kinds=kinds), _run(2, "cuda", kinds=kinds, transport="nccl"), rel=2e-3)
 
 
+def test_pens_native_scheduler_two_ranks_cpu_equal_single_process():
+    """PENS under the C++ scheduler: the restricted peer lists of step 2 derive from the replicated selection
+    counters, so every rank computes the same schedule."""
+    single = _run(1, "cpu", rounds=9, kinds="pens_native")
+    assert any(v for v in single["pens_native"]["best"].values()), "step 2 was never reached"
+    _compare(single, _run(2, "cpu", rounds=9, kinds="pens_native"), rel=1e-5, skip=("cache_left",))
+
+
 @pytest.mark.gpu
 def test_pens_two_ranks_cuda_equal_single_gpu():
     if torch.cuda.device_count() < 2:

@@ -337,3 +337,121 @@ def test_python_checkpoint_resumed_under_native_engine_returns_pending_snapshots
     sim.engine = "python"
     assert sum(len(q) for q in sim._msg_queues.values()) == 0
     g.CACHE.clear()
+
+
+# ---------------------------------------------------------------------------------------------
+# PENS under the C++ control plane: step switch between two pieces of a round, restricted peer lists
+# ---------------------------------------------------------------------------------------------
+def test_scheduler_run_in_pieces_and_peer_lists():
+    from gossipy_b200.ops.native import _try_import
+    C = _try_import()
+
+    def make():
+        s = C.GossipScheduler(9, 10, 1, 0.1, 0.9, 0.0, 5)
+        s.set_nodes([1] * 9, [i % 10 for i in range(9)], [10] * 9)
+        s.set_delay(1, 0, 4)
+        return s
+    a, b = make(), make()
+    whole = np.concatenate([a.run(1) for _ in range(3)])
+    pieces = np.concatenate([b.run_ticks(k) for k in (3, 7, 1, 0, 12, 7)])       # 30 ticks in odd pieces
+    assert np.array_equal(whole, pieces) and a.clock == b.clock == 30
+    b.set_peer_list(2, [7, 8])
+    b.set_peer_list(4, [0])
+    ev = np.concatenate([b.run(1) for _ in range(20)])
+    sends = ev[ev[:, 0] == C.EV_SEND]
+    assert set(sends[sends[:, 2] == 2][:, 3].tolist()) == {7, 8}
+    assert set(sends[sends[:, 2] == 4][:, 3].tolist()) == {0}
+    assert len(set(sends[sends[:, 2] == 3][:, 3].tolist())) > 2                  # the others keep their neighbourhood
+    b.set_peer_list(2, [])
+    ev = np.concatenate([b.run(1) for _ in range(20)])
+    sends = ev[ev[:, 0] == C.EV_SEND]
+    assert len(set(sends[sends[:, 2] == 2][:, 3].tolist())) > 2
+    with pytest.raises(Exception):
+        b.set_peer_list(0, [9])
+
+
+def _pens_sim(engine, rounds, step1_rounds=4, round_len=10, resume_from=None):
+    import gossipy_b200 as g
+    from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import TorchModelHandler
+    from gossipy_b200.model.nn import LogisticRegression
+    from gossipy_b200.node import PENSNode
+    from gossipy_b200.simul import GossipSimulator, SimulationEventReceiver, SimulationReport
+
+    class Sends(SimulationEventReceiver):
+        def __init__(self):
+            self.log = []
+
+        def update_message(self, failed, msg=None):
+            if not failed and msg is not None:
+                self.log.append((int(msg.timestamp), int(msg.sender), int(msg.receiver)))
+
+        def update_evaluation(self, *a, **k): pass
+        def update_timestep(self, t): pass
+        def update_end(self): pass
+
+    g.set_seed(11)
+    (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(700, 200)
+    disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=7, eval_on_user=False)
+    proto = TorchModelHandler(LogisticRegression(57, 2), torch.optim.SGD, {"lr": .5}, torch.nn.CrossEntropyLoss(),
+                              batch_size=16, create_model_mode=CreateModelMode.MERGE_UPDATE)
+    nodes = PENSNode.generate(disp, StaticP2PNetwork(7), proto, round_len, True, n_sampled=3, m_top=1,
+                              step1_rounds=step1_rounds)
+    sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
+    sim.progress = False
+    sim.engine = engine
+    rep, sends = SimulationReport(), Sends()
+    sim.add_receiver(rep)
+    sim.add_receiver(sends)
+    sim.init_nodes(seed=4)
+    sim.start(rounds)
+    return sim, rep, sends
+
+
+@pytest.mark.parametrize("round_len", [10, 5])
+def test_pens_runs_under_the_native_scheduler(round_len):
+    """PENSNode overrides ``timed_out`` / ``get_peer`` (ref node.py:716-741): the C++ scheduler takes both over --
+    the step switch falls between two pieces of a round, step 2 draws from the node's ``best_nodes``."""
+    import gossipy_b200 as g
+    sim, rep, sends = _pens_sim("native", rounds=9, step1_rounds=4, round_len=round_len)
+    assert "_scheduler" in sim.__dict__ and sim._native_supported() is None
+    t_sw = 4 * round_len
+    step1 = [s for s in sends.log if s[0] < t_sw]
+    step2 = [s for s in sends.log if s[0] >= t_sw]
+    assert step1 and step2
+    for node in sim.nodes.values():
+        assert node.step == 2 and node.best_nodes is not None
+        mine = [r for t, s, r in step1 if s == node.idx]
+        assert sum(node.selected.values()) == len(mine)               # what get_peer counts in step 1
+        assert all(node.selected[p] == mine.count(p) for p in node.selected)
+        if node.best_nodes:
+            assert {r for t, s, r in step2 if s == node.idx} <= set(node.best_nodes)
+    assert sum(sum(n.neigh_counter.values()) for n in sim.nodes.values()) > 0    # selections happened (n_sampled = 3)
+    assert any(n.best_nodes for n in sim.nodes.values())
+    acc = [m["accuracy"] for _, m in rep.get_evaluation(False)]
+    assert len(acc) == 9 and acc[-1] > 0.6
+    g.CACHE.clear()
+
+
+def test_pens_native_checkpoint_resume_is_exact(tmp_path):
+    import gossipy_b200 as g
+    from gossipy_b200.simul import GossipSimulator
+    full, rep_full, sends_full = _pens_sim("native", rounds=8, step1_rounds=3)
+    rows_full = {i: n.model_handler.row.clone() for i, n in full.nodes.items()}
+    g.CACHE.clear()
+    for cut in (2, 5):                    # one checkpoint inside step 1 (cached candidates), one inside step 2
+        sim, _, _ = _pens_sim("native", rounds=cut, step1_rounds=3)
+        path = str(tmp_path / ("pens%d.pkl" % cut))
+        sim.save(path)
+        g.CACHE.clear()
+        del sim
+        sim2 = GossipSimulator.load(path)
+        sim2.start(8 - cut, resume=True)
+        for i, n in sim2.nodes.items():
+            torch.testing.assert_close(n.model_handler.row, rows_full[i], rtol=1e-6, atol=1e-7)
+            assert n.best_nodes == full.nodes[i].best_nodes and n.selected == full.nodes[i].selected
+        rep2 = [r for r in sim2._receivers if type(r).__name__ == "SimulationReport"][0]
+        assert rep2._sent_messages == rep_full._sent_messages
+        g.CACHE.clear()
