@@ -37,6 +37,7 @@ _MODE = {CreateModelMode.UPDATE: 1, CreateModelMode.MERGE_UPDATE: 2, CreateModel
 
 
 _OPEN: List["LinearBank"] = []      # banks holding shared-memory segments (closed by parallel.runtime.shutdown)
+_BANK_SEQ = 0                        # banks created in this session (names their shared-memory segments)
 
 
 def close_all() -> None:
@@ -235,7 +236,9 @@ class LinearBank:
             self.slot_age = nat.tensor_from_ptr(base + off_age, [2 * cap], dev_index, True).view(torch.int64)
         else:
             from multiprocessing import shared_memory
-            names = ["gb200_bank_%s_%d" % (prt.session_tag(), r) for r in range(W)]
+            global _BANK_SEQ                  # (a resumed checkpoint builds a second bank in the same session)
+            _BANK_SEQ += 1
+            names = ["gb200_bank_%s_%d_%d" % (prt.session_tag(), _BANK_SEQ, r) for r in range(W)]
             mine = shared_memory.SharedMemory(name=names[self.rank], create=True, size=total)
             np.frombuffer(mine.buf, dtype=np.uint8)[:] = 0
             dist.barrier()
@@ -692,40 +695,85 @@ class LinearBank:
 
     # -- synchronise the object API -----------------------------------------------------------------------
     # -- checkpointing -----------------------------------------------------------------------------
-    def export_inflight(self, message_ids: List[int]) -> Dict[str, Any]:
-        """Snapshots of the messages that are still on the wire (ids from the scheduler's queues)."""
-        if self.multi:
-            raise NotImplementedError("checkpointing the banked engine with several ranks")
+    def export_inflight(self, message_ids: List[int], receivers: Optional[List[int]] = None) -> Dict[str, Any]:
+        """Snapshots of the messages that are still on the wire (ids from the scheduler's queues; ``receivers`` = the
+        node each of them travels to).  Several ranks: a snapshot lives in the bank of its receiver's rank, so every
+        rank contributes its part and all ranks end up with the complete set (every rank writes a full checkpoint)."""
         ids = np.asarray(message_ids, dtype=np.int64)
+        recv = np.asarray(receivers if receivers is not None else np.zeros(ids.size), dtype=np.int64)
         slots = self.slot_map[ids % _RING] if ids.size else np.zeros(0, dtype=np.int64)
         keep = slots >= 0
-        ids, slots = ids[keep], slots[keep]
-        idx = torch.as_tensor(slots, dtype=torch.int64, device=self.device)
-        out = {"ids": ids, "rows": self.S[idx].cpu(), "ages": self.slot_age[idx].cpu()}
+        ids, slots, recv = ids[keep], slots[keep], recv[keep]
+        ent = []
         if self.cacheneigh:                 # models waiting in the neighbour caches are state as well
             ent = [(n, s, sl) for n, cache in enumerate(self.cn_cache) for s, sl in sorted(cache.items())]
+        if self.multi:
+            return self._export_inflight_multi(ids, slots, recv, ent)
+        idx = torch.as_tensor(slots, dtype=torch.int64, device=self.device)
+        out = {"ids": ids, "receivers": recv, "rows": self.S[idx].cpu(), "ages": self.slot_age[idx].cpu()}
+        if self.cacheneigh:
             cidx = torch.as_tensor([e[2] for e in ent], dtype=torch.int64, device=self.device)
             out["cn"] = {"nodes": [e[0] for e in ent], "senders": [e[1] for e in ent],
                          "rows": self.S[cidx].cpu(), "ages": self.slot_age[cidx].cpu()}
         return out
 
+    def _export_inflight_multi(self, ids: np.ndarray, slots: np.ndarray, recv: np.ndarray, ent: List) -> Dict[str, Any]:
+        import torch.distributed as dist
+        self._barrier()                     # everything pushed towards this rank has landed
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+        def local(sl: np.ndarray):
+            idx = torch.as_tensor(sl, dtype=torch.int64, device=self.device)
+            return self.S[idx].cpu().clone(), self.slot_age[idx].cpu().clone()
+        mine = self.slot_rank[ids % _RING] == self.rank
+        part: Dict[str, Any] = {"ids": ids[mine], "receivers": recv[mine]}
+        part["rows"], part["ages"] = local(slots[mine])
+        own_ent = [e for e in ent if self.owner[e[0]] == self.rank]       # a cached model sits on its holder's rank
+        part["cn_nodes"], part["cn_senders"] = [e[0] for e in own_ent], [e[1] for e in own_ent]
+        part["cn_rows"], part["cn_ages"] = local(np.asarray([e[2] for e in own_ent], dtype=np.int64))
+        parts: List[Any] = [None] * self.world
+        dist.all_gather_object(parts, part)
+        out = {"ids": np.concatenate([q["ids"] for q in parts]), "receivers": np.concatenate([q["receivers"] for q in parts]),
+               "rows": torch.cat([q["rows"] for q in parts]), "ages": torch.cat([q["ages"] for q in parts])}
+        if self.cacheneigh:
+            out["cn"] = {"nodes": [n for q in parts for n in q["cn_nodes"]], "senders": [x for q in parts for x in q["cn_senders"]],
+                         "rows": torch.cat([q["cn_rows"] for q in parts]), "ages": torch.cat([q["cn_ages"] for q in parts])}
+        return out
+
+    def _place(self, dst_nodes: np.ndarray, rows: torch.Tensor, ages: torch.Tensor) -> Tuple[np.ndarray, np.ndarray]:
+        """Slots for restored snapshots that travel to / are cached at ``dst_nodes``; returns (slots, ranks)."""
+        k = int(dst_nodes.size)
+        if not self.multi:
+            slots = self._alloc(k)
+            idx = torch.as_tensor(slots, dtype=torch.int64, device=self.device)
+            self.S[idx] = rows.to(self.device)
+            self.slot_age[idx] = ages.to(self.device)
+            return slots, np.zeros(k, dtype=np.int64)
+        ranks = self.owner[dst_nodes]
+        slots = self._alloc_multi(ranks)            # replicated bookkeeping; every rank fills the slots of its own bank
+        mine = ranks == self.rank
+        if mine.any():
+            idx = torch.as_tensor(slots[mine], dtype=torch.int64, device=self.device)
+            sel = torch.as_tensor(np.flatnonzero(mine), dtype=torch.int64)
+            self.S[idx] = rows[sel].to(self.device)
+            self.slot_age[idx] = ages[sel].to(self.device)
+        return slots, ranks
+
     def import_inflight(self, st: Dict[str, Any]) -> None:
         cn = st.get("cn")
         if cn is not None and len(cn["nodes"]):
-            slots = self._alloc(len(cn["nodes"]))
-            idx = torch.as_tensor(slots, dtype=torch.int64, device=self.device)
-            self.S[idx] = cn["rows"].to(self.device)
-            self.slot_age[idx] = cn["ages"].to(self.device)
+            slots, _ = self._place(np.asarray(cn["nodes"], dtype=np.int64), cn["rows"], cn["ages"])
             for n, s, sl in zip(cn["nodes"], cn["senders"], slots.tolist()):
                 self.cn_cache[n][s] = sl
         ids = np.asarray(st["ids"], dtype=np.int64)
         if ids.size == 0:
             return
-        slots = self._alloc(int(ids.size))
-        idx = torch.as_tensor(slots, dtype=torch.int64, device=self.device)
-        self.S[idx] = st["rows"].to(self.device)
-        self.slot_age[idx] = st["ages"].to(self.device)
+        recv = np.asarray(st.get("receivers", np.zeros(ids.size)), dtype=np.int64)
+        slots, ranks = self._place(recv, st["rows"], st["ages"])
         self.slot_map[ids % _RING] = slots
+        if self.multi:
+            self.slot_rank[ids % _RING] = ranks
 
     def writeback(self) -> None:
         W = self.W[:, :self.D]

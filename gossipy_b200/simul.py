@@ -780,8 +780,8 @@ class GossipSimulator(SimulationEventSender):
             state = dict(sch.get_state())
             st["_scheduler_state"] = state
             if bank is not None:
-                pending = [int(r[1]) for r in state["msg_q"] if int(r[4]) != 2] + [int(r[1]) for r in state["rep_q"]]
-                st["_bank_inflight"] = bank.export_inflight(pending)
+                rows = [r for r in state["msg_q"] if int(r[4]) != 2] + list(state["rep_q"])     # (due, id, sender, receiver, ..)
+                st["_bank_inflight"] = bank.export_inflight([int(r[1]) for r in rows], [int(r[3]) for r in rows])
             if sx is not None:                       # (several ranks: the owners' slots are gathered, every rank saves all)
                 st["_exec_inflight"] = sx.export_inflight()
         return st

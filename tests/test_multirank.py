@@ -137,6 +137,17 @@ def test_generic_conv_model_two_ranks_cpu_equal_single_process():
     _compare(single, _run(2, "cpu", rounds=4, kinds="cnn_pushpull"), rel=1e-4)
 
 
+def test_banked_checkpoint_with_several_ranks_resumes_exactly():
+    """save / load of the banked engine with two and three ranks: snapshots on the wire (and cached models) live in the bank
+    of their receiver's rank, are gathered into every rank's checkpoint and restored by their owners only."""
+    single = _run(1, "cpu", rounds=6, kinds=BKINDS)
+    _compare(single, _run(1, "cpu", rounds=6, kinds=BKINDS, checkpoint=True), rel=1e-5)
+    for world in (2, 3):
+        multi = _run(world, "cpu", rounds=6, kinds=BKINDS, checkpoint=True)
+        assert all(v["banked"] for v in multi.values())
+        _compare(single, multi, rel=1e-5)
+
+
 @pytest.mark.gpu
 def test_checkpoint_with_two_ranks_cuda_resumes_exactly():
     if torch.cuda.device_count() < 2:
