@@ -2,10 +2,10 @@
 // streams WITHOUT going back to Python per event.
 //
 // The reference walks Python objects for every message (gossipy/simul.py:389-451 -> node.py:171-204 ->
-// handler.py:117-136).  For the common set-up -- plain GossipNode, TorchModelHandler / LimitedMergeTMH
-// whose local update is one fused kernel (1-hidden-layer MLP / logistic regression, SGD, cross-entropy),
-// modes MERGE_UPDATE / UPDATE / PASS -- everything an event needs is a handful of integers and device
-// pointers, so the whole round is enqueued from C++:
+// handler.py:117-136).  For handlers whose local update is one fused kernel (1-hidden-layer MLP / logistic
+// regression, SGD with or without momentum, cross-entropy) -- GossipNode, PassThroughNode, CacheNeighNode,
+// SamplingBasedNode, PartitioningBasedNode, All2AllGossipNode; all four CreateModelModes -- everything an event
+// needs is a handful of integers and device pointers, so the whole round is enqueued from C++:
 //
 //   SEND / REPLY_SEND  snapshot kernel  slot <- sender's row            on the SENDER's stream
 //   DELIVER / REPLY    MERGE_UPDATE: fused merge + local-update kernel (reads the slot)

@@ -1,12 +1,13 @@
 """Glue of the native executor (``csrc/exec/executor.cpp``): a round's event list is enqueued from C++.
 
-Eligible simulations (``eligible`` returns ``None``): a :class:`GossipSimulator` or
-:class:`TokenizedGossipSimulator` of plain :class:`GossipNode` s whose handlers are
-:class:`TorchModelHandler` s / :class:`LimitedMergeTMH` s on the fused kernel path (1-hidden-layer ReLU MLP
-or logistic regression, momentum-free SGD, mean cross-entropy), mode ``MERGE_UPDATE`` / ``UPDATE`` /
-``PASS``, identical hyper-parameters on all nodes.  That covers the headline benchmark and the reference's
-MLP / logistic-regression scripts.  Everything else keeps the per-event Python executor (or the bank for
-linear learners).
+Eligible simulations (``eligible`` returns ``None``): a :class:`GossipSimulator`, :class:`TokenizedGossipSimulator`
+or (asynchronous) :class:`All2AllGossipSimulator` whose nodes are all of ONE class -- :class:`GossipNode`,
+:class:`PassThroughNode`, :class:`CacheNeighNode`, :class:`SamplingBasedNode` + :class:`SamplingTMH`,
+:class:`PartitioningBasedNode` + :class:`PartitionedTMH`, :class:`All2AllGossipNode` + :class:`WeightedTMH` -- with
+handlers on the fused kernel path (1-hidden-layer ReLU MLP or logistic regression, SGD with or without momentum, mean
+cross-entropy), any :class:`CreateModelMode` the node class allows, identical hyper-parameters on all nodes.
+Everything else (``PENSNode``, generic autograd models) keeps the per-event Python executor on the same native
+schedule, linear learners the bank (``engine/bank.py``).
 
 Several ranks: every rank drives its own executor over the same event list (replicated books), launches
 the work of its own nodes only, and the snapshot slots are rows of the symmetric arenas
