@@ -6,7 +6,8 @@ or (asynchronous) :class:`All2AllGossipSimulator` whose nodes are all of ONE cla
 :class:`PartitioningBasedNode` + :class:`PartitionedTMH`, :class:`All2AllGossipNode` + :class:`WeightedTMH` -- with
 handlers on the fused kernel path (1-hidden-layer ReLU MLP or logistic regression, SGD with or without momentum, mean
 cross-entropy), any :class:`CreateModelMode` the node class allows, identical hyper-parameters on all nodes.
-Everything else (``PENSNode``, generic autograd models) keeps the per-event Python executor on the same native
+A :class:`PENSNode` population joins once every node has left its selection phase (step 2 = plain deliveries).
+Everything else (PENS step 1, generic autograd models) keeps the per-event Python executor on the same native
 schedule, linear learners the bank (``engine/bank.py``).
 
 Several ranks: every rank drives its own executor over the same event list (replicated books), launches
@@ -50,7 +51,8 @@ def eligible(sim: Any) -> Optional[str]:
     ids = sorted(sim.nodes)
     if ids != list(range(len(ids))):
         return "node ids must be 0..N-1"
-    from ..node import All2AllGossipNode, CacheNeighNode, PartitioningBasedNode, PassThroughNode, SamplingBasedNode
+    from ..node import (All2AllGossipNode, CacheNeighNode, PartitioningBasedNode, PassThroughNode, PENSNode,
+                        SamplingBasedNode)
     if a2a:
         if sim.protocol != AntiEntropyProtocol.PUSH:
             return "all-to-all: protocol %s" % sim.protocol.name
@@ -70,7 +72,11 @@ def eligible(sim: Any) -> Optional[str]:
             return "all-to-all needs All2AllGossipNode + WeightedTMH"
         if weighted and (h.mode != CreateModelMode.MERGE_UPDATE or node.local_cache and "_stream_exec" not in sim.__dict__):
             return "all-to-all: mode %s / caches filled by another executor" % h.mode.name
-        if type(node) not in (GossipNode, PassThroughNode, CacheNeighNode) and not partitioned and not sampled and not weighted:
+        # a PENSNode that has left its selection phase consumes a delivery like a plain node (ref node.py:752-757);
+        # its restricted peer choice lives in the scheduler
+        pens2 = type(node) is PENSNode and node.step == 2 and type(h) is H.TorchModelHandler
+        if (type(node) not in (GossipNode, PassThroughNode, CacheNeighNode) and not partitioned and not sampled
+                and not weighted and not pens2):
             return "node class %s" % type(node).__name__
         if type(node) in (PassThroughNode, CacheNeighNode) and not getattr(node, "_keyed_draws", False):
             return "node-side draws from the host stream"

@@ -440,7 +440,9 @@ class GossipSimulator(SimulationEventSender):
             return "extension not built"
         for node in self.nodes.values():
             cls = type(node)
-            if cls is PENSNode:          # its step switch and peer choice are driven from _run_native (_pens_switch)
+            if cls is PENSNode:          # its step switch and peer choice are driven from _run_native
+                if self.protocol != AntiEntropyProtocol.PUSH:
+                    return "PENSNode sends PUSH messages whatever the protocol"
                 continue
             if cls.timed_out is not GossipNode.timed_out and not isinstance(node, All2AllGossipNode):
                 return "node class overrides timed_out"
@@ -535,6 +537,10 @@ class GossipSimulator(SimulationEventSender):
                                 "were discarded." % lost)
             else:
                 self._clock = 0
+        pens = [n for n in self.nodes.values() if type(n) is PENSNode]
+        for node in pens:                  # resumed run: the restricted peer lists are configuration, not scheduler state
+            if node.step == 2 and node.best_nodes:
+                sch.set_peer_list(node.idx, [int(p) for p in node.best_nodes])
         use_bank = self.batched is True or (self.batched == "auto" and (
             GlobalSettings().get_device().type == "cuda" or self.n_nodes >= 512))
         if use_bank and type(self) is GossipSimulator:
@@ -545,17 +551,13 @@ class GossipSimulator(SimulationEventSender):
                 return
         if self.native_executor and type(self) in (GossipSimulator, TokenizedGossipSimulator, All2AllGossipSimulator):
             from .engine import stream_exec as _sx
-            if _sx.eligible(self) is None:
+            if _sx.eligible(self) is None and self._handover_to_executor():
                 self._run_native_streamed(sch, n_rounds)
                 return
         msgs = self._native_msgs
         prev_finish = None
-        pens = [n for n in self.nodes.values() if type(n) is PENSNode]
-        for node in pens:                  # resumed run: the restricted peer lists are configuration, not scheduler state
-            if node.step == 2 and node.best_nodes:
-                sch.set_peer_list(node.idx, [int(p) for p in node.best_nodes])
         try:
-            for _ in range(n_rounds):
+            for rnd in range(n_rounds):
                 if self.stream_inputs:
                     self._stream_round_inputs()
                 eval_nodes: List[GossipNode] = []
@@ -591,11 +593,53 @@ class GossipSimulator(SimulationEventSender):
                 prev_finish = finish
                 self._clock = int(sch.clock)
                 self.notify_timestep(t_last)
+                if pens and self.native_executor and rnd + 1 < n_rounds and all(n.step == 2 for n in pens):
+                    # every PENS node has left its selection phase: from here on a delivery is a plain merge + update,
+                    # the rest of the run is enqueued from C++ (messages on the wire move into the executor's slots)
+                    from .engine import stream_exec as _sx
+                    if _sx.eligible(self) is None and self._handover_to_executor():
+                        if prev_finish is not None:
+                            prev_finish()
+                        self._run_native_streamed(sch, n_rounds - rnd - 1)
+                        return
+                    pens = []               # not eligible (generic model, ...): no need to ask again
         except KeyboardInterrupt:
             LOG.warning("Simulation interrupted by user.")
         if prev_finish is not None:
             prev_finish()
         self.notify_end()
+
+    def _handover_to_executor(self) -> bool:
+        """Messages the per-event executor left on the wire (``_native_msgs``: snapshot handlers in ``CACHE``) become
+        in-flight snapshot slots of the C++ executor.  ``False`` = they carry something the conversion does not cover
+        (partition ids, degrees, ...) and the per-event executor keeps the run."""
+        msgs = self.__dict__.get("_native_msgs") or {}
+        if not msgs:
+            return True
+        if "_stream_exec" in self.__dict__ or "_exec_inflight" in self.__dict__:
+            return False
+        from .core import CreateModelMode
+        mode = self.nodes[0].model_handler.mode
+        if mode == CreateModelMode.UPDATE_MERGE or any(m.value is not None and len(m.value) != 1 for m in msgs.values()):
+            return False
+        from .parallel import runtime as _prt
+        ids, ranks, ages, rows = [], [], [], []
+        for mid in sorted(msgs):
+            msg = msgs[mid]
+            if msg.value is None:            # a PULL request carries no model
+                continue
+            snap = CACHE[msg.value[0]]
+            ids.append(int(mid))
+            ranks.append(int(_prt.rank_of(msg.sender)) if _prt.active() else 0)
+            ages.append(int(snap.n_updates))
+            rows.append(snap.row.detach().cpu().clone())    # (several ranks: only the sender's rank holds the values, and
+            CACHE.drop(msg.value[0])                        #  only that rank fills the slot)
+        msgs.clear()
+        if ids:
+            import torch
+            self.__dict__["_exec_inflight"] = {"ids": ids, "ranks": ranks, "ages": ages, "extra": [[] for _ in ids],
+                                               "rows": torch.stack(rows)}
+        return True
 
     # native engine: execute bankable set-ups (linear learners) many nodes per launch.  "auto" = on a GPU, or from
     # 512 nodes on the CPU (where the bank's vectorised-over-nodes update loses to per-node calls for a few big shards)

@@ -198,7 +198,14 @@ def test_pens_native_scheduler_two_ranks_cpu_equal_single_process():
     counters, so every rank computes the same schedule."""
     single = _run(1, "cpu", rounds=9, kinds="pens_native")
     assert any(v for v in single["pens_native"]["best"].values()), "step 2 was never reached"
-    _compare(single, _run(2, "cpu", rounds=9, kinds="pens_native"), rel=1e-5, skip=("cache_left",))
+    assert single["pens_native"]["cpp_executor"], "step 2 should have moved to the C++ executor"
+    multi = _run(2, "cpu", rounds=9, kinds="pens_native")
+    assert multi["pens_native"]["cpp_executor"]
+    _compare(single, multi, rel=1e-5, skip=("cache_left",))
+    # interrupted in step 1 (candidates cached on their receivers' ranks) and in step 2 (slots of the C++ executor)
+    _compare(single, _run(2, "cpu", rounds=9, kinds="pens_native", checkpoint=True), rel=1e-5, skip=("cache_left",))
+    single = _run(1, "cpu", rounds=14, kinds="pens_native")
+    _compare(single, _run(2, "cpu", rounds=14, kinds="pens_native", checkpoint=True), rel=1e-5, skip=("cache_left",))
 
 
 @pytest.mark.gpu

@@ -370,7 +370,7 @@ def test_scheduler_run_in_pieces_and_peer_lists():
         b.set_peer_list(0, [9])
 
 
-def _pens_sim(engine, rounds, step1_rounds=4, round_len=10, resume_from=None):
+def _pens_sim(engine, rounds, step1_rounds=4, round_len=10, executor=True):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork
     from gossipy_b200.data import DataDispatcher, synthetic
@@ -402,6 +402,7 @@ def _pens_sim(engine, rounds, step1_rounds=4, round_len=10, resume_from=None):
     sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
     sim.progress = False
     sim.engine = engine
+    sim.native_executor = executor          # False: per-event executor also in step 2 (real messages reach the receivers)
     rep, sends = SimulationReport(), Sends()
     sim.add_receiver(rep)
     sim.add_receiver(sends)
@@ -415,7 +416,7 @@ def test_pens_runs_under_the_native_scheduler(round_len):
     """PENSNode overrides ``timed_out`` / ``get_peer`` (ref node.py:716-741): the C++ scheduler takes both over --
     the step switch falls between two pieces of a round, step 2 draws from the node's ``best_nodes``."""
     import gossipy_b200 as g
-    sim, rep, sends = _pens_sim("native", rounds=9, step1_rounds=4, round_len=round_len)
+    sim, rep, sends = _pens_sim("native", rounds=9, step1_rounds=4, round_len=round_len, executor=False)
     assert "_scheduler" in sim.__dict__ and sim._native_supported() is None
     t_sw = 4 * round_len
     step1 = [s for s in sends.log if s[0] < t_sw]
@@ -455,3 +456,27 @@ def test_pens_native_checkpoint_resume_is_exact(tmp_path):
         rep2 = [r for r in sim2._receivers if type(r).__name__ == "SimulationReport"][0]
         assert rep2._sent_messages == rep_full._sent_messages
         g.CACHE.clear()
+
+
+def test_pens_step_two_moves_to_the_cpp_executor():
+    """Once every PENS node has left its selection phase a delivery is a plain merge + update: the rest of the run is
+    enqueued from C++ (messages on the wire become executor slots) and equals the per-event executor's run."""
+    import gossipy_b200 as g
+    from gossipy_b200.simul import GossipSimulator
+    ref, rep_ref, sends_ref = _pens_sim("native", rounds=9, step1_rounds=3, executor=False)
+    assert "_stream_exec" not in ref.__dict__
+    rows_ref = {i: n.model_handler.row.clone() for i, n in ref.nodes.items()}
+    g.CACHE.clear()
+    sim, rep, sends = _pens_sim("native", rounds=9, step1_rounds=3)
+    assert "_stream_exec" in sim.__dict__ and not sim._native_msgs
+    for i, n in sim.nodes.items():
+        torch.testing.assert_close(n.model_handler.row, rows_ref[i], rtol=1e-6, atol=1e-7)
+        assert int(n.model_handler.n_updates) == int(ref.nodes[i].model_handler.n_updates)
+        assert n.best_nodes == ref.nodes[i].best_nodes
+    assert (rep._sent_messages, rep._failed_messages, rep._total_size) == \
+        (rep_ref._sent_messages, rep_ref._failed_messages, rep_ref._total_size)
+    for (t1, m1), (t2, m2) in zip(rep.get_evaluation(False), rep_ref.get_evaluation(False)):
+        assert t1 == t2
+        for k in m1:
+            assert m1[k] == pytest.approx(m2[k], abs=1e-6)
+    g.CACHE.clear()
