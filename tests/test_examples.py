@@ -36,6 +36,9 @@ def test_all2all_synchronous_rounds_and_pens():
     out = _run("main_all2all.py", GOSSIPY_SYNC=1, GOSSIPY_NODES=4)
     assert "sent=36" in out                     # 3 rounds x 4 nodes x 3 peers
     _run("main_onoszko_2021.py", GOSSIPY_NODES=4)
+    from gossipy_b200.ops.native import native_available
+    if native_available():                      # PENS on the C++ schedule (step switch between two pieces of a round)
+        _run("main_onoszko_2021.py", GOSSIPY_NODES=4, GOSSIPY_ENGINE="native")
 
 
 def test_danner_script_with_the_cpp_executor():
