@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--device", default="cuda" if torch.cuda.is_available() else "cpu")
     ap.add_argument("--engine", default="native")
     ap.add_argument("--no-executor", action="store_true", help="per-event Python executor instead of the C++ one")
+    ap.add_argument("--metrics-every", type=int, default=1,
+                    help="several ranks: exchange the evaluation results every k rounds (sim.metrics_sync_every)")
     a = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     dev = a.device
@@ -140,6 +142,7 @@ def main():
     sim.engine = a.engine
     if a.no_executor:
         sim.native_executor = False
+    sim.metrics_sync_every = a.metrics_every
     rep = SimulationReport()
     sim.add_receiver(rep)
     sim.init_nodes(seed=42)

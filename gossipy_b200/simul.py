@@ -351,6 +351,14 @@ class GossipSimulator(SimulationEventSender):
         def finish() -> None:
             # everything is enqueued; only now touch the host (one wait per round, not per node)
             from .parallel import runtime as _prt
+            if _prt.active() and int(self.metrics_sync_every) > 1:
+                # several ranks: keep this rank's results and exchange them every k rounds (one all-reduce for k rounds
+                # instead of one per round; the receivers see the same evaluations in the same order, k rounds later)
+                backlog = self.__dict__.setdefault("_metric_backlog", [])
+                backlog.append((t, [p.result() for p in local], [p.result() for p in glob]))
+                if len(backlog) >= int(self.metrics_sync_every):
+                    self._flush_metrics()
+                return
             if local:
                 self.notify_evaluation(t, True, _prt.share_metrics([p.result() for p in local]))
             if glob:
@@ -361,6 +369,30 @@ class GossipSimulator(SimulationEventSender):
             return finish
         finish()
         return None
+
+    metrics_sync_every = 1      # several ranks: rounds between two exchanges of the evaluation results (1 = every round)
+
+    def _flush_metrics(self) -> None:
+        """Share the evaluation results kept back by ``metrics_sync_every`` and report them in order."""
+        backlog = self.__dict__.pop("_metric_backlog", None)
+        if not backlog:
+            return
+        from .parallel import runtime as _prt
+        flat = [d for _, loc, glob in backlog for d in loc + glob]
+        shared = _prt.share_metrics(flat)
+        pos = 0
+        for t, loc, glob in backlog:
+            if loc:
+                self.notify_evaluation(t, True, shared[pos:pos + len(loc)])
+                pos += len(loc)
+            if glob:
+                self.notify_evaluation(t, False, shared[pos:pos + len(glob)])
+                pos += len(glob)
+        _check_device_fault()
+
+    def notify_end(self) -> None:
+        self._flush_metrics()
+        super().notify_end()
 
     def _stream_round_inputs(self) -> None:
         """Fresh inputs for the coming round: host (pinned) -> device, async on each node's stream."""
@@ -795,6 +827,7 @@ class GossipSimulator(SimulationEventSender):
         Model rows are pulled off the device as CPU tensors; the clock and the pending message
         queues are part of the state, so ``load(...).start(n, resume=True)`` continues the run.
         """
+        self._flush_metrics()                # (several ranks save collectively: results held back are exchanged first)
         with open(filename, "wb") as f:
             _pickler.dump({"simul": self, "cache": CACHE.get_cache()}, f)
 

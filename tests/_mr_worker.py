@@ -245,6 +245,8 @@ def run(kind, device, rounds):
     from gossipy_b200.parallel import runtime as prt
     sim, rep, start_args = build(kind, device)
     sim.init_nodes(seed=5)
+    if os.environ.get("MR_METRICS_EVERY"):       # exchange the evaluation results every k rounds instead of every round
+        sim.metrics_sync_every = int(os.environ["MR_METRICS_EVERY"])
     if os.environ.get("MR_CHECKPOINT"):
         # interrupted run: half of the rounds, checkpoint (every rank writes its own file), reload, resume
         import tempfile

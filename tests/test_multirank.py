@@ -24,8 +24,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(world, device, rounds=3, kinds=KINDS, transport=None, arena_rows=None, checkpoint=False):
+def _run(world, device, rounds=3, kinds=KINDS, transport=None, arena_rows=None, checkpoint=False, metrics_every=None):
     env = dict(os.environ, OMP_NUM_THREADS="1")
+    if metrics_every:
+        env["MR_METRICS_EVERY"] = str(metrics_every)
     if checkpoint:
         env["MR_CHECKPOINT"] = "1"
     if transport:
@@ -108,6 +110,15 @@ def test_checkpoint_with_several_ranks_resumes_exactly():
     single = _run(1, "cpu", rounds=6, kinds=kinds)
     _compare(single, _run(1, "cpu", rounds=6, kinds=kinds, checkpoint=True), rel=1e-5)
     _compare(single, _run(2, "cpu", rounds=6, kinds=kinds, checkpoint=True), rel=1e-5)
+
+
+def test_metrics_exchanged_every_k_rounds_give_the_same_report():
+    """``metrics_sync_every = k``: one all-reduce of the evaluation results per k rounds (and at the end / before a
+    checkpoint) -- the report is the one of the per-round exchange."""
+    kinds = "mlp_pushpull,x_mlp_pushpull,pegasos"
+    single = _run(1, "cpu", rounds=7, kinds=kinds)
+    _compare(single, _run(2, "cpu", rounds=7, kinds=kinds, metrics_every=3), rel=1e-5)
+    _compare(single, _run(2, "cpu", rounds=7, kinds=kinds, metrics_every=3, checkpoint=True), rel=1e-5)
 
 
 def test_symmetric_arenas_grow_when_they_run_out():
