@@ -174,10 +174,10 @@ class SymmetricArenas:
             tag = prt.session_tag()
             names = ["gb200_%s_%d_%d_%d" % (tag, self.row_numel, seg, r) for r in range(self.world)]
             mine = shared_memory.SharedMemory(name=names[prt.rank()], create=True, size=total)
+            _unlink_at_exit()
             np.frombuffer(mine.buf, dtype=np.uint8)[:] = 0
             dist.barrier()
-            shms = [mine if r == prt.rank() else shared_memory.SharedMemory(name=names[r])
-                    for r in range(self.world)]
+            shms = [mine if r == prt.rank() else attach_shm(names[r]) for r in range(self.world)]
             dist.barrier()
             self._shm.append(shms)
             _SHM_KEEPALIVE.extend(shms)
@@ -212,6 +212,36 @@ class SymmetricArenas:
 
 
 _SHM_KEEPALIVE: List = []
+
+
+_EXIT_HOOK = [False]
+
+
+def _unlink_at_exit() -> None:
+    """A script that never calls ``parallel.runtime.shutdown`` must not leave its segments in /dev/shm."""
+    if not _EXIT_HOOK[0]:
+        import atexit
+        _EXIT_HOOK[0] = True
+        atexit.register(lambda: _quiet(reset_arenas))
+
+
+def _quiet(fn) -> None:
+    try:
+        fn()
+    except Exception:
+        pass
+
+
+def attach_shm(name: str):
+    """Map a peer's POSIX shared-memory segment.  Python (< 3.13) registers every attached segment with this process's
+    resource tracker, which then unlinks it -- or warns about a "leak" -- at exit although the creator owns it."""
+    from multiprocessing import resource_tracker, shared_memory
+    shm = shared_memory.SharedMemory(name=name)
+    try:
+        resource_tracker.unregister(shm._name, "shared_memory")
+    except Exception:
+        pass
+    return shm
 
 
 _ARENAS: Dict[tuple, RowArena] = {}

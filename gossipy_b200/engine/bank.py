@@ -29,6 +29,7 @@ import torch
 
 from .. import ops
 from ..core import CreateModelMode
+from . import arena as _arena
 
 _RING = 1 << 22     # in-flight message ids are far younger than this
 
@@ -240,9 +241,10 @@ class LinearBank:
             _BANK_SEQ += 1
             names = ["gb200_bank_%s_%d_%d" % (prt.session_tag(), _BANK_SEQ, r) for r in range(W)]
             mine = shared_memory.SharedMemory(name=names[self.rank], create=True, size=total)
+            _arena._unlink_at_exit()
             np.frombuffer(mine.buf, dtype=np.uint8)[:] = 0
             dist.barrier()
-            self._shm = [mine if r == self.rank else shared_memory.SharedMemory(name=names[r]) for r in range(W)]
+            self._shm = [mine if r == self.rank else _arena.attach_shm(names[r]) for r in range(W)]
             dist.barrier()
             _OPEN.append(self)
             self._S_of = [torch.frombuffer(sh.buf, dtype=torch.float32, count=cap * Dp).view(cap, Dp) for sh in self._shm]
