@@ -370,7 +370,7 @@ def test_scheduler_run_in_pieces_and_peer_lists():
         b.set_peer_list(0, [9])
 
 
-def _pens_sim(engine, rounds, step1_rounds=4, round_len=10, executor=True):
+def _pens_sim(engine, rounds, step1_rounds=4, round_len=10, executor=True, faults=False):
     import gossipy_b200 as g
     from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork
     from gossipy_b200.data import DataDispatcher, synthetic
@@ -399,7 +399,11 @@ def _pens_sim(engine, rounds, step1_rounds=4, round_len=10, executor=True):
                               batch_size=16, create_model_mode=CreateModelMode.MERGE_UPDATE)
     nodes = PENSNode.generate(disp, StaticP2PNetwork(7), proto, round_len, True, n_sampled=3, m_top=1,
                               step1_rounds=step1_rounds)
-    sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH)
+    kw = {}
+    if faults:              # messages stay on the wire across round boundaries, some are lost
+        from gossipy_b200.core import UniformDelay
+        kw = dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 14))
+    sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH, **kw)
     sim.progress = False
     sim.engine = engine
     sim.native_executor = executor          # False: per-event executor also in step 2 (real messages reach the receivers)
@@ -436,14 +440,15 @@ def test_pens_runs_under_the_native_scheduler(round_len):
     g.CACHE.clear()
 
 
-def test_pens_native_checkpoint_resume_is_exact(tmp_path):
+@pytest.mark.parametrize("faults", [False, True])
+def test_pens_native_checkpoint_resume_is_exact(tmp_path, faults):
     import gossipy_b200 as g
     from gossipy_b200.simul import GossipSimulator
-    full, rep_full, sends_full = _pens_sim("native", rounds=8, step1_rounds=3)
+    full, rep_full, sends_full = _pens_sim("native", rounds=8, step1_rounds=3, faults=faults)
     rows_full = {i: n.model_handler.row.clone() for i, n in full.nodes.items()}
     g.CACHE.clear()
     for cut in (2, 5):                    # one checkpoint inside step 1 (cached candidates), one inside step 2
-        sim, _, _ = _pens_sim("native", rounds=cut, step1_rounds=3)
+        sim, _, _ = _pens_sim("native", rounds=cut, step1_rounds=3, faults=faults)
         path = str(tmp_path / ("pens%d.pkl" % cut))
         sim.save(path)
         g.CACHE.clear()
@@ -458,16 +463,27 @@ def test_pens_native_checkpoint_resume_is_exact(tmp_path):
         g.CACHE.clear()
 
 
-def test_pens_step_two_moves_to_the_cpp_executor():
+@pytest.mark.parametrize("faults", [False, True])
+def test_pens_step_two_moves_to_the_cpp_executor(faults, monkeypatch):
     """Once every PENS node has left its selection phase a delivery is a plain merge + update: the rest of the run is
     enqueued from C++ (messages on the wire become executor slots) and equals the per-event executor's run."""
     import gossipy_b200 as g
     from gossipy_b200.simul import GossipSimulator
-    ref, rep_ref, sends_ref = _pens_sim("native", rounds=9, step1_rounds=3, executor=False)
+    ref, rep_ref, sends_ref = _pens_sim("native", rounds=9, step1_rounds=3, executor=False, faults=faults)
     assert "_stream_exec" not in ref.__dict__
     rows_ref = {i: n.model_handler.row.clone() for i, n in ref.nodes.items()}
     g.CACHE.clear()
-    sim, rep, sends = _pens_sim("native", rounds=9, step1_rounds=3)
+    moved = []
+    orig = GossipSimulator._handover_to_executor
+
+    def spy(self):
+        n = len(self._native_msgs)
+        ok = orig(self)
+        moved.append((n, ok, len(self.__dict__.get("_exec_inflight", {}).get("ids", []))))
+        return ok
+    monkeypatch.setattr(GossipSimulator, "_handover_to_executor", spy)
+    sim, rep, sends = _pens_sim("native", rounds=9, step1_rounds=3, faults=faults)
+    assert moved and moved[-1][1] and (not faults or moved[-1][0] > 0 and moved[-1][2] == moved[-1][0])
     assert "_stream_exec" in sim.__dict__ and not sim._native_msgs
     for i, n in sim.nodes.items():
         torch.testing.assert_close(n.model_handler.row, rows_ref[i], rtol=1e-6, atol=1e-7)
