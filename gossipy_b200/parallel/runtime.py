@@ -45,7 +45,16 @@ def init(rank: Optional[int] = None, world: Optional[int] = None,
         transport = os.environ.get("GOSSIPY_B200_TRANSPORT", "")
     if not transport:
         transport = "p2p"
-    _state["transport"] = transport if world > 1 else "none"
+    transport = {"nccl-baseline": "nccl"}.get(transport, transport)
+    if transport not in ("p2p", "nccl", "loopback"):
+        raise ValueError("transport must be p2p, nccl (nccl-baseline) or loopback, not %r" % (transport,))
+    if transport == "loopback":
+        # no inter-rank transport: this process hosts ALL nodes on its own device (every rank of a job then runs the
+        # whole simulation by itself) -- the single-device reference point for the other two transports
+        rank, world = 0, 1
+        _state["rank"], _state["world"] = 0, 1
+        GlobalSettings().set_topology(0, 1)
+    _state["transport"] = transport if world > 1 else ("loopback" if transport == "loopback" else "none")
     if arena_capacity is None and os.environ.get("GOSSIPY_B200_ARENA_ROWS"):
         arena_capacity = int(os.environ["GOSSIPY_B200_ARENA_ROWS"])     # rows per segment of the symmetric arenas
     _state["arena_capacity"] = arena_capacity
@@ -88,17 +97,92 @@ def transport() -> str:
     return _state["transport"]
 
 
-def set_num_nodes(n: int, placement: Optional[List[int]] = None) -> None:
-    """Fix the node -> rank placement (block placement unless an explicit list is given)."""
+class Placement:
+    """Which rank (GPU) hosts which gossip node.
+
+    ``Placement.block(n, world)`` keeps neighbouring ids together (the default: node ``i`` on rank ``i * world // n``),
+    ``Placement.round_robin(n, world)`` deals them out, ``Placement.explicit([...])`` takes one rank per node and
+    ``Placement.by_load(weights, world)`` balances per-node costs (e.g. shard sizes) greedily, heaviest first.
+    Every rank must install the same placement before ``init_nodes``::
+
+        runtime.set_num_nodes(n, Placement.by_load([len(disp[i][0][0]) for i in range(n)], world))
+    """
+
+    def __init__(self, ranks: List[int], world: Optional[int] = None) -> None:
+        self.ranks = [int(r) for r in ranks]
+        self.world = int(world) if world is not None else (max(self.ranks) + 1 if self.ranks else 1)
+        if any(r < 0 or r >= self.world for r in self.ranks):
+            raise ValueError("placement names a rank outside 0..%d" % (self.world - 1))
+
+    @classmethod
+    def block(cls, n: int, world: int) -> "Placement":
+        return cls([min(world - 1, i * world // n) for i in range(n)], world)
+
+    @classmethod
+    def round_robin(cls, n: int, world: int) -> "Placement":
+        return cls([i % world for i in range(n)], world)
+
+    @classmethod
+    def explicit(cls, ranks: List[int], world: Optional[int] = None) -> "Placement":
+        return cls(ranks, world)
+
+    @classmethod
+    def by_load(cls, weights: List[float], world: int) -> "Placement":
+        load = [0.0] * world
+        ranks = [0] * len(weights)
+        for i in sorted(range(len(weights)), key=lambda k: (-float(weights[k]), k)):
+            r = min(range(world), key=lambda q: (load[q], q))
+            ranks[i] = r
+            load[r] += float(weights[i])
+        return cls(ranks, world)
+
+    def rank_of(self, node_id: int) -> int:
+        return self.ranks[node_id]
+
+    def nodes_of(self, rank: int) -> List[int]:
+        return [i for i, r in enumerate(self.ranks) if r == rank]
+
+    def __len__(self) -> int:
+        return len(self.ranks)
+
+    def __eq__(self, other: Any) -> bool:
+        return isinstance(other, Placement) and self.ranks == other.ranks and self.world == other.world
+
+    def __repr__(self) -> str:
+        return "Placement(%s, world=%d)" % (self.ranks, self.world)
+
+
+def set_num_nodes(n: int, placement: Any = None) -> None:
+    """Fix the node -> rank placement: a :class:`Placement`, one rank per node, or ``None`` = keep an installed
+    placement of ``n`` nodes, else block placement (what ``init_nodes`` calls)."""
+    if isinstance(placement, Placement):
+        placement = placement.ranks
+    if placement is None:
+        prev = _state["placement"]
+        placement = prev if prev is not None and len(prev) == int(n) else None
+    else:
+        placement = [int(r) for r in placement]
+        if len(placement) != int(n):
+            raise ValueError("placement has %d entries for %d nodes" % (len(placement), int(n)))
+        if any(r < 0 or r >= max(1, _state["world"]) for r in placement):
+            raise ValueError("placement names a rank outside the job")
     _state["n_nodes"] = int(n)
-    _state["placement"] = list(placement) if placement is not None else None
+    _state["placement"] = placement
+
+
+def placement() -> Optional[Placement]:
+    """The installed placement (``None`` when single-process or before ``set_num_nodes``)."""
+    n, w = _state["n_nodes"], _state["world"]
+    if w == 1 or not n:
+        return None
+    return Placement([rank_of(i) for i in range(n)], w)
 
 
 def rank_of(node_id: int) -> int:
     """Rank that owns gossip node ``node_id`` (0 when single-process)."""
     w = _state["world"]
     if w == 1 or node_id is None or node_id < 0:
-        return 0 if w == 1 else (0 if node_id is None or node_id < 0 else 0)
+        return 0
     pl = _state["placement"]
     if pl is not None:
         return pl[node_id]

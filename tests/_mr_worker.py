@@ -244,7 +244,14 @@ def run(kind, device, rounds):
     import gossipy_b200 as g
     from gossipy_b200.parallel import runtime as prt
     sim, rep, start_args = build(kind, device)
+    if os.environ.get("MR_PLACEMENT") and prt.active():     # a non-default node -> rank map, installed before init_nodes
+        n, w = sim.n_nodes, prt.world()
+        pl = {"round_robin": prt.Placement.round_robin(n, w),
+              "by_load": prt.Placement.by_load([1 + (i * 7) % 5 for i in range(n)], w)}[os.environ["MR_PLACEMENT"]]
+        prt.set_num_nodes(n, pl)
     sim.init_nodes(seed=5)
+    if os.environ.get("MR_PLACEMENT") and prt.active():
+        assert prt.placement() == pl, (prt.placement(), pl)
     if os.environ.get("MR_METRICS_EVERY"):       # exchange the evaluation results every k rounds instead of every round
         sim.metrics_sync_every = int(os.environ["MR_METRICS_EVERY"])
     if os.environ.get("MR_CHECKPOINT"):

@@ -24,8 +24,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(world, device, rounds=3, kinds=KINDS, transport=None, arena_rows=None, checkpoint=False, metrics_every=None):
+def _run(world, device, rounds=3, kinds=KINDS, transport=None, arena_rows=None, checkpoint=False, metrics_every=None,
+         placement=None):
     env = dict(os.environ, OMP_NUM_THREADS="1")
+    if placement:
+        env["MR_PLACEMENT"] = placement
     if metrics_every:
         env["MR_METRICS_EVERY"] = str(metrics_every)
     if checkpoint:
@@ -79,6 +82,12 @@ def test_nccl_transport_two_and_three_ranks_cpu_equal_single_process():
         _compare(single, _run(world, "cpu", kinds=kinds, transport="nccl"), rel=1e-5)
 
 
+def test_loopback_transport_runs_everything_in_every_process():
+    """``transport="loopback"``: no inter-rank transport, every process of the job hosts all nodes itself."""
+    kinds = "mlp_pushpull,x_mlp_pushpull"
+    _compare(_run(1, "cpu", kinds=kinds), _run(2, "cpu", kinds=kinds, transport="loopback"), rel=1e-6)
+
+
 def test_pens_two_and_three_ranks_cpu_equal_single_process():
     """PENS: the top-m choice is made on the owner from device results and broadcast; both steps run."""
     single = _run(1, "cpu", rounds=9, kinds="pens")
@@ -110,6 +119,15 @@ def test_checkpoint_with_several_ranks_resumes_exactly():
     single = _run(1, "cpu", rounds=6, kinds=kinds)
     _compare(single, _run(1, "cpu", rounds=6, kinds=kinds, checkpoint=True), rel=1e-5)
     _compare(single, _run(2, "cpu", rounds=6, kinds=kinds, checkpoint=True), rel=1e-5)
+
+
+def test_explicit_placements_give_the_single_process_result():
+    """``runtime.Placement``: round-robin and load-balanced node -> rank maps (installed before ``init_nodes``, which keeps
+    them) instead of the default blocks; Python executor, C++ executor and the bank."""
+    kinds = "mlp_pushpull,x_mlp_pushpull,x_cacheneigh,bank_pegasos"
+    single = _run(1, "cpu", rounds=4, kinds=kinds)
+    _compare(single, _run(2, "cpu", rounds=4, kinds=kinds, placement="round_robin"), rel=1e-5)
+    _compare(single, _run(3, "cpu", rounds=4, kinds=kinds, placement="by_load"), rel=1e-5)
 
 
 def test_metrics_exchanged_every_k_rounds_give_the_same_report():
