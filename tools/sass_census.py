@@ -22,16 +22,20 @@ COLS = OrderedDict([
 ])
 
 
-def main():
+def census():
+    """{kernel name: {"n": instructions, column: count, ...}} of the built extension (``None`` if it is not built)."""
     so = sorted(glob.glob(os.path.join(ROOT, "gossipy_b200", "_C*.so")))
     if not so:
-        sys.exit("extension not built")
+        return None
     out = subprocess.run(["cuobjdump", "-sass", so[0]], capture_output=True, text=True, check=True).stdout
+    mangled = list(OrderedDict.fromkeys(re.findall(r"^\s*Function : (\S+)", out, flags=re.M)))
+    names = subprocess.run(["c++filt"], input="\n".join(mangled), capture_output=True, text=True).stdout.splitlines()
+    demangled = dict(zip(mangled, names))
     kernels, cur = OrderedDict(), None
     for line in out.splitlines():
         m = re.match(r"\s*Function : (\S+)", line)
         if m:
-            name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+            name = demangled.get(m.group(1), m.group(1)).strip()
             cur = kernels.setdefault(re.sub(r"\(.*", "", name), {"n": 0, **{c: 0 for c in COLS}})
             continue
         if cur is None or "/*" not in line:
@@ -44,6 +48,13 @@ def main():
         for c, pat in COLS.items():
             if re.search(pat, ins):
                 cur[c] += 1
+    return kernels
+
+
+def main():
+    kernels = census()
+    if kernels is None:
+        sys.exit("extension not built")
     path = os.path.join(ROOT, "profiles", "sass", "CENSUS.md")
     with open(path, "w") as f:
         f.write("# SASS instruction census of gossipy_b200/_C.so (cuobjdump -sass, sm_100a; `python tools/sass_census.py`)\n\n")
