@@ -586,6 +586,11 @@ class GossipSimulator(SimulationEventSender):
             if _sx.eligible(self) is None and self._handover_to_executor():
                 self._run_native_streamed(sch, n_rounds)
                 return
+        if self.__dict__.get("_exec_inflight") and self.__dict__["_exec_inflight"].get("ids"):
+            # messages on the wire are snapshot slots of the C++ executor (a checkpoint taken under it): the per-event
+            # executor cannot deliver them
+            raise RuntimeError("this run was checkpointed under the C++ executor with messages on the wire; resume it with "
+                               "native_executor = True (and the same handlers)")
         msgs = self._native_msgs
         prev_finish = None
         try:
