@@ -298,6 +298,13 @@ def _standardize(X: np.ndarray) -> np.ndarray:
     return (X - mu) / sd
 
 
+def _fallback_allowed(flag: bool) -> bool:
+    """Synthetic stand-ins are opt-in: per call (``synthetic_fallback=True``) or for a whole process through the
+    environment (``GOSSIPY_SYNTHETIC_FALLBACK=1``, what ``python -m gossipy_b200.compat --synthetic`` sets to run
+    unmodified reference scripts on a machine without network)."""
+    return bool(flag) or os.environ.get("GOSSIPY_SYNTHETIC_FALLBACK", "") == "1"
+
+
 def load_classification_dataset(name_or_path: str, normalize: bool = True,
                                 as_tensor: bool = True, synthetic_fallback: bool = False):
     """Load a classification data set by name or svmlight path (ref ``data/__init__.py:561-624``).
@@ -319,7 +326,7 @@ def load_classification_dataset(name_or_path: str, normalize: bool = True,
         try:
             X, y = _download_named(name_or_path)
         except Exception as exc:
-            if not synthetic_fallback:
+            if not _fallback_allowed(synthetic_fallback):
                 raise
             LOG.warning("'%s' cannot be downloaded (%s): using synthetic data of the same shape"
                         % (name_or_path, type(exc).__name__))
@@ -368,7 +375,7 @@ def load_recsys_dataset(name: str, path: str = ".", synthetic_fallback: bool = F
     try:
         folder = download_and_unzip("https://files.grouplens.org/datasets/movielens/%s.zip" % name)[0]
     except Exception as exc:
-        if not synthetic_fallback:
+        if not _fallback_allowed(synthetic_fallback):
             raise
         LOG.warning("'%s' cannot be downloaded (%s): using synthetic ratings of the same shape"
                     % (name, type(exc).__name__))
@@ -407,7 +414,7 @@ def get_CIFAR10(path: str = "./data", as_tensor: bool = True, synthetic_fallback
     try:
         tr, te = _torchvision_pair("CIFAR10", path)
     except Exception as exc:
-        if not synthetic_fallback:
+        if not _fallback_allowed(synthetic_fallback):
             raise
         LOG.warning("CIFAR-10 unavailable (%s): synthetic CIFAR-shape data" % type(exc).__name__)
         return synthetic.images_like("cifar10", as_tensor=as_tensor)
@@ -423,7 +430,7 @@ def get_FashionMNIST(path: str = "./data", as_tensor: bool = True, synthetic_fal
     try:
         tr, te = _torchvision_pair("FashionMNIST", path)
     except Exception as exc:
-        if not synthetic_fallback:
+        if not _fallback_allowed(synthetic_fallback):
             raise
         LOG.warning("FashionMNIST unavailable (%s): synthetic MNIST-shape data" % type(exc).__name__)
         return synthetic.images_like("fashionmnist", as_tensor=as_tensor)
