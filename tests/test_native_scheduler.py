@@ -1,5 +1,7 @@
 """The C++ scheduler (csrc/sched) against the Python round loop: same semantics, different RNG streams,
 so deterministic set-ups must agree exactly and randomised ones statistically."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -495,4 +497,66 @@ def test_pens_step_two_moves_to_the_cpp_executor(faults, monkeypatch):
         assert t1 == t2
         for k in m1:
             assert m1[k] == pytest.approx(m2[k], abs=1e-6)
+    g.CACHE.clear()
+
+
+def test_pens_random_setups_executor_and_checkpoints_equal_per_event_runs():
+    """Seeded sweep over node count, n_sampled / m_top, length of the selection phase, round lengths, async nodes, faults
+    and a checkpoint somewhere: the run that moves to the C++ executor (and is interrupted) equals the per-event run."""
+    import random
+    import gossipy_b200 as g
+    from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork, UniformDelay
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.model.handler import TorchModelHandler
+    from gossipy_b200.model.nn import LogisticRegression
+    from gossipy_b200.node import PENSNode
+    from gossipy_b200.simul import GossipSimulator, SimulationReport
+
+    def run(executor, n, ns, mt, s1, rounds, faults, rl, sync, seed, cut=None, path=None):
+        g.CACHE.clear()
+        g.set_seed(seed)
+        (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(60 * n, 100)
+        disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
+        proto = TorchModelHandler(LogisticRegression(57, 2), torch.optim.SGD, {"lr": .3}, torch.nn.CrossEntropyLoss(),
+                                  batch_size=16, create_model_mode=CreateModelMode.MERGE_UPDATE)
+        nodes = PENSNode.generate(disp, StaticP2PNetwork(n), proto, rl, sync, n_sampled=ns, m_top=mt, step1_rounds=s1)
+        kw = dict(drop_prob=.15, online_prob=.8, delay=UniformDelay(0, 13)) if faults else {}
+        sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH, **kw)
+        sim.progress = False
+        sim.engine = "native"
+        sim.native_executor = executor
+        rep = SimulationReport()
+        sim.add_receiver(rep)
+        sim.init_nodes(seed=seed)
+        if cut:
+            sim.start(cut)
+            sim.save(path)
+            g.CACHE.clear()
+            sim = GossipSimulator.load(path)
+            rep = [r for r in sim._receivers if type(r).__name__ == "SimulationReport"][0]
+            sim.start(rounds - cut, resume=True)
+        else:
+            sim.start(rounds)
+        rows = torch.stack([sim.nodes[i].model_handler.row.clone() for i in range(n)])
+        ages = [int(sim.nodes[i].model_handler.n_updates) for i in range(n)]
+        return rows, ages, (rep._sent_messages, rep._failed_messages, rep._total_size), "_stream_exec" in sim.__dict__
+
+    import tempfile
+    rnd = random.Random(20260921)
+    moved = 0
+    with tempfile.TemporaryDirectory() as tmp:
+        for case in range(10):
+            n = rnd.randint(3, 8)
+            ns = rnd.randint(1, min(4, n - 1))
+            mt, s1 = rnd.randint(1, ns), rnd.randint(0, 3)
+            rounds = rnd.randint(s1 + 2, s1 + 4)
+            args = (n, ns, mt, s1, rounds, rnd.random() < .6, rnd.choice([10, 10, 5, 20]), rnd.random() < .7, rnd.randint(0, 10 ** 6))
+            cut = rnd.choice([None, rnd.randint(1, rounds - 1)])
+            a = run(False, *args)
+            b = run(True, *args, cut=cut, path=os.path.join(tmp, "c%d.pkl" % case))
+            moved += b[3]
+            torch.testing.assert_close(a[0], b[0], rtol=1e-6, atol=1e-7, msg=lambda m: "%s cut=%s: %s" % (args, cut, m))
+            assert a[1] == b[1] and a[2] == b[2], (args, cut)
+    assert moved >= 4
     g.CACHE.clear()
