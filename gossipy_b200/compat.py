@@ -12,8 +12,8 @@ As a runner::
 ``--synthetic``       data sets that cannot be downloaded are replaced by synthetic data of the same shape
 ``--max-rounds N``    clamps every ``start(n_rounds)`` (the reference scripts run 100 - 1 000 rounds)
 ``--engine native``   C++ scheduler + executor / bank instead of the Python loop (scripts never set ``sim.engine``)
-``--native-utility``  tokenized runs: the constant the script's ``utility_fun`` returns (reference scripts: 1), so that the
-                      C++ scheduler can evaluate the token accounts
+``--native-utility``  tokenized runs: the utility the C++ scheduler evaluates the token accounts with (not needed when the
+                      script's ``utility_fun`` is ``lambda ...: <int>`` like in the reference scripts -- that is recognised)
 ``--device``          ``GlobalSettings().set_device`` before the script starts
 """
 from __future__ import annotations

@@ -939,8 +939,28 @@ class TokenizedGossipSimulator(GossipSimulator):
     def __getstate__(self) -> Dict[str, Any]:
         return super().__getstate__()
 
+    def _constant_utility(self) -> Optional[int]:
+        """The utility the C++ scheduler evaluates the token accounts with: ``native_utility`` if set, else the constant
+        ``utility_fun`` returns when its body is nothing but ``return <int>`` (the reference scripts' ``lambda mh1, mh2,
+        msg: 1``) -- decided from the byte code, the function is never called for it."""
+        if self.native_utility is not None:
+            return int(self.native_utility)
+        import dis
+        try:
+            ops = [i for i in dis.get_instructions(self.utility_fun) if i.opname not in ("RESUME", "NOP", "CACHE")]
+        except TypeError:
+            return None
+        value: Any = None
+        if len(ops) == 1 and ops[0].opname == "RETURN_CONST":
+            value = ops[0].argval
+        elif len(ops) == 2 and ops[0].opname == "LOAD_CONST" and ops[1].opname == "RETURN_VALUE":
+            value = ops[0].argval
+        if isinstance(value, (int, np.integer)) and not isinstance(value, bool):
+            return int(value)
+        return None
+
     def _native_supported(self) -> Optional[str]:
-        if self.native_utility is None:
+        if self._constant_utility() is None:
             return "utility_fun is a Python callback (set native_utility to a constant to go native)"
         if GlobalSettings().reference_compat:
             return "reference_compat mimics B4 in the Python loop only"
@@ -949,7 +969,7 @@ class TokenizedGossipSimulator(GossipSimulator):
     def _configure_scheduler(self, sch) -> None:
         super()._configure_scheduler(sch)
         kind, C, A, k = self.token_account_proto.spec()
-        sch.set_token_account(int(kind) + 1, int(C), int(A), max(1, int(k)), int(self.native_utility))
+        sch.set_token_account(int(kind) + 1, int(C), int(A), max(1, int(k)), int(self._constant_utility()))
 
 
 class All2AllGossipSimulator(GossipSimulator):

@@ -560,3 +560,29 @@ def test_pens_random_setups_executor_and_checkpoints_equal_per_event_runs():
             assert a[1] == b[1] and a[2] == b[2], (args, cut)
     assert moved >= 4
     g.CACHE.clear()
+
+
+def test_constant_utility_functions_are_recognised_from_their_byte_code():
+    """A tokenized run goes native when ``utility_fun`` is nothing but ``return <int>`` (the reference scripts' lambda);
+    anything that computes keeps the Python loop unless ``native_utility`` says otherwise."""
+    from gossipy_b200.flow_control import SimpleTokenAccount
+    from gossipy_b200.simul import TokenizedGossipSimulator
+
+    def const_def(mh1, mh2, msg):
+        return 2
+
+    def computes(mh1, mh2, msg):
+        return 1 if msg is not None else 0
+
+    sim = TokenizedGossipSimulator.__new__(TokenizedGossipSimulator)
+    for fn, want in ((lambda mh1, mh2, msg: 1, 1), (const_def, 2), (computes, None), (lambda a, b, m: True, None),
+                     (lambda a, b, m: 1.5, None), (len, None)):
+        sim.utility_fun = fn
+        assert sim._constant_utility() == want, fn
+    sim.native_utility = 3
+    assert sim._constant_utility() == 3
+    del sim.native_utility
+    # end to end: the helper's simulation passes a lambda and no native_utility
+    rep, rows, s = _sim("native", __import__("gossipy_b200.core", fromlist=["x"]).AntiEntropyProtocol.PUSH, tokenized=SimpleTokenAccount(C=2), rounds=3)
+    s.native_utility = None
+    assert s._constant_utility() == 1 and s._native_supported() is None
