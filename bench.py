@@ -297,7 +297,8 @@ def run_native(args, rank, world):
         h2d = sum(int(n.data[0][0].numel()) * 4 + int(n.data[0][1].numel()) * 8 for n in sim.nodes.values())
         e2e = {"value": K / (ms_e / 1e3), "unit": "rounds/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": N_NODES * D_OUT * D_OUT * 4, "ms_per_step": ms_e / K}
-    dtype = ops.train_dtype()
+    dtype = ops.train_dtype() if torch.cuda.is_available() else \
+        "fp32 (no GPU: the PyTorch reference implementations of the fused operations, ops/torch_ref.py)"
     n_main = len(acc)
     tf32 = None
     if not args.no_tf32 and torch.cuda.is_available() and ops.TRAIN_IMPL in ("", "tc8"):
