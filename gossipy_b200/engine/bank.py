@@ -777,6 +777,23 @@ class LinearBank:
         if self.multi:
             self.slot_rank[ids % _RING] = ranks
 
+    def drop_inflight(self) -> None:
+        """A fresh ``start`` forgets the messages on the wire: every slot that is not a cached model (cache-neighbour nodes:
+        node state) goes back to its pool.  Replicated bookkeeping, no device work."""
+        cached = [dict() for _ in range(self.world)]
+        if self.cacheneigh:
+            for node, cache in enumerate(self.cn_cache):
+                for sl in cache.values():
+                    cached[int(self.owner[node]) if self.multi else 0][int(sl)] = True
+        self.slot_map[:] = -1
+        if self.multi:
+            for r in range(self.world):
+                free = np.asarray([s for s in range(self.cap - 1, -1, -1) if s not in cached[r]], dtype=np.int64)
+                self.free_r[r], self.n_free_r[r], self.pending_r[r] = free, int(free.size), []
+        else:
+            self.free = np.asarray([s for s in range(self.cap - 1, -1, -1) if s not in cached[0]], dtype=np.int64)
+            self.n_free = int(self.free.size)
+
     def writeback(self) -> None:
         W = self.W[:, :self.D]
         age = self.age

@@ -459,6 +459,17 @@ class StreamExec:
         merged = {k: v for part in gathered for k, v in part.items()}
         return torch.stack([merged[(int(r), int(s))] for r, s in where])
 
+    def drop_inflight(self) -> int:
+        """Release the slots of the messages that are still on the wire (a fresh ``start`` forgets them; models cached by
+        cache-neighbour / all-to-all nodes are node state and stay).  Replicated: every rank drops the same ids."""
+        ids = [int(r[0]) for r in self.ex.inflight()]
+        if ids:
+            ev = np.zeros((len(ids), 6), dtype=np.int32)
+            ev[:, 0] = int(self.C.EV_DROP)
+            ev[:, 4] = ids
+            self.ex.run(ev, 0)
+        return len(ids)
+
     def export_inflight(self) -> Dict[str, Any]:
         rows = self.ex.inflight()
         out = {"ids": [int(r[0]) for r in rows], "ranks": [int(r[1]) for r in rows], "ages": [int(r[3]) for r in rows],

@@ -257,6 +257,30 @@ class GossipSimulator(SimulationEventSender):
             p.result()
 
     # -- message plumbing ---------------------------------------------------------------------
+    def _forget_messages_on_the_wire(self) -> None:
+        """A fresh ``start`` (no ``resume``) restarts the clock with the models as they are; what the previous run left on the
+        wire is gone, like in the reference where the queues are locals of ``start`` (ref ``simul.py:385-386``) -- but its
+        snapshots go back to the arenas / the executor's slot pools (same leak class as B10)."""
+        pending: List[Message] = []
+        for queues in (self.__dict__.get("_msg_queues"), self.__dict__.get("_rep_queues")):
+            for msgs in (queues or {}).values():
+                pending.extend(msgs)
+        pending.extend((self.__dict__.get("_native_msgs") or {}).values())
+        for msg in pending:
+            key = _model_key(msg)
+            if key is not None:
+                CACHE.drop(key)
+        if self.__dict__.get("_native_msgs"):
+            self._native_msgs.clear()
+        sx = self.__dict__.get("_stream_exec")
+        if sx is not None:
+            sx.drop_inflight()
+        bank = self.__dict__.get("_bank")
+        if bank is not None:
+            bank.drop_inflight()
+        self.__dict__.pop("_exec_inflight", None)
+        self.__dict__.pop("_bank_inflight", None)
+
     def _lost(self, msg: Optional[Message]) -> None:
         """Account a lost message and free its in-flight snapshot (FIX B10)."""
         self.notify_message(True)
@@ -406,6 +430,7 @@ class GossipSimulator(SimulationEventSender):
             "The simulator is not inizialized. Please, call the method 'init_nodes'."
         LOG.info("Simulation started.")
         if not resume:
+            self._forget_messages_on_the_wire()
             self._clock = 0
             self._msg_queues = defaultdict(list)
             self._rep_queues = defaultdict(list)
@@ -548,6 +573,8 @@ class GossipSimulator(SimulationEventSender):
             sch.set_state(saved)
             self.__dict__.setdefault("_native_msgs", {})
         elif sch is None or not resume:
+            if not resume:
+                self._forget_messages_on_the_wire()
             sch = self.__dict__["_scheduler"] = self._make_scheduler()
             self._native_msgs: Dict[int, Message] = {}
             self.__dict__.pop("_bank_inflight", None)
@@ -586,11 +613,13 @@ class GossipSimulator(SimulationEventSender):
             if _sx.eligible(self) is None and self._handover_to_executor():
                 self._run_native_streamed(sch, n_rounds)
                 return
-        if self.__dict__.get("_exec_inflight") and self.__dict__["_exec_inflight"].get("ids"):
+        sx_prev = self.__dict__.get("_stream_exec")
+        if ((self.__dict__.get("_exec_inflight") and self.__dict__["_exec_inflight"].get("ids"))
+                or (resume and sx_prev is not None and len(sx_prev.ex.inflight()) > 0)):
             # messages on the wire are snapshot slots of the C++ executor (a checkpoint taken under it): the per-event
             # executor cannot deliver them
-            raise RuntimeError("this run was checkpointed under the C++ executor with messages on the wire; resume it with "
-                               "native_executor = True (and the same handlers)")
+            raise RuntimeError("messages on the wire are snapshot slots of the C++ executor (this run, or the checkpoint it was "
+                               "loaded from, used it); resume with native_executor = True and the same handlers")
         msgs = self._native_msgs
         prev_finish = None
         try:

@@ -586,3 +586,54 @@ def test_constant_utility_functions_are_recognised_from_their_byte_code():
     rep, rows, s = _sim("native", __import__("gossipy_b200.core", fromlist=["x"]).AntiEntropyProtocol.PUSH, tokenized=SimpleTokenAccount(C=2), rounds=3)
     s.native_utility = None
     assert s._constant_utility() == 1 and s._native_supported() is None
+
+
+@pytest.mark.parametrize("path", ["python-loop", "per-event", "executor", "bank"])
+def test_fresh_starts_do_not_leak_what_was_on_the_wire(path):
+    """``start`` without ``resume`` restarts the clock and forgets the messages in flight (like the reference, whose
+    queues are locals of ``start``) -- their snapshots must go back to the arenas / slot pools, run after run."""
+    import gossipy_b200 as g
+    from gossipy_b200.core import AntiEntropyProtocol, CreateModelMode, StaticP2PNetwork, UniformDelay
+    from gossipy_b200.data import DataDispatcher, synthetic
+    from gossipy_b200.data.handler import ClassificationDataHandler
+    from gossipy_b200.engine import arena
+    from gossipy_b200.model.handler import PegasosHandler, TorchModelHandler
+    from gossipy_b200.model.nn import AdaLine, LogisticRegression
+    from gossipy_b200.node import GossipNode
+    from gossipy_b200.simul import GossipSimulator
+    g.CACHE.clear()
+    g.set_seed(5)
+    n = 8
+    base = sum(a.live for a in arena._ARENAS.values())       # rows of earlier tests' simulations that are still alive
+    (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(50 * n, 80)
+    if path == "bank":
+        ytr, yte = 2 * ytr - 1, 2 * yte - 1
+        proto = PegasosHandler(AdaLine(57), 0.01, CreateModelMode.MERGE_UPDATE)
+    else:
+        proto = TorchModelHandler(LogisticRegression(57, 2), torch.optim.SGD, {"lr": .3}, torch.nn.CrossEntropyLoss(),
+                                  batch_size=16, create_model_mode=CreateModelMode.MERGE_UPDATE)
+    disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
+    nodes = GossipNode.generate(disp, StaticP2PNetwork(n), proto, 10, True)
+    sim = GossipSimulator(nodes, disp, 10, AntiEntropyProtocol.PUSH_PULL, delay=UniformDelay(5, 25))   # always something in flight
+    sim.progress = False
+    sim.engine = "python" if path == "python-loop" else "native"
+    sim.native_executor = path == "executor"
+    sim.batched = path == "bank"
+    sim.init_nodes(seed=1)
+
+    def in_use():
+        if path == "executor":
+            return len(sim._stream_exec.ex.inflight())
+        if path == "bank":
+            return sim._bank.cap - sim._bank.n_free
+        return sum(a.live for a in arena._ARENAS.values()) - base
+    seen = []
+    for _ in range(4):
+        sim.start(3)
+        seen.append(in_use())
+    assert ("_stream_exec" in sim.__dict__) == (path == "executor") and ("_bank" in sim.__dict__) == (path == "bank")
+    assert seen[0] > (n if path in ("python-loop", "per-event") else 0), seen      # something was on the wire at the cut
+    assert max(seen[1:]) <= seen[0] + n, seen                                      # ... and it does not pile up
+    sim._forget_messages_on_the_wire()
+    assert in_use() == (n if path in ("python-loop", "per-event") else 0)
+    g.CACHE.clear()
