@@ -238,12 +238,13 @@ public:
     void set_partition(int n_parts, uintptr_t part_id, const std::vector<uintptr_t>& seg_ptrs, const std::vector<int>& seg_counts) {
         if (n_parts < 1 || n_parts > kMaxPartsByValue) throw std::invalid_argument("1..16 partitions supported by the native executor");
         if ((int)seg_ptrs.size() != n_parts || (int)seg_counts.size() != n_parts) throw std::invalid_argument("one segment table per partition");
-        if (mode_ != 2) throw std::invalid_argument("partitioned models run MERGE_UPDATE in the native executor");
+        if (mode_ != 2 && mode_ != 1) throw std::invalid_argument("partitioned models run MERGE_UPDATE or UPDATE in the native executor");
         n_parts_ = n_parts; part_id_ = reinterpret_cast<const int64_t*>(part_id);
         seg_ptrs_ = seg_ptrs; seg_counts_ = seg_counts;
         for (Node& nd : nodes_) nd.ages_v.assign(n_parts, 0);
     }
     void set_partition_callbacks(py::function merge_part, py::function train_part) { cb_merge_part_ = merge_part; cb_train_part_ = train_part; }
+    void set_partition_update_callback(py::function f) { cb_update_part_ = std::move(f); }
     void set_node_ages(int i, const std::vector<int64_t>& ages, int64_t model_msgs) {
         Node& nd = nodes_.at(i);
         if ((int)ages.size() != n_parts_) throw std::invalid_argument("one age per partition");
@@ -329,7 +330,10 @@ public:
             if (kv.second.first < 0) throw std::logic_error("an elided snapshot outlived its round");
             const Slot& sl = pools_[kv.second.first][kv.second.second];
             std::vector<int64_t> r{kv.first, kv.second.first, kv.second.second, sl.age};
-            if (n_parts_ > 0) { r.push_back(sl.pid); r.insert(r.end(), sl.ages_v.begin(), sl.ages_v.end()); }
+            if (n_parts_ > 0) {
+                r.push_back(sl.pid); r.insert(r.end(), sl.ages_v.begin(), sl.ages_v.end());
+                if (mode_ == 1) r.push_back(sl.counter);    // partitioned UPDATE keys the copy's update with it
+            }
             else if (mode_ == 3) r.push_back(sl.counter);
             if (!deg_.empty()) r.push_back(sl.sender);
             v.push_back(r);
@@ -348,7 +352,10 @@ public:
             sl.state = 1;                                   // (debug mode) holds a snapshot again
             sl.refs = 1;
             sl.age = r.at(3);
-            if (n_parts_ > 0) { sl.pid = (int)r.at(4); sl.ages_v.assign(r.begin() + 5, r.begin() + 5 + n_parts_); }
+            if (n_parts_ > 0) {
+                sl.pid = (int)r.at(4); sl.ages_v.assign(r.begin() + 5, r.begin() + 5 + n_parts_);
+                if (mode_ == 1) sl.counter = r.at(5 + n_parts_);
+            }
             else if (mode_ == 3) sl.counter = r.at(4);
             if (!deg_.empty()) sl.sender = (int)r.back();
             inflight_[(int32_t)r.at(0)] = {rk, s};
@@ -694,7 +701,35 @@ private:
             else if (sl.written && !hoist)                      // (a slot restored from a checkpoint has no writer event)
                 cuda_check(cudaStreamWaitEvent(nd.stream, sl.written, 0), "wait for the snapshot");
         }
-        if (n_parts_ > 0) {                                // partitioned MERGE_UPDATE: merge one partition, then train
+        if (n_parts_ > 0 && mode == 1) {
+            // partitioned UPDATE (model/handler.py::PartitionedTMH.__call__, reference handler.py:497-506): a private copy of
+            // the received model is trained on the own data -- with ITS per-partition ages scaling the gradient, keyed like
+            // the Python scratch copy (this node, the sender's counter + 1, the sender's total age) --, then partition `pid`
+            // of the copy is merged into the own model with the age weights.  The own model is not trained.
+            const int pid = sl.pid;
+            const int st = steps_of(nd);
+            int64_t age_tmp = 0; for (int64_t v : sl.ages_v) age_tmp += v;
+            const uint64_t key_tmp = key_of(node, sl.counter + 1, age_tmp);
+            const int64_t a = nd.ages_v[pid], b = sl.ages_v[pid] + st;
+            float w1 = .5f, w2 = .5f;
+            if (a + b > 0) { w1 = (float)((double)a / (double)(a + b)); w2 = (float)((double)b / (double)(a + b)); }
+            if (exec) {
+                if (cuda_) {
+                    if (nd.scratch == nullptr) throw std::runtime_error("partitioned UPDATE needs a scratch row per node (set_node_scratch)");
+                    const PeerSync none{nullptr, 0, nullptr, nullptr};
+                    launch_merge_pair(nd.scratch, sl.data, 0.f, 1.f, 0, row_floats_, sync, nd.stream);
+                    Node tmp = nd; tmp.row = nd.scratch;
+                    train(tmp, nullptr, 1.f, 0.f, key_tmp, none, &sl.ages_v);
+                    launch_merge_segments(nd.row, nd.scratch, reinterpret_cast<const int64_t*>(seg_ptrs_[pid]), seg_counts_[pid], w1, w2, none, nd.stream);
+                } else {
+                    cb_update_part_(node, rk, s, (int64_t)sl.gen, (int64_t)key_tmp, sl.ages_v, pid, w1, w2);
+                }
+                launches_ += 3;
+            }
+            nd.ages_v[pid] = std::max(a, b);
+            nd.age = 0; for (int64_t v : nd.ages_v) nd.age += v;
+            nd.version += 1;
+        } else if (n_parts_ > 0) {                         // partitioned MERGE_UPDATE: merge one partition, then train
             const int pid = sl.pid;
             const int64_t a = nd.ages_v[pid], b = sl.ages_v[pid];
             float w1 = .5f, w2 = .5f;                      // sampling.py::mixing_weights: (0, 0) -> (1, 1)
@@ -832,7 +867,7 @@ private:
     std::vector<std::vector<Slot>> pools_;          // per owner rank
     std::vector<std::deque<int>> free_;             // FIFO: a slot is reused as late as possible (see snapshot())
     std::unordered_map<int32_t, std::pair<int, int>> inflight_;     // message id -> (rank, slot)
-    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_merge_, cb_sample_merge_, cb_kway_;
+    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_part_, cb_update_merge_, cb_sample_merge_, cb_kway_;
     bool a2a_ = false;                               // All2AllGossipNode mode
     bool cn_ = false;                                // CacheNeighNode mode
     float momentum_ = 0.f, dampening_ = 0.f; bool nesterov_ = false;     // fused momentum-SGD (0 = plain SGD)
@@ -878,6 +913,7 @@ void bind_executor(py::module_& m) {
         .def("set_callbacks", &StreamExecutor::set_callbacks)
         .def("set_partition", &StreamExecutor::set_partition)
         .def("set_partition_callbacks", &StreamExecutor::set_partition_callbacks)
+        .def("set_partition_update_callback", &StreamExecutor::set_partition_update_callback)
         .def("set_node_ages", &StreamExecutor::set_node_ages)
         .def("ages_v", &StreamExecutor::ages_v)
         .def("model_msgs", &StreamExecutor::model_msgs)

@@ -95,7 +95,7 @@ def eligible(sim: Any) -> Optional[str]:
         if not (h._fused or momentum) or h.layout.int_buffers:
             return "handler is not on the fused kernel path"
         if partitioned:
-            if h.mode != CreateModelMode.MERGE_UPDATE:
+            if h.mode not in (CreateModelMode.MERGE_UPDATE, CreateModelMode.UPDATE):
                 return "partitioned models: mode %s" % h.mode.name
             if h.tm_partition.n_parts > 16:
                 return "more than 16 partitions"
@@ -204,7 +204,8 @@ class StreamExec:
             if not self.cuda:
                 self.ex.set_kway_callback(self._cb_kway)
         self._scratch = None
-        if h0.mode == CreateModelMode.UPDATE_MERGE:      # one private row per node of this rank for the copy that is trained
+        if h0.mode == CreateModelMode.UPDATE_MERGE or (self.n_parts and h0.mode == CreateModelMode.UPDATE):
+            # one private row per node of this rank for the copy of a received model that is trained
             mine = [i for i in ids if self.owner[i] == self.rank]
             self._scratch = torch.zeros(max(1, len(mine)), self.row_numel, dtype=torch.float32, device=self.device)
             self._scratch_of = {i: k for k, i in enumerate(mine)}
@@ -212,6 +213,7 @@ class StreamExec:
                 self.ex.set_node_scratch(i, self._scratch[k].data_ptr())
             if not self.cuda:
                 self.ex.set_update_merge_callback(self._cb_update_merge)
+                self.ex.set_partition_update_callback(self._cb_update_part)
         self.bind_nodes()
 
     def _add_pool_rows(self, k: int) -> None:
@@ -402,6 +404,20 @@ class StreamExec:
     def _cb_merge_part(self, node: int, rank: int, slot: int, pid: int, w1: float, w2: float, gen: int) -> None:
         src, sync = self._slot(rank, slot, gen)
         ops.merge_segments(self.sim.nodes[node].model_handler.row, src, self._segs[pid], float(w1), float(w2), sync)
+
+    def _cb_update_part(self, node: int, rank: int, slot: int, gen: int, key: int, ages: List[int], pid: int, w1: float,
+                        w2: float) -> None:
+        """Partitioned UPDATE: train a private copy of the received model (its ages scale the gradient), merge its
+        partition ``pid`` into the own model."""
+        h = self.sim.nodes[node].model_handler
+        x, y = self._data[node]
+        tmp = self._scratch[self._scratch_of[node]]
+        src, sync = self._slot(rank, slot, gen)
+        ops.merge_pair(tmp, src, 0.0, 1.0, sync=sync)
+        fn = ops.mlp1_train if self.family == "mlp1" else ops.logreg_train
+        fn(tmp, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key),
+           (self._part_id, torch.as_tensor(ages, dtype=torch.int64)))
+        ops.merge_segments(h.row, tmp, self._segs[pid], float(w1), float(w2), None)
 
     def _cb_train_part(self, node: int, key: int, ages: List[int]) -> None:
         h = self.sim.nodes[node].model_handler

@@ -150,7 +150,7 @@ def build(kind, device):
         sim.engine = "native"
         sim.native_executor = True
         start_args = (UniformMixing(net),)
-    elif kind in ("x_part_mlp", "x_part_logreg"):
+    elif kind in ("x_part_mlp", "x_part_logreg", "x_part_update"):
         # partitioned models through the C++ executor: keyed partition draws, ages per partition, segment merges
         if kind == "x_part_mlp":
             (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
@@ -160,7 +160,8 @@ def build(kind, device):
             n, bs, net, prt_ = 6, 16, LogisticRegression(57, 2), AntiEntropyProtocol.PUSH
         disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)
         proto = PartitionedTMH(net, TorchModelPartition(net, 4), torch.optim.SGD, {"lr": .5, "weight_decay": .001},
-                               torch.nn.CrossEntropyLoss(), batch_size=bs, create_model_mode=CreateModelMode.MERGE_UPDATE)
+                               torch.nn.CrossEntropyLoss(), batch_size=bs,
+                               create_model_mode=CreateModelMode.UPDATE if kind == "x_part_update" else CreateModelMode.MERGE_UPDATE)
         nodes = PartitioningBasedNode.generate(disp, StaticP2PNetwork(n), proto, 10, True)
         sim = GossipSimulator(nodes, disp, 10, prt_, delay=UniformDelay(0, 2))
         sim.engine = "native"

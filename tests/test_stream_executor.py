@@ -140,7 +140,12 @@ def test_native_executor_modes_and_variants(kw):
 
 @pytest.mark.parametrize("kw", [dict(model="logreg", protocol="PUSH", partitioned=4, faults=True),
                                 dict(model="mlp", protocol="PUSH_PULL", partitioned=3),
-                                dict(model="logreg", protocol="PULL", partitioned=7, faults=True, sync=False)])
+                                dict(model="logreg", protocol="PULL", partitioned=7, faults=True, sync=False),
+                                # UPDATE (the mode of the reference's main_hegedus_2021.py): a private copy of the received model
+                                # is trained with ITS ages, its partition merged into the (untrained) own model
+                                dict(model="logreg", protocol="PUSH", partitioned=4, faults=True, mode="UPDATE", tokenized=True),
+                                dict(model="mlp", protocol="PUSH_PULL", partitioned=3, mode="UPDATE"),
+                                dict(model="logreg", protocol="PULL", partitioned=5, faults=True, sync=False, mode="UPDATE")])
 def test_native_executor_partitioned_models(kw):
     """PartitioningBasedNode + PartitionedTMH (reference node.py:566-659, handler.py:455-525) from C++: keyed partition
     draw, per-partition ages on the wire, segment merge with age weights, 1/age-scaled local update."""
@@ -200,7 +205,8 @@ def test_native_executor_cache_neighbour_nodes(kw):
 
 
 @pytest.mark.parametrize("kw", [dict(model="logreg", protocol="PUSH", partitioned=4, faults=True), dict(model="logreg", protocol="PUSH_PULL", sampled=.3, faults=True),
-                                dict(model="logreg", protocol="PUSH", passthrough=True, faults=True, n=7)])
+                                dict(model="logreg", protocol="PUSH", passthrough=True, faults=True, n=7),
+                                dict(model="logreg", protocol="PUSH_PULL", partitioned=4, faults=True, mode="UPDATE")])
 def test_executor_checkpoint_of_keyed_node_classes_is_exact(kw, tmp_path):
     """Node classes with keyed draws (partition ids, samples, accept draws): building the scheduler again after a load must not
     consume a draw (it used to: the partitioned resume was off by one message counter)."""
