@@ -22,6 +22,7 @@ Python callbacks into :mod:`gossipy_b200.ops`, which makes the native bookkeepin
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -97,6 +98,11 @@ def eligible(sim: Any) -> Optional[str]:
         if partitioned:
             if h.mode not in (CreateModelMode.MERGE_UPDATE, CreateModelMode.UPDATE):
                 return "partitioned models: mode %s" % h.mode.name
+            if (h.mode == CreateModelMode.UPDATE and h.device.type == "cuda"
+                    and os.environ.get("GOSSIPY_EXEC_PART_UPDATE", "") != "1"):
+                # the launch sequence (copy, train the copy with ages by value, segment merge) was written after the last
+                # GPU session: bit-identical to the per-event executor on CPU, not yet run on a GPU -> opt-in there
+                return "partitioned UPDATE on CUDA is opt-in (GOSSIPY_EXEC_PART_UPDATE=1) until it has been validated on a GPU"
             if h.tm_partition.n_parts > 16:
                 return "more than 16 partitions"
         elif h.mode not in (CreateModelMode.MERGE_UPDATE, CreateModelMode.UPDATE, CreateModelMode.UPDATE_MERGE,
