@@ -245,6 +245,7 @@ public:
     }
     void set_partition_callbacks(py::function merge_part, py::function train_part) { cb_merge_part_ = merge_part; cb_train_part_ = train_part; }
     void set_partition_update_callback(py::function f) { cb_update_part_ = std::move(f); }
+    void set_sample_update_callback(py::function f) { cb_sample_update_ = std::move(f); }
     void set_node_ages(int i, const std::vector<int64_t>& ages, int64_t model_msgs) {
         Node& nd = nodes_.at(i);
         if ((int)ages.size() != n_parts_) throw std::invalid_argument("one age per partition");
@@ -334,7 +335,7 @@ public:
                 r.push_back(sl.pid); r.insert(r.end(), sl.ages_v.begin(), sl.ages_v.end());
                 if (mode_ == 1) r.push_back(sl.counter);    // partitioned UPDATE keys the copy's update with it
             }
-            else if (mode_ == 3) r.push_back(sl.counter);
+            else if (mode_ == 3 || (sample_k_ > 0 && mode_ == 1)) r.push_back(sl.counter);
             if (!deg_.empty()) r.push_back(sl.sender);
             v.push_back(r);
         }
@@ -356,7 +357,7 @@ public:
                 sl.pid = (int)r.at(4); sl.ages_v.assign(r.begin() + 5, r.begin() + 5 + n_parts_);
                 if (mode_ == 1) sl.counter = r.at(5 + n_parts_);
             }
-            else if (mode_ == 3) sl.counter = r.at(4);
+            else if (mode_ == 3 || (sample_k_ > 0 && mode_ == 1)) sl.counter = r.at(4);
             if (!deg_.empty()) sl.sender = (int)r.back();
             inflight_[(int32_t)r.at(0)] = {rk, s};
         }
@@ -751,6 +752,30 @@ private:
             const int st = steps_of(nd);
             for (int64_t& v : nd.ages_v) v += st;
             nd.age += (int64_t)st * n_parts_;
+        } else if (sample_k_ > 0 && mode == 1) {
+            // sampled UPDATE (model/handler.py::SamplingTMH.__call__, reference handler.py:440-452): the receiver draws the
+            // coordinate sample (one of its update keys), trains a private copy of the received model on its data (keyed
+            // like the Python scratch copy) and merges the sampled coordinates of the copy; its own age does not move
+            nd.counter += 1;
+            uint64_t h = mix64(seed_);
+            const uint64_t parts[3] = {0x5A3Full, (uint64_t)node, key_of(node, nd) & 0xFFFFFFFFull};
+            for (uint64_t p : parts) h = mix64(h ^ p);
+            const uint64_t key_s = h & ((1ull << 63) - 1);
+            const uint64_t key_tmp = key_of(node, sl.counter + 1, sl.age);
+            if (exec) {
+                if (cuda_) {
+                    if (nd.sample_idx == nullptr || nd.scratch == nullptr) throw std::runtime_error("sampled UPDATE needs sample buffers and a scratch row per node");
+                    const PeerSync none{nullptr, 0, nullptr, nullptr};
+                    launch_keyed_randint(nd.sample_idx, sample_k_, n_params_, key_s, nd.stream);
+                    launch_merge_pair(nd.scratch, sl.data, 0.f, 1.f, 0, row_floats_, sync, nd.stream);
+                    Node tmp = nd; tmp.row = nd.scratch;
+                    train(tmp, nullptr, 1.f, 0.f, key_tmp, none);
+                    launch_merge_indexed(nd.row, nd.scratch, nd.sample_idx, sample_k_, .5f, .5f, nd.sample_val, none, nd.stream);
+                } else {
+                    cb_sample_update_(node, rk, s, (int64_t)sl.gen, (int64_t)key_s, (int64_t)key_tmp);
+                }
+                launches_ += 5;
+            }
         } else if (sample_k_ > 0) {                        // sampled MERGE_UPDATE: merge k keyed coordinates, then train
             nd.counter += 1;                               // SamplingTMH.draw_sample consumes one update key ...
             uint64_t h = mix64(seed_);
@@ -867,7 +892,7 @@ private:
     std::vector<std::vector<Slot>> pools_;          // per owner rank
     std::vector<std::deque<int>> free_;             // FIFO: a slot is reused as late as possible (see snapshot())
     std::unordered_map<int32_t, std::pair<int, int>> inflight_;     // message id -> (rank, slot)
-    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_part_, cb_update_merge_, cb_sample_merge_, cb_kway_;
+    py::function cb_snapshot_, cb_train_, cb_adopt_, cb_merge_part_, cb_train_part_, cb_update_part_, cb_update_merge_, cb_sample_merge_, cb_sample_update_, cb_kway_;
     bool a2a_ = false;                               // All2AllGossipNode mode
     bool cn_ = false;                                // CacheNeighNode mode
     float momentum_ = 0.f, dampening_ = 0.f; bool nesterov_ = false;     // fused momentum-SGD (0 = plain SGD)
@@ -914,6 +939,7 @@ void bind_executor(py::module_& m) {
         .def("set_partition", &StreamExecutor::set_partition)
         .def("set_partition_callbacks", &StreamExecutor::set_partition_callbacks)
         .def("set_partition_update_callback", &StreamExecutor::set_partition_update_callback)
+        .def("set_sample_update_callback", &StreamExecutor::set_sample_update_callback)
         .def("set_node_ages", &StreamExecutor::set_node_ages)
         .def("ages_v", &StreamExecutor::ages_v)
         .def("model_msgs", &StreamExecutor::model_msgs)

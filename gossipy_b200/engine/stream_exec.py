@@ -89,8 +89,11 @@ def eligible(sim: Any) -> Optional[str]:
             return "neighbour caches filled by another executor"
         if type(h) not in (H.TorchModelHandler, H.LimitedMergeTMH) and not partitioned and not sampled and not weighted:
             return "handler class %s" % type(h).__name__
-        if sampled and h.mode != CreateModelMode.MERGE_UPDATE:
+        if sampled and h.mode not in (CreateModelMode.MERGE_UPDATE, CreateModelMode.UPDATE):
             return "sampled models: mode %s" % h.mode.name
+        if (sampled and h.mode == CreateModelMode.UPDATE and h.device.type == "cuda"
+                and os.environ.get("GOSSIPY_EXEC_PART_UPDATE", "") != "1"):
+            return "sampled UPDATE on CUDA is opt-in (GOSSIPY_EXEC_PART_UPDATE=1) until it has been validated on a GPU"
         momentum = bool(h.__dict__.get("_fused_momentum")) and not h._fused
         if momentum:            # torch.optim.SGD with momentum inside the tensor-core kernel: plain nodes, MERGE_UPDATE
             n_i = int(node.data[0][0].shape[0]) if isinstance(node.data[0], (tuple, list)) else 0
@@ -214,7 +217,7 @@ class StreamExec:
             if not self.cuda:
                 self.ex.set_kway_callback(self._cb_kway)
         self._scratch = None
-        if h0.mode == CreateModelMode.UPDATE_MERGE or (self.n_parts and h0.mode == CreateModelMode.UPDATE):
+        if h0.mode == CreateModelMode.UPDATE_MERGE or ((self.n_parts or self.sample_k) and h0.mode == CreateModelMode.UPDATE):
             # one private row per node of this rank for the copy of a received model that is trained
             mine = [i for i in ids if self.owner[i] == self.rank]
             self._scratch = torch.zeros(max(1, len(mine)), self.row_numel, dtype=torch.float32, device=self.device)
@@ -224,6 +227,7 @@ class StreamExec:
             if not self.cuda:
                 self.ex.set_update_merge_callback(self._cb_update_merge)
                 self.ex.set_partition_update_callback(self._cb_update_part)
+                self.ex.set_sample_update_callback(self._cb_sample_update)
         self.bind_nodes()
 
     def _add_pool_rows(self, k: int) -> None:
@@ -410,6 +414,18 @@ class StreamExec:
         src, sync = self._slot(rank, slot, gen)
         idx = ops.keyed_randint(self.sample_k, self.n_params, int(key), self.device)
         ops.merge_indexed(self.sim.nodes[node].model_handler.row, src, idx, 0.5, 0.5, sync)
+
+    def _cb_sample_update(self, node: int, rank: int, slot: int, gen: int, key_s: int, key_tmp: int) -> None:
+        """Sampled UPDATE: train a private copy of the received model, merge its sampled coordinates into the own model."""
+        h = self.sim.nodes[node].model_handler
+        x, y = self._data[node]
+        tmp = self._scratch[self._scratch_of[node]]
+        src, sync = self._slot(rank, slot, gen)
+        ops.merge_pair(tmp, src, 0.0, 1.0, sync=sync)
+        fn = ops.mlp1_train if self.family == "mlp1" else ops.logreg_train
+        fn(tmp, x, y, self.dims, self.bs, self.epochs, self.lr, self.wd, int(key_tmp), None)
+        idx = ops.keyed_randint(self.sample_k, self.n_params, int(key_s), self.device)
+        ops.merge_indexed(h.row, tmp, idx, 0.5, 0.5, None)
 
     def _cb_merge_part(self, node: int, rank: int, slot: int, pid: int, w1: float, w2: float, gen: int) -> None:
         src, sync = self._slot(rank, slot, gen)

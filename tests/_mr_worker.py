@@ -166,7 +166,8 @@ def build(kind, device):
         sim = GossipSimulator(nodes, disp, 10, prt_, delay=UniformDelay(0, 2))
         sim.engine = "native"
         sim.native_executor = True
-    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge", "x_passthrough", "x_sampled", "x_cacheneigh", "x_momentum"):
+    elif kind in ("x_mlp_pushpull", "x_limited_push", "x_update_pull", "x_update_merge", "x_passthrough", "x_sampled", "x_sampled_update",
+                  "x_cacheneigh", "x_momentum"):
         # native engine + the C++ executor (csrc/exec): one executor per rank over the same event list
         if kind == "x_mlp_pushpull":
             (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(640, 200)
@@ -175,11 +176,13 @@ def build(kind, device):
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
             n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), LimitedMergeTMH, {"age_diff_threshold": 2}
             proto_, kws = AntiEntropyProtocol.PUSH, dict(drop_prob=.1, online_prob=.8, delay=UniformDelay(0, 2), sampling_eval=.5)
-        elif kind == "x_sampled":
+        elif kind in ("x_sampled", "x_sampled_update"):
             from gossipy_b200.model.handler import SamplingTMH
             from gossipy_b200.node import SamplingBasedNode
             (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(600, 200)
             n, bs, net, cls, kwh = 6, 16, LogisticRegression(57, 2), (lambda *a, **k: SamplingTMH(.3, *a, **k)), {}
+            if kind == "x_sampled_update":
+                kwh = {"create_model_mode": CreateModelMode.UPDATE}
             proto_, kws = AntiEntropyProtocol.PUSH_PULL, dict(delay=UniformDelay(0, 2))
         elif kind == "x_momentum":
             (Xtr, ytr), (Xte, yte) = synthetic.mnist_like(480, 200)
@@ -212,7 +215,7 @@ def build(kind, device):
                 if i > 1:
                     A[i, 0] = A[0, i] = 1
             nodes = PassThroughNode.generate(disp, StaticP2PNetwork(n, A), proto, 10, True)
-        elif kind == "x_sampled":
+        elif kind in ("x_sampled", "x_sampled_update"):
             nodes = SamplingBasedNode.generate(disp, StaticP2PNetwork(n), proto, 10, True)
         elif kind == "x_cacheneigh":
             from gossipy_b200.node import CacheNeighNode

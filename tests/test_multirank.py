@@ -103,7 +103,7 @@ XKINDS = "x_mlp_pushpull,x_limited_push,x_update_pull,x_update_merge,x_passthrou
 def test_cpp_executor_two_and_three_ranks_cpu_equal_single_process():
     """csrc/exec with several ranks: replicated books, each rank launches its own nodes, snapshot slots in the
     symmetric arenas with the ready/done handshake (here: shared-memory flags, host-side waits)."""
-    kinds = XKINDS + ",x_part_update"        # (partitioned UPDATE: validated on CPU only so far, not part of the GPU list)
+    kinds = XKINDS + ",x_part_update,x_sampled_update"    # (UPDATE of partitioned / sampled models: CPU only so far)
     single = _run(1, "cpu", rounds=4, kinds=kinds)
     assert all(v["cpp_executor"] for v in single.values())
     for world in (2, 3):
@@ -116,7 +116,7 @@ def test_checkpoint_with_several_ranks_resumes_exactly():
     """save / load with two ranks: every rank writes a complete checkpoint (the owners' in-flight snapshot slots and cached
     models are gathered), only owners restore row values, a barrier separates restoring from reading; the interrupted run
     equals the uninterrupted single-process run -- Python executor and C++ executor (delays, caches, partitioned models)."""
-    kinds = "mlp_pushpull,limited_pull,x_update_pull,x_limited_push,x_all2all,x_cacheneigh,x_part_logreg,x_part_update"
+    kinds = "mlp_pushpull,limited_pull,x_update_pull,x_limited_push,x_all2all,x_cacheneigh,x_part_logreg,x_part_update,x_sampled_update"
     single = _run(1, "cpu", rounds=6, kinds=kinds)
     _compare(single, _run(1, "cpu", rounds=6, kinds=kinds, checkpoint=True), rel=1e-5)
     _compare(single, _run(2, "cpu", rounds=6, kinds=kinds, checkpoint=True), rel=1e-5)

@@ -176,7 +176,12 @@ def test_native_executor_pass_through_nodes(kw):
 
 @pytest.mark.parametrize("kw", [dict(model="logreg", protocol="PUSH", sampled=.3, faults=True),
                                 dict(model="mlp", protocol="PUSH_PULL", sampled=.1),
-                                dict(model="logreg", protocol="PULL", sampled=.5, faults=True, sync=False)])
+                                dict(model="logreg", protocol="PULL", sampled=.5, faults=True, sync=False),
+                                # UPDATE: the receiver draws the sample, trains a private copy of the received model and merges
+                                # the copy's sampled coordinates; its own age does not move
+                                dict(model="logreg", protocol="PUSH", sampled=.3, faults=True, mode="UPDATE", tokenized=True),
+                                dict(model="mlp", protocol="PUSH_PULL", sampled=.1, mode="UPDATE"),
+                                dict(model="logreg", protocol="PULL", sampled=.5, faults=True, sync=False, mode="UPDATE")])
 def test_native_executor_sampled_models(kw):
     """SamplingBasedNode + SamplingTMH (reference node.py:499-562, handler.py:426-452) from C++: the receiver's keyed
     coordinate sample (with replacement), indexed merge, local update."""
@@ -206,7 +211,8 @@ def test_native_executor_cache_neighbour_nodes(kw):
 
 @pytest.mark.parametrize("kw", [dict(model="logreg", protocol="PUSH", partitioned=4, faults=True), dict(model="logreg", protocol="PUSH_PULL", sampled=.3, faults=True),
                                 dict(model="logreg", protocol="PUSH", passthrough=True, faults=True, n=7),
-                                dict(model="logreg", protocol="PUSH_PULL", partitioned=4, faults=True, mode="UPDATE")])
+                                dict(model="logreg", protocol="PUSH_PULL", partitioned=4, faults=True, mode="UPDATE"),
+                                dict(model="logreg", protocol="PUSH_PULL", sampled=.3, faults=True, mode="UPDATE")])
 def test_executor_checkpoint_of_keyed_node_classes_is_exact(kw, tmp_path):
     """Node classes with keyed draws (partition ids, samples, accept draws): building the scheduler again after a load must not
     consume a draw (it used to: the partitioned resume was off by one message counter)."""
