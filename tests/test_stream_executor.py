@@ -541,8 +541,8 @@ def test_native_executor_variants_random_setups():
     @given(kind=st.sampled_from(["a2a", "sampled", "part", "momentum"]), model=st.sampled_from(["logreg", "mlp"]),
            protocol=st.sampled_from(["PUSH", "PULL", "PUSH_PULL"]), faults=st.booleans(), sync=st.booleans(), n=st.integers(2, 8),
            rounds=st.integers(1, 4), tokenized=st.booleans(), frac=st.sampled_from([.05, .3, 1.0]), parts=st.sampled_from([2, 4, 7]),
-           ring=st.booleans(), nesterov=st.booleans())
-    def check(kind, model, protocol, faults, sync, n, rounds, tokenized, frac, parts, ring, nesterov):
+           ring=st.booleans(), nesterov=st.booleans(), update=st.booleans())
+    def check(kind, model, protocol, faults, sync, n, rounds, tokenized, frac, parts, ring, nesterov, update):
         if kind == "a2a":
             kw = dict(model=model, n=max(n, 3) if ring else n, rounds=rounds, faults=faults, sync=sync, mixing="ring" if ring else "uniform")
             sim_a, rep_a = _a2a_sim(False, **kw)
@@ -550,9 +550,9 @@ def test_native_executor_variants_random_setups():
         else:
             kw = dict(model=model, protocol=protocol, faults=faults, sync=sync, n=n, rounds=rounds, tokenized=tokenized)
             if kind == "sampled":
-                kw["sampled"] = frac
+                kw.update(sampled=frac, mode="UPDATE" if update else "MERGE_UPDATE")
             elif kind == "part":
-                kw["partitioned"] = parts
+                kw.update(partitioned=parts, mode="UPDATE" if update else "MERGE_UPDATE")
             else:
                 kw.update(model="mlp", momentum={"momentum": .9, "nesterov": nesterov})
             sim_a, rep_a = _sim(False, **kw)
