@@ -36,6 +36,7 @@ def main():
     from gossipy_b200.simul import GossipSimulator
     g.LOG.setLevel(50)
     g.GlobalSettings().set_device("cpu")
+    g.set_seed(1)                      # (the nodes' timeout offsets come from the host stream)
     n = a.nodes
     (Xtr, ytr), (Xte, yte) = synthetic.spambase_like(20 * n, 50)
     disp = DataDispatcher(ClassificationDataHandler(Xtr, ytr, Xte, yte), n=n, eval_on_user=False)

@@ -50,6 +50,8 @@ struct Stream {   // one independent random stream
     Stream() : key(0), ctr(0) {}
     Stream(uint64_t seed, uint64_t purpose) : key(mix64(mix64(seed) ^ purpose)), ctr(0) {}
     uint64_t next() { return mix64(key ^ (ctr++ * 0xD1342543DE82EF95ull)); }
+    uint64_t at(uint64_t c) const { return mix64(key ^ (c * 0xD1342543DE82EF95ull)); }      // the draw `next()` makes at ctr == c
+    double uniform_at(uint64_t c) const { return (double)(at(c) >> 11) * (1.0 / 9007199254740992.0); }
     double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }   // [0, 1)
     uint64_t below(uint64_t n) { return n <= 1 ? 0 : next() % n; }
 };
@@ -119,7 +121,6 @@ public:
         order_.resize(n_);
         for (int i = 0; i < n_; ++i) order_[i] = i;
         accounts_.resize(n_);
-        online_mask_.assign(n_, 1);
     }
 
     void set_nodes(const std::vector<int>& sync, const std::vector<int>& delta_i, const std::vector<int>& round_len) {
@@ -128,6 +129,7 @@ public:
         sync_ = sync; offset_ = delta_i; round_len_ = round_len;
         for (int i = 0; i < n_; ++i)
             if (!sync_[i] && offset_[i] < 1) offset_[i] = 1;     // guard
+        queue_valid_ = false;
     }
     void set_topology(const std::vector<int64_t>& indptr, const std::vector<int32_t>& indices) {
         if ((int)indptr.size() != n_ + 1) throw std::invalid_argument("indptr must have n+1 entries");
@@ -163,8 +165,13 @@ public:
         const int64_t first = clock_, last = clock_ + ticks;
         for (int64_t t = first; t < last; ++t) {
             if (t % delta_ == 0) shuffle();
-            for (int idx = 0; idx < n_; ++idx) tick_node(order_[idx], t);
-            for (int i = 0; i < n_; ++i) online_mask_[i] = r_online_.uniform() <= online_ ? 1 : 0;
+            if (dense_) {
+                for (int idx = 0; idx < n_; ++idx) tick_node(order_[idx], t);
+            } else {
+                fire_due(t);
+            }
+            online_base_ = r_online_.ctr;                    // this tick's availability draws: one per node, in node order
+            r_online_.ctr += (uint64_t)n_;
             deliver_messages(t);
             deliver_replies(t);
             if ((t + 1) % delta_ == 0) evaluate(t);
@@ -177,7 +184,13 @@ public:
     }
 
     int64_t clock() const { return clock_; }
-    void set_clock(int64_t c) { clock_ = c; }
+    void set_clock(int64_t c) { clock_ = c; queue_valid_ = false; }
+    // The tick loop of the reference (and of this class until round 2) looks at every node in every tick: N x delta timeout
+    // tests and N x delta availability draws per round.  The default loop visits only the nodes that time out at a tick
+    // (a queue keyed by their next timeout, processed in the round's shuffled order) and evaluates the availability draw of
+    // a node only when a message reaches it (the stream is counter based: draw (tick, node) is addressable).  Same events,
+    // same stream counters; `dense = true` keeps the old loop (tests compare the two).
+    void set_dense_loop(bool dense) { dense_ = dense; queue_valid_ = false; }
     int64_t sent() const { return sent_; }
     int64_t failed() const { return failed_; }
     int64_t total_size() const { return total_size_; }
@@ -231,6 +244,7 @@ public:
         };
         load(msg_q_, d["msg_q"].cast<std::vector<std::vector<int64_t>>>());
         load(rep_q_, d["rep_q"].cast<std::vector<std::vector<int64_t>>>());
+        queue_valid_ = false;
         clock_ = d["clock"].cast<int64_t>(); sent_ = d["sent"].cast<int64_t>(); failed_ = d["failed"].cast<int64_t>();
         total_size_ = d["total_size"].cast<int64_t>(); next_id_ = d["next_id"].cast<int32_t>();
     }
@@ -248,6 +262,46 @@ private:
     }
     void shuffle() {   // Fisher-Yates
         for (int i = n_ - 1; i > 0; --i) std::swap(order_[i], order_[(int)r_order_.below((uint64_t)i + 1)]);
+        pos_valid_ = false;
+    }
+    bool is_online(int i) const { return online_ >= 1.0 || r_online_.uniform_at(online_base_ + (uint64_t)i) <= online_; }
+    int64_t period_of(int i) const { return sync_[i] ? (int64_t)round_len_[i] : (int64_t)offset_[i]; }
+    // first tick >= t at which node i times out (-1: never)
+    int64_t first_timeout(int i, int64_t t) const {
+        const int64_t p = period_of(i);
+        if (p <= 0) return -1;
+        if (sync_[i]) {
+            if (offset_[i] < 0 || offset_[i] >= p) return -1;
+            return t + (((int64_t)offset_[i] - t % p) + p) % p;
+        }
+        return (t + p - 1) / p * p;
+    }
+    void rebuild_queue(int64_t t) {
+        due_.clear();
+        for (int i = 0; i < n_; ++i) {
+            const int64_t f = first_timeout(i, t);
+            if (f >= 0) due_[f].push_back(i);
+        }
+        queue_valid_ = true;
+    }
+    void fire_due(int64_t t) {
+        if (!queue_valid_) rebuild_queue(t);
+        auto it = due_.find(t);
+        if (it == due_.end()) return;
+        std::vector<int> nodes = std::move(it->second);
+        due_.erase(it);
+        if (nodes.size() > 1) {                              // the reference walks the round's shuffled order
+            if (!pos_valid_) {
+                pos_.resize(n_);
+                for (int k = 0; k < n_; ++k) pos_[order_[k]] = k;
+                pos_valid_ = true;
+            }
+            std::sort(nodes.begin(), nodes.end(), [this](int a, int b) { return pos_[a] < pos_[b]; });
+        }
+        for (int i : nodes) {
+            tick_node(i, t);
+            due_[t + period_of(i)].push_back(i);
+        }
     }
     bool timed_out(int i, int64_t t) const {
         return sync_[i] ? (t % round_len_[i]) == offset_[i] : (t % offset_[i]) == 0;
@@ -312,7 +366,7 @@ private:
         std::deque<Msg>& q = it->second;                     // may grow while we walk it (delay-0 reactive sends)
         for (size_t k = 0; k < q.size(); ++k) {
             const Msg m = q[k];
-            if (!online_mask_[m.receiver]) { lost(m, t); continue; }
+            if (!is_online(m.receiver)) { lost(m, t); continue; }
             emit(EV_DELIVER, t, m.sender, m.receiver, m.id, m.type);
             const bool wants_reply = m.type == MT_PULL || m.type == MT_PUSH_PULL;
             if (wants_reply) {
@@ -338,7 +392,7 @@ private:
         auto it = rep_q_.find(t);
         if (it == rep_q_.end()) return;
         for (const Msg& r : it->second) {
-            if (online_mask_[r.receiver]) {
+            if (is_online(r.receiver)) {
                 ++sent_; total_size_ += r.size;              // replies are counted at delivery (simul.py:425)
                 emit(EV_REPLY_DELIVER, t, r.receiver, r.sender, r.id, r.type);
             } else {
@@ -366,7 +420,10 @@ private:
     int64_t size_model_ = 1, size_pull_ = 1;
     std::vector<TokenAccount> accounts_; bool tokenized_ = false; int64_t utility_ = 1;
     bool broadcast_ = false, emit_timeouts_ = false;
-    std::vector<uint8_t> online_mask_;
+    uint64_t online_base_ = 0;                             // counter of this tick's first availability draw
+    bool dense_ = false, queue_valid_ = false, pos_valid_ = false;
+    std::map<int64_t, std::vector<int>> due_;              // next timeout -> nodes
+    std::vector<int> pos_;                                 // position of every node in the round's shuffled order
     std::map<int64_t, std::deque<Msg>> msg_q_, rep_q_;
     std::vector<int32_t> events_;
     int64_t clock_ = 0, sent_ = 0, failed_ = 0, total_size_ = 0;
@@ -386,6 +443,7 @@ void bind_scheduler(py::module_& m) {
         .def("set_token_account", &GossipScheduler::set_token_account)
         .def("set_broadcast", &GossipScheduler::set_broadcast)
         .def("set_peer_list", &GossipScheduler::set_peer_list)
+        .def("set_dense_loop", &GossipScheduler::set_dense_loop)
         .def("run", &GossipScheduler::run, py::arg("rounds") = 1)
         .def("run_ticks", &GossipScheduler::run_ticks, py::arg("ticks"))
         .def_property("clock", &GossipScheduler::clock, &GossipScheduler::set_clock)

@@ -104,3 +104,57 @@ def test_event_stream_is_a_valid_history(cfg, rounds, cut):
     n_eval = int((kind == C.EV_EVAL).sum())
     expect = rounds * (n if cfg[5] == 0 else max(int(n * cfg[5]), 1))
     assert n_eval == expect
+
+
+def test_sparse_tick_loop_produces_the_dense_loops_events():
+    """The default loop visits only the nodes that time out at a tick and evaluates availability draws on demand; the dense
+    loop (every node, every tick -- what the reference does) must give the same events, counters and stream positions:
+    random mixes of sync / async nodes, round lengths, topologies, faults, token accounts, broadcasts, pieces, restores."""
+    import random
+    from gossipy_b200.ops.native import _try_import
+    C = _try_import()
+    rnd = random.Random(7)
+    for case in range(60):
+        n = rnd.randint(2, 40)
+        delta = rnd.choice([5, 10, 10, 25])
+        proto = rnd.choice([1, 2, 3])
+        drop, online = rnd.choice([0.0, 0.2]), rnd.choice([1.0, 1.0, 0.7, 0.2])
+        seed = rnd.randint(0, 10 ** 9)
+        sync = [rnd.random() < .7 for _ in range(n)]
+        rl = [rnd.choice([delta, delta, 2 * delta, 3, delta + 1]) for _ in range(n)]
+        off = [rnd.randint(0, rl[i] + 1) if sync[i] else rnd.randint(0, 2 * delta) for i in range(n)]
+        ring = rnd.random() < .3
+        tok = rnd.choice([0, 0, 3, 5, 2])
+        bcast = rnd.random() < .2 and proto == 1
+        delay = rnd.choice([(0, 0, 0), (1, 0, 2 * delta), (2, 0.01, 1)])
+
+        def make(dense):
+            s = C.GossipScheduler(n, delta, proto, drop, online, rnd_eval, seed)
+            s.set_nodes([int(v) for v in sync], off, rl)
+            if ring:
+                s.set_topology(list(range(n + 1)), [(i + 1) % n for i in range(n)])
+            s.set_delay(*delay)
+            s.set_message_sizes(50, 1)
+            if tok:
+                s.set_token_account(tok, 6, 3, 1, 1)
+            if bcast:
+                s.set_broadcast(True)
+            s.set_dense_loop(dense)
+            return s
+        rnd_eval = rnd.choice([0.0, 0.3])
+        a, b = make(True), make(False)
+        pieces = [rnd.randint(0, 3 * delta) for _ in range(6)]
+        ev_a = [a.run_ticks(k) for k in pieces]
+        ev_b = []
+        for j, k in enumerate(pieces):
+            if j == 3:                      # restore in the middle: the timeout queue is rebuilt from the clock
+                st = dict(b.get_state())
+                b = make(False)
+                b.set_state(st)
+            ev_b.append(b.run_ticks(k))
+        for x, y in zip(ev_a, ev_b):
+            assert np.array_equal(x, y), (case, n, delta, proto, sync, rl, off)
+        sa, sb = dict(a.get_state()), dict(b.get_state())
+        assert sa["streams"] == sb["streams"] and sa["order"] == sb["order"] and sa["msg_q"] == sb["msg_q"] and sa["rep_q"] == sb["rep_q"]
+        assert (a.sent, a.failed, a.total_size, a.clock) == (b.sent, b.failed, b.total_size, b.clock)
+        assert a.token_balances() == b.token_balances()
