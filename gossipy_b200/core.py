@@ -165,6 +165,7 @@ class P2PNetwork(ABC):
             assert num_nodes == topology.shape[0], \
                 "The number of nodes must match the number of rows of the topology!"
         self._num_nodes = int(num_nodes)
+        self._clique = topology is None     # implicit clique: the C++ scheduler indexes it without a peer table
         self._topology: Dict[int, List[int]] = {}
         if topology is None:
             for i in range(num_nodes):

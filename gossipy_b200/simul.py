@@ -28,7 +28,7 @@ import numpy as np
 
 from . import CACHE, LOG, CacheKey, GlobalSettings
 from .core import (AntiEntropyProtocol, ConstantDelay, Delay, Message, MessageType, MixingMatrix,
-                   UniformMixing)
+                   StaticP2PNetwork, UniformMixing)
 from .data import DataDispatcher
 from .flow_control import TokenAccount
 from .model.handler import ModelHandler, PendingEval
@@ -533,8 +533,11 @@ class GossipSimulator(SimulationEventSender):
         sch.set_nodes([1 if self.nodes[i].sync else 0 for i in ids], [int(self.nodes[i].delta) for i in ids],
                       [int(self.nodes[i].round_len) for i in ids])
         net = self.nodes[0].p2p_net
-        indptr, indices = net.as_csr()
-        sch.set_topology([int(v) for v in indptr], [int(v) for v in indices])
+        if not (type(net) is StaticP2PNetwork and net.__dict__.get("_clique", False)):
+            # (an implicit clique needs no peer table: the scheduler's default enumerates "everybody but me" in the order of
+            # StaticP2PNetwork's lists -- at 4 141 nodes the table would have 17 M entries and take seconds to hand over)
+            indptr, indices = net.as_csr()
+            sch.set_topology(indptr.tolist(), indices.tolist())
         if isinstance(self.delay, UniformDelay):
             sch.set_delay(1, float(self.delay._min_delay), float(self.delay._max_delay))
         elif isinstance(self.delay, LinearDelay):

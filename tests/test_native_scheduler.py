@@ -637,3 +637,18 @@ def test_fresh_starts_do_not_leak_what_was_on_the_wire(path):
     sim._forget_messages_on_the_wire()
     assert in_use() == (n if path in ("python-loop", "per-event") else 0)
     g.CACHE.clear()
+
+
+def test_implicit_clique_needs_no_peer_table():
+    """``StaticP2PNetwork(n)`` (no topology): the scheduler's built-in clique enumerates the peers in the order of the
+    network's lists, so the schedule equals the one driven by the explicit n x (n - 1) table."""
+    from gossipy_b200.core import AntiEntropyProtocol
+    rep, rows, sim = _sim("native", AntiEntropyProtocol.PUSH_PULL, n=7, drop=.1, online=.8, rounds=1)
+    a = sim._make_scheduler()
+    b = sim._make_scheduler()
+    indptr, indices = sim.nodes[0].p2p_net.as_csr()
+    assert len(indices) == 7 * 6
+    b.set_topology(indptr.tolist(), indices.tolist())
+    ea = np.concatenate([a.run(1) for _ in range(30)])
+    eb = np.concatenate([b.run(1) for _ in range(30)])
+    assert np.array_equal(ea, eb) and len(ea) > 400
