@@ -22,6 +22,7 @@ are written back when the run ends, so the object API sees the same final state.
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -38,6 +39,7 @@ _MODE = {CreateModelMode.UPDATE: 1, CreateModelMode.MERGE_UPDATE: 2, CreateModel
 
 
 _OPEN: List["LinearBank"] = []      # banks holding shared-memory segments (closed by parallel.runtime.shutdown)
+_PINNED_IDX = os.environ.get("GOSSIPY_BANK_PINNED_IDX", "") == "1"
 _BANK_SEQ = 0                        # banks created in this session (names their shared-memory segments)
 
 
@@ -341,7 +343,13 @@ class LinearBank:
                 self.mode, self.lr)
 
     def _idx(self, a) -> torch.Tensor:
-        return torch.as_tensor(np.asarray(a, dtype=np.int32), device=self.device)
+        arr = np.asarray(a, dtype=np.int32)
+        if _PINNED_IDX and self.device.type == "cuda" and arr.size:
+            # a pageable host -> device copy blocks the host until the stream has drained, i.e. it serialises host and device
+            # once per launch; through pinned memory the copy is asynchronous (the caching host allocator keeps the staging
+            # block alive until the copy has run).  Written after the last GPU session: opt-in (GOSSIPY_BANK_PINNED_IDX=1)
+            return torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().to(self.device, non_blocking=True)
+        return torch.as_tensor(arr, device=self.device)
 
     def _snapshot(self, senders, slots) -> None:
         if len(senders) == 0:
