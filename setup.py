@@ -1,8 +1,9 @@
 """Packaging of gossipy_b200.  The sm_100a extension is built IN-TREE by ``__graft_entry__.build()`` (nvcc for the
 kernels, g++ against the torch headers for the bindings / scheduler / executor):
 
-    python setup.py build_ext --inplace        # = python -c "import __graft_entry__ as g; g.build()"
-    pip install --no-build-isolation -e .      # editable install; builds the extension first
+    python setup.py build_ext --inplace        # = python -c "import __graft_entry__ as g; g.build()"   (verified)
+    pip install --no-build-isolation -e .      # editable install (build_py / develop build the extension first; not exercised
+                                               # in the build container, which must not write outside the repository)
 """
 import os
 import sys
